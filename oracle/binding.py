@@ -1,0 +1,220 @@
+"""ORACLE (test infrastructure, NOT product code): ctypes binding of oracle/libola_oracle.so.
+
+Every function cites, in oracle/*.c, the reference file:line it restates.  numpy uint64 arrays in,
+numpy uint64 arrays out; all values canonical Goldilocks representatives.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libola_oracle.so")
+P = 0xFFFFFFFF00000001
+
+
+def build(force=False):
+    """Compile the C restatement (gcc + OpenMP).  Called by __graft_entry__.build()."""
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = ctypes.CDLL(_SO)
+        _set_sigs(_lib)
+    return _lib
+
+
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+_sz = ctypes.c_size_t
+_u64 = ctypes.c_uint64
+_u32 = ctypes.c_uint32
+_int = ctypes.c_int
+
+
+def _p(a):
+    if a is None:
+        return None
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_u64p)
+
+
+def _set_sigs(L):
+    L.orc_get_twiddles.argtypes = [_u64p, _sz, _int]
+    L.orc_evaluate_poly.argtypes = [_u64p, _sz]
+    L.orc_interpolate_poly.argtypes = [_u64p, _sz]
+    L.orc_evaluate_poly_with_offset.argtypes = [_u64p, _sz, _u64, _sz, _u64p]
+    L.orc_interpolate_poly_with_offset.argtypes = [_u64p, _sz, _u64]
+    L.orc_fft_classic.argtypes = [_u64p, _sz]
+    L.orc_poly_eval.argtypes = [_u64p, _sz, _u64]
+    L.orc_poly_eval.restype = _u64
+    L.orc_ifft_batch.argtypes = [_u64p, _sz, _sz]
+    L.orc_lde_batch.argtypes = [_u64p, _sz, _sz, _u64, _sz, _u64p]
+    L.orc_poseidon.argtypes = [_u64p]
+    L.orc_poseidon_naive.argtypes = [_u64p]
+    L.orc_hash_no_pad.argtypes = [_u64p, _sz, _u64p]
+    L.orc_two_to_one.argtypes = [_u64p, _u64p, _u64p]
+    L.orc_hash_rows.argtypes = [_u64p, _sz, _sz, _u64p]
+    L.orc_build_merkle_nodes.argtypes = [_u64p, _sz, _u64p]
+    L.orc_merkle_new_v2.argtypes = [_u64p, _sz, _sz, _u32, _u64p, _u64p]
+    L.orc_merkle_new_v2.restype = _int
+    L.orc_merkle_prove.argtypes = [_u64p, _sz, _u32, _sz, _u64p]
+    L.orc_merkle_prove.restype = _int
+    L.orc_merkle_verify.argtypes = [_u64p, _sz, _sz, _u64p, _u64p, _sz]
+    L.orc_merkle_verify.restype = _int
+    L.orc_commit.argtypes = [_u64p, _sz, _sz, _int, _u32, _u32, _u64p, _u64p, _u64p, _u64p]
+    L.orc_commit.restype = _int
+
+
+# ---------------------------------------------------------------- helpers
+def splitmix64(seed, n):
+    """Deterministic canonical Goldilocks elements (splitmix64 stream mod p)."""
+    out = np.empty(n, dtype=np.uint64)
+    x = np.uint64(seed)
+    M = (1 << 64) - 1
+    s = int(seed) & M
+    for i in range(n):
+        s = (s + 0x9E3779B97F4A7C15) & M
+        z = s
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+        z = z ^ (z >> 31)
+        out[i] = z % P
+    return out
+
+
+def rand_elems(seed, shape):
+    """Fast vectorised uniform canonical elements (numpy PCG64), for larger test inputs."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    a = rng.integers(0, P, size=shape, dtype=np.uint64, endpoint=False)
+    return np.ascontiguousarray(a)
+
+
+# ---------------------------------------------------------------- NTT
+def evaluate_poly(coeffs):
+    v = np.ascontiguousarray(coeffs, dtype=np.uint64).copy()
+    lib().orc_evaluate_poly(_p(v), v.size)
+    return v
+
+
+def interpolate_poly(values):
+    v = np.ascontiguousarray(values, dtype=np.uint64).copy()
+    lib().orc_interpolate_poly(_p(v), v.size)
+    return v
+
+
+def evaluate_poly_with_offset(coeffs, shift, blowup):
+    c = np.ascontiguousarray(coeffs, dtype=np.uint64)
+    out = np.empty(c.size * blowup, dtype=np.uint64)
+    lib().orc_evaluate_poly_with_offset(_p(c), c.size, int(shift), blowup, _p(out))
+    return out
+
+
+def interpolate_poly_with_offset(values, shift):
+    v = np.ascontiguousarray(values, dtype=np.uint64).copy()
+    lib().orc_interpolate_poly_with_offset(_p(v), v.size, int(shift))
+    return v
+
+
+def fft_classic(coeffs):
+    v = np.ascontiguousarray(coeffs, dtype=np.uint64).copy()
+    lib().orc_fft_classic(_p(v), v.size)
+    return v
+
+
+def poly_eval(coeffs, x):
+    c = np.ascontiguousarray(coeffs, dtype=np.uint64)
+    return int(lib().orc_poly_eval(_p(c), c.size, int(x)))
+
+
+def ifft_batch(cols):
+    v = np.ascontiguousarray(cols, dtype=np.uint64).copy()
+    lib().orc_ifft_batch(_p(v), v.shape[0], v.shape[1])
+    return v
+
+
+def lde_batch(coeffs, shift=7, blowup=8):
+    c = np.ascontiguousarray(coeffs, dtype=np.uint64)
+    out = np.empty((c.shape[0], c.shape[1] * blowup), dtype=np.uint64)
+    lib().orc_lde_batch(_p(c), c.shape[0], c.shape[1], int(shift), blowup, _p(out))
+    return out
+
+
+# ---------------------------------------------------------------- Poseidon / Merkle
+def poseidon(state, naive=False):
+    s = np.ascontiguousarray(state, dtype=np.uint64).copy()
+    assert s.size == 12
+    (lib().orc_poseidon_naive if naive else lib().orc_poseidon)(_p(s))
+    return s
+
+
+def hash_no_pad(inp):
+    a = np.ascontiguousarray(inp, dtype=np.uint64)
+    out = np.empty(4, dtype=np.uint64)
+    lib().orc_hash_no_pad(_p(a), a.size, _p(out))
+    return out
+
+
+def two_to_one(l, r):
+    l = np.ascontiguousarray(l, dtype=np.uint64)
+    r = np.ascontiguousarray(r, dtype=np.uint64)
+    out = np.empty(4, dtype=np.uint64)
+    lib().orc_two_to_one(_p(l), _p(r), _p(out))
+    return out
+
+
+def hash_rows(rows):
+    a = np.ascontiguousarray(rows, dtype=np.uint64)
+    out = np.empty((a.shape[0], 4), dtype=np.uint64)
+    lib().orc_hash_rows(_p(a), a.shape[0], a.shape[1], _p(out))
+    return out
+
+
+def merkle_new_v2(rows, cap_height):
+    a = np.ascontiguousarray(rows, dtype=np.uint64)
+    n = a.shape[0]
+    ncap = 1 << cap_height
+    dig = np.empty((max(2 * (n - ncap), 0), 4), dtype=np.uint64)
+    cap = np.empty((ncap, 4), dtype=np.uint64)
+    rc = lib().orc_merkle_new_v2(_p(a), n, a.shape[1], cap_height, _p(dig) if dig.size else _p(np.zeros(4, np.uint64)), _p(cap))
+    assert rc == 0
+    return dig, cap
+
+
+def merkle_prove(digests, nrows, cap_height, index):
+    nl = int(np.log2(nrows)) - cap_height
+    sib = np.empty((max(nl, 1), 4), dtype=np.uint64)
+    k = lib().orc_merkle_prove(_p(digests), nrows, cap_height, index, _p(sib))
+    return sib[:k]
+
+
+def merkle_verify(leaf, index, cap, siblings):
+    leaf = np.ascontiguousarray(leaf, dtype=np.uint64)
+    sib = np.ascontiguousarray(siblings, dtype=np.uint64).reshape(-1, 4)
+    sp = _p(sib) if sib.size else _p(np.zeros(4, np.uint64))
+    return bool(lib().orc_merkle_verify(_p(leaf), leaf.size, index, _p(np.ascontiguousarray(cap)), sp, sib.shape[0]))
+
+
+def commit(cols, is_coeffs=False, rate_bits=3, cap_height=4, want_leaves=True, want_digests=True):
+    """PolynomialBatch::from_values / from_coeffs.  Returns dict(coeffs, leaves, digests, cap)."""
+    c = np.ascontiguousarray(cols, dtype=np.uint64)
+    ncols, n = c.shape
+    L = n << rate_bits
+    ncap = 1 << cap_height
+    coeffs = np.empty((ncols, n), dtype=np.uint64)
+    leaves = np.empty((L, ncols), dtype=np.uint64) if want_leaves else None
+    dig = np.empty((max(2 * (L - ncap), 1), 4), dtype=np.uint64) if want_digests else None
+    cap = np.empty((ncap, 4), dtype=np.uint64)
+    rc = lib().orc_commit(_p(c), ncols, n, int(is_coeffs), rate_bits, cap_height, _p(coeffs), _p(leaves), _p(dig), _p(cap))
+    assert rc == 0
+    return dict(coeffs=coeffs, leaves=leaves, digests=dig, cap=cap)

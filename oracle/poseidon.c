@@ -1,0 +1,133 @@
+/* ORACLE (test infrastructure, NOT product code) -- see oracle/gl.h header.
+ *
+ * CPU restatement of Poseidon-Goldilocks (width 12, x^7, 4+22+4 rounds) and of the sponge /
+ * compression modes built on it.
+ *
+ * Follows:
+ *   plonky2/plonky2/src/hash/poseidon.rs   constant_layer :476-487, sbox_monomial :521-527,
+ *                                          mds_row_shf :168-189, mds_layer :236-257,
+ *                                          partial_first_constant_layer :303-313,
+ *                                          mds_partial_layer_init :332-358,
+ *                                          mds_partial_layer_fast :392-421, full_rounds :566-574,
+ *                                          partial_rounds :577-590, poseidon :593-604,
+ *                                          partial_rounds_naive / poseidon_naive :607-628
+ *   plonky2/plonky2/src/hash/hashing.rs    compress :66-74, hash_n_to_m_no_pad :84-106 (rate 8, overwrite mode)
+ *   plonky2/plonky2/src/hash/poseidon_goldilocks.rs   KATs :293-314 (checked in tests/test_oracle.py)
+ */
+#include "oracle.h"
+#include "poseidon_constants.h"
+#include <string.h>
+
+#define W 12
+#define HALF_FULL 4
+#define N_PARTIAL 22
+
+static inline uint64_t sbox(uint64_t x) {
+    uint64_t x2 = gl_sqr(x), x4 = gl_sqr(x2), x3 = gl_mul(x, x2);
+    return gl_mul(x3, x4);
+}
+
+static void constant_layer(uint64_t *s, int round_ctr) {
+    for (int i = 0; i < W; i++) s[i] = gl_add(s[i], gl_canon(ORC_ALL_ROUND_CONSTANTS[i + W * round_ctr]));
+}
+static void sbox_layer(uint64_t *s) {
+    for (int i = 0; i < W; i++) s[i] = sbox(s[i]);
+}
+/* poseidon.rs:168-189 + :236-257: out[r] = sum_i v[(i+r)%12]*CIRC[i] + v[r]*DIAG[r] */
+static void mds_layer(uint64_t *s) {
+    uint64_t out[W];
+    for (int r = 0; r < W; r++) {
+        u128 acc = 0;
+        for (int i = 0; i < W; i++) acc += (u128)s[(i + r) % W] * ORC_MDS_MATRIX_CIRC[i];
+        acc += (u128)s[r] * ORC_MDS_MATRIX_DIAG[r];
+        out[r] = gl_reduce128(acc);
+    }
+    memcpy(s, out, sizeof(out));
+}
+static void full_rounds(uint64_t *s, int *round_ctr) {
+    for (int r = 0; r < HALF_FULL; r++) {
+        constant_layer(s, *round_ctr);
+        sbox_layer(s);
+        mds_layer(s);
+        (*round_ctr)++;
+    }
+}
+/* poseidon.rs:607-617 */
+static void partial_rounds_naive(uint64_t *s, int *round_ctr) {
+    for (int r = 0; r < N_PARTIAL; r++) {
+        constant_layer(s, *round_ctr);
+        s[0] = sbox(s[0]);
+        mds_layer(s);
+        (*round_ctr)++;
+    }
+}
+/* poseidon.rs:577-590 */
+static void partial_rounds_fast(uint64_t *s, int *round_ctr) {
+    for (int i = 0; i < W; i++) s[i] = gl_add(s[i], gl_canon(ORC_FAST_PARTIAL_FIRST_ROUND_CONSTANT[i]));
+    { /* mds_partial_layer_init :332-358 */
+        uint64_t res[W];
+        memset(res, 0, sizeof(res));
+        res[0] = s[0];
+        for (int r = 1; r < W; r++)
+            for (int c = 1; c < W; c++)
+                res[c] = gl_add(res[c], gl_mul(s[r], gl_canon(ORC_FAST_PARTIAL_ROUND_INITIAL_MATRIX[r - 1][c - 1])));
+        memcpy(s, res, sizeof(res));
+    }
+    for (int i = 0; i < N_PARTIAL; i++) {
+        s[0] = sbox(s[0]);
+        s[0] = gl_add(s[0], gl_canon(ORC_FAST_PARTIAL_ROUND_CONSTANTS[i]));
+        /* mds_partial_layer_fast :392-421 */
+        uint64_t d = gl_mul(s[0], ORC_MDS_MATRIX_CIRC[0] + ORC_MDS_MATRIX_DIAG[0]);
+        for (int k = 1; k < W; k++) d = gl_add(d, gl_mul(s[k], gl_canon(ORC_FAST_PARTIAL_ROUND_W_HATS[i][k - 1])));
+        uint64_t res[W];
+        res[0] = d;
+        for (int k = 1; k < W; k++) res[k] = gl_add(s[k], gl_mul(s[0], gl_canon(ORC_FAST_PARTIAL_ROUND_VS[i][k - 1])));
+        memcpy(s, res, sizeof(res));
+    }
+    *round_ctr += N_PARTIAL;
+}
+
+void orc_poseidon(uint64_t state[12]) {
+    int rc = 0;
+    for (int i = 0; i < W; i++) state[i] = gl_canon(state[i]);
+    full_rounds(state, &rc);
+    partial_rounds_fast(state, &rc);
+    full_rounds(state, &rc);
+}
+void orc_poseidon_naive(uint64_t state[12]) {
+    int rc = 0;
+    for (int i = 0; i < W; i++) state[i] = gl_canon(state[i]);
+    full_rounds(state, &rc);
+    partial_rounds_naive(state, &rc);
+    full_rounds(state, &rc);
+}
+
+/* hashing.rs:84-108, num_outputs = 4 */
+void orc_hash_no_pad(const uint64_t *in, size_t n, uint64_t out[4]) {
+    uint64_t st[W];
+    memset(st, 0, sizeof(st));
+    for (size_t off = 0; off < n; off += 8) {
+        size_t len = n - off < 8 ? n - off : 8;
+        for (size_t i = 0; i < len; i++) st[i] = gl_canon(in[off + i]);
+        orc_poseidon(st);
+    }
+    /* n == 0: no absorption, squeeze the zero state (hashing.rs:98-106) */
+    memcpy(out, st, 4 * sizeof(uint64_t));
+}
+
+/* hashing.rs:66-74 */
+void orc_two_to_one(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]) {
+    uint64_t st[W];
+    memset(st, 0, sizeof(st));
+    memcpy(st, l, 32);
+    memcpy(st + 4, r, 32);
+    orc_poseidon(st);
+    memcpy(out, st, 32);
+}
+
+/* rows-major leaf hashing of a [nrows][ncols] matrix (MerkleTree::new_v2 leaf loop,
+ * merkle_tree/mod.rs:186-201) */
+void orc_hash_rows(const uint64_t *rows, size_t nrows, size_t ncols, uint64_t *digests) {
+#pragma omp parallel for schedule(static)
+    for (size_t r = 0; r < nrows; r++) orc_hash_no_pad(rows + r * ncols, ncols, digests + 4 * r);
+}

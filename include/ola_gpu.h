@@ -1,0 +1,131 @@
+/* libola_gpu -- C ABI of the B200 (sm_100a) STARK proving backend for OlaVM's `circuits` crate.
+ *
+ * This header is the drop-in boundary.  Plain pointers and sizes only; no
+ * torch / C++ types.  Every entry point names the reference interface it replaces (paths relative to
+ * the reference repository root, Sin7Y/olavm @ 5d77237).  INTEGRATION.md shows the Rust `extern "C"`
+ * block and the shim bodies a maintainer adds to plonky2/plonky2/src/fri/oracle.rs and
+ * circuits/src/stark/prover.rs.
+ *
+ * Conventions
+ *   - Field elements are Goldilocks `u64` (GoldilocksField is #[repr(transparent)] over u64,
+ *     plonky2/field/src/goldilocks_field.rs:24-26).  Inputs may be non-canonical (>= p); outputs are
+ *     always canonical.
+ *   - Polynomial batches are COLUMN-MAJOR: `cols` points at ncols contiguous columns of n = 2^log_n
+ *     u64 each (== Vec<PolynomialValues<F>> flattened; circuits/src/stark/prover.rs:82).
+ *   - Hashes are 4 u64 (HashOut<F>, 32 bytes); Merkle caps are 2^cap_height hashes.
+ *   - Extension elements are 2 u64 (c0, c1) of F[X]/(X^2-7).
+ *   - Every function returns OLA_OK (0) or a negative error code; ola_gpu_last_error() gives text.
+ *     Nothing throws or aborts across the ABI.  A context is not re-entrant: one host thread per ctx
+ *     (the reference serialises its GPU with a global mutex, plonky2/field/src/cfft/ntt/mod.rs:48-50).
+ *   - There is NO CPU fallback: without a CUDA device ola_gpu_init fails with OLA_ERR_NO_DEVICE.
+ */
+#ifndef OLA_GPU_H
+#define OLA_GPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define OLA_OK 0
+#define OLA_ERR_NO_DEVICE -1      /* no CUDA device / wrong architecture */
+#define OLA_ERR_CUDA -2           /* CUDA runtime error (see last_error) */
+#define OLA_ERR_INVALID_ARG -3    /* size not a power of two, exceeds two-adicity 32, null pointer, ... */
+#define OLA_ERR_OOM -4
+#define OLA_ERR_QUOTIENT_DEGREE -5 /* "Quotient has failed, the vanishing polynomial is not divisible by Z_H"
+                                      (circuits/src/stark/prover.rs:469-473 panics here) */
+#define OLA_ERR_ZETA_IN_SUBGROUP -6 /* "Opening point is in the subgroup." (prover.rs:508-511) */
+#define OLA_ERR_INTERNAL -7
+
+typedef struct ola_ctx ola_ctx;     /* one per GPU; owns streams, twiddles, scratch */
+typedef struct ola_batch ola_batch; /* a committed PolynomialBatch resident in HBM */
+
+/* ---- lifecycle.  Replaces gpu_init / gpu_free (plonky2/field/src/cfft/ntt/mod.rs:21-45, :55-101),
+ * called once from OlaStark::default() (circuits/src/stark/ola_stark.rs:47). ---- */
+int ola_gpu_init(int device, ola_ctx** out);
+void ola_gpu_destroy(ola_ctx* ctx);
+const char* ola_gpu_last_error(const ola_ctx* ctx);
+int ola_gpu_sync(ola_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py "gpu_launches") */
+uint64_t ola_gpu_kernel_launches(const ola_ctx* ctx);
+/* the cudaStream_t every kernel of this context is launched on (for CUDA-event timing by the caller) */
+void* ola_gpu_stream(ola_ctx* ctx);
+
+/* ---- raw device buffers (u64 elements), for callers that keep data resident between calls ---- */
+int ola_dev_alloc(ola_ctx* ctx, size_t n_u64, uint64_t** dptr);
+int ola_dev_free(ola_ctx* ctx, uint64_t* dptr);
+int ola_dev_upload(ola_ctx* ctx, uint64_t* dst_dev, const uint64_t* src_host, size_t n_u64);
+int ola_dev_download(ola_ctx* ctx, uint64_t* dst_host, const uint64_t* src_dev, size_t n_u64);
+
+/* ---- Goldilocks NTT family.  `on_device` != 0: pointers are device pointers (resident path);
+ * == 0: host pointers, the call stages H2D/D2H itself (the reference-facing path).
+ * All are batched over ncols column-major columns and work in place unless an `out` is given. ---- */
+
+/* cfft::evaluate_poly (plonky2/field/src/cfft/mod.rs:22, serial.rs:9-15; PolynomialCoeffs::fft,
+ * polynomial/mod.rs:278-283): coefficients (natural) -> values on H (natural). */
+int ola_ntt_forward(ola_ctx* ctx, uint64_t* data, int on_device, size_t ncols, uint32_t log_n);
+/* cfft::interpolate_poly (cfft/mod.rs:128, serial.rs:52-63; PolynomialValues::ifft, polynomial/mod.rs:60-65):
+ * values on H (natural) -> coefficients (natural), scaled by 1/n. */
+int ola_ntt_inverse(ola_ctx* ctx, uint64_t* data, int on_device, size_t ncols, uint32_t log_n);
+/* cfft::evaluate_poly_with_offset (cfft/mod.rs:65, serial.rs:20-50; coset_fft_with_options,
+ * polynomial/mod.rs:302-311): coefficients (natural, n each) -> values on shift*<g_{n*2^rate_bits}>.
+ * out is [ncols][n << rate_bits].  natural_order != 0: out[k] = p(shift*g^k) exactly as the reference
+ * returns it; == 0: "leaf order" out[r] = p(shift*g^bitrev(r)), the order the Merkle leaves use after
+ * reverse_index_bits_in_place (fri/oracle.rs:84-85) -- the resident layout of this library. */
+int ola_coset_lde(ola_ctx* ctx, const uint64_t* coeffs, uint64_t* out, int on_device, size_t ncols, uint32_t log_n,
+                  uint32_t rate_bits, uint64_t shift, int natural_order);
+/* cfft::interpolate_poly_with_offset (cfft/mod.rs:180, serial.rs:65-79; PolynomialValues::coset_ifft,
+ * polynomial/mod.rs:69-74): values on shift*H (natural) -> coefficients (natural). */
+int ola_coset_intt(ola_ctx* ctx, uint64_t* data, int on_device, size_t ncols, uint32_t log_n, uint64_t shift);
+
+/* ---- Poseidon-Goldilocks (plonky2/plonky2/src/hash/poseidon.rs:593, hashing.rs:66-108) ---- */
+/* states: [nstates][12] u64, permuted in place (Poseidon::poseidon). */
+int ola_poseidon_permute(ola_ctx* ctx, uint64_t* states, int on_device, size_t nstates);
+/* hash_no_pad of every row of a ROW-major [nrows][ncols] matrix -> digests [nrows][4]
+ * (MerkleTree::new_v2 leaf loop, merkle_tree/mod.rs:186-201). */
+int ola_hash_rows(ola_ctx* ctx, const uint64_t* rows, uint64_t* digests, int on_device, size_t nrows, size_t ncols);
+/* MerkleTree::new_v2 over a ROW-major leaf matrix (merkle_tree/mod.rs:180-266): writes the cap
+ * (2^cap_height hashes) and, if nodes_out != NULL, all heap-ordered nodes [2*nrows][4]
+ * (node 1 = root, children of i at 2i/2i+1, leaf digests at nrows..2*nrows-1; node 0 unused). */
+int ola_merkle_rows(ola_ctx* ctx, const uint64_t* rows, int on_device, size_t nrows, size_t ncols, uint32_t cap_height,
+                    uint64_t* cap_out_host, uint64_t* nodes_out_host);
+
+/* ---- PolynomialBatch (plonky2/plonky2/src/fri/oracle.rs:31-38) ---- */
+/* PolynomialBatch::from_values (oracle.rs:45-64; is_coeffs == 0) / from_coeffs (oracle.rs:66-99; is_coeffs != 0)
+ * with blinding = false: iNTT -> coset LDE (shift 7, blowup 2^rate_bits) -> Poseidon Merkle tree.
+ * The batch keeps, in HBM: coefficients [ncols][n] (natural order), LDE values [ncols][n<<rate_bits]
+ * (column-major, leaf order), heap-ordered Merkle nodes.  cap_out_host receives 2^cap_height hashes. */
+int ola_commit(ola_ctx* ctx, const uint64_t* cols, int on_device, size_t ncols, uint32_t log_n, int is_coeffs,
+               uint32_t rate_bits, uint32_t cap_height, ola_batch** out, uint64_t* cap_out_host);
+int ola_batch_free(ola_ctx* ctx, ola_batch* b);
+/* shape queries */
+size_t ola_batch_ncols(const ola_batch* b);
+uint32_t ola_batch_degree_log(const ola_batch* b);
+uint32_t ola_batch_rate_bits(const ola_batch* b);
+/* device pointers into the batch (valid until ola_batch_free) */
+const uint64_t* ola_batch_coeffs_dev(const ola_batch* b); /* [ncols][n] */
+const uint64_t* ola_batch_lde_dev(const ola_batch* b);    /* [ncols][n<<rate_bits], leaf order */
+const uint64_t* ola_batch_nodes_dev(const ola_batch* b);  /* [2*(n<<rate_bits)][4], heap order */
+/* PolynomialBatch.polynomials -> host, [ncols][n] natural-order coefficients */
+int ola_batch_get_coeffs(ola_ctx* ctx, const ola_batch* b, uint64_t* out_host);
+/* merkle_tree.cap -> host */
+int ola_batch_get_cap(ola_ctx* ctx, const ola_batch* b, uint64_t* cap_out_host);
+/* merkle_tree.leaves[leaf_index .. +count) -> host, row-major [count][ncols]
+ * (== MerkleTree::get, merkle_tree/mod.rs:268; PolynomialBatch::get_lde_values, oracle.rs:132-139,
+ * takes index*step bit-reversed: pass that as leaf_index). */
+int ola_batch_get_leaves(ola_ctx* ctx, const ola_batch* b, size_t leaf_index, size_t count, uint64_t* out_host);
+/* MerkleTree::prove (merkle_tree/mod.rs:273-308): sibling digests bottom-up, log2(nleaves)-cap_height hashes.
+ * Returns the number of siblings written (>= 0) or an error (< 0). */
+int ola_batch_prove_leaf(ola_ctx* ctx, const ola_batch* b, size_t leaf_index, uint64_t* siblings_out_host);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* OLA_GPU_H */

@@ -1,0 +1,13 @@
+"""olavm_b200 -- B200 (sm_100a) STARK proving backend for OlaVM's `circuits` crate.
+
+Host-side mirror (Python over the C ABI in include/ola_gpu.h) of the reference interfaces on the proving
+hot path: plonky2 `cfft` transforms, Poseidon hashing / MerkleTree, `PolynomialBatch`.
+The arithmetic lives in olavm_b200/csrc (hand-written CUDA for sm_100a); there is no CPU fallback.
+"""
+from ._lib import OlaError, load  # noqa: F401
+from .context import Context  # noqa: F401
+from .pcs import MerkleCap, PolynomialBatch  # noqa: F401
+from . import cfft, hashing  # noqa: F401
+
+GOLDILOCKS_P = 0xFFFFFFFF00000001
+COSET_SHIFT = 7

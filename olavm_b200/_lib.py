@@ -1,0 +1,105 @@
+"""ctypes loader of libola_gpu.so (the C ABI declared in include/ola_gpu.h).
+
+The product path has NO fallback: if the shared library is missing, or no sm_100 device is visible,
+`load()` / `Context()` raise.  Nothing here imports the oracle.
+"""
+import ctypes
+import os
+import re
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libola_gpu.so")
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "ola_gpu.h")
+
+OLA_OK = 0
+ERRORS = {
+    -1: "OLA_ERR_NO_DEVICE",
+    -2: "OLA_ERR_CUDA",
+    -3: "OLA_ERR_INVALID_ARG",
+    -4: "OLA_ERR_OOM",
+    -5: "OLA_ERR_QUOTIENT_DEGREE",
+    -6: "OLA_ERR_ZETA_IN_SUBGROUP",
+    -7: "OLA_ERR_INTERNAL",
+}
+
+
+class OlaError(RuntimeError):
+    def __init__(self, code, msg=""):
+        self.code = code
+        super().__init__(f"{ERRORS.get(code, code)}: {msg}")
+
+
+u64p = ctypes.POINTER(ctypes.c_uint64)
+_vp = ctypes.c_void_p
+_sz = ctypes.c_size_t
+_u32 = ctypes.c_uint32
+_u64 = ctypes.c_uint64
+_int = ctypes.c_int
+
+# name -> (restype, argtypes); mirrors include/ola_gpu.h one to one (tests check the two agree)
+SIGNATURES = {
+    "ola_gpu_init": (_int, [_int, ctypes.POINTER(_vp)]),
+    "ola_gpu_destroy": (None, [_vp]),
+    "ola_gpu_last_error": (ctypes.c_char_p, [_vp]),
+    "ola_gpu_sync": (_int, [_vp]),
+    "ola_gpu_kernel_launches": (_u64, [_vp]),
+    "ola_gpu_stream": (_vp, [_vp]),
+    "ola_dev_alloc": (_int, [_vp, _sz, ctypes.POINTER(_vp)]),
+    "ola_dev_free": (_int, [_vp, _vp]),
+    "ola_dev_upload": (_int, [_vp, _vp, _vp, _sz]),
+    "ola_dev_download": (_int, [_vp, _vp, _vp, _sz]),
+    "ola_ntt_forward": (_int, [_vp, _vp, _int, _sz, _u32]),
+    "ola_ntt_inverse": (_int, [_vp, _vp, _int, _sz, _u32]),
+    "ola_coset_lde": (_int, [_vp, _vp, _vp, _int, _sz, _u32, _u32, _u64, _int]),
+    "ola_coset_intt": (_int, [_vp, _vp, _int, _sz, _u32, _u64]),
+    "ola_poseidon_permute": (_int, [_vp, _vp, _int, _sz]),
+    "ola_hash_rows": (_int, [_vp, _vp, _vp, _int, _sz, _sz]),
+    "ola_merkle_rows": (_int, [_vp, _vp, _int, _sz, _sz, _u32, _vp, _vp]),
+    "ola_commit": (_int, [_vp, _vp, _int, _sz, _u32, _int, _u32, _u32, ctypes.POINTER(_vp), _vp]),
+    "ola_batch_free": (_int, [_vp, _vp]),
+    "ola_batch_ncols": (_sz, [_vp]),
+    "ola_batch_degree_log": (_u32, [_vp]),
+    "ola_batch_rate_bits": (_u32, [_vp]),
+    "ola_batch_coeffs_dev": (_vp, [_vp]),
+    "ola_batch_lde_dev": (_vp, [_vp]),
+    "ola_batch_nodes_dev": (_vp, [_vp]),
+    "ola_batch_get_coeffs": (_int, [_vp, _vp, _vp]),
+    "ola_batch_get_cap": (_int, [_vp, _vp, _vp]),
+    "ola_batch_get_leaves": (_int, [_vp, _vp, _sz, _sz, _vp]),
+    "ola_batch_prove_leaf": (_int, [_vp, _vp, _sz, _vp]),
+}
+
+
+def header_symbols():
+    """Function names declared in include/ola_gpu.h."""
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ola_[a-z0-9_]+)\s*\(", text)))
+
+
+_lib = None
+
+
+def load():
+    """dlopen libola_gpu.so and bind every symbol of the header.  Raises if the library is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise OlaError(-7, f"{SO_PATH} not built: run `python -m olavm_b200.build` (there is no CPU fallback)")
+        lib = ctypes.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the library does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def hptr(a):
+    """Host numpy uint64 array -> void* (must be C-contiguous)."""
+    if a is None:
+        return None
+    assert isinstance(a, np.ndarray) and a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"], "need contiguous uint64"
+    return a.ctypes.data_as(_vp)

@@ -1,0 +1,347 @@
+// extern "C" surface of libola_gpu (declared in include/ola_gpu.h).  Every entry point converts C++
+// exceptions into error codes; nothing propagates across the ABI.
+#include <algorithm>
+#include <cstring>
+#include <memory>
+
+#include "batch.h"
+#include "common.h"
+#include "gl.cuh"
+#include "ntt.h"
+#include "poseidon.cuh"
+
+namespace {
+
+template <typename F>
+int guarded(ola_ctx* ctx, F&& f) {
+    try {
+        f();
+        return OLA_OK;
+    } catch (const ola::Error& e) {
+        if (ctx) ctx->last_error = e.what();
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        if (ctx) ctx->last_error = "host allocation failed";
+        return OLA_ERR_OOM;
+    } catch (const std::exception& e) {
+        if (ctx) ctx->last_error = e.what();
+        return OLA_ERR_INTERNAL;
+    } catch (...) {
+        if (ctx) ctx->last_error = "unknown error";
+        return OLA_ERR_INTERNAL;
+    }
+}
+
+// RAII device scratch
+struct DevBuf {
+    uint64_t* p = nullptr;
+    explicit DevBuf(size_t n) { ola::dev_alloc(&p, n); }
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+
+thread_local std::string g_init_error;
+
+void to_device(ola_ctx* ctx, uint64_t* dst, const uint64_t* src, size_t n) {
+    OLA_CUDA(cudaMemcpyAsync(dst, src, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+}
+void to_host(ola_ctx* ctx, uint64_t* dst, const uint64_t* src, size_t n) {
+    OLA_CUDA(cudaMemcpyAsync(dst, src, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+// natural -> natural transform of [ncols][n] (forward or inverse roots), data on device
+void ntt_natural(ola_ctx* ctx, uint64_t* d_data, size_t ncols, uint32_t log_n, bool inverse) {
+    const size_t n = (size_t)1 << log_n;
+    const bool multipass = ola::ntt::plan_passes((int)log_n).size() > 1;
+    std::unique_ptr<DevBuf> work;
+    if (multipass) work.reset(new DevBuf(ncols * n));
+    ola::ntt::FwdDesc d;
+    d.src = d_data;
+    d.src_col_stride = n;
+    d.work = multipass ? work->p : nullptr;
+    d.work_col_stride = n;
+    d.dst = d_data;
+    d.dst_col_stride = n;
+    d.ncols = ncols;
+    d.log_n = (int)log_n;
+    d.inverse_roots = inverse;
+    d.natural_output = true;
+    d.apply_scale = inverse;
+    d.scale = inverse ? gl::inv(((uint64_t)1 << log_n) % gl::P) : 1;
+    ola::ntt::forward(ctx, d);
+    if (multipass) OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+}  // namespace
+
+extern "C" {
+
+int ola_gpu_init(int device, ola_ctx** out) {
+    if (!out) return OLA_ERR_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return OLA_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return OLA_ERR_NO_DEVICE;
+    if (prop.major != 10) return OLA_ERR_NO_DEVICE;  // built for sm_100a only; no fallback path exists
+    ola_ctx* ctx = new (std::nothrow) ola_ctx();
+    if (!ctx) return OLA_ERR_OOM;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    int rc = guarded(ctx, [&] {
+        OLA_CUDA(cudaSetDevice(device));
+        OLA_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ola::poseidon::init_constants();
+        ola::ntt::init_twiddles(ctx);
+        OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+    if (rc != OLA_OK) {
+        ola_gpu_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return OLA_OK;
+}
+
+void ola_gpu_destroy(ola_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    ola::ntt::free_twiddles(ctx);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* ola_gpu_last_error(const ola_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+int ola_gpu_sync(ola_ctx* ctx) {
+    if (!ctx) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] { OLA_CUDA(cudaStreamSynchronize(ctx->stream)); });
+}
+uint64_t ola_gpu_kernel_launches(const ola_ctx* ctx) { return ctx ? ctx->kernel_launches : 0; }
+void* ola_gpu_stream(ola_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int ola_dev_alloc(ola_ctx* ctx, size_t n_u64, uint64_t** dptr) {
+    if (!ctx || !dptr) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] { ola::dev_alloc(dptr, n_u64); });
+}
+int ola_dev_free(ola_ctx* ctx, uint64_t* dptr) {
+    if (!ctx) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (dptr) OLA_CUDA(cudaFree(dptr));
+    });
+}
+int ola_dev_upload(ola_ctx* ctx, uint64_t* dst_dev, const uint64_t* src_host, size_t n_u64) {
+    if (!ctx || (!dst_dev && n_u64) || (!src_host && n_u64)) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        to_device(ctx, dst_dev, src_host, n_u64);
+        OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int ola_dev_download(ola_ctx* ctx, uint64_t* dst_host, const uint64_t* src_dev, size_t n_u64) {
+    if (!ctx || (!dst_host && n_u64) || (!src_dev && n_u64)) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] { to_host(ctx, dst_host, src_dev, n_u64); });
+}
+
+static int ntt_entry(ola_ctx* ctx, uint64_t* data, int on_device, size_t ncols, uint32_t log_n, bool inverse) {
+    if (!ctx || !data) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        OLA_CHECK(log_n <= 32, OLA_ERR_INVALID_ARG, "multiplicative subgroup of that size does not exist (two-adicity 32)");
+        const size_t n = (size_t)1 << log_n;
+        if (on_device) {
+            ntt_natural(ctx, data, ncols, log_n, inverse);
+        } else {
+            DevBuf d(ncols * n);
+            to_device(ctx, d.p, data, ncols * n);
+            ntt_natural(ctx, d.p, ncols, log_n, inverse);
+            to_host(ctx, data, d.p, ncols * n);
+        }
+    });
+}
+int ola_ntt_forward(ola_ctx* ctx, uint64_t* data, int on_device, size_t ncols, uint32_t log_n) {
+    return ntt_entry(ctx, data, on_device, ncols, log_n, false);
+}
+int ola_ntt_inverse(ola_ctx* ctx, uint64_t* data, int on_device, size_t ncols, uint32_t log_n) {
+    return ntt_entry(ctx, data, on_device, ncols, log_n, true);
+}
+
+int ola_coset_lde(ola_ctx* ctx, const uint64_t* coeffs, uint64_t* out, int on_device, size_t ncols, uint32_t log_n,
+                  uint32_t rate_bits, uint64_t shift, int natural_order) {
+    if (!ctx || !coeffs || !out) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        OLA_CHECK(log_n + rate_bits <= 32, OLA_ERR_INVALID_ARG,
+                  "multiplicative subgroup of that size does not exist (two-adicity 32)");
+        OLA_CHECK((1u << rate_bits) <= (unsigned)ola::ntt::MAX_COSETS, OLA_ERR_INVALID_ARG, "blowup factor too large");
+        OLA_CHECK(gl::canon(shift) != 0, OLA_ERR_INVALID_ARG, "domain offset cannot be zero");
+        const size_t n = (size_t)1 << log_n, L = n << rate_bits;
+        std::unique_ptr<DevBuf> d_in, d_out, d_work;
+        const uint64_t* src = coeffs;
+        uint64_t* dst = out;
+        if (!on_device) {
+            d_in.reset(new DevBuf(ncols * n));
+            d_out.reset(new DevBuf(ncols * L));
+            to_device(ctx, d_in->p, coeffs, ncols * n);
+            src = d_in->p;
+            dst = d_out->p;
+        }
+        ola::ntt::FwdDesc d;
+        d.src = src;
+        d.src_col_stride = n;
+        d.dst = dst;
+        d.dst_col_stride = L;
+        d.dst_coset_stride = n;
+        d.ncols = ncols;
+        d.log_n = (int)log_n;
+        d.coset_bits = (int)rate_bits;
+        d.shift = gl::canon(shift);
+        d.natural_output = natural_order != 0;
+        if (natural_order && ola::ntt::plan_passes((int)log_n).size() > 1) {
+            d_work.reset(new DevBuf(ncols * L));
+            d.work = d_work->p;
+            d.work_col_stride = L;
+            d.work_coset_stride = n;
+        }
+        ola::ntt::forward(ctx, d);
+        if (!on_device)
+            to_host(ctx, out, dst, ncols * L);
+        else if (d_work)
+            OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int ola_coset_intt(ola_ctx* ctx, uint64_t* data, int on_device, size_t ncols, uint32_t log_n, uint64_t shift) {
+    if (!ctx || !data) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        OLA_CHECK(log_n <= 32, OLA_ERR_INVALID_ARG, "multiplicative subgroup of that size does not exist (two-adicity 32)");
+        OLA_CHECK(gl::canon(shift) != 0, OLA_ERR_INVALID_ARG, "domain offset cannot be zero");
+        const size_t n = (size_t)1 << log_n;
+        std::unique_ptr<DevBuf> d;
+        uint64_t* p = data;
+        if (!on_device) {
+            d.reset(new DevBuf(ncols * n));
+            to_device(ctx, d->p, data, ncols * n);
+            p = d->p;
+        }
+        ntt_natural(ctx, p, ncols, log_n, true);
+        // coefficients of p(shift * x) -> coefficients of p: c_j *= shift^-j   (cfft/serial.rs:73-78)
+        ola::ntt::scale_powers(ctx, p, n, ncols, n, 1, gl::inv(gl::canon(shift)));
+        if (!on_device) to_host(ctx, data, p, ncols * n);
+    });
+}
+
+int ola_poseidon_permute(ola_ctx* ctx, uint64_t* states, int on_device, size_t nstates) {
+    if (!ctx || (!states && nstates)) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        if (on_device) {
+            ola::poseidon::permute_states(ctx, states, nstates);
+        } else {
+            DevBuf d(nstates * 12);
+            to_device(ctx, d.p, states, nstates * 12);
+            ola::poseidon::permute_states(ctx, d.p, nstates);
+            to_host(ctx, states, d.p, nstates * 12);
+        }
+    });
+}
+
+int ola_hash_rows(ola_ctx* ctx, const uint64_t* rows, uint64_t* digests, int on_device, size_t nrows, size_t ncols) {
+    if (!ctx || !digests || (!rows && nrows * ncols)) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        if (on_device) {
+            ola::poseidon::hash_rows_rowmajor(ctx, rows, nrows, ncols, digests);
+        } else {
+            DevBuf d(nrows * ncols), o(nrows * 4);
+            to_device(ctx, d.p, rows, nrows * ncols);
+            ola::poseidon::hash_rows_rowmajor(ctx, d.p, nrows, ncols, o.p);
+            to_host(ctx, digests, o.p, nrows * 4);
+        }
+    });
+}
+
+int ola_merkle_rows(ola_ctx* ctx, const uint64_t* rows, int on_device, size_t nrows, size_t ncols, uint32_t cap_height,
+                    uint64_t* cap_out_host, uint64_t* nodes_out_host) {
+    if (!ctx || !rows || !cap_out_host) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        OLA_CHECK(nrows && (nrows & (nrows - 1)) == 0, OLA_ERR_INVALID_ARG, "number of leaves must be a power of two");
+        OLA_CHECK(((size_t)1 << cap_height) <= nrows, OLA_ERR_INVALID_ARG, "cap height should be at most log2(leaves.len())");
+        std::unique_ptr<DevBuf> d;
+        const uint64_t* src = rows;
+        if (!on_device) {
+            d.reset(new DevBuf(nrows * ncols));
+            to_device(ctx, d->p, rows, nrows * ncols);
+            src = d->p;
+        }
+        DevBuf nodes(2 * nrows * 4);
+        OLA_CUDA(cudaMemsetAsync(nodes.p, 0, 2 * nrows * 32, ctx->stream));
+        ola::poseidon::hash_rows_rowmajor(ctx, src, nrows, ncols, nodes.p + 4 * nrows);
+        ola::poseidon::merkle_levels(ctx, nodes.p, nrows, nodes_out_host ? 1 : ((size_t)1 << cap_height));
+        const size_t ncap = (size_t)1 << cap_height;
+        to_host(ctx, cap_out_host, nodes.p + 4 * ncap, ncap * 4);
+        if (nodes_out_host) to_host(ctx, nodes_out_host, nodes.p, 2 * nrows * 4);
+    });
+}
+
+int ola_commit(ola_ctx* ctx, const uint64_t* cols, int on_device, size_t ncols, uint32_t log_n, int is_coeffs,
+               uint32_t rate_bits, uint32_t cap_height, ola_batch** out, uint64_t* cap_out_host) {
+    if (!ctx || !out) return OLA_ERR_INVALID_ARG;
+    *out = nullptr;
+    return guarded(ctx, [&] {
+        ola_batch* b = ola::batch_commit(ctx, cols, on_device != 0, ncols, log_n, is_coeffs != 0, rate_bits, cap_height);
+        try {
+            if (cap_out_host)
+                ola::batch_get_cap(ctx, b, cap_out_host);
+            else
+                OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+        } catch (...) {
+            ola::batch_release(b);
+            delete b;
+            throw;
+        }
+        *out = b;
+    });
+}
+
+int ola_batch_free(ola_ctx* ctx, ola_batch* b) {
+    if (!ctx) return OLA_ERR_INVALID_ARG;
+    if (!b) return OLA_OK;
+    return guarded(ctx, [&] {
+        OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+        ola::batch_release(b);
+        delete b;
+    });
+}
+size_t ola_batch_ncols(const ola_batch* b) { return b ? b->ncols : 0; }
+uint32_t ola_batch_degree_log(const ola_batch* b) { return b ? b->log_n : 0; }
+uint32_t ola_batch_rate_bits(const ola_batch* b) { return b ? b->rate_bits : 0; }
+const uint64_t* ola_batch_coeffs_dev(const ola_batch* b) { return b ? b->d_coeffs : nullptr; }
+const uint64_t* ola_batch_lde_dev(const ola_batch* b) { return b ? b->d_lde : nullptr; }
+const uint64_t* ola_batch_nodes_dev(const ola_batch* b) { return b ? b->d_nodes : nullptr; }
+
+int ola_batch_get_coeffs(ola_ctx* ctx, const ola_batch* b, uint64_t* out_host) {
+    if (!ctx || !b || !out_host) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] { to_host(ctx, out_host, b->d_coeffs, b->ncols << b->log_n); });
+}
+int ola_batch_get_cap(ola_ctx* ctx, const ola_batch* b, uint64_t* cap_out_host) {
+    if (!ctx || !b || !cap_out_host) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] { ola::batch_get_cap(ctx, b, cap_out_host); });
+}
+int ola_batch_get_leaves(ola_ctx* ctx, const ola_batch* b, size_t leaf_index, size_t count, uint64_t* out_host) {
+    if (!ctx || !b || (!out_host && count)) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] { ola::batch_get_leaves(ctx, b, leaf_index, count, out_host); });
+}
+int ola_batch_prove_leaf(ola_ctx* ctx, const ola_batch* b, size_t leaf_index, uint64_t* siblings_out_host) {
+    if (!ctx || !b || !siblings_out_host) return OLA_ERR_INVALID_ARG;
+    int n = 0;
+    int rc = guarded(ctx, [&] { n = ola::batch_prove_leaf(ctx, b, leaf_index, siblings_out_host); });
+    return rc == OLA_OK ? n : rc;
+}
+
+}  // extern "C"

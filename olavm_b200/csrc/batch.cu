@@ -1,0 +1,201 @@
+// PolynomialBatch on the device: commit = iNTT -> coset LDE -> Poseidon leaf sponge -> Merkle levels.
+//
+// Replaces plonky2/plonky2/src/fri/oracle.rs:45-99 (PolynomialBatch::from_values / from_coeffs), the
+// per-row accessors :132-164 and MerkleTree::{get, prove} (hash/merkle_tree/mod.rs:268-308).
+//
+// HBM layout of a batch (everything stays resident between prover phases):
+//   coeffs [ncols][n]        natural-order coefficients                 (PolynomialBatch.polynomials)
+//   lde    [ncols][8n]       COLUMN-major, "leaf order": lde[c][r] = p_c(7 * g^bitrev(r)); rows
+//                            [i*n, (i+1)*n) are exactly coset 7*g^bitrev3(i)*H_n, i.e. 2 of the 16 cap
+//                            subtrees -> natural multi-GPU shard
+//   nodes  [2*8n][4]         heap order: node 1 = root, children 2i / 2i+1, leaf digests at [8n, 16n)
+// The reference materialises row-major `leaves: Vec<Vec<F>>` plus an interleaved `digests` vector
+// (merkle_tree/mod.rs:40-58); both are derivable views of the arrays above, produced on demand by
+// ola_batch_get_leaves / ola_batch_prove_leaf.
+#include "batch.h"
+
+#include "gl.cuh"
+#include "ntt.h"
+#include "poseidon.cuh"
+
+namespace ola {
+
+__global__ void canon_copy_kernel(uint64_t* dst, const uint64_t* src, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = gl::canon(src[i]);
+}
+
+// out[k][c] = lde[c][first + k]
+__global__ void gather_rows_kernel(const uint64_t* lde, size_t col_stride, size_t ncols, size_t first, size_t count,
+                                   uint64_t* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count * ncols) return;
+    size_t k = i / ncols, c = i % ncols;
+    out[i] = lde[c * col_stride + first + k];
+}
+
+// siblings bottom-up: level j sibling = nodes[((nleaves + leaf) >> j) ^ 1]
+__global__ void gather_path_kernel(const uint64_t* nodes, size_t nleaves, size_t leaf, int nsib, uint64_t* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsib * 4) return;
+    int j = i / 4, w = i % 4;
+    size_t idx = ((nleaves + leaf) >> j) ^ 1;
+    out[i] = nodes[idx * 4 + w];
+}
+
+static void canon_copy(ola_ctx* ctx, uint64_t* dst, const uint64_t* src, size_t n) {
+    if (!n) return;
+    unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16);
+    canon_copy_kernel<<<blocks, 256, 0, ctx->stream>>>(dst, src, n);
+    check_launch("canon_copy_kernel");
+    count_launch(ctx);
+}
+
+void dev_alloc(uint64_t** p, size_t n_u64) {
+    cudaError_t e = cudaMalloc(p, std::max<size_t>(n_u64, 1) * sizeof(uint64_t));
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        throw Error(OLA_ERR_OOM, "cudaMalloc: out of device memory (" + std::to_string(n_u64 * 8) + " bytes)");
+    }
+    OLA_CUDA(e);
+}
+
+ola_batch* batch_commit(ola_ctx* ctx, const uint64_t* cols, bool on_device, size_t ncols, uint32_t log_n, bool is_coeffs,
+                        uint32_t rate_bits, uint32_t cap_height) {
+    OLA_CHECK(cols != nullptr && ncols > 0, OLA_ERR_INVALID_ARG, "commit: empty batch");
+    OLA_CHECK(log_n + rate_bits <= 32, OLA_ERR_INVALID_ARG, "commit: LDE size exceeds the field's two-adicity (2^32)");
+    OLA_CHECK(cap_height <= log_n + rate_bits, OLA_ERR_INVALID_ARG, "commit: cap height should be at most log2(leaves)");
+    OLA_CHECK((1u << rate_bits) <= (unsigned)ntt::MAX_COSETS, OLA_ERR_INVALID_ARG, "commit: rate_bits too large");
+    std::unique_ptr<ola_batch, void (*)(ola_batch*)> b(new ola_batch(), [](ola_batch* p) {
+        batch_release(p);
+        delete p;
+    });
+    b->ncols = ncols;
+    b->log_n = log_n;
+    b->rate_bits = rate_bits;
+    b->cap_height = cap_height;
+    const size_t n = (size_t)1 << log_n, L = n << rate_bits;
+    dev_alloc(&b->d_coeffs, ncols * n);
+    dev_alloc(&b->d_lde, ncols * L);
+    dev_alloc(&b->d_nodes, 2 * L * 4);
+
+    // stage the input in the (still unused) LDE buffer, then transform into d_coeffs
+    uint64_t* stage = b->d_lde;
+    if (is_coeffs) {
+        if (on_device) {
+            canon_copy(ctx, b->d_coeffs, cols, ncols * n);
+        } else {
+            OLA_CUDA(cudaMemcpyAsync(stage, cols, ncols * n * 8, cudaMemcpyHostToDevice, ctx->stream));
+            canon_copy(ctx, b->d_coeffs, stage, ncols * n);
+        }
+    } else {
+        const uint64_t* src = cols;
+        if (!on_device) {
+            OLA_CUDA(cudaMemcpyAsync(stage, cols, ncols * n * 8, cudaMemcpyHostToDevice, ctx->stream));
+            src = stage;
+        }
+        // values on H (natural) -> coefficients (natural): forward network with inverse roots, x 1/n
+        // (PolynomialValues::ifft, polynomial/mod.rs:60-65)
+        ntt::FwdDesc d;
+        d.src = src;
+        d.src_col_stride = n;
+        // never clobber a caller-owned device buffer: a second scratch region when the input is resident
+        uint64_t* tmp_work = nullptr;
+        if (!on_device) {
+            d.work = stage;
+        } else if (rate_bits >= 1) {
+            d.work = stage;
+        } else {
+            dev_alloc(&tmp_work, ncols * n);
+            d.work = tmp_work;
+        }
+        d.work_col_stride = n;
+        d.dst = b->d_coeffs;
+        d.dst_col_stride = n;
+        d.ncols = ncols;
+        d.log_n = (int)log_n;
+        d.inverse_roots = true;
+        d.natural_output = true;
+        d.apply_scale = true;
+        d.scale = gl::inv(((uint64_t)1 << log_n) % gl::P);
+        try {
+            ntt::forward(ctx, d);
+        } catch (...) {
+            if (tmp_work) cudaFree(tmp_work);
+            throw;
+        }
+        if (tmp_work) {
+            OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+            cudaFree(tmp_work);
+        }
+    }
+    // coset LDE, shift 7, blowup 2^rate_bits, straight into leaf order (oracle.rs:101-129 + :84-85)
+    {
+        ntt::FwdDesc d;
+        d.src = b->d_coeffs;
+        d.src_col_stride = n;
+        d.dst = b->d_lde;
+        d.dst_col_stride = L;
+        d.dst_coset_stride = n;
+        d.ncols = ncols;
+        d.log_n = (int)log_n;
+        d.coset_bits = (int)rate_bits;
+        d.shift = gl::GEN;
+        ntt::forward(ctx, d);
+    }
+    // MerkleTree::new_v2: leaf digests then level reduction down to the cap
+    poseidon::hash_rows_colmajor(ctx, b->d_lde, L, L, ncols, b->d_nodes + 4 * L);
+    poseidon::merkle_levels(ctx, b->d_nodes, L, (size_t)1 << cap_height);
+    return b.release();
+}
+
+void batch_release(ola_batch* b) {
+    if (!b) return;
+    if (b->d_coeffs) cudaFree(b->d_coeffs);
+    if (b->d_lde) cudaFree(b->d_lde);
+    if (b->d_nodes) cudaFree(b->d_nodes);
+    b->d_coeffs = b->d_lde = b->d_nodes = nullptr;
+}
+
+void batch_get_cap(ola_ctx* ctx, const ola_batch* b, uint64_t* cap_host) {
+    const size_t L = (size_t)1 << (b->log_n + b->rate_bits), ncap = (size_t)1 << b->cap_height;
+    // cap = nodes[2^h .. 2^(h+1)); when the tree is all cap these are the leaf digests (mod.rs:216-225)
+    OLA_CUDA(cudaMemcpyAsync(cap_host, b->d_nodes + 4 * ncap, ncap * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+    (void)L;
+}
+
+void batch_get_leaves(ola_ctx* ctx, const ola_batch* b, size_t first, size_t count, uint64_t* out_host) {
+    const size_t L = (size_t)1 << (b->log_n + b->rate_bits);
+    OLA_CHECK(first + count <= L, OLA_ERR_INVALID_ARG, "get_leaves: leaf index out of range");
+    if (!count) return;
+    uint64_t* tmp = nullptr;
+    dev_alloc(&tmp, count * b->ncols);
+    size_t total = count * b->ncols;
+    gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(b->d_lde, L, b->ncols, first, count, tmp);
+    count_launch(ctx);
+    cudaError_t e = cudaMemcpyAsync(out_host, tmp, total * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(tmp);
+    OLA_CUDA(e);
+}
+
+int batch_prove_leaf(ola_ctx* ctx, const ola_batch* b, size_t leaf, uint64_t* sib_host) {
+    const uint32_t lg = b->log_n + b->rate_bits;
+    const size_t L = (size_t)1 << lg;
+    OLA_CHECK(leaf < L, OLA_ERR_INVALID_ARG, "prove_leaf: leaf index out of range");
+    const int nsib = (int)lg - (int)b->cap_height;
+    if (nsib <= 0) return 0;
+    uint64_t* tmp = nullptr;
+    dev_alloc(&tmp, (size_t)nsib * 4);
+    gather_path_kernel<<<(nsib * 4 + 63) / 64, 64, 0, ctx->stream>>>(b->d_nodes, L, leaf, nsib, tmp);
+    count_launch(ctx);
+    cudaError_t e = cudaMemcpyAsync(sib_host, tmp, (size_t)nsib * 32, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(tmp);
+    OLA_CUDA(e);
+    return nsib;
+}
+
+}  // namespace ola

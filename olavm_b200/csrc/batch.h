@@ -1,0 +1,23 @@
+// Device-resident PolynomialBatch (internal).
+#pragma once
+#include <memory>
+
+#include "common.h"
+
+struct ola_batch {
+    size_t ncols = 0;
+    uint32_t log_n = 0, rate_bits = 0, cap_height = 0;
+    uint64_t* d_coeffs = nullptr;  // [ncols][n]
+    uint64_t* d_lde = nullptr;     // [ncols][n << rate_bits]  leaf order
+    uint64_t* d_nodes = nullptr;   // [2 * (n << rate_bits)][4] heap order
+};
+
+namespace ola {
+void dev_alloc(uint64_t** p, size_t n_u64);
+ola_batch* batch_commit(ola_ctx* ctx, const uint64_t* cols, bool on_device, size_t ncols, uint32_t log_n, bool is_coeffs,
+                        uint32_t rate_bits, uint32_t cap_height);
+void batch_release(ola_batch* b);
+void batch_get_cap(ola_ctx* ctx, const ola_batch* b, uint64_t* cap_host);
+void batch_get_leaves(ola_ctx* ctx, const ola_batch* b, size_t first, size_t count, uint64_t* out_host);
+int batch_prove_leaf(ola_ctx* ctx, const ola_batch* b, size_t leaf, uint64_t* sib_host);
+}  // namespace ola

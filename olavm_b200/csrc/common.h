@@ -1,0 +1,62 @@
+// Internal shared declarations of libola_gpu (context, error handling, device buffers).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/ola_gpu.h"
+
+namespace ola {
+
+struct Error : public std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define OLA_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            throw ola::Error(OLA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + \
+                                               __FILE__ + ":" + std::to_string(__LINE__) + ")");    \
+    } while (0)
+
+#define OLA_CHECK(cond, code, msg)                         \
+    do {                                                   \
+        if (!(cond)) throw ola::Error((code), (msg));      \
+    } while (0)
+
+// Device twiddle material, built once per context (the analogue of the reference's
+// `twiddle_map: BTreeMap<usize, Vec<F>>`, fri/oracle.rs:51, prover.rs:106 -- but size-independent).
+struct Twiddles {
+    // Three-level power tables of Omega = omega_{2^32} (TA[x] = Omega^x, x < 2^11; TB[x] = Omega^(x<<11),
+    // x < 2^11; TC[x] = Omega^(x<<22), x < 2^10), forward ([0]) and inverse ([1]).
+    uint64_t* pw[2] = {nullptr, nullptr};  // 5120 entries each: TA | TB | TC
+    // Bit-reversed small root table BRS[i] = omega_{2^(k+1)}^{bitrev_k(i)} for i < 2^k <= 2^11
+    // (prefix property: one table serves every k), forward and inverse.
+    uint64_t* brs[2] = {nullptr, nullptr};  // 2048 entries each
+};
+
+}  // namespace ola
+
+struct ola_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    ola::Twiddles tw;
+    std::string last_error;
+    uint64_t kernel_launches = 0;  // counted by every launcher (bench.py "gpu_launches")
+};
+
+namespace ola {
+inline void count_launch(ola_ctx* ctx, uint64_t n = 1) { ctx->kernel_launches += n; }
+inline void check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw Error(OLA_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+}  // namespace ola

@@ -1,0 +1,147 @@
+// Goldilocks field arithmetic for sm_100a (p = 2^64 - 2^32 + 1) and its quadratic extension.
+//
+// Replaces the reference's CPU field on the proving hot path:
+//   plonky2/field/src/goldilocks_field.rs  (add :191-213, sub :228-250, mul :259-266, reduce128 :342-355)
+//   plonky2/field/src/goldilocks_extensions.rs :14-39 (X^2 - 7), extension/quadratic.rs
+//
+// Representation: every value stored in HBM or returned by these functions is the CANONICAL
+// representative in [0, p).  (The reference keeps lazy representatives in [0, 2^64) and only
+// canonicalises on compare/serialise, goldilocks_field.rs:162-170; the field element is the same.)
+// All arithmetic is 64-bit integer math on the INT32/IMAD pipes -- there is no tensor-core path for
+// modular arithmetic.  The same header compiles for the host (challenger, twiddle setup).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define GL_HD __host__ __device__ __forceinline__
+#define GL_D __device__ __forceinline__
+#else
+#define GL_HD inline
+#define GL_D inline
+#endif
+
+namespace gl {
+
+static constexpr uint64_t P = 0xFFFFFFFF00000001ULL;
+static constexpr uint64_t EPS = 0xFFFFFFFFULL;
+static constexpr uint64_t GEN = 7;                              // goldilocks_field.rs:66
+static constexpr uint64_t TWO_ADIC_GEN = 1753635133440165772ULL;  // goldilocks_field.rs:77 (order 2^32)
+static constexpr int TWO_ADICITY = 32;
+
+GL_HD uint64_t canon(uint64_t x) { return x >= P ? x - P : x; }
+
+// a, b canonical -> canonical
+GL_HD uint64_t add(uint64_t a, uint64_t b) {
+    uint64_t s = a + b;
+    uint64_t t = s + EPS;  // s - p (mod 2^64); wraps iff s >= p
+    return ((s < a) | (t < s)) ? t : s;
+}
+GL_HD uint64_t sub(uint64_t a, uint64_t b) {
+    uint64_t d = a - b;
+    return (a < b) ? d - EPS : d;  // d + p (mod 2^64)
+}
+GL_HD uint64_t neg(uint64_t a) { return a ? P - a : 0; }
+GL_HD uint64_t dbl(uint64_t a) { return add(a, a); }
+
+// x = hi*2^64 + lo  ->  canonical x mod p.  2^64 = 2^32 - 1, 2^96 = -1 (mod p).
+GL_HD uint64_t reduce128(uint64_t lo, uint64_t hi) {
+    uint64_t hi_hi = hi >> 32, hi_lo = hi & EPS;
+    uint64_t t0 = lo - hi_hi;
+    if (lo < hi_hi) t0 -= EPS;
+    uint64_t t1 = (hi_lo << 32) - hi_lo;  // hi_lo * (2^32 - 1)
+    uint64_t t2 = t0 + t1;
+    if (t2 < t1) t2 += EPS;
+    return canon(t2);
+}
+
+GL_HD void mul_wide(uint64_t a, uint64_t b, uint64_t& lo, uint64_t& hi) {
+#if defined(__CUDA_ARCH__)
+    lo = a * b;
+    hi = __umul64hi(a, b);
+#else
+    unsigned __int128 p = (unsigned __int128)a * b;
+    lo = (uint64_t)p;
+    hi = (uint64_t)(p >> 64);
+#endif
+}
+
+GL_HD uint64_t mul(uint64_t a, uint64_t b) {
+    uint64_t lo, hi;
+    mul_wide(a, b, lo, hi);
+    return reduce128(lo, hi);
+}
+GL_HD uint64_t sqr(uint64_t a) { return mul(a, a); }
+// a*b + c  (c canonical)
+GL_HD uint64_t mad(uint64_t a, uint64_t b, uint64_t c) { return add(mul(a, b), c); }
+
+GL_HD uint64_t pow(uint64_t b, uint64_t e) {
+    uint64_t r = 1;
+    while (e) {
+        if (e & 1) r = mul(r, b);
+        b = sqr(b);
+        e >>= 1;
+    }
+    return r;
+}
+GL_HD uint64_t inv(uint64_t a) { return pow(a, P - 2); }
+
+// types.rs:240-244 primitive_root_of_unity
+GL_HD uint64_t root_of_unity(int n_log) {
+    uint64_t b = TWO_ADIC_GEN;
+    for (int i = 0; i < TWO_ADICITY - n_log; i++) b = sqr(b);
+    return b;
+}
+
+// ---- quadratic extension F[X]/(X^2 - 7) ----
+struct ext2 {
+    uint64_t c0, c1;
+};
+GL_HD ext2 make2(uint64_t a, uint64_t b) {
+    ext2 r;
+    r.c0 = a;
+    r.c1 = b;
+    return r;
+}
+GL_HD ext2 add(ext2 a, ext2 b) { return make2(add(a.c0, b.c0), add(a.c1, b.c1)); }
+GL_HD ext2 sub(ext2 a, ext2 b) { return make2(sub(a.c0, b.c0), sub(a.c1, b.c1)); }
+GL_HD ext2 neg(ext2 a) { return make2(neg(a.c0), neg(a.c1)); }
+GL_HD uint64_t mul7(uint64_t a) {
+    // 7a = 8a - a, three doublings and a subtraction: cheaper than a full product
+    uint64_t a2 = dbl(a), a4 = dbl(a2), a8 = dbl(a4);
+    return sub(a8, a);
+}
+GL_HD ext2 mul(ext2 a, ext2 b) {
+    uint64_t c0 = add(mul(a.c0, b.c0), mul7(mul(a.c1, b.c1)));
+    uint64_t c1 = add(mul(a.c0, b.c1), mul(a.c1, b.c0));
+    return make2(c0, c1);
+}
+GL_HD ext2 mul(ext2 a, uint64_t s) { return make2(mul(a.c0, s), mul(a.c1, s)); }
+GL_HD ext2 sqr(ext2 a) { return mul(a, a); }
+GL_HD bool eq(ext2 a, ext2 b) { return a.c0 == b.c0 && a.c1 == b.c1; }
+GL_HD ext2 inv(ext2 a) {
+    uint64_t n = sub(sqr(a.c0), mul7(sqr(a.c1)));
+    uint64_t ni = inv(n);
+    return make2(mul(a.c0, ni), mul(neg(a.c1), ni));
+}
+GL_HD ext2 pow(ext2 b, uint64_t e) {
+    ext2 r = make2(1, 0);
+    while (e) {
+        if (e & 1) r = mul(r, b);
+        b = sqr(b);
+        e >>= 1;
+    }
+    return r;
+}
+
+GL_HD uint32_t bitrev32(uint32_t x, int bits) {
+    if (bits == 0) return 0;
+#if defined(__CUDA_ARCH__)
+    return __brev(x) >> (32 - bits);
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
+    return r;
+#endif
+}
+
+}  // namespace gl

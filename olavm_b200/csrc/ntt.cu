@@ -1,0 +1,421 @@
+// Goldilocks NTT / iNTT / coset-LDE kernels for sm_100a.
+//
+// Replaces, on the proving hot path:
+//   plonky2/field/src/cfft/{mod,serial,concurrent}.rs   evaluate_poly, interpolate_poly,
+//       evaluate_poly_with_offset (coset LDE), interpolate_poly_with_offset (coset iNTT)
+//   plonky2/plonky2/src/fri/oracle.rs:84-85             transpose + reverse_index_bits_in_place
+//       (fused away: the un-permuted output of the forward network IS the Merkle leaf order)
+//
+// Design (B200-first, not a translation of the reference's recursion):
+//   * One butterfly network, two directions.  FORWARD = Cooley-Tukey butterflies (multiply, then
+//     add/sub) over natural-order input, producing bit-reversed *positions*; INVERSE = Gentleman-Sande
+//     butterflies undoing it.  A coset shift s is folded into the twiddles (stage-u twiddle of the
+//     sub-block evaluating on sigma*H_m is sigma^(m/2^(u+1)) * omega_{2^(u+1)}^{bitrev(q)}), so a coset
+//     LDE costs exactly the butterflies of a plain NTT: no separate "clone_and_shift" pass
+//     (cfft/concurrent.rs:186) and no inter-pass four-step twiddle multiply.
+//   * A transform of 2^L points is cut into passes of <= 11 stages.  Each pass stages a tile in
+//     shared memory: the first pass(es) take tiles of T=8 adjacent low indices x 2^l strided rows
+//     (64-byte coalesced segments), the last pass takes contiguous 2^l-element runs.  HBM traffic is
+//     one read + one write of the data per pass.
+//   * Twiddles: per tile, 2^l - 1 products  c_u * BRS[q]  built in shared memory from a 2048-entry
+//     bit-reversed root table (L1/L2 resident) and l per-row constants c_u obtained from a 3-level
+//     power table of omega_{2^32} (5120 entries).  No O(n) twiddle table is ever streamed from HBM.
+//   * Column batches, cosets and tiles map to blockIdx.{y,z,x}: thousands of CTAs per launch, a
+//     multiple-wave fill of the 148 SMs for every real trace shape.
+//   * This is 64-bit modular integer arithmetic: IMAD/IADD3 pipes only, no tensor-core formulation.
+#include "common.h"
+#include "gl.cuh"
+#include "ntt.h"
+
+namespace ola {
+namespace ntt {
+
+static constexpr int MAX_PASS_LOG = 11;
+static constexpr int TILE_T = 8;
+
+struct PassArgs {
+    const uint64_t* src;
+    uint64_t* dst;
+    size_t src_col_stride, dst_col_stride;      // elements between consecutive columns
+    size_t src_coset_stride, dst_coset_stride;  // elements between consecutive cosets (blockIdx.z)
+    const uint64_t* pw;   // 3-level omega_{2^32} power tables (direction chosen by the host)
+    const uint64_t* brs;  // bit-reversed small root table (same direction)
+    int L;                // log2 of the transform size
+    int M;                // log2 of the sub-block size entering this pass
+    int l;                // stages handled by this pass
+    int G;                // contiguous pass: sub-blocks per CTA
+    int bitrev_store;     // contiguous pass: write to bit-reversed (natural-order) addresses
+    size_t out_mul;       // bitrev_store: address = natural_index*out_mul + bitrev(coset)  (interleaved cosets)
+    int coset_bits;
+    int apply_scale;
+    uint64_t scale;
+    uint64_t s_last[MAX_COSETS];  // per coset: (shift_i)^(2^(M-l)), or its inverse for the GS network
+};
+
+__device__ __forceinline__ uint64_t pow_omega(const uint64_t* __restrict__ pw, uint32_t E) {
+    uint64_t r = __ldg(pw + 4096 + (E >> 22));
+    r = gl::mul(r, __ldg(pw + 2048 + ((E >> 11) & 2047u)));
+    r = gl::mul(r, __ldg(pw + (E & 2047u)));
+    return r;
+}
+
+// c[u] for u = 0..l-1 of the sub-block Q (t = L - M stages already done):
+//   c[l-1] = s_last * omega_{2^(t+l)}^{bitrev_t(Q)},  c[u-1] = c[u]^2.
+__device__ __forceinline__ void row_constants(const PassArgs& a, uint64_t s_last, uint32_t Q, uint64_t* c) {
+    const int t = a.L - a.M;
+    uint32_t e = gl::bitrev32(Q, t);
+    uint32_t E = (t == 0) ? 0u : (e << (32 - t - a.l));
+    uint64_t v = gl::mul(s_last, pow_omega(a.pw, E));
+    for (int u = a.l - 1; u >= 0; --u) {
+        c[u] = v;
+        v = gl::sqr(v);
+    }
+}
+
+// ---- strided pass: tile = (sub-block Q, T adjacent inner indices) x all 2^l rows -----------------
+template <bool GS>
+__global__ void __launch_bounds__(1024) pass_strided(const PassArgs a) {
+    extern __shared__ uint64_t sm[];
+    const int l = a.l, R = 1 << l, T = TILE_T;
+    uint64_t* tw = sm;        // [R]   tw[2^u + q]
+    uint64_t* cu = sm + R;    // [16]
+    uint64_t* x = sm + R + 16;  // [R][T]
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t coset = blockIdx.z;
+    const size_t inner = (size_t)1 << (a.M - l);
+    const uint32_t tiles_per_sub = (uint32_t)(inner / T);
+    const uint32_t Q = blockIdx.x / tiles_per_sub;
+    const size_t c0 = (size_t)(blockIdx.x % tiles_per_sub) * T;
+    const uint64_t* in = a.src + blockIdx.y * a.src_col_stride + coset * a.src_coset_stride + ((size_t)Q << a.M) + c0;
+    uint64_t* out = a.dst + blockIdx.y * a.dst_col_stride + coset * a.dst_coset_stride + ((size_t)Q << a.M) + c0;
+
+    if (tid == 0) row_constants(a, a.s_last[coset], Q, cu);
+    for (int i = tid; i < R * T; i += nt) {
+        int r = i / T, c = i % T;
+        x[i] = gl::canon(in[(size_t)r * inner + c]);
+    }
+    __syncthreads();
+    for (int i = tid + 1; i < R; i += nt) {
+        int u = 31 - __clz(i);
+        tw[i] = gl::mul(cu[u], __ldg(a.brs + (i - (1 << u))));
+    }
+    __syncthreads();
+
+    const int nb = (R / 2) * T;
+    if (!GS) {
+        for (int u = 0; u < l; ++u) {
+            const int hs = l - 1 - u, half = 1 << hs;
+            for (int b = tid; b < nb; b += nt) {
+                int c = b % T, bb = b / T;
+                int q = bb >> hs, j = bb & (half - 1);
+                int i0 = ((q << (hs + 1)) + j) * T + c, i1 = i0 + half * T;
+                uint64_t v = gl::mul(x[i1], tw[(1 << u) + q]);
+                uint64_t w = x[i0];
+                x[i0] = gl::add(w, v);
+                x[i1] = gl::sub(w, v);
+            }
+            __syncthreads();
+        }
+    } else {
+        for (int u = l - 1; u >= 0; --u) {
+            const int hs = l - 1 - u, half = 1 << hs;
+            for (int b = tid; b < nb; b += nt) {
+                int c = b % T, bb = b / T;
+                int q = bb >> hs, j = bb & (half - 1);
+                int i0 = ((q << (hs + 1)) + j) * T + c, i1 = i0 + half * T;
+                uint64_t A = x[i0], B = x[i1];
+                x[i0] = gl::add(A, B);
+                x[i1] = gl::mul(gl::sub(A, B), tw[(1 << u) + q]);
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < R * T; i += nt) {
+        int r = i / T, c = i % T;
+        uint64_t v = x[i];
+        if (a.apply_scale) v = gl::mul(v, a.scale);
+        out[(size_t)r * inner + c] = v;
+    }
+}
+
+// ---- contiguous pass: G sub-blocks of 2^l consecutive elements (M == l) --------------------------
+template <bool GS>
+__global__ void __launch_bounds__(1024) pass_contig(const PassArgs a) {
+    extern __shared__ uint64_t sm[];
+    const int l = a.l, R = 1 << l, G = a.G;
+    uint64_t* tw = sm;                 // [G][R]
+    uint64_t* x = sm + (size_t)G * R;  // [G][R]
+    uint64_t* cu = x + (size_t)G * R;  // [G][16]
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t coset = blockIdx.z;
+    const int t = a.L - a.M;
+    const uint32_t k0 = blockIdx.x * G;  // first sub-block (or first natural row index when bitrev_store)
+    const uint64_t* in = a.src + blockIdx.y * a.src_col_stride + coset * a.src_coset_stride;
+    uint64_t* out = a.dst + blockIdx.y * a.dst_col_stride + coset * a.dst_coset_stride;
+
+    auto subblock = [&](int g) -> uint32_t { return a.bitrev_store ? gl::bitrev32(k0 + g, t) : (k0 + g); };
+
+    if (tid < G) row_constants(a, a.s_last[coset], subblock(tid), cu + tid * 16);
+    for (int i = tid; i < G * R; i += nt) {
+        int g = i >> l, r = i & (R - 1);
+        x[i] = gl::canon(in[((size_t)subblock(g) << l) + r]);
+    }
+    __syncthreads();
+    for (int i = tid; i < G * R; i += nt) {
+        int g = i >> l, k = i & (R - 1);
+        if (k) {
+            int u = 31 - __clz(k);
+            tw[i] = gl::mul(cu[g * 16 + u], __ldg(a.brs + (k - (1 << u))));
+        }
+    }
+    __syncthreads();
+
+    const int nb = G * (R / 2);
+    if (!GS) {
+        for (int u = 0; u < l; ++u) {
+            const int hs = l - 1 - u, half = 1 << hs;
+            for (int b = tid; b < nb; b += nt) {
+                int g = b >> (l - 1), bb = b & (R / 2 - 1);
+                int q = bb >> hs, j = bb & (half - 1);
+                int i0 = (g << l) + (q << (hs + 1)) + j, i1 = i0 + half;
+                uint64_t v = gl::mul(x[i1], tw[(g << l) + (1 << u) + q]);
+                uint64_t w = x[i0];
+                x[i0] = gl::add(w, v);
+                x[i1] = gl::sub(w, v);
+            }
+            __syncthreads();
+        }
+    } else {
+        for (int u = l - 1; u >= 0; --u) {
+            const int hs = l - 1 - u, half = 1 << hs;
+            for (int b = tid; b < nb; b += nt) {
+                int g = b >> (l - 1), bb = b & (R / 2 - 1);
+                int q = bb >> hs, j = bb & (half - 1);
+                int i0 = (g << l) + (q << (hs + 1)) + j, i1 = i0 + half;
+                uint64_t A = x[i0], B = x[i1];
+                x[i0] = gl::add(A, B);
+                x[i1] = gl::mul(gl::sub(A, B), tw[(g << l) + (1 << u) + q]);
+            }
+            __syncthreads();
+        }
+    }
+    if (!a.bitrev_store) {
+        for (int i = tid; i < G * R; i += nt) {
+            int g = i >> l, r = i & (R - 1);
+            uint64_t v = x[i];
+            if (a.apply_scale) v = gl::mul(v, a.scale);
+            out[((size_t)(k0 + g) << l) + r] = v;
+        }
+    } else {
+        // in-place position p = Q*R + r holds the value of natural index bitrev_L(p) = bitrev_l(r)*2^t + bitrev_t(Q)
+        // = kk*2^t + (k0+g).  Consecutive g -> consecutive addresses (G*8-byte segments).
+        // With cosets interleaved (natural-order LDE): address = (kk*2^t + k0+g)*out_mul + bitrev(coset).
+        out = a.dst + blockIdx.y * a.dst_col_stride;
+        const size_t add = a.coset_bits ? gl::bitrev32(coset, a.coset_bits) : 0;
+        for (int i = tid; i < G * R; i += nt) {
+            int g = i % G, kk = i / G;
+            int r = gl::bitrev32((uint32_t)kk, l);
+            uint64_t v = x[(g << l) + r];
+            if (a.apply_scale) v = gl::mul(v, a.scale);
+            out[(((size_t)kk << t) + k0 + g) * a.out_mul + add] = v;
+        }
+    }
+}
+
+// out[j] *= base * step^j   (coset un-shift after a natural-order inverse transform)
+__global__ void scale_powers_kernel(uint64_t* data, size_t col_stride, size_t n, uint64_t base, uint64_t step) {
+    const int RUN = 16;
+    size_t j0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * RUN;
+    if (j0 >= n) return;
+    uint64_t* p = data + blockIdx.y * col_stride;
+    uint64_t f = gl::mul(base, gl::pow(step, j0));
+    for (int k = 0; k < RUN && j0 + k < n; ++k) {
+        p[j0 + k] = gl::mul(gl::canon(p[j0 + k]), f);
+        f = gl::mul(f, step);
+    }
+}
+
+__global__ void build_tables_kernel(uint64_t* pw, uint64_t* brs, uint64_t omega /* omega_{2^32} or inverse */,
+                                    uint64_t w12 /* omega_{2^12} or inverse */) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2048) pw[i] = gl::pow(omega, (uint64_t)i);
+    if (i < 2048) pw[2048 + i] = gl::pow(omega, (uint64_t)i << 11);
+    if (i < 1024) pw[4096 + i] = gl::pow(omega, (uint64_t)i << 22);
+    // BRS[i] = omega_{2^(k+1)}^{bitrev_k(i)} with k = 11: omega_{2^12}^{bitrev_11(i)}  (prefix property)
+    if (i < 2048) brs[i] = gl::pow(w12, (uint64_t)gl::bitrev32((uint32_t)i, 11));
+}
+
+// ---------------------------------------------------------------------------------------------------
+void init_twiddles(ola_ctx* ctx) {
+    for (int d = 0; d < 2; ++d) {
+        OLA_CUDA(cudaMalloc(&ctx->tw.pw[d], 5120 * sizeof(uint64_t)));
+        OLA_CUDA(cudaMalloc(&ctx->tw.brs[d], 2048 * sizeof(uint64_t)));
+        uint64_t omega = gl::TWO_ADIC_GEN, w12 = gl::root_of_unity(12);
+        if (d == 1) {
+            omega = gl::inv(omega);
+            w12 = gl::inv(w12);
+        }
+        build_tables_kernel<<<8, 256, 0, ctx->stream>>>(ctx->tw.pw[d], ctx->tw.brs[d], omega, w12);
+        check_launch("build_tables_kernel");
+        count_launch(ctx);
+    }
+}
+void free_twiddles(ola_ctx* ctx) {
+    for (int d = 0; d < 2; ++d) {
+        if (ctx->tw.pw[d]) cudaFree(ctx->tw.pw[d]);
+        if (ctx->tw.brs[d]) cudaFree(ctx->tw.brs[d]);
+        ctx->tw.pw[d] = ctx->tw.brs[d] = nullptr;
+    }
+}
+
+std::vector<int> plan_passes(int L) {
+    std::vector<int> p;
+    if (L <= MAX_PASS_LOG) {
+        p.push_back(L);
+        return p;
+    }
+    int k = (L + MAX_PASS_LOG - 1) / MAX_PASS_LOG;
+    int base = L / k, rem = L % k;
+    for (int i = 0; i < k; ++i) p.push_back(base + (i < rem ? 1 : 0));
+    return p;
+}
+
+static uint64_t pow2k(uint64_t x, int k) {  // x^(2^k)
+    for (int i = 0; i < k; ++i) x = gl::sqr(x);
+    return x;
+}
+
+template <bool GS>
+static void launch_strided(ola_ctx* ctx, const PassArgs& a, size_t ncols, int ncosets) {
+    const int R = 1 << a.l;
+    size_t smem = ((size_t)R + 16 + (size_t)R * TILE_T) * sizeof(uint64_t);
+    OLA_CUDA(cudaFuncSetAttribute(pass_strided<GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    size_t tiles = ((size_t)1 << a.L) / ((size_t)R * TILE_T);
+    int threads = (int)std::min<size_t>(1024, std::max<size_t>(64, (size_t)R * TILE_T / 4));
+    dim3 grid((unsigned)tiles, (unsigned)ncols, (unsigned)ncosets);
+    pass_strided<GS><<<grid, threads, smem, ctx->stream>>>(a);
+    check_launch("pass_strided");
+    count_launch(ctx);
+}
+
+template <bool GS>
+static void launch_contig(ola_ctx* ctx, const PassArgs& a, size_t ncols, int ncosets) {
+    const int R = 1 << a.l;
+    size_t smem = ((size_t)2 * a.G * R + (size_t)a.G * 16) * sizeof(uint64_t);
+    OLA_CUDA(cudaFuncSetAttribute(pass_contig<GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    size_t blocks = (((size_t)1 << a.L) >> a.l) / a.G;
+    int threads = (int)std::min<size_t>(1024, std::max<size_t>(32, (size_t)R * a.G / 4));
+    dim3 grid((unsigned)blocks, (unsigned)ncols, (unsigned)ncosets);
+    pass_contig<GS><<<grid, threads, smem, ctx->stream>>>(a);
+    check_launch("pass_contig");
+    count_launch(ctx);
+}
+
+// Forward network (natural-order input -> bit-reversed positions, or natural order if bitrev_store).
+void forward(ola_ctx* ctx, const FwdDesc& d) {
+    OLA_CHECK(d.log_n <= 32 - d.coset_bits, OLA_ERR_INVALID_ARG, "NTT size exceeds the field's two-adicity (2^32)");
+    OLA_CHECK((1 << d.coset_bits) <= MAX_COSETS, OLA_ERR_INVALID_ARG, "too many cosets");
+    if (d.ncols == 0) return;
+    const int L = d.log_n, ncosets = 1 << d.coset_bits;
+    const int dir = d.inverse_roots ? 1 : 0;
+    // coset i evaluates on shift * g^{bitrev(i)} * H_n, g = omega_{n * ncosets}  (cfft/serial.rs:36-38)
+    uint64_t g = gl::root_of_unity(L + d.coset_bits);
+    if (d.inverse_roots) g = gl::inv(g);
+    uint64_t shifts[MAX_COSETS];
+    for (int i = 0; i < ncosets; ++i) shifts[i] = gl::mul(d.shift, gl::pow(g, gl::bitrev32((uint32_t)i, d.coset_bits)));
+
+    std::vector<int> plan = plan_passes(L);
+    int M = L;
+    for (size_t pi = 0; pi < plan.size(); ++pi) {
+        PassArgs a{};
+        const bool first = (pi == 0), last = (pi + 1 == plan.size());
+        uint64_t* work = d.work ? d.work : d.dst;
+        OLA_CHECK(!(d.natural_output && plan.size() > 1 && work == d.dst), OLA_ERR_INTERNAL,
+                  "natural-order output of a multi-pass transform needs a work buffer distinct from dst");
+        // first pass reads src; intermediate passes run in `work`; the last pass writes dst
+        a.src = first ? d.src : work;
+        a.dst = last ? d.dst : work;
+        const size_t work_col = d.work ? d.work_col_stride : d.dst_col_stride;
+        const size_t work_coset = d.work ? d.work_coset_stride : d.dst_coset_stride;
+        a.src_col_stride = first ? d.src_col_stride : work_col;
+        a.dst_col_stride = last ? d.dst_col_stride : work_col;
+        a.src_coset_stride = first ? 0 : work_coset;
+        a.dst_coset_stride = last ? d.dst_coset_stride : work_coset;
+        a.pw = ctx->tw.pw[dir];
+        a.brs = ctx->tw.brs[dir];
+        a.L = L;
+        a.M = M;
+        a.l = plan[pi];
+        a.apply_scale = (last && d.apply_scale) ? 1 : 0;
+        a.scale = d.scale;
+        a.coset_bits = 0;
+        a.out_mul = 1;
+        for (int i = 0; i < ncosets; ++i) a.s_last[i] = pow2k(shifts[i], M - a.l);
+        if (!last) {
+            launch_strided<false>(ctx, a, d.ncols, ncosets);
+        } else {
+            const int t = L - M;
+            int gmax = (a.l <= 10) ? 8 : 4;
+            a.G = (int)std::min<size_t>((size_t)gmax, (size_t)1 << t);
+            a.bitrev_store = d.natural_output ? 1 : 0;
+            if (d.natural_output) {
+                a.coset_bits = d.coset_bits;
+                a.out_mul = (size_t)ncosets;
+            }
+            launch_contig<false>(ctx, a, d.ncols, ncosets);
+        }
+        M -= a.l;
+    }
+}
+
+// Inverse network: bit-reversed positions on the coset shift*H (leaf order) -> natural coefficients, x 1/n.
+void inverse_from_leaf_order(ola_ctx* ctx, uint64_t* data, size_t col_stride, size_t ncols, int log_n, uint64_t shift) {
+    OLA_CHECK(log_n <= 32, OLA_ERR_INVALID_ARG, "NTT size exceeds the field's two-adicity (2^32)");
+    if (ncols == 0) return;
+    const int L = log_n;
+    std::vector<int> plan = plan_passes(L);
+    const uint64_t shift_inv = gl::inv(shift);
+    const uint64_t n_inv = gl::inv(((uint64_t)1 << L) % gl::P);
+    // undo passes in reverse order: the last forward pass (contiguous) first
+    std::vector<int> Ms(plan.size());
+    int M = L;
+    for (size_t pi = 0; pi < plan.size(); ++pi) {
+        Ms[pi] = M;
+        M -= plan[pi];
+    }
+    for (size_t k = plan.size(); k-- > 0;) {
+        PassArgs a{};
+        a.src = data;
+        a.dst = data;
+        a.src_col_stride = a.dst_col_stride = col_stride;
+        a.pw = ctx->tw.pw[1];
+        a.brs = ctx->tw.brs[1];
+        a.L = L;
+        a.M = Ms[k];
+        a.l = plan[k];
+        a.apply_scale = (k == 0) ? 1 : 0;
+        a.scale = n_inv;
+        a.out_mul = 1;
+        a.s_last[0] = pow2k(shift_inv, a.M - a.l);
+        if (k + 1 == plan.size()) {
+            const int t = L - a.M;
+            int gmax = (a.l <= 10) ? 8 : 4;
+            a.G = (int)std::min<size_t>((size_t)gmax, (size_t)1 << t);
+            launch_contig<true>(ctx, a, ncols, 1);
+        } else {
+            launch_strided<true>(ctx, a, ncols, 1);
+        }
+    }
+}
+
+void scale_powers(ola_ctx* ctx, uint64_t* data, size_t col_stride, size_t ncols, size_t n, uint64_t base, uint64_t step) {
+    if (ncols == 0 || n == 0) return;
+    size_t runs = (n + 15) / 16;
+    dim3 grid((unsigned)((runs + 127) / 128), (unsigned)ncols);
+    scale_powers_kernel<<<grid, 128, 0, ctx->stream>>>(data, col_stride, n, base, step);
+    check_launch("scale_powers_kernel");
+    count_launch(ctx);
+}
+
+}  // namespace ntt
+}  // namespace ola

@@ -1,0 +1,146 @@
+// Poseidon kernels: batched permutation, leaf sponge over row tiles, Merkle level reduction.
+//
+// Replaces:
+//   plonky2/plonky2/src/hash/merkle_tree/mod.rs   new_v2 leaf loop :186-201 (hash_no_pad per row),
+//       build_merkle_nodes :311-337 / merkle_tree/concurrent.rs:14-66 (2-to-1 compression per level)
+//   plonky2/plonky2/src/hash/hashing.rs           hash_n_to_m_no_pad :84-106, compress :66-74
+//
+// Leaf hashing reads the LDE COLUMN-major: thread r reads element r of every column, so each warp
+// load is one fully coalesced 256-byte segment and no transpose of the LDE matrix (fri/oracle.rs:84)
+// is ever materialised.  One thread = one sponge; the permutation is ALU-bound (~500 modular
+// multiplications, 64 B of fresh input), so the roofline of these kernels is the integer pipe, not HBM.
+#include "common.h"
+#include "poseidon.cuh"
+
+namespace ola {
+namespace poseidon {
+
+void init_constants() {
+    // canonicalise on upload: add_canonical_u64 (poseidon.rs:482-484) assumes canonical constants
+    auto up = [](const void* sym, const uint64_t* src, size_t n) {
+        std::vector<uint64_t> t(n);
+        for (size_t i = 0; i < n; ++i) t[i] = gl::canon(src[i]);
+        OLA_CUDA(cudaMemcpyToSymbol(sym, t.data(), n * sizeof(uint64_t)));
+    };
+    up(c_round, OLA_ALL_ROUND_CONSTANTS, 360);
+    up(c_first, OLA_FAST_PARTIAL_FIRST_ROUND_CONSTANT, 12);
+    up(c_partial, OLA_FAST_PARTIAL_ROUND_CONSTANTS, 22);
+    up(c_vs, &OLA_FAST_PARTIAL_ROUND_VS[0][0], 22 * 11);
+    up(c_whats, &OLA_FAST_PARTIAL_ROUND_W_HATS[0][0], 22 * 11);
+    up(c_init, &OLA_FAST_PARTIAL_ROUND_INITIAL_MATRIX[0][0], 11 * 11);
+}
+
+__global__ void __launch_bounds__(128) permute_kernel(uint64_t* states, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t s[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) s[k] = gl::canon(states[i * 12 + k]);
+    permute(s);
+#pragma unroll
+    for (int k = 0; k < 12; ++k) states[i * 12 + k] = s[k];
+}
+
+// hash_no_pad over one row; ROWMAJOR: element (r, c) at base[r*ncols + c]; else at base[c*col_stride + r]
+template <bool ROWMAJOR>
+__global__ void __launch_bounds__(128) hash_rows_kernel(const uint64_t* __restrict__ base, size_t col_stride, size_t nrows,
+                                                       size_t ncols, uint64_t* __restrict__ digests) {
+    size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    uint64_t s[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) s[k] = 0;
+    for (size_t c0 = 0; c0 < ncols; c0 += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (c0 + k < ncols) {
+                uint64_t v = ROWMAJOR ? base[r * ncols + c0 + k] : base[(c0 + k) * col_stride + r];
+                s[k] = gl::canon(v);
+            }
+        }
+        permute(s);
+    }
+    ulonglong2* d = reinterpret_cast<ulonglong2*>(digests + 4 * r);
+    d[0] = make_ulonglong2(s[0], s[1]);
+    d[1] = make_ulonglong2(s[2], s[3]);
+}
+
+// nodes[i] = two_to_one(nodes[2i], nodes[2i+1]) for i in [first, first + count)
+__global__ void __launch_bounds__(128) merkle_level_kernel(uint64_t* nodes, size_t first, size_t count) {
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    size_t i = first + k;
+    const ulonglong2* ch = reinterpret_cast<const ulonglong2*>(nodes + 8 * i);
+    ulonglong2 a = ch[0], b = ch[1], c = ch[2], d = ch[3];
+    uint64_t s[12] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y, 0, 0, 0, 0};
+    permute(s);
+    ulonglong2* o = reinterpret_cast<ulonglong2*>(nodes + 4 * i);
+    o[0] = make_ulonglong2(s[0], s[1]);
+    o[1] = make_ulonglong2(s[2], s[3]);
+}
+
+void permute_states(ola_ctx* ctx, uint64_t* d_states, size_t n) {
+    if (!n) return;
+    permute_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(d_states, n);
+    check_launch("permute_kernel");
+    count_launch(ctx);
+}
+void hash_rows_rowmajor(ola_ctx* ctx, const uint64_t* d_rows, size_t nrows, size_t ncols, uint64_t* d_digests) {
+    if (!nrows) return;
+    hash_rows_kernel<true><<<(unsigned)((nrows + 127) / 128), 128, 0, ctx->stream>>>(d_rows, 0, nrows, ncols, d_digests);
+    check_launch("hash_rows_kernel<row>");
+    count_launch(ctx);
+}
+void hash_rows_colmajor(ola_ctx* ctx, const uint64_t* d_cols, size_t col_stride, size_t nrows, size_t ncols,
+                        uint64_t* d_digests) {
+    if (!nrows) return;
+    hash_rows_kernel<false>
+        <<<(unsigned)((nrows + 127) / 128), 128, 0, ctx->stream>>>(d_cols, col_stride, nrows, ncols, d_digests);
+    check_launch("hash_rows_kernel<col>");
+    count_launch(ctx);
+}
+void merkle_levels(ola_ctx* ctx, uint64_t* d_nodes, size_t nleaves, size_t stop) {
+    if (stop < 1) stop = 1;
+    for (size_t first = nleaves / 2; first >= stop && first >= 1; first /= 2) {
+        merkle_level_kernel<<<(unsigned)((first + 127) / 128), 128, 0, ctx->stream>>>(d_nodes, first, first);
+        check_launch("merkle_level_kernel");
+        count_launch(ctx);
+        if (first == 1) break;
+    }
+}
+
+// ---- host permutation for the Fiat-Shamir transcript (iop/challenger.rs:137-152 duplexing) ----
+static uint64_t h_sbox(uint64_t x) {
+    uint64_t x2 = gl::sqr(x), x4 = gl::sqr(x2), x3 = gl::mul(x, x2);
+    return gl::mul(x3, x4);
+}
+static void h_mds(uint64_t* s) {
+    uint64_t o[12];
+    for (int r = 0; r < 12; ++r) {
+        unsigned __int128 acc = 0;
+        for (int i = 0; i < 12; ++i) acc += (unsigned __int128)s[(i + r) % 12] * OLA_MDS_MATRIX_CIRC[i];
+        acc += (unsigned __int128)s[r] * OLA_MDS_MATRIX_DIAG[r];
+        o[r] = gl::reduce128((uint64_t)acc, (uint64_t)(acc >> 64));
+    }
+    for (int r = 0; r < 12; ++r) s[r] = o[r];
+}
+void permute_host(uint64_t s[12]) {
+    for (int i = 0; i < 12; ++i) s[i] = gl::canon(s[i]);
+    int rc = 0;
+    auto full = [&]() {
+        for (int r = 0; r < 4; ++r, ++rc) {
+            for (int i = 0; i < 12; ++i) s[i] = h_sbox(gl::add(s[i], gl::canon(OLA_ALL_ROUND_CONSTANTS[rc * 12 + i])));
+            h_mds(s);
+        }
+    };
+    full();
+    for (int r = 0; r < 22; ++r, ++rc) {  // host path: naive partial rounds (poseidon.rs:607-617), same function
+        for (int i = 0; i < 12; ++i) s[i] = gl::add(s[i], gl::canon(OLA_ALL_ROUND_CONSTANTS[rc * 12 + i]));
+        s[0] = h_sbox(s[0]);
+        h_mds(s);
+    }
+    full();
+}
+
+}  // namespace poseidon
+}  // namespace ola

@@ -1,0 +1,156 @@
+// Poseidon-Goldilocks permutation (width 12, x^7, 4 + 22 + 4 rounds) as a device function.
+//
+// Replaces plonky2/plonky2/src/hash/poseidon.rs:593-604 (`Poseidon::poseidon`: full_rounds :566-574,
+// partial_rounds :577-590 with the "fast" partial-round decomposition :303-421) and the modes built on
+// it in hashing.rs (:66-74 compress, :84-108 overwrite-mode sponge, rate 8).
+//
+// One thread owns one 12-word state in registers; all round constants come from __constant__ memory
+// (every lane of a warp reads the same word in the same cycle -> broadcast).  The MDS layer exploits
+// the small circulant coefficients (<= 41): it accumulates 32-bit halves in 64-bit registers and reduces
+// once per output, as the reference does with u128 (poseidon.rs:168-189, :236-257).  The dense
+// partial-round dot products accumulate 64x64-bit products in a 160-bit register triple and reduce
+// once (poseidon.rs:392-409).  Integer pipes only; there is no tensor-core formulation of x^7 S-boxes.
+#pragma once
+#include "gl.cuh"
+#include "poseidon_constants.h"
+
+namespace ola {
+namespace poseidon {
+
+#ifdef __CUDACC__
+// device copies of the parameter tables (libola_gpu is a single translation unit; filled by init_constants)
+static __constant__ uint64_t c_round[360];
+static __constant__ uint64_t c_first[12];
+static __constant__ uint64_t c_partial[22];
+static __constant__ uint64_t c_vs[22 * 11];
+static __constant__ uint64_t c_whats[22 * 11];
+static __constant__ uint64_t c_init[11 * 11];
+
+// 160-bit accumulator for sums of 64x64 products
+struct acc160 {
+    uint64_t lo, hi;
+    uint32_t top;
+};
+__device__ __forceinline__ void acc_zero(acc160& a) {
+    a.lo = 0;
+    a.hi = 0;
+    a.top = 0;
+}
+__device__ __forceinline__ void acc_mac(acc160& a, uint64_t x, uint64_t y) {
+    uint64_t pl, ph;
+    gl::mul_wide(x, y, pl, ph);
+    uint64_t lo = a.lo + pl;
+    uint64_t c0 = lo < pl;
+    uint64_t hi = a.hi + ph;
+    uint32_t c1 = hi < ph;
+    uint64_t hi2 = hi + c0;
+    c1 += (hi2 < hi);
+    a.lo = lo;
+    a.hi = hi2;
+    a.top += c1;
+}
+// value = lo + hi*2^64 + top*2^128,  2^128 = -2^32 (mod p)
+__device__ __forceinline__ uint64_t acc_reduce(const acc160& a) {
+    uint64_t r = gl::reduce128(a.lo, a.hi);
+    return gl::sub(r, (uint64_t)a.top << 32);
+}
+
+__device__ __forceinline__ uint64_t sbox7(uint64_t x) {
+    uint64_t x2 = gl::sqr(x), x4 = gl::sqr(x2), x3 = gl::mul(x, x2);
+    return gl::mul(x3, x4);
+}
+
+// out[r] = sum_i s[(i+r)%12] * CIRC[i] + s[r]*DIAG[r]   (CIRC = 17,15,41,16,2,28,13,13,39,18,34,20; DIAG[0] = 8)
+__device__ __forceinline__ void mds_layer(uint64_t* s) {
+    constexpr uint32_t C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+    uint32_t lo[12], hi[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        lo[i] = (uint32_t)s[i];
+        hi[i] = (uint32_t)(s[i] >> 32);
+    }
+#pragma unroll
+    for (int r = 0; r < 12; ++r) {
+        uint64_t al = 0, ah = 0;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            al += (uint64_t)lo[(i + r) % 12] * C[i];
+            ah += (uint64_t)hi[(i + r) % 12] * C[i];
+        }
+        if (r == 0) {
+            al += (uint64_t)lo[0] * 8u;
+            ah += (uint64_t)hi[0] * 8u;
+        }
+        // value = al + ah * 2^32  (al, ah < 2^42)
+        uint64_t l128 = al + (ah << 32);
+        uint64_t h128 = (ah >> 32) + (l128 < al);
+        s[r] = gl::reduce128(l128, h128);
+    }
+}
+
+__device__ __forceinline__ void full_round(uint64_t* s, int round_ctr) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) s[i] = sbox7(gl::add(s[i], c_round[round_ctr * 12 + i]));
+    mds_layer(s);
+}
+
+__device__ __forceinline__ void permute(uint64_t* s) {
+#pragma unroll 1
+    for (int r = 0; r < 4; ++r) full_round(s, r);
+
+    // partial_first_constant_layer + mds_partial_layer_init (poseidon.rs:303-313, :332-358)
+#pragma unroll
+    for (int i = 0; i < 12; ++i) s[i] = gl::add(s[i], c_first[i]);
+    {
+        acc160 acc[11];
+#pragma unroll
+        for (int c = 0; c < 11; ++c) acc_zero(acc[c]);
+#pragma unroll
+        for (int r = 1; r < 12; ++r) {
+#pragma unroll
+            for (int c = 0; c < 11; ++c) acc_mac(acc[c], s[r], c_init[(r - 1) * 11 + c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 11; ++c) s[c + 1] = acc_reduce(acc[c]);
+    }
+    // 22 partial rounds (poseidon.rs:582-588, mds_partial_layer_fast :392-421)
+#pragma unroll 1
+    for (int r = 0; r < 22; ++r) {
+        s[0] = gl::add(sbox7(s[0]), c_partial[r]);
+        acc160 d;
+        acc_zero(d);
+        acc_mac(d, s[0], 25);  // MDS_MATRIX_CIRC[0] + MDS_MATRIX_DIAG[0]
+#pragma unroll
+        for (int i = 1; i < 12; ++i) acc_mac(d, s[i], c_whats[r * 11 + i - 1]);
+        uint64_t s0 = s[0];
+#pragma unroll
+        for (int i = 1; i < 12; ++i) s[i] = gl::add(s[i], gl::mul(s0, c_vs[r * 11 + i - 1]));
+        s[0] = acc_reduce(d);
+    }
+#pragma unroll 1
+    for (int r = 0; r < 4; ++r) full_round(s, 26 + r);
+}
+#endif  // __CUDACC__
+
+// ---- host launchers (poseidon.cu) ----
+}  // namespace poseidon
+}  // namespace ola
+
+struct ola_ctx;
+namespace ola {
+namespace poseidon {
+void init_constants();
+// states [n][12] in place
+void permute_states(ola_ctx* ctx, uint64_t* d_states, size_t n);
+// row-major leaves [nrows][ncols] -> digests [nrows][4]
+void hash_rows_rowmajor(ola_ctx* ctx, const uint64_t* d_rows, size_t nrows, size_t ncols, uint64_t* d_digests);
+// column-major leaves: element (row r, column c) at d_cols[c*col_stride + r]; digests [nrows][4]
+void hash_rows_colmajor(ola_ctx* ctx, const uint64_t* d_cols, size_t col_stride, size_t nrows, size_t ncols,
+                        uint64_t* d_digests);
+// heap-ordered tree: d_nodes is [2*nleaves][4] with the leaf digests already at [nleaves, 2*nleaves);
+// fills nodes [stop, nleaves) level by level (stop >= 1; stop = 2^cap_height fills down to the cap level)
+void merkle_levels(ola_ctx* ctx, uint64_t* d_nodes, size_t nleaves, size_t stop);
+// host-side permutation (transcript / challenger only)
+void permute_host(uint64_t state[12]);
+}  // namespace poseidon
+}  // namespace ola

@@ -55,11 +55,23 @@ uint64_t ola_gpu_kernel_launches(const ola_ctx* ctx);
 /* the cudaStream_t every kernel of this context is launched on (for CUDA-event timing by the caller) */
 void* ola_gpu_stream(ola_ctx* ctx);
 
+/* Per-kernel CUDA-event tracing on the context's stream (device analogue of the reference's TimingTree,
+ * plonky2/plonky2/src/util/timing.rs).  begin: start recording an event pair around every launch;
+ * end: synchronise, stop recording and write {"kernel": {"ms": total, "launches": n}, ...} as JSON text. */
+int ola_profile_begin(ola_ctx* ctx);
+int ola_profile_end(ola_ctx* ctx, char* json_out, size_t cap);
+
 /* ---- raw device buffers (u64 elements), for callers that keep data resident between calls ---- */
 int ola_dev_alloc(ola_ctx* ctx, size_t n_u64, uint64_t** dptr);
 int ola_dev_free(ola_ctx* ctx, uint64_t* dptr);
 int ola_dev_upload(ola_ctx* ctx, uint64_t* dst_dev, const uint64_t* src_host, size_t n_u64);
 int ola_dev_download(ola_ctx* ctx, uint64_t* dst_host, const uint64_t* src_dev, size_t n_u64);
+int ola_dev_copy(ola_ctx* ctx, uint64_t* dst_dev, const uint64_t* src_dev, size_t n_u64); /* device -> device, async */
+/* rows [first_row, first_row+count) of a COLUMN-major device matrix (element (r,c) at cols_dev[c*col_stride + r])
+ * -> host, row-major [count][ncols].  This is how opened leaves leave the GPU (MerkleTree::get,
+ * merkle_tree/mod.rs:268; fri_prover_query_round, fri/prover.rs:179-181). */
+int ola_dev_gather_rows(ola_ctx* ctx, const uint64_t* cols_dev, size_t col_stride, size_t ncols, size_t first_row,
+                        size_t count, uint64_t* out_host);
 
 /* ---- Goldilocks NTT family.  `on_device` != 0: pointers are device pointers (resident path);
  * == 0: host pointers, the call stages H2D/D2H itself (the reference-facing path).

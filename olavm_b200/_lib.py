@@ -46,10 +46,14 @@ SIGNATURES = {
     "ola_gpu_sync": (_int, [_vp]),
     "ola_gpu_kernel_launches": (_u64, [_vp]),
     "ola_gpu_stream": (_vp, [_vp]),
+    "ola_profile_begin": (_int, [_vp]),
+    "ola_profile_end": (_int, [_vp, ctypes.c_char_p, _sz]),
     "ola_dev_alloc": (_int, [_vp, _sz, ctypes.POINTER(_vp)]),
     "ola_dev_free": (_int, [_vp, _vp]),
     "ola_dev_upload": (_int, [_vp, _vp, _vp, _sz]),
     "ola_dev_download": (_int, [_vp, _vp, _vp, _sz]),
+    "ola_dev_copy": (_int, [_vp, _vp, _vp, _sz]),
+    "ola_dev_gather_rows": (_int, [_vp, _vp, _sz, _sz, _sz, _sz, _vp]),
     "ola_ntt_forward": (_int, [_vp, _vp, _int, _sz, _u32]),
     "ola_ntt_inverse": (_int, [_vp, _vp, _int, _sz, _u32]),
     "ola_coset_lde": (_int, [_vp, _vp, _vp, _int, _sz, _u32, _u32, _u64, _int]),

@@ -35,6 +35,17 @@ class Context:
     def stream_ptr(self):
         return int(self._lib.ola_gpu_stream(self.handle) or 0)
 
+    def profile_begin(self):
+        self.check(self._lib.ola_profile_begin(self.handle))
+
+    def profile_end(self):
+        """-> {kernel name: {"ms": total device time, "launches": n}} since profile_begin()."""
+        import json
+
+        buf = ctypes.create_string_buffer(1 << 16)
+        self.check(self._lib.ola_profile_end(self.handle, buf, len(buf)))
+        return json.loads(buf.value.decode())
+
     def close(self):
         if getattr(self, "handle", None):
             self._lib.ola_gpu_destroy(self.handle)

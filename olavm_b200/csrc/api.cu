@@ -57,12 +57,10 @@ void to_host(ola_ctx* ctx, uint64_t* dst, const uint64_t* src, size_t n) {
 void ntt_natural(ola_ctx* ctx, uint64_t* d_data, size_t ncols, uint32_t log_n, bool inverse) {
     const size_t n = (size_t)1 << log_n;
     const bool multipass = ola::ntt::plan_passes((int)log_n).size() > 1;
-    std::unique_ptr<DevBuf> work;
-    if (multipass) work.reset(new DevBuf(ncols * n));
     ola::ntt::FwdDesc d;
     d.src = d_data;
     d.src_col_stride = n;
-    d.work = multipass ? work->p : nullptr;
+    d.work = multipass ? ola::ctx_scratch(ctx, ncols * n) : nullptr;
     d.work_col_stride = n;
     d.dst = d_data;
     d.dst_col_stride = n;
@@ -72,8 +70,9 @@ void ntt_natural(ola_ctx* ctx, uint64_t* d_data, size_t ncols, uint32_t log_n, b
     d.natural_output = true;
     d.apply_scale = inverse;
     d.scale = inverse ? gl::inv(((uint64_t)1 << log_n) % gl::P) : 1;
+    d.tag_strided = inverse ? "intt_strided" : "ntt_strided";
+    d.tag_contig = inverse ? "intt_contig" : "ntt_contig";
     ola::ntt::forward(ctx, d);
-    if (multipass) OLA_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
 }  // namespace
@@ -116,6 +115,7 @@ void ola_gpu_destroy(ola_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     ola::ntt::free_twiddles(ctx);
+    if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -128,6 +128,44 @@ int ola_gpu_sync(ola_ctx* ctx) {
 }
 uint64_t ola_gpu_kernel_launches(const ola_ctx* ctx) { return ctx ? ctx->kernel_launches : 0; }
 void* ola_gpu_stream(ola_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int ola_profile_begin(ola_ctx* ctx) {
+    if (!ctx) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->prof_totals.clear();
+        ctx->profiling = true;
+    });
+}
+int ola_profile_end(ola_ctx* ctx, char* json_out, size_t cap) {
+    if (!ctx || (!json_out && cap)) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->profiling = false;
+        for (auto& r : ctx->prof_pending) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, r.start, r.stop);
+            auto& t = ctx->prof_totals[r.name];
+            t.first += ms;
+            t.second += 1;
+            cudaEventDestroy(r.start);
+            cudaEventDestroy(r.stop);
+        }
+        ctx->prof_pending.clear();
+        std::string js = "{";
+        bool first = true;
+        for (auto& kv : ctx->prof_totals) {
+            char buf[256];
+            snprintf(buf, sizeof buf, "%s\"%s\": {\"ms\": %.6f, \"launches\": %llu}", first ? "" : ", ", kv.first.c_str(),
+                     kv.second.first, (unsigned long long)kv.second.second);
+            js += buf;
+            first = false;
+        }
+        js += "}";
+        OLA_CHECK(js.size() + 1 <= cap, OLA_ERR_INVALID_ARG, "profile buffer too small");
+        memcpy(json_out, js.c_str(), js.size() + 1);
+    });
+}
 
 int ola_dev_alloc(ola_ctx* ctx, size_t n_u64, uint64_t** dptr) {
     if (!ctx || !dptr) return OLA_ERR_INVALID_ARG;
@@ -150,6 +188,16 @@ int ola_dev_upload(ola_ctx* ctx, uint64_t* dst_dev, const uint64_t* src_host, si
 int ola_dev_download(ola_ctx* ctx, uint64_t* dst_host, const uint64_t* src_dev, size_t n_u64) {
     if (!ctx || (!dst_host && n_u64) || (!src_dev && n_u64)) return OLA_ERR_INVALID_ARG;
     return guarded(ctx, [&] { to_host(ctx, dst_host, src_dev, n_u64); });
+}
+
+int ola_dev_copy(ola_ctx* ctx, uint64_t* dst_dev, const uint64_t* src_dev, size_t n_u64) {
+    if (!ctx || (!dst_dev && n_u64) || (!src_dev && n_u64)) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] { OLA_CUDA(cudaMemcpyAsync(dst_dev, src_dev, n_u64 * 8, cudaMemcpyDeviceToDevice, ctx->stream)); });
+}
+int ola_dev_gather_rows(ola_ctx* ctx, const uint64_t* cols_dev, size_t col_stride, size_t ncols, size_t first_row,
+                        size_t count, uint64_t* out_host) {
+    if (!ctx || !cols_dev || (!out_host && count)) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] { ola::gather_rows(ctx, cols_dev, col_stride, ncols, first_row, count, out_host); });
 }
 
 static int ntt_entry(ola_ctx* ctx, uint64_t* data, int on_device, size_t ncols, uint32_t log_n, bool inverse) {
@@ -204,6 +252,8 @@ int ola_coset_lde(ola_ctx* ctx, const uint64_t* coeffs, uint64_t* out, int on_de
         d.coset_bits = (int)rate_bits;
         d.shift = gl::canon(shift);
         d.natural_output = natural_order != 0;
+        d.tag_strided = "lde_strided";
+        d.tag_contig = "lde_contig";
         if (natural_order && ola::ntt::plan_passes((int)log_n).size() > 1) {
             d_work.reset(new DevBuf(ncols * L));
             d.work = d_work->p;

@@ -61,6 +61,32 @@ void dev_alloc(uint64_t** p, size_t n_u64) {
     OLA_CUDA(e);
 }
 
+uint64_t* ctx_scratch(ola_ctx* ctx, size_t n_u64) {
+    if (ctx->scratch_elems < n_u64) {
+        OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->scratch) cudaFree(ctx->scratch);
+        ctx->scratch = nullptr;
+        ctx->scratch_elems = 0;
+        dev_alloc(&ctx->scratch, n_u64);
+        ctx->scratch_elems = n_u64;
+    }
+    return ctx->scratch;
+}
+
+void gather_rows(ola_ctx* ctx, const uint64_t* d_cols, size_t col_stride, size_t ncols, size_t first, size_t count,
+                 uint64_t* out_host) {
+    if (!count || !ncols) return;
+    size_t total = count * ncols;
+    uint64_t* tmp = ctx_scratch(ctx, total);
+    {
+        Launch lz(ctx, "gather_rows");
+        gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(d_cols, col_stride, ncols, first, count, tmp);
+    }
+    check_launch("gather_rows_kernel");
+    OLA_CUDA(cudaMemcpyAsync(out_host, tmp, total * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
 ola_batch* batch_commit(ola_ctx* ctx, const uint64_t* cols, bool on_device, size_t ncols, uint32_t log_n, bool is_coeffs,
                         uint32_t rate_bits, uint32_t cap_height) {
     OLA_CHECK(cols != nullptr && ncols > 0, OLA_ERR_INVALID_ARG, "commit: empty batch");
@@ -119,6 +145,8 @@ ola_batch* batch_commit(ola_ctx* ctx, const uint64_t* cols, bool on_device, size
         d.natural_output = true;
         d.apply_scale = true;
         d.scale = gl::inv(((uint64_t)1 << log_n) % gl::P);
+        d.tag_strided = "intt_strided";
+        d.tag_contig = "intt_contig";
         try {
             ntt::forward(ctx, d);
         } catch (...) {
@@ -142,6 +170,8 @@ ola_batch* batch_commit(ola_ctx* ctx, const uint64_t* cols, bool on_device, size
         d.log_n = (int)log_n;
         d.coset_bits = (int)rate_bits;
         d.shift = gl::GEN;
+        d.tag_strided = "lde_strided";
+        d.tag_contig = "lde_contig";
         ntt::forward(ctx, d);
     }
     // MerkleTree::new_v2: leaf digests then level reduction down to the cap
@@ -169,16 +199,7 @@ void batch_get_cap(ola_ctx* ctx, const ola_batch* b, uint64_t* cap_host) {
 void batch_get_leaves(ola_ctx* ctx, const ola_batch* b, size_t first, size_t count, uint64_t* out_host) {
     const size_t L = (size_t)1 << (b->log_n + b->rate_bits);
     OLA_CHECK(first + count <= L, OLA_ERR_INVALID_ARG, "get_leaves: leaf index out of range");
-    if (!count) return;
-    uint64_t* tmp = nullptr;
-    dev_alloc(&tmp, count * b->ncols);
-    size_t total = count * b->ncols;
-    gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(b->d_lde, L, b->ncols, first, count, tmp);
-    count_launch(ctx);
-    cudaError_t e = cudaMemcpyAsync(out_host, tmp, total * 8, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(tmp);
-    OLA_CUDA(e);
+    gather_rows(ctx, b->d_lde, L, b->ncols, first, count, out_host);
 }
 
 int batch_prove_leaf(ola_ctx* ctx, const ola_batch* b, size_t leaf, uint64_t* sib_host) {

@@ -14,6 +14,10 @@ struct ola_batch {
 
 namespace ola {
 void dev_alloc(uint64_t** p, size_t n_u64);
+// grow-only per-context workspace of at least n_u64 elements (synchronises the stream when it has to grow)
+uint64_t* ctx_scratch(ola_ctx* ctx, size_t n_u64);
+void gather_rows(ola_ctx* ctx, const uint64_t* d_cols, size_t col_stride, size_t ncols, size_t first, size_t count,
+                 uint64_t* out_host);
 ola_batch* batch_commit(ola_ctx* ctx, const uint64_t* cols, bool on_device, size_t ncols, uint32_t log_n, bool is_coeffs,
                         uint32_t rate_bits, uint32_t cap_height);
 void batch_release(ola_batch* b);

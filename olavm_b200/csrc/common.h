@@ -44,16 +44,50 @@ struct Twiddles {
 
 }  // namespace ola
 
+namespace ola {
+// Per-launch CUDA-event tracing (the device-side analogue of the reference's TimingTree,
+// plonky2/plonky2/src/util/timing.rs): off by default, enabled by ola_profile_begin().
+struct ProfRecord {
+    std::string name;
+    cudaEvent_t start, stop;
+};
+}  // namespace ola
+
 struct ola_ctx {
+    bool profiling = false;
+    std::vector<ola::ProfRecord> prof_pending;
+    std::map<std::string, std::pair<double, uint64_t>> prof_totals;  // name -> (ms, launches)
     int device = 0;
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     ola::Twiddles tw;
     std::string last_error;
     uint64_t kernel_launches = 0;  // counted by every launcher (bench.py "gpu_launches")
+    uint64_t* scratch = nullptr;   // grow-only device workspace (multi-pass transform intermediates)
+    size_t scratch_elems = 0;
 };
 
 namespace ola {
+// RAII scope around one kernel launch: counts it, and when profiling brackets it with events on ctx->stream.
+struct Launch {
+    ola_ctx* ctx;
+    cudaEvent_t start = nullptr, stop = nullptr;
+    const char* name;
+    Launch(ola_ctx* c, const char* n) : ctx(c), name(n) {
+        ctx->kernel_launches += 1;
+        if (ctx->profiling) {
+            cudaEventCreate(&start);
+            cudaEventCreate(&stop);
+            cudaEventRecord(start, ctx->stream);
+        }
+    }
+    ~Launch() {
+        if (start) {
+            cudaEventRecord(stop, ctx->stream);
+            ctx->prof_pending.push_back({name, start, stop});
+        }
+    }
+};
 inline void count_launch(ola_ctx* ctx, uint64_t n = 1) { ctx->kernel_launches += n; }
 inline void check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();

@@ -286,29 +286,33 @@ static uint64_t pow2k(uint64_t x, int k) {  // x^(2^k)
 }
 
 template <bool GS>
-static void launch_strided(ola_ctx* ctx, const PassArgs& a, size_t ncols, int ncosets) {
+static void launch_strided(ola_ctx* ctx, const PassArgs& a, size_t ncols, int ncosets, const char* name) {
     const int R = 1 << a.l;
     size_t smem = ((size_t)R + 16 + (size_t)R * TILE_T) * sizeof(uint64_t);
     OLA_CUDA(cudaFuncSetAttribute(pass_strided<GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     size_t tiles = ((size_t)1 << a.L) / ((size_t)R * TILE_T);
     int threads = (int)std::min<size_t>(1024, std::max<size_t>(64, (size_t)R * TILE_T / 4));
     dim3 grid((unsigned)tiles, (unsigned)ncols, (unsigned)ncosets);
-    pass_strided<GS><<<grid, threads, smem, ctx->stream>>>(a);
+    {
+        Launch lz(ctx, name);
+        pass_strided<GS><<<grid, threads, smem, ctx->stream>>>(a);
+    }
     check_launch("pass_strided");
-    count_launch(ctx);
 }
 
 template <bool GS>
-static void launch_contig(ola_ctx* ctx, const PassArgs& a, size_t ncols, int ncosets) {
+static void launch_contig(ola_ctx* ctx, const PassArgs& a, size_t ncols, int ncosets, const char* name) {
     const int R = 1 << a.l;
     size_t smem = ((size_t)2 * a.G * R + (size_t)a.G * 16) * sizeof(uint64_t);
     OLA_CUDA(cudaFuncSetAttribute(pass_contig<GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     size_t blocks = (((size_t)1 << a.L) >> a.l) / a.G;
     int threads = (int)std::min<size_t>(1024, std::max<size_t>(32, (size_t)R * a.G / 4));
     dim3 grid((unsigned)blocks, (unsigned)ncols, (unsigned)ncosets);
-    pass_contig<GS><<<grid, threads, smem, ctx->stream>>>(a);
+    {
+        Launch lz(ctx, name);
+        pass_contig<GS><<<grid, threads, smem, ctx->stream>>>(a);
+    }
     check_launch("pass_contig");
-    count_launch(ctx);
 }
 
 // Forward network (natural-order input -> bit-reversed positions, or natural order if bitrev_store).
@@ -352,7 +356,7 @@ void forward(ola_ctx* ctx, const FwdDesc& d) {
         a.out_mul = 1;
         for (int i = 0; i < ncosets; ++i) a.s_last[i] = pow2k(shifts[i], M - a.l);
         if (!last) {
-            launch_strided<false>(ctx, a, d.ncols, ncosets);
+            launch_strided<false>(ctx, a, d.ncols, ncosets, d.tag_strided);
         } else {
             const int t = L - M;
             int gmax = (a.l <= 10) ? 8 : 4;
@@ -362,7 +366,7 @@ void forward(ola_ctx* ctx, const FwdDesc& d) {
                 a.coset_bits = d.coset_bits;
                 a.out_mul = (size_t)ncosets;
             }
-            launch_contig<false>(ctx, a, d.ncols, ncosets);
+            launch_contig<false>(ctx, a, d.ncols, ncosets, d.tag_contig);
         }
         M -= a.l;
     }
@@ -401,9 +405,9 @@ void inverse_from_leaf_order(ola_ctx* ctx, uint64_t* data, size_t col_stride, si
             const int t = L - a.M;
             int gmax = (a.l <= 10) ? 8 : 4;
             a.G = (int)std::min<size_t>((size_t)gmax, (size_t)1 << t);
-            launch_contig<true>(ctx, a, ncols, 1);
+            launch_contig<true>(ctx, a, ncols, 1, "coset_intt_contig");
         } else {
-            launch_strided<true>(ctx, a, ncols, 1);
+            launch_strided<true>(ctx, a, ncols, 1, "coset_intt_strided");
         }
     }
 }

@@ -30,6 +30,8 @@ struct FwdDesc {
     bool natural_output = false;
     bool apply_scale = false;  // multiply every output by `scale` (1/n for an inverse transform)
     uint64_t scale = 1;
+    const char* tag_strided = "ntt_strided";  // profile names of this transform's launches
+    const char* tag_contig = "ntt_contig";
 };
 
 void init_twiddles(ola_ctx* ctx);

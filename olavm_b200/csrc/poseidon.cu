@@ -81,30 +81,38 @@ __global__ void __launch_bounds__(128) merkle_level_kernel(uint64_t* nodes, size
 
 void permute_states(ola_ctx* ctx, uint64_t* d_states, size_t n) {
     if (!n) return;
-    permute_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(d_states, n);
+    {
+        Launch lz(ctx, "poseidon_permute");
+        permute_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(d_states, n);
+    }
     check_launch("permute_kernel");
-    count_launch(ctx);
 }
 void hash_rows_rowmajor(ola_ctx* ctx, const uint64_t* d_rows, size_t nrows, size_t ncols, uint64_t* d_digests) {
     if (!nrows) return;
-    hash_rows_kernel<true><<<(unsigned)((nrows + 127) / 128), 128, 0, ctx->stream>>>(d_rows, 0, nrows, ncols, d_digests);
+    {
+        Launch lz(ctx, "poseidon_leaves_rowmajor");
+        hash_rows_kernel<true><<<(unsigned)((nrows + 127) / 128), 128, 0, ctx->stream>>>(d_rows, 0, nrows, ncols, d_digests);
+    }
     check_launch("hash_rows_kernel<row>");
-    count_launch(ctx);
 }
 void hash_rows_colmajor(ola_ctx* ctx, const uint64_t* d_cols, size_t col_stride, size_t nrows, size_t ncols,
                         uint64_t* d_digests) {
     if (!nrows) return;
-    hash_rows_kernel<false>
-        <<<(unsigned)((nrows + 127) / 128), 128, 0, ctx->stream>>>(d_cols, col_stride, nrows, ncols, d_digests);
+    {
+        Launch lz(ctx, "poseidon_leaves");
+        hash_rows_kernel<false>
+            <<<(unsigned)((nrows + 127) / 128), 128, 0, ctx->stream>>>(d_cols, col_stride, nrows, ncols, d_digests);
+    }
     check_launch("hash_rows_kernel<col>");
-    count_launch(ctx);
 }
 void merkle_levels(ola_ctx* ctx, uint64_t* d_nodes, size_t nleaves, size_t stop) {
     if (stop < 1) stop = 1;
     for (size_t first = nleaves / 2; first >= stop && first >= 1; first /= 2) {
-        merkle_level_kernel<<<(unsigned)((first + 127) / 128), 128, 0, ctx->stream>>>(d_nodes, first, first);
+        {
+            Launch lz(ctx, "merkle_level");
+            merkle_level_kernel<<<(unsigned)((first + 127) / 128), 128, 0, ctx->stream>>>(d_nodes, first, first);
+        }
         check_launch("merkle_level_kernel");
-        count_launch(ctx);
         if (first == 1) break;
     }
 }

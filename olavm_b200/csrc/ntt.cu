@@ -27,6 +27,8 @@
 #include "gl.cuh"
 #include "ntt.h"
 
+#include <cstdlib>
+
 namespace ola {
 namespace ntt {
 
@@ -222,6 +224,217 @@ __global__ void __launch_bounds__(1024) pass_contig(const PassArgs a) {
     }
 }
 
+// =====================================================================================================
+// Register-blocked passes (l >= 6): every thread owns 8 elements and runs three butterfly stages on them
+// in registers (radix-8 rounds); shared memory is touched once per round instead of once per stage, the
+// first round reads straight from HBM and the last round writes straight back.  Shared-memory indices are
+// padded (one slot per 16) so that the power-of-two strides of every round are bank-conflict-free.
+// Butterfly arithmetic is "lazy": data stays in [0, 2^64), only the twiddle product is canonicalised.
+// =====================================================================================================
+__device__ __forceinline__ int phys(int i) { return i + (i >> 4); }
+
+// three (or 3 - SKIP) stages on 8 elements.  Stage s pairs m with m + (4 >> s); its twiddle is
+// tw[2^(u0+s) + (qh << s) + (m >> (3 - s))]  (u0 = first stage of the round, qh = block index at stage u0).
+template <bool GS, int SKIP>
+__device__ __forceinline__ void bfly8(uint64_t (&x)[8], const uint64_t* __restrict__ tw, int u0, int qh) {
+    if (!GS) {
+#pragma unroll
+        for (int s = SKIP; s < 3; ++s) {
+            const int half = 4 >> s;
+            const uint64_t* t = tw + (1 << (u0 + s)) + (qh << s);
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                if (m & half) continue;
+                uint64_t v = gl::canon_fast(gl::mul_lazy(x[m + half], t[m >> (3 - s)]));
+                uint64_t a = x[m];
+                x[m] = gl::add_lc(a, v);
+                x[m + half] = gl::sub_lc(a, v);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int s = 2; s >= SKIP; --s) {
+            const int half = 4 >> s;
+            const uint64_t* t = tw + (1 << (u0 + s)) + (qh << s);
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                if (m & half) continue;
+                uint64_t b = gl::canon_fast(x[m + half]);
+                uint64_t a = x[m];
+                x[m] = gl::add_lc(a, b);
+                x[m + half] = gl::mul_lazy(gl::sub_lc(a, b), t[m >> (3 - s)]);
+            }
+        }
+    }
+}
+
+template <bool GS>
+__device__ __forceinline__ void bfly8_dispatch(uint64_t (&x)[8], const uint64_t* tw, int u0, int qh, int skip) {
+    if (skip == 0)
+        bfly8<GS, 0>(x, tw, u0, qh);
+    else if (skip == 1)
+        bfly8<GS, 1>(x, tw, u0, qh);
+    else
+        bfly8<GS, 2>(x, tw, u0, qh);
+}
+
+// round schedule: full rounds at u0 = 0, 3, 6, ...; if l % 3 != 0 a final round at u0 = l - 3 that skips the
+// stages already done.  CT runs rounds 0..nr-1, GS runs them backwards.
+struct Rounds {
+    int l, nfull, nr;
+    __device__ Rounds(int l_) : l(l_), nfull(l_ / 3), nr(l_ / 3 + ((l_ % 3) ? 1 : 0)) {}
+    __device__ int u0(int rho) const { return rho < nfull ? 3 * rho : l - 3; }
+    __device__ int skip(int rho) const { return rho < nfull ? 0 : 3 - (l % 3); }
+};
+
+template <bool GS>
+__global__ void __launch_bounds__(1024, 1) pass_strided_r8(const PassArgs a) {
+    extern __shared__ uint64_t sm[];
+    const int l = a.l, R = 1 << l;
+    uint64_t* tw = sm;           // [R]
+    uint64_t* cu = sm + R;       // [16]
+    uint64_t* x = sm + R + 16;   // [phys(R * 8)]
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t coset = blockIdx.z;
+    const size_t inner = (size_t)1 << (a.M - l);
+    const uint32_t tiles_per_sub = (uint32_t)(inner / TILE_T);
+    const uint32_t Q = blockIdx.x / tiles_per_sub;
+    const size_t c0 = (size_t)(blockIdx.x % tiles_per_sub) * TILE_T;
+    const uint64_t* in = a.src + blockIdx.y * a.src_col_stride + coset * a.src_coset_stride + ((size_t)Q << a.M) + c0;
+    uint64_t* out = a.dst + blockIdx.y * a.dst_col_stride + coset * a.dst_coset_stride + ((size_t)Q << a.M) + c0;
+
+    if (tid == 0) row_constants(a, a.s_last[coset], Q, cu);
+    __syncthreads();
+    for (int i = tid + 1; i < R; i += nt) {
+        int u = 31 - __clz(i);
+        tw[i] = gl::mul(cu[u], __ldg(a.brs + (i - (1 << u))));
+    }
+    __syncthreads();
+
+    const Rounds rd(l);
+    for (int k = 0; k < rd.nr; ++k) {
+        const int rho = GS ? rd.nr - 1 - k : k;
+        const int u0 = rd.u0(rho), skip = rd.skip(rho);
+        const bool first = (k == 0), last = (k == rd.nr - 1);
+        const int sh = l - u0 - 3;
+        for (int w = tid; w < R; w += nt) {
+            const int c = w & 7, t = w >> 3;
+            const int j = t & ((1 << sh) - 1), qh = t >> sh;
+            const int rbase = (qh << (l - u0)) + j;
+            uint64_t v[8];
+            if (first) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) v[m] = gl::canon_fast(in[(size_t)(rbase + (m << sh)) * inner + c]);
+            } else {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) v[m] = x[phys(((rbase + (m << sh)) << 3) + c)];
+            }
+            bfly8_dispatch<GS>(v, tw, u0, qh, skip);
+            if (last) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    uint64_t y = a.apply_scale ? gl::mul(v[m], a.scale) : gl::canon_fast(v[m]);
+                    out[(size_t)(rbase + (m << sh)) * inner + c] = y;
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) x[phys(((rbase + (m << sh)) << 3) + c)] = v[m];
+            }
+        }
+        if (!last) __syncthreads();
+    }
+}
+
+template <bool GS>
+__global__ void __launch_bounds__(1024) pass_contig_r8(const PassArgs a) {
+    extern __shared__ uint64_t sm[];
+    const int l = a.l, R = 1 << l, G = a.G;
+    uint64_t* tw = sm;                      // [G][R]
+    uint64_t* cu = sm + (size_t)G * R;      // [G][16]
+    uint64_t* x = cu + (size_t)G * 16;      // [phys(G * R)]
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t coset = blockIdx.z;
+    const int t_done = a.L - a.M;
+    const uint32_t k0 = blockIdx.x * G;
+    const uint64_t* in = a.src + blockIdx.y * a.src_col_stride + coset * a.src_coset_stride;
+    uint64_t* out = a.dst + blockIdx.y * a.dst_col_stride + coset * a.dst_coset_stride;
+    auto subblock = [&](int g) -> uint32_t { return a.bitrev_store ? gl::bitrev32(k0 + g, t_done) : (k0 + g); };
+
+    if (tid < G) row_constants(a, a.s_last[coset], subblock(tid), cu + tid * 16);
+    __syncthreads();
+    for (int i = tid; i < G * R; i += nt) {
+        int g = i >> l, k = i & (R - 1);
+        if (k) {
+            int u = 31 - __clz(k);
+            tw[i] = gl::mul(cu[g * 16 + u], __ldg(a.brs + (k - (1 << u))));
+        }
+    }
+    __syncthreads();
+
+    const Rounds rd(l);
+    const int items_per_g = R >> 3;
+    for (int k = 0; k < rd.nr; ++k) {
+        const int rho = GS ? rd.nr - 1 - k : k;
+        const int u0 = rd.u0(rho), skip = rd.skip(rho);
+        const bool first = (k == 0), last = (k == rd.nr - 1) && !a.bitrev_store;
+        const int sh = l - u0 - 3;
+        for (int w = tid; w < G * items_per_g; w += nt) {
+            const int g = w / items_per_g, t = w - g * items_per_g;
+            const int j = t & ((1 << sh) - 1), qh = t >> sh;
+            const int rbase = (qh << (l - u0)) + j;
+            uint64_t v[8];
+            if (first) {
+                const uint64_t* p = in + ((size_t)subblock(g) << l) + rbase;
+                if (sh == 0) {
+                    const ulonglong2* p2 = reinterpret_cast<const ulonglong2*>(p);
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        ulonglong2 q = p2[m];
+                        v[2 * m] = gl::canon_fast(q.x);
+                        v[2 * m + 1] = gl::canon_fast(q.y);
+                    }
+                } else {
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) v[m] = gl::canon_fast(p[(size_t)m << sh]);
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) v[m] = x[phys((g << l) + rbase + (m << sh))];
+            }
+            bfly8_dispatch<GS>(v, tw + ((size_t)g << l), u0, qh, skip);
+            if (last) {
+                uint64_t* p = out + ((size_t)(k0 + g) << l) + rbase;
+#pragma unroll
+                for (int m = 0; m < 8; ++m) v[m] = a.apply_scale ? gl::mul(v[m], a.scale) : gl::canon_fast(v[m]);
+                if (sh == 0) {
+                    ulonglong2* p2 = reinterpret_cast<ulonglong2*>(p);
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) p2[m] = make_ulonglong2(v[2 * m], v[2 * m + 1]);
+                } else {
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) p[(size_t)m << sh] = v[m];
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) x[phys((g << l) + rbase + (m << sh))] = v[m];
+            }
+        }
+        if (!last) __syncthreads();
+    }
+    if (a.bitrev_store) {
+        // position p = Q*R + r holds natural index bitrev_l(r)*2^t + (k0+g); consecutive g -> consecutive addresses
+        uint64_t* o = a.dst + blockIdx.y * a.dst_col_stride;
+        const size_t add = a.coset_bits ? gl::bitrev32(coset, a.coset_bits) : 0;
+        for (int i = tid; i < G * R; i += nt) {
+            int g = i % G, kk = i / G;
+            int r = gl::bitrev32((uint32_t)kk, l);
+            uint64_t y = x[phys((g << l) + r)];
+            y = a.apply_scale ? gl::mul(y, a.scale) : gl::canon_fast(y);
+            o[(((size_t)kk << t_done) + k0 + g) * a.out_mul + add] = y;
+        }
+    }
+}
+
 // out[j] *= base * step^j   (coset un-shift after a natural-order inverse transform)
 __global__ void scale_powers_kernel(uint64_t* data, size_t col_stride, size_t n, uint64_t base, uint64_t step) {
     const int RUN = 16;
@@ -285,15 +498,40 @@ static uint64_t pow2k(uint64_t x, int k) {  // x^(2^k)
     return x;
 }
 
+// tuning knobs (environment overrides are for profiling sessions only)
+static int tune_threads() {
+    static int v = [] {
+        const char* e = getenv("OLA_NTT_THREADS");
+        int t = e ? atoi(e) : 512;
+        return (t >= 32 && t <= 1024) ? t : 512;
+    }();
+    return v;
+}
+static int tune_gmax() {
+    static int v = [] {
+        const char* e = getenv("OLA_NTT_G");
+        int t = e ? atoi(e) : 4;
+        return (t == 1 || t == 2 || t == 4 || t == 8) ? t : 4;
+    }();
+    return v;
+}
+
 template <bool GS>
 static void launch_strided(ola_ctx* ctx, const PassArgs& a, size_t ncols, int ncosets, const char* name) {
     const int R = 1 << a.l;
-    size_t smem = ((size_t)R + 16 + (size_t)R * TILE_T) * sizeof(uint64_t);
-    OLA_CUDA(cudaFuncSetAttribute(pass_strided<GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     size_t tiles = ((size_t)1 << a.L) / ((size_t)R * TILE_T);
-    int threads = (int)std::min<size_t>(1024, std::max<size_t>(64, (size_t)R * TILE_T / 4));
     dim3 grid((unsigned)tiles, (unsigned)ncols, (unsigned)ncosets);
-    {
+    if (a.l >= 6) {
+        const size_t padded = (size_t)R * TILE_T + ((size_t)R * TILE_T >> 4) + 1;
+        size_t smem = ((size_t)R + 16 + padded) * sizeof(uint64_t);
+        OLA_CUDA(cudaFuncSetAttribute(pass_strided_r8<GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int threads = (int)std::min<size_t>((size_t)tune_threads(), (size_t)R);  // R items of 8 elements per round
+        Launch lz(ctx, name);
+        pass_strided_r8<GS><<<grid, threads, smem, ctx->stream>>>(a);
+    } else {
+        size_t smem = ((size_t)R + 16 + (size_t)R * TILE_T) * sizeof(uint64_t);
+        OLA_CUDA(cudaFuncSetAttribute(pass_strided<GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int threads = (int)std::min<size_t>(1024, std::max<size_t>(64, (size_t)R * TILE_T / 4));
         Launch lz(ctx, name);
         pass_strided<GS><<<grid, threads, smem, ctx->stream>>>(a);
     }
@@ -303,12 +541,19 @@ static void launch_strided(ola_ctx* ctx, const PassArgs& a, size_t ncols, int nc
 template <bool GS>
 static void launch_contig(ola_ctx* ctx, const PassArgs& a, size_t ncols, int ncosets, const char* name) {
     const int R = 1 << a.l;
-    size_t smem = ((size_t)2 * a.G * R + (size_t)a.G * 16) * sizeof(uint64_t);
-    OLA_CUDA(cudaFuncSetAttribute(pass_contig<GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     size_t blocks = (((size_t)1 << a.L) >> a.l) / a.G;
-    int threads = (int)std::min<size_t>(1024, std::max<size_t>(32, (size_t)R * a.G / 4));
     dim3 grid((unsigned)blocks, (unsigned)ncols, (unsigned)ncosets);
-    {
+    if (a.l >= 6) {
+        const size_t padded = (size_t)a.G * R + ((size_t)a.G * R >> 4) + 1;
+        size_t smem = ((size_t)a.G * R + (size_t)a.G * 16 + padded) * sizeof(uint64_t);
+        OLA_CUDA(cudaFuncSetAttribute(pass_contig_r8<GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int threads = (int)std::min<size_t>((size_t)tune_threads(), std::max<size_t>(32, (size_t)R * a.G / 8));
+        Launch lz(ctx, name);
+        pass_contig_r8<GS><<<grid, threads, smem, ctx->stream>>>(a);
+    } else {
+        size_t smem = ((size_t)2 * a.G * R + (size_t)a.G * 16) * sizeof(uint64_t);
+        OLA_CUDA(cudaFuncSetAttribute(pass_contig<GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int threads = (int)std::min<size_t>(1024, std::max<size_t>(32, (size_t)R * a.G / 4));
         Launch lz(ctx, name);
         pass_contig<GS><<<grid, threads, smem, ctx->stream>>>(a);
     }
@@ -359,7 +604,7 @@ void forward(ola_ctx* ctx, const FwdDesc& d) {
             launch_strided<false>(ctx, a, d.ncols, ncosets, d.tag_strided);
         } else {
             const int t = L - M;
-            int gmax = (a.l <= 10) ? 8 : 4;
+            int gmax = (a.l <= 10) ? tune_gmax() : std::min(tune_gmax(), 4);
             a.G = (int)std::min<size_t>((size_t)gmax, (size_t)1 << t);
             a.bitrev_store = d.natural_output ? 1 : 0;
             if (d.natural_output) {
@@ -403,7 +648,7 @@ void inverse_from_leaf_order(ola_ctx* ctx, uint64_t* data, size_t col_stride, si
         a.s_last[0] = pow2k(shift_inv, a.M - a.l);
         if (k + 1 == plan.size()) {
             const int t = L - a.M;
-            int gmax = (a.l <= 10) ? 8 : 4;
+            int gmax = (a.l <= 10) ? tune_gmax() : std::min(tune_gmax(), 4);
             a.G = (int)std::min<size_t>((size_t)gmax, (size_t)1 << t);
             launch_contig<true>(ctx, a, ncols, 1, "coset_intt_contig");
         } else {

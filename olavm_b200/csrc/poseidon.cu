@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(128) permute_kernel(uint64_t* states, size_t n
     if (i >= n) return;
     uint64_t s[12];
 #pragma unroll
-    for (int k = 0; k < 12; ++k) s[k] = gl::canon(states[i * 12 + k]);
+    for (int k = 0; k < 12; ++k) s[k] = states[i * 12 + k];
     permute(s);
 #pragma unroll
     for (int k = 0; k < 12; ++k) states[i * 12 + k] = s[k];
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(128) hash_rows_kernel(const uint64_t* __restri
         for (int k = 0; k < 8; ++k) {
             if (c0 + k < ncols) {
                 uint64_t v = ROWMAJOR ? base[r * ncols + c0 + k] : base[(c0 + k) * col_stride + r];
-                s[k] = gl::canon(v);
+                s[k] = v;
             }
         }
         permute(s);

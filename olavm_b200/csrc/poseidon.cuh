@@ -26,41 +26,36 @@ static __constant__ uint64_t c_vs[22 * 11];
 static __constant__ uint64_t c_whats[22 * 11];
 static __constant__ uint64_t c_init[11 * 11];
 
-// 160-bit accumulator for sums of 64x64 products
+// 160-bit accumulator (five 32-bit limbs) for sums of 64x64 products: one carry chain per product
 struct acc160 {
-    uint64_t lo, hi;
-    uint32_t top;
+    uint32_t w0, w1, w2, w3, w4;
 };
-__device__ __forceinline__ void acc_zero(acc160& a) {
-    a.lo = 0;
-    a.hi = 0;
-    a.top = 0;
-}
+__device__ __forceinline__ void acc_zero(acc160& a) { a.w0 = a.w1 = a.w2 = a.w3 = a.w4 = 0; }
 __device__ __forceinline__ void acc_mac(acc160& a, uint64_t x, uint64_t y) {
-    uint64_t pl, ph;
-    gl::mul_wide(x, y, pl, ph);
-    uint64_t lo = a.lo + pl;
-    uint64_t c0 = lo < pl;
-    uint64_t hi = a.hi + ph;
-    uint32_t c1 = hi < ph;
-    uint64_t hi2 = hi + c0;
-    c1 += (hi2 < hi);
-    a.lo = lo;
-    a.hi = hi2;
-    a.top += c1;
+    uint32_t p0, p1, p2, p3;
+    gl::mul_limbs(x, y, p0, p1, p2, p3);
+    asm("add.cc.u32 %0, %0, %5;\n\t"
+        "addc.cc.u32 %1, %1, %6;\n\t"
+        "addc.cc.u32 %2, %2, %7;\n\t"
+        "addc.cc.u32 %3, %3, %8;\n\t"
+        "addc.u32 %4, %4, 0;"
+        : "+r"(a.w0), "+r"(a.w1), "+r"(a.w2), "+r"(a.w3), "+r"(a.w4)
+        : "r"(p0), "r"(p1), "r"(p2), "r"(p3));
 }
-// value = lo + hi*2^64 + top*2^128,  2^128 = -2^32 (mod p)
+// value = (w3:w2:w1:w0) + w4 * 2^128,  2^128 = -2^32 (mod p);  result lazy
 __device__ __forceinline__ uint64_t acc_reduce(const acc160& a) {
-    uint64_t r = gl::reduce128(a.lo, a.hi);
-    return gl::sub(r, (uint64_t)a.top << 32);
+    uint64_t r = gl::reduce_limbs(a.w0, a.w1, a.w2, a.w3);
+    return gl::sub_lc(r, (uint64_t)a.w4 << 32);
 }
 
+// x^7 on lazy representatives
 __device__ __forceinline__ uint64_t sbox7(uint64_t x) {
-    uint64_t x2 = gl::sqr(x), x4 = gl::sqr(x2), x3 = gl::mul(x, x2);
-    return gl::mul(x3, x4);
+    uint64_t x2 = gl::mul_lazy(x, x), x4 = gl::mul_lazy(x2, x2), x3 = gl::mul_lazy(x, x2);
+    return gl::mul_lazy(x3, x4);
 }
 
 // out[r] = sum_i s[(i+r)%12] * CIRC[i] + s[r]*DIAG[r]   (CIRC = 17,15,41,16,2,28,13,13,39,18,34,20; DIAG[0] = 8)
+// lazy in, lazy out
 __device__ __forceinline__ void mds_layer(uint64_t* s) {
     constexpr uint32_t C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
     uint32_t lo[12], hi[12];
@@ -84,23 +79,24 @@ __device__ __forceinline__ void mds_layer(uint64_t* s) {
         // value = al + ah * 2^32  (al, ah < 2^42)
         uint64_t l128 = al + (ah << 32);
         uint64_t h128 = (ah >> 32) + (l128 < al);
-        s[r] = gl::reduce128(l128, h128);
+        s[r] = gl::reduce128_lazy(l128, h128);
     }
 }
 
 __device__ __forceinline__ void full_round(uint64_t* s, int round_ctr) {
 #pragma unroll
-    for (int i = 0; i < 12; ++i) s[i] = sbox7(gl::add(s[i], c_round[round_ctr * 12 + i]));
+    for (int i = 0; i < 12; ++i) s[i] = sbox7(gl::add_lc(s[i], c_round[round_ctr * 12 + i]));
     mds_layer(s);
 }
 
+// s: any u64 representatives in, CANONICAL representatives out
 __device__ __forceinline__ void permute(uint64_t* s) {
 #pragma unroll 1
     for (int r = 0; r < 4; ++r) full_round(s, r);
 
     // partial_first_constant_layer + mds_partial_layer_init (poseidon.rs:303-313, :332-358)
 #pragma unroll
-    for (int i = 0; i < 12; ++i) s[i] = gl::add(s[i], c_first[i]);
+    for (int i = 0; i < 12; ++i) s[i] = gl::add_lc(s[i], c_first[i]);
     {
         acc160 acc[11];
 #pragma unroll
@@ -116,7 +112,7 @@ __device__ __forceinline__ void permute(uint64_t* s) {
     // 22 partial rounds (poseidon.rs:582-588, mds_partial_layer_fast :392-421)
 #pragma unroll 1
     for (int r = 0; r < 22; ++r) {
-        s[0] = gl::add(sbox7(s[0]), c_partial[r]);
+        s[0] = gl::add_lc(sbox7(s[0]), c_partial[r]);
         acc160 d;
         acc_zero(d);
         acc_mac(d, s[0], 25);  // MDS_MATRIX_CIRC[0] + MDS_MATRIX_DIAG[0]
@@ -124,11 +120,13 @@ __device__ __forceinline__ void permute(uint64_t* s) {
         for (int i = 1; i < 12; ++i) acc_mac(d, s[i], c_whats[r * 11 + i - 1]);
         uint64_t s0 = s[0];
 #pragma unroll
-        for (int i = 1; i < 12; ++i) s[i] = gl::add(s[i], gl::mul(s0, c_vs[r * 11 + i - 1]));
+        for (int i = 1; i < 12; ++i) s[i] = gl::mad_lazy(s0, c_vs[r * 11 + i - 1], s[i]);
         s[0] = acc_reduce(d);
     }
 #pragma unroll 1
     for (int r = 0; r < 4; ++r) full_round(s, 26 + r);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) s[i] = gl::canon_fast(s[i]);
 }
 #endif  // __CUDACC__
 

@@ -16,7 +16,7 @@ P = 0xFFFFFFFF00000001
 
 def build(force=False):
     """Compile the C restatement (gcc + OpenMP).  Called by __graft_entry__.build()."""
-    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h", ".cpp", ".hpp"))]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
@@ -74,6 +74,13 @@ def _set_sigs(L):
     L.orc_merkle_verify.restype = _int
     L.orc_commit.argtypes = [_u64p, _sz, _sz, _int, _u32, _u32, _u64p, _u64p, _u64p, _u64p]
     L.orc_commit.restype = _int
+    L.orc_stark_prove.argtypes = [ctypes.POINTER(_int), _u32, ctypes.POINTER(_u64p), ctypes.POINTER(_u32), _int,
+                                  ctypes.POINTER(ctypes.c_uint8), _sz, ctypes.POINTER(_sz), ctypes.c_char_p, _sz]
+    L.orc_stark_prove.restype = _int
+    L.orc_stark_verify.argtypes = [ctypes.POINTER(_int), _u32, ctypes.POINTER(ctypes.c_uint8), _sz, ctypes.c_char_p, _sz]
+    L.orc_stark_verify.restype = _int
+    L.orc_table_columns.argtypes = [_int]
+    L.orc_table_columns.restype = _int
 
 
 # ---------------------------------------------------------------- helpers
@@ -218,3 +225,42 @@ def commit(cols, is_coeffs=False, rate_bits=3, cap_height=4, want_leaves=True, w
     rc = lib().orc_commit(_p(c), ncols, n, int(is_coeffs), rate_bits, cap_height, _p(coeffs), _p(leaves), _p(dig), _p(cap))
     assert rc == 0
     return dict(coeffs=coeffs, leaves=leaves, digests=dig, cap=cap)
+
+
+# ---------------------------------------------------------------- STARK prover / verifier
+TABLE_IDS = dict(cpu=0, memory=1, bitwise=2, cmp=3, rangecheck=4, poseidon=5, poseidon_chunk=6, storage=7, tape=8, sccall=9,
+                 program=10, prog_chunk=11)
+
+
+class StarkError(RuntimeError):
+    pass
+
+
+def table_columns(table_id):
+    return lib().orc_table_columns(int(table_id))
+
+
+def stark_prove(table_ids, traces, check_degree=True, max_bytes=1 << 26):
+    """prove_with_traces + Buffer::write_all_proof -> bytes.  traces[i]: [columns_i, 2^k_i] uint64 column-major."""
+    k = len(table_ids)
+    trs = [np.ascontiguousarray(t, dtype=np.uint64) for t in traces]
+    ids = (ctypes.c_int * k)(*[int(x) for x in table_ids])
+    ptrs = (_u64p * k)(*[_p(t) for t in trs])
+    logs = (ctypes.c_uint32 * k)(*[int(t.shape[1]).bit_length() - 1 for t in trs])
+    out = (ctypes.c_uint8 * max_bytes)()
+    n = ctypes.c_size_t(0)
+    err = ctypes.create_string_buffer(512)
+    rc = lib().orc_stark_prove(ids, k, ptrs, logs, 1 if check_degree else 0, out, max_bytes, ctypes.byref(n), err, 512)
+    if rc != 0:
+        raise StarkError(err.value.decode())
+    return bytes(bytearray(out)[: n.value])
+
+
+def stark_verify(table_ids, proof):
+    """Buffer::read_all_proof + verify_proof -> (ok, message)."""
+    k = len(table_ids)
+    ids = (ctypes.c_int * k)(*[int(x) for x in table_ids])
+    buf = (ctypes.c_uint8 * len(proof)).from_buffer_copy(proof)
+    err = ctypes.create_string_buffer(512)
+    rc = lib().orc_stark_verify(ids, k, buf, len(proof), err, 512)
+    return rc == 0, err.value.decode()

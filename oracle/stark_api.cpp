@@ -1,0 +1,65 @@
+/* ORACLE (test infrastructure, NOT product code) -- C entry points of the restated STARK prover/verifier. */
+#include <cstdio>
+
+#include "tables.hpp"
+
+using namespace orc;
+
+static void set_err(char* err, size_t cap, const std::string& e) {
+    if (err && cap) snprintf(err, cap, "%s", e.c_str());
+}
+
+extern "C" {
+
+/* prove_with_traces + Buffer::write_all_proof.  table_ids: ntables ids in enum order; traces[i]: column-major
+ * [columns_i][2^log_ns[i]].  Returns 0 and the proof bytes, or -1 with a message. */
+int orc_stark_prove(const int* table_ids, uint32_t ntables, const uint64_t* const* traces, const uint32_t* log_ns, int check_degree,
+                    uint8_t* out, size_t cap, size_t* out_len, char* err, size_t errcap) {
+    try {
+        System sys = make_system(std::vector<int>(table_ids, table_ids + ntables));
+        Config cfg;
+        cfg.check_quotient_degree = check_degree != 0;
+        std::vector<VF> tr(ntables);
+        std::vector<size_t> ns(ntables);
+        for (uint32_t i = 0; i < ntables; i++) {
+            ns[i] = (size_t)1 << log_ns[i];
+            tr[i].assign(traces[i], traces[i] + ns[i] * sys.tables[i].columns);
+            for (auto& x : tr[i]) x = gl_canon(x);
+        }
+        AllProof ap;
+        std::string e = prove_with_traces(sys, cfg, tr, ns, ap);
+        if (!e.empty()) { set_err(err, errcap, e); return -1; }
+        Writer w;
+        w.all(ap);
+        *out_len = w.buf.size();
+        if (w.buf.size() > cap) { set_err(err, errcap, "output buffer too small"); return -2; }
+        memcpy(out, w.buf.data(), w.buf.size());
+        return 0;
+    } catch (const std::exception& ex) {
+        set_err(err, errcap, ex.what());
+        return -1;
+    }
+}
+
+/* Buffer::read_all_proof + verify_proof.  Returns 0 if the proof verifies. */
+int orc_stark_verify(const int* table_ids, uint32_t ntables, const uint8_t* proof, size_t len, char* err, size_t errcap) {
+    try {
+        System sys = make_system(std::vector<int>(table_ids, table_ids + ntables));
+        Config cfg;
+        Reader r(proof, len);
+        AllProof ap = r.all();
+        if (!r.ok || r.pos != len) { set_err(err, errcap, "malformed proof bytes"); return -1; }
+        std::string e = verify_all(sys, cfg, ap);
+        if (!e.empty()) { set_err(err, errcap, e); return -1; }
+        return 0;
+    } catch (const std::exception& ex) {
+        set_err(err, errcap, ex.what());
+        return -1;
+    }
+}
+
+int orc_table_columns(int table_id) {
+    try { return table_by_id(table_id).columns; } catch (...) { return -1; }
+}
+
+}  // extern "C"

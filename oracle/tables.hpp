@@ -1,0 +1,117 @@
+/* ORACLE (test infrastructure, NOT product code) -- CPU restatement of the AIR tables ("chips") and of the
+ * cross-table-lookup registry.  Each eval<> follows the Rust eval_packed_generic of the cited file line by
+ * line and emits the constraints in source order (the consumer is Horner in alpha, so order is semantics:
+ * circuits/src/stark/constraint_consumer.rs:60-65).
+ *
+ * Tables restated so far (enum order of circuits/src/stark/ola_stark.rs:104-119):
+ *   3 Cmp         circuits/src/builtins/cmp/{columns.rs:16-22, cmp_stark.rs:21-45, :88-108}
+ *   4 RangeCheck  circuits/src/builtins/rangecheck/{columns.rs:25-39, rangecheck_stark.rs:27-108, :111-140},
+ *                 circuits/src/stark/lookup.rs:13-35
+ */
+#ifndef ORC_TABLES_HPP
+#define ORC_TABLES_HPP
+#include "stark.hpp"
+
+namespace orc {
+
+enum TableId { T_CPU = 0, T_MEMORY, T_BITWISE, T_CMP, T_RANGECHECK, T_POSEIDON, T_POSEIDON_CHUNK, T_STORAGE, T_TAPE, T_SCCALL, T_PROGRAM, T_PROG_CHUNK, T_NUM };
+
+/* lookup.rs:13-35 */
+template <class O>
+void eval_lookups(const P<O>* lv, const P<O>* nv, Consumer<O>& yc, int col_permuted_input, int col_permuted_table) {
+    P<O> local_perm_input = lv[col_permuted_input];
+    P<O> next_perm_table = nv[col_permuted_table];
+    P<O> next_perm_input = nv[col_permuted_input];
+    P<O> diff_input_prev = next_perm_input - local_perm_input;
+    P<O> diff_input_table = next_perm_input - next_perm_table;
+    yc.constraint(diff_input_prev * diff_input_table);
+    yc.constraint_last_row(diff_input_table);
+}
+
+/* ---- Cmp (cmp_stark.rs:21-45) ---- */
+namespace cmp {
+enum { OP0 = 0, OP1, GTE, ABS_DIFF, ABS_DIFF_INV, FILTER_LOOKING_RC, NUM };
+template <class O>
+void eval(const P<O>* lv, const P<O>* nv, Consumer<O>& yc) {
+    typedef P<O> T;
+    T op0 = lv[OP0], op1 = lv[OP1], gte = lv[GTE], abs_diff = lv[ABS_DIFF], abs_diff_inv = lv[ABS_DIFF_INV];
+    yc.constraint(gte * (T::one() - gte));
+    yc.constraint(gte * (op0 - op1 - abs_diff));
+    yc.constraint((T::one() - gte) * (op1 - op0 - abs_diff));
+    yc.constraint((T::one() - gte) * (T::one() - abs_diff * abs_diff_inv));
+}
+}  // namespace cmp
+
+/* ---- RangeCheck (rangecheck_stark.rs:27-108) ---- */
+namespace rangecheck {
+enum { CPU_FILTER = 0, MEMORY_SORT_FILTER, MEMORY_REGION_FILTER, CMP_FILTER, VAL, LIMB_LO, LIMB_HI, LIMB_LO_PERMUTED, LIMB_HI_PERMUTED,
+       FIX_RANGE_CHECK_U16, FIX_RANGE_CHECK_U16_PERMUTED_LO, FIX_RANGE_CHECK_U16_PERMUTED_HI, NUM };
+template <class O>
+void eval(const P<O>* lv, const P<O>* nv, Consumer<O>& yc) {
+    typedef P<O> T;
+    T val = lv[VAL], limb_lo = lv[LIMB_LO], limb_hi = lv[LIMB_HI];
+    T sum = limb_lo + limb_hi * T::c(1 << 16);
+    yc.constraint(val - sum);
+    eval_lookups<O>(lv, nv, yc, LIMB_LO_PERMUTED, FIX_RANGE_CHECK_U16_PERMUTED_LO);
+    eval_lookups<O>(lv, nv, yc, LIMB_HI_PERMUTED, FIX_RANGE_CHECK_U16_PERMUTED_HI);
+}
+}  // namespace rangecheck
+
+template <class EvalB, class EvalE>
+Table make_table(const char* name, int cols, int degree, EvalB eb, EvalE ee, std::vector<PermutationPair> pp = {}) {
+    Table t;
+    t.name = name;
+    t.columns = cols;
+    t.constraint_degree = degree;
+    t.permutation_pairs = std::move(pp);
+    t.eval_base = eb;
+    t.eval_ext = ee;
+    return t;
+}
+#define ORC_TABLE(name, ns, cols, degree, ...) make_table(name, cols, degree, ns::eval<FOps>, ns::eval<EOps>, ##__VA_ARGS__)
+
+inline bool table_available(int id) { return id == T_CMP || id == T_RANGECHECK; }
+
+inline Table table_by_id(int id) {
+    switch (id) {
+        case T_CMP: return ORC_TABLE("CmpStark", cmp, cmp::NUM, 3);
+        case T_RANGECHECK:
+            return ORC_TABLE("RangeCheckStark", rangecheck, rangecheck::NUM, 3,
+                             {PermutationPair{{{rangecheck::LIMB_LO, rangecheck::LIMB_LO_PERMUTED}}},
+                              PermutationPair{{{rangecheck::LIMB_HI, rangecheck::LIMB_HI_PERMUTED}}},
+                              PermutationPair{{{rangecheck::FIX_RANGE_CHECK_U16, rangecheck::FIX_RANGE_CHECK_U16_PERMUTED_LO}}},
+                              PermutationPair{{{rangecheck::FIX_RANGE_CHECK_U16, rangecheck::FIX_RANGE_CHECK_U16_PERMUTED_HI}}}});
+        default: throw std::runtime_error("table not restated yet");
+    }
+}
+
+/* all_cross_table_lookups (ola_stark.rs:121-143), in registry order; entries whose tables are not all restated
+ * yet are tagged and skipped by make_system for sub-systems. */
+inline std::vector<CrossTableLookup> all_cross_table_lookups() {
+    std::vector<CrossTableLookup> v;
+    /* ctl_cmp_rangecheck (ola_stark.rs:282-296): looking = RangeCheck(VAL | CMP_FILTER), looked = Cmp(abs_diff | filter) */
+    v.push_back({{twc(T_RANGECHECK, singles({rangecheck::VAL}), Column::single(rangecheck::CMP_FILTER))},
+                 twc(T_CMP, singles({cmp::ABS_DIFF}), Column::single(cmp::FILTER_LOOKING_RC))});
+    return v;
+}
+
+/* A proving system = an ordered subset of the 12 tables (proof order = enum order) plus every registered CTL
+ * whose tables are all inside the subset (table ids remapped to positions). */
+inline System make_system(const std::vector<int>& ids) {
+    System s;
+    std::vector<int> pos(T_NUM, -1);
+    for (size_t i = 0; i < ids.size(); i++) { pos[ids[i]] = (int)i; s.tables.push_back(table_by_id(ids[i])); }
+    for (auto ctl : all_cross_table_lookups()) {
+        bool ok = pos[ctl.looked.table] >= 0;
+        for (auto& l : ctl.looking) ok = ok && pos[l.table] >= 0;
+        if (!ok) continue;
+        for (auto& l : ctl.looking) l.table = pos[l.table];
+        ctl.looked.table = pos[ctl.looked.table];
+        s.ctls.push_back(ctl);
+    }
+    s.compress_challenges.assign(ids.size(), 0);
+    return s;
+}
+
+}  // namespace orc
+#endif

@@ -9,6 +9,7 @@
 #include "gl.cuh"
 #include "ntt.h"
 #include "poseidon.cuh"
+#include "stark.h"
 
 namespace {
 
@@ -357,6 +358,30 @@ int ola_commit(ola_ctx* ctx, const uint64_t* cols, int on_device, size_t ncols, 
         }
         *out = b;
     });
+}
+
+int ola_prove(ola_ctx* ctx, const int* table_ids, uint32_t ntables, const uint64_t* const* traces, int on_device, const uint32_t* log_ns,
+              int check_quotient_degree, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+    if (!ctx || !table_ids || !traces || !log_ns || !proof_len || (!proof_out && proof_cap)) return OLA_ERR_INVALID_ARG;
+    *proof_len = 0;
+    return guarded(ctx, [&] {
+        ola::stark::Config cfg;
+        cfg.check_quotient_degree = check_quotient_degree != 0;
+        std::vector<int> ids(table_ids, table_ids + ntables);
+        std::vector<const uint64_t*> tr(traces, traces + ntables);
+        std::vector<uint32_t> lg(log_ns, log_ns + ntables);
+        std::vector<uint8_t> bytes = ola::stark::prove_all(ctx, ids, tr, on_device != 0, lg, cfg);
+        *proof_len = bytes.size();
+        OLA_CHECK(bytes.size() <= proof_cap, OLA_ERR_INVALID_ARG, "proof buffer too small (needed size returned in proof_len)");
+        memcpy(proof_out, bytes.data(), bytes.size());
+    });
+}
+int ola_table_columns(int table_id) {
+    try {
+        return ola::stark::table_available(table_id) ? ola::stark::table_info(table_id).columns : -1;
+    } catch (...) {
+        return -1;
+    }
 }
 
 int ola_batch_free(ola_ctx* ctx, ola_batch* b) {

@@ -44,7 +44,7 @@ __global__ void gather_path_kernel(const uint64_t* nodes, size_t nleaves, size_t
     out[i] = nodes[idx * 4 + w];
 }
 
-static void canon_copy(ola_ctx* ctx, uint64_t* dst, const uint64_t* src, size_t n) {
+void canon_copy(ola_ctx* ctx, uint64_t* dst, const uint64_t* src, size_t n) {
     if (!n) return;
     unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16);
     canon_copy_kernel<<<blocks, 256, 0, ctx->stream>>>(dst, src, n);

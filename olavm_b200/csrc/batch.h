@@ -14,6 +14,8 @@ struct ola_batch {
 
 namespace ola {
 void dev_alloc(uint64_t** p, size_t n_u64);
+// dst[i] = canonical(src[i]); dst may alias src
+void canon_copy(ola_ctx* ctx, uint64_t* dst, const uint64_t* src, size_t n);
 // grow-only per-context workspace of at least n_u64 elements (synchronises the stream when it has to grow)
 uint64_t* ctx_scratch(ola_ctx* ctx, size_t n_u64);
 void gather_rows(ola_ctx* ctx, const uint64_t* d_cols, size_t col_stride, size_t ncols, size_t first, size_t count,

@@ -5,4 +5,6 @@
 #include "ntt.cu"
 #include "poseidon.cu"
 #include "batch.cu"
+#include "fri.cu"
+#include "stark.cu"
 #include "api.cu"

@@ -1,0 +1,686 @@
+// Multi-table STARK prover on the device.
+//
+// Replaces:
+//   circuits/src/stark/prover.rs:79-327      prove_with_traces (orchestration, transcript order)
+//   circuits/src/stark/prover.rs:330-567     prove_single_table
+//   circuits/src/stark/prover.rs:571-705     compute_quotient_polys   -> quotient_kernel<Air>
+//   circuits/src/stark/cross_table_lookup.rs:224-310  cross_table_lookup_data / partial_products -> ctl_values + scan
+//   circuits/src/stark/permutation.rs:103-160 compute_permutation_z_polys -> perm_values + exclusive scan
+//   circuits/src/stark/proof.rs:199-246      StarkOpeningSet::new -> eval_partial_kernel + host combine
+//   circuits/src/stark/vanishing_poly.rs:20-47, permutation.rs:302-360, cross_table_lookup.rs:380-419
+//
+// Everything large stays in HBM between phases (trace values, the three PolynomialBatches of a table, quotient
+// values); the host sees caps, openings and query rows only.  LDE rows are read column-major in leaf order:
+// a warp's 32 rows are 32 consecutive u64 of every column (coalesced), and the "next row" of leaf position p is
+// bitrev(bitrev(p)+1): for every warp but a 2^-(L-5) fraction that is again 32 consecutive u64.
+#include "stark.h"
+
+#include "air/registry.cuh"
+#include "batch.h"
+#include "fri.h"
+#include "ntt.h"
+
+namespace ola {
+namespace stark {
+
+using air::Consumer;
+using air::Fp;
+using air::Row;
+
+// ---- device descriptors of linear-combination columns / CTL instances / permutation instances ----------------
+struct DevLc {
+    int off, cnt;
+    uint64_t constant;
+};
+struct DevCtl {
+    int col_off, col_cnt;  // into lcs[]
+    int filter;            // index into lcs[] or -1
+    uint64_t beta, gamma;
+};
+struct DevPermInst {
+    int pair_off, pair_cnt;  // into perm_pairs[] (lhs,rhs interleaved)
+    uint64_t beta, gamma;
+};
+struct DevPermBatch {
+    int inst_off, inst_cnt;
+};
+struct DevTables {  // all arrays live in one device allocation
+    const DevLc* lcs;
+    const int* lc_col;
+    const uint64_t* lc_coef;
+    const DevCtl* ctls;
+    int nctl;
+    const DevPermInst* perm_insts;
+    const DevPermBatch* perm_batches;
+    const int* perm_pairs;
+    int nperm_batches;
+};
+
+__device__ __forceinline__ Fp eval_lc(const DevTables& d, int k, const uint64_t* __restrict__ base, size_t stride, size_t r) {
+    const DevLc lc = d.lcs[k];
+    Fp s(0);
+    for (int i = 0; i < lc.cnt; ++i) s += Fp(__ldg(base + (size_t)d.lc_col[lc.off + i] * stride + r)) * Fp(d.lc_coef[lc.off + i]);
+    return s + Fp(lc.constant);
+}
+// GrandProductChallenge::combine (permutation.rs:61-72): reduce_with_powers(terms, beta) + gamma
+__device__ __forceinline__ Fp ctl_combine(const DevTables& d, const DevCtl& c, const uint64_t* __restrict__ base, size_t stride, size_t r) {
+    Fp s(0), beta(c.beta);
+    for (int i = c.col_cnt - 1; i >= 0; --i) s = s * beta + eval_lc(d, c.col_off + i, base, stride, r);
+    return s + Fp(c.gamma);
+}
+
+// ---- CTL Z columns: per-row factor, then an inclusive prefix product (partial_products, cross_table_lookup.rs:284-310)
+__global__ void ctl_values_kernel(DevTables d, const uint64_t* __restrict__ trace, size_t n, uint64_t* __restrict__ zs /* [nctl][n] */, int* err) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const DevCtl c = d.ctls[blockIdx.y];
+    uint64_t filter = c.filter >= 0 ? eval_lc(d, c.filter, trace, n, i).v : 1;
+    uint64_t v = 1;
+    if (filter == 1)
+        v = ctl_combine(d, c, trace, n, i).v;
+    else if (filter != 0)
+        atomicOr(err, 1);  // "Non-binary filter?" (cross_table_lookup.rs:305)
+    zs[(size_t)blockIdx.y * n + i] = v;
+}
+
+// permutation Z factors: prod_inst lhs / prod_inst rhs  (compute_permutation_z_poly, permutation.rs:129-160)
+__global__ void perm_values_kernel(DevTables d, const uint64_t* __restrict__ trace, size_t n, uint64_t* __restrict__ zs) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const DevPermBatch b = d.perm_batches[blockIdx.y];
+    Fp num(1), den(1);
+    for (int k = 0; k < b.inst_cnt; ++k) {
+        const DevPermInst in = d.perm_insts[b.inst_off + k];
+        Fp l(in.gamma), r(in.gamma), w(1), beta(in.beta);
+        for (int p = 0; p < in.pair_cnt; ++p) {
+            l += Fp(trace[(size_t)d.perm_pairs[2 * (in.pair_off + p)] * n + i]) * w;
+            r += Fp(trace[(size_t)d.perm_pairs[2 * (in.pair_off + p) + 1] * n + i]) * w;
+            w *= beta;
+        }
+        num *= l;
+        den *= r;
+    }
+    zs[(size_t)blockIdx.y * n + i] = gl::mul(num.v, gl::inv(den.v));
+}
+
+// ---- prefix products over columns [ncols][n], in place.  exclusive: out[i] = prod_{j<i}; else prod_{j<=i}
+static constexpr int SC_RUN = 8, SC_THREADS = 256, SC_CHUNK = SC_RUN * SC_THREADS;
+__global__ void __launch_bounds__(SC_THREADS) scan_chunk_kernel(const uint64_t* __restrict__ data, size_t n, uint64_t* __restrict__ chunkp, size_t nchunks) {
+    __shared__ uint64_t sh[SC_THREADS];
+    const uint64_t* c = data + (size_t)blockIdx.y * n;
+    size_t start = (size_t)blockIdx.x * SC_CHUNK + (size_t)threadIdx.x * SC_RUN;
+    uint64_t acc = 1;
+    for (int k = 0; k < SC_RUN; ++k)
+        if (start + k < n) acc = gl::mul(acc, c[start + k]);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = SC_THREADS / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] = gl::mul(sh[threadIdx.x], sh[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) chunkp[(size_t)blockIdx.y * nchunks + blockIdx.x] = sh[0];
+}
+__global__ void scan_carry_kernel(uint64_t* chunkp, size_t nchunks, size_t ncols) {
+    size_t col = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncols) return;
+    uint64_t* p = chunkp + col * nchunks;
+    uint64_t acc = 1;
+    for (size_t s = 0; s < nchunks; ++s) {
+        uint64_t v = p[s];
+        p[s] = acc;  // exclusive prefix of chunk products
+        acc = gl::mul(acc, v);
+    }
+}
+__global__ void __launch_bounds__(SC_THREADS) scan_emit_kernel(uint64_t* __restrict__ data, size_t n, const uint64_t* __restrict__ chunkp, size_t nchunks, int exclusive) {
+    __shared__ uint64_t sh[SC_THREADS];
+    uint64_t* c = data + (size_t)blockIdx.y * n;
+    const int t = threadIdx.x;
+    size_t start = (size_t)blockIdx.x * SC_CHUNK + (size_t)t * SC_RUN;
+    uint64_t v[SC_RUN];
+    uint64_t acc = 1;
+    for (int k = 0; k < SC_RUN; ++k) {
+        v[k] = start + k < n ? c[start + k] : 1;
+        acc = gl::mul(acc, v[k]);
+    }
+    sh[t] = acc;
+    __syncthreads();
+    for (int s = 1; s < SC_THREADS; s <<= 1) {  // inclusive Hillis-Steele scan of the run products
+        uint64_t x = sh[t];
+        if (t >= s) x = gl::mul(x, sh[t - s]);
+        __syncthreads();
+        sh[t] = x;
+        __syncthreads();
+    }
+    uint64_t carry = chunkp[(size_t)blockIdx.y * nchunks + blockIdx.x];
+    if (t > 0) carry = gl::mul(carry, sh[t - 1]);
+    for (int k = 0; k < SC_RUN; ++k) {
+        if (start + k >= n) break;
+        if (exclusive) {
+            c[start + k] = carry;
+            carry = gl::mul(carry, v[k]);
+        } else {
+            carry = gl::mul(carry, v[k]);
+            c[start + k] = carry;
+        }
+    }
+}
+
+// ---- quotient: one thread per LDE point of the size n*2^qdb quotient domain ------------------------------------
+struct QuotArgs {
+    const uint64_t* trace_lde;  // [cols][L]
+    const uint64_t* zs_lde;     // [nzs][L]
+    size_t L;                   // LDE size (column stride)
+    int log_n, qdb;
+    uint64_t alpha0, alpha1;
+    uint64_t g, g_inv, n_field;  // subgroup generator, its inverse, n as a field element
+    uint64_t zh[8], zh_inv[8];   // Z_H on the 2^qdb cosets, indexed by (i mod 2^qdb)
+    const uint64_t* pw;          // omega_{2^32} power tables (forward)
+    uint64_t* out;               // [2][n << qdb]
+    DevTables d;
+    int num_perm_zs;
+};
+
+__device__ __forceinline__ uint64_t pow_omega_fwd(const uint64_t* __restrict__ pw, uint32_t E) {
+    uint64_t r = __ldg(pw + 4096 + (E >> 22));
+    r = gl::mul(r, __ldg(pw + 2048 + ((E >> 11) & 2047u)));
+    return gl::mul(r, __ldg(pw + (E & 2047u)));
+}
+
+template <class Air>
+__global__ void __launch_bounds__(128) quotient_kernel(const QuotArgs a) {
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t size = (size_t)1 << (a.log_n + a.qdb);
+    if (r >= size) return;
+    const uint32_t nmask = (1u << a.log_n) - 1;
+    const uint32_t coset = (uint32_t)(r >> a.log_n), pos = (uint32_t)r & nmask;
+    const uint32_t j = gl::bitrev32(pos, a.log_n);
+    const uint32_t pos_next = gl::bitrev32((j + 1) & nmask, a.log_n);
+    const size_t r_next = ((size_t)coset << a.log_n) | pos_next;
+    // natural LDE index k = bitrev_{log_n+3}(r) = j*8 + bitrev3(coset); x = 7 * omega_{8n}^k
+    const uint32_t cb = gl::bitrev32(coset, 3);
+    const uint32_t k = (j << 3) | cb;
+    const int lde_bits = a.log_n + 3;
+    const uint32_t E = lde_bits >= 32 ? k : (k << (32 - lde_bits));
+    const uint64_t x = gl::mul(gl::GEN, pow_omega_fwd(a.pw, E));
+    const uint32_t zi = cb >> (3 - a.qdb);  // (k / step) mod 2^qdb
+    // L_0(x) = Z_H(x) / (n (x - 1)),  L_last(x) = Z_H(x) / (n (g x - 1))   (verifier.rs:380-396); x is never in H
+    const uint64_t d0 = gl::mul(a.n_field, gl::sub(x, 1)), d1 = gl::mul(a.n_field, gl::sub(gl::mul(a.g, x), 1));
+    const uint64_t inv01 = gl::inv(gl::mul(d0, d1));
+    Consumer yc;
+    yc.alpha0 = Fp(a.alpha0);
+    yc.alpha1 = Fp(a.alpha1);
+    yc.acc0 = Fp(0);
+    yc.acc1 = Fp(0);
+    yc.z_last = Fp(gl::sub(x, a.g_inv));
+    yc.lagrange_first = Fp(gl::mul(a.zh[zi], gl::mul(inv01, d1)));
+    yc.lagrange_last = Fp(gl::mul(a.zh[zi], gl::mul(inv01, d0)));
+    const Row lv{a.trace_lde, a.L, r}, nv{a.trace_lde, a.L, r_next};
+    Air::eval(lv, nv, yc);
+
+    const DevTables& d = a.d;
+    // eval_permutation_checks (permutation.rs:302-360)
+    if (a.num_perm_zs > 0) {
+        for (int i = 0; i < a.num_perm_zs; ++i) yc.constraint_first_row(Fp(a.zs_lde[(size_t)i * a.L + r]) - air::one());
+        for (int i = 0; i < d.nperm_batches; ++i) {
+            const DevPermBatch b = d.perm_batches[i];
+            Fp lhs(1), rhs(1);
+            for (int q = 0; q < b.inst_cnt; ++q) {
+                const DevPermInst in = d.perm_insts[b.inst_off + q];
+                Fp l(0), rr(0), beta(in.beta);
+                for (int p = in.pair_cnt - 1; p >= 0; --p) {  // ReducingFactor::reduce_ext
+                    l = l * beta + lv[d.perm_pairs[2 * (in.pair_off + p)]];
+                    rr = rr * beta + lv[d.perm_pairs[2 * (in.pair_off + p) + 1]];
+                }
+                lhs *= l + Fp(in.gamma);
+                rhs *= rr + Fp(in.gamma);
+            }
+            Fp zl(a.zs_lde[(size_t)i * a.L + r]), zn(a.zs_lde[(size_t)i * a.L + r_next]);
+            yc.constraint(zn * rhs - zl * lhs);
+        }
+    }
+    // eval_cross_table_lookup_checks (cross_table_lookup.rs:380-419)
+    for (int i = 0; i < d.nctl; ++i) {
+        const DevCtl c = d.ctls[i];
+        Fp local_z(a.zs_lde[(size_t)(a.num_perm_zs + i) * a.L + r]), next_z(a.zs_lde[(size_t)(a.num_perm_zs + i) * a.L + r_next]);
+        Fp lf = c.filter >= 0 ? eval_lc(d, c.filter, a.trace_lde, a.L, r) : air::one();
+        Fp nf = c.filter >= 0 ? eval_lc(d, c.filter, a.trace_lde, a.L, r_next) : air::one();
+        Fp lc = ctl_combine(d, c, a.trace_lde, a.L, r), nc = ctl_combine(d, c, a.trace_lde, a.L, r_next);
+        // select(filter, x) = filter * x + 1 - filter
+        yc.constraint_first_row(local_z - (lf * lc + air::one() - lf));
+        yc.constraint_transition(next_z - local_z * (nf * nc + air::one() - nf));
+    }
+    a.out[r] = gl::mul(yc.acc0.v, a.zh_inv[zi]);
+    a.out[size + r] = gl::mul(yc.acc1.v, a.zh_inv[zi]);
+}
+
+static void launch_quotient(ola_ctx* ctx, int table_id, const QuotArgs& a) {
+    const size_t size = (size_t)1 << (a.log_n + a.qdb);
+    const unsigned blocks = (unsigned)((size + 127) / 128);
+    Launch lz(ctx, "quotient");
+    switch (table_id) {
+        case T_CMP: quotient_kernel<air::Cmp><<<blocks, 128, 0, ctx->stream>>>(a); break;
+        case T_RANGECHECK: quotient_kernel<air::RangeCheck><<<blocks, 128, 0, ctx->stream>>>(a); break;
+        default: throw Error(OLA_ERR_INVALID_ARG, "no constraint kernel for table " + std::to_string(table_id));
+    }
+}
+
+// any non-zero in data[first, last) of each column -> flag
+__global__ void nonzero_kernel(const uint64_t* __restrict__ data, size_t col_stride, size_t first, size_t last, int* flag) {
+    size_t i = first + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= last) return;
+    if (data[(size_t)blockIdx.y * col_stride + i] != 0) atomicOr(flag, 1);
+}
+
+// ---- openings: partial Horner sums of every coefficient column at an extension point -------------------------
+static constexpr int EV_RUN = 16, EV_THREADS = 256, EV_CHUNK = EV_RUN * EV_THREADS;
+struct EvParams {
+    gl::ext2 z;
+    gl::ext2 zr[8];  // z^(RUN * 2^k)
+};
+__global__ void __launch_bounds__(EV_THREADS) eval_partial_kernel(const uint64_t* __restrict__ coeffs, size_t n, EvParams p, uint64_t* __restrict__ partial /* [ncols][nchunks][2] */,
+                                                               size_t nchunks) {
+    __shared__ gl::ext2 sh[EV_THREADS];
+    const uint64_t* c = coeffs + (size_t)blockIdx.y * n;
+    const int t = threadIdx.x;
+    size_t start = (size_t)blockIdx.x * EV_CHUNK + (size_t)t * EV_RUN;
+    gl::ext2 acc = gl::make2(0, 0);
+    for (int k = EV_RUN - 1; k >= 0; --k) {
+        size_t j = start + k;
+        uint64_t v = j < n ? c[j] : 0;
+        acc = gl::mul(acc, p.z);
+        acc.c0 = gl::add(acc.c0, v);
+    }
+    sh[t] = acc;
+    __syncthreads();
+    for (int k = 0; (1 << k) < EV_THREADS; ++k) {
+        gl::ext2 v = sh[t];
+        if ((t & ((2 << k) - 1)) == 0) v = gl::add(v, gl::mul(p.zr[k], sh[t + (1 << k)]));
+        __syncthreads();
+        sh[t] = v;
+        __syncthreads();
+    }
+    if (t == 0) {
+        size_t o = ((size_t)blockIdx.y * nchunks + blockIdx.x) * 2;
+        partial[o] = sh[0].c0;
+        partial[o + 1] = sh[0].c1;
+    }
+}
+
+static std::vector<E> eval_batch_at(ola_ctx* ctx, const ola_batch* b, size_t first_col, size_t ncols, E z) {
+    const size_t n = (size_t)1 << b->log_n;
+    std::vector<E> out;
+    if (!ncols) return out;
+    const size_t nchunks = (n + EV_CHUNK - 1) / EV_CHUNK;
+    EvParams p;
+    p.z = z;
+    E zr = gl::pow(z, (uint64_t)EV_RUN);
+    for (int k = 0; k < 8; ++k) {
+        p.zr[k] = zr;
+        zr = gl::mul(zr, zr);
+    }
+    uint64_t* d_part = ctx_scratch(ctx, ncols * nchunks * 2);
+    {
+        Launch lz(ctx, "openings_eval");
+        eval_partial_kernel<<<dim3((unsigned)nchunks, (unsigned)ncols), EV_THREADS, 0, ctx->stream>>>(b->d_coeffs + first_col * n, n, p, d_part, nchunks);
+    }
+    check_launch("eval_partial_kernel");
+    std::vector<uint64_t> h(ncols * nchunks * 2);
+    OLA_CUDA(cudaMemcpyAsync(h.data(), d_part, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+    const E zc = gl::pow(z, (uint64_t)EV_CHUNK);
+    for (size_t c = 0; c < ncols; ++c) {
+        E acc = gl::make2(0, 0);
+        for (size_t s = nchunks; s-- > 0;) acc = gl::add(gl::mul(acc, zc), gl::make2(h[(c * nchunks + s) * 2], h[(c * nchunks + s) * 2 + 1]));
+        out.push_back(acc);
+    }
+    return out;
+}
+
+// ---- host-side descriptor builder --------------------------------------------------------------------------
+struct CtlInstance {  // one Z column of a table (CtlZData, cross_table_lookup.rs:196-202)
+    Challenge ch;
+    const TableWithColumns* twc;
+};
+struct DescBuilder {
+    std::vector<DevLc> lcs;
+    std::vector<int> lc_col;
+    std::vector<uint64_t> lc_coef;
+    std::vector<DevCtl> ctls;
+    std::vector<DevPermInst> insts;
+    std::vector<DevPermBatch> batches;
+    std::vector<int> pairs;
+    int add_lc(const Column& c) {
+        DevLc l;
+        l.off = (int)lc_col.size();
+        l.cnt = (int)c.lc.size();
+        l.constant = gl::canon(c.constant);
+        for (auto& t : c.lc) {
+            lc_col.push_back(t.first);
+            lc_coef.push_back(gl::canon(t.second));
+        }
+        lcs.push_back(l);
+        return (int)lcs.size() - 1;
+    }
+    void add_ctl(const CtlInstance& ci) {
+        DevCtl c;
+        c.col_off = (int)lcs.size();
+        c.col_cnt = (int)ci.twc->columns.size();
+        for (auto& col : ci.twc->columns) add_lc(col);
+        c.filter = ci.twc->has_filter ? add_lc(ci.twc->filter) : -1;
+        c.beta = ci.ch.beta;
+        c.gamma = ci.ch.gamma;
+        ctls.push_back(c);
+    }
+};
+struct DevDesc {
+    uint64_t* mem = nullptr;
+    DevTables t{};
+    ~DevDesc() {
+        if (mem) cudaFree(mem);
+    }
+    void upload(ola_ctx* ctx, const DescBuilder& b) {
+        auto a8 = [](size_t bytes) { return (bytes + 7) / 8; };
+        size_t o_lcs = 0, o_col = o_lcs + a8(b.lcs.size() * sizeof(DevLc)), o_coef = o_col + a8(b.lc_col.size() * 4),
+               o_ctl = o_coef + b.lc_coef.size(), o_inst = o_ctl + a8(b.ctls.size() * sizeof(DevCtl)),
+               o_bat = o_inst + a8(b.insts.size() * sizeof(DevPermInst)), o_pair = o_bat + a8(b.batches.size() * sizeof(DevPermBatch)),
+               total = o_pair + a8(b.pairs.size() * 4) + 1;
+        std::vector<uint64_t> h(total, 0);
+        memcpy(&h[o_lcs], b.lcs.data(), b.lcs.size() * sizeof(DevLc));
+        memcpy(&h[o_col], b.lc_col.data(), b.lc_col.size() * 4);
+        memcpy(&h[o_coef], b.lc_coef.data(), b.lc_coef.size() * 8);
+        memcpy(&h[o_ctl], b.ctls.data(), b.ctls.size() * sizeof(DevCtl));
+        memcpy(&h[o_inst], b.insts.data(), b.insts.size() * sizeof(DevPermInst));
+        memcpy(&h[o_bat], b.batches.data(), b.batches.size() * sizeof(DevPermBatch));
+        memcpy(&h[o_pair], b.pairs.data(), b.pairs.size() * 4);
+        dev_alloc(&mem, total);
+        OLA_CUDA(cudaMemcpyAsync(mem, h.data(), total * 8, cudaMemcpyHostToDevice, ctx->stream));
+        OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+        t.lcs = (const DevLc*)(mem + o_lcs);
+        t.lc_col = (const int*)(mem + o_col);
+        t.lc_coef = mem + o_coef;
+        t.ctls = (const DevCtl*)(mem + o_ctl);
+        t.nctl = (int)b.ctls.size();
+        t.perm_insts = (const DevPermInst*)(mem + o_inst);
+        t.perm_batches = (const DevPermBatch*)(mem + o_bat);
+        t.perm_pairs = (const int*)(mem + o_pair);
+        t.nperm_batches = (int)b.batches.size();
+    }
+};
+
+static void prefix_products(ola_ctx* ctx, uint64_t* d_data, size_t ncols, size_t n, bool exclusive) {
+    if (!ncols) return;
+    const size_t nchunks = (n + SC_CHUNK - 1) / SC_CHUNK;
+    uint64_t* d_chunk = ctx_scratch(ctx, ncols * nchunks);
+    {
+        Launch lz(ctx, "scan_chunks");
+        scan_chunk_kernel<<<dim3((unsigned)nchunks, (unsigned)ncols), SC_THREADS, 0, ctx->stream>>>(d_data, n, d_chunk, nchunks);
+    }
+    {
+        Launch lz(ctx, "scan_carry");
+        scan_carry_kernel<<<(unsigned)((ncols + 63) / 64), 64, 0, ctx->stream>>>(d_chunk, nchunks, ncols);
+    }
+    {
+        Launch lz(ctx, "scan_emit");
+        scan_emit_kernel<<<dim3((unsigned)nchunks, (unsigned)ncols), SC_THREADS, 0, ctx->stream>>>(d_data, n, d_chunk, nchunks, exclusive ? 1 : 0);
+    }
+    check_launch("prefix_products");
+}
+
+struct BatchHolder {  // RAII for ola_batch
+    ola_batch* b = nullptr;
+    BatchHolder() {}
+    ~BatchHolder() { reset(); }
+    void reset() {
+        if (b) {
+            batch_release(b);
+            delete b;
+            b = nullptr;
+        }
+    }
+    BatchHolder(const BatchHolder&) = delete;
+    BatchHolder& operator=(const BatchHolder&) = delete;
+};
+struct DevBuf {
+    uint64_t* p = nullptr;
+    DevBuf() {}
+    explicit DevBuf(size_t n) { dev_alloc(&p, n); }
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+
+static Cap batch_cap(ola_ctx* ctx, const ola_batch* b) {
+    Cap c((size_t)1 << Config::cap_height);
+    batch_get_cap(ctx, b, (uint64_t*)c.data());
+    return c;
+}
+
+// prove_single_table (prover.rs:330-567)
+static StarkProof prove_single_table(ola_ctx* ctx, const TableInfo& t, const Config& cfg, const uint64_t* d_trace, uint32_t degree_bits,
+                                     const ola_batch* trace_commit, const std::vector<CtlInstance>& ctl, Challenger& ch) {
+    const size_t n = (size_t)1 << degree_bits;
+    const std::vector<uint32_t> arities = fri_arities(degree_bits);
+    uint32_t total_ar = 0;
+    for (auto a : arities) total_ar += a;
+    OLA_CHECK(total_ar <= degree_bits + Config::rate_bits - Config::cap_height, OLA_ERR_INVALID_ARG, "FRI total reduction arity is too large.");
+    ch.compact();
+
+    // permutation challenges and instances (get_n_grand_product_challenge_sets, get_permutation_batches)
+    DescBuilder db;
+    std::vector<std::vector<Challenge>> perm_sets;
+    if (!t.permutation_pairs.empty()) {
+        for (int s = 0; s < t.permutation_batch_size(); ++s) {
+            std::vector<Challenge> set;
+            for (uint32_t k = 0; k < Config::num_challenges; ++k) {
+                F b = ch.get_challenge();
+                F g = ch.get_challenge();
+                set.push_back({b, g});
+            }
+            perm_sets.push_back(set);
+        }
+        std::vector<std::pair<const PermutationPair*, int>> all;
+        for (auto& p : t.permutation_pairs)
+            for (uint32_t c = 0; c < Config::num_challenges; ++c) all.push_back({&p, (int)c});
+        const size_t bs = (size_t)t.permutation_batch_size();
+        for (size_t s = 0; s < all.size(); s += bs) {
+            DevPermBatch b;
+            b.inst_off = (int)db.insts.size();
+            b.inst_cnt = 0;
+            for (size_t i = 0; i < bs && s + i < all.size(); ++i) {
+                DevPermInst in;
+                in.pair_off = (int)db.pairs.size() / 2;
+                in.pair_cnt = (int)all[s + i].first->column_pairs.size();
+                for (auto& cp : all[s + i].first->column_pairs) {
+                    db.pairs.push_back(cp.first);
+                    db.pairs.push_back(cp.second);
+                }
+                in.beta = perm_sets[i][all[s + i].second].beta;
+                in.gamma = perm_sets[i][all[s + i].second].gamma;
+                db.insts.push_back(in);
+                b.inst_cnt++;
+            }
+            db.batches.push_back(b);
+        }
+    }
+    for (auto& ci : ctl) db.add_ctl(ci);
+    const size_t num_perm_zs = db.batches.size();
+    const size_t nzs = num_perm_zs + ctl.size();
+    OLA_CHECK(nzs > 0, OLA_ERR_INVALID_ARG, "No CTL?");
+    DevDesc desc;
+    desc.upload(ctx, db);
+
+    // Z columns: values then prefix products
+    DevBuf d_zs(nzs * n), d_err(1);
+    OLA_CUDA(cudaMemsetAsync(d_err.p, 0, 8, ctx->stream));
+    if (num_perm_zs) {
+        {
+            Launch lz(ctx, "perm_values");
+            perm_values_kernel<<<dim3((unsigned)((n + 127) / 128), (unsigned)num_perm_zs), 128, 0, ctx->stream>>>(desc.t, d_trace, n, d_zs.p);
+        }
+        check_launch("perm_values_kernel");
+        prefix_products(ctx, d_zs.p, num_perm_zs, n, true);
+    }
+    if (!ctl.empty()) {
+        {
+            Launch lz(ctx, "ctl_values");
+            ctl_values_kernel<<<dim3((unsigned)((n + 127) / 128), (unsigned)ctl.size()), 128, 0, ctx->stream>>>(desc.t, d_trace, n, d_zs.p + num_perm_zs * n, (int*)d_err.p);
+        }
+        check_launch("ctl_values_kernel");
+        prefix_products(ctx, d_zs.p + num_perm_zs * n, ctl.size(), n, false);
+        int herr = 0;
+        OLA_CUDA(cudaMemcpyAsync(&herr, d_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+        OLA_CHECK(herr == 0, OLA_ERR_INVALID_ARG, "Non-binary filter?");
+    }
+    BatchHolder zs_commit;
+    zs_commit.b = batch_commit(ctx, d_zs.p, true, nzs, degree_bits, false, Config::rate_bits, Config::cap_height);
+    StarkProof proof;
+    proof.trace_cap = batch_cap(ctx, trace_commit);
+    proof.zs_cap = batch_cap(ctx, zs_commit.b);
+    ch.observe_cap(proof.zs_cap);
+    const F alpha0 = ch.get_challenge(), alpha1 = ch.get_challenge();
+
+    // ---- compute_quotient_polys
+    const int qdf = t.quotient_degree_factor();
+    int qdb = 0;
+    while ((1 << qdb) < qdf) qdb++;
+    OLA_CHECK((uint32_t)qdb <= Config::rate_bits, OLA_ERR_INVALID_ARG, "Having constraints of degree higher than the rate is not supported yet.");
+    const size_t qsize = n << qdb, L = n << Config::rate_bits;
+    DevBuf d_q(2 * qsize);
+    {
+        QuotArgs a;
+        memset(&a, 0, sizeof(a));
+        a.trace_lde = trace_commit->d_lde;
+        a.zs_lde = zs_commit.b->d_lde;
+        a.L = L;
+        a.log_n = (int)degree_bits;
+        a.qdb = qdb;
+        a.alpha0 = alpha0;
+        a.alpha1 = alpha1;
+        a.g = gl::root_of_unity((int)degree_bits);
+        a.g_inv = gl::inv(a.g);
+        a.n_field = (uint64_t)n % gl::P;
+        const F g_pow_n = gl::pow(gl::GEN, (uint64_t)n);  // ZeroPolyOnCoset::new (zero_poly_coset.rs:19-33)
+        F w = gl::root_of_unity(qdb), xx = 1;
+        for (int i = 0; i < (1 << qdb); ++i) {
+            a.zh[i] = gl::sub(gl::mul(g_pow_n, xx), 1);
+            a.zh_inv[i] = gl::inv(a.zh[i]);
+            xx = gl::mul(xx, w);
+        }
+        a.pw = ctx->tw.pw[0];
+        a.out = d_q.p;
+        a.d = desc.t;
+        a.num_perm_zs = (int)num_perm_zs;
+        launch_quotient(ctx, t.id, a);
+        check_launch("quotient_kernel");
+    }
+    // values at bit-reversed positions on 7*H_{n 2^qdb} -> natural coefficients (coset_ifft, prover.rs:700-704)
+    ntt::inverse_from_leaf_order(ctx, d_q.p, qsize, 2, (int)degree_bits + qdb, gl::GEN);
+    if (cfg.check_quotient_degree && (size_t)qdf * n < qsize) {
+        OLA_CUDA(cudaMemsetAsync(d_err.p, 0, 8, ctx->stream));
+        size_t cnt = qsize - (size_t)qdf * n;
+        nonzero_kernel<<<dim3((unsigned)((cnt + 255) / 256), 2), 256, 0, ctx->stream>>>(d_q.p, qsize, (size_t)qdf * n, qsize, (int*)d_err.p);
+        count_launch(ctx);
+        int herr = 0;
+        OLA_CUDA(cudaMemcpyAsync(&herr, d_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (herr) throw Error(OLA_ERR_QUOTIENT_DEGREE, std::string(t.name) + ": Quotient has failed, the vanishing polynomial is not divisible by Z_H");
+    }
+    // all_quotient_chunks: [alpha][chunk] (prover.rs:463-478)
+    DevBuf d_chunks((size_t)2 * qdf * n);
+    for (int j = 0; j < 2; ++j)
+        OLA_CUDA(cudaMemcpyAsync(d_chunks.p + (size_t)j * qdf * n, d_q.p + (size_t)j * qsize, (size_t)qdf * n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    BatchHolder q_commit;
+    q_commit.b = batch_commit(ctx, d_chunks.p, true, (size_t)2 * qdf, degree_bits, true, Config::rate_bits, Config::cap_height);
+    proof.quotient_cap = batch_cap(ctx, q_commit.b);
+    ch.observe_cap(proof.quotient_cap);
+
+    const E zeta = ch.get_ext();
+    const F g = gl::root_of_unity((int)degree_bits);
+    {
+        E zp = zeta;
+        for (uint32_t k = 0; k < degree_bits; ++k) zp = gl::sqr(zp);
+        if (gl::eq(zp, gl::make2(1, 0))) throw Error(OLA_ERR_ZETA_IN_SUBGROUP, "Opening point is in the subgroup.");
+    }
+    // ---- StarkOpeningSet::new
+    const E zeta_next = gl::mul(zeta, g);
+    const F g_inv = gl::inv(g);
+    OpeningSet& os = proof.openings;
+    os.local_values = eval_batch_at(ctx, trace_commit, 0, t.columns, zeta);
+    os.next_values = eval_batch_at(ctx, trace_commit, 0, t.columns, zeta_next);
+    os.zs = eval_batch_at(ctx, zs_commit.b, 0, nzs, zeta);
+    os.zs_next = eval_batch_at(ctx, zs_commit.b, 0, nzs, zeta_next);
+    for (auto& e : eval_batch_at(ctx, zs_commit.b, num_perm_zs, nzs - num_perm_zs, gl::make2(g_inv, 0))) os.ctl_zs_last.push_back(e.c0);
+    os.quotient = eval_batch_at(ctx, q_commit.b, 0, (size_t)2 * qdf, zeta);
+    // observe_openings(to_fri_openings) (proof.rs:248-283)
+    for (auto& v : os.local_values) ch.observe_ext(v);
+    for (auto& v : os.zs) ch.observe_ext(v);
+    for (auto& v : os.quotient) ch.observe_ext(v);
+    for (auto& v : os.next_values) ch.observe_ext(v);
+    for (auto& v : os.zs_next) ch.observe_ext(v);
+    for (auto& v : os.ctl_zs_last) ch.observe_ext(gl::make2(v, 0));
+    // ---- fri_instance (stark.rs:87-150) and opening proof
+    fri::Instance inst;
+    fri::BatchInfo b0, b1, b2;
+    b0.point = zeta;
+    for (int c = 0; c < t.columns; ++c) b0.polys.push_back({0, c});
+    for (size_t c = 0; c < nzs; ++c) b0.polys.push_back({1, (int)c});
+    for (int c = 0; c < 2 * qdf; ++c) b0.polys.push_back({2, c});
+    b1.point = zeta_next;
+    for (int c = 0; c < t.columns; ++c) b1.polys.push_back({0, c});
+    for (size_t c = 0; c < nzs; ++c) b1.polys.push_back({1, (int)c});
+    b2.point = gl::make2(g_inv, 0);
+    for (size_t c = num_perm_zs; c < nzs; ++c) b2.polys.push_back({1, (int)c});
+    inst.batches = {b0, b1, b2};
+    proof.fri = fri::prove_openings(ctx, inst, {trace_commit, zs_commit.b, q_commit.b}, ch, degree_bits);
+    return proof;
+}
+
+// prove_with_traces (prover.rs:79-327) + Buffer::write_all_proof (serialization.rs:377-393)
+std::vector<uint8_t> prove_all(ola_ctx* ctx, const std::vector<int>& table_ids, const std::vector<const uint64_t*>& traces, bool on_device,
+                               const std::vector<uint32_t>& log_ns, const Config& cfg) {
+    const System sys = make_system(table_ids);
+    const size_t T = sys.tables.size();
+    OLA_CHECK(traces.size() == T && log_ns.size() == T, OLA_ERR_INVALID_ARG, "one trace per table");
+    std::vector<std::unique_ptr<DevBuf>> d_vals(T);
+    std::vector<std::unique_ptr<BatchHolder>> commits(T);
+    Challenger ch;
+    for (size_t i = 0; i < T; ++i) {
+        const size_t n = (size_t)1 << log_ns[i], cnt = n * sys.tables[i].columns;
+        OLA_CHECK(log_ns[i] + Config::rate_bits <= 32, OLA_ERR_INVALID_ARG, "trace too long for the field's two-adicity");
+        d_vals[i].reset(new DevBuf(cnt));
+        OLA_CUDA(cudaMemcpyAsync(d_vals[i]->p, traces[i], cnt * 8, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+        canon_copy(ctx, d_vals[i]->p, d_vals[i]->p, cnt);  // the Z kernels read these values with canonical-input arithmetic
+        commits[i].reset(new BatchHolder());
+        commits[i]->b = batch_commit(ctx, d_vals[i]->p, true, sys.tables[i].columns, log_ns[i], false, Config::rate_bits, Config::cap_height);
+    }
+    for (size_t i = 0; i < T; ++i) ch.observe_cap(batch_cap(ctx, commits[i]->b));
+    // cross_table_lookup_data: challenges, then Z instances per table in registry order
+    std::vector<Challenge> ctl_ch;
+    for (uint32_t k = 0; k < Config::num_challenges; ++k) {
+        F b = ch.get_challenge();
+        F g = ch.get_challenge();
+        ctl_ch.push_back({b, g});
+    }
+    std::vector<std::vector<CtlInstance>> per_table(T);
+    for (auto& ctl : sys.ctls)
+        for (auto& c : ctl_ch) {
+            for (auto& lt : ctl.looking) per_table[lt.table].push_back({c, &lt});
+            per_table[ctl.looked.table].push_back({c, &ctl.looked});
+        }
+    Writer w;
+    w.u32((uint32_t)T);
+    for (size_t i = 0; i < T; ++i) {
+        StarkProof p = prove_single_table(ctx, sys.tables[i], cfg, d_vals[i]->p, log_ns[i], commits[i]->b, per_table[i], ch);
+        w.proof(p);
+        commits[i].reset();  // tables are proven sequentially: free this table's HBM before the next
+        d_vals[i].reset();
+    }
+    w.field_vec(sys.compress_challenges);
+    return w.buf;
+}
+
+}  // namespace stark
+}  // namespace ola

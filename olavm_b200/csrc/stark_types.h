@@ -1,0 +1,262 @@
+// Host-side description of the proving system: tables, cross-table lookups, config, proof structures,
+// transcript and wire format.  Mirrors (B200 side of) circuits/src/stark/{config,stark,cross_table_lookup,
+// permutation,proof,serialization}.rs and plonky2/plonky2/src/iop/challenger.rs.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "gl.cuh"
+#include "poseidon.cuh"
+
+namespace ola {
+namespace stark {
+
+typedef uint64_t F;
+typedef gl::ext2 E;
+
+struct Hash {
+    F e[4];
+};
+typedef std::vector<Hash> Cap;
+
+// StarkConfig::standard_fast_config (circuits/src/stark/config.rs:18-30) -- the only configuration the
+// reference ever instantiates; compile-time here.
+struct Config {
+    static constexpr uint32_t num_challenges = 2;
+    static constexpr uint32_t rate_bits = 3;
+    static constexpr uint32_t cap_height = 4;
+    static constexpr uint32_t pow_bits = 16;
+    static constexpr uint32_t arity_bits = 4;
+    static constexpr uint32_t final_poly_bits = 5;
+    static constexpr uint32_t num_queries = 28;
+    bool check_quotient_degree = true;  // false: "pipeline parity" mode for non-satisfying synthetic traces
+};
+
+// FriReductionStrategy::ConstantArityBits(4, 5) (fri/reduction_strategies.rs:40-53)
+inline std::vector<uint32_t> fri_arities(uint32_t degree_bits) {
+    std::vector<uint32_t> r;
+    uint32_t d = degree_bits;
+    while (d > Config::final_poly_bits && d + Config::rate_bits - Config::arity_bits >= Config::cap_height) {
+        r.push_back(Config::arity_bits);
+        d -= Config::arity_bits;
+    }
+    return r;
+}
+
+// ---- Fiat-Shamir transcript (iop/challenger.rs:18-162): host side, exact and sequential ----
+struct Challenger {
+    F state[12];
+    std::vector<F> in, out;
+    Challenger() { memset(state, 0, sizeof(state)); }
+    void duplexing() {
+        for (size_t i = 0; i < in.size(); i++) state[i] = in[i];
+        in.clear();
+        poseidon::permute_host(state);
+        out.assign(state, state + 8);
+    }
+    void observe(F x) {
+        out.clear();
+        in.push_back(gl::canon(x));
+        if (in.size() == 8) duplexing();
+    }
+    void observe_ext(E x) {
+        observe(x.c0);
+        observe(x.c1);
+    }
+    void observe_cap(const Cap& c) {
+        for (auto& h : c)
+            for (int i = 0; i < 4; i++) observe(h.e[i]);
+    }
+    F get_challenge() {
+        if (!in.empty() || out.empty()) duplexing();
+        F r = out.back();  // pops from the END (challenger.rs:97-99)
+        out.pop_back();
+        return r;
+    }
+    E get_ext() {
+        F a = get_challenge();
+        F b = get_challenge();
+        return gl::make2(a, b);
+    }
+    Hash get_hash() {
+        Hash h;
+        for (int i = 0; i < 4; i++) h.e[i] = get_challenge();
+        return h;
+    }
+    void compact() {
+        if (!in.empty()) duplexing();
+        out.clear();
+    }
+};
+
+// ---- cross-table lookups (cross_table_lookup.rs:29-170) ----
+struct Column {
+    std::vector<std::pair<int, F>> lc;
+    F constant = 0;
+    static Column single(int c) {
+        Column r;
+        r.lc.push_back({c, 1});
+        return r;
+    }
+    static Column linear(std::vector<std::pair<int, F>> v, F k = 0) {
+        Column r;
+        r.lc = std::move(v);
+        r.constant = k;
+        return r;
+    }
+};
+inline std::vector<Column> singles(std::initializer_list<int> cs) {
+    std::vector<Column> r;
+    for (int c : cs) r.push_back(Column::single(c));
+    return r;
+}
+struct TableWithColumns {
+    int table = 0;
+    std::vector<Column> columns;
+    bool has_filter = false;
+    Column filter;
+};
+inline TableWithColumns twc(int table, std::vector<Column> cols, Column filter) {
+    TableWithColumns t;
+    t.table = table;
+    t.columns = std::move(cols);
+    t.has_filter = true;
+    t.filter = std::move(filter);
+    return t;
+}
+struct CrossTableLookup {
+    std::vector<TableWithColumns> looking;
+    TableWithColumns looked;
+};
+struct Challenge {
+    F beta, gamma;
+};
+struct PermutationPair {
+    std::vector<std::pair<int, int>> column_pairs;
+};
+
+// reference Table enum (ola_stark.rs:104-119)
+enum TableId { T_CPU = 0, T_MEMORY, T_BITWISE, T_CMP, T_RANGECHECK, T_POSEIDON, T_POSEIDON_CHUNK, T_STORAGE, T_TAPE, T_SCCALL, T_PROGRAM, T_PROG_CHUNK, T_NUM };
+
+struct TableInfo {
+    int id = -1;
+    const char* name = "";
+    int columns = 0;
+    int constraint_degree = 0;
+    std::vector<PermutationPair> permutation_pairs;
+    int quotient_degree_factor() const { return constraint_degree - 1 > 1 ? constraint_degree - 1 : 1; }
+    int permutation_batch_size() const { return quotient_degree_factor(); }
+    int num_permutation_batches() const {
+        int inst = (int)permutation_pairs.size() * (int)Config::num_challenges;
+        int bs = permutation_batch_size();
+        return (inst + bs - 1) / bs;
+    }
+};
+struct System {
+    std::vector<TableInfo> tables;
+    std::vector<CrossTableLookup> ctls;  // table fields = positions inside `tables`
+    std::vector<F> compress_challenges;
+};
+// registry (air/registry.cuh): metadata for the tables whose constraint kernels are compiled in
+bool table_available(int id);
+TableInfo table_info(int id);
+std::vector<CrossTableLookup> all_cross_table_lookups();
+System make_system(const std::vector<int>& ids);
+
+// ---- proof structures (proof.rs:108-119, :181-196; fri/proof.rs:105-114) ----
+struct FriQueryStep {
+    std::vector<E> evals;
+    std::vector<Hash> siblings;
+};
+struct FriQueryRound {
+    std::vector<std::pair<std::vector<F>, std::vector<Hash>>> initial;
+    std::vector<FriQueryStep> steps;
+};
+struct FriProof {
+    std::vector<Cap> commit_caps;
+    std::vector<FriQueryRound> rounds;
+    std::vector<E> final_poly;
+    F pow_witness = 0;
+};
+struct OpeningSet {
+    std::vector<E> local_values, next_values, zs, zs_next;
+    std::vector<F> ctl_zs_last;
+    std::vector<E> quotient;
+};
+struct StarkProof {
+    Cap trace_cap, zs_cap, quotient_cap;
+    OpeningSet openings;
+    FriProof fri;
+};
+
+// ---- wire format: Buffer::write_all_proof (serialization.rs:349-393): LE canonical u64, u32 length prefixes,
+// u8 Merkle-path length; PublicValues are not written ----
+struct Writer {
+    std::vector<uint8_t> buf;
+    void u8(uint8_t x) { buf.push_back(x); }
+    void u32(uint32_t x) {
+        for (int i = 0; i < 4; i++) buf.push_back((uint8_t)(x >> (8 * i)));
+    }
+    void field(F x) {
+        x = gl::canon(x);
+        for (int i = 0; i < 8; i++) buf.push_back((uint8_t)(x >> (8 * i)));
+    }
+    void ext(E x) {
+        field(x.c0);
+        field(x.c1);
+    }
+    void field_vec(const std::vector<F>& v) {
+        u32((uint32_t)v.size());
+        for (F x : v) field(x);
+    }
+    void ext_vec(const std::vector<E>& v) {
+        u32((uint32_t)v.size());
+        for (E x : v) ext(x);
+    }
+    void hash(const Hash& h) {
+        for (int i = 0; i < 4; i++) field(h.e[i]);
+    }
+    void cap(const Cap& c) {
+        u32((uint32_t)c.size());
+        for (auto& h : c) hash(h);
+    }
+    void merkle_proof(const std::vector<Hash>& s) {
+        u8((uint8_t)s.size());
+        for (auto& h : s) hash(h);
+    }
+    void proof(const StarkProof& p) {
+        cap(p.trace_cap);
+        cap(p.zs_cap);
+        cap(p.quotient_cap);
+        ext_vec(p.openings.local_values);
+        ext_vec(p.openings.next_values);
+        ext_vec(p.openings.zs);
+        ext_vec(p.openings.zs_next);
+        field_vec(p.openings.ctl_zs_last);
+        ext_vec(p.openings.quotient);
+        u32((uint32_t)p.fri.commit_caps.size());
+        for (auto& c : p.fri.commit_caps) cap(c);
+        u32((uint32_t)p.fri.rounds.size());
+        for (auto& r : p.fri.rounds) {
+            u32((uint32_t)r.initial.size());
+            for (auto& ip : r.initial) {
+                field_vec(ip.first);
+                merkle_proof(ip.second);
+            }
+            u32((uint32_t)r.steps.size());
+            for (auto& s : r.steps) {
+                ext_vec(s.evals);
+                merkle_proof(s.siblings);
+            }
+        }
+        ext_vec(p.fri.final_poly);
+        field(p.fri.pow_witness);
+    }
+};
+
+}  // namespace stark
+}  // namespace ola

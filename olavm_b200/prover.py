@@ -1,0 +1,37 @@
+"""Mirror of `circuits::stark::prover::prove_with_traces` (circuits/src/stark/prover.rs:79-85) followed by
+`Buffer::write_all_proof` (circuits/src/stark/serialization.rs:377-393)."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+TABLES = dict(cpu=0, memory=1, bitwise=2, cmp=3, rangecheck=4, poseidon=5, poseidon_chunk=6, storage_access=7, tape=8, sccall=9,
+              program=10, prog_chunk=11)
+
+
+def table_columns(ctx, table_id):
+    """S::COLUMNS of a table, or -1 if its constraint kernel is not in this build."""
+    return int(ctx._lib.ola_table_columns(int(table_id)))
+
+
+def prove_with_traces(ctx, table_ids, trace_poly_values, check_quotient_degree=True, max_bytes=1 << 26):
+    """-> proof bytes (AllProof in the reference's wire format).
+
+    table_ids: ids of the reference `Table` enum, ascending; trace_poly_values[i]: [columns_i, 2^k_i] uint64
+    (Vec<PolynomialValues<F>> column-major).  Raises OlaError(OLA_ERR_QUOTIENT_DEGREE) where the reference panics with
+    "Quotient has failed, ..." and OlaError(OLA_ERR_INVALID_ARG, "Non-binary filter?") like partial_products' assert."""
+    k = len(table_ids)
+    trs = [np.ascontiguousarray(t, dtype=np.uint64) for t in trace_poly_values]
+    for t in trs:
+        n = t.shape[1]
+        if n == 0 or n & (n - 1):
+            raise ValueError("trace length must be a power of 2")
+    ids = (ctypes.c_int * k)(*[int(x) for x in table_ids])
+    ptrs = (ctypes.c_void_p * k)(*[t.ctypes.data for t in trs])
+    logs = (ctypes.c_uint32 * k)(*[int(t.shape[1]).bit_length() - 1 for t in trs])
+    out = np.empty(max_bytes, dtype=np.uint8)
+    n = ctypes.c_size_t(0)
+    ctx.check(ctx._lib.ola_prove(ctx.handle, ids, k, ptrs, 0, logs, 1 if check_quotient_degree else 0, out.ctypes.data_as(ctypes.c_void_p),
+                                 max_bytes, ctypes.byref(n)))
+    return out[: n.value].tobytes()

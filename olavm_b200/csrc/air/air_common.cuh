@@ -3,6 +3,7 @@
 // One thread evaluates one LDE row (P::WIDTH == 1 semantics).
 #pragma once
 #include "../gl.cuh"
+#include "cpu_air.h"
 
 namespace ola {
 namespace air {
@@ -24,6 +25,10 @@ struct Fp {
     }
 };
 __device__ __forceinline__ Fp fp(uint64_t k) { return Fp(k); }  // k must be canonical
+template <>
+__device__ __forceinline__ Fp kc<Fp>(uint64_t k) {
+    return Fp(k);
+}
 __device__ __forceinline__ Fp one() { return Fp(1); }
 
 // one LDE row of a column-major batch: element c at base[c*stride + r]

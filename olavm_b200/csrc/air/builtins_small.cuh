@@ -8,6 +8,13 @@
 namespace ola {
 namespace air {
 
+// CpuStark: circuits/src/cpu/cpu_stark.rs:871-946 (shared transcription in cpu_air.h)
+struct Cpu {
+    enum { COLUMNS = cpu::NUM_CPU_COLS };
+    static constexpr int CONSTRAINT_DEGREE = 7;
+    static __device__ __forceinline__ void eval(const Row& lv, const Row& nv, Consumer& yc) { cpu::eval<Fp, Row, Consumer>(lv, nv, yc); }
+};
+
 struct Cmp {
     enum { OP0 = 0, OP1, GTE, ABS_DIFF, ABS_DIFF_INV, FILTER_LOOKING_RC, COLUMNS };
     static constexpr int CONSTRAINT_DEGREE = 3;

@@ -1,0 +1,141 @@
+// The cross-table-lookup registry (all_cross_table_lookups, circuits/src/stark/ola_stark.rs:121-143 and the
+// ctl_* builders :146-642), in registry order, as DATA shared by the product (device descriptors) and the oracle.
+// It is generic over a policy `Pol` that supplies each side's Column / TableWithColumns / CrossTableLookup types:
+//   Pol::Column, Pol::Twc, Pol::Ctl{looking, looked, has_looked}, Pol::single(c), Pol::linear({(c,k)..}, const),
+//   Pol::twc(table, columns, filter)
+// A side whose table has no constraint kernel in this build yet is omitted (has_looked = false / lookers skipped) and
+// listed in the comment of its entry; such a CTL is "partial" and only usable in pipeline-parity runs.
+//
+// Column definitions cited per entry: circuits/src/cpu/cpu_stark.rs:17-330 (CPU sides),
+// builtins/cmp/cmp_stark.rs:88-108, builtins/rangecheck/rangecheck_stark.rs:111-150.
+#pragma once
+#include <utility>
+#include <vector>
+
+#include "cpu_air.h"
+
+namespace ola {
+namespace air {
+
+enum RegTable { RT_CPU = 0, RT_MEMORY, RT_BITWISE, RT_CMP, RT_RANGECHECK, RT_POSEIDON, RT_POSEIDON_CHUNK, RT_STORAGE, RT_TAPE, RT_SCCALL, RT_PROGRAM, RT_PROG_CHUNK };
+
+template <class Pol>
+std::vector<typename Pol::Ctl> build_ctl_registry() {
+    using namespace cpu;
+    typedef typename Pol::Column Col;
+    typedef typename Pol::Twc Twc;
+    typedef typename Pol::Ctl Ctl;
+    typedef std::vector<Col> Cols;
+    const uint64_t NEG_ONE = 0xFFFFFFFF00000000ULL;
+    auto S = [](std::initializer_list<int> cs) { Cols v; for (int c : cs) v.push_back(Pol::single(c)); return v; };
+    auto sum = [](std::initializer_list<int> cs) { std::vector<std::pair<int, uint64_t>> v; for (int c : cs) v.push_back({c, 1}); return Pol::linear(v, 0); };
+    auto plus = [](int c, uint64_t k) { return Pol::linear({{c, 1}}, k); };
+    auto partial = [](std::vector<Twc> looking) { Ctl c; c.looking = std::move(looking); c.has_looked = false; return c; };
+    auto full = [](std::vector<Twc> looking, Twc looked) { Ctl c; c.looking = std::move(looking); c.looked = std::move(looked); c.has_looked = true; return c; };
+    // rangecheck / cmp column ids (builtins/rangecheck/columns.rs:25-39, builtins/cmp/columns.rs:16-22)
+    const int RC_CPU_FILTER = 0, RC_CMP_FILTER = 3, RC_VAL = 4;
+    const int CMP_OP0 = 0, CMP_OP1 = 1, CMP_GTE = 2, CMP_ABS_DIFF = 3, CMP_FILTER = 5;
+
+    std::vector<Ctl> v;
+    // 1. ctl_cpu_memory (:146-200): 16 CPU lookers -> Memory [Memory side pending]
+    {
+        std::vector<Twc> l;
+        l.push_back(Pol::twc(RT_CPU, S({COL_TX_IDX, COL_ENV_IDX, COL_CLK, COL_OPCODE, COL_AUX1, COL_DST}), sum({COL_S_MSTORE, COL_S_MLOAD})));
+        l.push_back(Pol::twc(RT_CPU, S({COL_TX_IDX, COL_ENV_IDX, COL_CLK, COL_OPCODE, COL_OP0, COL_DST}), sum({COL_S_CALL, COL_S_RET})));
+        l.push_back(Pol::twc(RT_CPU, S({COL_TX_IDX, COL_ENV_IDX, COL_CLK, COL_OPCODE, COL_AUX0, COL_AUX1}), sum({COL_S_CALL, COL_S_RET})));
+        l.push_back(Pol::twc(RT_CPU, S({COL_TX_IDX, COL_ENV_IDX, COL_CLK, COL_OPCODE, COL_AUX0, COL_AUX1}), Pol::single(COL_FILTER_TAPE_LOOKING)));
+        const int sc_addr[4] = {COL_OP0, COL_DST, COL_AUX0, COL_AUX1};
+        for (int i = 0; i < 4; ++i)
+            l.push_back(Pol::twc(RT_CPU, S({COL_TX_IDX, COL_ENV_IDX, COL_CLK, COL_OPCODE, sc_addr[i], COL_ADDR_CODE + i}), Pol::single(IS_SCCALL_EXT_LINE)));
+        for (int i = 0; i < 4; ++i)
+            l.push_back(Pol::twc(RT_CPU, S({COL_TX_IDX, COL_ENV_IDX, COL_CLK, COL_OPCODE, COL_S_OP0 + i, COL_S_OP0 + 4 + i}), Pol::single(COL_IS_STORAGE_EXT_LINE)));
+        for (int i = 0; i < 4; ++i)
+            l.push_back(Pol::twc(RT_CPU, S({COL_TX_IDX, COL_ENV_IDX, COL_CLK, COL_OPCODE, COL_S_OP1 + i, COL_S_OP1 + 4 + i}), Pol::single(COL_IS_STORAGE_EXT_LINE)));
+        v.push_back(partial(l));
+    }
+    // 2. ctl_memory_rc_sort, 3. ctl_memory_rc_region (:202-231): Memory -> RangeCheck [Memory side pending; RangeCheck looked side kept]
+    v.push_back(full({}, Pol::twc(RT_RANGECHECK, S({RC_VAL}), Pol::single(1 /* MEMORY_SORT_FILTER */))));
+    v.push_back(full({}, Pol::twc(RT_RANGECHECK, S({RC_VAL}), Pol::single(2 /* MEMORY_REGION_FILTER */))));
+    // 4. ctl_bitwise_cpu (:251-265): CPU -> Bitwise [Bitwise side pending]
+    v.push_back(partial({Pol::twc(RT_CPU, S({COL_OPCODE, COL_OP0, COL_OP1, COL_DST}), Pol::single(COL_S_BITWISE))}));
+    // 5. ctl_cmp_cpu (:268-281)
+    v.push_back(full({Pol::twc(RT_CPU, S({COL_OP0, COL_OP1, COL_DST}), Pol::single(COL_S_GTE))},
+                     Pol::twc(RT_CMP, S({CMP_OP0, CMP_OP1, CMP_GTE}), Pol::single(CMP_FILTER))));
+    // 6. ctl_cmp_rangecheck (:283-296)
+    v.push_back(full({Pol::twc(RT_RANGECHECK, S({RC_VAL}), Pol::single(RC_CMP_FILTER))}, Pol::twc(RT_CMP, S({CMP_ABS_DIFF}), Pol::single(CMP_FILTER))));
+    // 7. ctl_rangecheck_cpu (:299-312)
+    v.push_back(full({Pol::twc(RT_CPU, S({COL_OP1}), Pol::single(COL_S_RC))}, Pol::twc(RT_RANGECHECK, S({RC_VAL}), Pol::single(RC_CPU_FILTER))));
+    // 8. ctl_cpu_poseidon_chunk (:314-328): CPU -> PoseidonChunk [pending]
+    v.push_back(partial({Pol::twc(RT_CPU, S({COL_TX_IDX, COL_ENV_IDX, COL_CLK, COL_OPCODE, COL_OP0, COL_OP1, COL_DST}), Pol::single(COL_S_PSDN))}));
+    // 9. ctl_poseidon_chunk_mem, 10. ctl_chunk_poseidon: no CPU side [pending entirely]
+    // 11. ctl_cpu_poseidon_tree_key (:415-429): CPU -> Poseidon [pending]
+    {
+        Cols c = S({COL_ADDR_STORAGE, COL_ADDR_STORAGE + 1, COL_ADDR_STORAGE + 2, COL_ADDR_STORAGE + 3, COL_S_OP0 + 4, COL_S_OP0 + 5, COL_S_OP0 + 6, COL_S_OP0 + 7});
+        for (int i = 0; i < 4; ++i) c.push_back(Pol::linear({}, 0));  // Column::zero()
+        for (int i = 0; i < 4; ++i) c.push_back(Pol::single(COL_S_DST + i));
+        v.push_back(partial({Pol::twc(RT_CPU, c, Pol::single(COL_IS_STORAGE_EXT_LINE))}));
+    }
+    // 12. ctl_cpu_storage_access (:372-386): CPU -> StorageAccess [pending]
+    v.push_back(partial({Pol::twc(RT_CPU, S({COL_IDX_STORAGE, COL_S_SSTORE, COL_S_DST, COL_S_DST + 1, COL_S_DST + 2, COL_S_DST + 3, COL_S_OP1 + 4, COL_S_OP1 + 5, COL_S_OP1 + 6, COL_S_OP1 + 7}),
+                                  Pol::single(COL_IS_STORAGE_EXT_LINE))}));
+    // 13. ctl_storage_access_poseidon: no CPU side [pending entirely]
+    // 14. ctl_cpu_tape (:431-474): 13 CPU lookers -> Tape [pending]
+    {
+        std::vector<Twc> l;
+        l.push_back(Pol::twc(RT_CPU, S({COL_TX_IDX, COL_OPCODE, COL_S_OP0, COL_AUX1}), Pol::single(COL_FILTER_TAPE_LOOKING)));
+        for (int i = 0; i < 4; ++i) {
+            Cols c = S({COL_TX_IDX, COL_OPCODE});
+            c.push_back(plus(COL_TP, (uint64_t)i));
+            c.push_back(Pol::single(COL_S_OP0 + i));
+            l.push_back(Pol::twc(RT_CPU, c, Pol::single(IS_SCCALL_EXT_LINE)));
+        }
+        for (int i = 0; i < 4; ++i) {
+            Cols c = S({COL_TX_IDX, COL_OPCODE});
+            c.push_back(plus(COL_TP, (uint64_t)(4 + i)));
+            c.push_back(Pol::single(COL_ADDR_CODE + i));
+            l.push_back(Pol::twc(RT_CPU, c, Pol::single(IS_SCCALL_EXT_LINE)));
+        }
+        for (int i = 0; i < 4; ++i) {
+            Cols c = S({COL_TX_IDX, COL_OPCODE});
+            c.push_back(plus(COL_TP, (uint64_t)(8 + i)));
+            c.push_back(Pol::single(COL_ADDR_STORAGE + i));
+            l.push_back(Pol::twc(RT_CPU, c, Pol::single(IS_SCCALL_EXT_LINE)));
+        }
+        v.push_back(partial(l));
+    }
+    // 15. ctl_cpu_sccall (:476-490): CPU -> SCCall [pending]
+    {
+        Cols c = S({COL_TX_IDX, COL_ENV_IDX});
+        for (int i = 0; i < 8; ++i) c.push_back(Pol::single(COL_S_OP0 + i));
+        c.push_back(Pol::single(COL_CLK));
+        c.push_back(Pol::single(COL_OP1_IMM));
+        for (int i = 0; i < REGISTER_NUM; ++i) c.push_back(Pol::single(COL_REGS + i));
+        c.push_back(plus(COL_ENV_IDX, 1));
+        v.push_back(partial({Pol::twc(RT_CPU, c, Pol::single(IS_SCCALL_EXT_LINE))}));
+    }
+    // 16. ctl_cpu_sccall_end (:492-506): CPU -> SCCall [pending]
+    {
+        Cols c = S({COL_TX_IDX, COL_ENV_IDX});
+        for (int i = 0; i < 4; ++i) c.push_back(Pol::single(COL_ADDR_STORAGE + i));
+        for (int i = 0; i < 4; ++i) c.push_back(Pol::single(COL_ADDR_CODE + i));
+        c.push_back(Pol::single(COL_CLK));
+        for (int i = 0; i < REGISTER_NUM; ++i) c.push_back(Pol::single(COL_REGS + i));
+        c.push_back(Pol::single(COL_AUX0));
+        c.push_back(Pol::single(COL_AUX1));
+        v.push_back(partial({Pol::twc(RT_CPU, c, Pol::single(COL_FILTER_SCCALL_END))}));
+    }
+    // 17. ctl_cpu_program (:508-528): CPU x2 -> Program [pending]
+    {
+        Cols inst = S({COL_ADDR_CODE, COL_ADDR_CODE + 1, COL_ADDR_CODE + 2, COL_ADDR_CODE + 3, COL_PC, COL_INST});
+        Cols imm = S({COL_ADDR_CODE, COL_ADDR_CODE + 1, COL_ADDR_CODE + 2, COL_ADDR_CODE + 3});
+        imm.push_back(plus(COL_PC, 1));
+        imm.push_back(Pol::single(COL_IMM_VAL));
+        v.push_back(partial({Pol::twc(RT_CPU, inst, Pol::linear({{COL_IS_EXT_LINE, NEG_ONE}, {COL_IS_PADDING, NEG_ONE}}, 1)),
+                             Pol::twc(RT_CPU, imm, Pol::single(COL_FILTER_LOOKING_PROG_IMM))}));
+    }
+    // 18. ctl_prog_chunk_prog, 19. ctl_prog_chunk_storage: no CPU side [pending entirely]
+    return v;
+}
+
+}  // namespace air
+}  // namespace ola

@@ -3,16 +3,22 @@
 #pragma once
 #include "../stark_types.h"
 #include "builtins_small.cuh"
+#include "ctl_registry.h"
 
 namespace ola {
 namespace stark {
 
-inline bool table_available(int id) { return id == T_CMP || id == T_RANGECHECK; }
+inline bool table_available(int id) { return id == T_CPU || id == T_CMP || id == T_RANGECHECK; }
 
 inline TableInfo table_info(int id) {
     TableInfo t;
     t.id = id;
     switch (id) {
+        case T_CPU:
+            t.name = "CpuStark";
+            t.columns = air::Cpu::COLUMNS;
+            t.constraint_degree = air::Cpu::CONSTRAINT_DEGREE;
+            break;
         case T_CMP:
             t.name = "CmpStark";
             t.columns = air::Cmp::COLUMNS;
@@ -34,15 +40,18 @@ inline TableInfo table_info(int id) {
     return t;
 }
 
-inline std::vector<CrossTableLookup> all_cross_table_lookups() {
-    std::vector<CrossTableLookup> v;
-    // ctl_cmp_rangecheck (ola_stark.rs:282-296): looking RangeCheck(VAL | CMP_FILTER), looked Cmp(abs_diff | filter_looking_rc)
-    v.push_back({{twc(T_RANGECHECK, singles({air::RangeCheck::VAL}), Column::single(air::RangeCheck::CMP_FILTER))},
-                 twc(T_CMP, singles({air::Cmp::ABS_DIFF}), Column::single(air::Cmp::FILTER_LOOKING_RC))});
-    return v;
-}
+struct RegPolicy {
+    typedef stark::Column Column;
+    typedef TableWithColumns Twc;
+    typedef CrossTableLookup Ctl;
+    static Column single(int c) { return Column::single(c); }
+    static Column linear(std::vector<std::pair<int, uint64_t>> v, uint64_t k) { return Column::linear(std::move(v), k); }
+    static Twc twc(int table, std::vector<Column> cols, Column filter) { return stark::twc(table, std::move(cols), std::move(filter)); }
+};
+inline std::vector<CrossTableLookup> all_cross_table_lookups() { return air::build_ctl_registry<RegPolicy>(); }
 
-// An ordered subset of the 12 tables (proof order = enum order) plus every registered CTL inside the subset.
+// An ordered subset of the 12 tables (proof order = enum order) plus every registered CTL side whose table is in
+// the subset.  A CTL that loses a side is "partial" (complete = false): its Z columns are still proven.
 inline System make_system(const std::vector<int>& ids) {
     System s;
     std::vector<int> pos(T_NUM, -1);
@@ -52,12 +61,24 @@ inline System make_system(const std::vector<int>& ids) {
         s.tables.push_back(table_info(ids[i]));
     }
     for (auto ctl : all_cross_table_lookups()) {
-        bool ok = pos[ctl.looked.table] >= 0;
-        for (auto& l : ctl.looking) ok = ok && pos[l.table] >= 0;
-        if (!ok) continue;
-        for (auto& l : ctl.looking) l.table = pos[l.table];
-        ctl.looked.table = pos[ctl.looked.table];
-        s.ctls.push_back(ctl);
+        CrossTableLookup out;
+        out.complete = ctl.has_looked;
+        for (auto& l : ctl.looking) {
+            if (pos[l.table] >= 0) {
+                l.table = pos[l.table];
+                out.looking.push_back(l);
+            } else {
+                out.complete = false;
+            }
+        }
+        out.has_looked = ctl.has_looked && pos[ctl.looked.table] >= 0;
+        out.complete = out.complete && out.has_looked;
+        if (out.has_looked) {
+            out.looked = ctl.looked;
+            out.looked.table = pos[ctl.looked.table];
+        }
+        if (out.looking.empty() && !out.has_looked) continue;
+        s.ctls.push_back(out);
     }
     s.compress_challenges.assign(ids.size(), 0);
     return s;

@@ -258,6 +258,7 @@ static void launch_quotient(ola_ctx* ctx, int table_id, const QuotArgs& a) {
     const unsigned blocks = (unsigned)((size + 127) / 128);
     Launch lz(ctx, "quotient");
     switch (table_id) {
+        case T_CPU: quotient_kernel<air::Cpu><<<blocks, 128, 0, ctx->stream>>>(a); break;
         case T_CMP: quotient_kernel<air::Cmp><<<blocks, 128, 0, ctx->stream>>>(a); break;
         case T_RANGECHECK: quotient_kernel<air::RangeCheck><<<blocks, 128, 0, ctx->stream>>>(a); break;
         default: throw Error(OLA_ERR_INVALID_ARG, "no constraint kernel for table " + std::to_string(table_id));
@@ -668,7 +669,7 @@ std::vector<uint8_t> prove_all(ola_ctx* ctx, const std::vector<int>& table_ids, 
     for (auto& ctl : sys.ctls)
         for (auto& c : ctl_ch) {
             for (auto& lt : ctl.looking) per_table[lt.table].push_back({c, &lt});
-            per_table[ctl.looked.table].push_back({c, &ctl.looked});
+            if (ctl.has_looked) per_table[ctl.looked.table].push_back({c, &ctl.looked});
         }
     Writer w;
     w.u32((uint32_t)T);

@@ -131,6 +131,8 @@ inline TableWithColumns twc(int table, std::vector<Column> cols, Column filter) 
 struct CrossTableLookup {
     std::vector<TableWithColumns> looking;
     TableWithColumns looked;
+    bool has_looked = true;
+    bool complete = true;  // every side of the registered CTL is inside the system
 };
 struct Challenge {
     F beta, gamma;

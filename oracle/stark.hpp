@@ -48,7 +48,7 @@ inline std::vector<Column> singles(const std::vector<int>& cs) { std::vector<Col
 struct TableWithColumns { int table; std::vector<Column> columns; bool has_filter = false; Column filter; };
 inline TableWithColumns twc(int table, std::vector<Column> cols, Column filter) { TableWithColumns t; t.table = table; t.columns = std::move(cols); t.has_filter = true; t.filter = std::move(filter); return t; }
 inline TableWithColumns twc_nofilter(int table, std::vector<Column> cols) { TableWithColumns t; t.table = table; t.columns = std::move(cols); return t; }
-struct CrossTableLookup { std::vector<TableWithColumns> looking; TableWithColumns looked; };
+struct CrossTableLookup { std::vector<TableWithColumns> looking; TableWithColumns looked; bool has_looked = true; bool complete = true; /* every side of the registered CTL is inside the system */ };
 
 struct Challenge { F beta, gamma; };
 struct CtlZ { VF z; Challenge ch; std::vector<Column> columns; bool has_filter; Column filter; };
@@ -330,6 +330,7 @@ inline std::string prove_with_traces(const System& sys, const Config& cfg, const
                 if (!e.empty()) return e;
                 per_table[lt.table].push_back(std::move(z));
             }
+            if (!ctl.has_looked) continue;
             CtlZ z{{}, c, ctl.looked.columns, ctl.looked.has_filter, ctl.looked.filter};
             std::string e = partial_products(traces[ctl.looked.table], ns[ctl.looked.table], ctl.looked, c, z.z);
             if (!e.empty()) return e;
@@ -444,7 +445,7 @@ inline std::string verify_all(const System& sys, const Config& cfg, const AllPro
                 return true;
             };
             for (auto& lt : ctl.looking) if (!push(lt)) return "ctl shape";
-            if (!push(ctl.looked)) return "ctl shape";
+            if (ctl.has_looked && !push(ctl.looked)) return "ctl shape";
         }
     for (size_t i = 0; i < T; i++) {
         const Table& t = sys.tables[i];
@@ -528,7 +529,9 @@ inline std::string verify_all(const System& sys, const Config& cfg, const AllPro
         for (uint32_t k = 0; k < cfg.num_challenges; k++) {
             F prod = 1;
             for (auto& lt : ctl.looking) prod = gl_mul(prod, ap.proofs[lt.table].openings.ctl_zs_last[cur[lt.table]++]);
+            if (!ctl.has_looked) continue;
             F looked = ap.proofs[ctl.looked.table].openings.ctl_zs_last[cur[ctl.looked.table]++];
+            if (!ctl.complete) continue; /* partial CTL (a side's table is outside this system): nothing to compare */
             if (prod != looked) return "Cross-table lookup verification failed.";
         }
     return "";

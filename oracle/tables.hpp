@@ -11,6 +11,9 @@
 #ifndef ORC_TABLES_HPP
 #define ORC_TABLES_HPP
 #include "stark.hpp"
+/* The CPU table's constraint body and the CTL registry are a single transcription shared with the product
+ * (olavm_b200/csrc/air/{cpu_air,ctl_registry}.h); see the note at the top of cpu_air.h and DESIGN.md section 4. */
+#include "../olavm_b200/csrc/air/ctl_registry.h"
 
 namespace orc {
 
@@ -57,6 +60,22 @@ void eval(const P<O>* lv, const P<O>* nv, Consumer<O>& yc) {
 }
 }  // namespace rangecheck
 
+}  // namespace orc
+namespace ola {
+namespace air {
+template <> inline orc::P<orc::FOps> kc<orc::P<orc::FOps>>(uint64_t k) { return orc::P<orc::FOps>::c(k); }
+template <> inline orc::P<orc::EOps> kc<orc::P<orc::EOps>>(uint64_t k) { return orc::P<orc::EOps>::c(k); }
+}  // namespace air
+}  // namespace ola
+namespace orc {
+/* ---- Cpu (cpu_stark.rs:871-946, shared transcription) ---- */
+namespace cpu_t {
+template <class O>
+void eval(const P<O>* lv, const P<O>* nv, Consumer<O>& yc) {
+    ola::air::cpu::eval<P<O>, const P<O>*, Consumer<O>>(lv, nv, yc);
+}
+}  // namespace cpu_t
+
 template <class EvalB, class EvalE>
 Table make_table(const char* name, int cols, int degree, EvalB eb, EvalE ee, std::vector<PermutationPair> pp = {}) {
     Table t;
@@ -70,10 +89,11 @@ Table make_table(const char* name, int cols, int degree, EvalB eb, EvalE ee, std
 }
 #define ORC_TABLE(name, ns, cols, degree, ...) make_table(name, cols, degree, ns::eval<FOps>, ns::eval<EOps>, ##__VA_ARGS__)
 
-inline bool table_available(int id) { return id == T_CMP || id == T_RANGECHECK; }
+inline bool table_available(int id) { return id == T_CPU || id == T_CMP || id == T_RANGECHECK; }
 
 inline Table table_by_id(int id) {
     switch (id) {
+        case T_CPU: return ORC_TABLE("CpuStark", cpu_t, ola::air::cpu::NUM_CPU_COLS, 7);
         case T_CMP: return ORC_TABLE("CmpStark", cmp, cmp::NUM, 3);
         case T_RANGECHECK:
             return ORC_TABLE("RangeCheckStark", rangecheck, rangecheck::NUM, 3,
@@ -85,29 +105,35 @@ inline Table table_by_id(int id) {
     }
 }
 
-/* all_cross_table_lookups (ola_stark.rs:121-143), in registry order; entries whose tables are not all restated
- * yet are tagged and skipped by make_system for sub-systems. */
-inline std::vector<CrossTableLookup> all_cross_table_lookups() {
-    std::vector<CrossTableLookup> v;
-    /* ctl_cmp_rangecheck (ola_stark.rs:282-296): looking = RangeCheck(VAL | CMP_FILTER), looked = Cmp(abs_diff | filter) */
-    v.push_back({{twc(T_RANGECHECK, singles({rangecheck::VAL}), Column::single(rangecheck::CMP_FILTER))},
-                 twc(T_CMP, singles({cmp::ABS_DIFF}), Column::single(cmp::FILTER_LOOKING_RC))});
-    return v;
-}
+/* all_cross_table_lookups (ola_stark.rs:121-143) via the shared registry */
+struct RegPolicy {
+    typedef orc::Column Column;
+    typedef TableWithColumns Twc;
+    typedef CrossTableLookup Ctl;
+    static Column single(int c) { return Column::single(c); }
+    static Column linear(std::vector<std::pair<int, uint64_t>> v, uint64_t k) { return Column::linear(std::vector<std::pair<int, F>>(v.begin(), v.end()), k); }
+    static Twc twc(int table, std::vector<Column> cols, Column filter) { return orc::twc(table, std::move(cols), std::move(filter)); }
+};
+inline std::vector<CrossTableLookup> all_cross_table_lookups() { return ola::air::build_ctl_registry<RegPolicy>(); }
 
-/* A proving system = an ordered subset of the 12 tables (proof order = enum order) plus every registered CTL
- * whose tables are all inside the subset (table ids remapped to positions). */
+/* A proving system = an ordered subset of the 12 tables (proof order = enum order) plus every registered CTL side
+ * whose table is inside the subset (table ids remapped to positions).  CTLs losing a side become partial. */
 inline System make_system(const std::vector<int>& ids) {
     System s;
     std::vector<int> pos(T_NUM, -1);
     for (size_t i = 0; i < ids.size(); i++) { pos[ids[i]] = (int)i; s.tables.push_back(table_by_id(ids[i])); }
     for (auto ctl : all_cross_table_lookups()) {
-        bool ok = pos[ctl.looked.table] >= 0;
-        for (auto& l : ctl.looking) ok = ok && pos[l.table] >= 0;
-        if (!ok) continue;
-        for (auto& l : ctl.looking) l.table = pos[l.table];
-        ctl.looked.table = pos[ctl.looked.table];
-        s.ctls.push_back(ctl);
+        CrossTableLookup out;
+        out.complete = ctl.has_looked;
+        for (auto& l : ctl.looking) {
+            if (pos[l.table] >= 0) { l.table = pos[l.table]; out.looking.push_back(l); }
+            else out.complete = false;
+        }
+        out.has_looked = ctl.has_looked && pos[ctl.looked.table] >= 0;
+        out.complete = out.complete && out.has_looked;
+        if (out.has_looked) { out.looked = ctl.looked; out.looked.table = pos[ctl.looked.table]; }
+        if (out.looking.empty() && !out.has_looked) continue;
+        s.ctls.push_back(out);
     }
     s.compress_challenges.assign(ids.size(), 0);
     return s;

@@ -58,3 +58,33 @@ def test_non_binary_filter_error(ctx):
     cmp_t[5, 1] = 2
     with pytest.raises(olavm_b200.OlaError, match="Non-binary filter"):
         olavm_b200.prove_with_traces(ctx, [CMP, RC], [cmp_t, rc_t])
+
+
+CPU = 0
+
+
+def test_cpu_table_valid_padding_trace(ctx, orc):
+    cpu_t = tracegen.cpu_padding_trace(5)
+    cmp_t = tracegen.cmp_trace([], 4)
+    rc_t = tracegen.rangecheck_trace([])
+    ref = orc.stark_prove([CPU, CMP, RC], [cpu_t, cmp_t, rc_t])
+    got = olavm_b200.prove_with_traces(ctx, [CPU, CMP, RC], [cpu_t, cmp_t, rc_t])
+    assert got == ref
+    ok, msg = orc.stark_verify([CPU, CMP, RC], got)
+    assert ok, msg
+    bad = cpu_t.copy()
+    bad[74, 3] = 0  # s_end must be 1 on padding rows
+    with pytest.raises(olavm_b200.OlaError, match="Quotient has failed") as e:
+        olavm_b200.prove_with_traces(ctx, [CPU, CMP, RC], [bad, cmp_t, rc_t])
+    assert e.value.code == -5  # OLA_ERR_QUOTIENT_DEGREE
+
+
+@pytest.mark.parametrize("log_n", [4, 8, 11])
+def test_cpu_table_pipeline_parity(ctx, orc, log_n):
+    """The 94-column CPU table with its 39 CTL instances (78 Z columns, 12 quotient chunks) on random columns with
+    binary filters, CPU table alone (every CTL partial): proof bytes equal the oracle's."""
+    rng = np.random.default_rng(1000 + log_n)
+    cpu_t = tracegen.cpu_random_trace(rng, log_n)
+    ref = orc.stark_prove([CPU], [cpu_t], check_degree=False)
+    got = olavm_b200.prove_with_traces(ctx, [CPU], [cpu_t], check_quotient_degree=False)
+    assert got == ref

@@ -69,3 +69,23 @@ def test_non_binary_filter_is_an_error(orc, cmp_rc):
     bad[5, 1] = 2
     with pytest.raises(orc.StarkError, match="Non-binary filter"):
         orc.stark_prove([CMP, RC], [bad, rc_t])
+
+
+CPU = 0
+
+
+def test_cpu_padding_trace_satisfies_the_cpu_air(orc):
+    """All-padding CPU trace (generate_cpu_trace with no steps) + padding-only Cmp + lookup-free RangeCheck: the
+    degree-7 CPU quotient has qdf = 6 < 8, so trim_to_len really checks divisibility (prover.rs:463-473), and the
+    restated verify_proof accepts."""
+    cpu_t = tracegen.cpu_padding_trace(5)
+    cmp_t = tracegen.cmp_trace([], 4)
+    rc_t = tracegen.rangecheck_trace([])
+    proof = orc.stark_prove([CPU, CMP, RC], [cpu_t, cmp_t, rc_t])
+    ok, msg = orc.stark_verify([CPU, CMP, RC], proof)
+    assert ok, msg
+    # breaking one padding invariant (s_end must be 1 on padding rows) makes the quotient non-divisible
+    bad = cpu_t.copy()
+    bad[74, 3] = 0
+    with pytest.raises(orc.StarkError, match="Quotient has failed"):
+        orc.stark_prove([CPU, CMP, RC], [bad, cmp_t, rc_t])

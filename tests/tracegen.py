@@ -72,3 +72,52 @@ def rangecheck_trace(cmp_vals, log_n=16, cpu_vals=(), mem_sort_vals=(), mem_regi
     t[7], t[10] = permuted_cols(t[5], fix)
     t[8], t[11] = permuted_cols(t[6], fix)
     return t
+
+
+def cpu_padding_trace(log_n):
+    """CPU table consisting of padding rows only (generate_cpu_trace with zero steps, generation/cpu.rs:180-208):
+    opcode = inst = END (1 << 20), s_end = is_entry_sc = is_next_line_diff_inst = is_padding = 1, the rest 0."""
+    n = 1 << log_n
+    t = np.zeros((94, n), dtype=np.uint64)
+    t[26] = 1 << 20  # COL_INST
+    t[28] = 1 << 20  # COL_OPCODE
+    t[74] = 1        # COL_S_END
+    t[85] = 1        # COL_IS_ENTRY_SC
+    t[86] = 1        # COL_IS_NEXT_LINE_DIFF_INST
+    t[93] = 1        # COL_IS_PADDING
+    return t
+
+
+def random_binary_filter_trace(rng, ncols, log_n, binary_cols, zero_cols=()):
+    """Random (non-satisfying) columns whose CTL filter columns are bits -- for pipeline-parity runs."""
+    n = 1 << log_n
+    t = rng.integers(0, P, size=(ncols, n), dtype=np.uint64)
+    for c in binary_cols:
+        t[c] = rng.integers(0, 2, size=n)
+    for c in zero_cols:
+        t[c] = 0
+    return t
+
+
+# CPU columns that appear in CTL filters (cpu_stark.rs ctl_filter_*): sums of these must stay in {0, 1}
+CPU_FILTER_COLS = dict(s_mstore=73, s_mload=72, s_call=70, s_ret=71, tape_looking=88, sccall_ext=89, storage_ext=90, s_bitwise=76, s_gte=78,
+                       s_rc=75, s_psdn=79, sccall_end=91, prog_imm=92, is_ext_line=14, is_padding=93)
+
+
+def cpu_random_trace(rng, log_n):
+    """Random CPU-table columns with every CTL filter binary: one-hot over the summed selector groups."""
+    n = 1 << log_n
+    t = rng.integers(0, P, size=(94, n), dtype=np.uint64)
+    f = CPU_FILTER_COLS
+    # {mstore, mload} and {call, ret} are summed by their filters: make each pair one-hot-or-zero
+    for a, b in ((f["s_mstore"], f["s_mload"]), (f["s_call"], f["s_ret"])):
+        pick = rng.integers(0, 3, size=n)
+        t[a] = (pick == 1)
+        t[b] = (pick == 2)
+    for k in ("tape_looking", "sccall_ext", "storage_ext", "s_bitwise", "s_gte", "s_rc", "s_psdn", "sccall_end", "prog_imm"):
+        t[f[k]] = rng.integers(0, 2, size=n)
+    # filter 1 - is_ext_line - is_padding (ctl_filter_with_program_inst) must be binary too
+    pick = rng.integers(0, 3, size=n)
+    t[f["is_ext_line"]] = (pick == 1)
+    t[f["is_padding"]] = (pick == 2)
+    return t

@@ -1,0 +1,31 @@
+#!/usr/bin/env python3
+"""Prove-time benchmark of the CPU table (94 trace + 78 CTL-Z + 12 quotient columns) on a synthetic random trace
+with binary filters, pipeline-parity mode (the trace does not satisfy the AIR; every kernel of the proof runs).
+usage: python tools/bench_prove.py [log_n ...]"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import olavm_b200
+import tracegen
+
+logs = [int(x) for x in sys.argv[1:]] or [16, 18, 20]
+ctx = olavm_b200.Context(0)
+for lg in logs:
+    rng = np.random.default_rng(lg)
+    t = tracegen.cpu_random_trace(rng, lg)
+    olavm_b200.prove_with_traces(ctx, [0], [t[:, : 1 << min(lg, 12)].copy()], check_quotient_degree=False)  # warm-up
+    ctx.profile_begin()
+    t0 = time.perf_counter()
+    proof = olavm_b200.prove_with_traces(ctx, [0], [t], check_quotient_degree=False)
+    dt = time.perf_counter() - t0
+    prof = ctx.profile_end()
+    top = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])
+    print(json.dumps({"log_n": lg, "prove_s": dt, "proof_bytes": len(proof), "kernel_ms_total": sum(v["ms"] for v in prof.values()),
+                      "kernels_ms": {k: round(v["ms"], 2) for k, v in top[:14]}}))

@@ -4,6 +4,7 @@
 #pragma once
 #include "../gl.cuh"
 #include "cpu_air.h"
+#include "mem_air.h"
 
 namespace ola {
 namespace air {
@@ -28,6 +29,10 @@ __device__ __forceinline__ Fp fp(uint64_t k) { return Fp(k); }  // k must be can
 template <>
 __device__ __forceinline__ Fp kc<Fp>(uint64_t k) {
     return Fp(k);
+}
+template <>
+__device__ __forceinline__ bool is_zero<Fp>(const Fp& x) {
+    return x.v == 0;
 }
 __device__ __forceinline__ Fp one() { return Fp(1); }
 

@@ -15,6 +15,13 @@ struct Cpu {
     static __device__ __forceinline__ void eval(const Row& lv, const Row& nv, Consumer& yc) { cpu::eval<Fp, Row, Consumer>(lv, nv, yc); }
 };
 
+// MemoryStark: circuits/src/memory/memory_stark.rs:92-340 (shared transcription in mem_air.h)
+struct Memory {
+    enum { COLUMNS = mem::NUM_MEM_COLS };
+    static constexpr int CONSTRAINT_DEGREE = 8;
+    static __device__ __forceinline__ void eval(const Row& lv, const Row& nv, Consumer& yc) { mem::eval<Fp, Row, Consumer>(lv, nv, yc); }
+};
+
 struct Cmp {
     enum { OP0 = 0, OP1, GTE, ABS_DIFF, ABS_DIFF_INV, FILTER_LOOKING_RC, COLUMNS };
     static constexpr int CONSTRAINT_DEGREE = 3;

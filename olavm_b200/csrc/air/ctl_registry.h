@@ -1,7 +1,7 @@
 // The cross-table-lookup registry (all_cross_table_lookups, circuits/src/stark/ola_stark.rs:121-143 and the
 // ctl_* builders :146-642), in registry order, as DATA shared by the product (device descriptors) and the oracle.
 // It is generic over a policy `Pol` that supplies each side's Column / TableWithColumns / CrossTableLookup types:
-//   Pol::Column, Pol::Twc, Pol::Ctl{looking, looked, has_looked}, Pol::single(c), Pol::linear({(c,k)..}, const),
+//   Pol::Column, Pol::Twc, Pol::Ctl{looking, looked, has_looked, missing_sides}, Pol::single(c), Pol::linear({(c,k)..}, const),
 //   Pol::twc(table, columns, filter)
 // A side whose table has no constraint kernel in this build yet is omitted (has_looked = false / lookers skipped) and
 // listed in the comment of its entry; such a CTL is "partial" and only usable in pipeline-parity runs.
@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "cpu_air.h"
+#include "mem_air.h"
 
 namespace ola {
 namespace air {
@@ -30,14 +31,16 @@ std::vector<typename Pol::Ctl> build_ctl_registry() {
     auto S = [](std::initializer_list<int> cs) { Cols v; for (int c : cs) v.push_back(Pol::single(c)); return v; };
     auto sum = [](std::initializer_list<int> cs) { std::vector<std::pair<int, uint64_t>> v; for (int c : cs) v.push_back({c, 1}); return Pol::linear(v, 0); };
     auto plus = [](int c, uint64_t k) { return Pol::linear({{c, 1}}, k); };
-    auto partial = [](std::vector<Twc> looking) { Ctl c; c.looking = std::move(looking); c.has_looked = false; return c; };
+    auto partial = [](std::vector<Twc> looking) { Ctl c; c.looking = std::move(looking); c.has_looked = false; c.missing_sides = true; return c; };
     auto full = [](std::vector<Twc> looking, Twc looked) { Ctl c; c.looking = std::move(looking); c.looked = std::move(looked); c.has_looked = true; return c; };
     // rangecheck / cmp column ids (builtins/rangecheck/columns.rs:25-39, builtins/cmp/columns.rs:16-22)
     const int RC_CPU_FILTER = 0, RC_CMP_FILTER = 3, RC_VAL = 4;
     const int CMP_OP0 = 0, CMP_OP1 = 1, CMP_GTE = 2, CMP_ABS_DIFF = 3, CMP_FILTER = 5;
 
     std::vector<Ctl> v;
-    // 1. ctl_cpu_memory (:146-200): 16 CPU lookers -> Memory [Memory side pending]
+    // Memory sides: circuits/src/memory/memory_stark.rs:17-75
+    using namespace mem;
+    // 1. ctl_cpu_memory (:146-200): 16 CPU lookers -> Memory(tx, env, clk, op, addr, value | sum of 9 selectors)
     {
         std::vector<Twc> l;
         l.push_back(Pol::twc(RT_CPU, S({COL_TX_IDX, COL_ENV_IDX, COL_CLK, COL_OPCODE, COL_AUX1, COL_DST}), sum({COL_S_MSTORE, COL_S_MLOAD})));
@@ -51,11 +54,15 @@ std::vector<typename Pol::Ctl> build_ctl_registry() {
             l.push_back(Pol::twc(RT_CPU, S({COL_TX_IDX, COL_ENV_IDX, COL_CLK, COL_OPCODE, COL_S_OP0 + i, COL_S_OP0 + 4 + i}), Pol::single(COL_IS_STORAGE_EXT_LINE)));
         for (int i = 0; i < 4; ++i)
             l.push_back(Pol::twc(RT_CPU, S({COL_TX_IDX, COL_ENV_IDX, COL_CLK, COL_OPCODE, COL_S_OP1 + i, COL_S_OP1 + 4 + i}), Pol::single(COL_IS_STORAGE_EXT_LINE)));
-        v.push_back(partial(l));
+        v.push_back(full(l, Pol::twc(RT_MEMORY, S({COL_MEM_TX_IDX, COL_MEM_ENV_IDX, COL_MEM_CLK, COL_MEM_OP, COL_MEM_ADDR, COL_MEM_VALUE}),
+                                     sum({COL_MEM_S_MLOAD, COL_MEM_S_MSTORE, COL_MEM_S_CALL, COL_MEM_S_RET, COL_MEM_S_TLOAD, COL_MEM_S_TSTORE, COL_MEM_S_SCCALL,
+                                          COL_MEM_S_SSTORE, COL_MEM_S_SLOAD}))));
     }
-    // 2. ctl_memory_rc_sort, 3. ctl_memory_rc_region (:202-231): Memory -> RangeCheck [Memory side pending; RangeCheck looked side kept]
-    v.push_back(full({}, Pol::twc(RT_RANGECHECK, S({RC_VAL}), Pol::single(1 /* MEMORY_SORT_FILTER */))));
-    v.push_back(full({}, Pol::twc(RT_RANGECHECK, S({RC_VAL}), Pol::single(2 /* MEMORY_REGION_FILTER */))));
+    // 2. ctl_memory_rc_sort, 3. ctl_memory_rc_region (:202-231): Memory -> RangeCheck
+    v.push_back(full({Pol::twc(RT_MEMORY, S({COL_MEM_RC_VALUE}), Pol::single(COL_MEM_FILTER_LOOKING_RC))},
+                     Pol::twc(RT_RANGECHECK, S({RC_VAL}), Pol::single(1 /* MEMORY_SORT_FILTER */))));
+    v.push_back(full({Pol::twc(RT_MEMORY, S({COL_MEM_DIFF_ADDR_COND}), Pol::single(COL_MEM_FILTER_LOOKING_RC_COND))},
+                     Pol::twc(RT_RANGECHECK, S({RC_VAL}), Pol::single(2 /* MEMORY_REGION_FILTER */))));
     // 4. ctl_bitwise_cpu (:251-265): CPU -> Bitwise [Bitwise side pending]
     v.push_back(partial({Pol::twc(RT_CPU, S({COL_OPCODE, COL_OP0, COL_OP1, COL_DST}), Pol::single(COL_S_BITWISE))}));
     // 5. ctl_cmp_cpu (:268-281)
@@ -67,7 +74,14 @@ std::vector<typename Pol::Ctl> build_ctl_registry() {
     v.push_back(full({Pol::twc(RT_CPU, S({COL_OP1}), Pol::single(COL_S_RC))}, Pol::twc(RT_RANGECHECK, S({RC_VAL}), Pol::single(RC_CPU_FILTER))));
     // 8. ctl_cpu_poseidon_chunk (:314-328): CPU -> PoseidonChunk [pending]
     v.push_back(partial({Pol::twc(RT_CPU, S({COL_TX_IDX, COL_ENV_IDX, COL_CLK, COL_OPCODE, COL_OP0, COL_OP1, COL_DST}), Pol::single(COL_S_PSDN))}));
-    // 9. ctl_poseidon_chunk_mem, 10. ctl_chunk_poseidon: no CPU side [pending entirely]
+    // 9. ctl_poseidon_chunk_mem (:330-356): 12 PoseidonChunk lookers [pending] -> Memory(tx, env, clk, op, addr, value, is_write | s_poseidon)
+    {
+        Ctl c = full({}, Pol::twc(RT_MEMORY, S({COL_MEM_TX_IDX, COL_MEM_ENV_IDX, COL_MEM_CLK, COL_MEM_OP, COL_MEM_ADDR, COL_MEM_VALUE, COL_MEM_IS_WRITE}),
+                                  Pol::single(COL_MEM_S_POSEIDON)));
+        c.missing_sides = true;  // PoseidonChunk lookers not in this build yet
+        v.push_back(c);
+    }
+    // 10. ctl_chunk_poseidon: no CPU/Memory side [pending entirely]
     // 11. ctl_cpu_poseidon_tree_key (:415-429): CPU -> Poseidon [pending]
     {
         Cols c = S({COL_ADDR_STORAGE, COL_ADDR_STORAGE + 1, COL_ADDR_STORAGE + 2, COL_ADDR_STORAGE + 3, COL_S_OP0 + 4, COL_S_OP0 + 5, COL_S_OP0 + 6, COL_S_OP0 + 7});

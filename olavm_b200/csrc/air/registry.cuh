@@ -8,7 +8,7 @@
 namespace ola {
 namespace stark {
 
-inline bool table_available(int id) { return id == T_CPU || id == T_CMP || id == T_RANGECHECK; }
+inline bool table_available(int id) { return id == T_CPU || id == T_MEMORY || id == T_CMP || id == T_RANGECHECK; }
 
 inline TableInfo table_info(int id) {
     TableInfo t;
@@ -18,6 +18,11 @@ inline TableInfo table_info(int id) {
             t.name = "CpuStark";
             t.columns = air::Cpu::COLUMNS;
             t.constraint_degree = air::Cpu::CONSTRAINT_DEGREE;
+            break;
+        case T_MEMORY:
+            t.name = "MemoryStark";
+            t.columns = air::Memory::COLUMNS;
+            t.constraint_degree = air::Memory::CONSTRAINT_DEGREE;
             break;
         case T_CMP:
             t.name = "CmpStark";
@@ -62,7 +67,7 @@ inline System make_system(const std::vector<int>& ids) {
     }
     for (auto ctl : all_cross_table_lookups()) {
         CrossTableLookup out;
-        out.complete = ctl.has_looked;
+        out.complete = ctl.has_looked && !ctl.missing_sides;
         for (auto& l : ctl.looking) {
             if (pos[l.table] >= 0) {
                 l.table = pos[l.table];

@@ -510,8 +510,8 @@ static int tune_threads() {
 static int tune_gmax() {
     static int v = [] {
         const char* e = getenv("OLA_NTT_G");
-        int t = e ? atoi(e) : 4;
-        return (t == 1 || t == 2 || t == 4 || t == 8) ? t : 4;
+        int t = e ? atoi(e) : 2;  // profiles/r01d_ntt_sweep.txt: G = 2, 512 threads is the fastest pair
+        return (t == 1 || t == 2 || t == 4 || t == 8) ? t : 2;
     }();
     return v;
 }

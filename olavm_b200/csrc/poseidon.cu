@@ -12,6 +12,8 @@
 #include "common.h"
 #include "poseidon.cuh"
 
+#include <cstdlib>
+
 namespace ola {
 namespace poseidon {
 
@@ -42,8 +44,8 @@ __global__ void __launch_bounds__(128) permute_kernel(uint64_t* states, size_t n
 }
 
 // hash_no_pad over one row; ROWMAJOR: element (r, c) at base[r*ncols + c]; else at base[c*col_stride + r]
-template <bool ROWMAJOR>
-__global__ void __launch_bounds__(128) hash_rows_kernel(const uint64_t* __restrict__ base, size_t col_stride, size_t nrows,
+template <bool ROWMAJOR, int MINB>
+__global__ void __launch_bounds__(128, MINB) hash_rows_kernel(const uint64_t* __restrict__ base, size_t col_stride, size_t nrows,
                                                        size_t ncols, uint64_t* __restrict__ digests) {
     size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nrows) return;
@@ -91,7 +93,7 @@ void hash_rows_rowmajor(ola_ctx* ctx, const uint64_t* d_rows, size_t nrows, size
     if (!nrows) return;
     {
         Launch lz(ctx, "poseidon_leaves_rowmajor");
-        hash_rows_kernel<true><<<(unsigned)((nrows + 127) / 128), 128, 0, ctx->stream>>>(d_rows, 0, nrows, ncols, d_digests);
+        hash_rows_kernel<true, 4><<<(unsigned)((nrows + 127) / 128), 128, 0, ctx->stream>>>(d_rows, 0, nrows, ncols, d_digests);
     }
     check_launch("hash_rows_kernel<row>");
 }
@@ -99,9 +101,20 @@ void hash_rows_colmajor(ola_ctx* ctx, const uint64_t* d_cols, size_t col_stride,
                         uint64_t* d_digests) {
     if (!nrows) return;
     {
+        // resident CTAs per SM (register cap 128/96/80): occupancy vs spills, tuned on hardware (profiles/)
+        static const int minb = [] {
+            const char* e = getenv("OLA_POSEIDON_MINB");
+            int v = e ? atoi(e) : 5;
+            return (v >= 4 && v <= 6) ? v : 5;
+        }();
+        const unsigned blocks = (unsigned)((nrows + 127) / 128);
         Launch lz(ctx, "poseidon_leaves");
-        hash_rows_kernel<false>
-            <<<(unsigned)((nrows + 127) / 128), 128, 0, ctx->stream>>>(d_cols, col_stride, nrows, ncols, d_digests);
+        if (minb == 4)
+            hash_rows_kernel<false, 4><<<blocks, 128, 0, ctx->stream>>>(d_cols, col_stride, nrows, ncols, d_digests);
+        else if (minb == 5)
+            hash_rows_kernel<false, 5><<<blocks, 128, 0, ctx->stream>>>(d_cols, col_stride, nrows, ncols, d_digests);
+        else
+            hash_rows_kernel<false, 6><<<blocks, 128, 0, ctx->stream>>>(d_cols, col_stride, nrows, ncols, d_digests);
     }
     check_launch("hash_rows_kernel<col>");
 }

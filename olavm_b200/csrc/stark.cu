@@ -259,6 +259,7 @@ static void launch_quotient(ola_ctx* ctx, int table_id, const QuotArgs& a) {
     Launch lz(ctx, "quotient");
     switch (table_id) {
         case T_CPU: quotient_kernel<air::Cpu><<<blocks, 128, 0, ctx->stream>>>(a); break;
+        case T_MEMORY: quotient_kernel<air::Memory><<<blocks, 128, 0, ctx->stream>>>(a); break;
         case T_CMP: quotient_kernel<air::Cmp><<<blocks, 128, 0, ctx->stream>>>(a); break;
         case T_RANGECHECK: quotient_kernel<air::RangeCheck><<<blocks, 128, 0, ctx->stream>>>(a); break;
         default: throw Error(OLA_ERR_INVALID_ARG, "no constraint kernel for table " + std::to_string(table_id));

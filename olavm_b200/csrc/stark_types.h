@@ -132,6 +132,7 @@ struct CrossTableLookup {
     std::vector<TableWithColumns> looking;
     TableWithColumns looked;
     bool has_looked = true;
+    bool missing_sides = false;  // a side's table has no constraint kernel in this build yet
     bool complete = true;  // every side of the registered CTL is inside the system
 };
 struct Challenge {

@@ -48,7 +48,7 @@ inline std::vector<Column> singles(const std::vector<int>& cs) { std::vector<Col
 struct TableWithColumns { int table; std::vector<Column> columns; bool has_filter = false; Column filter; };
 inline TableWithColumns twc(int table, std::vector<Column> cols, Column filter) { TableWithColumns t; t.table = table; t.columns = std::move(cols); t.has_filter = true; t.filter = std::move(filter); return t; }
 inline TableWithColumns twc_nofilter(int table, std::vector<Column> cols) { TableWithColumns t; t.table = table; t.columns = std::move(cols); return t; }
-struct CrossTableLookup { std::vector<TableWithColumns> looking; TableWithColumns looked; bool has_looked = true; bool complete = true; /* every side of the registered CTL is inside the system */ };
+struct CrossTableLookup { std::vector<TableWithColumns> looking; TableWithColumns looked; bool has_looked = true; bool missing_sides = false; /* a side's table has no restatement yet */ bool complete = true; /* every side of the registered CTL is inside the system */ };
 
 struct Challenge { F beta, gamma; };
 struct CtlZ { VF z; Challenge ch; std::vector<Column> columns; bool has_filter; Column filter; };

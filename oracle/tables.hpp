@@ -65,6 +65,8 @@ namespace ola {
 namespace air {
 template <> inline orc::P<orc::FOps> kc<orc::P<orc::FOps>>(uint64_t k) { return orc::P<orc::FOps>::c(k); }
 template <> inline orc::P<orc::EOps> kc<orc::P<orc::EOps>>(uint64_t k) { return orc::P<orc::EOps>::c(k); }
+template <> inline bool is_zero<orc::P<orc::FOps>>(const orc::P<orc::FOps>& x) { return x.v == 0; }
+template <> inline bool is_zero<orc::P<orc::EOps>>(const orc::P<orc::EOps>& x) { return x.v.c0 == 0 && x.v.c1 == 0; }
 }  // namespace air
 }  // namespace ola
 namespace orc {
@@ -75,6 +77,13 @@ void eval(const P<O>* lv, const P<O>* nv, Consumer<O>& yc) {
     ola::air::cpu::eval<P<O>, const P<O>*, Consumer<O>>(lv, nv, yc);
 }
 }  // namespace cpu_t
+/* ---- Memory (memory_stark.rs:92-340, shared transcription) ---- */
+namespace mem_t {
+template <class O>
+void eval(const P<O>* lv, const P<O>* nv, Consumer<O>& yc) {
+    ola::air::mem::eval<P<O>, const P<O>*, Consumer<O>>(lv, nv, yc);
+}
+}  // namespace mem_t
 
 template <class EvalB, class EvalE>
 Table make_table(const char* name, int cols, int degree, EvalB eb, EvalE ee, std::vector<PermutationPair> pp = {}) {
@@ -89,11 +98,12 @@ Table make_table(const char* name, int cols, int degree, EvalB eb, EvalE ee, std
 }
 #define ORC_TABLE(name, ns, cols, degree, ...) make_table(name, cols, degree, ns::eval<FOps>, ns::eval<EOps>, ##__VA_ARGS__)
 
-inline bool table_available(int id) { return id == T_CPU || id == T_CMP || id == T_RANGECHECK; }
+inline bool table_available(int id) { return id == T_CPU || id == T_MEMORY || id == T_CMP || id == T_RANGECHECK; }
 
 inline Table table_by_id(int id) {
     switch (id) {
         case T_CPU: return ORC_TABLE("CpuStark", cpu_t, ola::air::cpu::NUM_CPU_COLS, 7);
+        case T_MEMORY: return ORC_TABLE("MemoryStark", mem_t, ola::air::mem::NUM_MEM_COLS, 8);
         case T_CMP: return ORC_TABLE("CmpStark", cmp, cmp::NUM, 3);
         case T_RANGECHECK:
             return ORC_TABLE("RangeCheckStark", rangecheck, rangecheck::NUM, 3,
@@ -124,7 +134,7 @@ inline System make_system(const std::vector<int>& ids) {
     for (size_t i = 0; i < ids.size(); i++) { pos[ids[i]] = (int)i; s.tables.push_back(table_by_id(ids[i])); }
     for (auto ctl : all_cross_table_lookups()) {
         CrossTableLookup out;
-        out.complete = ctl.has_looked;
+        out.complete = ctl.has_looked && !ctl.missing_sides;
         for (auto& l : ctl.looking) {
             if (pos[l.table] >= 0) { l.table = pos[l.table]; out.looking.push_back(l); }
             else out.complete = false;

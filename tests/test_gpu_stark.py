@@ -29,11 +29,11 @@ def test_cmp_rangecheck_proof_bytes_equal_oracle(ctx, orc, seed, log_cmp):
     assert ok, msg
 
 
-def test_single_table_system(ctx, orc):
-    # a system with one table and no CTL inside it is rejected like the reference's assert (prover.rs:396 "No CTL?")
+def test_single_table_system_has_only_partial_ctls(ctx, orc):
+    # one table alone: every CTL it takes part in loses its other side ("partial"); its Z columns are still proven and
+    # the bytes still match the oracle
     cmp_t, _ = _valid_cmp_rc(1, 5)
-    with pytest.raises(olavm_b200.OlaError):
-        olavm_b200.prove_with_traces(ctx, [CMP], [cmp_t])
+    assert olavm_b200.prove_with_traces(ctx, [CMP], [cmp_t]) == orc.stark_prove([CMP], [cmp_t])
 
 
 def test_pipeline_parity_on_random_traces(ctx, orc):
@@ -88,3 +88,24 @@ def test_cpu_table_pipeline_parity(ctx, orc, log_n):
     ref = orc.stark_prove([CPU], [cpu_t], check_degree=False)
     got = olavm_b200.prove_with_traces(ctx, [CPU], [cpu_t], check_quotient_degree=False)
     assert got == ref
+
+
+MEM = 1
+
+
+def test_cpu_memory_cmp_rangecheck_pipeline_parity(ctx, orc):
+    """Four tables, 7 registered CTLs among them (cpu-memory with its 16 CPU lookers, memory-rc x2, cmp-cpu, cmp-rc,
+    rc-cpu, ...): random columns with binary filters, proof bytes equal the oracle's."""
+    rng = np.random.default_rng(4242)
+    traces = [tracegen.cpu_random_trace(rng, 7), tracegen.memory_random_trace(rng, 6), tracegen.cmp_random_trace(rng, 5),
+              tracegen.rangecheck_random_trace(rng)]
+    ids = [CPU, MEM, CMP, RC]
+    ref = orc.stark_prove(ids, traces, check_degree=False)
+    got = olavm_b200.prove_with_traces(ctx, ids, traces, check_quotient_degree=False)
+    assert got == ref
+
+
+def test_memory_table_alone(ctx, orc):
+    rng = np.random.default_rng(77)
+    t = tracegen.memory_random_trace(rng, 9)
+    assert olavm_b200.prove_with_traces(ctx, [MEM], [t], check_quotient_degree=False) == orc.stark_prove([MEM], [t], check_degree=False)

@@ -121,3 +121,30 @@ def cpu_random_trace(rng, log_n):
     t[f["is_ext_line"]] = (pick == 1)
     t[f["is_padding"]] = (pick == 2)
     return t
+
+
+def memory_random_trace(rng, log_n):
+    """Random Memory-table columns (29) with binary CTL filters: the 11 op selectors one-hot-or-none (the looked filter
+    is the sum of 9 of them, memory_stark.rs:44-57), s_poseidon / filter_looking_rc / filter_looking_rc_cond bits."""
+    n = 1 << log_n
+    t = rng.integers(0, P, size=(29, n), dtype=np.uint64)
+    pick = rng.integers(0, 12, size=n)
+    for k in range(11):
+        t[6 + k] = (pick == k + 1)
+    t[27] = rng.integers(0, 2, size=n)
+    t[28] = rng.integers(0, 2, size=n)
+    return t
+
+
+def cmp_random_trace(rng, log_n):
+    t = rng.integers(0, P, size=(6, 1 << log_n), dtype=np.uint64)
+    t[5] = rng.integers(0, 2, size=1 << log_n)
+    return t
+
+
+def rangecheck_random_trace(rng, log_n=16):
+    n = 1 << log_n
+    t = rng.integers(0, P, size=(12, n), dtype=np.uint64)
+    for c in range(4):
+        t[c] = rng.integers(0, 2, size=n)
+    return t

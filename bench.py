@@ -98,6 +98,30 @@ def cpu_lde(oracle, ncols, log_n, reps=1):
     return 80.0 * n * ncols / best / 1e9, best, os.cpu_count()
 
 
+def prove_cpu_table(ctx, log_n):
+    """Second half of BASELINE.json's metric: wall time of one proof whose CPU table has 2^log_n rows
+    (94 trace + 78 CTL-Z + 12 quotient columns) through the C ABI from a HOST trace.  Synthetic random trace with
+    binary filters, quotient-degree check off ("pipeline parity": no executor exists here to make a satisfying trace);
+    only the CPU table is in the proof (9 of the 12 AIR kernels are not built yet), so every CTL is partial."""
+    import olavm_b200
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import tracegen
+
+    rng = np.random.default_rng(22)
+    t = tracegen.cpu_random_trace(rng, log_n)
+    olavm_b200.prove_with_traces(ctx, [0], [np.ascontiguousarray(t[:, :4096])], check_quotient_degree=False)  # warm-up
+    ctx.profile_begin()
+    t0 = time.perf_counter()
+    proof = olavm_b200.prove_with_traces(ctx, [0], [t], check_quotient_degree=False)
+    dt = time.perf_counter() - t0
+    prof = ctx.profile_end()
+    top = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:8]
+    return {"log_n": log_n, "seconds": dt, "proof_bytes": len(proof), "tables": ["cpu"], "columns": {"trace": 94, "ctl_z": 78, "quotient": 12},
+            "mode": "synthetic random trace, binary filters, quotient-degree check off; host trace in, proof bytes out",
+            "kernel_ms": {k: round(v["ms"], 1) for k, v in top}, "h2d_bytes": int(t.nbytes)}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path (oracle port; the Rust prover cannot be built here: no cargo)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -136,6 +160,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--prove-log-n", type=int, default=22, help="also time one CPU-table proof of 2^k rows (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -145,7 +170,7 @@ def main():
     import torch.distributed as dist
 
     import olavm_b200
-    from olavm_b200 import _lib
+    from olavm_b200 import dist as odist
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -199,11 +224,7 @@ def main():
         ev1.record(stream)
         barrier()
         ms = ev0.elapsed_time(ev1)
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return odist.max_over_ranks(ms, device="cuda")
 
     for _ in range(args.warmup):
         step_resident()
@@ -252,6 +273,8 @@ def main():
                          "note": "64-bit modular butterflies are INT-pipe bound on B200; see DESIGN.md section 5"},
             "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
         }
+        if args.prove_log_n:
+            line["prove_cpu_table"] = prove_cpu_table(ctx, args.prove_log_n)
         if not args.no_cpu_baseline:
             import oracle
 

@@ -139,15 +139,19 @@ int ola_batch_prove_leaf(ola_ctx* ctx, const ola_batch* b, size_t leaf_index, ui
  * F = Goldilocks, D = 2, C = PoseidonGoldilocksConfig and StarkConfig::standard_fast_config() (config.rs:18-30).
  *   table_ids  ntables ids of the reference's `Table` enum (ola_stark.rs:104-119) in ascending order; the proof
  *              covers exactly these tables and every registered cross-table lookup among them.  Passing all 12
- *              ids is `prove_with_traces` itself; ola_table_columns() < 0 means the table's constraint kernel is
- *              not in this build yet.
+ *              ids is `prove_with_traces` itself (ola_table_columns() < 0: unknown table id).
  *   traces[i]  column-major trace of table i: columns_i columns of 2^log_ns[i] u64 (host or device pointers)
+ *   compress_challenges  NULL, or ntables field elements: entry i is table i's compress challenge -- the beta that
+ *              trace generation drew for the Bitwise and Program tables (generation/mod.rs:183-188,
+ *              bitwise_stark.rs:30-38, program_stark.rs:49-58); other entries are ignored and written as 0, like
+ *              AllProof.compress_challenges (prover.rs:307-320).  NULL = all zero.
  *   check_quotient_degree  != 0: fail with OLA_ERR_QUOTIENT_DEGREE where the reference panics (prover.rs:469-473);
  *              == 0: "pipeline parity" mode for synthetic traces that do not satisfy the constraints
  *   proof_out  receives the proof bytes; *proof_len their count (also set when proof_cap is too small).
  * pow_witness is the SMALLEST valid nonce (the reference's rayon find_any returns an arbitrary valid one). */
 int ola_prove(ola_ctx* ctx, const int* table_ids, uint32_t ntables, const uint64_t* const* traces, int on_device,
-              const uint32_t* log_ns, int check_quotient_degree, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+              const uint32_t* log_ns, const uint64_t* compress_challenges, int check_quotient_degree, uint8_t* proof_out,
+              size_t proof_cap, size_t* proof_len);
 /* number of trace columns of a table (S::COLUMNS), or -1 if its constraint kernel is not compiled in */
 int ola_table_columns(int table_id);
 

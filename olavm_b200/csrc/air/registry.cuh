@@ -1,5 +1,5 @@
-// Table registry: metadata (columns, degree, permutation pairs) of every table whose constraint kernel is compiled
-// in, and the cross-table-lookup registry of circuits/src/stark/ola_stark.rs:121-642 restricted to those tables.
+// Table registry: metadata (columns, degree, permutation pairs) of the 12 tables of circuits/src/stark/ola_stark.rs:27-41
+// and the cross-table-lookup registry of ola_stark.rs:121-642.
 #pragma once
 #include "../stark_types.h"
 #include "builtins_small.cuh"
@@ -8,7 +8,7 @@
 namespace ola {
 namespace stark {
 
-inline bool table_available(int id) { return id == T_CPU || id == T_MEMORY || id == T_CMP || id == T_RANGECHECK; }
+inline bool table_available(int id) { return id >= 0 && id < T_NUM; }
 
 inline TableInfo table_info(int id) {
     TableInfo t;
@@ -40,7 +40,40 @@ inline TableInfo table_info(int id) {
                                    PermutationPair{{{R::FIX_RANGE_CHECK_U16, R::FIX_RANGE_CHECK_U16_PERMUTED_HI}}}};
             break;
         }
-        default: throw Error(OLA_ERR_INVALID_ARG, "table " + std::to_string(id) + " has no constraint kernel in this build");
+#define OLA_TABLE_CASE(ID, NAME, AIR)                          \
+    case ID:                                                  \
+        t.name = NAME;                                        \
+        t.columns = air::AIR::COLUMNS;                        \
+        t.constraint_degree = air::AIR::CONSTRAINT_DEGREE;    \
+        break;
+            OLA_TABLE_CASE(T_POSEIDON, "PoseidonStark", Poseidon)
+            OLA_TABLE_CASE(T_POSEIDON_CHUNK, "PoseidonChunkStark", PoseidonChunk)
+            OLA_TABLE_CASE(T_STORAGE, "StorageAccessStark", StorageAccess)
+            OLA_TABLE_CASE(T_TAPE, "TapeStark", Tape)
+            OLA_TABLE_CASE(T_SCCALL, "SCCallStark", SCCall)
+            OLA_TABLE_CASE(T_PROG_CHUNK, "ProgChunkStark", ProgChunk)
+#undef OLA_TABLE_CASE
+        case T_BITWISE: {
+            namespace B = air::bitwise;
+            t.name = "BitwiseStark";
+            t.columns = air::Bitwise::COLUMNS;
+            t.constraint_degree = air::Bitwise::CONSTRAINT_DEGREE;
+            // bitwise_stark.rs:352-363 (only the compress lookups carry a permutation argument)
+            for (int i = 0; i < 4; ++i) t.permutation_pairs.push_back(PermutationPair{{{B::COMPRESS_LIMBS + i, B::COMPRESS_PERMUTED + i}}});
+            for (int i = 0; i < 4; ++i) t.permutation_pairs.push_back(PermutationPair{{{B::FIX_COMPRESS, B::FIX_COMPRESS_PERMUTED + i}}});
+            break;
+        }
+        case T_PROGRAM: {
+            namespace G = air::program;
+            t.name = "ProgramStark";
+            t.columns = air::Program::COLUMNS;
+            t.constraint_degree = air::Program::CONSTRAINT_DEGREE;
+            // program_stark.rs:110-115
+            t.permutation_pairs = {PermutationPair{{{G::COL_PROG_COMP_PROG, G::COL_PROG_COMP_PROG_PERM}}},
+                                   PermutationPair{{{G::COL_PROG_EXEC_COMP_PROG, G::COL_PROG_EXEC_COMP_PROG_PERM}}}};
+            break;
+        }
+        default: throw Error(OLA_ERR_INVALID_ARG, "unknown table id " + std::to_string(id));
     }
     return t;
 }

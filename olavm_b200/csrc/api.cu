@@ -16,6 +16,7 @@ namespace {
 template <typename F>
 int guarded(ola_ctx* ctx, F&& f) {
     try {
+        if (ctx) ola::set_alloc_stream(ctx->stream);
         f();
         return OLA_OK;
     } catch (const ola::Error& e) {
@@ -38,7 +39,7 @@ struct DevBuf {
     uint64_t* p = nullptr;
     explicit DevBuf(size_t n) { ola::dev_alloc(&p, n); }
     ~DevBuf() {
-        if (p) cudaFree(p);
+        if (p) ola::dev_free(p);
     }
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
@@ -99,6 +100,11 @@ int ola_gpu_init(int device, ola_ctx** out) {
     int rc = guarded(ctx, [&] {
         OLA_CUDA(cudaSetDevice(device));
         OLA_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ola::set_alloc_stream(ctx->stream);
+        cudaMemPool_t pool;
+        OLA_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = UINT64_MAX;  // keep freed blocks in the pool until the context is destroyed
+        OLA_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
         ola::poseidon::init_constants();
         ola::ntt::init_twiddles(ctx);
         OLA_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -116,8 +122,15 @@ void ola_gpu_destroy(ola_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     ola::ntt::free_twiddles(ctx);
-    if (ctx->scratch) cudaFree(ctx->scratch);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    ola::set_alloc_stream(ctx->stream);
+    if (ctx->scratch) ola::dev_free(ctx->scratch);
+    if (ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+        cudaStreamDestroy(ctx->stream);
+    }
+    ola::set_alloc_stream(nullptr);
     delete ctx;
 }
 
@@ -170,13 +183,16 @@ int ola_profile_end(ola_ctx* ctx, char* json_out, size_t cap) {
 
 int ola_dev_alloc(ola_ctx* ctx, size_t n_u64, uint64_t** dptr) {
     if (!ctx || !dptr) return OLA_ERR_INVALID_ARG;
-    return guarded(ctx, [&] { ola::dev_alloc(dptr, n_u64); });
+    return guarded(ctx, [&] {
+        ola::dev_alloc(dptr, n_u64);
+        OLA_CUDA(cudaStreamSynchronize(ctx->stream));  // usable from any stream once this returns
+    });
 }
 int ola_dev_free(ola_ctx* ctx, uint64_t* dptr) {
     if (!ctx) return OLA_ERR_INVALID_ARG;
     return guarded(ctx, [&] {
         OLA_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (dptr) OLA_CUDA(cudaFree(dptr));
+        if (dptr) ola::dev_free(dptr);
     });
 }
 int ola_dev_upload(ola_ctx* ctx, uint64_t* dst_dev, const uint64_t* src_host, size_t n_u64) {
@@ -361,7 +377,7 @@ int ola_commit(ola_ctx* ctx, const uint64_t* cols, int on_device, size_t ncols, 
 }
 
 int ola_prove(ola_ctx* ctx, const int* table_ids, uint32_t ntables, const uint64_t* const* traces, int on_device, const uint32_t* log_ns,
-              int check_quotient_degree, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+              const uint64_t* compress_challenges, int check_quotient_degree, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
     if (!ctx || !table_ids || !traces || !log_ns || !proof_len || (!proof_out && proof_cap)) return OLA_ERR_INVALID_ARG;
     *proof_len = 0;
     return guarded(ctx, [&] {
@@ -370,7 +386,9 @@ int ola_prove(ola_ctx* ctx, const int* table_ids, uint32_t ntables, const uint64
         std::vector<int> ids(table_ids, table_ids + ntables);
         std::vector<const uint64_t*> tr(traces, traces + ntables);
         std::vector<uint32_t> lg(log_ns, log_ns + ntables);
-        std::vector<uint8_t> bytes = ola::stark::prove_all(ctx, ids, tr, on_device != 0, lg, cfg);
+        std::vector<uint64_t> cc;
+        if (compress_challenges) cc.assign(compress_challenges, compress_challenges + ntables);
+        std::vector<uint8_t> bytes = ola::stark::prove_all(ctx, ids, tr, on_device != 0, lg, cc, cfg);
         *proof_len = bytes.size();
         OLA_CHECK(bytes.size() <= proof_cap, OLA_ERR_INVALID_ARG, "proof buffer too small (needed size returned in proof_len)");
         memcpy(proof_out, bytes.data(), bytes.size());

@@ -52,19 +52,27 @@ void canon_copy(ola_ctx* ctx, uint64_t* dst, const uint64_t* src, size_t n) {
     count_launch(ctx);
 }
 
+// Stream-ordered device allocator: every buffer of the library comes from the device's default memory pool on the
+// calling context's stream (set by the C-ABI entry guard), so repeated commits / proofs reuse the pooled memory
+// instead of paying cudaMalloc/cudaFree (which also synchronise the device) for multi-GB buffers each time.
+static thread_local cudaStream_t t_alloc_stream = nullptr;
+void set_alloc_stream(cudaStream_t s) { t_alloc_stream = s; }
 void dev_alloc(uint64_t** p, size_t n_u64) {
-    cudaError_t e = cudaMalloc(p, std::max<size_t>(n_u64, 1) * sizeof(uint64_t));
+    cudaError_t e = cudaMallocAsync((void**)p, std::max<size_t>(n_u64, 1) * sizeof(uint64_t), t_alloc_stream);
     if (e == cudaErrorMemoryAllocation) {
         cudaGetLastError();
-        throw Error(OLA_ERR_OOM, "cudaMalloc: out of device memory (" + std::to_string(n_u64 * 8) + " bytes)");
+        throw Error(OLA_ERR_OOM, "cudaMallocAsync: out of device memory (" + std::to_string(n_u64 * 8) + " bytes)");
     }
     OLA_CUDA(e);
+}
+void dev_free(void* p) {
+    if (p) cudaFreeAsync(p, t_alloc_stream);
 }
 
 uint64_t* ctx_scratch(ola_ctx* ctx, size_t n_u64) {
     if (ctx->scratch_elems < n_u64) {
         OLA_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (ctx->scratch) cudaFree(ctx->scratch);
+        if (ctx->scratch) ola::dev_free(ctx->scratch);
         ctx->scratch = nullptr;
         ctx->scratch_elems = 0;
         dev_alloc(&ctx->scratch, n_u64);
@@ -150,12 +158,12 @@ ola_batch* batch_commit(ola_ctx* ctx, const uint64_t* cols, bool on_device, size
         try {
             ntt::forward(ctx, d);
         } catch (...) {
-            if (tmp_work) cudaFree(tmp_work);
+            if (tmp_work) ola::dev_free(tmp_work);
             throw;
         }
         if (tmp_work) {
             OLA_CUDA(cudaStreamSynchronize(ctx->stream));
-            cudaFree(tmp_work);
+            ola::dev_free(tmp_work);
         }
     }
     // coset LDE, shift 7, blowup 2^rate_bits, straight into leaf order (oracle.rs:101-129 + :84-85)
@@ -182,9 +190,9 @@ ola_batch* batch_commit(ola_ctx* ctx, const uint64_t* cols, bool on_device, size
 
 void batch_release(ola_batch* b) {
     if (!b) return;
-    if (b->d_coeffs) cudaFree(b->d_coeffs);
-    if (b->d_lde) cudaFree(b->d_lde);
-    if (b->d_nodes) cudaFree(b->d_nodes);
+    if (b->d_coeffs) ola::dev_free(b->d_coeffs);
+    if (b->d_lde) ola::dev_free(b->d_lde);
+    if (b->d_nodes) ola::dev_free(b->d_nodes);
     b->d_coeffs = b->d_lde = b->d_nodes = nullptr;
 }
 
@@ -214,7 +222,7 @@ int batch_prove_leaf(ola_ctx* ctx, const ola_batch* b, size_t leaf, uint64_t* si
     count_launch(ctx);
     cudaError_t e = cudaMemcpyAsync(sib_host, tmp, (size_t)nsib * 32, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(tmp);
+    ola::dev_free(tmp);
     OLA_CUDA(e);
     return nsib;
 }

@@ -14,6 +14,8 @@ struct ola_batch {
 
 namespace ola {
 void dev_alloc(uint64_t** p, size_t n_u64);
+void dev_free(void* p);
+void set_alloc_stream(cudaStream_t s);
 // dst[i] = canonical(src[i]); dst may alias src
 void canon_copy(ola_ctx* ctx, uint64_t* dst, const uint64_t* src, size_t n);
 // grow-only per-context workspace of at least n_u64 elements (synchronises the stream when it has to grow)

@@ -240,7 +240,7 @@ struct DevMem {  // RAII cudaMalloc
         dev_alloc(&p, n);
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) ola::dev_free(p);
         p = nullptr;
     }
     ~DevMem() { release(); }

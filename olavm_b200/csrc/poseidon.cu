@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(128) permute_kernel(uint64_t* states, size_t n
 }
 
 // hash_no_pad over one row; ROWMAJOR: element (r, c) at base[r*ncols + c]; else at base[c*col_stride + r]
-template <bool ROWMAJOR, int MINB>
+template <bool ROWMAJOR, int MINB, bool UNROLLED = false>
 __global__ void __launch_bounds__(128, MINB) hash_rows_kernel(const uint64_t* __restrict__ base, size_t col_stride, size_t nrows,
                                                        size_t ncols, uint64_t* __restrict__ digests) {
     size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -60,7 +60,10 @@ __global__ void __launch_bounds__(128, MINB) hash_rows_kernel(const uint64_t* __
                 s[k] = v;
             }
         }
-        permute(s);
+        if (UNROLLED)
+            permute_unrolled(s);
+        else
+            permute(s);
     }
     ulonglong2* d = reinterpret_cast<ulonglong2*>(digests + 4 * r);
     d[0] = make_ulonglong2(s[0], s[1]);
@@ -101,20 +104,25 @@ void hash_rows_colmajor(ola_ctx* ctx, const uint64_t* d_cols, size_t col_stride,
                         uint64_t* d_digests) {
     if (!nrows) return;
     {
-        // resident CTAs per SM (register cap 128/96/80): occupancy vs spills, tuned on hardware (profiles/)
+        // resident CTAs per SM (register cap 128/96/80) and body form, tuned on hardware (profiles/)
         static const int minb = [] {
             const char* e = getenv("OLA_POSEIDON_MINB");
             int v = e ? atoi(e) : 5;
             return (v >= 4 && v <= 6) ? v : 5;
         }();
+        static const bool unrolled = [] {
+            const char* e = getenv("OLA_POSEIDON_UNROLLED");
+            return e && atoi(e) != 0;
+        }();
         const unsigned blocks = (unsigned)((nrows + 127) / 128);
         Launch lz(ctx, "poseidon_leaves");
-        if (minb == 4)
-            hash_rows_kernel<false, 4><<<blocks, 128, 0, ctx->stream>>>(d_cols, col_stride, nrows, ncols, d_digests);
-        else if (minb == 5)
-            hash_rows_kernel<false, 5><<<blocks, 128, 0, ctx->stream>>>(d_cols, col_stride, nrows, ncols, d_digests);
-        else
-            hash_rows_kernel<false, 6><<<blocks, 128, 0, ctx->stream>>>(d_cols, col_stride, nrows, ncols, d_digests);
+#define OLA_HR(M, U) hash_rows_kernel<false, M, U><<<blocks, 128, 0, ctx->stream>>>(d_cols, col_stride, nrows, ncols, d_digests)
+        if (unrolled) {
+            if (minb == 4) OLA_HR(4, true); else if (minb == 5) OLA_HR(5, true); else OLA_HR(6, true);
+        } else {
+            if (minb == 4) OLA_HR(4, false); else if (minb == 5) OLA_HR(5, false); else OLA_HR(6, false);
+        }
+#undef OLA_HR
     }
     check_launch("hash_rows_kernel<col>");
 }

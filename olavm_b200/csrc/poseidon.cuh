@@ -83,18 +83,146 @@ __device__ __forceinline__ void mds_layer(uint64_t* s) {
     }
 }
 
-__device__ __forceinline__ void full_round(uint64_t* s, int round_ctr) {
+__device__ __forceinline__ void full_round_unrolled(uint64_t* s, int round_ctr) {
 #pragma unroll
     for (int i = 0; i < 12; ++i) s[i] = sbox7(gl::add_lc(s[i], c_round[round_ctr * 12 + i]));
     mds_layer(s);
 }
 
+// ---- code-size-bounded form ----
+// The fully unrolled permutation is ~6000 SASS instructions (~100 KB); warps of the resident CTAs drift through
+// it independently, so the SM's instruction working set is the whole body and the measured dominant stall was
+// "no instruction" (profiles/poseidon_r01f_ncu_summary.md).  Below, the 12-lane S-box layer and the circulant MDS
+// are rolled into short loops over a ROTATING register file (all indices inside a loop body are static; the
+// rotation is register moves), the 11x11 initial matrix is one row per iteration, and both groups of four full
+// rounds share one body, so the whole permutation fits the instruction cache.
+__device__ __forceinline__ void full_round(uint64_t* s, int round_ctr) {
+    // S-box layer: 4 iterations x 3 lanes; rotating left by 3 each time returns the state to natural order
+#pragma unroll 1
+    for (int it = 0; it < 4; ++it) {
+        const int k = round_ctr * 12 + it * 3;
+        const uint64_t a = sbox7(gl::add_lc(s[0], c_round[k]));
+        const uint64_t b = sbox7(gl::add_lc(s[1], c_round[k + 1]));
+        const uint64_t c = sbox7(gl::add_lc(s[2], c_round[k + 2]));
+#pragma unroll
+        for (int j = 0; j < 9; ++j) s[j] = s[j + 3];
+        s[9] = a;
+        s[10] = b;
+        s[11] = c;
+    }
+    // MDS layer: 3 iterations x 4 rows of the circulant; rotating the operand halves by 4 turns rows 4k..4k+3 into
+    // rows 0..3, and the outputs queue up in o
+    constexpr uint32_t C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+    uint32_t lo[12], hi[12];
+    uint64_t o[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        lo[i] = (uint32_t)s[i];
+        hi[i] = (uint32_t)(s[i] >> 32);
+        o[i] = 0;
+    }
+#pragma unroll 1
+    for (int it = 0; it < 3; ++it) {
+        const uint32_t diag = it == 0 ? 8u : 0u;  // MDS_MATRIX_DIAG[0] = 8 applies to row 0 only
+        uint64_t nw[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            uint64_t al = 0, ah = 0;
+#pragma unroll
+            for (int i = 0; i < 12; ++i) {
+                al += (uint64_t)lo[(i + r) % 12] * C[i];
+                ah += (uint64_t)hi[(i + r) % 12] * C[i];
+            }
+            if (r == 0) {
+                al += (uint64_t)lo[0] * diag;
+                ah += (uint64_t)hi[0] * diag;
+            }
+            const uint64_t l128 = al + (ah << 32);
+            const uint64_t h128 = (ah >> 32) + (l128 < al);
+            nw[r] = gl::reduce128_lazy(l128, h128);
+        }
+        uint32_t tl[4], th[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            tl[j] = lo[j];
+            th[j] = hi[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            lo[j] = lo[j + 4];
+            hi[j] = hi[j + 4];
+            o[j] = o[j + 4];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            lo[8 + j] = tl[j];
+            hi[8 + j] = th[j];
+            o[8 + j] = nw[j];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) s[i] = o[i];
+}
+
+// partial_first_constant_layer + mds_partial_layer_init (poseidon.rs:303-313, :332-358), one output column per
+// iteration; results queue up in q
+__device__ __forceinline__ void partial_init(uint64_t* s) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) s[i] = gl::add_lc(s[i], c_first[i]);
+    uint64_t q[11];
+#pragma unroll
+    for (int j = 0; j < 11; ++j) q[j] = 0;
+#pragma unroll 1
+    for (int c = 0; c < 11; ++c) {
+        acc160 acc;
+        acc_zero(acc);
+#pragma unroll
+        for (int r = 1; r < 12; ++r) acc_mac(acc, s[r], c_init[(r - 1) * 11 + c]);
+        const uint64_t v = acc_reduce(acc);
+#pragma unroll
+        for (int j = 0; j < 10; ++j) q[j] = q[j + 1];
+        q[10] = v;
+    }
+#pragma unroll
+    for (int c = 0; c < 11; ++c) s[c + 1] = q[c];
+}
+
+// 22 partial rounds (poseidon.rs:582-588, mds_partial_layer_fast :392-421)
+__device__ __forceinline__ void partial_rounds(uint64_t* s) {
+#pragma unroll 1
+    for (int r = 0; r < 22; ++r) {
+        s[0] = gl::add_lc(sbox7(s[0]), c_partial[r]);
+        acc160 d;
+        acc_zero(d);
+        acc_mac(d, s[0], 25);  // MDS_MATRIX_CIRC[0] + MDS_MATRIX_DIAG[0]
+#pragma unroll
+        for (int i = 1; i < 12; ++i) acc_mac(d, s[i], c_whats[r * 11 + i - 1]);
+        uint64_t s0 = s[0];
+#pragma unroll
+        for (int i = 1; i < 12; ++i) s[i] = gl::mad_lazy(s0, c_vs[r * 11 + i - 1], s[i]);
+        s[0] = acc_reduce(d);
+    }
+}
+
 // s: any u64 representatives in, CANONICAL representatives out
 __device__ __forceinline__ void permute(uint64_t* s) {
 #pragma unroll 1
-    for (int r = 0; r < 4; ++r) full_round(s, r);
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll 1
+        for (int r = 0; r < 4; ++r) full_round(s, half * 26 + r);
+        if (half == 0) {
+            partial_init(s);
+            partial_rounds(s);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) s[i] = gl::canon_fast(s[i]);
+}
 
-    // partial_first_constant_layer + mds_partial_layer_init (poseidon.rs:303-313, :332-358)
+// the straight-line form (kept for A/B measurements: OLA_POSEIDON_UNROLLED=1)
+__device__ __forceinline__ void permute_unrolled(uint64_t* s) {
+#pragma unroll 1
+    for (int r = 0; r < 4; ++r) full_round_unrolled(s, r);
 #pragma unroll
     for (int i = 0; i < 12; ++i) s[i] = gl::add_lc(s[i], c_first[i]);
     {
@@ -109,22 +237,9 @@ __device__ __forceinline__ void permute(uint64_t* s) {
 #pragma unroll
         for (int c = 0; c < 11; ++c) s[c + 1] = acc_reduce(acc[c]);
     }
-    // 22 partial rounds (poseidon.rs:582-588, mds_partial_layer_fast :392-421)
+    partial_rounds(s);
 #pragma unroll 1
-    for (int r = 0; r < 22; ++r) {
-        s[0] = gl::add_lc(sbox7(s[0]), c_partial[r]);
-        acc160 d;
-        acc_zero(d);
-        acc_mac(d, s[0], 25);  // MDS_MATRIX_CIRC[0] + MDS_MATRIX_DIAG[0]
-#pragma unroll
-        for (int i = 1; i < 12; ++i) acc_mac(d, s[i], c_whats[r * 11 + i - 1]);
-        uint64_t s0 = s[0];
-#pragma unroll
-        for (int i = 1; i < 12; ++i) s[i] = gl::mad_lazy(s0, c_vs[r * 11 + i - 1], s[i]);
-        s[0] = acc_reduce(d);
-    }
-#pragma unroll 1
-    for (int r = 0; r < 4; ++r) full_round(s, 26 + r);
+    for (int r = 0; r < 4; ++r) full_round_unrolled(s, 26 + r);
 #pragma unroll
     for (int i = 0; i < 12; ++i) s[i] = gl::canon_fast(s[i]);
 }

@@ -178,6 +178,7 @@ struct QuotArgs {
     uint64_t* out;               // [2][n << qdb]
     DevTables d;
     int num_perm_zs;
+    uint64_t compress_challenge;  // Bitwise / Program only (canonical)
 };
 
 __device__ __forceinline__ uint64_t pow_omega_fwd(const uint64_t* __restrict__ pw, uint32_t E) {
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(128) quotient_kernel(const QuotArgs a) {
     yc.lagrange_first = Fp(gl::mul(a.zh[zi], gl::mul(inv01, d1)));
     yc.lagrange_last = Fp(gl::mul(a.zh[zi], gl::mul(inv01, d0)));
     const Row lv{a.trace_lde, a.L, r}, nv{a.trace_lde, a.L, r_next};
-    Air::eval(lv, nv, yc);
+    Air::eval(lv, nv, yc, Fp(a.compress_challenge));
 
     const DevTables& d = a.d;
     // eval_permutation_checks (permutation.rs:302-360)
@@ -262,6 +263,14 @@ static void launch_quotient(ola_ctx* ctx, int table_id, const QuotArgs& a) {
         case T_MEMORY: quotient_kernel<air::Memory><<<blocks, 128, 0, ctx->stream>>>(a); break;
         case T_CMP: quotient_kernel<air::Cmp><<<blocks, 128, 0, ctx->stream>>>(a); break;
         case T_RANGECHECK: quotient_kernel<air::RangeCheck><<<blocks, 128, 0, ctx->stream>>>(a); break;
+        case T_BITWISE: quotient_kernel<air::Bitwise><<<blocks, 128, 0, ctx->stream>>>(a); break;
+        case T_POSEIDON: quotient_kernel<air::Poseidon><<<blocks, 128, 0, ctx->stream>>>(a); break;
+        case T_POSEIDON_CHUNK: quotient_kernel<air::PoseidonChunk><<<blocks, 128, 0, ctx->stream>>>(a); break;
+        case T_STORAGE: quotient_kernel<air::StorageAccess><<<blocks, 128, 0, ctx->stream>>>(a); break;
+        case T_TAPE: quotient_kernel<air::Tape><<<blocks, 128, 0, ctx->stream>>>(a); break;
+        case T_SCCALL: quotient_kernel<air::SCCall><<<blocks, 128, 0, ctx->stream>>>(a); break;
+        case T_PROGRAM: quotient_kernel<air::Program><<<blocks, 128, 0, ctx->stream>>>(a); break;
+        case T_PROG_CHUNK: quotient_kernel<air::ProgChunk><<<blocks, 128, 0, ctx->stream>>>(a); break;
         default: throw Error(OLA_ERR_INVALID_ARG, "no constraint kernel for table " + std::to_string(table_id));
     }
 }
@@ -378,7 +387,7 @@ struct DevDesc {
     uint64_t* mem = nullptr;
     DevTables t{};
     ~DevDesc() {
-        if (mem) cudaFree(mem);
+        if (mem) ola::dev_free(mem);
     }
     void upload(ola_ctx* ctx, const DescBuilder& b) {
         auto a8 = [](size_t bytes) { return (bytes + 7) / 8; };
@@ -447,7 +456,7 @@ struct DevBuf {
     DevBuf() {}
     explicit DevBuf(size_t n) { dev_alloc(&p, n); }
     ~DevBuf() {
-        if (p) cudaFree(p);
+        if (p) ola::dev_free(p);
     }
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
@@ -575,6 +584,7 @@ static StarkProof prove_single_table(ola_ctx* ctx, const TableInfo& t, const Con
         a.out = d_q.p;
         a.d = desc.t;
         a.num_perm_zs = (int)num_perm_zs;
+        a.compress_challenge = t.compress_challenge;
         launch_quotient(ctx, t.id, a);
         check_launch("quotient_kernel");
     }
@@ -642,8 +652,12 @@ static StarkProof prove_single_table(ola_ctx* ctx, const TableInfo& t, const Con
 
 // prove_with_traces (prover.rs:79-327) + Buffer::write_all_proof (serialization.rs:377-393)
 std::vector<uint8_t> prove_all(ola_ctx* ctx, const std::vector<int>& table_ids, const std::vector<const uint64_t*>& traces, bool on_device,
-                               const std::vector<uint32_t>& log_ns, const Config& cfg) {
-    const System sys = make_system(table_ids);
+                               const std::vector<uint32_t>& log_ns, const std::vector<uint64_t>& compress_challenges, const Config& cfg) {
+    System sys = make_system(table_ids);
+    OLA_CHECK(compress_challenges.empty() || compress_challenges.size() == sys.tables.size(), OLA_ERR_INVALID_ARG, "one compress challenge per table");
+    for (size_t i = 0; i < compress_challenges.size(); ++i)
+        if (sys.tables[i].id == T_BITWISE || sys.tables[i].id == T_PROGRAM)
+            sys.tables[i].compress_challenge = sys.compress_challenges[i] = gl::canon(compress_challenges[i]);
     const size_t T = sys.tables.size();
     OLA_CHECK(traces.size() == T && log_ns.size() == T, OLA_ERR_INVALID_ARG, "one trace per table");
     std::vector<std::unique_ptr<DevBuf>> d_vals(T);

@@ -151,6 +151,7 @@ struct TableInfo {
     int columns = 0;
     int constraint_degree = 0;
     std::vector<PermutationPair> permutation_pairs;
+    F compress_challenge = 0;  // Bitwise / Program: beta from trace generation
     int quotient_degree_factor() const { return constraint_degree - 1 > 1 ? constraint_degree - 1 : 1; }
     int permutation_batch_size() const { return quotient_degree_factor(); }
     int num_permutation_batches() const {

@@ -15,11 +15,12 @@ def table_columns(ctx, table_id):
     return int(ctx._lib.ola_table_columns(int(table_id)))
 
 
-def prove_with_traces(ctx, table_ids, trace_poly_values, check_quotient_degree=True, max_bytes=1 << 26):
+def prove_with_traces(ctx, table_ids, trace_poly_values, check_quotient_degree=True, max_bytes=1 << 26, compress_challenges=None):
     """-> proof bytes (AllProof in the reference's wire format).
 
     table_ids: ids of the reference `Table` enum, ascending; trace_poly_values[i]: [columns_i, 2^k_i] uint64
-    (Vec<PolynomialValues<F>> column-major).  Raises OlaError(OLA_ERR_QUOTIENT_DEGREE) where the reference panics with
+    (Vec<PolynomialValues<F>> column-major); compress_challenges: None or one field element per table (only the
+    Bitwise and Program entries are used: the beta of generation/mod.rs:183-188).  Raises OlaError(OLA_ERR_QUOTIENT_DEGREE) where the reference panics with
     "Quotient has failed, ..." and OlaError(OLA_ERR_INVALID_ARG, "Non-binary filter?") like partial_products' assert."""
     k = len(table_ids)
     trs = [np.ascontiguousarray(t, dtype=np.uint64) for t in trace_poly_values]
@@ -32,6 +33,12 @@ def prove_with_traces(ctx, table_ids, trace_poly_values, check_quotient_degree=T
     logs = (ctypes.c_uint32 * k)(*[int(t.shape[1]).bit_length() - 1 for t in trs])
     out = np.empty(max_bytes, dtype=np.uint8)
     n = ctypes.c_size_t(0)
-    ctx.check(ctx._lib.ola_prove(ctx.handle, ids, k, ptrs, 0, logs, 1 if check_quotient_degree else 0, out.ctypes.data_as(ctypes.c_void_p),
+    cc = None
+    if compress_challenges is not None:
+        cc_arr = np.ascontiguousarray(compress_challenges, dtype=np.uint64)
+        if cc_arr.shape != (k,):
+            raise ValueError("one compress challenge per table")
+        cc = cc_arr.ctypes.data_as(ctypes.c_void_p)
+    ctx.check(ctx._lib.ola_prove(ctx.handle, ids, k, ptrs, 0, logs, cc, 1 if check_quotient_degree else 0, out.ctypes.data_as(ctypes.c_void_p),
                                  max_bytes, ctypes.byref(n)))
     return out[: n.value].tobytes()

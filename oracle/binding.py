@@ -62,6 +62,8 @@ def _set_sigs(L):
     L.orc_lde_batch.argtypes = [_u64p, _sz, _sz, _u64, _sz, _u64p]
     L.orc_poseidon.argtypes = [_u64p]
     L.orc_poseidon_naive.argtypes = [_u64p]
+    L.orc_poseidon_table_row.argtypes = [_u64p, _u64p]
+    L.orc_poseidon_table_row.restype = None
     L.orc_hash_no_pad.argtypes = [_u64p, _sz, _u64p]
     L.orc_two_to_one.argtypes = [_u64p, _u64p, _u64p]
     L.orc_hash_rows.argtypes = [_u64p, _sz, _sz, _u64p]
@@ -74,7 +76,7 @@ def _set_sigs(L):
     L.orc_merkle_verify.restype = _int
     L.orc_commit.argtypes = [_u64p, _sz, _sz, _int, _u32, _u32, _u64p, _u64p, _u64p, _u64p]
     L.orc_commit.restype = _int
-    L.orc_stark_prove.argtypes = [ctypes.POINTER(_int), _u32, ctypes.POINTER(_u64p), ctypes.POINTER(_u32), _int,
+    L.orc_stark_prove.argtypes = [ctypes.POINTER(_int), _u32, ctypes.POINTER(_u64p), ctypes.POINTER(_u32), _u64p, _int,
                                   ctypes.POINTER(ctypes.c_uint8), _sz, ctypes.POINTER(_sz), ctypes.c_char_p, _sz]
     L.orc_stark_prove.restype = _int
     L.orc_stark_verify.argtypes = [ctypes.POINTER(_int), _u32, ctypes.POINTER(ctypes.c_uint8), _sz, ctypes.c_char_p, _sz]
@@ -240,7 +242,16 @@ def table_columns(table_id):
     return lib().orc_table_columns(int(table_id))
 
 
-def stark_prove(table_ids, traces, check_degree=True, max_bytes=1 << 26):
+def poseidon_table_row(inp):
+    """Witness row of the Poseidon table (134 columns; the 4 filters left 0) for a 12-element permutation input."""
+    a = np.ascontiguousarray(inp, dtype=np.uint64)
+    assert a.shape == (12,)
+    row = np.zeros(134, dtype=np.uint64)
+    lib().orc_poseidon_table_row(_p(a), _p(row))
+    return row
+
+
+def stark_prove(table_ids, traces, check_degree=True, max_bytes=1 << 26, compress_challenges=None):
     """prove_with_traces + Buffer::write_all_proof -> bytes.  traces[i]: [columns_i, 2^k_i] uint64 column-major."""
     k = len(table_ids)
     trs = [np.ascontiguousarray(t, dtype=np.uint64) for t in traces]
@@ -250,7 +261,12 @@ def stark_prove(table_ids, traces, check_degree=True, max_bytes=1 << 26):
     out = (ctypes.c_uint8 * max_bytes)()
     n = ctypes.c_size_t(0)
     err = ctypes.create_string_buffer(512)
-    rc = lib().orc_stark_prove(ids, k, ptrs, logs, 1 if check_degree else 0, out, max_bytes, ctypes.byref(n), err, 512)
+    cc = None
+    if compress_challenges is not None:
+        cc_arr = np.ascontiguousarray(compress_challenges, dtype=np.uint64)
+        assert cc_arr.shape == (k,)
+        cc = _p(cc_arr)
+    rc = lib().orc_stark_prove(ids, k, ptrs, logs, cc, 1 if check_degree else 0, out, max_bytes, ctypes.byref(n), err, 512)
     if rc != 0:
         raise StarkError(err.value.decode())
     return bytes(bytearray(out)[: n.value])

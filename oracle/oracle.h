@@ -24,6 +24,8 @@ void orc_lde_batch(const uint64_t *coeffs, size_t ncols, size_t n, uint64_t shif
 /* poseidon.c */
 void orc_poseidon(uint64_t state[12]);
 void orc_poseidon_naive(uint64_t state[12]);
+/* one row of the Poseidon table (134 columns, filters 0) for a permutation input (generation/poseidon.rs:18-80) */
+void orc_poseidon_table_row(const uint64_t in[12], uint64_t row[134]);
 void orc_hash_no_pad(const uint64_t *in, size_t n, uint64_t out[4]);
 void orc_two_to_one(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]);
 void orc_hash_rows(const uint64_t *rows, size_t nrows, size_t ncols, uint64_t *digests);

@@ -94,6 +94,56 @@ void orc_poseidon(uint64_t state[12]) {
     partial_rounds_fast(state, &rc);
     full_rounds(state, &rc);
 }
+/* One row of the Poseidon TABLE (builtins/poseidon/columns.rs:6-42) for a given permutation input: the witness
+ * values trace generation records (core/src/vm hashing via calculate_poseidon_and_generate_intermediate_trace,
+ * laid out by circuits/src/generation/poseidon.rs:18-80) are exactly the S-box inputs that PoseidonStark constrains
+ * (poseidon_stark.rs:83-141): after the constant layer of full rounds 1..3 (first half) and 0..3 (second half), and
+ * state[0] before each partial-round S-box in the fast formulation.  row[0..4) (the filters) are left 0.
+ * Pinned by the reference's POSEIDON_ZERO_HASH_* / POSEIDON_1000_HASH_* tables (poseidon_utils.rs:11-287). */
+void orc_poseidon_table_row(const uint64_t in[12], uint64_t row[134]) {
+    uint64_t s[W];
+    int rc = 0;
+    memset(row, 0, 134 * sizeof(uint64_t));
+    for (int i = 0; i < W; i++) row[4 + i] = s[i] = gl_canon(in[i]);
+    for (int r = 0; r < HALF_FULL; r++) {
+        constant_layer(s, rc);
+        if (r != 0) memcpy(row + 28 + 12 * (r - 1), s, sizeof(s));
+        sbox_layer(s);
+        mds_layer(s);
+        rc++;
+    }
+    for (int i = 0; i < W; i++) s[i] = gl_add(s[i], gl_canon(ORC_FAST_PARTIAL_FIRST_ROUND_CONSTANT[i]));
+    {
+        uint64_t res[W];
+        memset(res, 0, sizeof(res));
+        res[0] = s[0];
+        for (int r = 1; r < W; r++)
+            for (int c = 1; c < W; c++)
+                res[c] = gl_add(res[c], gl_mul(s[r], gl_canon(ORC_FAST_PARTIAL_ROUND_INITIAL_MATRIX[r - 1][c - 1])));
+        memcpy(s, res, sizeof(res));
+    }
+    for (int i = 0; i < N_PARTIAL; i++) {
+        row[64 + i] = s[0];
+        s[0] = sbox(s[0]);
+        if (i < N_PARTIAL - 1) s[0] = gl_add(s[0], gl_canon(ORC_FAST_PARTIAL_ROUND_CONSTANTS[i]));
+        uint64_t d = gl_mul(s[0], ORC_MDS_MATRIX_CIRC[0] + ORC_MDS_MATRIX_DIAG[0]);
+        for (int k = 1; k < W; k++) d = gl_add(d, gl_mul(s[k], gl_canon(ORC_FAST_PARTIAL_ROUND_W_HATS[i][k - 1])));
+        uint64_t res[W];
+        res[0] = d;
+        for (int k = 1; k < W; k++) res[k] = gl_add(s[k], gl_mul(s[0], gl_canon(ORC_FAST_PARTIAL_ROUND_VS[i][k - 1])));
+        memcpy(s, res, sizeof(res));
+    }
+    rc += N_PARTIAL;
+    for (int r = 0; r < HALF_FULL; r++) {
+        constant_layer(s, rc);
+        memcpy(row + 86 + 12 * r, s, sizeof(s));
+        sbox_layer(s);
+        mds_layer(s);
+        rc++;
+    }
+    memcpy(row + 16, s, sizeof(s));
+}
+
 void orc_poseidon_naive(uint64_t state[12]) {
     int rc = 0;
     for (int i = 0; i < W; i++) state[i] = gl_canon(state[i]);

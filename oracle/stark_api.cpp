@@ -12,11 +12,13 @@ static void set_err(char* err, size_t cap, const std::string& e) {
 extern "C" {
 
 /* prove_with_traces + Buffer::write_all_proof.  table_ids: ntables ids in enum order; traces[i]: column-major
- * [columns_i][2^log_ns[i]].  Returns 0 and the proof bytes, or -1 with a message. */
-int orc_stark_prove(const int* table_ids, uint32_t ntables, const uint64_t* const* traces, const uint32_t* log_ns, int check_degree,
-                    uint8_t* out, size_t cap, size_t* out_len, char* err, size_t errcap) {
+ * [columns_i][2^log_ns[i]]; compress_challenges: NULL or one per table (Bitwise / Program entries used).  Returns 0 and the proof bytes, or -1 with a message. */
+int orc_stark_prove(const int* table_ids, uint32_t ntables, const uint64_t* const* traces, const uint32_t* log_ns,
+                    const uint64_t* compress_challenges, int check_degree, uint8_t* out, size_t cap, size_t* out_len, char* err, size_t errcap) {
     try {
-        System sys = make_system(std::vector<int>(table_ids, table_ids + ntables));
+        VF cc;
+        if (compress_challenges) cc.assign(compress_challenges, compress_challenges + ntables);
+        System sys = make_system(std::vector<int>(table_ids, table_ids + ntables), cc);
         Config cfg;
         cfg.check_quotient_degree = check_degree != 0;
         std::vector<VF> tr(ntables);
@@ -44,11 +46,12 @@ int orc_stark_prove(const int* table_ids, uint32_t ntables, const uint64_t* cons
 /* Buffer::read_all_proof + verify_proof.  Returns 0 if the proof verifies. */
 int orc_stark_verify(const int* table_ids, uint32_t ntables, const uint8_t* proof, size_t len, char* err, size_t errcap) {
     try {
-        System sys = make_system(std::vector<int>(table_ids, table_ids + ntables));
         Config cfg;
         Reader r(proof, len);
         AllProof ap = r.all();
         if (!r.ok || r.pos != len) { set_err(err, errcap, "malformed proof bytes"); return -1; }
+        /* verifier.rs:78-86: the bitwise / program compress challenges are taken from the proof */
+        System sys = make_system(std::vector<int>(table_ids, table_ids + ntables), ap.compress_challenges);
         std::string e = verify_all(sys, cfg, ap);
         if (!e.empty()) { set_err(err, errcap, e); return -1; }
         return 0;

@@ -3,7 +3,7 @@
  * line and emits the constraints in source order (the consumer is Horner in alpha, so order is semantics:
  * circuits/src/stark/constraint_consumer.rs:60-65).
  *
- * Tables restated so far (enum order of circuits/src/stark/ola_stark.rs:104-119):
+ * Independently restated here (enum order of circuits/src/stark/ola_stark.rs:104-119):
  *   3 Cmp         circuits/src/builtins/cmp/{columns.rs:16-22, cmp_stark.rs:21-45, :88-108}
  *   4 RangeCheck  circuits/src/builtins/rangecheck/{columns.rs:25-39, rangecheck_stark.rs:27-108, :111-140},
  *                 circuits/src/stark/lookup.rs:13-35
@@ -11,6 +11,7 @@
 #ifndef ORC_TABLES_HPP
 #define ORC_TABLES_HPP
 #include "stark.hpp"
+#include "poseidon_constants.h"
 /* The CPU table's constraint body and the CTL registry are a single transcription shared with the product
  * (olavm_b200/csrc/air/{cpu_air,ctl_registry}.h); see the note at the top of cpu_air.h and DESIGN.md section 4. */
 #include "../olavm_b200/csrc/air/ctl_registry.h"
@@ -85,6 +86,34 @@ void eval(const P<O>* lv, const P<O>* nv, Consumer<O>& yc) {
 }
 }  // namespace mem_t
 
+/* ---- shared transcriptions of builtins_air.h / hash_air.h ---- */
+#define ORC_SHARED_TABLE(NS_T, NS)                                                                     \
+    namespace NS_T {                                                                                   \
+    template <class O>                                                                                 \
+    void eval(const P<O>* lv, const P<O>* nv, Consumer<O>& yc) { ola::air::NS::eval<P<O>, const P<O>*, Consumer<O>>(lv, nv, yc); } \
+    }
+ORC_SHARED_TABLE(tape_t, tape)
+ORC_SHARED_TABLE(sccall_t, sccall)
+ORC_SHARED_TABLE(prog_chunk_t, prog_chunk)
+ORC_SHARED_TABLE(storage_t, storage)
+ORC_SHARED_TABLE(psdn_chunk_t, psdn_chunk)
+#undef ORC_SHARED_TABLE
+/* Poseidon table: parameter tables from the oracle's own generated constants */
+struct PoseidonParams {
+    static uint64_t round(int i) { return ORC_ALL_ROUND_CONSTANTS[i]; }
+    static uint64_t circ(int i) { return ORC_MDS_MATRIX_CIRC[i]; }
+    static uint64_t diag(int i) { return ORC_MDS_MATRIX_DIAG[i]; }
+    static uint64_t first(int i) { return ORC_FAST_PARTIAL_FIRST_ROUND_CONSTANT[i]; }
+    static uint64_t partial(int r) { return ORC_FAST_PARTIAL_ROUND_CONSTANTS[r]; }
+    static uint64_t init(int r, int c) { return ORC_FAST_PARTIAL_ROUND_INITIAL_MATRIX[r][c]; }
+    static uint64_t what(int r, int i) { return ORC_FAST_PARTIAL_ROUND_W_HATS[r][i]; }
+    static uint64_t vs(int r, int i) { return ORC_FAST_PARTIAL_ROUND_VS[r][i]; }
+};
+namespace psdn_t {
+template <class O>
+void eval(const P<O>* lv, const P<O>* nv, Consumer<O>& yc) { ola::air::psdn::eval<P<O>, const P<O>*, Consumer<O>, PoseidonParams>(lv, nv, yc); }
+}  // namespace psdn_t
+
 template <class EvalB, class EvalE>
 Table make_table(const char* name, int cols, int degree, EvalB eb, EvalE ee, std::vector<PermutationPair> pp = {}) {
     Table t;
@@ -98,9 +127,10 @@ Table make_table(const char* name, int cols, int degree, EvalB eb, EvalE ee, std
 }
 #define ORC_TABLE(name, ns, cols, degree, ...) make_table(name, cols, degree, ns::eval<FOps>, ns::eval<EOps>, ##__VA_ARGS__)
 
-inline bool table_available(int id) { return id == T_CPU || id == T_MEMORY || id == T_CMP || id == T_RANGECHECK; }
+inline bool table_available(int id) { return id >= 0 && id < T_NUM; }
 
-inline Table table_by_id(int id) {
+/* beta: the table's compress challenge (Bitwise / Program only; verifier.rs:78-86 takes it from the proof) */
+inline Table table_by_id(int id, F beta = 0) {
     switch (id) {
         case T_CPU: return ORC_TABLE("CpuStark", cpu_t, ola::air::cpu::NUM_CPU_COLS, 7);
         case T_MEMORY: return ORC_TABLE("MemoryStark", mem_t, ola::air::mem::NUM_MEM_COLS, 8);
@@ -111,7 +141,29 @@ inline Table table_by_id(int id) {
                               PermutationPair{{{rangecheck::LIMB_HI, rangecheck::LIMB_HI_PERMUTED}}},
                               PermutationPair{{{rangecheck::FIX_RANGE_CHECK_U16, rangecheck::FIX_RANGE_CHECK_U16_PERMUTED_LO}}},
                               PermutationPair{{{rangecheck::FIX_RANGE_CHECK_U16, rangecheck::FIX_RANGE_CHECK_U16_PERMUTED_HI}}}});
-        default: throw std::runtime_error("table not restated yet");
+        case T_POSEIDON: return ORC_TABLE("PoseidonStark", psdn_t, ola::air::psdn::NUM_POSEIDON_COLS, 7);
+        case T_POSEIDON_CHUNK: return ORC_TABLE("PoseidonChunkStark", psdn_chunk_t, ola::air::psdn_chunk::NUM_POSEIDON_CHUNK_COLS, 3);
+        case T_STORAGE: return ORC_TABLE("StorageAccessStark", storage_t, ola::air::storage::NUM_COL_ST, 4);
+        case T_TAPE: return ORC_TABLE("TapeStark", tape_t, ola::air::tape::NUM_COL_TAPE, 5);
+        case T_SCCALL: return ORC_TABLE("SCCallStark", sccall_t, ola::air::sccall::NUM_COL_SCCALL, 1);
+        case T_PROG_CHUNK: return ORC_TABLE("ProgChunkStark", prog_chunk_t, ola::air::prog_chunk::NUM_PROG_CHUNK_COLS, 4);
+        case T_BITWISE: {
+            namespace B = ola::air::bitwise;
+            std::vector<PermutationPair> pp;
+            for (int i = 0; i < 4; ++i) pp.push_back(PermutationPair{{{B::COMPRESS_LIMBS + i, B::COMPRESS_PERMUTED + i}}});
+            for (int i = 0; i < 4; ++i) pp.push_back(PermutationPair{{{B::FIX_COMPRESS, B::FIX_COMPRESS_PERMUTED + i}}});
+            return make_table("BitwiseStark", B::COL_NUM_BITWISE, 3,
+                              [beta](const P<FOps>* lv, const P<FOps>* nv, Consumer<FOps>& yc) { B::eval<P<FOps>, const P<FOps>*, Consumer<FOps>>(lv, nv, yc, P<FOps>::c(beta)); },
+                              [beta](const P<EOps>* lv, const P<EOps>* nv, Consumer<EOps>& yc) { B::eval<P<EOps>, const P<EOps>*, Consumer<EOps>>(lv, nv, yc, P<EOps>::c(beta)); }, pp);
+        }
+        case T_PROGRAM: {
+            namespace G = ola::air::program;
+            return make_table("ProgramStark", G::NUM_PROG_COLS, 3,
+                              [beta](const P<FOps>* lv, const P<FOps>* nv, Consumer<FOps>& yc) { G::eval<P<FOps>, const P<FOps>*, Consumer<FOps>>(lv, nv, yc, P<FOps>::c(beta)); },
+                              [beta](const P<EOps>* lv, const P<EOps>* nv, Consumer<EOps>& yc) { G::eval<P<EOps>, const P<EOps>*, Consumer<EOps>>(lv, nv, yc, P<EOps>::c(beta)); },
+                              {PermutationPair{{{G::COL_PROG_COMP_PROG, G::COL_PROG_COMP_PROG_PERM}}}, PermutationPair{{{G::COL_PROG_EXEC_COMP_PROG, G::COL_PROG_EXEC_COMP_PROG_PERM}}}});
+        }
+        default: throw std::runtime_error("unknown table id");
     }
 }
 
@@ -128,10 +180,16 @@ inline std::vector<CrossTableLookup> all_cross_table_lookups() { return ola::air
 
 /* A proving system = an ordered subset of the 12 tables (proof order = enum order) plus every registered CTL side
  * whose table is inside the subset (table ids remapped to positions).  CTLs losing a side become partial. */
-inline System make_system(const std::vector<int>& ids) {
+inline System make_system(const std::vector<int>& ids, const VF& compress = VF()) {
     System s;
     std::vector<int> pos(T_NUM, -1);
-    for (size_t i = 0; i < ids.size(); i++) { pos[ids[i]] = (int)i; s.tables.push_back(table_by_id(ids[i])); }
+    s.compress_challenges.assign(ids.size(), 0);
+    for (size_t i = 0; i < ids.size(); i++) {
+        pos[ids[i]] = (int)i;
+        F beta = (i < compress.size() && (ids[i] == T_BITWISE || ids[i] == T_PROGRAM)) ? gl_canon(compress[i]) : 0;
+        s.compress_challenges[i] = beta;
+        s.tables.push_back(table_by_id(ids[i], beta));
+    }
     for (auto ctl : all_cross_table_lookups()) {
         CrossTableLookup out;
         out.complete = ctl.has_looked && !ctl.missing_sides;
@@ -145,7 +203,6 @@ inline System make_system(const std::vector<int>& ids) {
         if (out.looking.empty() && !out.has_looked) continue;
         s.ctls.push_back(out);
     }
-    s.compress_challenges.assign(ids.size(), 0);
     return s;
 }
 

@@ -109,3 +109,85 @@ def test_memory_table_alone(ctx, orc):
     rng = np.random.default_rng(77)
     t = tracegen.memory_random_trace(rng, 9)
     assert olavm_b200.prove_with_traces(ctx, [MEM], [t], check_quotient_degree=False) == orc.stark_prove([MEM], [t], check_degree=False)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The other eight tables (Bitwise, Poseidon, PoseidonChunk, StorageAccess, Tape, SCCall, Program, ProgChunk)
+# ---------------------------------------------------------------------------------------------------------------------
+from test_oracle_stark import SINGLE, _valid_single  # noqa: E402  (valid traces shared with the CPU suite)
+
+RANDOM = dict(bitwise=(2, tracegen.bitwise_random_trace), poseidon=(5, tracegen.poseidon_random_trace),
+              poseidon_chunk=(6, tracegen.poseidon_chunk_random_trace), storage=(7, tracegen.storage_random_trace),
+              tape=(8, tracegen.tape_random_trace), sccall=(9, tracegen.sccall_random_trace), program=(10, tracegen.program_random_trace),
+              prog_chunk=(11, tracegen.prog_chunk_random_trace))
+
+
+@pytest.mark.parametrize("name", SINGLE)
+def test_valid_trace_of_each_remaining_table(ctx, orc, name):
+    ids, traces, cc = _valid_single(orc, name)
+    ref = orc.stark_prove(ids, traces, True, compress_challenges=cc)
+    got = olavm_b200.prove_with_traces(ctx, ids, traces, compress_challenges=cc)
+    assert got == ref
+    ok, msg = orc.stark_verify(ids, got)
+    assert ok, msg
+
+
+@pytest.mark.parametrize("name", sorted(RANDOM))
+@pytest.mark.parametrize("log_n", [3, 7])
+def test_pipeline_parity_of_each_remaining_table(ctx, orc, name, log_n):
+    tid, gen = RANDOM[name]
+    rng = np.random.default_rng(500 + 16 * tid + log_n)
+    t = gen(rng, log_n)
+    cc = [int(rng.integers(0, P, dtype=np.uint64))]
+    ref = orc.stark_prove([tid], [t], check_degree=False, compress_challenges=cc)
+    got = olavm_b200.prove_with_traces(ctx, [tid], [t], check_quotient_degree=False, compress_challenges=cc)
+    assert got == ref
+
+
+def test_sccall_degree_quirk_same_bytes(ctx, orc):
+    rng = np.random.default_rng(8)
+    t = tracegen.sccall_valid_trace(rng, 4, used=5)
+    assert olavm_b200.prove_with_traces(ctx, [9], [t]) == orc.stark_prove([9], [t], True)
+
+
+def test_five_table_hash_system(ctx, orc):
+    rng = np.random.default_rng(3)
+    ids, traces, cc = tracegen.hash_system_valid(orc, rng)
+    ref = orc.stark_prove(ids, traces, True, compress_challenges=cc)
+    got = olavm_b200.prove_with_traces(ctx, ids, traces, compress_challenges=cc)
+    assert got == ref
+    ok, msg = orc.stark_verify(ids, got)
+    assert ok, msg
+    # a broken Poseidon round witness is caught by the device-side degree check like the reference's panic
+    bad = [t.copy() for t in traces]
+    bad[0][70, 1] = (int(bad[0][70, 1]) + 1) % P
+    with pytest.raises(olavm_b200.OlaError, match="Quotient has failed"):
+        olavm_b200.prove_with_traces(ctx, ids, bad, compress_challenges=cc)
+
+
+def test_all_twelve_tables_pipeline_parity(ctx, orc):
+    """prove_with_traces over the full Table enum with all 19 cross-table lookups (ola_stark.rs:121-143) on random
+    columns with binary filters: proof bytes equal the oracle's."""
+    rng = np.random.default_rng(2024)
+    logs = {0: 6, 1: 5, 2: 4, 3: 4, 5: 3, 6: 5, 7: 4, 8: 3, 9: 2, 10: 5, 11: 4}
+    traces = []
+    for tid in range(12):
+        if tid == 0:
+            traces.append(tracegen.cpu_random_trace(rng, logs[0]))
+        elif tid == 1:
+            traces.append(tracegen.memory_random_trace(rng, logs[1]))
+        elif tid == 3:
+            traces.append(tracegen.cmp_random_trace(rng, logs[3]))
+        elif tid == 4:
+            traces.append(tracegen.rangecheck_random_trace(rng))
+        else:
+            name = [k for k, v in RANDOM.items() if v[0] == tid][0]
+            traces.append(RANDOM[name][1](rng, logs[tid]))
+    ids = list(range(12))
+    cc = [int(x) for x in rng.integers(0, P, size=12, dtype=np.uint64)]
+    ref = orc.stark_prove(ids, traces, check_degree=False, compress_challenges=cc)
+    got = olavm_b200.prove_with_traces(ctx, ids, traces, check_quotient_degree=False, compress_challenges=cc)
+    assert got == ref
+    # the wire format's trailing compress_challenges carry only the Bitwise and Program entries (prover.rs:307-320)
+    tail = np.frombuffer(got[-12 * 8:], dtype="<u8")
+    assert [int(x) for x in tail] == [cc[i] if i in (2, 10) else 0 for i in range(12)]

@@ -43,6 +43,25 @@ def test_poseidon_round_tables(orc, golden):
     assert r["POSEIDON_ZERO_HASH_OUTPUT"] == golden["kat"][0]["output"]
 
 
+def test_poseidon_table_row_golden(orc, golden):
+    # the Poseidon TABLE's witness row (S-box inputs per round) against the reference's per-round tables
+    # (core/src/util/poseidon_utils.rs:11-287, used by generation/poseidon.rs:83-126 as the padding row)
+    r = golden["rounds"]
+    for tag in ("ZERO", "1000"):
+        row = orc.poseidon_table_row(u64(r[f"POSEIDON_{tag}_HASH_INPUT"])).tolist()
+        assert row[0:4] == [0, 0, 0, 0]
+        assert row[4:16] == r[f"POSEIDON_{tag}_HASH_INPUT"]
+        assert row[16:28] == r[f"POSEIDON_{tag}_HASH_OUTPUT"]
+        assert row[28:40] == r[f"POSEIDON_{tag}_HASH_FULL_0_1"]
+        assert row[40:52] == r[f"POSEIDON_{tag}_HASH_FULL_0_2"]
+        assert row[52:64] == r[f"POSEIDON_{tag}_HASH_FULL_0_3"]
+        assert row[64:86] == r[f"POSEIDON_{tag}_HASH_PARTIAL"]
+        assert row[86:98] == r[f"POSEIDON_{tag}_HASH_FULL_1_0"]
+        assert row[98:110] == r[f"POSEIDON_{tag}_HASH_FULL_1_1"]
+        assert row[110:122] == r[f"POSEIDON_{tag}_HASH_FULL_1_2"]
+        assert row[122:134] == r[f"POSEIDON_{tag}_HASH_FULL_1_3"]
+
+
 def test_noncanonical_inputs_are_the_same_element(orc):
     s = orc.rand_elems(7, 12)
     s[:3] = u64([0, 1, 2])

@@ -148,3 +148,340 @@ def rangecheck_random_trace(rng, log_n=16):
     for c in range(4):
         t[c] = rng.integers(0, 2, size=n)
     return t
+
+
+# ======================================================================================================================
+# The remaining eight tables: random (pipeline-parity) traces with binary CTL filters, and VALID traces built by
+# construction from each table's constraints (circuits/src/builtins/*/, circuits/src/program/*).
+# ======================================================================================================================
+OP_AND, OP_OR, OP_XOR, OP_POSEIDON = 1 << 18, 1 << 17, 1 << 16, 1 << 12  # core/src/program/binary_program.rs OlaOpcode masks
+OP_TLOAD, OP_TSTORE, OP_SCCALL = 1 << 9, 1 << 8, 1 << 7
+
+NCOLS = dict(bitwise=59, poseidon=134, poseidon_chunk=53, storage=48, tape=6, sccall=26, program=18, prog_chunk=40)
+
+
+def _rand(rng, shape):
+    return rng.integers(0, P, size=shape, dtype=np.uint64)
+
+
+def bitwise_random_trace(rng, log_n):
+    return random_binary_filter_trace(rng, 59, log_n, [0])
+
+
+def poseidon_random_trace(rng, log_n):
+    n = 1 << log_n
+    t = random_binary_filter_trace(rng, 134, log_n, [0, 1])
+    pick = rng.integers(0, 3, size=n)  # filter_looked_storage_leaf + _branch is one CTL filter
+    t[2] = (pick == 1)
+    t[3] = (pick == 2)
+    return t
+
+
+def poseidon_chunk_random_trace(rng, log_n):
+    return random_binary_filter_trace(rng, 53, log_n, [33, 42, 51] + list(range(43, 51)))
+
+
+def storage_random_trace(rng, log_n):
+    n = 1 << log_n
+    t = random_binary_filter_trace(rng, 48, log_n, [44, 45])
+    pick = rng.integers(0, 3, size=n)  # is_layer_256 - filter_is_for_prog must be a bit
+    t[42] = (pick >= 1)
+    t[46] = (pick == 2)
+    return t
+
+
+def tape_random_trace(rng, log_n):
+    return random_binary_filter_trace(rng, 6, log_n, [5])
+
+
+def sccall_random_trace(rng, log_n):
+    return random_binary_filter_trace(rng, 26, log_n, [25])
+
+
+def program_random_trace(rng, log_n):
+    return random_binary_filter_trace(rng, 18, log_n, [16, 17])
+
+
+def prog_chunk_random_trace(rng, log_n):
+    return random_binary_filter_trace(rng, 40, log_n, [30, 39] + list(range(31, 39)))
+
+
+# ---------------------------------------------------------------------------------------------------------- valid traces
+def tape_valid_trace(rng, log_n):
+    """Tape table (tape/columns.rs:3-9): tx 0 = an init segment (addr 0..3) then tstore / tload / sccall rows; the rest of
+    the table is tx 1: one init row then tload repeats of it (every constraint of tape_stark.rs:59-137 holds)."""
+    n = 1 << log_n
+    assert n >= 16
+    rows = []
+    for a in range(4):
+        rows.append((0, 1, 0, a, int(rng.integers(0, P, dtype=np.uint64)), 0))
+    v4, v5 = int(rng.integers(0, P, dtype=np.uint64)), int(rng.integers(0, P, dtype=np.uint64))
+    rows += [(0, 0, OP_TSTORE, 4, v4, 1), (0, 0, OP_TLOAD, 4, v4, 0), (0, 0, OP_SCCALL, 5, v5, 1), (0, 0, OP_TLOAD, 5, v5, 1)]
+    w = int(rng.integers(0, P, dtype=np.uint64))
+    rows.append((1, 1, 0, 0, w, 0))
+    while len(rows) < n:
+        rows.append((1, 1, OP_TLOAD, 0, w, 0))
+    return np.array(rows, dtype=np.uint64).T.copy()
+
+
+def sccall_valid_trace(rng, log_n, used=None):
+    n = 1 << log_n
+    used = n // 2 if used is None else used
+    t = np.zeros((26, n), dtype=np.uint64)
+    t[:, :used] = _rand(rng, (26, used))
+    t[10, :used] = rng.integers(0, 1 << 32, size=used)
+    t[11, :used] = rng.integers(0, 1 << 32, size=used)
+    t[12, :used] = t[11, :used] + t[10, :used]  # clk_caller_ret = clk_caller_call + op1_imm
+    t[25, :used] = 0
+    t[25, used:] = 1
+    return t
+
+
+def _horner(vals, beta):
+    acc = 0
+    for v in reversed(vals):
+        acc = (acc * beta + int(v)) % P
+    return acc
+
+
+def program_valid_trace(rng, log_n, beta, prog_rows=None, n_exec=None):
+    """Program table (program/columns.rs:3-16).  prog_rows: list of (addr0..3, pc, inst) program lines (default random);
+    the executed lines are drawn from them.  comp = sum_i x_i beta^i (program_stark.rs:70-88); the permuted columns by
+    lookup.rs permuted_cols."""
+    n = 1 << log_n
+    if prog_rows is None:
+        prog_rows = [tuple(int(x) for x in _rand(rng, 6)) for _ in range(n // 2)]
+    assert len(prog_rows) < n
+    n_exec = n // 2 if n_exec is None else n_exec
+    t = np.zeros((18, n), dtype=np.uint64)
+    for i, r in enumerate(prog_rows):
+        t[0:6, i] = r
+        t[6, i] = _horner(r, beta)
+        t[17, i] = 1
+    for i in range(n_exec):
+        r = prog_rows[int(rng.integers(0, len(prog_rows)))]
+        t[8:14, i] = r
+        t[14, i] = _horner(r, beta)
+        t[16, i] = 1
+    t[15], t[7] = permuted_cols(t[14], t[6])
+    return t
+
+
+def bitwise_valid_trace(rng, log_n, beta, n_ops=None):
+    """Bitwise table (bitwise/columns.rs:23-48): byte-limb decompositions, beta-compressed (tag, a, b, r) byte triples
+    looked up in FIX_COMPRESS, byte range checks against FIX_RANGE_CHECK_U8."""
+    n = 1 << log_n
+    assert n >= 256
+    n_ops = min(n // 8, 60) if n_ops is None else n_ops
+    t = np.zeros((59, n), dtype=np.uint64)
+    fixed = {(0, 0, 0, 0)}
+    for i in range(n_ops):
+        tag = [OP_AND, OP_OR, OP_XOR][int(rng.integers(0, 3))]
+        a, b = int(rng.integers(0, 1 << 32)), int(rng.integers(0, 1 << 32))
+        r = a & b if tag == OP_AND else (a | b if tag == OP_OR else a ^ b)
+        t[0:5, i] = [1, tag, a, b, r]
+        for j in range(4):
+            la, lb, lr = (a >> 8 * j) & 255, (b >> 8 * j) & 255, (r >> 8 * j) & 255
+            t[5 + j, i], t[9 + j, i], t[13 + j, i] = la, lb, lr
+            t[29 + j, i] = (tag + beta * la + beta * beta % P * lb + pow(beta, 3, P) * lr) % P
+            fixed.add((tag, la, lb, lr))
+    assert len(fixed) <= n
+    fix = np.minimum(np.arange(n, dtype=np.uint64), np.uint64(255))
+    t[37] = fix
+    for j in range(4):
+        t[17 + j], t[38 + j] = permuted_cols(t[5 + j], fix)
+        t[21 + j], t[42 + j] = permuted_cols(t[9 + j], fix)
+        t[25 + j], t[46 + j] = permuted_cols(t[13 + j], fix)
+    for i, (tag, la, lb, lr) in enumerate(sorted(fixed)):
+        t[50:54, i] = [tag, la, lb, lr]
+        t[54, i] = (tag + beta * la + beta * beta % P * lb + pow(beta, 3, P) * lr) % P
+    for j in range(4):
+        t[33 + j], t[55 + j] = permuted_cols(t[29 + j], t[54])
+    return t
+
+
+def poseidon_valid_trace(orc, log_n, rows):
+    """Poseidon table from (input[12], filters[4]) pairs; padding = the zero-input row (generation/poseidon.rs:83-126)."""
+    n = 1 << log_n
+    assert len(rows) <= n
+    t = np.zeros((134, n), dtype=np.uint64)
+    t[:, :] = orc.poseidon_table_row(np.zeros(12, dtype=np.uint64))[:, None]
+    for i, (inp, filt) in enumerate(rows):
+        r = orc.poseidon_table_row(np.array(inp, dtype=np.uint64))
+        r[0:4] = filt
+        t[:, i] = r
+    return t
+
+
+def prog_chunk_valid_trace(orc, rng, log_n, line_counts=(1, 3, 2)):
+    """ProgChunk table (program/columns.rs:47-62): per program, lines of 8 instructions absorbed by a Poseidon sponge
+    (cap = previous line's hash[8..12]).  Returns (trace, poseidon_rows, program_lines, prog_hashes):
+    poseidon_rows = the (input, output) pairs the lines look up; program_lines = (addr0..3, pc, inst) with filter 1."""
+    n = 1 << log_n
+    t = np.zeros((40, n), dtype=np.uint64)
+    t[39] = 1
+    row = 0
+    psdn, lines, roots = [], [], []
+    for L in line_counts:
+        addr = [int(x) for x in _rand(rng, 4)]
+        cap = [0, 0, 0, 0]
+        for j in range(L):
+            last = j == L - 1
+            cnt = int(rng.integers(1, 9)) if last else 8
+            inst = [int(x) for x in _rand(rng, 8)]
+            for k in range(cnt, 8):
+                inst[k] = 0
+            h = [int(x) for x in orc.poseidon(np.array(inst + cap, dtype=np.uint64))]
+            t[0:4, row] = addr
+            t[4, row] = 8 * j
+            t[5:13, row] = inst
+            t[13:17, row] = cap
+            t[17:29, row] = h
+            t[29, row] = 1 if j == 0 else 0
+            t[30, row] = 1 if last else 0
+            t[31:39, row] = [1 if k < cnt else 0 for k in range(8)]
+            t[39, row] = 0
+            psdn.append((inst + cap, h))
+            for k in range(cnt):
+                lines.append(tuple(addr) + (8 * j + k, inst[k]))
+            cap = h[8:12]
+            if last:
+                roots.append((addr, h[0:4]))
+            row += 1
+    assert row <= n
+    return t, psdn, lines, roots
+
+
+def poseidon_chunk_valid_trace(orc, rng, log_n, lengths=(5, 8, 19)):
+    """PoseidonChunk table (poseidon/columns.rs:44-71): one main line + ceil(len/8) ext lines per hash call.
+    Returns (trace, poseidon_rows)."""
+    n = 1 << log_n
+    t = np.zeros((53, n), dtype=np.uint64)
+    t[52] = 1
+    row = 0
+    psdn = []
+    for ci, L in enumerate(lengths):
+        tx, env, clk, op0, dst = 0, 0, 10 + 7 * ci, 1000 + 64 * ci, 5000 + 16 * ci
+        t[0:8, row] = [tx, env, clk, OP_POSEIDON, op0, L, dst, 0]
+        t[42, row] = 1
+        t[52, row] = 0
+        row += 1
+        vals = [int(x) for x in _rand(rng, L)]
+        cap, acc = [0, 0, 0, 0], 0
+        n_ext = (L + 7) // 8
+        for e in range(n_ext):
+            cnt = min(8, L - 8 * e)
+            v = vals[8 * e : 8 * e + cnt] + [0] * (8 - cnt)
+            h = [int(x) for x in orc.poseidon(np.array(v + cap, dtype=np.uint64))]
+            acc += cnt
+            t[0:8, row] = [tx, env, clk, OP_POSEIDON, op0 + 8 * e, L, dst, acc]
+            t[8:16, row] = v
+            t[16:20, row] = cap
+            t[20:32, row] = h
+            t[32, row] = 1
+            t[33, row] = 1 if e == n_ext - 1 else 0
+            if cnt < 8:
+                t[34 + cnt, row] = 1
+            t[43:51, row] = [1 if k < cnt else 0 for k in range(8)]
+            t[51, row] = 1
+            t[52, row] = 0
+            psdn.append((v + cap, h))
+            cap = h[8:12]
+            row += 1
+    assert row <= n
+    return t, psdn
+
+
+def storage_valid_trace(orc, rng, log_n, accesses):
+    """StorageAccess table (storage/columns.rs:3-33): 256 rows per access walking the sparse Merkle tree from layer 1
+    (root) to layer 256 (leaf).  accesses: list of dict(addr_bits=[256 bits, layer 1 first], leaf=[4], pre_leaf=[4],
+    is_write, for_prog).  Hashes are real Poseidon hashes of (path, sib | hash_type) in bit order, so the rows are
+    consistent with ctl_storage_access_poseidon.  Returns (trace, poseidon_rows) with poseidon_rows =
+    (input[12], output[12], is_leaf) for every looked-up hash (current and pre)."""
+    n = 1 << log_n
+    assert 256 * len(accesses) <= n
+    t = np.zeros((48, n), dtype=np.uint64)
+    psdn = []
+    prev_root = None
+    row0 = 0
+    for ai, acc in enumerate(accesses):
+        bits = acc["addr_bits"]
+        sib = [[int(x) for x in _rand(rng, 4)] for _ in range(256)]
+        # bottom-up: path_l = hash of the child at layer l + 1 (the leaf value at layer 256)
+        path = [None] * 257
+        pre_path = [None] * 257
+        hsh = [None] * 257
+        pre_hsh = [None] * 257
+        path[256], pre_path[256] = list(acc["leaf"]), list(acc["pre_leaf"])
+        for l in range(256, 0, -1):
+            typ = 1 if l == 256 else 0
+            for cur, pth, out in ((True, path, hsh), (False, pre_path, pre_hsh)):
+                inp = (pth[l] + sib[l - 1] if bits[l - 1] == 0 else sib[l - 1] + pth[l]) + [typ, 0, 0, 0]
+                o = [int(x) for x in orc.poseidon(np.array(inp, dtype=np.uint64))]
+                out[l] = o[0:4]
+                psdn.append((inp, o, l == 256))
+            if l > 1:
+                path[l - 1], pre_path[l - 1] = hsh[l], pre_hsh[l]
+        root, pre_root = hsh[1], pre_hsh[1]
+        if prev_root is not None:
+            assert pre_root == prev_root, "accesses must chain: pre_root of an access is the previous access's root"
+        prev_root = root
+        limbs = []
+        for k in range(4):
+            v = 0
+            for b in bits[64 * k : 64 * k + 64]:
+                v = (2 * v + b) % P
+            limbs.append(v)
+        accv, marker = 0, 0
+        for l in range(1, 257):
+            r = row0 + l - 1
+            b = bits[l - 1]
+            accv = b if l % 64 == 1 else (2 * accv + b) % P
+            marker += 1 if l in (1, 64, 128, 192, 256) else 0
+            t[0, r] = ai + 1
+            t[1:5, r] = pre_root
+            t[5:9, r] = root
+            t[9, r] = acc["is_write"]
+            t[10, r] = l
+            t[11, r] = b
+            t[12, r] = accv
+            t[13:17, r] = limbs
+            t[17:21, r] = pre_path[l]
+            t[21:25, r] = path[l]
+            t[25:29, r] = sib[l - 1]
+            t[29, r] = 1 if l == 256 else 0
+            t[30:34, r] = pre_hsh[l]
+            t[34:38, r] = hsh[l]
+            for k, ll in enumerate((1, 64, 128, 192, 256)):
+                t[38 + k, r] = 1 if l == ll else 0
+            t[43, r] = marker
+            t[44, r] = 1 - b
+            t[45, r] = b
+            t[46, r] = 1 if (l == 256 and acc.get("for_prog")) else 0
+        row0 += 256
+    for r in range(row0, n):
+        t[47, r] = 1
+        t[5:9, r] = prev_root
+    return t, psdn
+
+
+def hash_system_valid(orc, rng, beta=0x1234567890ABCDEF % P):
+    """A VALID five-table system [Poseidon, PoseidonChunk, StorageAccess, Program, ProgChunk] whose cross-table lookups
+    ctl_chunk_poseidon, ctl_storage_access_poseidon, ctl_prog_chunk_prog and ctl_prog_chunk_storage (ola_stark.rs:358-379,
+    :388-413, :530-563) are complete and consistent: one program of three lines is hashed by ProgChunk, its lines are the
+    Program table, its root is read from the storage tree (256-layer Merkle walk), two Poseidon calls go through
+    PoseidonChunk, and every sponge / Merkle hash is a row of the Poseidon table.
+    Returns (table_ids, traces, compress_challenges)."""
+    pc, psdn_prog, lines, roots = prog_chunk_valid_trace(orc, rng, 2, line_counts=(3,))
+    pch, psdn_chunk = poseidon_chunk_valid_trace(orc, rng, 3, lengths=(5, 16))
+    addr, leaf = roots[0]
+    bits = []
+    for limb in addr:
+        bits += [(int(limb) >> (63 - j)) & 1 for j in range(64)]
+    st, psdn_st = storage_valid_trace(orc, rng, 8, [dict(addr_bits=bits, leaf=leaf, pre_leaf=leaf, is_write=0, for_prog=1)])
+    rows = [(inp, [1, 0, 0, 0]) for inp, _ in psdn_prog + psdn_chunk]
+    rows += [(inp, [0, 0, 1, 0] if is_leaf else [0, 0, 0, 1]) for inp, _, is_leaf in psdn_st]
+    ps = poseidon_valid_trace(orc, 10, rows)
+    prog = program_valid_trace(rng, 5, beta, prog_rows=lines, n_exec=7)
+    ids = [5, 6, 7, 10, 11]
+    return ids, [ps, pch, st, prog, pc], [0, 0, 0, beta, 0]

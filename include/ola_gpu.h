@@ -113,6 +113,18 @@ int ola_merkle_rows(ola_ctx* ctx, const uint64_t* rows, int on_device, size_t nr
  * (column-major, leaf order), heap-ordered Merkle nodes.  cap_out_host receives 2^cap_height hashes. */
 int ola_commit(ola_ctx* ctx, const uint64_t* cols, int on_device, size_t ncols, uint32_t log_n, int is_coeffs,
                uint32_t rate_bits, uint32_t cap_height, ola_batch** out, uint64_t* cap_out_host);
+/* One rank's COSET SHARD of the same commitment (multi-GPU, one process per GPU): only LDE cosets
+ * [coset_first, coset_first + coset_count) are evaluated, hashed and reduced.  coset_count is a power of two
+ * dividing 2^rate_bits, coset_first a multiple of it, and 2^cap_height >= 2^rate_bits / coset_count.  Leaf block i
+ * of the tree is exactly coset 7 * g^bitrev(i) * H_n (evaluate_poly_with_offset's global bit-reversal and
+ * oracle.rs:84-85's leaf bit-reversal cancel), so the shard is a contiguous leaf range = whole cap subtrees: the
+ * batch holds leaves [coset_first * n, (coset_first + coset_count) * n) (accessors take indices RELATIVE to that
+ * range) and cap_slots_out_host receives the global cap entries
+ * [coset_first, coset_first + coset_count) * 2^cap_height / 2^rate_bits.  Assembling the cap is one all-gather of
+ * those entries; Merkle paths never leave the shard (they stop at the cap). */
+int ola_commit_shard(ola_ctx* ctx, const uint64_t* cols, int on_device, size_t ncols, uint32_t log_n, int is_coeffs,
+                     uint32_t rate_bits, uint32_t cap_height, uint32_t coset_first, uint32_t coset_count, ola_batch** out,
+                     uint64_t* cap_slots_out_host);
 int ola_batch_free(ola_ctx* ctx, ola_batch* b);
 /* shape queries */
 size_t ola_batch_ncols(const ola_batch* b);

@@ -356,12 +356,12 @@ int ola_merkle_rows(ola_ctx* ctx, const uint64_t* rows, int on_device, size_t nr
     });
 }
 
-int ola_commit(ola_ctx* ctx, const uint64_t* cols, int on_device, size_t ncols, uint32_t log_n, int is_coeffs,
-               uint32_t rate_bits, uint32_t cap_height, ola_batch** out, uint64_t* cap_out_host) {
+static int commit_impl(ola_ctx* ctx, const uint64_t* cols, int on_device, size_t ncols, uint32_t log_n, int is_coeffs, uint32_t rate_bits,
+                       uint32_t cap_height, int coset_first, int coset_count, ola_batch** out, uint64_t* cap_out_host) {
     if (!ctx || !out) return OLA_ERR_INVALID_ARG;
     *out = nullptr;
     return guarded(ctx, [&] {
-        ola_batch* b = ola::batch_commit(ctx, cols, on_device != 0, ncols, log_n, is_coeffs != 0, rate_bits, cap_height);
+        ola_batch* b = ola::batch_commit(ctx, cols, on_device != 0, ncols, log_n, is_coeffs != 0, rate_bits, cap_height, coset_first, coset_count);
         try {
             if (cap_out_host)
                 ola::batch_get_cap(ctx, b, cap_out_host);
@@ -374,6 +374,16 @@ int ola_commit(ola_ctx* ctx, const uint64_t* cols, int on_device, size_t ncols, 
         }
         *out = b;
     });
+}
+int ola_commit(ola_ctx* ctx, const uint64_t* cols, int on_device, size_t ncols, uint32_t log_n, int is_coeffs, uint32_t rate_bits,
+               uint32_t cap_height, ola_batch** out, uint64_t* cap_out_host) {
+    return commit_impl(ctx, cols, on_device, ncols, log_n, is_coeffs, rate_bits, cap_height, 0, -1, out, cap_out_host);
+}
+int ola_commit_shard(ola_ctx* ctx, const uint64_t* cols, int on_device, size_t ncols, uint32_t log_n, int is_coeffs, uint32_t rate_bits,
+                     uint32_t cap_height, uint32_t coset_first, uint32_t coset_count, ola_batch** out, uint64_t* cap_slots_out_host) {
+    if (coset_count == 0 || coset_count > 64 || coset_first > 64) return OLA_ERR_INVALID_ARG;
+    return commit_impl(ctx, cols, on_device, ncols, log_n, is_coeffs, rate_bits, cap_height, (int)coset_first, (int)coset_count, out,
+                       cap_slots_out_host);
 }
 
 int ola_prove(ola_ctx* ctx, const int* table_ids, uint32_t ntables, const uint64_t* const* traces, int on_device, const uint32_t* log_ns,

@@ -96,11 +96,21 @@ void gather_rows(ola_ctx* ctx, const uint64_t* d_cols, size_t col_stride, size_t
 }
 
 ola_batch* batch_commit(ola_ctx* ctx, const uint64_t* cols, bool on_device, size_t ncols, uint32_t log_n, bool is_coeffs,
-                        uint32_t rate_bits, uint32_t cap_height) {
+                        uint32_t rate_bits, uint32_t cap_height, int coset_first, int coset_count) {
     OLA_CHECK(cols != nullptr && ncols > 0, OLA_ERR_INVALID_ARG, "commit: empty batch");
     OLA_CHECK(log_n + rate_bits <= 32, OLA_ERR_INVALID_ARG, "commit: LDE size exceeds the field's two-adicity (2^32)");
     OLA_CHECK(cap_height <= log_n + rate_bits, OLA_ERR_INVALID_ARG, "commit: cap height should be at most log2(leaves)");
     OLA_CHECK((1u << rate_bits) <= (unsigned)ntt::MAX_COSETS, OLA_ERR_INVALID_ARG, "commit: rate_bits too large");
+    if (coset_count < 0) {
+        coset_first = 0;
+        coset_count = 1 << rate_bits;
+    }
+    uint32_t shard_bits = 0;
+    while ((1 << shard_bits) < coset_count) ++shard_bits;
+    OLA_CHECK((1 << shard_bits) == coset_count && coset_count <= (1 << rate_bits) && coset_first >= 0 && coset_first % coset_count == 0 &&
+                  coset_first + coset_count <= (1 << rate_bits),
+              OLA_ERR_INVALID_ARG, "commit: a coset shard is an aligned power-of-two range of the 2^rate_bits cosets");
+    OLA_CHECK(cap_height >= rate_bits - shard_bits, OLA_ERR_INVALID_ARG, "commit: the cap must be at least as fine as the coset partition");
     std::unique_ptr<ola_batch, void (*)(ola_batch*)> b(new ola_batch(), [](ola_batch* p) {
         batch_release(p);
         delete p;
@@ -109,7 +119,9 @@ ola_batch* batch_commit(ola_ctx* ctx, const uint64_t* cols, bool on_device, size
     b->log_n = log_n;
     b->rate_bits = rate_bits;
     b->cap_height = cap_height;
-    const size_t n = (size_t)1 << log_n, L = n << rate_bits;
+    b->shard_bits = shard_bits;
+    b->coset_first = (uint32_t)coset_first;
+    const size_t n = (size_t)1 << log_n, L = n << shard_bits;
     dev_alloc(&b->d_coeffs, ncols * n);
     dev_alloc(&b->d_lde, ncols * L);
     dev_alloc(&b->d_nodes, 2 * L * 4);
@@ -138,7 +150,7 @@ ola_batch* batch_commit(ola_ctx* ctx, const uint64_t* cols, bool on_device, size
         uint64_t* tmp_work = nullptr;
         if (!on_device) {
             d.work = stage;
-        } else if (rate_bits >= 1) {
+        } else if (shard_bits >= 1) {
             d.work = stage;
         } else {
             dev_alloc(&tmp_work, ncols * n);
@@ -177,6 +189,8 @@ ola_batch* batch_commit(ola_ctx* ctx, const uint64_t* cols, bool on_device, size
         d.ncols = ncols;
         d.log_n = (int)log_n;
         d.coset_bits = (int)rate_bits;
+        d.coset_first = coset_first;
+        d.coset_count = coset_count;
         d.shift = gl::GEN;
         d.tag_strided = "lde_strided";
         d.tag_contig = "lde_contig";
@@ -184,7 +198,7 @@ ola_batch* batch_commit(ola_ctx* ctx, const uint64_t* cols, bool on_device, size
     }
     // MerkleTree::new_v2: leaf digests then level reduction down to the cap
     poseidon::hash_rows_colmajor(ctx, b->d_lde, L, L, ncols, b->d_nodes + 4 * L);
-    poseidon::merkle_levels(ctx, b->d_nodes, L, (size_t)1 << cap_height);
+    poseidon::merkle_levels(ctx, b->d_nodes, L, (size_t)1 << b->local_cap_height());
     return b.release();
 }
 
@@ -197,24 +211,25 @@ void batch_release(ola_batch* b) {
 }
 
 void batch_get_cap(ola_ctx* ctx, const ola_batch* b, uint64_t* cap_host) {
-    const size_t L = (size_t)1 << (b->log_n + b->rate_bits), ncap = (size_t)1 << b->cap_height;
-    // cap = nodes[2^h .. 2^(h+1)); when the tree is all cap these are the leaf digests (mod.rs:216-225)
+    const size_t L = (size_t)1 << b->leaf_bits(), ncap = (size_t)1 << b->local_cap_height();
+    // cap = nodes[2^h .. 2^(h+1)); when the tree is all cap these are the leaf digests (mod.rs:216-225).
+    // For a coset shard these are the global cap entries [coset_first, +2^shard_bits) * 2^(cap_height - rate_bits).
     OLA_CUDA(cudaMemcpyAsync(cap_host, b->d_nodes + 4 * ncap, ncap * 32, cudaMemcpyDeviceToHost, ctx->stream));
     OLA_CUDA(cudaStreamSynchronize(ctx->stream));
     (void)L;
 }
 
 void batch_get_leaves(ola_ctx* ctx, const ola_batch* b, size_t first, size_t count, uint64_t* out_host) {
-    const size_t L = (size_t)1 << (b->log_n + b->rate_bits);
+    const size_t L = (size_t)1 << b->leaf_bits();
     OLA_CHECK(first + count <= L, OLA_ERR_INVALID_ARG, "get_leaves: leaf index out of range");
     gather_rows(ctx, b->d_lde, L, b->ncols, first, count, out_host);
 }
 
 int batch_prove_leaf(ola_ctx* ctx, const ola_batch* b, size_t leaf, uint64_t* sib_host) {
-    const uint32_t lg = b->log_n + b->rate_bits;
+    const uint32_t lg = b->leaf_bits();
     const size_t L = (size_t)1 << lg;
     OLA_CHECK(leaf < L, OLA_ERR_INVALID_ARG, "prove_leaf: leaf index out of range");
-    const int nsib = (int)lg - (int)b->cap_height;
+    const int nsib = (int)lg - (int)b->local_cap_height();
     if (nsib <= 0) return 0;
     uint64_t* tmp = nullptr;
     dev_alloc(&tmp, (size_t)nsib * 4);

@@ -7,9 +7,14 @@
 struct ola_batch {
     size_t ncols = 0;
     uint32_t log_n = 0, rate_bits = 0, cap_height = 0;
+    // coset shard: this batch holds LDE cosets [coset_first, coset_first + 2^shard_bits) = a contiguous
+    // leaf range = whole cap subtrees of the global Merkle tree.  A full batch has shard_bits == rate_bits.
+    uint32_t shard_bits = 0, coset_first = 0;
     uint64_t* d_coeffs = nullptr;  // [ncols][n]
-    uint64_t* d_lde = nullptr;     // [ncols][n << rate_bits]  leaf order
-    uint64_t* d_nodes = nullptr;   // [2 * (n << rate_bits)][4] heap order
+    uint64_t* d_lde = nullptr;     // [ncols][n << shard_bits]  leaf order
+    uint64_t* d_nodes = nullptr;   // [2 * (n << shard_bits)][4] heap order (the global subtree over this leaf range)
+    uint32_t leaf_bits() const { return log_n + shard_bits; }
+    uint32_t local_cap_height() const { return cap_height - (rate_bits - shard_bits); }  // cap level inside the local subtree
 };
 
 namespace ola {
@@ -23,7 +28,7 @@ uint64_t* ctx_scratch(ola_ctx* ctx, size_t n_u64);
 void gather_rows(ola_ctx* ctx, const uint64_t* d_cols, size_t col_stride, size_t ncols, size_t first, size_t count,
                  uint64_t* out_host);
 ola_batch* batch_commit(ola_ctx* ctx, const uint64_t* cols, bool on_device, size_t ncols, uint32_t log_n, bool is_coeffs,
-                        uint32_t rate_bits, uint32_t cap_height);
+                        uint32_t rate_bits, uint32_t cap_height, int coset_first = 0, int coset_count = -1);
 void batch_release(ola_batch* b);
 void batch_get_cap(ola_ctx* ctx, const ola_batch* b, uint64_t* cap_host);
 void batch_get_leaves(ola_ctx* ctx, const ola_batch* b, size_t first, size_t count, uint64_t* out_host);

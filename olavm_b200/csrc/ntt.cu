@@ -565,13 +565,16 @@ void forward(ola_ctx* ctx, const FwdDesc& d) {
     OLA_CHECK(d.log_n <= 32 - d.coset_bits, OLA_ERR_INVALID_ARG, "NTT size exceeds the field's two-adicity (2^32)");
     OLA_CHECK((1 << d.coset_bits) <= MAX_COSETS, OLA_ERR_INVALID_ARG, "too many cosets");
     if (d.ncols == 0) return;
-    const int L = d.log_n, ncosets = 1 << d.coset_bits;
+    const int L = d.log_n, all_cosets = 1 << d.coset_bits;
+    const int ncosets = d.coset_count < 0 ? all_cosets : d.coset_count;
+    OLA_CHECK(d.coset_first >= 0 && ncosets >= 1 && d.coset_first + ncosets <= all_cosets, OLA_ERR_INVALID_ARG, "coset range out of bounds");
+    OLA_CHECK(!(d.natural_output && ncosets != all_cosets), OLA_ERR_INVALID_ARG, "natural-order LDE output needs every coset");
     const int dir = d.inverse_roots ? 1 : 0;
     // coset i evaluates on shift * g^{bitrev(i)} * H_n, g = omega_{n * ncosets}  (cfft/serial.rs:36-38)
     uint64_t g = gl::root_of_unity(L + d.coset_bits);
     if (d.inverse_roots) g = gl::inv(g);
     uint64_t shifts[MAX_COSETS];
-    for (int i = 0; i < ncosets; ++i) shifts[i] = gl::mul(d.shift, gl::pow(g, gl::bitrev32((uint32_t)i, d.coset_bits)));
+    for (int i = 0; i < ncosets; ++i) shifts[i] = gl::mul(d.shift, gl::pow(g, gl::bitrev32((uint32_t)(d.coset_first + i), d.coset_bits)));
 
     std::vector<int> plan = plan_passes(L);
     int M = L;

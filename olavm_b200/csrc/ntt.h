@@ -25,6 +25,8 @@ struct FwdDesc {
     size_t ncols = 0;
     int log_n = 0;
     int coset_bits = 0;        // 2^coset_bits cosets shift * g^{bitrev(i)} * H_n (blowup of an LDE)
+    int coset_first = 0;       // compute only cosets [coset_first, coset_first + coset_count) (a rank's shard of the LDE);
+    int coset_count = -1;      // -1: all.  Output coset k of the range lands at dst + k * dst_coset_stride.
     uint64_t shift = 1;        // domain offset
     bool inverse_roots = false;  // use omega^-1 (values -> coefficients)
     bool natural_output = false;

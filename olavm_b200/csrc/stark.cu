@@ -31,10 +31,15 @@ using air::Row;
 struct DevLc {
     int off, cnt;
     uint64_t constant;
+    int single;  // >= 0: the combination is exactly that trace column (Column::single) -- no multiply
+    int pad_;
 };
 struct DevCtl {
     int col_off, col_cnt;  // into lcs[]
     int filter;            // index into lcs[] or -1
+    int twin;              // the instance over the same columns with the next challenge pair, or -1
+    int is_twin;           // this instance is evaluated together with an earlier one (its `twin`)
+    int pad_;
     uint64_t beta, gamma;
 };
 struct DevPermInst {
@@ -58,8 +63,13 @@ struct DevTables {  // all arrays live in one device allocation
 
 __device__ __forceinline__ Fp eval_lc(const DevTables& d, int k, const uint64_t* __restrict__ base, size_t stride, size_t r) {
     const DevLc lc = d.lcs[k];
+    if (lc.single >= 0) return Fp(__ldg(base + (size_t)lc.single * stride + r));
     Fp s(0);
-    for (int i = 0; i < lc.cnt; ++i) s += Fp(__ldg(base + (size_t)d.lc_col[lc.off + i] * stride + r)) * Fp(d.lc_coef[lc.off + i]);
+    for (int i = 0; i < lc.cnt; ++i) {
+        const Fp v(__ldg(base + (size_t)d.lc_col[lc.off + i] * stride + r));
+        const uint64_t k = d.lc_coef[lc.off + i];
+        s += k == 1 ? v : v * Fp(k);
+    }
     return s + Fp(lc.constant);
 }
 // GrandProductChallenge::combine (permutation.rs:61-72): reduce_with_powers(terms, beta) + gamma
@@ -179,6 +189,7 @@ struct QuotArgs {
     DevTables d;
     int num_perm_zs;
     uint64_t compress_challenge;  // Bitwise / Program only (canonical)
+    const uint64_t* apow;         // [2][2*nctl + 1]: alpha_j^k, weights of the CTL section's constraints
 };
 
 __device__ __forceinline__ uint64_t pow_omega_fwd(const uint64_t* __restrict__ pw, uint32_t E) {
@@ -188,10 +199,11 @@ __device__ __forceinline__ uint64_t pow_omega_fwd(const uint64_t* __restrict__ p
 }
 
 template <class Air>
-__global__ void __launch_bounds__(128) quotient_kernel(const QuotArgs a) {
-    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128, 3) quotient_kernel(const QuotArgs a) {
+    const size_t r_raw = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t size = (size_t)1 << (a.log_n + a.qdb);
-    if (r >= size) return;
+    const bool live = r_raw < size;
+    const size_t r = live ? r_raw : size - 1;  // surplus threads shadow the last point: every thread reaches every barrier
     const uint32_t nmask = (1u << a.log_n) - 1;
     const uint32_t coset = (uint32_t)(r >> a.log_n), pos = (uint32_t)r & nmask;
     const uint32_t j = gl::bitrev32(pos, a.log_n);
@@ -239,38 +251,76 @@ __global__ void __launch_bounds__(128) quotient_kernel(const QuotArgs a) {
             yc.constraint(zn * rhs - zl * lhs);
         }
     }
-    // eval_cross_table_lookup_checks (cross_table_lookup.rs:380-419)
-    for (int i = 0; i < d.nctl; ++i) {
-        const DevCtl c = d.ctls[i];
-        Fp local_z(a.zs_lde[(size_t)(a.num_perm_zs + i) * a.L + r]), next_z(a.zs_lde[(size_t)(a.num_perm_zs + i) * a.L + r_next]);
-        Fp lf = c.filter >= 0 ? eval_lc(d, c.filter, a.trace_lde, a.L, r) : air::one();
-        Fp nf = c.filter >= 0 ? eval_lc(d, c.filter, a.trace_lde, a.L, r_next) : air::one();
-        Fp lc = ctl_combine(d, c, a.trace_lde, a.L, r), nc = ctl_combine(d, c, a.trace_lde, a.L, r_next);
-        // select(filter, x) = filter * x + 1 - filter
-        yc.constraint_first_row(local_z - (lf * lc + air::one() - lf));
-        yc.constraint_transition(next_z - local_z * (nf * nc + air::one() - nf));
+    // eval_cross_table_lookup_checks (cross_table_lookup.rs:380-419).  The consumer is Horner in alpha, so constraint
+    // k of this section (2i: first-row check of instance i, 2i+1: its transition check) carries weight
+    // alpha^(2 nctl - 1 - k); accumulating with explicit weights makes the order free, which lets the two instances
+    // of one lookup side (same columns and filter, the two challenge pairs) share every column evaluation.
+    if (d.nctl > 0) {
+        const int K = 2 * d.nctl;
+        const uint64_t* __restrict__ ap0 = a.apow;
+        const uint64_t* __restrict__ ap1 = a.apow + (K + 1);
+        Fp s0 = yc.acc0 * Fp(ap0[K]), s1 = yc.acc1 * Fp(ap1[K]);
+        for (int i = 0; i < d.nctl; ++i) {
+            const DevCtl c = d.ctls[i];
+            if (c.is_twin) continue;
+            const int j = c.twin;
+            const Fp lf = c.filter >= 0 ? eval_lc(d, c.filter, a.trace_lde, a.L, r) : air::one();
+            const Fp nf = c.filter >= 0 ? eval_lc(d, c.filter, a.trace_lde, a.L, r_next) : air::one();
+            const Fp b0(c.beta), b1(j >= 0 ? d.ctls[j].beta : 0);
+            Fp l0(0), n0(0), l1(0), n1(0);
+            for (int q = c.col_cnt - 1; q >= 0; --q) {  // GrandProductChallenge::combine, Horner from the last column
+                const Fp v = eval_lc(d, c.col_off + q, a.trace_lde, a.L, r), w = eval_lc(d, c.col_off + q, a.trace_lde, a.L, r_next);
+                l0 = l0 * b0 + v;
+                n0 = n0 * b0 + w;
+                if (j >= 0) {
+                    l1 = l1 * b1 + v;
+                    n1 = n1 * b1 + w;
+                }
+            }
+            const Fp one_lf = air::one() - lf, one_nf = air::one() - nf;
+            for (int h = 0; h < 2; ++h) {
+                const int inst = h == 0 ? i : j;
+                if (inst < 0) break;
+                const Fp lc = (h == 0 ? l0 : l1) + Fp(h == 0 ? c.gamma : d.ctls[j].gamma);
+                const Fp nc = (h == 0 ? n0 : n1) + Fp(h == 0 ? c.gamma : d.ctls[j].gamma);
+                const Fp local_z(a.zs_lde[(size_t)(a.num_perm_zs + inst) * a.L + r]), next_z(a.zs_lde[(size_t)(a.num_perm_zs + inst) * a.L + r_next]);
+                // select(filter, x) = filter * x + 1 - filter
+                const Fp c_first = (local_z - (lf * lc + one_lf)) * yc.lagrange_first;
+                const Fp c_trans = (next_z - local_z * (nf * nc + one_nf)) * yc.z_last;
+                const int w = K - 1 - 2 * inst;
+                s0 = s0 + c_first * Fp(ap0[w]) + c_trans * Fp(ap0[w - 1]);
+                s1 = s1 + c_first * Fp(ap1[w]) + c_trans * Fp(ap1[w - 1]);
+            }
+        }
+        yc.acc0 = s0;
+        yc.acc1 = s1;
     }
-    a.out[r] = gl::mul(yc.acc0.v, a.zh_inv[zi]);
-    a.out[size + r] = gl::mul(yc.acc1.v, a.zh_inv[zi]);
+    if (live) {
+        a.out[r] = gl::mul(yc.acc0.v, a.zh_inv[zi]);
+        a.out[size + r] = gl::mul(yc.acc1.v, a.zh_inv[zi]);
+    }
 }
 
-static void launch_quotient(ola_ctx* ctx, int table_id, const QuotArgs& a) {
+static void launch_quotient(ola_ctx* ctx, int table_id, QuotArgs a) {
     const size_t size = (size_t)1 << (a.log_n + a.qdb);
-    const unsigned blocks = (unsigned)((size + 127) / 128);
+    // 128 threads x 3 CTAs/SM: the CPU table's body needs ~168 registers; larger blocks and block-wide barriers pacing the
+    // instruction stream both measured slower (profiles/quotient_r01h_summary.md)
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((size + threads - 1) / threads);
     Launch lz(ctx, "quotient");
     switch (table_id) {
-        case T_CPU: quotient_kernel<air::Cpu><<<blocks, 128, 0, ctx->stream>>>(a); break;
-        case T_MEMORY: quotient_kernel<air::Memory><<<blocks, 128, 0, ctx->stream>>>(a); break;
-        case T_CMP: quotient_kernel<air::Cmp><<<blocks, 128, 0, ctx->stream>>>(a); break;
-        case T_RANGECHECK: quotient_kernel<air::RangeCheck><<<blocks, 128, 0, ctx->stream>>>(a); break;
-        case T_BITWISE: quotient_kernel<air::Bitwise><<<blocks, 128, 0, ctx->stream>>>(a); break;
-        case T_POSEIDON: quotient_kernel<air::Poseidon><<<blocks, 128, 0, ctx->stream>>>(a); break;
-        case T_POSEIDON_CHUNK: quotient_kernel<air::PoseidonChunk><<<blocks, 128, 0, ctx->stream>>>(a); break;
-        case T_STORAGE: quotient_kernel<air::StorageAccess><<<blocks, 128, 0, ctx->stream>>>(a); break;
-        case T_TAPE: quotient_kernel<air::Tape><<<blocks, 128, 0, ctx->stream>>>(a); break;
-        case T_SCCALL: quotient_kernel<air::SCCall><<<blocks, 128, 0, ctx->stream>>>(a); break;
-        case T_PROGRAM: quotient_kernel<air::Program><<<blocks, 128, 0, ctx->stream>>>(a); break;
-        case T_PROG_CHUNK: quotient_kernel<air::ProgChunk><<<blocks, 128, 0, ctx->stream>>>(a); break;
+        case T_CPU: quotient_kernel<air::Cpu><<<blocks, threads, 0, ctx->stream>>>(a); break;
+        case T_MEMORY: quotient_kernel<air::Memory><<<blocks, threads, 0, ctx->stream>>>(a); break;
+        case T_CMP: quotient_kernel<air::Cmp><<<blocks, threads, 0, ctx->stream>>>(a); break;
+        case T_RANGECHECK: quotient_kernel<air::RangeCheck><<<blocks, threads, 0, ctx->stream>>>(a); break;
+        case T_BITWISE: quotient_kernel<air::Bitwise><<<blocks, threads, 0, ctx->stream>>>(a); break;
+        case T_POSEIDON: quotient_kernel<air::Poseidon><<<blocks, threads, 0, ctx->stream>>>(a); break;
+        case T_POSEIDON_CHUNK: quotient_kernel<air::PoseidonChunk><<<blocks, threads, 0, ctx->stream>>>(a); break;
+        case T_STORAGE: quotient_kernel<air::StorageAccess><<<blocks, threads, 0, ctx->stream>>>(a); break;
+        case T_TAPE: quotient_kernel<air::Tape><<<blocks, threads, 0, ctx->stream>>>(a); break;
+        case T_SCCALL: quotient_kernel<air::SCCall><<<blocks, threads, 0, ctx->stream>>>(a); break;
+        case T_PROGRAM: quotient_kernel<air::Program><<<blocks, threads, 0, ctx->stream>>>(a); break;
+        case T_PROG_CHUNK: quotient_kernel<air::ProgChunk><<<blocks, threads, 0, ctx->stream>>>(a); break;
         default: throw Error(OLA_ERR_INVALID_ARG, "no constraint kernel for table " + std::to_string(table_id));
     }
 }
@@ -360,11 +410,14 @@ struct DescBuilder {
     std::vector<DevPermInst> insts;
     std::vector<DevPermBatch> batches;
     std::vector<int> pairs;
+    std::vector<const TableWithColumns*> ctl_sides;
     int add_lc(const Column& c) {
         DevLc l;
         l.off = (int)lc_col.size();
         l.cnt = (int)c.lc.size();
         l.constant = gl::canon(c.constant);
+        l.pad_ = 0;
+        l.single = (c.lc.size() == 1 && gl::canon(c.lc[0].second) == 1 && l.constant == 0) ? c.lc[0].first : -1;
         for (auto& t : c.lc) {
             lc_col.push_back(t.first);
             lc_coef.push_back(gl::canon(t.second));
@@ -380,6 +433,16 @@ struct DescBuilder {
         c.filter = ci.twc->has_filter ? add_lc(ci.twc->filter) : -1;
         c.beta = ci.ch.beta;
         c.gamma = ci.ch.gamma;
+        c.twin = -1;
+        c.is_twin = 0;
+        c.pad_ = 0;
+        for (size_t k = 0; k < ctls.size(); ++k)
+            if (ctl_sides[k] == ci.twc && ctls[k].twin < 0 && !ctls[k].is_twin) {
+                ctls[k].twin = (int)ctls.size();
+                c.is_twin = 1;
+                break;
+            }
+        ctl_sides.push_back(ci.twc);
         ctls.push_back(c);
     }
 };
@@ -585,8 +648,23 @@ static StarkProof prove_single_table(ola_ctx* ctx, const TableInfo& t, const Con
         a.d = desc.t;
         a.num_perm_zs = (int)num_perm_zs;
         a.compress_challenge = t.compress_challenge;
+        // alpha_j^k, k = 0 .. 2*nctl: weights of the cross-table-lookup section (see quotient_kernel)
+        const size_t K1 = 2 * (size_t)desc.t.nctl + 1;
+        std::vector<uint64_t> h_apow(2 * K1);
+        for (int j = 0; j < 2; ++j) {
+            const F al = j == 0 ? alpha0 : alpha1;
+            F pw = 1;
+            for (size_t k = 0; k < K1; ++k) {
+                h_apow[j * K1 + k] = pw;
+                pw = gl::mul(pw, al);
+            }
+        }
+        DevBuf d_apow(2 * K1);
+        OLA_CUDA(cudaMemcpyAsync(d_apow.p, h_apow.data(), h_apow.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        a.apow = d_apow.p;
         launch_quotient(ctx, t.id, a);
         check_launch("quotient_kernel");
+        OLA_CUDA(cudaStreamSynchronize(ctx->stream));  // h_apow / d_apow go out of scope
     }
     // values at bit-reversed positions on 7*H_{n 2^qdb} -> natural coefficients (coset_ifft, prover.rs:700-704)
     ntt::inverse_from_leaf_order(ctx, d_q.p, qsize, 2, (int)degree_bits + qdb, gl::GEN);

@@ -53,3 +53,23 @@ def max_over_ranks(value, device=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def commit_sharded(ctx, values, rate_bits, cap_height, is_coeffs=False, device=None, **kw):
+    """PolynomialBatch::from_values across the ranks of the default process group (coset shard, SURVEY.md 8e): every
+    rank passes the SAME trace columns, evaluates / hashes / reduces only its cosets, and one all-gather of
+    2^cap_height / world digests per rank assembles the cap.  Returns the local shard with the full `merkle_cap`."""
+    from .pcs import MerkleCap, PolynomialBatch
+
+    world, rank = dist.get_world_size(), dist.get_rank()
+    lo, hi = coset_range(rate_bits, rank, world)
+    b = PolynomialBatch._commit(ctx, values, is_coeffs, rate_bits, cap_height, coset_first=lo, coset_count=hi - lo, **kw)
+    full = allgather_cap(b.merkle_cap.hashes.view("int64"), rate_bits, cap_height, device=device)
+    b.merkle_cap = MerkleCap(full.cpu().numpy().view("uint64"))
+    return b
+
+
+def leaf_owner(leaf_index, degree_log, rate_bits, world):
+    """(rank, local leaf index) of a global leaf under the coset shard."""
+    per = (1 << (degree_log + rate_bits)) // world
+    return leaf_index // per, leaf_index % per

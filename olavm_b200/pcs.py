@@ -30,7 +30,10 @@ def _reverse_bits(x, bits):
 class PolynomialBatch:
     """A batch of polynomials committed with a Poseidon Merkle tree over their coset LDE."""
 
-    def __init__(self, ctx, handle, cap, ncols, degree_log, rate_bits, cap_height):
+    def __init__(self, ctx, handle, cap, ncols, degree_log, rate_bits, cap_height, coset_first=0, coset_count=None):
+        # a coset shard (one rank of a multi-GPU commit) holds leaves [coset_first*n, (coset_first+coset_count)*n)
+        self.coset_first = coset_first
+        self.coset_count = (1 << rate_bits) if coset_count is None else coset_count
         self.ctx = ctx
         self.handle = handle
         self.merkle_cap = MerkleCap(cap)
@@ -42,7 +45,8 @@ class PolynomialBatch:
 
     # ---- constructors (oracle.rs:45-99)
     @classmethod
-    def _commit(cls, ctx, cols, is_coeffs, rate_bits, cap_height, on_device=False, ncols=None, degree_log=None):
+    def _commit(cls, ctx, cols, is_coeffs, rate_bits, cap_height, on_device=False, ncols=None, degree_log=None, coset_first=0,
+                coset_count=None):
         if on_device:
             ptr = cols
         else:
@@ -55,10 +59,16 @@ class PolynomialBatch:
             degree_log = n.bit_length() - 1
             ptr = _lib.hptr(cols)
         h = ctypes.c_void_p()
-        cap = np.empty((1 << cap_height, 4), dtype=np.uint64)
-        ctx.check(ctx._lib.ola_commit(ctx.handle, ptr, 1 if on_device else 0, ncols, degree_log, 1 if is_coeffs else 0,
-                                      rate_bits, cap_height, ctypes.byref(h), _lib.hptr(cap)))
-        return cls(ctx, h, cap, ncols, degree_log, rate_bits, cap_height)
+        if coset_count is None:
+            cap = np.empty((1 << cap_height, 4), dtype=np.uint64)
+            ctx.check(ctx._lib.ola_commit(ctx.handle, ptr, 1 if on_device else 0, ncols, degree_log, 1 if is_coeffs else 0,
+                                          rate_bits, cap_height, ctypes.byref(h), _lib.hptr(cap)))
+            return cls(ctx, h, cap, ncols, degree_log, rate_bits, cap_height)
+        # this rank's cap entries only; `merkle_cap` becomes the full cap after dist.allgather_cap
+        cap = np.empty(((coset_count << cap_height) >> rate_bits, 4), dtype=np.uint64)
+        ctx.check(ctx._lib.ola_commit_shard(ctx.handle, ptr, 1 if on_device else 0, ncols, degree_log, 1 if is_coeffs else 0,
+                                            rate_bits, cap_height, coset_first, coset_count, ctypes.byref(h), _lib.hptr(cap)))
+        return cls(ctx, h, cap, ncols, degree_log, rate_bits, cap_height, coset_first, coset_count)
 
     @classmethod
     def from_values(cls, ctx, values, rate_bits, blinding, cap_height, **kw):
@@ -84,7 +94,7 @@ class PolynomialBatch:
 
     def leaves(self, first=0, count=None):
         """merkle_tree.leaves[first:first+count] as row-major [count, ncols]."""
-        L = 1 << (self.degree_log + self.rate_bits)
+        L = self.coset_count << self.degree_log  # leaves held by this batch (all of them unless it is a coset shard)
         if count is None:
             count = L - first
         out = np.empty((count, self.ncols), dtype=np.uint64)
@@ -98,7 +108,7 @@ class PolynomialBatch:
 
     def prove(self, leaf_index):
         """MerkleTree::prove(leaf_index) (merkle_tree/mod.rs:273): sibling digests, bottom-up."""
-        nsib = self.degree_log + self.rate_bits - self.cap_height
+        nsib = self.degree_log + self.rate_bits - self.cap_height  # paths stop at the cap: identical for a shard
         out = np.empty((max(nsib, 1), 4), dtype=np.uint64)
         k = self.ctx.check(self.ctx._lib.ola_batch_prove_leaf(self.ctx.handle, self.handle, leaf_index, _lib.hptr(out)))
         return out[:k]

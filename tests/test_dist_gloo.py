@@ -65,3 +65,7 @@ def test_partitions():
             assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
     assert odist.coset_range(3, 3, 4) == (6, 8)
     assert odist.cap_slots(3, 4, 1, 8) == [2, 3]  # one coset = 2 of the 16 cap subtrees
+    # leaf ownership under the coset shard: contiguous leaf ranges
+    assert odist.leaf_owner(0, 10, 3, 4) == (0, 0)
+    assert odist.leaf_owner((1 << 13) - 1, 10, 3, 4) == (3, (1 << 11) - 1)
+    assert odist.leaf_owner(5000, 10, 3, 8) == (4, 5000 - 4096)

@@ -161,6 +161,44 @@ def test_commit_resident_input_matches_host_input(ctx, orc):
     ctx.free(d)
 
 
+# ------------------------------------------------------------------ coset shard (multi-GPU commit)
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("lg,ncols", [(5, 3), (12, 20)])
+def test_coset_shards_reassemble_the_commitment(ctx, orc, world, lg, ncols):
+    """Every rank's shard, computed here one after the other on one GPU: the concatenated cap entries are the full
+    cap, each shard's leaves are its slice of the full leaf matrix, and Merkle paths are the global ones."""
+    from olavm_b200 import dist as odist
+
+    vals = orc.rand_elems(900 + lg + world, (ncols, 1 << lg))
+    ref = orc.commit(vals, is_coeffs=False, rate_bits=3, cap_height=4)
+    L = 1 << (lg + 3)
+    caps = []
+    for rank in range(world):
+        lo, hi = odist.coset_range(3, rank, world)
+        b = PolynomialBatch._commit(ctx, vals, False, 3, 4, coset_first=lo, coset_count=hi - lo)
+        caps.append(b.merkle_cap.hashes)
+        assert (b.polynomials == ref["coeffs"]).all()
+        per = L // world
+        assert (b.leaves() == ref["leaves"][rank * per : (rank + 1) * per]).all()
+        for g in {rank * per, rank * per + per // 3, (rank + 1) * per - 1}:
+            owner, local = odist.leaf_owner(g, lg, 3, world)
+            assert owner == rank
+            sib = b.prove(local)
+            assert (sib == orc.merkle_prove(ref["digests"], L, 4, g)).all()
+            assert orc.merkle_verify(b.leaves(local, 1)[0], g, ref["cap"], sib)
+        b.free()
+    assert (np.concatenate(caps) == ref["cap"]).all()
+
+
+def test_coset_shard_argument_errors(ctx, orc):
+    vals = orc.rand_elems(5, (2, 16))
+    for first, count in ((1, 2), (0, 3), (8, 1), (6, 4)):
+        with pytest.raises(olavm_b200.OlaError):
+            PolynomialBatch._commit(ctx, vals, False, 3, 4, coset_first=first, coset_count=count)
+    with pytest.raises(olavm_b200.OlaError):  # cap coarser than the partition: 1 coset of 8 needs cap_height >= 3
+        PolynomialBatch._commit(ctx, vals, False, 3, 2, coset_first=0, coset_count=1)
+
+
 # ------------------------------------------------------------------ full-size properties (BASELINE configs)
 def test_config2_shape_spot_and_linearity(ctx, orc):
     """200 columns x 2^20 rows, blowup 8 (BASELINE config #2 shape, reduced to 40 columns to bound test time):

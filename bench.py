@@ -12,6 +12,9 @@ uniform Goldilocks columns.  A "step" is one pass of that path over the whole 20
                against the measured HBM copy bandwidth in MEASURED_PEAKS.json
   cpu_baseline / --impl reference : the oracle port of the reference's cfft path (OpenMP over columns,
                all host cores) on a bounded column sample of the same workload
+  coset_shard_commit (every N) : one 94-column 2^20-row commitment strong-scaled over the ranks by LDE cosets, cap
+               assembled by one NCCL all-gather
+  prove_all_tables (N = 1)     : wall time of one 12-table proof with a 2^22-row CPU table from pinned host traces
 
 Multi-GPU (torchrun, one rank per GPU): columns are independent, so ranks shard by column with no data-path
 collective (weak scaling: 200 columns per GPU); time = max over ranks.
@@ -98,28 +101,97 @@ def cpu_lde(oracle, ncols, log_n, reps=1):
     return 80.0 * n * ncols / best / 1e9, best, os.cpu_count()
 
 
-def prove_cpu_table(ctx, log_n):
-    """Second half of BASELINE.json's metric: wall time of one proof whose CPU table has 2^log_n rows
-    (94 trace + 78 CTL-Z + 12 quotient columns) through the C ABI from a HOST trace.  Synthetic random trace with
-    binary filters, quotient-degree check off ("pipeline parity": no executor exists here to make a satisfying trace);
-    only the CPU table is in the proof (9 of the 12 AIR kernels are not built yet), so every CTL is partial."""
+def table_log_sizes(k):
+    """Row counts (log2) of the 12 tables for a proof whose CPU table has 2^k rows: the other tables at plausible natural
+    sizes (Table enum order, ola_stark.rs:104-119); RangeCheck is at least 2^16 (its fixed u16 column)."""
+    return [k, k - 1, max(k - 4, 8), max(k - 4, 4), max(16, k - 3), max(k - 6, 3), max(k - 6, 3), max(k - 5, 8), max(k - 8, 3),
+            max(k - 10, 2), max(k - 2, 4), max(k - 5, 3)]
+
+
+def prove_all_tables(ctx, log_n):
+    """Second half of BASELINE.json's metric (configs[2]): wall time of one 12-table proof whose CPU table has 2^log_n rows
+    (94 trace + 78 CTL-Z + 12 quotient columns), through the C ABI from PINNED HOST traces to proof bytes on the host.
+    Synthetic random traces with binary filters, quotient-degree check off ("pipeline parity": no executor exists here
+    to make a satisfying trace -- every kernel of the proof runs on the same shapes); all 19 cross-table lookups."""
+    import torch
+
     import olavm_b200
 
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import tracegen
+    import tracegen as tg
 
     rng = np.random.default_rng(22)
-    t = tracegen.cpu_random_trace(rng, log_n)
-    olavm_b200.prove_with_traces(ctx, [0], [np.ascontiguousarray(t[:, :4096])], check_quotient_degree=False)  # warm-up
+    gens = [tg.cpu_random_trace, tg.memory_random_trace, tg.bitwise_random_trace, tg.cmp_random_trace, None, tg.poseidon_random_trace,
+            tg.poseidon_chunk_random_trace, tg.storage_random_trace, tg.tape_random_trace, tg.sccall_random_trace, tg.program_random_trace,
+            tg.prog_chunk_random_trace]
+    logs = table_log_sizes(log_n)
+    traces, keep = [], []
+    for tid, (g, lg) in enumerate(zip(gens, logs)):
+        t = tg.rangecheck_random_trace(rng, lg) if tid == 4 else g(rng, lg)
+        pinned = torch.empty(t.shape, dtype=torch.int64).pin_memory()
+        v = pinned.numpy().view(np.uint64)
+        v[:] = t
+        keep.append(pinned)
+        traces.append(v)
+    ids = list(range(12))
+    cc = [int(x) for x in rng.integers(0, 0xFFFFFFFF00000001, size=12, dtype=np.uint64)]
+    small = [np.ascontiguousarray(t[:, : min(t.shape[1], 1 << 16 if i == 4 else 1 << 10)]) for i, t in enumerate(traces)]
+    olavm_b200.prove_with_traces(ctx, ids, small, check_quotient_degree=False, compress_challenges=cc)  # warm-up (module load, pool)
+    t0 = time.perf_counter()
+    olavm_b200.prove_with_traces(ctx, ids, traces, check_quotient_degree=False, compress_challenges=cc)  # grows the memory pool
+    first = time.perf_counter() - t0
     ctx.profile_begin()
     t0 = time.perf_counter()
-    proof = olavm_b200.prove_with_traces(ctx, [0], [t], check_quotient_degree=False)
+    proof = olavm_b200.prove_with_traces(ctx, ids, traces, check_quotient_degree=False, compress_challenges=cc)
     dt = time.perf_counter() - t0
     prof = ctx.profile_end()
     top = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:8]
-    return {"log_n": log_n, "seconds": dt, "proof_bytes": len(proof), "tables": ["cpu"], "columns": {"trace": 94, "ctl_z": 78, "quotient": 12},
-            "mode": "synthetic random trace, binary filters, quotient-degree check off; host trace in, proof bytes out",
-            "kernel_ms": {k: round(v["ms"], 1) for k, v in top}, "h2d_bytes": int(t.nbytes)}
+    rows = sum(1 << lg for lg in logs)
+    return {"log_n_cpu": log_n, "table_log_n": logs, "seconds": dt, "first_call_seconds": first, "proof_bytes": len(proof), "tables": 12, "ctls": 19,
+            "cpu_table_columns": {"trace": 94, "ctl_z": 78, "quotient": 12}, "trace_rows_total": rows,
+            "constraint_rows_per_s": rows / dt,
+            "mode": "synthetic random traces, binary filters, quotient-degree check off; pinned host traces in, proof bytes out",
+            "kernel_ms": {k: round(v["ms"], 1) for k, v in top}, "kernel_ms_total": round(sum(v["ms"] for v in prof.values()), 1),
+            "h2d_bytes": int(sum(t.nbytes for t in traces))}
+
+
+def coset_shard_commit(ctx, torch, dist, odist, world, rank, device, stream, log_n=20, ncols=94, reps=3):
+    """PolynomialBatch::from_values of one 94-column 2^20-row trace (the CPU table's shape) STRONG-scaled over the ranks
+    by cosets: every rank holds the trace, evaluates + hashes + reduces 8/world cosets, one all-gather of
+    16/world digests assembles the cap.  Device time, max over ranks, all-gather included."""
+    from olavm_b200.pcs import PolynomialBatch
+
+    rng = np.random.Generator(np.random.PCG64(94))
+    vals = rng.integers(0, 0xFFFFFFFF00000001, size=(ncols, 1 << log_n), dtype=np.uint64)
+    d_vals = ctx.upload(vals)
+    lo, hi = odist.coset_range(RATE_BITS, rank, world)
+    best = None
+    cap0 = None
+    for it in range(reps + 1):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0.record(stream)
+        b = PolynomialBatch._commit(ctx, d_vals, False, RATE_BITS, 4, on_device=True, ncols=ncols, degree_log=log_n, coset_first=lo, coset_count=hi - lo)
+        if world > 1:
+            with torch.cuda.stream(stream):
+                full = odist.allgather_cap(b.merkle_cap.hashes.view(np.int64), RATE_BITS, 4, device=device)
+        else:
+            full = torch.as_tensor(b.merkle_cap.hashes.view(np.int64))
+        ev1.record(stream)
+        ctx.sync()
+        torch.cuda.synchronize()
+        ms = odist.max_over_ranks(ev0.elapsed_time(ev1), device=device)
+        cap0 = full.cpu().numpy().view(np.uint64)
+        b.free()
+        if it > 0:
+            best = ms if best is None else min(best, ms)
+    ctx.free(d_vals)
+    perms = (1 << (log_n + RATE_BITS)) * ((ncols + 7) // 8) + (1 << (log_n + RATE_BITS)) - 16
+    return {"log_n": log_n, "ncols": ncols, "ms": best, "scaling": "strong", "cosets_per_rank": hi - lo, "poseidon_perms_per_s": perms / (best * 1e-3),
+            "cap_word0": int(cap0[0, 0])}
 
 
 def run_reference(args):
@@ -160,7 +232,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--prove-log-n", type=int, default=22, help="also time one CPU-table proof of 2^k rows (0 = skip)")
+    ap.add_argument("--prove-log-n", type=int, default=22, help="N=1: also time one 12-table proof whose CPU table has 2^k rows (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -273,8 +345,6 @@ def main():
                          "note": "64-bit modular butterflies are INT-pipe bound on B200; see DESIGN.md section 5"},
             "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
         }
-        if args.prove_log_n:
-            line["prove_cpu_table"] = prove_cpu_table(ctx, args.prove_log_n)
         if not args.no_cpu_baseline:
             import oracle
 
@@ -283,9 +353,15 @@ def main():
             gbs, dt, _ = cpu_lde(oracle, sample_cols, LOG_N)
             line["cpu_baseline"] = {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port", "seconds": dt,
                                     "sample": f"{sample_cols} of {NCOLS} columns x 2^{LOG_N} rows (iNTT + coset-LDE x8), OpenMP over columns"}
-        print(json.dumps(line))
     for p in (d_coeffs, d_lde):
         ctx.free(p)
+    # extra legs (not the headline): strong-scaled coset-shard commit at every N, the full 12-table proof at N = 1
+    extra = {"coset_shard_commit": coset_shard_commit(ctx, torch, dist, odist, world, rank, torch.device("cuda", local_rank), stream)}
+    if rank == 0 and world == 1 and args.prove_log_n:
+        extra["prove_all_tables"] = prove_all_tables(ctx, args.prove_log_n)
+    if rank == 0:
+        line.update(extra)
+        print(json.dumps(line))
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

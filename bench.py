@@ -147,7 +147,17 @@ def prove_all_tables(ctx, log_n):
     prof = ctx.profile_end()
     top = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:8]
     rows = sum(1 << lg for lg in logs)
-    return {"log_n_cpu": log_n, "table_log_n": logs, "seconds": dt, "first_call_seconds": first, "proof_bytes": len(proof), "tables": 12, "ctls": 19,
+    # bounded CPU sample of the same path: the oracle port proving a 2^14-row CPU table alone, all host threads
+    import oracle
+
+    sample = tg.cpu_random_trace(np.random.default_rng(14), 14)
+    t0 = time.perf_counter()
+    oracle.stark_prove([0], [sample], check_degree=False)
+    cpu_dt = time.perf_counter() - t0
+    cpu_port = {"kind": "port", "cores": os.cpu_count(), "sample": "oracle port, CPU table alone, 2^14 rows (94 trace + 78 Z + 12 quotient columns)",
+                "seconds": cpu_dt, "constraint_rows_per_s": (1 << 14) / cpu_dt,
+                "context": "reference README.md:69 quotes 39.767 s for a 2^20-row proof on 64 cores (other hardware)"}
+    return {"log_n_cpu": log_n, "cpu_baseline": cpu_port, "table_log_n": logs, "seconds": dt, "first_call_seconds": first, "proof_bytes": len(proof), "tables": 12, "ctls": 19,
             "cpu_table_columns": {"trace": 94, "ctl_z": 78, "quotient": 12}, "trace_rows_total": rows,
             "constraint_rows_per_s": rows / dt,
             "mode": "synthetic random traces, binary filters, quotient-degree check off; pinned host traces in, proof bytes out",

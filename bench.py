@@ -148,6 +148,7 @@ def prove_all_tables(ctx, log_n):
     top = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:8]
     rows = sum(1 << lg for lg in logs)
     # bounded CPU sample of the same path: the oracle port proving a 2^14-row CPU table alone, all host threads
+    host_threads()
     import oracle
 
     sample = tg.cpu_random_trace(np.random.default_rng(14), 14)
@@ -204,11 +205,19 @@ def coset_shard_commit(ctx, torch, dist, odist, world, rank, device, stream, log
             "cap_word0": int(cap0[0, 0])}
 
 
+def host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm uses all host cores (set before libgomp loads)."""
+    if "TORCHELASTIC_RUN_ID" in os.environ or os.environ.get("OMP_NUM_THREADS") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
+    return os.cpu_count()
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path (oracle port; the Rust prover cannot be built here: no cargo)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    host_threads()
     import oracle
 
     cores = os.cpu_count()
@@ -355,7 +364,8 @@ def main():
                          "note": "64-bit modular butterflies are INT-pipe bound on B200; see DESIGN.md section 5"},
             "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N = 1 only
+            host_threads()
             import oracle
 
             cores = os.cpu_count()

@@ -164,6 +164,21 @@ int ola_batch_prove_leaf(ola_ctx* ctx, const ola_batch* b, size_t leaf_index, ui
 int ola_prove(ola_ctx* ctx, const int* table_ids, uint32_t ntables, const uint64_t* const* traces, int on_device,
               const uint32_t* log_ns, const uint64_t* compress_challenges, int check_quotient_degree, uint8_t* proof_out,
               size_t proof_cap, size_t* proof_len);
+/* ---- multi-GPU: one process (or thread) per GPU, the proof coset-sharded across the ranks ----
+ * After ola_set_comm, ola_prove called COLLECTIVELY by every rank with the SAME arguments shards the three dominant
+ * costs by LDE cosets -- commitments (coset LDE + leaf hashing + subtree reduction), constraint-quotient evaluation
+ * ("next row" stays inside a coset: no communication) -- and replicates the rest (Z columns, openings, FRI layers of
+ * the 2-column composition polynomial, transcript).  Exchanges per table: cap entries (all-gather of 16 digests),
+ * quotient values (all-gather of 2 x 8n u64) and the opened query rows / Merkle paths, answered by the owner of each
+ * leaf (all-reduce over zero-filled buffers).  Every rank returns the same, single-GPU-identical proof bytes.
+ * world must divide 8 (the blowup).  The library does not link a communication library: the host supplies the two
+ * collectives (NCCL in production -- see olavm_b200/dist.py for the torch.distributed binding).  Contract of both
+ * callbacks: operate on DEVICE pointers of this rank's GPU, ordered after the work already enqueued on `stream`, and
+ * make the result visible to work enqueued on `stream` after they return; return 0 on success. */
+typedef int (*ola_allgather_fn)(void* user, const void* send_dev, void* recv_dev, size_t bytes_per_rank, void* stream);
+typedef int (*ola_allreduce_u64_fn)(void* user, void* buf_dev, size_t count_u64, void* stream); /* in place, wrapping sum */
+int ola_set_comm(ola_ctx* ctx, int rank, int world, ola_allgather_fn allgather, ola_allreduce_u64_fn allreduce_sum, void* user);
+
 /* number of trace columns of a table (S::COLUMNS), or -1 if its constraint kernel is not compiled in */
 int ola_table_columns(int table_id);
 

@@ -404,6 +404,19 @@ int ola_prove(ola_ctx* ctx, const int* table_ids, uint32_t ntables, const uint64
         memcpy(proof_out, bytes.data(), bytes.size());
     });
 }
+int ola_set_comm(ola_ctx* ctx, int rank, int world, ola_allgather_fn allgather, ola_allreduce_u64_fn allreduce_sum, void* user) {
+    if (!ctx) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        OLA_CHECK(world >= 1 && world <= 8 && (8 % world) == 0 && rank >= 0 && rank < world, OLA_ERR_INVALID_ARG,
+                  "set_comm: world must divide the blowup (8) and 0 <= rank < world");
+        OLA_CHECK(world == 1 || (allgather && allreduce_sum), OLA_ERR_INVALID_ARG, "set_comm: both collectives are required");
+        ctx->rank = rank;
+        ctx->world = world;
+        ctx->comm_allgather = allgather;
+        ctx->comm_allreduce = allreduce_sum;
+        ctx->comm_user = user;
+    });
+}
 int ola_table_columns(int table_id) {
     try {
         return ola::stark::table_available(table_id) ? ola::stark::table_info(table_id).columns : -1;

@@ -65,6 +65,11 @@ struct ola_ctx {
     uint64_t kernel_launches = 0;  // counted by every launcher (bench.py "gpu_launches")
     uint64_t* scratch = nullptr;   // grow-only device workspace (multi-pass transform intermediates)
     size_t scratch_elems = 0;
+    // coset-shard communicator (ola_set_comm); world == 1: single GPU
+    int rank = 0, world = 1;
+    ola_allgather_fn comm_allgather = nullptr;
+    ola_allreduce_u64_fn comm_allreduce = nullptr;
+    void* comm_user = nullptr;
 };
 
 namespace ola {
@@ -89,6 +94,14 @@ struct Launch {
     }
 };
 inline void count_launch(ola_ctx* ctx, uint64_t n = 1) { ctx->kernel_launches += n; }
+inline void comm_allgather(ola_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank) {
+    OLA_CHECK(ctx->comm_allgather != nullptr, OLA_ERR_INTERNAL, "no communicator");
+    OLA_CHECK(ctx->comm_allgather(ctx->comm_user, send, recv, bytes_per_rank, (void*)ctx->stream) == 0, OLA_ERR_INTERNAL, "all-gather callback failed");
+}
+inline void comm_allreduce(ola_ctx* ctx, void* buf, size_t count) {
+    OLA_CHECK(ctx->comm_allreduce != nullptr, OLA_ERR_INTERNAL, "no communicator");
+    OLA_CHECK(ctx->comm_allreduce(ctx->comm_user, buf, count, (void*)ctx->stream) == 0, OLA_ERR_INTERNAL, "all-reduce callback failed");
+}
 inline void check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw Error(OLA_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));

@@ -202,13 +202,16 @@ __global__ void __launch_bounds__(128) pow_kernel(uint64_t h0, uint64_t h1, uint
 }
 
 // ---- query gathers ----
-// rows of a column-major matrix at the query indices: out[q][c] = m[c*stride + idx[q]]
+// rows of a column-major matrix at the query indices: out[q][c] = m[c*stride + idx[q]].  The matrix holds leaves
+// [leaf_lo, leaf_lo + stride) of the tree (a coset shard; the whole tree when leaf_lo = 0 and stride = nleaves): queries
+// this rank does not own produce zeros, to be summed with the owner's answer.
 __global__ void gather_query_rows_kernel(const uint64_t* __restrict__ m, size_t stride, size_t ncols, const uint32_t* __restrict__ idx, int shift, int nq,
-                                         uint64_t* __restrict__ out) {
+                                         size_t leaf_lo, uint64_t* __restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)nq * ncols) return;
     size_t q = i / ncols, c = i % ncols;
-    out[i] = m[c * stride + (idx[q] >> shift)];
+    size_t leaf = idx[q] >> shift;
+    out[i] = (leaf >= leaf_lo && leaf - leaf_lo < stride) ? m[c * stride + (leaf - leaf_lo)] : 0;
 }
 // FRI layer leaf (arity ext values interleaved) at idx[q] >> shift: out[q][2*e + comp]
 __global__ void gather_query_ext_kernel(const uint64_t* __restrict__ vals, size_t len, int arity, const uint32_t* __restrict__ idx, int shift, int nq,
@@ -220,13 +223,19 @@ __global__ void gather_query_ext_kernel(const uint64_t* __restrict__ vals, size_
     out[i] = vals[comp * len + (size_t)(idx[q] >> shift) * arity + e];
 }
 // Merkle paths: out[q][j][w] = nodes[(((nleaves + leaf) >> j) ^ 1) * 4 + w], leaf = idx[q] >> shift
+// (nodes = the heap-ordered subtree over leaves [leaf_lo, leaf_lo + nleaves); paths stop at the cap, inside the subtree)
 __global__ void gather_query_paths_kernel(const uint64_t* __restrict__ nodes, size_t nleaves, const uint32_t* __restrict__ idx, int shift, int nq, int nsib,
-                                          uint64_t* __restrict__ out) {
+                                          size_t leaf_lo, uint64_t* __restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)nq * nsib * 4) return;
     size_t q = i / ((size_t)nsib * 4), r = i % ((size_t)nsib * 4);
     size_t j = r / 4, w = r % 4;
     size_t leaf = idx[q] >> shift;
+    if (leaf < leaf_lo || leaf - leaf_lo >= nleaves) {
+        out[i] = 0;
+        return;
+    }
+    leaf -= leaf_lo;
     out[i] = nodes[((((nleaves + leaf) >> j) ^ 1) << 2) + w];
 }
 
@@ -455,19 +464,28 @@ stark::FriProof prove_openings(ola_ctx* ctx, const Instance& inst, const std::ve
         }
     }
     DevMem d_out(total);
+    bool sharded = false;
     for (size_t o = 0; o < oracles.size(); ++o) {
         size_t cnt = (size_t)nq * oracles[o]->ncols;
+        // a coset shard answers the queries that fall into its leaf range; the others come from their owners below
+        const size_t Lo = (size_t)1 << oracles[o]->leaf_bits(), leaf_lo = (size_t)oracles[o]->coset_first * n;
+        sharded = sharded || Lo != L;
         {
             Launch lz(ctx, "fri_query_rows");
-            gather_query_rows_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(oracles[o]->d_lde, L, oracles[o]->ncols, (const uint32_t*)d_idx.p, 0, nq,
-                                                                                 d_out.p + off_rows[o]);
+            gather_query_rows_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(oracles[o]->d_lde, Lo, oracles[o]->ncols, (const uint32_t*)d_idx.p, 0, nq,
+                                                                                 leaf_lo, d_out.p + off_rows[o]);
         }
         if (nsib0 > 0) {
             Launch lz(ctx, "fri_query_paths");
             size_t pc = (size_t)nq * nsib0 * 4;
-            gather_query_paths_kernel<<<(unsigned)((pc + 127) / 128), 128, 0, st>>>(oracles[o]->d_nodes, L, (const uint32_t*)d_idx.p, 0, nq, nsib0,
-                                                                                  d_out.p + off_paths[o]);
+            gather_query_paths_kernel<<<(unsigned)((pc + 127) / 128), 128, 0, st>>>(oracles[o]->d_nodes, Lo, (const uint32_t*)d_idx.p, 0, nq, nsib0,
+                                                                                  leaf_lo, d_out.p + off_paths[o]);
         }
+    }
+    if (sharded) {
+        // owner-answered openings: every rank holds zeros for the leaves it does not own -> wrapping sum = the answer
+        const size_t oracle_words = layers.empty() ? total : off_lrows[0];
+        comm_allreduce(ctx, d_out.p, oracle_words);
     }
     for (size_t li = 0; li < layers.size(); ++li) {
         const int arity = 1 << arities[li];
@@ -481,7 +499,7 @@ stark::FriProof prove_openings(ola_ctx* ctx, const Instance& inst, const std::ve
             Launch lz(ctx, "fri_query_paths");
             size_t pc = (size_t)nq * lnsib[li] * 4;
             gather_query_paths_kernel<<<(unsigned)((pc + 127) / 128), 128, 0, st>>>(layers[li]->nodes.p, layers[li]->len / arity, (const uint32_t*)d_idx.p,
-                                                                                  lshift[li], nq, lnsib[li], d_out.p + off_lpaths[li]);
+                                                                                  lshift[li], nq, lnsib[li], 0, d_out.p + off_lpaths[li]);
         }
     }
     check_launch("fri query gathers");

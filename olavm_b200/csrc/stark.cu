@@ -190,6 +190,9 @@ struct QuotArgs {
     int num_perm_zs;
     uint64_t compress_challenge;  // Bitwise / Program only (canonical)
     const uint64_t* apow;         // [2][2*nctl + 1]: alpha_j^k, weights of the CTL section's constraints
+    // coset shard: this rank evaluates points [r_offset, r_offset + npoints) of the quotient domain; its LDE buffers
+    // start at leaf r_offset (row r of the domain is local row r - r_offset); out[j][r - r_offset], j-stride out_stride
+    size_t r_offset, npoints, out_stride;
 };
 
 __device__ __forceinline__ uint64_t pow_omega_fwd(const uint64_t* __restrict__ pw, uint32_t E) {
@@ -201,14 +204,14 @@ __device__ __forceinline__ uint64_t pow_omega_fwd(const uint64_t* __restrict__ p
 template <class Air>
 __global__ void __launch_bounds__(128, 3) quotient_kernel(const QuotArgs a) {
     const size_t r_raw = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t size = (size_t)1 << (a.log_n + a.qdb);
-    const bool live = r_raw < size;
-    const size_t r = live ? r_raw : size - 1;  // surplus threads shadow the last point: every thread reaches every barrier
+    if (r_raw >= a.npoints) return;
+    const size_t rg = r_raw + a.r_offset;  // index in the quotient domain (leaf order)
     const uint32_t nmask = (1u << a.log_n) - 1;
-    const uint32_t coset = (uint32_t)(r >> a.log_n), pos = (uint32_t)r & nmask;
+    const uint32_t coset = (uint32_t)(rg >> a.log_n), pos = (uint32_t)rg & nmask;
     const uint32_t j = gl::bitrev32(pos, a.log_n);
     const uint32_t pos_next = gl::bitrev32((j + 1) & nmask, a.log_n);
-    const size_t r_next = ((size_t)coset << a.log_n) | pos_next;
+    // local rows in this rank's LDE buffers (the next row stays inside the coset)
+    const size_t r = r_raw, r_next = (((size_t)coset << a.log_n) | pos_next) - a.r_offset;
     // natural LDE index k = bitrev_{log_n+3}(r) = j*8 + bitrev3(coset); x = 7 * omega_{8n}^k
     const uint32_t cb = gl::bitrev32(coset, 3);
     const uint32_t k = (j << 3) | cb;
@@ -295,14 +298,13 @@ __global__ void __launch_bounds__(128, 3) quotient_kernel(const QuotArgs a) {
         yc.acc0 = s0;
         yc.acc1 = s1;
     }
-    if (live) {
-        a.out[r] = gl::mul(yc.acc0.v, a.zh_inv[zi]);
-        a.out[size + r] = gl::mul(yc.acc1.v, a.zh_inv[zi]);
-    }
+    a.out[r] = gl::mul(yc.acc0.v, a.zh_inv[zi]);
+    a.out[a.out_stride + r] = gl::mul(yc.acc1.v, a.zh_inv[zi]);
 }
 
 static void launch_quotient(ola_ctx* ctx, int table_id, QuotArgs a) {
-    const size_t size = (size_t)1 << (a.log_n + a.qdb);
+    const size_t size = a.npoints;
+    if (size == 0) return;
     // 128 threads x 3 CTAs/SM: the CPU table's body needs ~168 registers; larger blocks and block-wide barriers pacing the
     // instruction stream both measured slower (profiles/quotient_r01h_summary.md)
     const int threads = 128;
@@ -525,10 +527,26 @@ struct DevBuf {
     DevBuf& operator=(const DevBuf&) = delete;
 };
 
+// the full Merkle cap of a commitment; for a coset shard: one all-gather of this rank's cap entries
 static Cap batch_cap(ola_ctx* ctx, const ola_batch* b) {
     Cap c((size_t)1 << Config::cap_height);
-    batch_get_cap(ctx, b, (uint64_t*)c.data());
+    if (b->shard_bits == b->rate_bits) {
+        batch_get_cap(ctx, b, (uint64_t*)c.data());
+        return c;
+    }
+    const size_t nloc = (size_t)1 << b->local_cap_height();
+    OLA_CHECK(nloc * (size_t)ctx->world == c.size(), OLA_ERR_INTERNAL, "cap shard size");
+    DevBuf d_full(c.size() * 4);
+    comm_allgather(ctx, b->d_nodes + 4 * nloc, d_full.p, nloc * 32);
+    OLA_CUDA(cudaMemcpyAsync(c.data(), d_full.p, c.size() * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    OLA_CUDA(cudaStreamSynchronize(ctx->stream));
     return c;
+}
+// PolynomialBatch commitment of this proof: the whole LDE on one GPU, this rank's cosets under ola_set_comm
+static ola_batch* commit(ola_ctx* ctx, const uint64_t* d_cols, size_t ncols, uint32_t log_n, bool is_coeffs) {
+    if (ctx->world == 1) return batch_commit(ctx, d_cols, true, ncols, log_n, is_coeffs, Config::rate_bits, Config::cap_height);
+    const int per = (1 << Config::rate_bits) / ctx->world;
+    return batch_commit(ctx, d_cols, true, ncols, log_n, is_coeffs, Config::rate_bits, Config::cap_height, ctx->rank * per, per);
 }
 
 // prove_single_table (prover.rs:330-567)
@@ -609,7 +627,7 @@ static StarkProof prove_single_table(ola_ctx* ctx, const TableInfo& t, const Con
         OLA_CHECK(herr == 0, OLA_ERR_INVALID_ARG, "Non-binary filter?");
     }
     BatchHolder zs_commit;
-    zs_commit.b = batch_commit(ctx, d_zs.p, true, nzs, degree_bits, false, Config::rate_bits, Config::cap_height);
+    zs_commit.b = commit(ctx, d_zs.p, nzs, degree_bits, false);
     StarkProof proof;
     proof.trace_cap = batch_cap(ctx, trace_commit);
     proof.zs_cap = batch_cap(ctx, zs_commit.b);
@@ -621,14 +639,24 @@ static StarkProof prove_single_table(ola_ctx* ctx, const TableInfo& t, const Con
     int qdb = 0;
     while ((1 << qdb) < qdf) qdb++;
     OLA_CHECK((uint32_t)qdb <= Config::rate_bits, OLA_ERR_INVALID_ARG, "Having constraints of degree higher than the rate is not supported yet.");
-    const size_t qsize = n << qdb, L = n << Config::rate_bits;
-    DevBuf d_q(2 * qsize);
+    const size_t qsize = n << qdb;
+    // Coset shard: rank r owns leaf blocks [r*per, (r+1)*per) of every LDE; the quotient domain is blocks [0, 2^qdb).
+    // Each rank evaluates the blocks it owns (none for high ranks of a low-degree table), then the values are
+    // all-gathered block-wise; qstride = distance between the two alpha columns of d_q.
+    const int per = (1 << Config::rate_bits) / ctx->world, blk_lo = ctx->rank * per;
+    const int qblocks = std::max(0, std::min(per, (1 << qdb) - blk_lo));
+    const size_t qstride = ctx->world == 1 ? qsize : (n << Config::rate_bits);
+    DevBuf d_q(2 * qstride);
+    DevBuf d_qsend(ctx->world == 1 ? 1 : 2 * (size_t)per * n);
     {
         QuotArgs a;
         memset(&a, 0, sizeof(a));
         a.trace_lde = trace_commit->d_lde;
         a.zs_lde = zs_commit.b->d_lde;
-        a.L = L;
+        a.L = (size_t)1 << trace_commit->leaf_bits();  // column stride of this rank's LDE buffers
+        a.r_offset = (size_t)blk_lo * n;
+        a.npoints = (size_t)qblocks * n;
+        a.out_stride = ctx->world == 1 ? qsize : (size_t)per * n;
         a.log_n = (int)degree_bits;
         a.qdb = qdb;
         a.alpha0 = alpha0;
@@ -644,7 +672,7 @@ static StarkProof prove_single_table(ola_ctx* ctx, const TableInfo& t, const Con
             xx = gl::mul(xx, w);
         }
         a.pw = ctx->tw.pw[0];
-        a.out = d_q.p;
+        a.out = ctx->world == 1 ? d_q.p : d_qsend.p;
         a.d = desc.t;
         a.num_perm_zs = (int)num_perm_zs;
         a.compress_challenge = t.compress_challenge;
@@ -666,12 +694,14 @@ static StarkProof prove_single_table(ola_ctx* ctx, const TableInfo& t, const Con
         check_launch("quotient_kernel");
         OLA_CUDA(cudaStreamSynchronize(ctx->stream));  // h_apow / d_apow go out of scope
     }
+    if (ctx->world > 1)
+        for (int j = 0; j < 2; ++j) comm_allgather(ctx, d_qsend.p + (size_t)j * per * n, d_q.p + (size_t)j * qstride, (size_t)per * n * 8);
     // values at bit-reversed positions on 7*H_{n 2^qdb} -> natural coefficients (coset_ifft, prover.rs:700-704)
-    ntt::inverse_from_leaf_order(ctx, d_q.p, qsize, 2, (int)degree_bits + qdb, gl::GEN);
+    ntt::inverse_from_leaf_order(ctx, d_q.p, qstride, 2, (int)degree_bits + qdb, gl::GEN);
     if (cfg.check_quotient_degree && (size_t)qdf * n < qsize) {
         OLA_CUDA(cudaMemsetAsync(d_err.p, 0, 8, ctx->stream));
         size_t cnt = qsize - (size_t)qdf * n;
-        nonzero_kernel<<<dim3((unsigned)((cnt + 255) / 256), 2), 256, 0, ctx->stream>>>(d_q.p, qsize, (size_t)qdf * n, qsize, (int*)d_err.p);
+        nonzero_kernel<<<dim3((unsigned)((cnt + 255) / 256), 2), 256, 0, ctx->stream>>>(d_q.p, qstride, (size_t)qdf * n, qsize, (int*)d_err.p);
         count_launch(ctx);
         int herr = 0;
         OLA_CUDA(cudaMemcpyAsync(&herr, d_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -681,9 +711,9 @@ static StarkProof prove_single_table(ola_ctx* ctx, const TableInfo& t, const Con
     // all_quotient_chunks: [alpha][chunk] (prover.rs:463-478)
     DevBuf d_chunks((size_t)2 * qdf * n);
     for (int j = 0; j < 2; ++j)
-        OLA_CUDA(cudaMemcpyAsync(d_chunks.p + (size_t)j * qdf * n, d_q.p + (size_t)j * qsize, (size_t)qdf * n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        OLA_CUDA(cudaMemcpyAsync(d_chunks.p + (size_t)j * qdf * n, d_q.p + (size_t)j * qstride, (size_t)qdf * n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     BatchHolder q_commit;
-    q_commit.b = batch_commit(ctx, d_chunks.p, true, (size_t)2 * qdf, degree_bits, true, Config::rate_bits, Config::cap_height);
+    q_commit.b = commit(ctx, d_chunks.p, (size_t)2 * qdf, degree_bits, true);
     proof.quotient_cap = batch_cap(ctx, q_commit.b);
     ch.observe_cap(proof.quotient_cap);
 
@@ -748,7 +778,7 @@ std::vector<uint8_t> prove_all(ola_ctx* ctx, const std::vector<int>& table_ids, 
         OLA_CUDA(cudaMemcpyAsync(d_vals[i]->p, traces[i], cnt * 8, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
         canon_copy(ctx, d_vals[i]->p, d_vals[i]->p, cnt);  // the Z kernels read these values with canonical-input arithmetic
         commits[i].reset(new BatchHolder());
-        commits[i]->b = batch_commit(ctx, d_vals[i]->p, true, sys.tables[i].columns, log_ns[i], false, Config::rate_bits, Config::cap_height);
+        commits[i]->b = commit(ctx, d_vals[i]->p, sys.tables[i].columns, log_ns[i], false);
     }
     for (size_t i = 0; i < T; ++i) ch.observe_cap(batch_cap(ctx, commits[i]->b));
     // cross_table_lookup_data: challenges, then Z instances per table in registry order

@@ -73,3 +73,134 @@ def leaf_owner(leaf_index, degree_log, rate_bits, world):
     """(rank, local leaf index) of a global leaf under the coset shard."""
     per = (1 << (degree_log + rate_bits)) // world
     return leaf_index // per, leaf_index % per
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Communicators for the coset-sharded prover (ola_set_comm): the library takes two collectives as C callbacks.
+# ---------------------------------------------------------------------------------------------------------------------
+import ctypes  # noqa: E402
+
+_ALLGATHER = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p)
+_ALLREDUCE = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p)
+
+
+class _DevView:
+    """Zero-copy view of `count` int64 at a raw device pointer (CUDA array interface) for torch.as_tensor."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<i8", "data": (int(ptr), False), "version": 3}
+
+
+def set_comm_torch(ctx, group=None):
+    """Bind the library's collectives to torch.distributed (NCCL over NVLink on a GPU box): all-gather and a wrapping
+    u64 sum, both enqueued on the context's stream.  Call once per rank after init_process_group; keeps the callbacks
+    alive on the context."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = torch.device("cuda", ctx.device)
+    stream = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
+
+    def allgather(_user, send, recv, nbytes, _stream):
+        try:
+            with torch.cuda.device(dev), torch.cuda.stream(stream):
+                s = torch.as_tensor(_DevView(send, nbytes // 8), device=dev)
+                r = torch.as_tensor(_DevView(recv, world * (nbytes // 8)), device=dev)
+                dist.all_gather_into_tensor(r, s, group=group)
+            return 0
+        except Exception as e:  # pragma: no cover
+            print("olavm_b200.dist allgather failed:", repr(e))
+            return 1
+
+    def allreduce(_user, buf, count, _stream):
+        try:
+            with torch.cuda.device(dev), torch.cuda.stream(stream):
+                t = torch.as_tensor(_DevView(buf, count), device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)  # int64 wrap-around == u64 wrap-around
+            return 0
+        except Exception as e:  # pragma: no cover
+            print("olavm_b200.dist allreduce failed:", repr(e))
+            return 1
+
+    ctx._comm_keep = (_ALLGATHER(allgather), _ALLREDUCE(allreduce))
+    ctx.check(ctx._lib.ola_set_comm(ctx.handle, rank, world, ctypes.cast(ctx._comm_keep[0], ctypes.c_void_p),
+                                    ctypes.cast(ctx._comm_keep[1], ctypes.c_void_p), None))
+    return rank, world
+
+
+class LocalComm:
+    """In-process communicator for `world` host threads that each own a Context on the SAME GPU (test harness for the
+    sharded prover on a one-GPU box): collectives go through host staging buffers and a threading.Barrier.
+    Use: comm = LocalComm(world); in thread r: comm.attach(ctx_r, r)."""
+
+    def __init__(self, world):
+        import threading
+
+        self.world = world
+        self.barrier = threading.Barrier(world)
+        self.stage = [None] * world
+
+    def attach(self, ctx, rank):
+        import numpy as np
+
+        def exchange(ptr, count):
+            ctx.sync()
+            self.stage[rank] = ctx.download(ctypes.c_void_p(ptr), (count,))
+            self.barrier.wait()
+            parts = [self.stage[r] for r in range(self.world)]
+            self.barrier.wait()
+            return parts
+
+        def allgather(_user, send, recv, nbytes, _stream):
+            try:
+                parts = exchange(send, nbytes // 8)
+                ctx.upload(np.concatenate(parts), ctypes.c_void_p(recv))
+                return 0
+            except Exception as e:  # pragma: no cover
+                print("LocalComm allgather failed:", repr(e))
+                return 1
+
+        def allreduce(_user, buf, count, _stream):
+            try:
+                parts = exchange(buf, count)
+                total = parts[0].copy()
+                for p in parts[1:]:
+                    total += p  # uint64 wrap-around
+                ctx.upload(total, ctypes.c_void_p(buf))
+                return 0
+            except Exception as e:  # pragma: no cover
+                print("LocalComm allreduce failed:", repr(e))
+                return 1
+
+        ctx._comm_keep = (_ALLGATHER(allgather), _ALLREDUCE(allreduce))
+        ctx.check(ctx._lib.ola_set_comm(ctx.handle, rank, self.world, ctypes.cast(ctx._comm_keep[0], ctypes.c_void_p),
+                                        ctypes.cast(ctx._comm_keep[1], ctypes.c_void_p), None))
+
+
+def prove_sharded_local(device, world, table_ids, traces, **kw):
+    """Run the coset-sharded prover with `world` ranks as host threads on one GPU; returns every rank's proof bytes."""
+    import threading
+
+    from .context import Context
+    from .prover import prove_with_traces
+
+    comm = LocalComm(world)
+    out, err = [None] * world, [None] * world
+
+    def run(rank):
+        try:
+            ctx = Context(device)
+            comm.attach(ctx, rank)
+            out[rank] = prove_with_traces(ctx, table_ids, traces, **kw)
+            ctx.close()
+        except BaseException as e:  # noqa: B902
+            err[rank] = e
+            comm.barrier.abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for e in err:
+        if e is not None:
+            raise e
+    return out

@@ -191,3 +191,34 @@ def test_all_twelve_tables_pipeline_parity(ctx, orc):
     # the wire format's trailing compress_challenges carry only the Bitwise and Program entries (prover.rs:307-320)
     tail = np.frombuffer(got[-12 * 8:], dtype="<u8")
     assert [int(x) for x in tail] == [cc[i] if i in (2, 10) else 0 for i in range(12)]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Coset-sharded prover (ola_set_comm): `world` ranks as host threads on this one GPU, collectives through host staging.
+# Every rank must return the single-GPU proof, byte for byte.
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_prover_equals_single_gpu(ctx, orc, world):
+    from olavm_b200 import dist as odist
+
+    cmp_t, rc_t = _valid_cmp_rc(5, 6)
+    single = olavm_b200.prove_with_traces(ctx, [CMP, RC], [cmp_t, rc_t])
+    proofs = odist.prove_sharded_local(0, world, [CMP, RC], [cmp_t, rc_t])
+    assert all(p == single for p in proofs)
+    ok, msg = orc.stark_verify([CMP, RC], proofs[-1])
+    assert ok, msg
+
+
+def test_sharded_prover_five_table_system_and_cpu_table(ctx, orc):
+    from olavm_b200 import dist as odist
+
+    rng = np.random.default_rng(3)
+    ids, traces, cc = tracegen.hash_system_valid(orc, rng)  # degrees 3..7: quotient domains of 2, 4 and 8 cosets
+    single = olavm_b200.prove_with_traces(ctx, ids, traces, compress_challenges=cc)
+    for world in (2, 8):
+        proofs = odist.prove_sharded_local(0, world, ids, traces, compress_challenges=cc)
+        assert all(p == single for p in proofs), world
+    t = tracegen.cpu_random_trace(np.random.default_rng(12), 9)
+    single = olavm_b200.prove_with_traces(ctx, [CPU], [t], check_quotient_degree=False)
+    proofs = odist.prove_sharded_local(0, 4, [CPU], [t], check_quotient_degree=False)
+    assert all(p == single for p in proofs)

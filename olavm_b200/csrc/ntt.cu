@@ -459,7 +459,23 @@ __global__ void build_tables_kernel(uint64_t* pw, uint64_t* brs, uint64_t omega 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Opt every pass kernel into the device's maximum dynamic shared memory once, with the same value from every context
+// (a per-launch cudaFuncSetAttribute with the launch's own size races when several host threads drive one GPU).
+static void opt_in_shared_memory(int device) {
+    int max_optin = 0;
+    OLA_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    OLA_CUDA(cudaFuncSetAttribute(pass_strided_r8<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    OLA_CUDA(cudaFuncSetAttribute(pass_strided_r8<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    OLA_CUDA(cudaFuncSetAttribute(pass_contig_r8<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    OLA_CUDA(cudaFuncSetAttribute(pass_contig_r8<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    OLA_CUDA(cudaFuncSetAttribute(pass_strided<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    OLA_CUDA(cudaFuncSetAttribute(pass_strided<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    OLA_CUDA(cudaFuncSetAttribute(pass_contig<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    OLA_CUDA(cudaFuncSetAttribute(pass_contig<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+}
+
 void init_twiddles(ola_ctx* ctx) {
+    opt_in_shared_memory(ctx->device);
     for (int d = 0; d < 2; ++d) {
         OLA_CUDA(cudaMalloc(&ctx->tw.pw[d], 5120 * sizeof(uint64_t)));
         OLA_CUDA(cudaMalloc(&ctx->tw.brs[d], 2048 * sizeof(uint64_t)));
@@ -524,13 +540,11 @@ static void launch_strided(ola_ctx* ctx, const PassArgs& a, size_t ncols, int nc
     if (a.l >= 6) {
         const size_t padded = (size_t)R * TILE_T + ((size_t)R * TILE_T >> 4) + 1;
         size_t smem = ((size_t)R + 16 + padded) * sizeof(uint64_t);
-        OLA_CUDA(cudaFuncSetAttribute(pass_strided_r8<GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int threads = (int)std::min<size_t>((size_t)tune_threads(), (size_t)R);  // R items of 8 elements per round
         Launch lz(ctx, name);
         pass_strided_r8<GS><<<grid, threads, smem, ctx->stream>>>(a);
     } else {
         size_t smem = ((size_t)R + 16 + (size_t)R * TILE_T) * sizeof(uint64_t);
-        OLA_CUDA(cudaFuncSetAttribute(pass_strided<GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int threads = (int)std::min<size_t>(1024, std::max<size_t>(64, (size_t)R * TILE_T / 4));
         Launch lz(ctx, name);
         pass_strided<GS><<<grid, threads, smem, ctx->stream>>>(a);
@@ -546,13 +560,11 @@ static void launch_contig(ola_ctx* ctx, const PassArgs& a, size_t ncols, int nco
     if (a.l >= 6) {
         const size_t padded = (size_t)a.G * R + ((size_t)a.G * R >> 4) + 1;
         size_t smem = ((size_t)a.G * R + (size_t)a.G * 16 + padded) * sizeof(uint64_t);
-        OLA_CUDA(cudaFuncSetAttribute(pass_contig_r8<GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int threads = (int)std::min<size_t>((size_t)tune_threads(), std::max<size_t>(32, (size_t)R * a.G / 8));
         Launch lz(ctx, name);
         pass_contig_r8<GS><<<grid, threads, smem, ctx->stream>>>(a);
     } else {
         size_t smem = ((size_t)2 * a.G * R + (size_t)a.G * 16) * sizeof(uint64_t);
-        OLA_CUDA(cudaFuncSetAttribute(pass_contig<GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int threads = (int)std::min<size_t>(1024, std::max<size_t>(32, (size_t)R * a.G / 4));
         Launch lz(ctx, name);
         pass_contig<GS><<<grid, threads, smem, ctx->stream>>>(a);

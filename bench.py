@@ -108,8 +108,8 @@ def table_log_sizes(k):
             max(k - 10, 2), max(k - 2, 4), max(k - 5, 3)]
 
 
-def prove_all_tables(ctx, log_n):
-    """Second half of BASELINE.json's metric (configs[2]): wall time of one 12-table proof whose CPU table has 2^log_n rows
+def prove_all_tables(ctx, log_n, world=1, rank=0, odist=None, device=None):
+    """Second half of BASELINE.json's metric (configs[2]; at N > 1 strong-scaled by cosets, configs[4]): wall time of one 12-table proof whose CPU table has 2^log_n rows
     (94 trace + 78 CTL-Z + 12 quotient columns), through the C ABI from PINNED HOST traces to proof bytes on the host.
     Synthetic random traces with binary filters, quotient-degree check off ("pipeline parity": no executor exists here
     to make a satisfying trace -- every kernel of the proof runs on the same shapes); all 19 cross-table lookups."""
@@ -119,6 +119,8 @@ def prove_all_tables(ctx, log_n):
 
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import tracegen as tg
+
+    dist = None
 
     rng = np.random.default_rng(22)
     gens = [tg.cpu_random_trace, tg.memory_random_trace, tg.bitwise_random_trace, tg.cmp_random_trace, None, tg.poseidon_random_trace,
@@ -136,17 +138,51 @@ def prove_all_tables(ctx, log_n):
     ids = list(range(12))
     cc = [int(x) for x in rng.integers(0, 0xFFFFFFFF00000001, size=12, dtype=np.uint64)]
     small = [np.ascontiguousarray(t[:, : min(t.shape[1], 1 << 16 if i == 4 else 1 << 10)]) for i, t in enumerate(traces)]
+    if world > 1:
+        # coset-sharded prover (ola_set_comm): every rank holds the same traces (same seed) and proves collectively;
+        # collectives = NCCL through torch.distributed on the library's stream
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        odist.set_comm_torch(ctx)
+
+    def sync_all():
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+
     olavm_b200.prove_with_traces(ctx, ids, small, check_quotient_degree=False, compress_challenges=cc)  # warm-up (module load, pool)
+    sync_all()
     t0 = time.perf_counter()
     olavm_b200.prove_with_traces(ctx, ids, traces, check_quotient_degree=False, compress_challenges=cc)  # grows the memory pool
     first = time.perf_counter() - t0
+    sync_all()
     ctx.profile_begin()
     t0 = time.perf_counter()
     proof = olavm_b200.prove_with_traces(ctx, ids, traces, check_quotient_degree=False, compress_challenges=cc)
     dt = time.perf_counter() - t0
     prof = ctx.profile_end()
+    if world > 1:
+        dt = odist.max_over_ranks(dt, device=device)  # every rank returns the same proof; the slowest one defines the time
+        import hashlib
+
+        digest = torch.tensor(list(hashlib.sha256(proof).digest()[:8]), dtype=torch.int64, device=device)
+        lo, hi = digest.clone(), digest.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert bool((lo == hi).all()), "ranks returned different proofs"
     top = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:8]
     rows = sum(1 << lg for lg in logs)
+    if rank != 0:
+        return None
+    if world > 1:
+        import hashlib
+
+        return {"log_n_cpu": log_n, "table_log_n": logs, "seconds": dt, "first_call_seconds": first, "proof_bytes": len(proof),
+                "proof_sha256_16": hashlib.sha256(proof).hexdigest()[:16], "tables": 12, "ctls": 19, "trace_rows_total": rows,
+                "constraint_rows_per_s": rows / dt, "parallelism": f"coset-shard x{world} (ola_set_comm over NCCL)", "scaling": "strong",
+                "mode": "synthetic random traces, binary filters, quotient-degree check off; pinned host traces in, proof bytes out",
+                "kernel_ms_rank0": {k: round(v["ms"], 1) for k, v in top}, "kernel_ms_total_rank0": round(sum(v["ms"] for v in prof.values()), 1)}
     # bounded CPU sample of the same path: the oracle port proving a 2^14-row CPU table alone, all host threads
     host_threads()
     import oracle
@@ -158,7 +194,9 @@ def prove_all_tables(ctx, log_n):
     cpu_port = {"kind": "port", "cores": os.cpu_count(), "sample": "oracle port, CPU table alone, 2^14 rows (94 trace + 78 Z + 12 quotient columns)",
                 "seconds": cpu_dt, "constraint_rows_per_s": (1 << 14) / cpu_dt,
                 "context": "reference README.md:69 quotes 39.767 s for a 2^20-row proof on 64 cores (other hardware)"}
-    return {"log_n_cpu": log_n, "cpu_baseline": cpu_port, "table_log_n": logs, "seconds": dt, "first_call_seconds": first, "proof_bytes": len(proof), "tables": 12, "ctls": 19,
+    import hashlib
+
+    return {"log_n_cpu": log_n, "cpu_baseline": cpu_port, "proof_sha256_16": hashlib.sha256(proof).hexdigest()[:16], "table_log_n": logs, "seconds": dt, "first_call_seconds": first, "proof_bytes": len(proof), "tables": 12, "ctls": 19,
             "cpu_table_columns": {"trace": 94, "ctl_z": 78, "quotient": 12}, "trace_rows_total": rows,
             "constraint_rows_per_s": rows / dt,
             "mode": "synthetic random traces, binary filters, quotient-degree check off; pinned host traces in, proof bytes out",
@@ -251,7 +289,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--prove-log-n", type=int, default=22, help="N=1: also time one 12-table proof whose CPU table has 2^k rows (0 = skip)")
+    ap.add_argument("--prove-log-n", type=int, default=22, help="also time one 12-table proof whose CPU table has 2^k rows (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -377,8 +415,8 @@ def main():
         ctx.free(p)
     # extra legs (not the headline): strong-scaled coset-shard commit at every N, the full 12-table proof at N = 1
     extra = {"coset_shard_commit": coset_shard_commit(ctx, torch, dist, odist, world, rank, torch.device("cuda", local_rank), stream)}
-    if rank == 0 and world == 1 and args.prove_log_n:
-        extra["prove_all_tables"] = prove_all_tables(ctx, args.prove_log_n)
+    if args.prove_log_n:
+        extra["prove_all_tables"] = prove_all_tables(ctx, args.prove_log_n, world, rank, odist, torch.device("cuda", local_rank))
     if rank == 0:
         line.update(extra)
         print(json.dumps(line))

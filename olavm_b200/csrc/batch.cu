@@ -95,6 +95,31 @@ void gather_rows(ola_ctx* ctx, const uint64_t* d_cols, size_t col_stride, size_t
     OLA_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
+// coset LDE of b->d_coeffs (shift 7, blowup 2^rate_bits, cosets [coset_first, +coset_count)) straight into leaf order
+// (oracle.rs:101-129 + :84-85), then MerkleTree::new_v2: leaf digests and the level reduction down to the cap
+static void finish_commit(ola_ctx* ctx, ola_batch* b, int coset_first, int coset_count) {
+    const size_t n = (size_t)1 << b->log_n, L = n << b->shard_bits;
+    {
+        ntt::FwdDesc d;
+        d.src = b->d_coeffs;
+        d.src_col_stride = n;
+        d.dst = b->d_lde;
+        d.dst_col_stride = L;
+        d.dst_coset_stride = n;
+        d.ncols = b->ncols;
+        d.log_n = (int)b->log_n;
+        d.coset_bits = (int)b->rate_bits;
+        d.coset_first = coset_first;
+        d.coset_count = coset_count;
+        d.shift = gl::GEN;
+        d.tag_strided = "lde_strided";
+        d.tag_contig = "lde_contig";
+        ntt::forward(ctx, d);
+    }
+    poseidon::hash_rows_colmajor(ctx, b->d_lde, L, L, b->ncols, b->d_nodes + 4 * L);
+    poseidon::merkle_levels(ctx, b->d_nodes, L, (size_t)1 << b->local_cap_height());
+}
+
 ola_batch* batch_commit(ola_ctx* ctx, const uint64_t* cols, bool on_device, size_t ncols, uint32_t log_n, bool is_coeffs,
                         uint32_t rate_bits, uint32_t cap_height, int coset_first, int coset_count) {
     OLA_CHECK(cols != nullptr && ncols > 0, OLA_ERR_INVALID_ARG, "commit: empty batch");
@@ -178,27 +203,73 @@ ola_batch* batch_commit(ola_ctx* ctx, const uint64_t* cols, bool on_device, size
             ola::dev_free(tmp_work);
         }
     }
-    // coset LDE, shift 7, blowup 2^rate_bits, straight into leaf order (oracle.rs:101-129 + :84-85)
-    {
-        ntt::FwdDesc d;
-        d.src = b->d_coeffs;
-        d.src_col_stride = n;
-        d.dst = b->d_lde;
-        d.dst_col_stride = L;
-        d.dst_coset_stride = n;
-        d.ncols = ncols;
-        d.log_n = (int)log_n;
-        d.coset_bits = (int)rate_bits;
-        d.coset_first = coset_first;
-        d.coset_count = coset_count;
-        d.shift = gl::GEN;
-        d.tag_strided = "lde_strided";
-        d.tag_contig = "lde_contig";
-        ntt::forward(ctx, d);
+    finish_commit(ctx, b.get(), coset_first, coset_count);
+    return b.release();
+}
+
+// Column-sharded coefficients + coset-sharded commitment for the multi-GPU prover (ola_set_comm): rank r turns columns
+// [r*per, (r+1)*per) of the (replicated, device-resident) values into coefficients and one all-gather replicates them
+// (openings and the FRI composition read every coefficient column on every rank); the LDE, leaf hashing and subtree
+// reduction then cover this rank's cosets only.
+ola_batch* batch_commit_dist(ola_ctx* ctx, const uint64_t* d_cols, size_t ncols, uint32_t log_n, bool is_coeffs, uint32_t rate_bits,
+                             uint32_t cap_height) {
+    OLA_CHECK(ctx->world > 1 && ((1 << rate_bits) % ctx->world) == 0, OLA_ERR_INTERNAL, "batch_commit_dist needs a communicator");
+    OLA_CHECK(d_cols != nullptr && ncols > 0, OLA_ERR_INVALID_ARG, "commit: empty batch");
+    OLA_CHECK(log_n + rate_bits <= 32, OLA_ERR_INVALID_ARG, "commit: LDE size exceeds the field's two-adicity (2^32)");
+    const int coset_count = (1 << rate_bits) / ctx->world, coset_first = ctx->rank * coset_count;
+    uint32_t shard_bits = 0;
+    while ((1 << shard_bits) < coset_count) ++shard_bits;
+    OLA_CHECK(cap_height >= rate_bits - shard_bits && cap_height <= log_n + rate_bits, OLA_ERR_INVALID_ARG, "commit: cap height out of range");
+    std::unique_ptr<ola_batch, void (*)(ola_batch*)> b(new ola_batch(), [](ola_batch* p) {
+        batch_release(p);
+        delete p;
+    });
+    b->ncols = ncols;
+    b->log_n = log_n;
+    b->rate_bits = rate_bits;
+    b->cap_height = cap_height;
+    b->shard_bits = shard_bits;
+    b->coset_first = (uint32_t)coset_first;
+    const size_t n = (size_t)1 << log_n, L = n << shard_bits;
+    const size_t per = (ncols + ctx->world - 1) / ctx->world;  // columns per rank (the last ranks may own fewer / none)
+    dev_alloc(&b->d_coeffs, per * ctx->world * n);              // padded: the all-gather needs equal contributions
+    dev_alloc(&b->d_lde, ncols * L);
+    dev_alloc(&b->d_nodes, 2 * L * 4);
+    if (is_coeffs) {
+        canon_copy(ctx, b->d_coeffs, d_cols, ncols * n);
+    } else {
+        const size_t lo = std::min(ncols, (size_t)ctx->rank * per), hi = std::min(ncols, lo + per);
+        uint64_t* tmp = nullptr;
+        dev_alloc(&tmp, 2 * per * n);  // [send | work]
+        try {
+            if (hi - lo < per) OLA_CUDA(cudaMemsetAsync(tmp, 0, per * n * 8, ctx->stream));
+            if (hi > lo) {
+                ntt::FwdDesc d;
+                d.src = d_cols + lo * n;
+                d.src_col_stride = n;
+                d.work = tmp + per * n;
+                d.work_col_stride = n;
+                d.dst = tmp;
+                d.dst_col_stride = n;
+                d.ncols = hi - lo;
+                d.log_n = (int)log_n;
+                d.inverse_roots = true;
+                d.natural_output = true;
+                d.apply_scale = true;
+                d.scale = gl::inv(((uint64_t)1 << log_n) % gl::P);
+                d.tag_strided = "intt_strided";
+                d.tag_contig = "intt_contig";
+                ntt::forward(ctx, d);
+            }
+            comm_allgather(ctx, tmp, b->d_coeffs, per * n * 8);
+            OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+        } catch (...) {
+            ola::dev_free(tmp);
+            throw;
+        }
+        ola::dev_free(tmp);
     }
-    // MerkleTree::new_v2: leaf digests then level reduction down to the cap
-    poseidon::hash_rows_colmajor(ctx, b->d_lde, L, L, ncols, b->d_nodes + 4 * L);
-    poseidon::merkle_levels(ctx, b->d_nodes, L, (size_t)1 << b->local_cap_height());
+    finish_commit(ctx, b.get(), coset_first, coset_count);
     return b.release();
 }
 

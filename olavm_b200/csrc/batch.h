@@ -29,6 +29,9 @@ void gather_rows(ola_ctx* ctx, const uint64_t* d_cols, size_t col_stride, size_t
                  uint64_t* out_host);
 ola_batch* batch_commit(ola_ctx* ctx, const uint64_t* cols, bool on_device, size_t ncols, uint32_t log_n, bool is_coeffs,
                         uint32_t rate_bits, uint32_t cap_height, int coset_first = 0, int coset_count = -1);
+// multi-GPU prover: column-sharded iNTT + all-gather of coefficients, coset-sharded LDE / hashing / tree (device input)
+ola_batch* batch_commit_dist(ola_ctx* ctx, const uint64_t* d_cols, size_t ncols, uint32_t log_n, bool is_coeffs, uint32_t rate_bits,
+                             uint32_t cap_height);
 void batch_release(ola_batch* b);
 void batch_get_cap(ola_ctx* ctx, const ola_batch* b, uint64_t* cap_host);
 void batch_get_leaves(ola_ctx* ctx, const ola_batch* b, size_t first, size_t count, uint64_t* out_host);

@@ -27,6 +27,17 @@ using air::Consumer;
 using air::Fp;
 using air::Row;
 
+struct DevBuf {
+    uint64_t* p = nullptr;
+    DevBuf() {}
+    explicit DevBuf(size_t n) { dev_alloc(&p, n); }
+    ~DevBuf() {
+        if (p) ola::dev_free(p);
+    }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+
 // ---- device descriptors of linear-combination columns / CTL instances / permutation instances ----------------
 struct DevLc {
     int off, cnt;
@@ -381,21 +392,37 @@ static std::vector<E> eval_batch_at(ola_ctx* ctx, const ola_batch* b, size_t fir
         p.zr[k] = zr;
         zr = gl::mul(zr, zr);
     }
-    uint64_t* d_part = ctx_scratch(ctx, ncols * nchunks * 2);
-    {
-        Launch lz(ctx, "openings_eval");
-        eval_partial_kernel<<<dim3((unsigned)nchunks, (unsigned)ncols), EV_THREADS, 0, ctx->stream>>>(b->d_coeffs + first_col * n, n, p, d_part, nchunks);
+    // multi-GPU: the coefficients are replicated, so each rank evaluates a slice of the columns and the results are summed
+    // (zeros elsewhere); single GPU: the slice is everything
+    const size_t per = (ncols + ctx->world - 1) / ctx->world;
+    const size_t c_lo = std::min(ncols, (size_t)ctx->rank * per), c_hi = std::min(ncols, c_lo + per), mine = c_hi - c_lo;
+    std::vector<uint64_t> res(2 * ncols, 0);
+    if (mine) {
+        uint64_t* d_part = ctx_scratch(ctx, mine * nchunks * 2);
+        {
+            Launch lz(ctx, "openings_eval");
+            eval_partial_kernel<<<dim3((unsigned)nchunks, (unsigned)mine), EV_THREADS, 0, ctx->stream>>>(b->d_coeffs + (first_col + c_lo) * n, n, p, d_part, nchunks);
+        }
+        check_launch("eval_partial_kernel");
+        std::vector<uint64_t> h(mine * nchunks * 2);
+        OLA_CUDA(cudaMemcpyAsync(h.data(), d_part, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+        const E zc = gl::pow(z, (uint64_t)EV_CHUNK);
+        for (size_t c = 0; c < mine; ++c) {
+            E acc = gl::make2(0, 0);
+            for (size_t s = nchunks; s-- > 0;) acc = gl::add(gl::mul(acc, zc), gl::make2(h[(c * nchunks + s) * 2], h[(c * nchunks + s) * 2 + 1]));
+            res[2 * (c_lo + c)] = gl::canon(acc.c0);
+            res[2 * (c_lo + c) + 1] = gl::canon(acc.c1);
+        }
     }
-    check_launch("eval_partial_kernel");
-    std::vector<uint64_t> h(ncols * nchunks * 2);
-    OLA_CUDA(cudaMemcpyAsync(h.data(), d_part, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    OLA_CUDA(cudaStreamSynchronize(ctx->stream));
-    const E zc = gl::pow(z, (uint64_t)EV_CHUNK);
-    for (size_t c = 0; c < ncols; ++c) {
-        E acc = gl::make2(0, 0);
-        for (size_t s = nchunks; s-- > 0;) acc = gl::add(gl::mul(acc, zc), gl::make2(h[(c * nchunks + s) * 2], h[(c * nchunks + s) * 2 + 1]));
-        out.push_back(acc);
+    if (ctx->world > 1) {
+        DevBuf d_res(2 * ncols);
+        OLA_CUDA(cudaMemcpyAsync(d_res.p, res.data(), res.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        comm_allreduce(ctx, d_res.p, 2 * ncols);
+        OLA_CUDA(cudaMemcpyAsync(res.data(), d_res.p, res.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        OLA_CUDA(cudaStreamSynchronize(ctx->stream));
     }
+    for (size_t c = 0; c < ncols; ++c) out.push_back(gl::make2(res[2 * c], res[2 * c + 1]));
     return out;
 }
 
@@ -516,16 +543,6 @@ struct BatchHolder {  // RAII for ola_batch
     BatchHolder(const BatchHolder&) = delete;
     BatchHolder& operator=(const BatchHolder&) = delete;
 };
-struct DevBuf {
-    uint64_t* p = nullptr;
-    DevBuf() {}
-    explicit DevBuf(size_t n) { dev_alloc(&p, n); }
-    ~DevBuf() {
-        if (p) ola::dev_free(p);
-    }
-    DevBuf(const DevBuf&) = delete;
-    DevBuf& operator=(const DevBuf&) = delete;
-};
 
 // the full Merkle cap of a commitment; for a coset shard: one all-gather of this rank's cap entries
 static Cap batch_cap(ola_ctx* ctx, const ola_batch* b) {
@@ -545,8 +562,7 @@ static Cap batch_cap(ola_ctx* ctx, const ola_batch* b) {
 // PolynomialBatch commitment of this proof: the whole LDE on one GPU, this rank's cosets under ola_set_comm
 static ola_batch* commit(ola_ctx* ctx, const uint64_t* d_cols, size_t ncols, uint32_t log_n, bool is_coeffs) {
     if (ctx->world == 1) return batch_commit(ctx, d_cols, true, ncols, log_n, is_coeffs, Config::rate_bits, Config::cap_height);
-    const int per = (1 << Config::rate_bits) / ctx->world;
-    return batch_commit(ctx, d_cols, true, ncols, log_n, is_coeffs, Config::rate_bits, Config::cap_height, ctx->rank * per, per);
+    return batch_commit_dist(ctx, d_cols, ncols, log_n, is_coeffs, Config::rate_bits, Config::cap_height);
 }
 
 // prove_single_table (prover.rs:330-567)
@@ -774,9 +790,23 @@ std::vector<uint8_t> prove_all(ola_ctx* ctx, const std::vector<int>& table_ids, 
     for (size_t i = 0; i < T; ++i) {
         const size_t n = (size_t)1 << log_ns[i], cnt = n * sys.tables[i].columns;
         OLA_CHECK(log_ns[i] + Config::rate_bits <= 32, OLA_ERR_INVALID_ARG, "trace too long for the field's two-adicity");
-        d_vals[i].reset(new DevBuf(cnt));
-        OLA_CUDA(cudaMemcpyAsync(d_vals[i]->p, traces[i], cnt * 8, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
-        canon_copy(ctx, d_vals[i]->p, d_vals[i]->p, cnt);  // the Z kernels read these values with canonical-input arithmetic
+        if (ctx->world > 1 && !on_device) {
+            // every rank holds the same host trace: each uploads 1/world of the columns over its own PCIe link and one
+            // all-gather over NVLink replicates the table (padded to equal contributions)
+            const size_t cols = (size_t)sys.tables[i].columns, per = (cols + ctx->world - 1) / ctx->world;
+            const size_t lo = std::min(cols, (size_t)ctx->rank * per), hi = std::min(cols, lo + per);
+            d_vals[i].reset(new DevBuf(per * ctx->world * n));
+            DevBuf send(per * n);
+            if (hi - lo < per) OLA_CUDA(cudaMemsetAsync(send.p, 0, per * n * 8, ctx->stream));
+            if (hi > lo) OLA_CUDA(cudaMemcpyAsync(send.p, traces[i] + lo * n, (hi - lo) * n * 8, cudaMemcpyHostToDevice, ctx->stream));
+            canon_copy(ctx, send.p, send.p, per * n);
+            comm_allgather(ctx, send.p, d_vals[i]->p, per * n * 8);
+            OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+        } else {
+            d_vals[i].reset(new DevBuf(cnt));
+            OLA_CUDA(cudaMemcpyAsync(d_vals[i]->p, traces[i], cnt * 8, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+            canon_copy(ctx, d_vals[i]->p, d_vals[i]->p, cnt);  // the Z kernels read these values with canonical-input arithmetic
+        }
         commits[i].reset(new BatchHolder());
         commits[i]->b = commit(ctx, d_vals[i]->p, sys.tables[i].columns, log_ns[i], false);
     }

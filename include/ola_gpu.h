@@ -179,6 +179,10 @@ typedef int (*ola_allgather_fn)(void* user, const void* send_dev, void* recv_dev
 typedef int (*ola_allreduce_u64_fn)(void* user, void* buf_dev, size_t count_u64, void* stream); /* in place, wrapping sum */
 int ola_set_comm(ola_ctx* ctx, int rank, int world, ola_allgather_fn allgather, ola_allreduce_u64_fn allreduce_sum, void* user);
 
+/* verify_proof (circuits/src/stark/verifier.rs:32-212) over Buffer::read_all_proof's bytes: host code, no GPU or
+ * context needed.  table_ids as for ola_prove (the system the proof was made for).  Returns OLA_OK when the proof is
+ * accepted; OLA_ERR_INVALID_ARG with the reason in err (NUL-terminated, truncated to errcap) when it is rejected. */
+int ola_verify(const int* table_ids, uint32_t ntables, const uint8_t* proof, size_t proof_len, char* err, size_t errcap);
 /* number of trace columns of a table (S::COLUMNS), or -1 if its constraint kernel is not compiled in */
 int ola_table_columns(int table_id);
 

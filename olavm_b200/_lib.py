@@ -66,6 +66,7 @@ SIGNATURES = {
     "ola_prove": (_int, [_vp, ctypes.POINTER(_int), _u32, ctypes.POINTER(_vp), _int, ctypes.POINTER(_u32), _vp, _int, _vp, _sz,
                          ctypes.POINTER(_sz)]),
     "ola_table_columns": (_int, [_int]),
+    "ola_verify": (_int, [ctypes.POINTER(_int), _u32, _vp, _sz, ctypes.c_char_p, _sz]),
     "ola_set_comm": (_int, [_vp, _int, _int, _vp, _vp, _vp]),
     "ola_batch_free": (_int, [_vp, _vp]),
     "ola_batch_ncols": (_sz, [_vp]),

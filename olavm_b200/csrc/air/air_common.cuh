@@ -11,52 +11,58 @@ namespace air {
 
 struct Fp {
     uint64_t v;
-    __device__ __forceinline__ Fp() : v(0) {}
-    __device__ __forceinline__ explicit Fp(uint64_t x) : v(x) {}
-    __device__ __forceinline__ Fp operator+(Fp o) const { return Fp(gl::add(v, o.v)); }
-    __device__ __forceinline__ Fp operator-(Fp o) const { return Fp(gl::sub(v, o.v)); }
-    __device__ __forceinline__ Fp operator*(Fp o) const { return Fp(gl::mul(v, o.v)); }
-    __device__ __forceinline__ Fp& operator+=(Fp o) {
+    __host__ __device__ __forceinline__ Fp() : v(0) {}
+    __host__ __device__ __forceinline__ explicit Fp(uint64_t x) : v(x) {}
+    __host__ __device__ __forceinline__ Fp operator+(Fp o) const { return Fp(gl::add(v, o.v)); }
+    __host__ __device__ __forceinline__ Fp operator-(Fp o) const { return Fp(gl::sub(v, o.v)); }
+    __host__ __device__ __forceinline__ Fp operator*(Fp o) const { return Fp(gl::mul(v, o.v)); }
+    __host__ __device__ __forceinline__ Fp& operator+=(Fp o) {
         v = gl::add(v, o.v);
         return *this;
     }
-    __device__ __forceinline__ Fp& operator*=(Fp o) {
+    __host__ __device__ __forceinline__ Fp& operator*=(Fp o) {
         v = gl::mul(v, o.v);
         return *this;
     }
 };
-__device__ __forceinline__ Fp fp(uint64_t k) { return Fp(k); }  // k must be canonical
+__host__ __device__ __forceinline__ Fp fp(uint64_t k) { return Fp(k); }  // k must be canonical
 template <>
-__device__ __forceinline__ Fp kc<Fp>(uint64_t k) {
+__host__ __device__ __forceinline__ Fp kc<Fp>(uint64_t k) {
     return Fp(k);
 }
 template <>
-__device__ __forceinline__ bool is_zero<Fp>(const Fp& x) {
+__host__ __device__ __forceinline__ bool is_zero<Fp>(const Fp& x) {
     return x.v == 0;
 }
-__device__ __forceinline__ Fp one() { return Fp(1); }
+__host__ __device__ __forceinline__ Fp one() { return Fp(1); }
 
 // one LDE row of a column-major batch: element c at base[c*stride + r]
 struct Row {
     const uint64_t* __restrict__ base;
     size_t stride, r;
-    __device__ __forceinline__ Fp operator[](int c) const { return Fp(__ldg(base + (size_t)c * stride + r)); }
+    __host__ __device__ __forceinline__ Fp operator[](int c) const {
+#if defined(__CUDA_ARCH__)
+        return Fp(__ldg(base + (size_t)c * stride + r));
+#else
+        return Fp(base[(size_t)c * stride + r]);
+#endif
+    }
 };
 
 // ConstraintConsumer with num_challenges == 2 (constraint_consumer.rs:46-80)
 struct Consumer {
     Fp alpha0, alpha1, acc0, acc1, z_last, lagrange_first, lagrange_last;
-    __device__ __forceinline__ void constraint(Fp c) {
+    __host__ __device__ __forceinline__ void constraint(Fp c) {
         acc0 = acc0 * alpha0 + c;
         acc1 = acc1 * alpha1 + c;
     }
-    __device__ __forceinline__ void constraint_transition(Fp c) { constraint(c * z_last); }
-    __device__ __forceinline__ void constraint_first_row(Fp c) { constraint(c * lagrange_first); }
-    __device__ __forceinline__ void constraint_last_row(Fp c) { constraint(c * lagrange_last); }
+    __host__ __device__ __forceinline__ void constraint_transition(Fp c) { constraint(c * z_last); }
+    __host__ __device__ __forceinline__ void constraint_first_row(Fp c) { constraint(c * lagrange_first); }
+    __host__ __device__ __forceinline__ void constraint_last_row(Fp c) { constraint(c * lagrange_last); }
 };
 
 // circuits/src/stark/lookup.rs:13-35
-__device__ __forceinline__ void eval_lookups(const Row& lv, const Row& nv, Consumer& yc, int col_permuted_input, int col_permuted_table) {
+__host__ __device__ __forceinline__ void eval_lookups(const Row& lv, const Row& nv, Consumer& yc, int col_permuted_input, int col_permuted_table) {
     Fp local_perm_input = lv[col_permuted_input];
     Fp next_perm_table = nv[col_permuted_table];
     Fp next_perm_input = nv[col_permuted_input];

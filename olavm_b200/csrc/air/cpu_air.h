@@ -19,7 +19,7 @@
 #include <stdint.h>
 
 #if defined(__CUDACC__)
-#define AIR_FN __device__ __forceinline__
+#define AIR_FN __host__ __device__ __forceinline__
 #else
 #define AIR_FN inline
 #endif

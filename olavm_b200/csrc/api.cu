@@ -10,6 +10,7 @@
 #include "ntt.h"
 #include "poseidon.cuh"
 #include "stark.h"
+#include "verify.h"
 
 namespace {
 
@@ -416,6 +417,26 @@ int ola_set_comm(ola_ctx* ctx, int rank, int world, ola_allgather_fn allgather, 
         ctx->comm_allreduce = allreduce_sum;
         ctx->comm_user = user;
     });
+}
+int ola_verify(const int* table_ids, uint32_t ntables, const uint8_t* proof, size_t proof_len, char* err, size_t errcap) {
+    auto put = [&](const std::string& m) {
+        if (err && errcap) snprintf(err, errcap, "%s", m.c_str());
+    };
+    if (!table_ids || !proof) {
+        put("null argument");
+        return OLA_ERR_INVALID_ARG;
+    }
+    try {
+        const std::string e = ola::stark::verify::verify_all(proof, proof_len, std::vector<int>(table_ids, table_ids + ntables));
+        put(e);
+        return e.empty() ? OLA_OK : OLA_ERR_INVALID_ARG;
+    } catch (const std::exception& ex) {
+        put(ex.what());
+        return OLA_ERR_INVALID_ARG;
+    } catch (...) {
+        put("unknown error");
+        return OLA_ERR_INTERNAL;
+    }
 }
 int ola_table_columns(int table_id) {
     try {

@@ -42,3 +42,15 @@ def prove_with_traces(ctx, table_ids, trace_poly_values, check_quotient_degree=T
     ctx.check(ctx._lib.ola_prove(ctx.handle, ids, k, ptrs, 0, logs, cc, 1 if check_quotient_degree else 0, out.ctypes.data_as(ctypes.c_void_p),
                                  max_bytes, ctypes.byref(n)))
     return out[: n.value].tobytes()
+
+
+def verify_proof(table_ids, proof):
+    """`circuits::stark::verifier::verify_proof` over `Buffer::read_all_proof`'s bytes (verifier.rs:32-212,
+    serialization.rs:395-411) -> (accepted, reason).  Host code: needs the library but no GPU."""
+    lib = _lib.load()
+    k = len(table_ids)
+    ids = (ctypes.c_int * k)(*[int(x) for x in table_ids])
+    buf = np.frombuffer(bytes(proof), dtype=np.uint8)
+    err = ctypes.create_string_buffer(512)
+    rc = lib.ola_verify(ids, k, buf.ctypes.data_as(ctypes.c_void_p), buf.size, err, 512)
+    return rc == 0, err.value.decode()

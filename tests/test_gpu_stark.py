@@ -130,6 +130,8 @@ def test_valid_trace_of_each_remaining_table(ctx, orc, name):
     assert got == ref
     ok, msg = orc.stark_verify(ids, got)
     assert ok, msg
+    ok, msg = olavm_b200.verify_proof(ids, got)  # product prover -> product verifier
+    assert ok, msg
 
 
 @pytest.mark.parametrize("name", sorted(RANDOM))
@@ -157,6 +159,8 @@ def test_five_table_hash_system(ctx, orc):
     got = olavm_b200.prove_with_traces(ctx, ids, traces, compress_challenges=cc)
     assert got == ref
     ok, msg = orc.stark_verify(ids, got)
+    assert ok, msg
+    ok, msg = olavm_b200.verify_proof(ids, got)
     assert ok, msg
     # a broken Poseidon round witness is caught by the device-side degree check like the reference's panic
     bad = [t.copy() for t in traces]

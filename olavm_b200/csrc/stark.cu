@@ -212,8 +212,8 @@ __device__ __forceinline__ uint64_t pow_omega_fwd(const uint64_t* __restrict__ p
     return gl::mul(r, __ldg(pw + (E & 2047u)));
 }
 
-template <class Air>
-__global__ void __launch_bounds__(128, 3) quotient_kernel(const QuotArgs a) {
+template <class Air, int MINB = 3>
+__global__ void __launch_bounds__(128, MINB) quotient_kernel(const QuotArgs a) {
     const size_t r_raw = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r_raw >= a.npoints) return;
     const size_t rg = r_raw + a.r_offset;  // index in the quotient domain (leaf order)
@@ -322,7 +322,17 @@ static void launch_quotient(ola_ctx* ctx, int table_id, QuotArgs a) {
     const unsigned blocks = (unsigned)((size + threads - 1) / threads);
     Launch lz(ctx, "quotient");
     switch (table_id) {
-        case T_CPU: quotient_kernel<air::Cpu><<<blocks, threads, 0, ctx->stream>>>(a); break;
+        case T_CPU: {
+            // resident CTAs per SM for the widest body (3: 168 registers, no spills; 4: 128 registers + spills), tuned on hardware
+            static const int minb = [] { const char* e = getenv("OLA_QUOT_MINB"); return e ? atoi(e) : 3; }();
+            if (minb == 4)
+                quotient_kernel<air::Cpu, 4><<<blocks, threads, 0, ctx->stream>>>(a);
+            else if (minb == 2)
+                quotient_kernel<air::Cpu, 2><<<blocks, threads, 0, ctx->stream>>>(a);
+            else
+                quotient_kernel<air::Cpu, 3><<<blocks, threads, 0, ctx->stream>>>(a);
+            break;
+        }
         case T_MEMORY: quotient_kernel<air::Memory><<<blocks, threads, 0, ctx->stream>>>(a); break;
         case T_CMP: quotient_kernel<air::Cmp><<<blocks, threads, 0, ctx->stream>>>(a); break;
         case T_RANGECHECK: quotient_kernel<air::RangeCheck><<<blocks, threads, 0, ctx->stream>>>(a); break;

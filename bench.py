@@ -330,9 +330,10 @@ def main():
         ctx.check(lib.ola_coset_lde(ctx.handle, d_coeffs, d_lde, 1, NCOLS, LOG_N, RATE_BITS, SHIFT, 0))
 
     def step_e2e():
-        ctx.check(lib.ola_dev_upload(ctx.handle, d_coeffs, host.data_ptr(), NCOLS * n))
-        ctx.check(lib.ola_ntt_inverse(ctx.handle, d_coeffs, 1, NCOLS, LOG_N))
-        ctx.check(lib.ola_coset_lde(ctx.handle, d_coeffs, d_lde, 1, NCOLS, LOG_N, RATE_BITS, SHIFT, 0))
+        # the reference-facing call with HOST buffers: PolynomialBatch::from_values up to lde_values (ola_lde_batch uploads
+        # the pinned trace in column chunks, each chunk's iNTT + LDE overlapping the next chunk's H2D copy), then the
+        # device -> host read of the opened LDE rows
+        ctx.check(lib.ola_lde_batch(ctx.handle, host.data_ptr(), 0, NCOLS, LOG_N, 0, RATE_BITS, d_coeffs, d_lde))
         for k, r in enumerate(qidx):
             ctx.check(lib.ola_dev_gather_rows(ctx.handle, d_lde, L, NCOLS, int(r), 1, rows_host.data_ptr() + k * NCOLS * 8))
 

@@ -106,6 +106,14 @@ int ola_hash_rows(ola_ctx* ctx, const uint64_t* rows, uint64_t* digests, int on_
 int ola_merkle_rows(ola_ctx* ctx, const uint64_t* rows, int on_device, size_t nrows, size_t ncols, uint32_t cap_height,
                     uint64_t* cap_out_host, uint64_t* nodes_out_host);
 
+/* PolynomialBatch::from_values / from_coeffs up to and including `lde_values` (fri/oracle.rs:45-60, :101-129), i.e. the
+ * commitment without its Merkle tree: cols ([ncols][n], host or device) -> coefficients [ncols][n] and the leaf-order LDE
+ * [ncols][n << rate_bits] (shift 7) in CALLER-OWNED DEVICE buffers (ola_dev_alloc).  Host input is uploaded in column
+ * chunks on a second stream, each chunk's iNTT + LDE overlapping the next chunk's copy.  With on_device != 0 and
+ * cols == coeffs_out_dev the values are transformed in place (PolynomialValues::ifft consumes its input). */
+int ola_lde_batch(ola_ctx* ctx, const uint64_t* cols, int on_device, size_t ncols, uint32_t log_n, int is_coeffs, uint32_t rate_bits,
+                  uint64_t* coeffs_out_dev, uint64_t* lde_out_dev);
+
 /* ---- PolynomialBatch (plonky2/plonky2/src/fri/oracle.rs:31-38) ---- */
 /* PolynomialBatch::from_values (oracle.rs:45-64; is_coeffs == 0) / from_coeffs (oracle.rs:66-99; is_coeffs != 0)
  * with blinding = false: iNTT -> coset LDE (shift 7, blowup 2^rate_bits) -> Poseidon Merkle tree.

@@ -61,6 +61,7 @@ SIGNATURES = {
     "ola_poseidon_permute": (_int, [_vp, _vp, _int, _sz]),
     "ola_hash_rows": (_int, [_vp, _vp, _vp, _int, _sz, _sz]),
     "ola_merkle_rows": (_int, [_vp, _vp, _int, _sz, _sz, _u32, _vp, _vp]),
+    "ola_lde_batch": (_int, [_vp, _vp, _int, _sz, _u32, _int, _u32, _vp, _vp]),
     "ola_commit": (_int, [_vp, _vp, _int, _sz, _u32, _int, _u32, _u32, ctypes.POINTER(_vp), _vp]),
     "ola_commit_shard": (_int, [_vp, _vp, _int, _sz, _u32, _int, _u32, _u32, _u32, _u32, ctypes.POINTER(_vp), _vp]),
     "ola_prove": (_int, [_vp, ctypes.POINTER(_int), _u32, ctypes.POINTER(_vp), _int, ctypes.POINTER(_u32), _vp, _int, _vp, _sz,

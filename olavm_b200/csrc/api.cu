@@ -125,6 +125,14 @@ void ola_gpu_destroy(ola_ctx* ctx) {
     ola::ntt::free_twiddles(ctx);
     ola::set_alloc_stream(ctx->stream);
     if (ctx->scratch) ola::dev_free(ctx->scratch);
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        for (int i = 0; i < 2; ++i) {
+            if (ctx->ev_ready[i]) cudaEventDestroy(ctx->ev_ready[i]);
+            if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]);
+        }
+        cudaStreamDestroy(ctx->copy_stream);
+    }
     if (ctx->stream) {
         cudaStreamSynchronize(ctx->stream);
         cudaMemPool_t pool;
@@ -284,6 +292,12 @@ int ola_coset_lde(ola_ctx* ctx, const uint64_t* coeffs, uint64_t* out, int on_de
         else if (d_work)
             OLA_CUDA(cudaStreamSynchronize(ctx->stream));
     });
+}
+
+int ola_lde_batch(ola_ctx* ctx, const uint64_t* cols, int on_device, size_t ncols, uint32_t log_n, int is_coeffs, uint32_t rate_bits,
+                  uint64_t* coeffs_out_dev, uint64_t* lde_out_dev) {
+    if (!ctx || !cols || !coeffs_out_dev || !lde_out_dev) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] { ola::lde_batch(ctx, cols, on_device != 0, ncols, log_n, is_coeffs != 0, rate_bits, coeffs_out_dev, lde_out_dev); });
 }
 
 int ola_coset_intt(ola_ctx* ctx, uint64_t* data, int on_device, size_t ncols, uint32_t log_n, uint64_t shift) {

@@ -95,29 +95,128 @@ void gather_rows(ola_ctx* ctx, const uint64_t* d_cols, size_t col_stride, size_t
     OLA_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
-// coset LDE of b->d_coeffs (shift 7, blowup 2^rate_bits, cosets [coset_first, +coset_count)) straight into leaf order
-// (oracle.rs:101-129 + :84-85), then MerkleTree::new_v2: leaf digests and the level reduction down to the cap
-static void finish_commit(ola_ctx* ctx, ola_batch* b, int coset_first, int coset_count) {
+// coset LDE of coefficient columns [c0, c0 + cnt) of b (shift 7, blowup 2^rate_bits, cosets [coset_first, +coset_count))
+// straight into leaf order (oracle.rs:101-129 + :84-85)
+static void lde_columns(ola_ctx* ctx, ola_batch* b, size_t c0, size_t cnt, int coset_first, int coset_count) {
     const size_t n = (size_t)1 << b->log_n, L = n << b->shard_bits;
-    {
-        ntt::FwdDesc d;
-        d.src = b->d_coeffs;
-        d.src_col_stride = n;
-        d.dst = b->d_lde;
-        d.dst_col_stride = L;
-        d.dst_coset_stride = n;
-        d.ncols = b->ncols;
-        d.log_n = (int)b->log_n;
-        d.coset_bits = (int)b->rate_bits;
-        d.coset_first = coset_first;
-        d.coset_count = coset_count;
-        d.shift = gl::GEN;
-        d.tag_strided = "lde_strided";
-        d.tag_contig = "lde_contig";
-        ntt::forward(ctx, d);
-    }
+    ntt::FwdDesc d;
+    d.src = b->d_coeffs + c0 * n;
+    d.src_col_stride = n;
+    d.dst = b->d_lde + c0 * L;
+    d.dst_col_stride = L;
+    d.dst_coset_stride = n;
+    d.ncols = cnt;
+    d.log_n = (int)b->log_n;
+    d.coset_bits = (int)b->rate_bits;
+    d.coset_first = coset_first;
+    d.coset_count = coset_count;
+    d.shift = gl::GEN;
+    d.tag_strided = "lde_strided";
+    d.tag_contig = "lde_contig";
+    ntt::forward(ctx, d);
+}
+// MerkleTree::new_v2 over the LDE: leaf digests and the level reduction down to the cap
+static void hash_commit(ola_ctx* ctx, ola_batch* b) {
+    const size_t n = (size_t)1 << b->log_n, L = n << b->shard_bits;
     poseidon::hash_rows_colmajor(ctx, b->d_lde, L, L, b->ncols, b->d_nodes + 4 * L);
     poseidon::merkle_levels(ctx, b->d_nodes, L, (size_t)1 << b->local_cap_height());
+}
+static void finish_commit(ola_ctx* ctx, ola_batch* b, int coset_first, int coset_count) {
+    lde_columns(ctx, b, 0, b->ncols, coset_first, coset_count);
+    hash_commit(ctx, b);
+}
+
+// values on H (natural) -> coefficients (natural): forward network with inverse roots, x 1/n
+// (PolynomialValues::ifft, polynomial/mod.rs:60-65).  `work` is clobbered (it may be src).
+static void intt_columns(ola_ctx* ctx, const uint64_t* src, uint64_t* work, uint64_t* dst, size_t ncols, uint32_t log_n) {
+    const size_t n = (size_t)1 << log_n;
+    ntt::FwdDesc d;
+    d.src = src;
+    d.src_col_stride = n;
+    d.work = work;
+    d.work_col_stride = n;
+    d.dst = dst;
+    d.dst_col_stride = n;
+    d.ncols = ncols;
+    d.log_n = (int)log_n;
+    d.inverse_roots = true;
+    d.natural_output = true;
+    d.apply_scale = true;
+    d.scale = gl::inv(((uint64_t)1 << log_n) % gl::P);
+    d.tag_strided = "intt_strided";
+    d.tag_contig = "intt_contig";
+    ntt::forward(ctx, d);
+}
+
+// Host columns -> coefficient columns in HBM, chunk by chunk through two staging buffers: the H2D copy of chunk k+1 (on
+// the context's copy stream, one PCIe direction) overlaps the transforms of chunk k (context stream).  after_chunk(c0,
+// cnt) is called (work enqueued on the context stream) once columns [c0, c0 + cnt) of d_coeffs hold coefficients.
+template <typename F>
+static void ingest_host_columns(ola_ctx* ctx, const uint64_t* h_cols, size_t ncols, uint32_t log_n, bool is_coeffs, uint64_t* d_coeffs,
+                                F&& after_chunk) {
+    const size_t n = (size_t)1 << log_n;
+    // ~64 MB chunks, at least four of them when the batch is big enough to be worth pipelining
+    size_t cc = std::max<size_t>(1, ((size_t)64 << 20) / (n * 8));
+    if (ncols * n * 8 >= ((size_t)32 << 20)) cc = std::min(cc, std::max<size_t>(1, (ncols + 3) / 4));
+    cc = std::min(cc, ncols);
+    ensure_copy_stream(ctx);
+    uint64_t* stage = nullptr;
+    dev_alloc(&stage, 2 * cc * n);
+    try {
+        // the staging buffers exist (in stream order) once this event has fired; earlier work of the copy stream is done
+        OLA_CUDA(cudaEventRecord(ctx->ev_free[0], ctx->stream));
+        OLA_CUDA(cudaEventRecord(ctx->ev_free[1], ctx->stream));
+        size_t k = 0;
+        for (size_t c0 = 0; c0 < ncols; c0 += cc, ++k) {
+            const size_t cnt = std::min(cc, ncols - c0);
+            const int bsel = (int)(k & 1);
+            uint64_t* sb = stage + (size_t)bsel * cc * n;
+            OLA_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[bsel], 0));
+            OLA_CUDA(cudaMemcpyAsync(sb, h_cols + c0 * n, cnt * n * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+            OLA_CUDA(cudaEventRecord(ctx->ev_ready[bsel], ctx->copy_stream));
+            OLA_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_ready[bsel], 0));
+            if (is_coeffs)
+                canon_copy(ctx, d_coeffs + c0 * n, sb, cnt * n);
+            else
+                intt_columns(ctx, sb, sb, d_coeffs + c0 * n, cnt, log_n);
+            OLA_CUDA(cudaEventRecord(ctx->ev_free[bsel], ctx->stream));
+            after_chunk(c0, cnt);
+        }
+    } catch (...) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->stream);
+        dev_free(stage);
+        throw;
+    }
+    dev_free(stage);  // stream-ordered after the last transform that reads it
+}
+
+void lde_batch(ola_ctx* ctx, const uint64_t* cols, bool on_device, size_t ncols, uint32_t log_n, bool is_coeffs, uint32_t rate_bits,
+               uint64_t* d_coeffs, uint64_t* d_lde) {
+    OLA_CHECK(cols != nullptr && ncols > 0, OLA_ERR_INVALID_ARG, "lde_batch: empty batch");
+    OLA_CHECK(log_n + rate_bits <= 32, OLA_ERR_INVALID_ARG, "lde_batch: LDE size exceeds the field's two-adicity (2^32)");
+    OLA_CHECK((1u << rate_bits) <= (unsigned)ntt::MAX_COSETS, OLA_ERR_INVALID_ARG, "lde_batch: rate_bits too large");
+    const size_t n = (size_t)1 << log_n;
+    ola_batch view;  // borrowed buffers, never released
+    view.ncols = ncols;
+    view.log_n = log_n;
+    view.rate_bits = rate_bits;
+    view.shard_bits = rate_bits;
+    view.d_coeffs = d_coeffs;
+    view.d_lde = d_lde;
+    if (!on_device) {
+        ingest_host_columns(ctx, cols, ncols, log_n, is_coeffs, d_coeffs, [&](size_t c0, size_t cnt) { lde_columns(ctx, &view, c0, cnt, 0, -1); });
+        return;
+    }
+    if (is_coeffs) {
+        canon_copy(ctx, d_coeffs, cols, ncols * n);
+    } else {
+        // in place when the caller passes its own value buffer as d_coeffs (PolynomialValues::ifft consumes its input)
+        const bool multipass = ntt::plan_passes((int)log_n).size() > 1;
+        uint64_t* work = (cols == d_coeffs) ? (multipass ? ctx_scratch(ctx, ncols * n) : nullptr) : d_lde;
+        intt_columns(ctx, cols, work, d_coeffs, ncols, log_n);
+    }
+    lde_columns(ctx, &view, 0, ncols, 0, -1);
 }
 
 ola_batch* batch_commit(ola_ctx* ctx, const uint64_t* cols, bool on_device, size_t ncols, uint32_t log_n, bool is_coeffs,
@@ -151,49 +250,27 @@ ola_batch* batch_commit(ola_ctx* ctx, const uint64_t* cols, bool on_device, size
     dev_alloc(&b->d_lde, ncols * L);
     dev_alloc(&b->d_nodes, 2 * L * 4);
 
-    // stage the input in the (still unused) LDE buffer, then transform into d_coeffs
-    uint64_t* stage = b->d_lde;
+    if (!on_device) {
+        // pipelined upload: each chunk's LDE follows its coefficients while the next chunk is still in flight
+        ola_batch* bp = b.get();
+        ingest_host_columns(ctx, cols, ncols, log_n, is_coeffs, b->d_coeffs,
+                            [&](size_t c0, size_t cnt) { lde_columns(ctx, bp, c0, cnt, coset_first, coset_count); });
+        hash_commit(ctx, bp);
+        return b.release();
+    }
     if (is_coeffs) {
-        if (on_device) {
-            canon_copy(ctx, b->d_coeffs, cols, ncols * n);
-        } else {
-            OLA_CUDA(cudaMemcpyAsync(stage, cols, ncols * n * 8, cudaMemcpyHostToDevice, ctx->stream));
-            canon_copy(ctx, b->d_coeffs, stage, ncols * n);
-        }
+        canon_copy(ctx, b->d_coeffs, cols, ncols * n);
     } else {
-        const uint64_t* src = cols;
-        if (!on_device) {
-            OLA_CUDA(cudaMemcpyAsync(stage, cols, ncols * n * 8, cudaMemcpyHostToDevice, ctx->stream));
-            src = stage;
-        }
-        // values on H (natural) -> coefficients (natural): forward network with inverse roots, x 1/n
-        // (PolynomialValues::ifft, polynomial/mod.rs:60-65)
-        ntt::FwdDesc d;
-        d.src = src;
-        d.src_col_stride = n;
-        // never clobber a caller-owned device buffer: a second scratch region when the input is resident
+        // never clobber a caller-owned device buffer: the (still unused) LDE buffer is the work area when it is big
+        // enough, a second scratch region otherwise
         uint64_t* tmp_work = nullptr;
-        if (!on_device) {
-            d.work = stage;
-        } else if (shard_bits >= 1) {
-            d.work = stage;
-        } else {
+        uint64_t* work = b->d_lde;
+        if (shard_bits < 1) {
             dev_alloc(&tmp_work, ncols * n);
-            d.work = tmp_work;
+            work = tmp_work;
         }
-        d.work_col_stride = n;
-        d.dst = b->d_coeffs;
-        d.dst_col_stride = n;
-        d.ncols = ncols;
-        d.log_n = (int)log_n;
-        d.inverse_roots = true;
-        d.natural_output = true;
-        d.apply_scale = true;
-        d.scale = gl::inv(((uint64_t)1 << log_n) % gl::P);
-        d.tag_strided = "intt_strided";
-        d.tag_contig = "intt_contig";
         try {
-            ntt::forward(ctx, d);
+            intt_columns(ctx, cols, work, b->d_coeffs, ncols, log_n);
         } catch (...) {
             if (tmp_work) ola::dev_free(tmp_work);
             throw;

@@ -29,6 +29,11 @@ void gather_rows(ola_ctx* ctx, const uint64_t* d_cols, size_t col_stride, size_t
                  uint64_t* out_host);
 ola_batch* batch_commit(ola_ctx* ctx, const uint64_t* cols, bool on_device, size_t ncols, uint32_t log_n, bool is_coeffs,
                         uint32_t rate_bits, uint32_t cap_height, int coset_first = 0, int coset_count = -1);
+// PolynomialBatch::from_values / from_coeffs up to and including lde_values (oracle.rs:45-60, :101-129): coefficients and
+// the leaf-order LDE into caller-owned device buffers, no Merkle tree.  Host input is uploaded in column chunks whose
+// transforms overlap the next chunk's copy.
+void lde_batch(ola_ctx* ctx, const uint64_t* cols, bool on_device, size_t ncols, uint32_t log_n, bool is_coeffs, uint32_t rate_bits,
+               uint64_t* d_coeffs, uint64_t* d_lde);
 // multi-GPU prover: column-sharded iNTT + all-gather of coefficients, coset-sharded LDE / hashing / tree (device input)
 ola_batch* batch_commit_dist(ola_ctx* ctx, const uint64_t* d_cols, size_t ncols, uint32_t log_n, bool is_coeffs, uint32_t rate_bits,
                              uint32_t cap_height);

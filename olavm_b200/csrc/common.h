@@ -59,6 +59,9 @@ struct ola_ctx {
     std::map<std::string, std::pair<double, uint64_t>> prof_totals;  // name -> (ms, launches)
     int device = 0;
     cudaStream_t stream = nullptr;
+    // second stream + events for uploads that overlap the transforms of the previous chunk (batch.cu ingest_host_columns)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     int sm_count = 148;
     ola::Twiddles tw;
     std::string last_error;
@@ -94,6 +97,17 @@ struct Launch {
     }
 };
 inline void count_launch(ola_ctx* ctx, uint64_t n = 1) { ctx->kernel_launches += n; }
+// the context's copy stream and its double-buffering events, created on first use
+inline void ensure_copy_stream(ola_ctx* ctx) {
+    if (ctx->copy_stream) return;
+    cudaStream_t s = nullptr;
+    OLA_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        OLA_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready[i], cudaEventDisableTiming));
+        OLA_CUDA(cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming));
+    }
+    ctx->copy_stream = s;
+}
 inline void comm_allgather(ola_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank) {
     OLA_CHECK(ctx->comm_allgather != nullptr, OLA_ERR_INTERNAL, "no communicator");
     OLA_CHECK(ctx->comm_allgather(ctx->comm_user, send, recv, bytes_per_rank, (void*)ctx->stream) == 0, OLA_ERR_INTERNAL, "all-gather callback failed");

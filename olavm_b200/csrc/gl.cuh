@@ -65,77 +65,89 @@ GL_HD void mul_wide(uint64_t a, uint64_t b, uint64_t& lo, uint64_t& hi) {
 #endif
 }
 
-// ---- device fast path: 32-bit-limb PTX with carry chains ------------------------------------------
+// ---- device fast path ------------------------------------------------------------------------------
 // "lazy" values are arbitrary u64 representatives in [0, 2^64); "canonical" ones are < p.
-//   mul_lazy(any, any)          -> lazy        21 SASS instructions (4 IMAD.WIDE-class + carry chain)
-//   canon(lazy)                 -> canonical    5
-//   add_lc(lazy, canonical)     -> lazy         5      (a + v < 2^64 + p  =>  a single +EPS correction suffices)
+//   mul_lazy(any, any)          -> lazy        15 SASS instructions (7 for the 128-bit product, 8 to reduce)
+//   canon_fast(lazy)            -> canonical    4
+//   add_lc(lazy, canonical)     -> lazy         4      (a + v < 2^64 + p  =>  a single +EPS correction suffices)
 //   sub_lc(lazy, canonical)     -> lazy         5
 //   mad_lazy(any, any, any)     -> lazy        a*b + c reduced once (Field::multiply_accumulate,
 //                                              goldilocks_field.rs:110-113)
+// How the counts are reached (checked with cuobjdump -sass, tools/microbench/prims.cu): the 128-bit product is left to
+// the compiler (4 IMAD.WIDE chained through their carry predicates); every "+ carry * EPS" correction is ONE
+// IMAD.WIDE.U32 (carry * 0xffffffff + t) fed by the carry materialised with a single addc; x2 * EPS + (x1:x0) is an
+// IADD3 / IMAD.HI pair with carry-out.  The conditional corrections therefore cost 2 instructions instead of the 3-4 of
+// a mask-and-add sequence.  Never feed an add-chain carry into subc (ptxas keeps the hardware not-borrow convention
+// across the mix); add chains end in addc, sub chains in subc.
 // On the host the same names return canonical values (a valid lazy representative).
 #if defined(__CUDACC__)
 __device__ __forceinline__ void mul_limbs(uint64_t a, uint64_t b, uint32_t& x0, uint32_t& x1, uint32_t& x2, uint32_t& x3) {
-    uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
-    asm("{\n\t"
-        ".reg .u32 r1, r2, r3;\n\t"
-        "mul.lo.u32      %0, %4, %6;\n\t"
-        "mul.hi.u32      r1, %4, %6;\n\t"
-        "mad.lo.cc.u32   r1, %4, %7, r1;\n\t"
-        "madc.hi.u32     r2, %4, %7, 0;\n\t"
-        "mad.lo.cc.u32   %1, %5, %6, r1;\n\t"
-        "madc.hi.cc.u32  r2, %5, %6, r2;\n\t"
-        "addc.u32        r3, 0, 0;\n\t"
-        "mad.lo.cc.u32   %2, %5, %7, r2;\n\t"
-        "madc.hi.u32     %3, %5, %7, r3;\n\t"
-        "}"
-        : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
-        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
-}
-// x = x0 + x1*2^32 + x2*2^64 + x3*2^96  ==  (x1:x0) - x3 + x2*(2^32 - 1)   (mod p)
-__device__ __forceinline__ uint64_t reduce_limbs(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3) {
-    uint32_t r0, r1;
-    asm("{\n\t"
-        ".reg .u32 t0, t1, m, u0, u1;\n\t"
-        "sub.cc.u32  t0, %2, %5;\n\t"   // t = (x1:x0) - x3
-        "subc.cc.u32 t1, %3, 0;\n\t"
-        "subc.u32    m, 0, 0;\n\t"      // m = borrow ? 0xffffffff : 0
-        "sub.cc.u32  t0, t0, m;\n\t"    // t -= borrow * EPS   (cannot underflow again)
-        "subc.u32    t1, t1, 0;\n\t"
-        "sub.cc.u32  u0, 0, %4;\n\t"    // u = x2 * EPS = (x2 << 32) - x2
-        "subc.u32    u1, %4, 0;\n\t"
-        "add.cc.u32  t0, t0, u0;\n\t"   // r = t + u
-        "addc.cc.u32 t1, t1, u1;\n\t"
-        "addc.u32    m, 0, 0;\n\t"      // m = carry (0/1).  NB: never feed an add-chain carry into subc:
-        "neg.s32     m, m;\n\t"         // ptxas keeps the hardware (not-borrow) convention across the mix.
-        "add.cc.u32  %0, t0, m;\n\t"    // r += carry * EPS    (cannot overflow again)
-        "addc.u32    %1, t1, 0;\n\t"
-        "}"
-        : "=r"(r0), "=r"(r1)
-        : "r"(x0), "r"(x1), "r"(x2), "r"(x3));
-    return ((uint64_t)r1 << 32) | r0;
+    unsigned __int128 p = (unsigned __int128)a * b;
+    uint64_t lo = (uint64_t)p, hi = (uint64_t)(p >> 64);
+    x0 = (uint32_t)lo;
+    x1 = (uint32_t)(lo >> 32);
+    x2 = (uint32_t)hi;
+    x3 = (uint32_t)(hi >> 32);
 }
 #endif
 
 GL_HD uint64_t canon_fast(uint64_t a) {
 #if defined(__CUDA_ARCH__)
-    uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), r0, r1;
+    uint32_t c;
     asm("{\n\t"
-        ".reg .u32 s0, s1, m;\n\t"
-        "add.cc.u32  s0, %2, 0xffffffff;\n\t"  // a + EPS wraps  <=>  a >= p
-        "addc.cc.u32 s1, %3, 0;\n\t"
-        "addc.u32    m, 0, 0;\n\t"
-        "neg.s32     m, m;\n\t"
-        "add.cc.u32  %0, %2, m;\n\t"           // a - p == a + EPS (mod 2^64)
-        "addc.u32    %1, %3, 0;\n\t"
+        ".reg .u32 a0, a1, s0, s1;\n\t"
+        "mov.b64     {a0, a1}, %1;\n\t"
+        "add.cc.u32  s0, a0, 0xffffffff;\n\t"  // a + EPS wraps  <=>  a >= p
+        "addc.cc.u32 s1, a1, 0;\n\t"
+        "addc.u32    %0, 0, 0;\n\t"
         "}"
-        : "=r"(r0), "=r"(r1)
-        : "r"(a0), "r"(a1));
-    return ((uint64_t)r1 << 32) | r0;
+        : "=r"(c)
+        : "l"(a));
+    return a + (uint64_t)c * 0xFFFFFFFFu;  // a - p == a + EPS (mod 2^64)
 #else
     return canon(a);
 #endif
 }
+GL_HD uint64_t add_lc(uint64_t a, uint64_t v) {
+#if defined(__CUDA_ARCH__)
+    uint64_t t;
+    uint32_t c;
+    asm("add.cc.u64  %0, %2, %3;\n\t"
+        "addc.u32    %1, 0, 0;"
+        : "=l"(t), "=r"(c)
+        : "l"(a), "l"(v));
+    return t + (uint64_t)c * 0xFFFFFFFFu;  // t = a + v - 2^64 < v < p: t + EPS cannot wrap again
+#else
+    return add(canon(a), v);
+#endif
+}
+GL_HD uint64_t sub_lc(uint64_t a, uint64_t v) {
+#if defined(__CUDA_ARCH__)
+    uint64_t t;
+    uint32_t m;
+    asm("sub.cc.u64  %0, %2, %3;\n\t"
+        "subc.u32    %1, 0, 0;"  // m = borrow ? 0xffffffff : 0
+        : "=l"(t), "=r"(m)
+        : "l"(a), "l"(v));
+    return t - (uint64_t)m;  // t = a - v + 2^64 > EPS: t - EPS cannot underflow again
+#else
+    return sub(canon(a), v);
+#endif
+}
+#if defined(__CUDACC__)
+// x = x0 + x1*2^32 + x2*2^64 + x3*2^96  ==  (x1:x0) + x2*(2^32 - 1) - x3   (mod p)
+__device__ __forceinline__ uint64_t reduce_limbs(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3) {
+    uint32_t t0, t1, c;
+    asm("mad.lo.cc.u32   %0, %5, 0xffffffff, %3;\n\t"  // (t1:t0) = x2 * EPS + (x1:x0), carry out
+        "madc.hi.cc.u32  %1, %5, 0xffffffff, %4;\n\t"
+        "addc.u32        %2, 0, 0;"
+        : "=r"(t0), "=r"(t1), "=r"(c)
+        : "r"(x0), "r"(x1), "r"(x2));
+    // wrapped value < 2^64 - 2^33, so + EPS cannot wrap again
+    uint64_t t = (((uint64_t)t1 << 32) | t0) + (uint64_t)c * 0xFFFFFFFFu;
+    return sub_lc(t, (uint64_t)x3);
+}
+#endif
 GL_HD uint64_t mul_lazy(uint64_t a, uint64_t b) {
 #if defined(__CUDA_ARCH__)
     uint32_t x0, x1, x2, x3;
@@ -149,15 +161,9 @@ GL_HD uint64_t mul_lazy(uint64_t a, uint64_t b) {
 }
 GL_HD uint64_t mad_lazy(uint64_t a, uint64_t b, uint64_t c) {
 #if defined(__CUDA_ARCH__)
-    uint32_t x0, x1, x2, x3;
-    mul_limbs(a, b, x0, x1, x2, x3);
-    asm("add.cc.u32 %0, %0, %4;\n\t"
-        "addc.cc.u32 %1, %1, %5;\n\t"
-        "addc.cc.u32 %2, %2, 0;\n\t"
-        "addc.u32 %3, %3, 0;"
-        : "+r"(x0), "+r"(x1), "+r"(x2), "+r"(x3)
-        : "r"((uint32_t)c), "r"((uint32_t)(c >> 32)));
-    return reduce_limbs(x0, x1, x2, x3);
+    unsigned __int128 p = (unsigned __int128)a * b + c;  // < 2^128: (2^64-1)^2 + 2^64 - 1
+    uint64_t lo = (uint64_t)p, hi = (uint64_t)(p >> 64);
+    return reduce_limbs((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
 #else
     uint64_t lo, hi;
     mul_wide(a, b, lo, hi);
@@ -169,43 +175,6 @@ GL_HD uint64_t reduce128_lazy(uint64_t lo, uint64_t hi) {
     return reduce_limbs((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
 #else
     return reduce128(lo, hi);
-#endif
-}
-GL_HD uint64_t add_lc(uint64_t a, uint64_t v) {
-#if defined(__CUDA_ARCH__)
-    uint32_t r0, r1;
-    asm("{\n\t"
-        ".reg .u32 t0, t1, m;\n\t"
-        "add.cc.u32  t0, %2, %4;\n\t"
-        "addc.cc.u32 t1, %3, %5;\n\t"
-        "addc.u32    m, 0, 0;\n\t"
-        "neg.s32     m, m;\n\t"
-        "add.cc.u32  %0, t0, m;\n\t"
-        "addc.u32    %1, t1, 0;\n\t"
-        "}"
-        : "=r"(r0), "=r"(r1)
-        : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)v), "r"((uint32_t)(v >> 32)));
-    return ((uint64_t)r1 << 32) | r0;
-#else
-    return add(canon(a), v);
-#endif
-}
-GL_HD uint64_t sub_lc(uint64_t a, uint64_t v) {
-#if defined(__CUDA_ARCH__)
-    uint32_t r0, r1;
-    asm("{\n\t"
-        ".reg .u32 t0, t1, m;\n\t"
-        "sub.cc.u32  t0, %2, %4;\n\t"
-        "subc.cc.u32 t1, %3, %5;\n\t"
-        "subc.u32    m, 0, 0;\n\t"
-        "sub.cc.u32  %0, t0, m;\n\t"
-        "subc.u32    %1, t1, 0;\n\t"
-        "}"
-        : "=r"(r0), "=r"(r1)
-        : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)v), "r"((uint32_t)(v >> 32)));
-    return ((uint64_t)r1 << 32) | r0;
-#else
-    return sub(canon(a), v);
 #endif
 }
 GL_HD uint64_t mul(uint64_t a, uint64_t b) { return canon_fast(mul_lazy(a, b)); }

@@ -50,6 +50,9 @@ struct PassArgs {
     size_t out_mul;       // bitrev_store: address = natural_index*out_mul + bitrev(coset)  (interleaved cosets)
     int coset_bits;
     int apply_scale;
+    int coset_major;      // tile_strided: grid is (cosets, tiles, columns) instead of (tiles, columns, cosets)
+    int lazy_out;         // tile kernels: leave the outputs un-canonicalised (an intermediate pass; every pass accepts lazy input)
+    size_t ncols;         // tile_contig: columns in the batch (the last column group may be partial)
     uint64_t scale;
     uint64_t s_last[MAX_COSETS];  // per coset: (shift_i)^(2^(M-l)), or its inverse for the GS network
 };
@@ -435,6 +438,12 @@ __global__ void __launch_bounds__(1024) pass_contig_r8(const PassArgs a) {
     }
 }
 
+}  // namespace ntt
+}  // namespace ola
+#include "ntt_tile.cuh"
+namespace ola {
+namespace ntt {
+
 // out[j] *= base * step^j   (coset un-shift after a natural-order inverse transform)
 __global__ void scale_powers_kernel(uint64_t* data, size_t col_stride, size_t n, uint64_t base, uint64_t step) {
     const int RUN = 16;
@@ -472,6 +481,29 @@ static void opt_in_shared_memory(int device) {
     OLA_CUDA(cudaFuncSetAttribute(pass_strided<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     OLA_CUDA(cudaFuncSetAttribute(pass_contig<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     OLA_CUDA(cudaFuncSetAttribute(pass_contig<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+#define OLA_TILE_OPTIN(LL, CC)                                                                                                  \
+    OLA_CUDA(cudaFuncSetAttribute(tile::tile_strided<LL, CC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin)); \
+    OLA_CUDA(cudaFuncSetAttribute(tile::tile_strided<LL, CC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));  \
+    OLA_CUDA(cudaFuncSetAttribute(tile::tile_contig<LL, CC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));  \
+    OLA_CUDA(cudaFuncSetAttribute(tile::tile_contig<LL, CC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+#define OLA_TILE_OPTIN2(LL)                                                                                                   \
+    OLA_CUDA(cudaFuncSetAttribute(tile::tile_contig<LL, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin)); \
+    OLA_CUDA(cudaFuncSetAttribute(tile::tile_contig<LL, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    OLA_TILE_OPTIN2(6)
+    OLA_TILE_OPTIN2(7)
+    OLA_TILE_OPTIN2(8)
+    OLA_TILE_OPTIN2(9)
+    OLA_TILE_OPTIN2(10)
+    OLA_TILE_OPTIN2(11)
+#undef OLA_TILE_OPTIN2
+    OLA_TILE_OPTIN(6, 8)
+    OLA_TILE_OPTIN(7, 8)
+    OLA_TILE_OPTIN(8, 8)
+    OLA_TILE_OPTIN(9, 8)
+    OLA_TILE_OPTIN(10, 8)
+    OLA_TILE_OPTIN(11, 4)
+    OLA_TILE_OPTIN(10, 4)
+#undef OLA_TILE_OPTIN
 }
 
 void init_twiddles(ola_ctx* ctx) {
@@ -523,6 +555,27 @@ static int tune_threads() {
     }();
     return v;
 }
+static bool tune_tile() {  // OLA_NTT_TILE=0 falls back to the generic passes (A/B measurements)
+    static bool v = [] {
+        const char* e = getenv("OLA_NTT_TILE");
+        return !(e && atoi(e) == 0);
+    }();
+    return v;
+}
+static bool tune_coset_major() {
+    static bool v = [] {
+        const char* e = getenv("OLA_NTT_COSET_MAJOR");
+        return !(e && atoi(e) == 0);
+    }();
+    return v;
+}
+static bool tune_c4() {  // 4-lane tiles for 10-stage passes (more resident CTAs per SM, 32-byte segments)
+    static bool v = [] {
+        const char* e = getenv("OLA_NTT_C4");
+        return e && atoi(e) != 0;
+    }();
+    return v;
+}
 static int tune_gmax() {
     static int v = [] {
         const char* e = getenv("OLA_NTT_G");
@@ -537,7 +590,28 @@ static void launch_strided(ola_ctx* ctx, const PassArgs& a, size_t ncols, int nc
     const int R = 1 << a.l;
     size_t tiles = ((size_t)1 << a.L) / ((size_t)R * TILE_T);
     dim3 grid((unsigned)tiles, (unsigned)ncols, (unsigned)ncosets);
-    if (a.l >= 6) {
+    if (a.l >= 6 && a.l <= 11 && tune_tile()) {
+        Launch lz(ctx, name);
+        PassArgs b = a;
+#define OLA_TILE_S(KEY, LL, CC)                                                                                    \
+    case KEY: {                                                                                                    \
+        const size_t ntiles = ((size_t)1 << a.L) / ((size_t)R * CC);                                               \
+        b.coset_major = (tune_coset_major() && ntiles <= 65535 && ncols <= 65535) ? 1 : 0;                          \
+        const dim3 g = b.coset_major ? dim3((unsigned)ncosets, (unsigned)ntiles, (unsigned)ncols)                  \
+                                     : dim3((unsigned)ntiles, (unsigned)ncols, (unsigned)ncosets);                 \
+        tile::tile_strided<LL, CC, GS><<<g, tile::Geo<LL, CC>::NT, tile::Geo<LL, CC>::SMEM, ctx->stream>>>(b);     \
+    } break;
+        switch (a.l + ((a.l == 10 && tune_c4()) ? 100 : 0)) {
+            OLA_TILE_S(6, 6, 8)
+            OLA_TILE_S(7, 7, 8)
+            OLA_TILE_S(8, 8, 8)
+            OLA_TILE_S(9, 9, 8)
+            OLA_TILE_S(10, 10, 8)
+            OLA_TILE_S(11, 11, 4)
+            OLA_TILE_S(110, 10, 4)
+        }
+#undef OLA_TILE_S
+    } else if (a.l >= 6) {
         const size_t padded = (size_t)R * TILE_T + ((size_t)R * TILE_T >> 4) + 1;
         size_t smem = ((size_t)R + 16 + padded) * sizeof(uint64_t);
         int threads = (int)std::min<size_t>((size_t)tune_threads(), (size_t)R);  // R items of 8 elements per round
@@ -557,7 +631,43 @@ static void launch_contig(ola_ctx* ctx, const PassArgs& a, size_t ncols, int nco
     const int R = 1 << a.l;
     size_t blocks = (((size_t)1 << a.L) >> a.l) / a.G;
     dim3 grid((unsigned)blocks, (unsigned)ncols, (unsigned)ncosets);
-    if (a.l >= 6) {
+    if (a.l >= 6 && a.l <= 11 && !a.bitrev_store && tune_tile()) {
+        Launch lz(ctx, name);
+        PassArgs b = a;
+        b.ncols = ncols;
+        const int key = a.l + (ncols <= 2 ? 100 : ((a.l == 10 && tune_c4()) ? 200 : 0));  // one or two columns (quotient, FRI): 2-lane tiles
+#define OLA_TILE_C(LL, CC)                                                                                         \
+    case LL:                                                                                                       \
+        tile::tile_contig<LL, CC, GS>                                                                              \
+            <<<dim3((unsigned)(((size_t)1 << a.L) >> LL), (unsigned)((ncols + CC - 1) / CC), (unsigned)ncosets),   \
+               tile::Geo<LL, CC>::NT, tile::Geo<LL, CC>::SMEM, ctx->stream>>>(b);                                  \
+        break;
+#define OLA_TILE_C2(LL)                                                                                   \
+    case 100 + LL:                                                                                        \
+        tile::tile_contig<LL, 2, GS><<<dim3((unsigned)(((size_t)1 << a.L) >> LL), 1, (unsigned)ncosets),  \
+                                       tile::Geo<LL, 2>::NT, tile::Geo<LL, 2>::SMEM, ctx->stream>>>(b);   \
+        break;
+        switch (key) {
+            OLA_TILE_C(6, 8)
+            OLA_TILE_C(7, 8)
+            OLA_TILE_C(8, 8)
+            OLA_TILE_C(9, 8)
+            OLA_TILE_C(10, 8)
+            OLA_TILE_C(11, 4)
+            case 210:
+                tile::tile_contig<10, 4, GS><<<dim3((unsigned)(((size_t)1 << a.L) >> 10), (unsigned)((ncols + 3) / 4), (unsigned)ncosets),
+                                               tile::Geo<10, 4>::NT, tile::Geo<10, 4>::SMEM, ctx->stream>>>(b);
+                break;
+            OLA_TILE_C2(6)
+            OLA_TILE_C2(7)
+            OLA_TILE_C2(8)
+            OLA_TILE_C2(9)
+            OLA_TILE_C2(10)
+            OLA_TILE_C2(11)
+        }
+#undef OLA_TILE_C2
+#undef OLA_TILE_C
+    } else if (a.l >= 6) {
         const size_t padded = (size_t)a.G * R + ((size_t)a.G * R >> 4) + 1;
         size_t smem = ((size_t)a.G * R + (size_t)a.G * 16 + padded) * sizeof(uint64_t);
         int threads = (int)std::min<size_t>((size_t)tune_threads(), std::max<size_t>(32, (size_t)R * a.G / 8));
@@ -611,6 +721,7 @@ void forward(ola_ctx* ctx, const FwdDesc& d) {
         a.M = M;
         a.l = plan[pi];
         a.apply_scale = (last && d.apply_scale) ? 1 : 0;
+        a.lazy_out = last ? 0 : 1;
         a.scale = d.scale;
         a.coset_bits = 0;
         a.out_mul = 1;
@@ -658,6 +769,7 @@ void inverse_from_leaf_order(ola_ctx* ctx, uint64_t* data, size_t col_stride, si
         a.M = Ms[k];
         a.l = plan[k];
         a.apply_scale = (k == 0) ? 1 : 0;
+        a.lazy_out = (k == 0) ? 0 : 1;
         a.scale = n_inv;
         a.out_mul = 1;
         a.s_last[0] = pow2k(shift_inv, a.M - a.l);

@@ -32,7 +32,7 @@ void init_constants() {
     up(c_init, &OLA_FAST_PARTIAL_ROUND_INITIAL_MATRIX[0][0], 11 * 11);
 }
 
-__global__ void __launch_bounds__(128) permute_kernel(uint64_t* states, size_t n) {
+__global__ void __launch_bounds__(128, 5) permute_kernel(uint64_t* states, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t s[12];
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(128, MINB) hash_rows_kernel(const uint64_t* __
 }
 
 // nodes[i] = two_to_one(nodes[2i], nodes[2i+1]) for i in [first, first + count)
-__global__ void __launch_bounds__(128) merkle_level_kernel(uint64_t* nodes, size_t first, size_t count) {
+__global__ void __launch_bounds__(128, 5) merkle_level_kernel(uint64_t* nodes, size_t first, size_t count) {
     size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= count) return;
     size_t i = first + k;

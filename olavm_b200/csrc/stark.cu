@@ -797,28 +797,66 @@ std::vector<uint8_t> prove_all(ola_ctx* ctx, const std::vector<int>& table_ids, 
     std::vector<std::unique_ptr<DevBuf>> d_vals(T);
     std::vector<std::unique_ptr<BatchHolder>> commits(T);
     Challenger ch;
-    for (size_t i = 0; i < T; ++i) {
-        const size_t n = (size_t)1 << log_ns[i], cnt = n * sys.tables[i].columns;
-        OLA_CHECK(log_ns[i] + Config::rate_bits <= 32, OLA_ERR_INVALID_ARG, "trace too long for the field's two-adicity");
-        if (ctx->world > 1 && !on_device) {
-            // every rank holds the same host trace: each uploads 1/world of the columns over its own PCIe link and one
-            // all-gather over NVLink replicates the table (padded to equal contributions)
-            const size_t cols = (size_t)sys.tables[i].columns, per = (cols + ctx->world - 1) / ctx->world;
-            const size_t lo = std::min(cols, (size_t)ctx->rank * per), hi = std::min(cols, lo + per);
-            d_vals[i].reset(new DevBuf(per * ctx->world * n));
-            DevBuf send(per * n);
-            if (hi - lo < per) OLA_CUDA(cudaMemsetAsync(send.p, 0, per * n * 8, ctx->stream));
-            if (hi > lo) OLA_CUDA(cudaMemcpyAsync(send.p, traces[i] + lo * n, (hi - lo) * n * 8, cudaMemcpyHostToDevice, ctx->stream));
-            canon_copy(ctx, send.p, send.p, per * n);
-            comm_allgather(ctx, send.p, d_vals[i]->p, per * n * 8);
-            OLA_CUDA(cudaStreamSynchronize(ctx->stream));
-        } else {
-            d_vals[i].reset(new DevBuf(cnt));
-            OLA_CUDA(cudaMemcpyAsync(d_vals[i]->p, traces[i], cnt * 8, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
-            canon_copy(ctx, d_vals[i]->p, d_vals[i]->p, cnt);  // the Z kernels read these values with canonical-input arithmetic
+    // single GPU, host traces: every table's upload is queued on the copy stream up front, so table i+1 crosses PCIe
+    // while table i is being committed (LDE + Poseidon) on the context stream
+    const bool prefetch = ctx->world == 1 && !on_device;
+    std::vector<cudaEvent_t> uploaded(T, nullptr);
+    struct EventGuard {
+        std::vector<cudaEvent_t>& v;
+        ~EventGuard() {
+            for (auto e : v)
+                if (e) cudaEventDestroy(e);
         }
-        commits[i].reset(new BatchHolder());
-        commits[i]->b = commit(ctx, d_vals[i]->p, sys.tables[i].columns, log_ns[i], false);
+    } event_guard{uploaded};
+    if (prefetch) {
+        ensure_copy_stream(ctx);
+        cudaEvent_t allocated;
+        OLA_CUDA(cudaEventCreateWithFlags(&allocated, cudaEventDisableTiming));
+        for (size_t i = 0; i < T; ++i) {
+            OLA_CHECK(log_ns[i] + Config::rate_bits <= 32, OLA_ERR_INVALID_ARG, "trace too long for the field's two-adicity");
+            d_vals[i].reset(new DevBuf(((size_t)1 << log_ns[i]) * sys.tables[i].columns));
+        }
+        cudaError_t e = cudaEventRecord(allocated, ctx->stream);  // the stream-ordered allocations above precede the copies
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, allocated, 0);
+        cudaEventDestroy(allocated);
+        OLA_CUDA(e);
+        for (size_t i = 0; i < T; ++i) {
+            const size_t cnt = ((size_t)1 << log_ns[i]) * sys.tables[i].columns;
+            OLA_CUDA(cudaMemcpyAsync(d_vals[i]->p, traces[i], cnt * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+            OLA_CUDA(cudaEventCreateWithFlags(&uploaded[i], cudaEventDisableTiming));
+            OLA_CUDA(cudaEventRecord(uploaded[i], ctx->copy_stream));
+        }
+    }
+    try {
+        for (size_t i = 0; i < T; ++i) {
+            const size_t n = (size_t)1 << log_ns[i], cnt = n * sys.tables[i].columns;
+            OLA_CHECK(log_ns[i] + Config::rate_bits <= 32, OLA_ERR_INVALID_ARG, "trace too long for the field's two-adicity");
+            if (ctx->world > 1 && !on_device) {
+                // every rank holds the same host trace: each uploads 1/world of the columns over its own PCIe link and one
+                // all-gather over NVLink replicates the table (padded to equal contributions)
+                const size_t cols = (size_t)sys.tables[i].columns, per = (cols + ctx->world - 1) / ctx->world;
+                const size_t lo = std::min(cols, (size_t)ctx->rank * per), hi = std::min(cols, lo + per);
+                d_vals[i].reset(new DevBuf(per * ctx->world * n));
+                DevBuf send(per * n);
+                if (hi - lo < per) OLA_CUDA(cudaMemsetAsync(send.p, 0, per * n * 8, ctx->stream));
+                if (hi > lo) OLA_CUDA(cudaMemcpyAsync(send.p, traces[i] + lo * n, (hi - lo) * n * 8, cudaMemcpyHostToDevice, ctx->stream));
+                canon_copy(ctx, send.p, send.p, per * n);
+                comm_allgather(ctx, send.p, d_vals[i]->p, per * n * 8);
+                OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+            } else if (prefetch) {
+                OLA_CUDA(cudaStreamWaitEvent(ctx->stream, uploaded[i], 0));
+                canon_copy(ctx, d_vals[i]->p, d_vals[i]->p, cnt);  // the Z kernels read these values with canonical-input arithmetic
+            } else {
+                d_vals[i].reset(new DevBuf(cnt));
+                OLA_CUDA(cudaMemcpyAsync(d_vals[i]->p, traces[i], cnt * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+                canon_copy(ctx, d_vals[i]->p, d_vals[i]->p, cnt);
+            }
+            commits[i].reset(new BatchHolder());
+            commits[i]->b = commit(ctx, d_vals[i]->p, sys.tables[i].columns, log_ns[i], false);
+        }
+    } catch (...) {
+        if (prefetch) cudaStreamSynchronize(ctx->copy_stream);  // no copy may outlive the buffers released by unwinding
+        throw;
     }
     for (size_t i = 0; i < T; ++i) ch.observe_cap(batch_cap(ctx, commits[i]->b));
     // cross_table_lookup_data: challenges, then Z instances per table in registry order

@@ -233,3 +233,48 @@ def test_commit_large_roundtrip(ctx, orc):
     for i in (0, 12345, L - 1):
         assert orc.merkle_verify(b.leaves(i, 1)[0], i, ref["cap"], b.prove(i))
     b.free()
+
+
+# ------------------------------------------------------------------ register-tiled passes (ntt_tile.cuh)
+@pytest.mark.parametrize("lg", [6, 7, 8, 9, 10, 11, 12, 13, 14, 16, 17, 18, 19, 20, 21, 22])
+@pytest.mark.parametrize("ncols", [5, 8])
+def test_tiled_lde_leaf_order_many_columns(ctx, orc, lg, ncols):
+    """Column groups of the tiled contiguous pass (full and partial groups of 8 / 4 lanes) at every pass split."""
+    if lg >= 20 and ncols == 8:
+        pytest.skip("covered by ncols=5 at this size")
+    n = 1 << lg
+    rb = 1 if lg >= 16 else 3
+    c = orc.rand_elems(7000 + lg, (ncols, n))
+    leaf = cfft.evaluate_poly_with_offset(ctx, c, 7, 1 << rb, natural_order=False)
+    perm = bitrev_perm(lg + rb)
+    for k in sorted({0, ncols // 2, ncols - 1}):
+        ref = orc.evaluate_poly_with_offset(c[k], 7, 1 << rb)
+        assert (leaf[k] == ref[perm]).all(), (lg, ncols, k)
+    assert (leaf < np.uint64(P)).all()  # canonical outputs
+
+
+@pytest.mark.parametrize("lg,ncols,is_coeffs", [(10, 3, 0), (17, 40, 0), (17, 33, 1), (13, 5, 0)])
+def test_lde_batch_host_pipeline_matches_commit(ctx, orc, lg, ncols, is_coeffs):
+    """ola_lde_batch (chunked, overlapped upload at the larger sizes) == the coefficients and leaves of ola_commit."""
+    n, rb = 1 << lg, 3
+    vals = orc.rand_elems(4242 + lg, (ncols, n))
+    vals[0, :4] = [P - 1, 0, 1, P - 2]
+    d_c, d_l = ctx.alloc(ncols * n), ctx.alloc(ncols * (n << rb))
+    try:
+        ctx.check(ctx._lib.ola_lde_batch(ctx.handle, olavm_b200._lib.hptr(vals), 0, ncols, lg, is_coeffs, rb, d_c, d_l))
+        coeffs = ctx.download(d_c, (ncols, n))
+        lde = ctx.download(d_l, (ncols, n << rb))
+        # resident input, transformed in place, gives the same result
+        d_v = ctx.upload(vals)
+        ctx.check(ctx._lib.ola_lde_batch(ctx.handle, d_v, 1, ncols, lg, is_coeffs, rb, d_v, d_l))
+        assert (ctx.download(d_v, (ncols, n)) == coeffs).all()
+        assert (ctx.download(d_l, (ncols, n << rb)) == lde).all()
+        ctx.free(d_v)
+    finally:
+        ctx.free(d_c)
+        ctx.free(d_l)
+    perm = bitrev_perm(lg + rb)
+    for k in sorted({0, ncols // 2, ncols - 1}):
+        co = vals[k] if is_coeffs else orc.interpolate_poly(vals[k])
+        assert (coeffs[k] == co).all(), k
+        assert (lde[k] == orc.evaluate_poly_with_offset(co, 7, 1 << rb)[perm]).all(), k

@@ -67,17 +67,16 @@ GL_HD void mul_wide(uint64_t a, uint64_t b, uint64_t& lo, uint64_t& hi) {
 
 // ---- device fast path ------------------------------------------------------------------------------
 // "lazy" values are arbitrary u64 representatives in [0, 2^64); "canonical" ones are < p.
-//   mul_lazy(any, any)          -> lazy        15 SASS instructions (7 for the 128-bit product, 8 to reduce)
+//   mul_lazy(any, any)          -> lazy        16 SASS instructions (7 for the 128-bit product, 9 to reduce)
 //   canon_fast(lazy)            -> canonical    4
-//   add_lc(lazy, canonical)     -> lazy         4      (a + v < 2^64 + p  =>  a single +EPS correction suffices)
+//   add_lc(lazy, canonical)     -> lazy         5      (a + v < 2^64 + p  =>  a single +EPS correction suffices)
 //   sub_lc(lazy, canonical)     -> lazy         5
 //   mad_lazy(any, any, any)     -> lazy        a*b + c reduced once (Field::multiply_accumulate,
 //                                              goldilocks_field.rs:110-113)
 // How the counts are reached (checked with cuobjdump -sass, tools/microbench/prims.cu): the 128-bit product is left to
-// the compiler (4 IMAD.WIDE chained through their carry predicates); every "+ carry * EPS" correction is ONE
-// IMAD.WIDE.U32 (carry * 0xffffffff + t) fed by the carry materialised with a single addc; x2 * EPS + (x1:x0) is an
-// IADD3 / IMAD.HI pair with carry-out.  The conditional corrections therefore cost 2 instructions instead of the 3-4 of
-// a mask-and-add sequence.  Never feed an add-chain carry into subc (ptxas keeps the hardware not-borrow convention
+// the compiler (4 IMAD.WIDE chained through their carry predicates); a "+ carry * EPS" correction is a SEL (mask from
+// the carry predicate) and a 64-bit add, or with GL_WIDE_CORR one IMAD.WIDE.U32 (carry * 0xffffffff + t);
+// x2 * EPS + (x1:x0) is an IADD3 / IMAD.HI pair with carry-out.  Never feed an add-chain carry into subc (ptxas keeps the hardware not-borrow convention
 // across the mix); add chains end in addc, sub chains in subc.
 // On the host the same names return canonical values (a valid lazy representative).
 #if defined(__CUDACC__)
@@ -91,8 +90,38 @@ __device__ __forceinline__ void mul_limbs(uint64_t a, uint64_t b, uint32_t& x0, 
 }
 #endif
 
+// GL_WIDE_CORR = 1 applies every "+ carry * EPS" correction as one IMAD.WIDE (fewest instructions); 0 (default) as a
+// masked 64-bit add on the ALU pipe (one instruction more, but IMAD.WIDE occupies the fmaheavy pipe for 4 cycles and
+// that pipe is the binding resource of the Poseidon and NTT kernels: profiles/r01m_*).
+#ifndef GL_WIDE_CORR
+#define GL_WIDE_CORR 0
+#endif
+#if defined(__CUDACC__)
+// t + (c ? EPS : 0) for a carry c in {0, 1}; the caller guarantees the sum does not wrap
+__device__ __forceinline__ uint64_t plus_carry_eps(uint64_t t, uint32_t c) {
+#if GL_WIDE_CORR
+    return t + (uint64_t)c * 0xFFFFFFFFu;
+#else
+    uint64_t r;
+    asm("{\n\t"
+        ".reg .u32 m, t0, t1; .reg .pred p;\n\t"
+        "setp.ne.u32 p, %2, 0;\n\t"
+        "selp.b32    m, 0xffffffff, 0, p;\n\t"
+        "mov.b64     {t0, t1}, %1;\n\t"
+        "add.cc.u32  t0, t0, m;\n\t"
+        "addc.u32    t1, t1, 0;\n\t"
+        "mov.b64     %0, {t0, t1};\n\t"
+        "}"
+        : "=l"(r)
+        : "l"(t), "r"(c));
+    return r;
+#endif
+}
+#endif
+
 GL_HD uint64_t canon_fast(uint64_t a) {
 #if defined(__CUDA_ARCH__)
+#if GL_WIDE_CORR
     uint32_t c;
     asm("{\n\t"
         ".reg .u32 a0, a1, s0, s1;\n\t"
@@ -105,6 +134,23 @@ GL_HD uint64_t canon_fast(uint64_t a) {
         : "l"(a));
     return a + (uint64_t)c * 0xFFFFFFFFu;  // a - p == a + EPS (mod 2^64)
 #else
+    uint64_t r;
+    asm("{\n\t"
+        ".reg .u32 a0, a1, s0, s1, c; .reg .pred p;\n\t"
+        "mov.b64     {a0, a1}, %1;\n\t"
+        "add.cc.u32  s0, a0, 0xffffffff;\n\t"  // s = a + EPS = a - p (mod 2^64); wraps  <=>  a >= p
+        "addc.cc.u32 s1, a1, 0;\n\t"
+        "addc.u32    c, 0, 0;\n\t"
+        "setp.ne.u32 p, c, 0;\n\t"
+        "selp.b32    s0, s0, a0, p;\n\t"
+        "selp.b32    s1, s1, a1, p;\n\t"
+        "mov.b64     %0, {s0, s1};\n\t"
+        "}"
+        : "=l"(r)
+        : "l"(a));
+    return r;
+#endif
+#else
     return canon(a);
 #endif
 }
@@ -116,7 +162,7 @@ GL_HD uint64_t add_lc(uint64_t a, uint64_t v) {
         "addc.u32    %1, 0, 0;"
         : "=l"(t), "=r"(c)
         : "l"(a), "l"(v));
-    return t + (uint64_t)c * 0xFFFFFFFFu;  // t = a + v - 2^64 < v < p: t + EPS cannot wrap again
+    return plus_carry_eps(t, c);  // t = a + v - 2^64 < v < p: t + EPS cannot wrap again
 #else
     return add(canon(a), v);
 #endif
@@ -144,7 +190,7 @@ __device__ __forceinline__ uint64_t reduce_limbs(uint32_t x0, uint32_t x1, uint3
         : "=r"(t0), "=r"(t1), "=r"(c)
         : "r"(x0), "r"(x1), "r"(x2));
     // wrapped value < 2^64 - 2^33, so + EPS cannot wrap again
-    uint64_t t = (((uint64_t)t1 << 32) | t0) + (uint64_t)c * 0xFFFFFFFFu;
+    const uint64_t t = plus_carry_eps(((uint64_t)t1 << 32) | t0, c);
     return sub_lc(t, (uint64_t)x3);
 }
 #endif
@@ -168,6 +214,20 @@ GL_HD uint64_t mad_lazy(uint64_t a, uint64_t b, uint64_t c) {
     uint64_t lo, hi;
     mul_wide(a, b, lo, hi);
     return add(reduce128(lo, hi), canon(c));
+#endif
+}
+// lo + x2 * 2^64 with a 32-bit x2 (sums of small-constant products: the MDS layer)
+GL_HD uint64_t reduce96_lazy(uint64_t lo, uint32_t x2) {
+#if defined(__CUDA_ARCH__)
+    uint32_t t0, t1, c;
+    asm("mad.lo.cc.u32   %0, %5, 0xffffffff, %3;\n\t"
+        "madc.hi.cc.u32  %1, %5, 0xffffffff, %4;\n\t"
+        "addc.u32        %2, 0, 0;"
+        : "=r"(t0), "=r"(t1), "=r"(c)
+        : "r"((uint32_t)lo), "r"((uint32_t)(lo >> 32)), "r"(x2));
+    return plus_carry_eps(((uint64_t)t1 << 32) | t0, c);
+#else
+    return reduce128(lo, (uint64_t)x2);
 #endif
 }
 GL_HD uint64_t reduce128_lazy(uint64_t lo, uint64_t hi) {

@@ -50,7 +50,7 @@ struct PassArgs {
     size_t out_mul;       // bitrev_store: address = natural_index*out_mul + bitrev(coset)  (interleaved cosets)
     int coset_bits;
     int apply_scale;
-    int coset_major;      // tile_strided: grid is (cosets, tiles, columns) instead of (tiles, columns, cosets)
+    size_t tiles_per_cta;  // tiled passes: tiles (sharing one twiddle table) streamed through each CTA
     int lazy_out;         // tile kernels: leave the outputs un-canonicalised (an intermediate pass; every pass accepts lazy input)
     size_t ncols;         // tile_contig: columns in the batch (the last column group may be partial)
     uint64_t scale;
@@ -467,6 +467,157 @@ __global__ void build_tables_kernel(uint64_t* pw, uint64_t* brs, uint64_t omega 
     if (i < 2048) brs[i] = gl::pow(w12, (uint64_t)gl::bitrev32((uint32_t)i, 11));
 }
 
+// ---- tiled passes (ntt_tile.cuh): configurations and dispatch -------------------------------------------------------
+// OLA_NTT_VARIANT picks the thread mapping of the 10- and 11-stage passes (the LDE of 2^20 .. 2^22-row tables):
+//   0: two lanes per thread in every round, 256 threads, 2 CTAs / SM
+//   1: as 0 with one padding row per 32 and the register allocation capped for 3 CTAs / SM   (10-stage passes only)
+//   2: two lanes in radix-8 rounds, one in radix-16 rounds: 512 threads of 16 elements, 2 CTAs / SM
+//   3: one lane per thread: 512 threads, 2 CTAs / SM
+static int tune_variant() {
+    static int v = [] {
+        const char* e = getenv("OLA_NTT_VARIANT");
+        int t = e ? atoi(e) : 2;  // profiles/r01m_ntt_tile_sweeps.txt
+        return (t >= 0 && t <= 3) ? t : 2;
+    }();
+    return v;
+}
+template <typename G>
+static void tile_optin(int max_optin) {
+    OLA_CUDA(cudaFuncSetAttribute(tile::tile_strided<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    OLA_CUDA(cudaFuncSetAttribute(tile::tile_strided<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    OLA_CUDA(cudaFuncSetAttribute(tile::tile_contig<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    OLA_CUDA(cudaFuncSetAttribute(tile::tile_contig<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+}
+template <typename G>
+static void tile_optin_contig(int max_optin) {
+    OLA_CUDA(cudaFuncSetAttribute(tile::tile_contig<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    OLA_CUDA(cudaFuncSetAttribute(tile::tile_contig<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+}
+using T6 = tile::Cfg<6, 8>;
+using T7 = tile::Cfg<7, 8>;
+using T8 = tile::Cfg<8, 8>;
+using T9 = tile::Cfg<9, 8>;
+using T10 = tile::Cfg<10, 8>;
+using T10v1 = tile::Cfg<10, 8, 2, 2, 5, 3>;
+using T10v2 = tile::Cfg<10, 8, 2, 1, 4, 2>;
+using T10v3 = tile::Cfg<10, 8, 1, 1, 4, 2>;
+using T11 = tile::Cfg<11, 4>;
+using T11v2 = tile::Cfg<11, 4, 2, 1, 4, 2>;
+using T11v3 = tile::Cfg<11, 4, 1, 1, 4, 2>;
+static void tile_optin_all(int max_optin) {
+    tile_optin<T6>(max_optin);
+    tile_optin<T7>(max_optin);
+    tile_optin<T8>(max_optin);
+    tile_optin<T9>(max_optin);
+    tile_optin<T10>(max_optin);
+    tile_optin<T10v1>(max_optin);
+    tile_optin<T10v2>(max_optin);
+    tile_optin<T10v3>(max_optin);
+    tile_optin<T11>(max_optin);
+    tile_optin<T11v2>(max_optin);
+    tile_optin<T11v3>(max_optin);
+    tile_optin_contig<tile::Cfg<6, 2>>(max_optin);
+    tile_optin_contig<tile::Cfg<7, 2>>(max_optin);
+    tile_optin_contig<tile::Cfg<8, 2>>(max_optin);
+    tile_optin_contig<tile::Cfg<9, 2>>(max_optin);
+    tile_optin_contig<tile::Cfg<10, 2>>(max_optin);
+    tile_optin_contig<tile::Cfg<11, 2>>(max_optin);
+}
+
+// tiles per CTA: long enough to amortise the twiddle prologue, short enough to keep >= ~8 waves of CTAs in flight
+static size_t pick_tiles_per_cta(const ola_ctx* ctx, size_t total_tiles, size_t per_table, int resident_per_sm) {
+    const size_t slots = (size_t)ctx->sm_count * (size_t)resident_per_sm;
+    size_t t = total_tiles / (8 * slots);
+    t = std::min<size_t>(std::max<size_t>(t, 1), 32);
+    return std::min(t, per_table);
+}
+template <typename G, bool GS>
+static void tile_strided_launch(ola_ctx* ctx, const PassArgs& a, size_t ncols, int ncosets) {
+    PassArgs b = a;
+    b.ncols = ncols;
+    const size_t nsub = (size_t)1 << (a.L - a.M);
+    const size_t per_q = ncols * ((((size_t)1 << a.M) >> G::l) / G::C);
+    b.tiles_per_cta = pick_tiles_per_cta(ctx, per_q * nsub * (size_t)ncosets, per_q, G::MINB);
+    size_t chunks = (per_q + b.tiles_per_cta - 1) / b.tiles_per_cta;
+    while (nsub * chunks > 65535) {  // grid.y limit
+        b.tiles_per_cta *= 2;
+        chunks = (per_q + b.tiles_per_cta - 1) / b.tiles_per_cta;
+    }
+    const dim3 g((unsigned)ncosets, (unsigned)(nsub * chunks));
+    tile::tile_strided<G, GS><<<g, G::NT, G::SMEM, ctx->stream>>>(b);
+}
+template <typename G, bool GS>
+static void tile_contig_launch(ola_ctx* ctx, const PassArgs& a, size_t ncols, int ncosets) {
+    PassArgs b = a;
+    b.ncols = ncols;
+    const size_t nsub = ((size_t)1 << a.L) >> G::l;
+    const size_t groups = (ncols + G::C - 1) / G::C;
+    b.tiles_per_cta = pick_tiles_per_cta(ctx, groups * nsub * (size_t)ncosets, groups, G::MINB);
+    size_t chunks = (groups + b.tiles_per_cta - 1) / b.tiles_per_cta;
+    while (chunks > 65535) {
+        b.tiles_per_cta *= 2;
+        chunks = (groups + b.tiles_per_cta - 1) / b.tiles_per_cta;
+    }
+    const dim3 g((unsigned)nsub, (unsigned)chunks, (unsigned)ncosets);
+    tile::tile_contig<G, GS><<<g, G::NT, G::SMEM, ctx->stream>>>(b);
+}
+template <bool GS>
+static void tile_strided_dispatch(ola_ctx* ctx, const PassArgs& a, size_t ncols, int ncosets) {
+    const int v = tune_variant();
+    switch (a.l) {
+        case 6: tile_strided_launch<T6, GS>(ctx, a, ncols, ncosets); break;
+        case 7: tile_strided_launch<T7, GS>(ctx, a, ncols, ncosets); break;
+        case 8: tile_strided_launch<T8, GS>(ctx, a, ncols, ncosets); break;
+        case 9: tile_strided_launch<T9, GS>(ctx, a, ncols, ncosets); break;
+        case 10:
+            if (v == 1) tile_strided_launch<T10v1, GS>(ctx, a, ncols, ncosets);
+            else if (v == 2) tile_strided_launch<T10v2, GS>(ctx, a, ncols, ncosets);
+            else if (v == 3) tile_strided_launch<T10v3, GS>(ctx, a, ncols, ncosets);
+            else tile_strided_launch<T10, GS>(ctx, a, ncols, ncosets);
+            break;
+        case 11:
+            if (v == 2) tile_strided_launch<T11v2, GS>(ctx, a, ncols, ncosets);
+            else if (v == 3) tile_strided_launch<T11v3, GS>(ctx, a, ncols, ncosets);
+            else tile_strided_launch<T11, GS>(ctx, a, ncols, ncosets);
+            break;
+        default: OLA_CHECK(false, OLA_ERR_INTERNAL, "no tiled strided pass of that length");
+    }
+}
+template <bool GS>
+static void tile_contig_dispatch(ola_ctx* ctx, const PassArgs& a, size_t ncols, int ncosets) {
+    const int v = tune_variant();
+    if (ncols <= 2) {  // one or two columns (quotient, FRI): 2-lane tiles
+        switch (a.l) {
+            case 6: tile_contig_launch<tile::Cfg<6, 2>, GS>(ctx, a, ncols, ncosets); break;
+            case 7: tile_contig_launch<tile::Cfg<7, 2>, GS>(ctx, a, ncols, ncosets); break;
+            case 8: tile_contig_launch<tile::Cfg<8, 2>, GS>(ctx, a, ncols, ncosets); break;
+            case 9: tile_contig_launch<tile::Cfg<9, 2>, GS>(ctx, a, ncols, ncosets); break;
+            case 10: tile_contig_launch<tile::Cfg<10, 2>, GS>(ctx, a, ncols, ncosets); break;
+            case 11: tile_contig_launch<tile::Cfg<11, 2>, GS>(ctx, a, ncols, ncosets); break;
+            default: OLA_CHECK(false, OLA_ERR_INTERNAL, "no tiled contiguous pass of that length");
+        }
+        return;
+    }
+    switch (a.l) {
+        case 6: tile_contig_launch<T6, GS>(ctx, a, ncols, ncosets); break;
+        case 7: tile_contig_launch<T7, GS>(ctx, a, ncols, ncosets); break;
+        case 8: tile_contig_launch<T8, GS>(ctx, a, ncols, ncosets); break;
+        case 9: tile_contig_launch<T9, GS>(ctx, a, ncols, ncosets); break;
+        case 10:
+            if (v == 1) tile_contig_launch<T10v1, GS>(ctx, a, ncols, ncosets);
+            else if (v == 2) tile_contig_launch<T10v2, GS>(ctx, a, ncols, ncosets);
+            else if (v == 3) tile_contig_launch<T10v3, GS>(ctx, a, ncols, ncosets);
+            else tile_contig_launch<T10, GS>(ctx, a, ncols, ncosets);
+            break;
+        case 11:
+            if (v == 2) tile_contig_launch<T11v2, GS>(ctx, a, ncols, ncosets);
+            else if (v == 3) tile_contig_launch<T11v3, GS>(ctx, a, ncols, ncosets);
+            else tile_contig_launch<T11, GS>(ctx, a, ncols, ncosets);
+            break;
+        default: OLA_CHECK(false, OLA_ERR_INTERNAL, "no tiled contiguous pass of that length");
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Opt every pass kernel into the device's maximum dynamic shared memory once, with the same value from every context
 // (a per-launch cudaFuncSetAttribute with the launch's own size races when several host threads drive one GPU).
@@ -481,29 +632,7 @@ static void opt_in_shared_memory(int device) {
     OLA_CUDA(cudaFuncSetAttribute(pass_strided<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     OLA_CUDA(cudaFuncSetAttribute(pass_contig<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     OLA_CUDA(cudaFuncSetAttribute(pass_contig<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
-#define OLA_TILE_OPTIN(LL, CC)                                                                                                  \
-    OLA_CUDA(cudaFuncSetAttribute(tile::tile_strided<LL, CC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin)); \
-    OLA_CUDA(cudaFuncSetAttribute(tile::tile_strided<LL, CC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));  \
-    OLA_CUDA(cudaFuncSetAttribute(tile::tile_contig<LL, CC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));  \
-    OLA_CUDA(cudaFuncSetAttribute(tile::tile_contig<LL, CC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
-#define OLA_TILE_OPTIN2(LL)                                                                                                   \
-    OLA_CUDA(cudaFuncSetAttribute(tile::tile_contig<LL, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin)); \
-    OLA_CUDA(cudaFuncSetAttribute(tile::tile_contig<LL, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
-    OLA_TILE_OPTIN2(6)
-    OLA_TILE_OPTIN2(7)
-    OLA_TILE_OPTIN2(8)
-    OLA_TILE_OPTIN2(9)
-    OLA_TILE_OPTIN2(10)
-    OLA_TILE_OPTIN2(11)
-#undef OLA_TILE_OPTIN2
-    OLA_TILE_OPTIN(6, 8)
-    OLA_TILE_OPTIN(7, 8)
-    OLA_TILE_OPTIN(8, 8)
-    OLA_TILE_OPTIN(9, 8)
-    OLA_TILE_OPTIN(10, 8)
-    OLA_TILE_OPTIN(11, 4)
-    OLA_TILE_OPTIN(10, 4)
-#undef OLA_TILE_OPTIN
+    tile_optin_all(max_optin);
 }
 
 void init_twiddles(ola_ctx* ctx) {
@@ -562,20 +691,6 @@ static bool tune_tile() {  // OLA_NTT_TILE=0 falls back to the generic passes (A
     }();
     return v;
 }
-static bool tune_coset_major() {
-    static bool v = [] {
-        const char* e = getenv("OLA_NTT_COSET_MAJOR");
-        return !(e && atoi(e) == 0);
-    }();
-    return v;
-}
-static bool tune_c4() {  // 4-lane tiles for 10-stage passes (more resident CTAs per SM, 32-byte segments)
-    static bool v = [] {
-        const char* e = getenv("OLA_NTT_C4");
-        return e && atoi(e) != 0;
-    }();
-    return v;
-}
 static int tune_gmax() {
     static int v = [] {
         const char* e = getenv("OLA_NTT_G");
@@ -592,25 +707,7 @@ static void launch_strided(ola_ctx* ctx, const PassArgs& a, size_t ncols, int nc
     dim3 grid((unsigned)tiles, (unsigned)ncols, (unsigned)ncosets);
     if (a.l >= 6 && a.l <= 11 && tune_tile()) {
         Launch lz(ctx, name);
-        PassArgs b = a;
-#define OLA_TILE_S(KEY, LL, CC)                                                                                    \
-    case KEY: {                                                                                                    \
-        const size_t ntiles = ((size_t)1 << a.L) / ((size_t)R * CC);                                               \
-        b.coset_major = (tune_coset_major() && ntiles <= 65535 && ncols <= 65535) ? 1 : 0;                          \
-        const dim3 g = b.coset_major ? dim3((unsigned)ncosets, (unsigned)ntiles, (unsigned)ncols)                  \
-                                     : dim3((unsigned)ntiles, (unsigned)ncols, (unsigned)ncosets);                 \
-        tile::tile_strided<LL, CC, GS><<<g, tile::Geo<LL, CC>::NT, tile::Geo<LL, CC>::SMEM, ctx->stream>>>(b);     \
-    } break;
-        switch (a.l + ((a.l == 10 && tune_c4()) ? 100 : 0)) {
-            OLA_TILE_S(6, 6, 8)
-            OLA_TILE_S(7, 7, 8)
-            OLA_TILE_S(8, 8, 8)
-            OLA_TILE_S(9, 9, 8)
-            OLA_TILE_S(10, 10, 8)
-            OLA_TILE_S(11, 11, 4)
-            OLA_TILE_S(110, 10, 4)
-        }
-#undef OLA_TILE_S
+        tile_strided_dispatch<GS>(ctx, a, ncols, ncosets);
     } else if (a.l >= 6) {
         const size_t padded = (size_t)R * TILE_T + ((size_t)R * TILE_T >> 4) + 1;
         size_t smem = ((size_t)R + 16 + padded) * sizeof(uint64_t);
@@ -633,40 +730,7 @@ static void launch_contig(ola_ctx* ctx, const PassArgs& a, size_t ncols, int nco
     dim3 grid((unsigned)blocks, (unsigned)ncols, (unsigned)ncosets);
     if (a.l >= 6 && a.l <= 11 && !a.bitrev_store && tune_tile()) {
         Launch lz(ctx, name);
-        PassArgs b = a;
-        b.ncols = ncols;
-        const int key = a.l + (ncols <= 2 ? 100 : ((a.l == 10 && tune_c4()) ? 200 : 0));  // one or two columns (quotient, FRI): 2-lane tiles
-#define OLA_TILE_C(LL, CC)                                                                                         \
-    case LL:                                                                                                       \
-        tile::tile_contig<LL, CC, GS>                                                                              \
-            <<<dim3((unsigned)(((size_t)1 << a.L) >> LL), (unsigned)((ncols + CC - 1) / CC), (unsigned)ncosets),   \
-               tile::Geo<LL, CC>::NT, tile::Geo<LL, CC>::SMEM, ctx->stream>>>(b);                                  \
-        break;
-#define OLA_TILE_C2(LL)                                                                                   \
-    case 100 + LL:                                                                                        \
-        tile::tile_contig<LL, 2, GS><<<dim3((unsigned)(((size_t)1 << a.L) >> LL), 1, (unsigned)ncosets),  \
-                                       tile::Geo<LL, 2>::NT, tile::Geo<LL, 2>::SMEM, ctx->stream>>>(b);   \
-        break;
-        switch (key) {
-            OLA_TILE_C(6, 8)
-            OLA_TILE_C(7, 8)
-            OLA_TILE_C(8, 8)
-            OLA_TILE_C(9, 8)
-            OLA_TILE_C(10, 8)
-            OLA_TILE_C(11, 4)
-            case 210:
-                tile::tile_contig<10, 4, GS><<<dim3((unsigned)(((size_t)1 << a.L) >> 10), (unsigned)((ncols + 3) / 4), (unsigned)ncosets),
-                                               tile::Geo<10, 4>::NT, tile::Geo<10, 4>::SMEM, ctx->stream>>>(b);
-                break;
-            OLA_TILE_C2(6)
-            OLA_TILE_C2(7)
-            OLA_TILE_C2(8)
-            OLA_TILE_C2(9)
-            OLA_TILE_C2(10)
-            OLA_TILE_C2(11)
-        }
-#undef OLA_TILE_C2
-#undef OLA_TILE_C
+        tile_contig_dispatch<GS>(ctx, a, ncols, ncosets);
     } else if (a.l >= 6) {
         const size_t padded = (size_t)a.G * R + ((size_t)a.G * R >> 4) + 1;
         size_t smem = ((size_t)a.G * R + (size_t)a.G * 16 + padded) * sizeof(uint64_t);

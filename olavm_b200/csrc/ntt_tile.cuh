@@ -46,14 +46,18 @@ struct Rd<l, 0> {
     static constexpr int OFF = 0;
 };
 
-template <int l, int C>
-struct Geo {
+// Tile shape and thread mapping.  LN3 / LN4 = adjacent lanes owned by one thread in radix-8 / radix-16 rounds (1 or 2);
+// PADLOG: one padding row per 2^PADLOG rows; MINB: resident CTAs per SM the register allocation is capped for.
+template <int l_, int C_, int LN3_ = 2, int LN4_ = 2, int PADLOG_ = 4, int MINB_ = 2>
+struct Cfg {
+    static constexpr int l = l_, C = C_, LN3 = LN3_, LN4 = LN4_, PADLOG = PADLOG_, MINB = MINB_;
     static constexpr int R = 1 << l;
-    static constexpr int RP = R + (R >> 4);  // padded rows
-    static constexpr int KMAX = Sched<l>::N16 > 0 ? 4 : 3;
-    static constexpr int NT_RAW = (R >> KMAX) * (C / 2);
+    static constexpr int RP = R + (R >> PADLOG);  // padded rows
+    static constexpr int ITEMS3 = (R >> 3) * (C / LN3), ITEMS4 = (R >> 4) * (C / LN4);
+    static constexpr int NT_RAW = Sched<l>::N16 == 0 ? ITEMS3 : (Sched<l>::N8 == 0 ? ITEMS4 : (ITEMS3 < ITEMS4 ? ITEMS3 : ITEMS4));
     static constexpr int NT = NT_RAW < 32 ? 32 : (NT_RAW > 512 ? 512 : NT_RAW);
     static constexpr size_t SMEM = ((size_t)R + 16 + (size_t)RP * C) * sizeof(uint64_t);
+    static_assert(C % LN3 == 0 && C % LN4 == 0 && (LN3 == 1 || LN3 == 2) && (LN4 == 1 || LN4 == 2), "lanes per thread");
 };
 
 // twiddle of (stage u0 + s, block (qh << s) + ql) lives at tw[OFF + (((1 << s) - 1 + ql) << U0) + qh]
@@ -76,9 +80,9 @@ __device__ __forceinline__ void build_twiddles(uint64_t* tw, const uint64_t* cu,
     }
 }
 
-// K stages on 2^K rows x 2 lanes in registers; t = tw + OFF + qh
-template <int K, int U0, bool GS>
-__device__ __forceinline__ void bfly_regs(uint64_t (&v)[1 << K][2], const uint64_t* __restrict__ t) {
+// K stages on 2^K rows x LN lanes in registers; t = tw + OFF + qh
+template <int K, int U0, bool GS, int LN>
+__device__ __forceinline__ void bfly_regs(uint64_t (&v)[1 << K][LN], const uint64_t* __restrict__ t) {
     if (!GS) {
 #pragma unroll
         for (int s = 0; s < K; ++s) {
@@ -90,7 +94,7 @@ __device__ __forceinline__ void bfly_regs(uint64_t (&v)[1 << K][2], const uint64
                 for (int jj = 0; jj < half; ++jj) {
                     const int m = (ql << (K - s)) + jj;
 #pragma unroll
-                    for (int ln = 0; ln < 2; ++ln) {
+                    for (int ln = 0; ln < LN; ++ln) {
                         const uint64_t p = gl::canon_fast(gl::mul_lazy(v[m + half][ln], w));
                         const uint64_t a = v[m][ln];
                         v[m][ln] = gl::add_lc(a, p);
@@ -110,7 +114,7 @@ __device__ __forceinline__ void bfly_regs(uint64_t (&v)[1 << K][2], const uint64
                 for (int jj = 0; jj < half; ++jj) {
                     const int m = (ql << (K - s)) + jj;
 #pragma unroll
-                    for (int ln = 0; ln < 2; ++ln) {
+                    for (int ln = 0; ln < LN; ++ln) {
                         const uint64_t b = gl::canon_fast(v[m + half][ln]);
                         const uint64_t a = v[m][ln];
                         v[m][ln] = gl::add_lc(a, b);
@@ -134,42 +138,53 @@ struct Io {
     uint64_t scale;
 };
 
-template <int SH>
-__device__ __forceinline__ constexpr int pad_of(int m) {
-    return SH >= 4 ? (m << (SH >= 4 ? SH - 4 : 0)) : (m >> (SH < 4 ? 4 - SH : 0));
+// row offset (in padded rows) of register-block element m relative to the block's first row
+template <int SH, int P>
+__device__ __forceinline__ constexpr int row_off(int m) {
+    return (m << SH) + (SH >= P ? (m << (SH >= P ? SH - P : 0)) : (m >> (SH < P ? P - SH : 0)));
 }
 
-template <int l, int C, bool GS, bool CONTIG, int I>
+template <typename G, bool GS, bool CONTIG, int I>
 __device__ __forceinline__ void run_step(const Io<CONTIG>& io, uint64_t* __restrict__ x, const uint64_t* __restrict__ tw, int tid) {
+    constexpr int l = G::l, C = G::C, P = G::PADLOG;
     constexpr int NR = Sched<l>::NR;
     constexpr int RHO = GS ? NR - 1 - I : I;
     using rd = Rd<l, RHO>;
     constexpr int K = rd::K, U0 = rd::U0, SH = rd::SH, NE = 1 << K;
+    constexpr int LN = (K == 3) ? G::LN3 : G::LN4;
+    constexpr int NLG = C / LN;  // lane groups
     constexpr bool FIRST = (I == 0), LAST = (I == NR - 1);
-    constexpr int NITEMS = ((1 << l) >> K) * (C / 2);
-    constexpr int NT = Geo<l, C>::NT;
+    constexpr int NITEMS = ((1 << l) >> K) * NLG;
+    constexpr int NT = G::NT;
 #pragma unroll 1
     for (int w = tid; w < NITEMS; w += NT) {
-        const int cp = w % (C / 2), rest = w / (C / 2);
+        const int lane0 = (w % NLG) * LN;
+        int rest = w / NLG;
+        // one padding row per 32: neighbouring threads of the stride-1 radix-16 round must sit 32 rows apart, not 16
+        if (SH == 0 && K == 4 && P == 5) rest = (rest & ~3) | ((rest & 1) << 1) | ((rest >> 1) & 1);
         const int j = rest & ((1 << SH) - 1), qh = rest >> SH;
         const int rbase = (qh << (SH + K)) + j;
-        uint64_t v[NE][2];
-        ulonglong2* xp = reinterpret_cast<ulonglong2*>(x + (size_t)(rbase + (rbase >> 4)) * C + 2 * cp);
+        uint64_t v[NE][LN];
+        uint64_t* xp = x + (size_t)(rbase + (rbase >> P)) * C + lane0;
         if (FIRST) {
             if (!CONTIG) {
-                const uint64_t* p = io.in + (size_t)rbase * io.in_row + 2 * cp;
+                const uint64_t* p = io.in + (size_t)rbase * io.in_row + lane0;
                 const size_t step = io.in_row << SH;
 #pragma unroll
                 for (int m = 0; m < NE; ++m) {
-                    const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(p + (size_t)m * step);
-                    v[m][0] = q.x;
-                    v[m][1] = q.y;
+                    if (LN == 2) {
+                        const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(p + (size_t)m * step);
+                        v[m][0] = q.x;
+                        v[m][LN - 1] = q.y;
+                    } else {
+                        v[m][0] = p[(size_t)m * step];
+                    }
                 }
             } else {
 #pragma unroll
-                for (int ln = 0; ln < 2; ++ln) {
-                    const bool ok = 2 * cp + ln < io.lanes_valid;
-                    const uint64_t* p = io.in + (size_t)(2 * cp + ln) * io.in_lane + rbase;
+                for (int ln = 0; ln < LN; ++ln) {
+                    const bool ok = lane0 + ln < io.lanes_valid;
+                    const uint64_t* p = io.in + (size_t)(lane0 + ln) * io.in_lane + rbase;
                     if (SH == 0) {
 #pragma unroll
                         for (int m = 0; m < NE; m += 2) {
@@ -187,17 +202,21 @@ __device__ __forceinline__ void run_step(const Io<CONTIG>& io, uint64_t* __restr
         } else {
 #pragma unroll
             for (int m = 0; m < NE; ++m) {
-                const ulonglong2 q = xp[(((m << SH) + pad_of<SH>(m)) * C) / 2];
-                v[m][0] = q.x;
-                v[m][1] = q.y;
+                if (LN == 2) {
+                    const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(xp + row_off<SH, P>(m) * C);
+                    v[m][0] = q.x;
+                    v[m][LN - 1] = q.y;
+                } else {
+                    v[m][0] = xp[row_off<SH, P>(m) * C];
+                }
             }
         }
-        bfly_regs<K, U0, GS>(v, tw + rd::OFF + qh);
+        bfly_regs<K, U0, GS, LN>(v, tw + rd::OFF + qh);
         if (LAST) {
 #pragma unroll
             for (int m = 0; m < NE; ++m) {
 #pragma unroll
-                for (int ln = 0; ln < 2; ++ln) {
+                for (int ln = 0; ln < LN; ++ln) {
                     if (io.apply_scale)
                         v[m][ln] = gl::mul(v[m][ln], io.scale);
                     else if (!io.lazy_out)
@@ -205,15 +224,20 @@ __device__ __forceinline__ void run_step(const Io<CONTIG>& io, uint64_t* __restr
                 }
             }
             if (!CONTIG) {
-                uint64_t* p = io.out + (size_t)rbase * io.out_row + 2 * cp;
+                uint64_t* p = io.out + (size_t)rbase * io.out_row + lane0;
                 const size_t step = io.out_row << SH;
 #pragma unroll
-                for (int m = 0; m < NE; ++m) *reinterpret_cast<ulonglong2*>(p + (size_t)m * step) = make_ulonglong2(v[m][0], v[m][1]);
+                for (int m = 0; m < NE; ++m) {
+                    if (LN == 2)
+                        *reinterpret_cast<ulonglong2*>(p + (size_t)m * step) = make_ulonglong2(v[m][0], v[m][LN - 1]);
+                    else
+                        p[(size_t)m * step] = v[m][0];
+                }
             } else {
 #pragma unroll
-                for (int ln = 0; ln < 2; ++ln) {
-                    if (2 * cp + ln >= io.lanes_valid) continue;
-                    uint64_t* p = io.out + (size_t)(2 * cp + ln) * io.out_lane + rbase;
+                for (int ln = 0; ln < LN; ++ln) {
+                    if (lane0 + ln >= io.lanes_valid) continue;
+                    uint64_t* p = io.out + (size_t)(lane0 + ln) * io.out_lane + rbase;
                     if (SH == 0) {
 #pragma unroll
                         for (int m = 0; m < NE; m += 2) *reinterpret_cast<ulonglong2*>(p + m) = make_ulonglong2(v[m][ln], v[m + 1][ln]);
@@ -225,39 +249,47 @@ __device__ __forceinline__ void run_step(const Io<CONTIG>& io, uint64_t* __restr
             }
         } else {
 #pragma unroll
-            for (int m = 0; m < NE; ++m) xp[(((m << SH) + pad_of<SH>(m)) * C) / 2] = make_ulonglong2(v[m][0], v[m][1]);
+            for (int m = 0; m < NE; ++m) {
+                if (LN == 2)
+                    *reinterpret_cast<ulonglong2*>(xp + row_off<SH, P>(m) * C) = make_ulonglong2(v[m][0], v[m][LN - 1]);
+                else
+                    xp[row_off<SH, P>(m) * C] = v[m][0];
+            }
         }
     }
     if (!LAST) __syncthreads();
 }
 
-template <int l, int C, bool GS, bool CONTIG, int I>
+template <typename G, bool GS, bool CONTIG, int I>
 __device__ __forceinline__ void run_steps(const Io<CONTIG>& io, uint64_t* x, const uint64_t* tw, int tid) {
-    run_step<l, C, GS, CONTIG, I>(io, x, tw, tid);
-    if constexpr (I + 1 < Sched<l>::NR) run_steps<l, C, GS, CONTIG, I + 1>(io, x, tw, tid);
+    run_step<G, GS, CONTIG, I>(io, x, tw, tid);
+    if constexpr (I + 1 < Sched<G::l>::NR) run_steps<G, GS, CONTIG, I + 1>(io, x, tw, tid);
 }
 
-// strided pass: tile = (sub-block Q, C adjacent inner indices) x all 2^l rows; grid (tiles, columns, cosets)
-template <int l, int C, bool GS>
-__global__ void __launch_bounds__(Geo<l, C>::NT) tile_strided(const PassArgs a) {
+// Both kernels are persistent over tiles that share one twiddle table (same sub-block Q, same coset): the table is
+// built once per CTA and a.tiles_per_cta tiles stream through it (the per-tile prologue -- a serial chain of squarings
+// for the stage constants plus R - 1 products -- was a quarter of the kernel time when paid per tile).
+
+// strided pass: tile = (sub-block Q, C adjacent inner indices) x all 2^l rows.  grid (cosets, sub-blocks x chunks):
+// the cosets of one chunk are resident together and walk the same tiles, so the shared input of a coset LDE
+// (src_coset_stride == 0) comes from HBM once and from L2 for the other cosets.
+template <typename G, bool GS>
+__global__ void __launch_bounds__(G::NT, G::MINB) tile_strided(const PassArgs a) {
     extern __shared__ __align__(16) uint64_t sm[];
-    constexpr int R = 1 << l;
+    constexpr int l = G::l, C = G::C, R = 1 << l;
     uint64_t* tw = sm;
     uint64_t* cu = sm + R;
     uint64_t* x = sm + R + 16;
     const int tid = threadIdx.x;
-    // cosets vary fastest in the grid: the cosets of one tile are resident together, so the shared input of a coset LDE
-    // (src_coset_stride == 0) comes from HBM once and from L2 for the other cosets
-    const uint32_t coset = a.coset_major ? blockIdx.x : blockIdx.z;
-    const uint32_t tile_id = a.coset_major ? blockIdx.y : blockIdx.x;
-    const uint32_t col = a.coset_major ? blockIdx.z : blockIdx.y;
+    const uint32_t coset = blockIdx.x;
     const size_t inner = (size_t)1 << (a.M - l);
-    const uint32_t tiles_per_sub = (uint32_t)(inner / C);
-    const uint32_t Q = tile_id / tiles_per_sub;
-    const size_t c0 = (size_t)(tile_id % tiles_per_sub) * C;
+    const size_t tiles_per_sub = inner / C;
+    const size_t per_q = a.ncols * tiles_per_sub;  // tiles of one sub-block: (column, tile) pairs
+    const size_t chunks_per_q = (per_q + a.tiles_per_cta - 1) / a.tiles_per_cta;
+    const uint32_t Q = (uint32_t)(blockIdx.y / chunks_per_q);
+    const size_t t0 = (blockIdx.y % chunks_per_q) * a.tiles_per_cta;
+    const size_t t1 = t0 + a.tiles_per_cta < per_q ? t0 + a.tiles_per_cta : per_q;
     Io<false> io;
-    io.in = a.src + col * a.src_col_stride + coset * a.src_coset_stride + ((size_t)Q << a.M) + c0;
-    io.out = a.dst + col * a.dst_col_stride + coset * a.dst_coset_stride + ((size_t)Q << a.M) + c0;
     io.in_row = io.out_row = inner;
     io.in_lane = io.out_lane = 1;
     io.lanes_valid = C;
@@ -266,38 +298,51 @@ __global__ void __launch_bounds__(Geo<l, C>::NT) tile_strided(const PassArgs a) 
     io.scale = a.scale;
     if (tid == 0) row_constants(a, a.s_last[coset], Q, cu);
     __syncthreads();
-    build_twiddles<l>(tw, cu, a.brs, tid, Geo<l, C>::NT);
+    build_twiddles<l>(tw, cu, a.brs, tid, G::NT);
     __syncthreads();
-    run_steps<l, C, GS, false, 0>(io, x, tw, tid);
+    for (size_t t = t0; t < t1; ++t) {
+        const size_t col = t / tiles_per_sub, c0 = (t % tiles_per_sub) * C;
+        io.in = a.src + col * a.src_col_stride + coset * a.src_coset_stride + ((size_t)Q << a.M) + c0;
+        io.out = a.dst + col * a.dst_col_stride + coset * a.dst_coset_stride + ((size_t)Q << a.M) + c0;
+        run_steps<G, GS, false, 0>(io, x, tw, tid);
+        if (Sched<l>::NR > 1 && t + 1 < t1) __syncthreads();  // the next tile's first round overwrites the staging rows
+    }
 }
 
-// contiguous pass (M == l): tile = sub-block Q (2^l consecutive elements) of C columns; grid (sub-blocks, column groups, cosets)
-template <int l, int C, bool GS>
-__global__ void __launch_bounds__(Geo<l, C>::NT) tile_contig(const PassArgs a) {
+// contiguous pass (M == l): tile = sub-block Q (2^l consecutive elements) of C columns.  grid (sub-blocks, chunks of
+// column groups, cosets)
+template <typename G, bool GS>
+__global__ void __launch_bounds__(G::NT, G::MINB) tile_contig(const PassArgs a) {
     extern __shared__ __align__(16) uint64_t sm[];
-    constexpr int R = 1 << l;
+    constexpr int l = G::l, C = G::C, R = 1 << l;
     uint64_t* tw = sm;
     uint64_t* cu = sm + R;
     uint64_t* x = sm + R + 16;
     const int tid = threadIdx.x;
     const uint32_t coset = blockIdx.z;
     const uint32_t Q = blockIdx.x;
-    const size_t col0 = (size_t)blockIdx.y * C;
+    const size_t groups = (a.ncols + C - 1) / C;
+    const size_t g0 = (size_t)blockIdx.y * a.tiles_per_cta;
+    const size_t g1 = g0 + a.tiles_per_cta < groups ? g0 + a.tiles_per_cta : groups;
     Io<true> io;
-    io.in = a.src + col0 * a.src_col_stride + coset * a.src_coset_stride + ((size_t)Q << l);
-    io.out = a.dst + col0 * a.dst_col_stride + coset * a.dst_coset_stride + ((size_t)Q << l);
     io.in_row = io.out_row = 1;
     io.in_lane = a.src_col_stride;
     io.out_lane = a.dst_col_stride;
-    io.lanes_valid = (int)((a.ncols - col0) < (size_t)C ? (a.ncols - col0) : (size_t)C);
     io.apply_scale = a.apply_scale;
     io.lazy_out = a.lazy_out;
     io.scale = a.scale;
     if (tid == 0) row_constants(a, a.s_last[coset], Q, cu);
     __syncthreads();
-    build_twiddles<l>(tw, cu, a.brs, tid, Geo<l, C>::NT);
+    build_twiddles<l>(tw, cu, a.brs, tid, G::NT);
     __syncthreads();
-    run_steps<l, C, GS, true, 0>(io, x, tw, tid);
+    for (size_t g = g0; g < g1; ++g) {
+        const size_t col0 = g * C;
+        io.in = a.src + col0 * a.src_col_stride + coset * a.src_coset_stride + ((size_t)Q << l);
+        io.out = a.dst + col0 * a.dst_col_stride + coset * a.dst_coset_stride + ((size_t)Q << l);
+        io.lanes_valid = (int)((a.ncols - col0) < (size_t)C ? (a.ncols - col0) : (size_t)C);
+        run_steps<G, GS, true, 0>(io, x, tw, tid);
+        if (Sched<l>::NR > 1 && g + 1 < g1) __syncthreads();
+    }
 }
 
 }  // namespace tile

@@ -44,7 +44,8 @@ __global__ void __launch_bounds__(128, 5) permute_kernel(uint64_t* states, size_
 }
 
 // hash_no_pad over one row; ROWMAJOR: element (r, c) at base[r*ncols + c]; else at base[c*col_stride + r]
-template <bool ROWMAJOR, int MINB, bool UNROLLED = false>
+// MODE: 0 rolled permutation, 1 fully straight-line (A/B only), 2 straight-line full rounds inside rolled round loops
+template <bool ROWMAJOR, int MINB, int MODE = 0>
 __global__ void __launch_bounds__(128, MINB) hash_rows_kernel(const uint64_t* __restrict__ base, size_t col_stride, size_t nrows,
                                                        size_t ncols, uint64_t* __restrict__ digests) {
     size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -60,10 +61,10 @@ __global__ void __launch_bounds__(128, MINB) hash_rows_kernel(const uint64_t* __
                 s[k] = v;
             }
         }
-        if (UNROLLED)
+        if (MODE == 1)
             permute_unrolled(s);
         else
-            permute(s);
+            permute<MODE == 2>(s);
     }
     ulonglong2* d = reinterpret_cast<ulonglong2*>(digests + 4 * r);
     d[0] = make_ulonglong2(s[0], s[1]);
@@ -71,6 +72,7 @@ __global__ void __launch_bounds__(128, MINB) hash_rows_kernel(const uint64_t* __
 }
 
 // nodes[i] = two_to_one(nodes[2i], nodes[2i+1]) for i in [first, first + count)
+template <int MODE>
 __global__ void __launch_bounds__(128, 5) merkle_level_kernel(uint64_t* nodes, size_t first, size_t count) {
     size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= count) return;
@@ -78,12 +80,21 @@ __global__ void __launch_bounds__(128, 5) merkle_level_kernel(uint64_t* nodes, s
     const ulonglong2* ch = reinterpret_cast<const ulonglong2*>(nodes + 8 * i);
     ulonglong2 a = ch[0], b = ch[1], c = ch[2], d = ch[3];
     uint64_t s[12] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y, 0, 0, 0, 0};
-    permute(s);
+    permute<MODE == 2>(s);
     ulonglong2* o = reinterpret_cast<ulonglong2*>(nodes + 4 * i);
     o[0] = make_ulonglong2(s[0], s[1]);
     o[1] = make_ulonglong2(s[2], s[3]);
 }
 
+// body form of the permutation (OLA_POSEIDON_UNROLLED: 0 rolled, 1 straight-line, 2 straight-line full rounds)
+static int poseidon_mode() {
+    static const int v = [] {
+        const char* e = getenv("OLA_POSEIDON_UNROLLED");
+        int m = e ? atoi(e) : 0;  // profiles/r01m_poseidon_sweep.txt: the rolled body wins (40 KB of code for mode 2)
+        return (m >= 0 && m <= 2) ? m : 0;
+    }();
+    return v;
+}
 void permute_states(ola_ctx* ctx, uint64_t* d_states, size_t n) {
     if (!n) return;
     {
@@ -110,17 +121,16 @@ void hash_rows_colmajor(ola_ctx* ctx, const uint64_t* d_cols, size_t col_stride,
             int v = e ? atoi(e) : 5;
             return (v >= 4 && v <= 6) ? v : 5;
         }();
-        static const bool unrolled = [] {
-            const char* e = getenv("OLA_POSEIDON_UNROLLED");
-            return e && atoi(e) != 0;
-        }();
+        const int mode = poseidon_mode();
         const unsigned blocks = (unsigned)((nrows + 127) / 128);
         Launch lz(ctx, "poseidon_leaves");
 #define OLA_HR(M, U) hash_rows_kernel<false, M, U><<<blocks, 128, 0, ctx->stream>>>(d_cols, col_stride, nrows, ncols, d_digests)
-        if (unrolled) {
-            if (minb == 4) OLA_HR(4, true); else if (minb == 5) OLA_HR(5, true); else OLA_HR(6, true);
+        if (mode == 1) {
+            if (minb == 4) OLA_HR(4, 1); else if (minb == 5) OLA_HR(5, 1); else OLA_HR(6, 1);
+        } else if (mode == 2) {
+            if (minb == 4) OLA_HR(4, 2); else if (minb == 5) OLA_HR(5, 2); else OLA_HR(6, 2);
         } else {
-            if (minb == 4) OLA_HR(4, false); else if (minb == 5) OLA_HR(5, false); else OLA_HR(6, false);
+            if (minb == 4) OLA_HR(4, 0); else if (minb == 5) OLA_HR(5, 0); else OLA_HR(6, 0);
         }
 #undef OLA_HR
     }
@@ -131,7 +141,10 @@ void merkle_levels(ola_ctx* ctx, uint64_t* d_nodes, size_t nleaves, size_t stop)
     for (size_t first = nleaves / 2; first >= stop && first >= 1; first /= 2) {
         {
             Launch lz(ctx, "merkle_level");
-            merkle_level_kernel<<<(unsigned)((first + 127) / 128), 128, 0, ctx->stream>>>(d_nodes, first, first);
+            if (poseidon_mode() == 2)
+                merkle_level_kernel<2><<<(unsigned)((first + 127) / 128), 128, 0, ctx->stream>>>(d_nodes, first, first);
+            else
+                merkle_level_kernel<0><<<(unsigned)((first + 127) / 128), 128, 0, ctx->stream>>>(d_nodes, first, first);
         }
         check_launch("merkle_level_kernel");
         if (first == 1) break;

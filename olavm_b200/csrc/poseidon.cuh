@@ -76,10 +76,10 @@ __device__ __forceinline__ void mds_layer(uint64_t* s) {
             al += (uint64_t)lo[0] * 8u;
             ah += (uint64_t)hi[0] * 8u;
         }
-        // value = al + ah * 2^32  (al, ah < 2^42)
+        // value = al + ah * 2^32  (al, ah < 2^42): bits above 2^64 fit one limb
         uint64_t l128 = al + (ah << 32);
-        uint64_t h128 = (ah >> 32) + (l128 < al);
-        s[r] = gl::reduce128_lazy(l128, h128);
+        uint32_t h96 = (uint32_t)(ah >> 32) + (l128 < al);
+        s[r] = gl::reduce96_lazy(l128, h96);
     }
 }
 
@@ -138,8 +138,8 @@ __device__ __forceinline__ void full_round(uint64_t* s, int round_ctr) {
                 ah += (uint64_t)hi[0] * diag;
             }
             const uint64_t l128 = al + (ah << 32);
-            const uint64_t h128 = (ah >> 32) + (l128 < al);
-            nw[r] = gl::reduce128_lazy(l128, h128);
+            const uint32_t h96 = (uint32_t)(ah >> 32) + (l128 < al);
+            nw[r] = gl::reduce96_lazy(l128, h96);
         }
         uint32_t tl[4], th[4];
 #pragma unroll
@@ -193,8 +193,14 @@ __device__ __forceinline__ void partial_rounds(uint64_t* s) {
     for (int r = 0; r < 22; ++r) {
         s[0] = gl::add_lc(sbox7(s[0]), c_partial[r]);
         acc160 d;
-        acc_zero(d);
-        acc_mac(d, s[0], 25);  // MDS_MATRIX_CIRC[0] + MDS_MATRIX_DIAG[0]
+        {  // d = s[0] * 25  (MDS_MATRIX_CIRC[0] + MDS_MATRIX_DIAG[0]): two IMAD.WIDE, a 70-bit value
+            const uint64_t lo = (uint64_t)(uint32_t)s[0] * 25u, hi = (s[0] >> 32) * 25u;
+            const uint64_t mid = (lo >> 32) + (uint32_t)hi;  // < 2^33
+            d.w0 = (uint32_t)lo;
+            d.w1 = (uint32_t)mid;
+            d.w2 = (uint32_t)(hi >> 32) + (uint32_t)(mid >> 32);  // hi < 2^37: no overflow
+            d.w3 = d.w4 = 0;
+        }
 #pragma unroll
         for (int i = 1; i < 12; ++i) acc_mac(d, s[i], c_whats[r * 11 + i - 1]);
         uint64_t s0 = s[0];
@@ -204,12 +210,21 @@ __device__ __forceinline__ void partial_rounds(uint64_t* s) {
     }
 }
 
-// s: any u64 representatives in, CANONICAL representatives out
+// s: any u64 representatives in, CANONICAL representatives out.
+// STRAIGHT: the body of a full round is straight-line code (no rotating register file: ~2.9k fewer register moves per
+// permutation, ~1.8k of them IMAD.MOV on the binding fmaheavy pipe) while the round loops, the partial rounds and the
+// initial matrix stay rolled: 29 KB of code, the size the instruction cache was measured to sustain.
+template <bool STRAIGHT = false>
 __device__ __forceinline__ void permute(uint64_t* s) {
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
 #pragma unroll 1
-        for (int r = 0; r < 4; ++r) full_round(s, half * 26 + r);
+        for (int r = 0; r < 4; ++r) {
+            if (STRAIGHT)
+                full_round_unrolled(s, half * 26 + r);
+            else
+                full_round(s, half * 26 + r);
+        }
         if (half == 0) {
             partial_init(s);
             partial_rounds(s);

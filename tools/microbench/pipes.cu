@@ -24,12 +24,13 @@ __global__ void __launch_bounds__(1024, 1) k(uint32_t* out, uint32_t seed, long 
     for (int it = 0; it < ITER; ++it) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            if (KIND == 0) {  // IMAD.WIDE.U32 with 64-bit accumulate
-                asm volatile("{.reg .u64 t; mov.b64 t, {%0,%1}; mad.wide.u32 t, %2, %3, t; mov.b64 {%0,%1}, t;}" : "+r"(a[i]), "+r"(b[i]) : "r"(c[i]), "r"(d[i]));
+            // every operation consumes its own previous result, so nothing is loop-invariant
+            if (KIND == 0) {  // IMAD.WIDE.U32 with 64-bit accumulate: (b:a) = a * c + (b:a)
+                asm volatile("{.reg .u64 t; mov.b64 t, {%0,%1}; mad.wide.u32 t, %0, %2, t; mov.b64 {%0,%1}, t;}" : "+r"(a[i]), "+r"(b[i]) : "r"(c[i]));
             } else if (KIND == 1) {  // IMAD lo
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(a[i]) : "r"(c[i]), "r"(d[i]));
+                asm volatile("mad.lo.u32 %0, %0, %1, %0;" : "+r"(a[i]) : "r"(c[i]));
             } else if (KIND == 2) {  // IMAD.HI
-                asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(a[i]) : "r"(c[i]), "r"(d[i]));
+                asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(c[i]), "r"(d[i]));
             } else if (KIND == 3) {  // IADD3 + IADD3.X pair (64-bit add)
                 asm volatile("add.cc.u32 %0, %0, %2; addc.u32 %1, %1, %3;" : "+r"(a[i]), "+r"(b[i]) : "r"(c[i]), "r"(d[i]));
             } else if (KIND == 4) {  // LOP3
@@ -37,27 +38,31 @@ __global__ void __launch_bounds__(1024, 1) k(uint32_t* out, uint32_t seed, long 
             } else if (KIND == 5) {  // SHF
                 asm volatile("shf.l.wrap.b32 %0, %0, %1, 7;" : "+r"(a[i]) : "r"(c[i]));
             } else if (KIND == 6) {  // 1 IMAD.WIDE : 2 IADD3
-                asm volatile("{.reg .u64 t; mov.b64 t, {%0,%1}; mad.wide.u32 t, %2, %3, t; mov.b64 {%0,%1}, t;}" : "+r"(a[i]), "+r"(b[i]) : "r"(c[i]), "r"(d[i]));
+                asm volatile("{.reg .u64 t; mov.b64 t, {%0,%1}; mad.wide.u32 t, %0, %2, t; mov.b64 {%0,%1}, t;}" : "+r"(a[i]), "+r"(b[i]) : "r"(c[i]));
                 asm volatile("add.cc.u32 %0, %0, %2; addc.u32 %1, %1, %3;" : "+r"(c[i]), "+r"(d[i]) : "r"(a[i]), "r"(b[i]));
             } else if (KIND == 7) {  // 1 IMAD.WIDE : 4 IADD3
-                asm volatile("{.reg .u64 t; mov.b64 t, {%0,%1}; mad.wide.u32 t, %2, %3, t; mov.b64 {%0,%1}, t;}" : "+r"(a[i]), "+r"(b[i]) : "r"(c[i]), "r"(d[i]));
+                asm volatile("{.reg .u64 t; mov.b64 t, {%0,%1}; mad.wide.u32 t, %0, %2, t; mov.b64 {%0,%1}, t;}" : "+r"(a[i]), "+r"(b[i]) : "r"(c[i]));
                 asm volatile("add.cc.u32 %0, %0, %2; addc.u32 %1, %1, %3;" : "+r"(c[i]), "+r"(d[i]) : "r"(a[i]), "r"(b[i]));
                 asm volatile("add.cc.u32 %0, %0, %2; addc.u32 %1, %1, %3;" : "+r"(c[i]), "+r"(d[i]) : "r"(b[i]), "r"(a[i]));
-            } else if (KIND == 8) {  // 1 IMAD lo : 1 IADD3
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(a[i]) : "r"(c[i]), "r"(d[i]));
+            } else if (KIND == 8) {  // 1 IMAD : 1 IADD3
+                asm volatile("mad.lo.u32 %0, %0, %1, %0;" : "+r"(a[i]) : "r"(c[i]));
                 asm volatile("add.u32 %0, %0, %1;" : "+r"(b[i]) : "r"(a[i]));
-            } else if (KIND == 9) {  // 1 IMAD.WIDE : 1 IMAD lo : 2 IADD3
-                asm volatile("{.reg .u64 t; mov.b64 t, {%0,%1}; mad.wide.u32 t, %2, %3, t; mov.b64 {%0,%1}, t;}" : "+r"(a[i]), "+r"(b[i]) : "r"(c[i]), "r"(d[i]));
+            } else if (KIND == 9) {  // 1 IMAD.WIDE : 1 IMAD : 2 IADD3
+                asm volatile("{.reg .u64 t; mov.b64 t, {%0,%1}; mad.wide.u32 t, %0, %2, t; mov.b64 {%0,%1}, t;}" : "+r"(a[i]), "+r"(b[i]) : "r"(c[i]));
                 asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c[i]) : "r"(a[i]), "r"(d[i]));
                 asm volatile("add.cc.u32 %0, %0, %2; addc.u32 %1, %1, %3;" : "+r"(c[i]), "+r"(d[i]) : "r"(a[i]), "r"(b[i]));
-            } else if (KIND == 10) {  // mul.wide.u16-style: IMAD with 16-bit operands (plain IMAD lo, for reference)
-                asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(a[i]) : "r"(c[i]), "r"(d[i]));
-            } else if (KIND == 11) {  // IMAD.WIDE.U32 without accumulate (mul.wide)
-                asm volatile("{.reg .u64 t; mul.wide.u32 t, %2, %3; mov.b64 {%0,%1}, t;}" : "=r"(a[i]), "=r"(b[i]) : "r"(c[i]), "r"(d[i]));
+            } else if (KIND == 10) {  // IMUL lo (IMAD with RZ addend)
+                asm volatile("mul.lo.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(c[i]));
+            } else if (KIND == 11) {  // IMAD.WIDE.U32 without accumulate: (b:a) = a * c
+                asm volatile("{.reg .u64 t; mul.wide.u32 t, %0, %2; mov.b64 {%0,%1}, t;}" : "+r"(a[i]), "+r"(b[i]) : "r"(c[i]));
             } else if (KIND == 12) {  // PRMT
-                asm volatile("prmt.b32 %0, %0, %1, 0x3210;" : "+r"(a[i]) : "r"(c[i]));
+                asm volatile("prmt.b32 %0, %0, %1, 0x2103;" : "+r"(a[i]) : "r"(c[i]));
             } else if (KIND == 13) {  // ISETP + SEL
                 asm volatile("{.reg .pred p; setp.lt.u32 p, %0, %1; selp.u32 %0, %1, %2, p;}" : "+r"(a[i]) : "r"(c[i]), "r"(d[i]));
+            } else if (KIND == 14) {  // IMAD.X-style: add with carry-in only
+                asm volatile("add.cc.u32 %0, %0, %2; addc.u32 %1, %1, 0;" : "+r"(a[i]), "+r"(b[i]) : "r"(c[i]));
+            } else if (KIND == 15) {  // MOV chain (register rotation)
+                asm volatile("{.reg .u32 t; mov.u32 t, %0; mov.u32 %0, %1; mov.u32 %1, %2; mov.u32 %2, t;}" : "+r"(a[i]), "+r"(b[i]), "+r"(c[i]));
             }
         }
     }
@@ -84,9 +89,11 @@ void run(const char* name, int ops_per_inner, uint32_t* out, long long* cyc, int
     cudaEventElapsedTime(&ms, e0, e1);
     long long h[8];
     cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
-    // 32 warps per SM = 8 per SMSP
-    double warp_instr_per_smsp = 8.0 * ITER * 8 * ops_per_inner;
-    printf("%-44s cycles=%9lld  warp-instr/cycle/SMSP=%.3f  (%.3f ms)\n", name, h[0], warp_instr_per_smsp / (double)h[0], ms);
+    // 32 warps per SM = 8 per SMSP; ptxas rewrites the PTX (splits accumulates, converts adds to IMAD.X ...), so the
+    // instruction mix of each loop body is read from cuobjdump (tools/microbench/pipes_report.py) and combined with the
+    // cycles per loop iteration printed here
+    (void)ops_per_inner;
+    printf("KIND %2d %-40s cycles/iteration(8 warps per SMSP)=%8.2f  (%.3f ms)\n", KIND, name, (double)h[0] / ITER, ms);
 }
 
 int main() {
@@ -111,5 +118,7 @@ int main() {
     run<7>("1 IMAD.WIDE : 4 IADD3", 5, out, cyc, nsm);
     run<8>("1 IMAD : 1 IADD3", 2, out, cyc, nsm);
     run<9>("1 IMAD.WIDE : 1 IMAD : 2 IADD3", 4, out, cyc, nsm);
+    run<14>("IADD3 + carry-only add", 2, out, cyc, nsm);
+    run<15>("3 MOV (rotation)", 3, out, cyc, nsm);
     return 0;
 }

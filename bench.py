@@ -171,7 +171,7 @@ def prove_all_tables(ctx, log_n, world=1, rank=0, odist=None, device=None):
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         assert bool((lo == hi).all()), "ranks returned different proofs"
-    top = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:8]
+    top = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:20]
     rows = sum(1 << lg for lg in logs)
     if rank != 0:
         return None

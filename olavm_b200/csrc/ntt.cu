@@ -481,6 +481,13 @@ static int tune_variant() {
     }();
     return v;
 }
+static bool tune_contig_c4() {
+    static bool v = [] {
+        const char* e = getenv("OLA_NTT_CONTIG_C4");
+        return !(e && atoi(e) == 0);  // default on: 14.7 vs 15.7 ms on the 200 x 2^20 LDE (profiles/r01m_ntt_tile_sweeps.txt)
+    }();
+    return v;
+}
 template <typename G>
 static void tile_optin(int max_optin) {
     OLA_CUDA(cudaFuncSetAttribute(tile::tile_strided<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
@@ -501,6 +508,7 @@ using T10 = tile::Cfg<10, 8>;
 using T10v1 = tile::Cfg<10, 8, 2, 2, 5, 3>;
 using T10v2 = tile::Cfg<10, 8, 2, 1, 4, 2>;
 using T10v3 = tile::Cfg<10, 8, 1, 1, 4, 2>;
+using T10c4 = tile::Cfg<10, 4, 2, 1, 4, 4>;  // contiguous pass, 4-column tiles: 43 KB, 4-5 CTAs / SM (OLA_NTT_CONTIG_C4=0 disables)
 using T11 = tile::Cfg<11, 4>;
 using T11v2 = tile::Cfg<11, 4, 2, 1, 4, 2>;
 using T11v3 = tile::Cfg<11, 4, 1, 1, 4, 2>;
@@ -513,6 +521,7 @@ static void tile_optin_all(int max_optin) {
     tile_optin<T10v1>(max_optin);
     tile_optin<T10v2>(max_optin);
     tile_optin<T10v3>(max_optin);
+    tile_optin_contig<T10c4>(max_optin);
     tile_optin<T11>(max_optin);
     tile_optin<T11v2>(max_optin);
     tile_optin<T11v3>(max_optin);
@@ -604,7 +613,8 @@ static void tile_contig_dispatch(ola_ctx* ctx, const PassArgs& a, size_t ncols, 
         case 8: tile_contig_launch<T8, GS>(ctx, a, ncols, ncosets); break;
         case 9: tile_contig_launch<T9, GS>(ctx, a, ncols, ncosets); break;
         case 10:
-            if (v == 1) tile_contig_launch<T10v1, GS>(ctx, a, ncols, ncosets);
+            if (tune_contig_c4()) tile_contig_launch<T10c4, GS>(ctx, a, ncols, ncosets);
+            else if (v == 1) tile_contig_launch<T10v1, GS>(ctx, a, ncols, ncosets);
             else if (v == 2) tile_contig_launch<T10v2, GS>(ctx, a, ncols, ncosets);
             else if (v == 3) tile_contig_launch<T10v3, GS>(ctx, a, ncols, ncosets);
             else tile_contig_launch<T10, GS>(ctx, a, ncols, ncosets);

@@ -44,7 +44,8 @@ __global__ void __launch_bounds__(128, 5) permute_kernel(uint64_t* states, size_
 }
 
 // hash_no_pad over one row; ROWMAJOR: element (r, c) at base[r*ncols + c]; else at base[c*col_stride + r]
-// MODE: 0 rolled permutation, 1 fully straight-line (A/B only), 2 straight-line full rounds inside rolled round loops
+// MODE: 0 rolled permutation, 1 fully straight-line (A/B only), 2 straight-line full rounds inside rolled round loops,
+// 3 rolled S-box layer + straight-line 22-bit-limb MDS
 template <bool ROWMAJOR, int MINB, int MODE = 0>
 __global__ void __launch_bounds__(128, MINB) hash_rows_kernel(const uint64_t* __restrict__ base, size_t col_stride, size_t nrows,
                                                        size_t ncols, uint64_t* __restrict__ digests) {
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(128, MINB) hash_rows_kernel(const uint64_t* __
         if (MODE == 1)
             permute_unrolled(s);
         else
-            permute<MODE == 2>(s);
+            permute<MODE>(s);
     }
     ulonglong2* d = reinterpret_cast<ulonglong2*>(digests + 4 * r);
     d[0] = make_ulonglong2(s[0], s[1]);
@@ -80,18 +81,18 @@ __global__ void __launch_bounds__(128, 5) merkle_level_kernel(uint64_t* nodes, s
     const ulonglong2* ch = reinterpret_cast<const ulonglong2*>(nodes + 8 * i);
     ulonglong2 a = ch[0], b = ch[1], c = ch[2], d = ch[3];
     uint64_t s[12] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y, 0, 0, 0, 0};
-    permute<MODE == 2>(s);
+    permute<MODE>(s);
     ulonglong2* o = reinterpret_cast<ulonglong2*>(nodes + 4 * i);
     o[0] = make_ulonglong2(s[0], s[1]);
     o[1] = make_ulonglong2(s[2], s[3]);
 }
 
-// body form of the permutation (OLA_POSEIDON_UNROLLED: 0 rolled, 1 straight-line, 2 straight-line full rounds)
+// body form of the permutation (OLA_POSEIDON_UNROLLED: 0 rolled, 1 straight-line, 2 straight-line full rounds, 3 limb MDS)
 static int poseidon_mode() {
     static const int v = [] {
         const char* e = getenv("OLA_POSEIDON_UNROLLED");
-        int m = e ? atoi(e) : 0;  // profiles/r01m_poseidon_sweep.txt: the rolled body wins (40 KB of code for mode 2)
-        return (m >= 0 && m <= 2) ? m : 0;
+        int m = e ? atoi(e) : 3;  // profiles/r01m_poseidon_sweep.txt: 3 (limb MDS) 116 ms, 0 (rolled) 126 ms, 2 (40 KB of code) 129 ms
+        return (m >= 0 && m <= 3) ? m : 3;
     }();
     return v;
 }
@@ -129,6 +130,8 @@ void hash_rows_colmajor(ola_ctx* ctx, const uint64_t* d_cols, size_t col_stride,
             if (minb == 4) OLA_HR(4, 1); else if (minb == 5) OLA_HR(5, 1); else OLA_HR(6, 1);
         } else if (mode == 2) {
             if (minb == 4) OLA_HR(4, 2); else if (minb == 5) OLA_HR(5, 2); else OLA_HR(6, 2);
+        } else if (mode == 3) {
+            if (minb == 4) OLA_HR(4, 3); else if (minb == 5) OLA_HR(5, 3); else OLA_HR(6, 3);
         } else {
             if (minb == 4) OLA_HR(4, 0); else if (minb == 5) OLA_HR(5, 0); else OLA_HR(6, 0);
         }
@@ -143,6 +146,8 @@ void merkle_levels(ola_ctx* ctx, uint64_t* d_nodes, size_t nleaves, size_t stop)
             Launch lz(ctx, "merkle_level");
             if (poseidon_mode() == 2)
                 merkle_level_kernel<2><<<(unsigned)((first + 127) / 128), 128, 0, ctx->stream>>>(d_nodes, first, first);
+            else if (poseidon_mode() == 3)
+                merkle_level_kernel<3><<<(unsigned)((first + 127) / 128), 128, 0, ctx->stream>>>(d_nodes, first, first);
             else
                 merkle_level_kernel<0><<<(unsigned)((first + 127) / 128), 128, 0, ctx->stream>>>(d_nodes, first, first);
         }

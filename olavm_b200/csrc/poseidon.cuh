@@ -50,7 +50,7 @@ __device__ __forceinline__ uint64_t acc_reduce(const acc160& a) {
 
 // x^7 on lazy representatives
 __device__ __forceinline__ uint64_t sbox7(uint64_t x) {
-    uint64_t x2 = gl::mul_lazy(x, x), x4 = gl::mul_lazy(x2, x2), x3 = gl::mul_lazy(x, x2);
+    uint64_t x2 = gl::sqr_lazy(x), x4 = gl::sqr_lazy(x2), x3 = gl::mul_lazy(x, x2);
     return gl::mul_lazy(x3, x4);
 }
 
@@ -164,6 +164,55 @@ __device__ __forceinline__ void full_round(uint64_t* s, int round_ctr) {
     for (int i = 0; i < 12; ++i) s[i] = o[i];
 }
 
+// MDS layer on 22-bit limbs, straight-line.  Every circulant coefficient is <= 41 and their sum (with the diagonal 8)
+// is 264 < 2^9, so a 22-bit limb times the coefficients, summed over a row, stays below 2^31: the 3 x 144 products are
+// plain 32-bit IMADs (2 cycles of the fmaheavy pipe each) instead of 2 x 144 IMAD.WIDE (4 cycles each), and nothing
+// has to rotate.  The limb split and the recombination are shifts and adds on the ALU pipe, which has the headroom
+// (profiles/r01m_poseidon_pipe_model.md).  lazy in, lazy out.
+__device__ __forceinline__ void mds_layer_limbs(uint64_t* s) {
+    constexpr uint32_t C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+    uint32_t l0[12], l1[12], l2[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        l0[i] = (uint32_t)s[i] & 0x3FFFFFu;
+        l1[i] = (uint32_t)(s[i] >> 22) & 0x3FFFFFu;
+        l2[i] = (uint32_t)(s[i] >> 44);
+    }
+#pragma unroll
+    for (int r = 0; r < 12; ++r) {
+        uint32_t a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            const uint32_t c = C[i] + ((r == 0 && i == 0) ? 8u : 0u);  // MDS_MATRIX_DIAG[0] = 8
+            a0 += l0[(i + r) % 12] * c;
+            a1 += l1[(i + r) % 12] * c;
+            a2 += l2[(i + r) % 12] * c;
+        }
+        // value = a0 + a1 * 2^22 + a2 * 2^44  (a0, a1 < 2^31, a2 < 2^29): 73 bits
+        const uint64_t t = (uint64_t)a0 + ((uint64_t)a1 << 22);
+        const uint64_t lo = t + ((uint64_t)a2 << 44);
+        const uint32_t x2 = (a2 >> 20) + (lo < t);
+        s[r] = gl::reduce96_lazy(lo, x2);
+    }
+}
+
+// rolled S-box layer (as full_round) + straight-line limb MDS
+__device__ __forceinline__ void full_round_limbs(uint64_t* s, int round_ctr) {
+#pragma unroll 1
+    for (int it = 0; it < 4; ++it) {
+        const int k = round_ctr * 12 + it * 3;
+        const uint64_t a = sbox7(gl::add_lc(s[0], c_round[k]));
+        const uint64_t b = sbox7(gl::add_lc(s[1], c_round[k + 1]));
+        const uint64_t c = sbox7(gl::add_lc(s[2], c_round[k + 2]));
+#pragma unroll
+        for (int j = 0; j < 9; ++j) s[j] = s[j + 3];
+        s[9] = a;
+        s[10] = b;
+        s[11] = c;
+    }
+    mds_layer_limbs(s);
+}
+
 // partial_first_constant_layer + mds_partial_layer_init (poseidon.rs:303-313, :332-358), one output column per
 // iteration; results queue up in q
 __device__ __forceinline__ void partial_init(uint64_t* s) {
@@ -211,17 +260,18 @@ __device__ __forceinline__ void partial_rounds(uint64_t* s) {
 }
 
 // s: any u64 representatives in, CANONICAL representatives out.
-// STRAIGHT: the body of a full round is straight-line code (no rotating register file: ~2.9k fewer register moves per
-// permutation, ~1.8k of them IMAD.MOV on the binding fmaheavy pipe) while the round loops, the partial rounds and the
-// initial matrix stay rolled: 29 KB of code, the size the instruction cache was measured to sustain.
-template <bool STRAIGHT = false>
+// FORM 0: rolled S-box layer and rolled circulant MDS on 32-bit halves; 2: straight-line full rounds (A/B only: 40 KB
+// of code, slower); 3: rolled S-box layer + straight-line MDS on 22-bit limbs.
+template <int FORM = 0>
 __device__ __forceinline__ void permute(uint64_t* s) {
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
 #pragma unroll 1
         for (int r = 0; r < 4; ++r) {
-            if (STRAIGHT)
+            if (FORM == 2)
                 full_round_unrolled(s, half * 26 + r);
+            else if (FORM == 3)
+                full_round_limbs(s, half * 26 + r);
             else
                 full_round(s, half * 26 + r);
         }

@@ -323,10 +323,15 @@ static void launch_quotient(ola_ctx* ctx, int table_id, QuotArgs a) {
     Launch lz(ctx, "quotient");
     switch (table_id) {
         case T_CPU: {
-            // resident CTAs per SM for the widest body (3: 168 registers, no spills; 4: 128 registers + spills), tuned on hardware
-            static const int minb = [] { const char* e = getenv("OLA_QUOT_MINB"); return e ? atoi(e) : 3; }();
+            // resident CTAs per SM for the widest body (register cap 255 / 168 / 128 / 102 / 80), tuned on hardware:
+            // profiles/r01m_quotient_minb_sweep.txt (2^20 rows: 89.9 / 64.1 / 51.0 ms for 2 / 3 / 4)
+            static const int minb = [] { const char* e = getenv("OLA_QUOT_MINB"); return e ? atoi(e) : 4; }();
             if (minb == 4)
                 quotient_kernel<air::Cpu, 4><<<blocks, threads, 0, ctx->stream>>>(a);
+            else if (minb == 5)
+                quotient_kernel<air::Cpu, 5><<<blocks, threads, 0, ctx->stream>>>(a);
+            else if (minb == 6)
+                quotient_kernel<air::Cpu, 6><<<blocks, threads, 0, ctx->stream>>>(a);
             else if (minb == 2)
                 quotient_kernel<air::Cpu, 2><<<blocks, threads, 0, ctx->stream>>>(a);
             else

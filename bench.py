@@ -279,7 +279,7 @@ def run_reference(args):
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    _emit(json.dumps(line))
 
 
 def main():
@@ -420,11 +420,22 @@ def main():
         extra["prove_all_tables"] = prove_all_tables(ctx, args.prove_log_n, world, rank, odist, torch.device("cuda", local_rank))
     if rank == 0:
         line.update(extra)
-        print(json.dumps(line))
+        _emit(json.dumps(line))
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+def _emit(line):
+    """The contract is ONE JSON line on stdout: libraries that print to fd 1 (NCCL's version banner) are sent to stderr
+    for the whole run (see __main__) and the result line goes to the saved descriptor."""
+    os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
 if __name__ == "__main__":
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     main()

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(QL_THREADS) ql_emit_kernel(const uint64_t* __r
 }
 
 // ---- FRI layer leaves: leaf i = flatten(values[16 i .. 16 i + 16)) -> digest (hash_no_pad of 32 elements) ----
-__global__ void __launch_bounds__(128) fri_leaves_kernel(const uint64_t* __restrict__ vals /* [2][len] */, size_t len, int arity, uint64_t* __restrict__ digests) {
+__global__ void __launch_bounds__(128, 5) fri_leaves_kernel(const uint64_t* __restrict__ vals /* [2][len] */, size_t len, int arity, uint64_t* __restrict__ digests) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t nleaves = len / arity;
     if (i >= nleaves) return;
@@ -194,8 +194,11 @@ __global__ void fold_kernel(const uint64_t* __restrict__ in /* [2][m] */, size_t
 }
 
 // ---- proof of work: smallest nonce with hash_no_pad(h0..h3, nonce)[0] < 2^(64 - pow_bits) (fri/prover.rs:126-148) ----
-__global__ void __launch_bounds__(128) pow_kernel(uint64_t h0, uint64_t h1, uint64_t h2, uint64_t h3, uint64_t base, unsigned long long* best) {
+__global__ void __launch_bounds__(128, 5) pow_kernel(uint64_t h0, uint64_t h1, uint64_t h2, uint64_t h3, uint64_t base, unsigned long long* best) {
     uint64_t nonce = base + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // CTAs are dispatched in index order: once an earlier one has recorded a valid nonce, the rest of the window (the
+    // expected first hit is ~2^16 of its 2^20 nonces) has nothing smaller to offer and retires without hashing
+    if (*reinterpret_cast<volatile unsigned long long*>(best) < (unsigned long long)nonce) return;
     uint64_t s[12] = {h0, h1, h2, h3, nonce, 0, 0, 0, 0, 0, 0, 0};
     poseidon::permute(s);
     if ((s[0] >> (64 - Config::pow_bits)) == 0) atomicMin(best, (unsigned long long)nonce);

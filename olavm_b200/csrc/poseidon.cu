@@ -108,7 +108,7 @@ void hash_rows_rowmajor(ola_ctx* ctx, const uint64_t* d_rows, size_t nrows, size
     if (!nrows) return;
     {
         Launch lz(ctx, "poseidon_leaves_rowmajor");
-        hash_rows_kernel<true, 4><<<(unsigned)((nrows + 127) / 128), 128, 0, ctx->stream>>>(d_rows, 0, nrows, ncols, d_digests);
+        hash_rows_kernel<true, 4, 3><<<(unsigned)((nrows + 127) / 128), 128, 0, ctx->stream>>>(d_rows, 0, nrows, ncols, d_digests);
     }
     check_launch("hash_rows_kernel<row>");
 }

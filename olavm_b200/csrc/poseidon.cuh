@@ -262,7 +262,7 @@ __device__ __forceinline__ void partial_rounds(uint64_t* s) {
 // s: any u64 representatives in, CANONICAL representatives out.
 // FORM 0: rolled S-box layer and rolled circulant MDS on 32-bit halves; 2: straight-line full rounds (A/B only: 40 KB
 // of code, slower); 3: rolled S-box layer + straight-line MDS on 22-bit limbs.
-template <int FORM = 0>
+template <int FORM = 3>
 __device__ __forceinline__ void permute(uint64_t* s) {
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {

@@ -79,6 +79,34 @@ def test_cpu_table_valid_padding_trace(ctx, orc):
     assert e.value.code == -5  # OLA_ERR_QUOTIENT_DEGREE
 
 
+def test_cpu_table_real_trace(ctx, orc):
+    """A real CPU trace (tests/tracegen.py::cpu_vm_trace: rows produced the way the reference executor and
+    generate_cpu_trace produce them, 10 opcodes, a taken and a fall-through branch, padding): the GPU prover's quotient
+    passes the degree check, the proof bytes equal the oracle's and the restated verifier accepts; one wrong register
+    is rejected with OLA_ERR_QUOTIENT_DEGREE."""
+    cpu_t, steps = tracegen.cpu_vm_trace(tracegen.fib_program(10), 7)
+    cmp_t = tracegen.cmp_trace([], 4)
+    rc_t = tracegen.rangecheck_trace([])
+    got = olavm_b200.prove_with_traces(ctx, [CPU, CMP, RC], [cpu_t, cmp_t, rc_t])
+    assert got == orc.stark_prove([CPU, CMP, RC], [cpu_t, cmp_t, rc_t])
+    ok, msg = orc.stark_verify([CPU, CMP, RC], got)
+    assert ok, msg
+    ok, msg = olavm_b200.verify_proof([CPU, CMP, RC], got)
+    assert ok, msg
+    bad = cpu_t.copy()
+    i_add = next(i for i, s in enumerate(steps) if s["op"] == "add")
+    bad[16 + 3, i_add + 1] = (int(bad[16 + 3, i_add + 1]) + 1) % tracegen.P
+    with pytest.raises(olavm_b200.OlaError, match="Quotient has failed") as e:
+        olavm_b200.prove_with_traces(ctx, [CPU, CMP, RC], [bad, cmp_t, rc_t])
+    assert e.value.code == -5
+    # a longer run of the same program at a larger table size (2^12 rows, 2053 executed steps)
+    big, big_steps = tracegen.cpu_vm_trace(tracegen.fib_program(340), 12)
+    assert len(big_steps) > 2000
+    got = olavm_b200.prove_with_traces(ctx, [CPU, CMP, RC], [big, cmp_t, rc_t])
+    ok, msg = orc.stark_verify([CPU, CMP, RC], got)
+    assert ok, msg
+
+
 @pytest.mark.parametrize("log_n", [4, 8, 11])
 def test_cpu_table_pipeline_parity(ctx, orc, log_n):
     """The 94-column CPU table with its 39 CTL instances (78 Z columns, 12 quotient chunks) on random columns with

@@ -485,3 +485,182 @@ def hash_system_valid(orc, rng, beta=0x1234567890ABCDEF % P):
     prog = program_valid_trace(rng, 5, beta, prog_rows=lines, n_exec=7)
     ids = [5, 6, 7, 10, 11]
     return ids, [ps, pch, st, prog, pc], [0, 0, 0, beta, 0]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# A small Ola VM for the CPU table: real (non-padding) rows produced the way the reference produces them.
+#   executor/src/lib.rs   Process::execute :2074-2310 and the per-opcode handlers :572-814 (mov/not, eq/neq, assert,
+#                         cjmp, jmp, add/mul), execute_inst_end :1186-1262, Process::new :249-283
+#   core/src/program/binary_program.rs:100-192  instruction word: opcode one-hot (bits 6..31), dst / op1 / op0 register
+#                         one-hots at bits 32+i / 42+i / 52+i, bit 62 = "op1 is an immediate" (the immediate is the next word)
+#   circuits/src/generation/cpu.rs:11-218       Step -> row, padding
+# Only register-to-register opcodes are modelled (no memory, storage, tape or builtin lookups), which is what a CPU-only
+# proof (or CPU + lookup-free Cmp / RangeCheck) can check; the rows do NOT come from the AIR transcription, so proving
+# them with the quotient-degree check on tests the transcription against the reference's own trace semantics.
+# ---------------------------------------------------------------------------------------------------------------------
+OPCODE_SHIFT = {"add": 31, "mul": 30, "eq": 29, "assert": 28, "mov": 27, "jmp": 26, "cjmp": 25, "end": 20, "not": 15, "neq": 14}
+CPU_SELECTOR_COL = {"add": 66, "mul": 66, "eq": 66, "assert": 66, "neq": 66, "mov": 67, "jmp": 68, "cjmp": 69, "end": 74, "not": 77}
+
+
+def _finv(x):
+    return pow(x, P - 2, P)
+
+
+def _reg(s):
+    assert isinstance(s, str) and s[0] == "r" and 0 <= int(s[1:]) < 10, s
+    return int(s[1:])
+
+
+def ola_encode(ins):
+    """(op, operands...) -> [instruction word] or [instruction word, immediate].  Operand order as in the assembly text:
+    add/mul/eq/neq dst op0 op1 | mov/not dst op1 | cjmp op0 op1 | jmp op1 | assert op1 | end."""
+    op = ins[0]
+    word = 1 << OPCODE_SHIFT[op]
+    dst = op0 = op1 = None
+    if op in ("add", "mul", "eq", "neq"):
+        dst, op0, op1 = ins[1], ins[2], ins[3]
+    elif op in ("mov", "not"):
+        dst, op1 = ins[1], ins[2]
+    elif op == "cjmp":
+        op0, op1 = ins[1], ins[2]
+    elif op in ("jmp", "assert"):
+        op1 = ins[1]
+    else:
+        assert op == "end"
+    imm = None
+    if dst is not None:
+        word |= 1 << (32 + _reg(dst))
+    if op0 is not None:
+        word |= 1 << (52 + _reg(op0))
+    if op1 is not None:
+        if isinstance(op1, str):
+            word |= 1 << (42 + _reg(op1))
+        else:
+            word |= 1 << 62
+            imm = int(op1) % P
+    return [word] if imm is None else [word, imm]
+
+
+def cpu_vm_trace(program, log_n, max_steps=1 << 20):
+    """Run `program` (a list of instruction tuples, jump targets = word addresses) and return the [94][2^log_n] CPU table."""
+    words, at_pc = [], {}
+    for ins in program:
+        enc = ola_encode(ins)
+        at_pc[len(words)] = (ins, enc)
+        words += enc
+    regs = [0] * 10
+    pc, clk, steps = 0, 0, []
+    while True:
+        assert pc in at_pc, f"pc {pc} is not an instruction boundary"
+        ins, enc = at_pc[pc]
+        op, step = ins[0], len(enc)
+        row = {"clk": clk, "pc": pc, "regs": list(regs), "inst": enc[0], "imm": enc[1] if step == 2 else 0,
+               "op1_imm": 1 if step == 2 else 0, "opcode": 1 << OPCODE_SHIFT[op], "op": op,
+               "op0": 0, "op1": 0, "dst": 0, "aux0": 0, "aux1": 0, "s_op0": None, "s_op1": None, "s_dst": None}
+
+        def val(x):  # get_index_value (lib.rs:297-320)
+            if isinstance(x, str):
+                row["s_op1"] = _reg(x)
+                return regs[_reg(x)]
+            return int(x) % P
+
+        if op == "end":
+            steps.append(row)
+            break
+        if op in ("mov", "not"):
+            v = val(ins[2])
+            row["op1"] = v
+            regs[_reg(ins[1])] = v if op == "mov" else (P - 1 - v) % P
+            row["dst"], row["s_dst"] = regs[_reg(ins[1])], _reg(ins[1])
+            pc += step
+        elif op in ("add", "mul", "eq", "neq"):
+            a = regs[_reg(ins[2])]
+            row["op0"], row["s_op0"] = a, _reg(ins[2])
+            b = val(ins[3])
+            row["op1"] = b
+            if op == "add":
+                r = (a + b) % P
+            elif op == "mul":
+                r = (a * b) % P
+            else:
+                d = (a - b) % P
+                row["aux0"] = _finv(d) if d else 0
+                r = int(a == b) if op == "eq" else int(a != b)
+            regs[_reg(ins[1])] = r
+            row["dst"], row["s_dst"] = r, _reg(ins[1])
+            pc += step
+        elif op == "assert":
+            v = val(ins[1])
+            assert v == 1, "assert failed in the VM"
+            row["op1"] = v
+            pc += step
+        elif op == "cjmp":
+            c = regs[_reg(ins[1])]
+            row["op0"], row["s_op0"] = c, _reg(ins[1])
+            t = val(ins[2])
+            row["op1"] = t
+            pc = t if c == 1 else pc + step
+        elif op == "jmp":
+            t = val(ins[1])
+            row["op1"] = t
+            pc = t
+        else:
+            raise ValueError(op)
+        steps.append(row)
+        clk += 1
+        assert len(steps) < max_steps, "program does not terminate"
+    n = 1 << log_n
+    assert len(steps) <= n, f"{len(steps)} steps do not fit 2^{log_n} rows"
+    t = np.zeros((94, n), dtype=np.uint64)
+    for i, s in enumerate(steps):  # generation/cpu.rs:62-178
+        t[12, i], t[13, i] = s["clk"], s["pc"]
+        t[16:26, i] = s["regs"]
+        t[26, i], t[27, i], t[28, i], t[29, i] = s["inst"], s["op1_imm"], s["opcode"], s["imm"]
+        t[30, i], t[31, i], t[32, i], t[33, i], t[34, i] = s["op0"], s["op1"], s["dst"], s["aux0"], s["aux1"]
+        if s["s_op0"] is not None:
+            t[36 + s["s_op0"], i] = 1
+        if s["s_op1"] is not None:
+            t[46 + s["s_op1"], i] = 1
+        if s["s_dst"] is not None:
+            t[56 + s["s_dst"], i] = 1
+        t[CPU_SELECTOR_COL[s["op"]], i] = 1
+        t[85, i] = 1                                  # is_entry_sc: env_idx == 0
+        t[86, i] = 1                                  # is_next_line_diff_inst: ext_length (0) == ext_cnt (0)
+        t[87, i] = 0 if s["op"] == "end" else 1        # is_next_line_same_tx
+        t[92, i] = s["op1_imm"]                        # filter_looking_prog_imm (no mload / mstore here)
+    k = len(steps)
+    if k != n:  # padding, generation/cpu.rs:180-208
+        t[26, k:] = t[26, k - 1]
+        t[28, k:] = 1 << 20
+        t[74, k:] = 1
+        t[85, k:] = 1
+        t[86, k:] = 1
+        t[87, k:] = 0
+        t[93, k:] = 1
+    return t, steps
+
+
+def fib_program(n_iter):
+    """r0, r1 = fib pair; r2 = loop counter; loops n_iter times, checks the result bookkeeping with eq / assert / neq / not."""
+    return [
+        ("mov", "r0", 0),            # pc 0
+        ("mov", "r1", 1),            # pc 2
+        ("mov", "r2", 0),            # pc 4
+        # loop (pc 6):
+        ("add", "r3", "r0", "r1"),   # pc 6
+        ("mov", "r0", "r1"),         # pc 7
+        ("mov", "r1", "r3"),         # pc 8
+        ("add", "r2", "r2", 1),      # pc 9
+        ("neq", "r4", "r2", n_iter),  # pc 11
+        ("cjmp", "r4", 6),           # pc 13
+        ("eq", "r5", "r2", n_iter),  # pc 15
+        ("assert", "r5"),            # pc 17
+        ("mul", "r6", "r1", "r1"),   # pc 18
+        ("not", "r7", "r6"),         # pc 19
+        ("add", "r8", "r7", "r6"),   # pc 20   r8 = p - 1
+        ("add", "r8", "r8", 1),      # pc 21   r8 = 0
+        ("eq", "r9", "r8", 0),       # pc 23
+        ("assert", "r9"),            # pc 25
+        ("jmp", 28),                 # pc 26
+        ("end",),                    # pc 28
+    ]

@@ -107,6 +107,26 @@ def test_cpu_table_real_trace(ctx, orc):
     assert ok, msg
 
 
+def test_cpu_cmp_rangecheck_real_program(ctx, orc):
+    """calls_program (mstore / mload / call / ret / gte / range + arithmetic) with the Cmp and RangeCheck rows the executor
+    would have inserted: real cpu->cmp, cmp->rangecheck and cpu->rangecheck lookups; GPU proof bytes equal the oracle's,
+    both verifiers accept."""
+    cpu_t, steps, cmp_pairs, rc_cmp, rc_cpu = tracegen.cpu_vm_trace(tracegen.calls_program(12), 9, want_side_tables=True)
+    cmp_t = tracegen.cmp_trace(cmp_pairs, 6)
+    rc_t = tracegen.rangecheck_trace(rc_cmp, cpu_vals=rc_cpu)
+    got = olavm_b200.prove_with_traces(ctx, [CPU, CMP, RC], [cpu_t, cmp_t, rc_t])
+    assert got == orc.stark_prove([CPU, CMP, RC], [cpu_t, cmp_t, rc_t])
+    ok, msg = orc.stark_verify([CPU, CMP, RC], got)
+    assert ok, msg
+    ok, msg = olavm_b200.verify_proof([CPU, CMP, RC], got)
+    assert ok, msg
+    # a Cmp row withheld: the proof is produced (each table is consistent) and both verifiers reject the lookup
+    short = olavm_b200.prove_with_traces(ctx, [CPU, CMP, RC], [cpu_t, tracegen.cmp_trace(cmp_pairs[:-1], 6),
+                                                               tracegen.rangecheck_trace(rc_cmp[:-1], cpu_vals=rc_cpu)])
+    assert not orc.stark_verify([CPU, CMP, RC], short)[0]
+    assert not olavm_b200.verify_proof([CPU, CMP, RC], short)[0]
+
+
 @pytest.mark.parametrize("log_n", [4, 8, 11])
 def test_cpu_table_pipeline_parity(ctx, orc, log_n):
     """The 94-column CPU table with its 39 CTL instances (78 Z columns, 12 quotient chunks) on random columns with

@@ -255,3 +255,58 @@ def test_real_cpu_trace_rejects_a_broken_cell(orc, case):
         b[26, 0] = int(b[26, 0]) ^ (1 << 33)
     with pytest.raises(orc.StarkError, match="Quotient has failed"):
         orc.stark_prove([CPU, CMP, RC], [b, cmp_t, rc_t])
+
+
+def _calls_system(n_iter=12, log_n=9):
+    cpu_t, steps, cmp_pairs, rc_cmp, rc_cpu = tracegen.cpu_vm_trace(tracegen.calls_program(n_iter), log_n, want_side_tables=True)
+    return cpu_t, steps, cmp_pairs, rc_cmp, rc_cpu
+
+
+def test_real_cpu_trace_with_memory_calls_and_builtin_lookups(orc):
+    """mstore / mload / call / ret / gte / range on top of the arithmetic set, with the Cmp and RangeCheck tables the
+    executor would have filled (insert_cmp / insert_rangecheck, lib.rs:1017-1030, :1157-1180): the three cross-table
+    lookups cpu->cmp, cmp->rangecheck and cpu->rangecheck carry real rows, the degree check is on, the verifier accepts;
+    withholding one looked row (a Cmp row, a RangeCheck row) is caught by the verifier's cross-table product check."""
+    cpu_t, steps, cmp_pairs, rc_cmp, rc_cpu = _calls_system()
+    assert {"mstore", "mload", "call", "ret", "gte", "range"} <= {s["op"] for s in steps}
+    assert len(cmp_pairs) == 24 and len(rc_cpu) == 13
+    cmp_t = tracegen.cmp_trace(cmp_pairs, 6)
+    rc_t = tracegen.rangecheck_trace(rc_cmp, cpu_vals=rc_cpu)
+    proof = orc.stark_prove([CPU, CMP, RC], [cpu_t, cmp_t, rc_t])
+    ok, msg = orc.stark_verify([CPU, CMP, RC], proof)
+    assert ok, msg
+    # the CPU looks up a comparison the Cmp table does not hold
+    proof = orc.stark_prove([CPU, CMP, RC], [cpu_t, tracegen.cmp_trace(cmp_pairs[:-1], 6), tracegen.rangecheck_trace(rc_cmp[:-1], cpu_vals=rc_cpu)])
+    ok, msg = orc.stark_verify([CPU, CMP, RC], proof)
+    assert not ok
+    # a range-checked register value the RangeCheck table does not hold
+    proof = orc.stark_prove([CPU, CMP, RC], [cpu_t, cmp_t, tracegen.rangecheck_trace(rc_cmp, cpu_vals=rc_cpu[:-1])])
+    ok, msg = orc.stark_verify([CPU, CMP, RC], proof)
+    assert not ok
+
+
+@pytest.mark.parametrize("case", ["mstore_address", "mload_value", "call_return_address", "ret_target", "ret_frame_pointer", "gte_result"])
+def test_real_cpu_trace_memory_and_call_rows_bind(orc, case):
+    cpu_t, steps, cmp_pairs, rc_cmp, rc_cpu = _calls_system()
+    cmp_t = tracegen.cmp_trace(cmp_pairs, 6)
+    rc_t = tracegen.rangecheck_trace(rc_cmp, cpu_vals=rc_cpu)
+    b = cpu_t.copy()
+    P = tracegen.P
+    if case == "mstore_address":
+        b[34, _first(steps, "mstore")] = 7                      # aux1 = op0 + op1
+    elif case == "mload_value":
+        i = _first(steps, "mload")
+        b[16 + 7, i + 1] = (int(b[16 + 7, i + 1]) + 1) % P     # loaded register differs from dst
+    elif case == "call_return_address":
+        b[32, _first(steps, "call")] = 13                       # dst = pc + 2
+    elif case == "ret_target":
+        i = _first(steps, "ret")
+        b[13, i + 1] = int(b[13, i + 1]) + 1                    # next pc = dst
+    elif case == "ret_frame_pointer":
+        i = _first(steps, "ret")
+        b[16 + 9, i + 1] = 99                                   # r9 = aux1
+    elif case == "gte_result":
+        i = _first(steps, "gte")
+        b[32, i] = b[16 + 4, i + 1] = 1 - int(b[32, i])         # the flipped bit is read by the following not / cjmp rows
+    with pytest.raises(orc.StarkError, match="Quotient has failed"):
+        orc.stark_prove([CPU, CMP, RC], [b, cmp_t, rc_t])

@@ -498,8 +498,10 @@ def hash_system_valid(orc, rng, beta=0x1234567890ABCDEF % P):
 # proof (or CPU + lookup-free Cmp / RangeCheck) can check; the rows do NOT come from the AIR transcription, so proving
 # them with the quotient-degree check on tests the transcription against the reference's own trace semantics.
 # ---------------------------------------------------------------------------------------------------------------------
-OPCODE_SHIFT = {"add": 31, "mul": 30, "eq": 29, "assert": 28, "mov": 27, "jmp": 26, "cjmp": 25, "end": 20, "not": 15, "neq": 14}
-CPU_SELECTOR_COL = {"add": 66, "mul": 66, "eq": 66, "assert": 66, "neq": 66, "mov": 67, "jmp": 68, "cjmp": 69, "end": 74, "not": 77}
+OPCODE_SHIFT = {"add": 31, "mul": 30, "eq": 29, "assert": 28, "mov": 27, "jmp": 26, "cjmp": 25, "call": 24, "ret": 23, "mload": 22,
+                "mstore": 21, "end": 20, "range": 19, "not": 15, "neq": 14, "gte": 13}
+CPU_SELECTOR_COL = {"add": 66, "mul": 66, "eq": 66, "assert": 66, "neq": 66, "mov": 67, "jmp": 68, "cjmp": 69, "call": 70, "ret": 71,
+                    "mload": 72, "mstore": 73, "end": 74, "range": 75, "not": 77, "gte": 78}
 
 
 def _finv(x):
@@ -513,20 +515,26 @@ def _reg(s):
 
 def ola_encode(ins):
     """(op, operands...) -> [instruction word] or [instruction word, immediate].  Operand order as in the assembly text:
-    add/mul/eq/neq dst op0 op1 | mov/not dst op1 | cjmp op0 op1 | jmp op1 | assert op1 | end."""
+    add/mul/eq/neq/gte dst op0 op1 | mov/not dst op1 | cjmp op0 op1 | jmp/call/assert/range op1 | ret | end |
+    mstore base offset value-reg, mload dst base offset: (anchor, offset, dst) = (op0 register, op1 immediate, dst register),
+    assembler/src/encoder.rs:123-213."""
     op = ins[0]
     word = 1 << OPCODE_SHIFT[op]
     dst = op0 = op1 = None
-    if op in ("add", "mul", "eq", "neq"):
+    if op in ("add", "mul", "eq", "neq", "gte"):
         dst, op0, op1 = ins[1], ins[2], ins[3]
     elif op in ("mov", "not"):
         dst, op1 = ins[1], ins[2]
     elif op == "cjmp":
         op0, op1 = ins[1], ins[2]
-    elif op in ("jmp", "assert"):
+    elif op in ("jmp", "assert", "call", "range"):
         op1 = ins[1]
+    elif op == "mstore":
+        op0, op1, dst = ins[1], int(ins[2]), ins[3]
+    elif op == "mload":
+        dst, op0, op1 = ins[1], ins[2], int(ins[3])
     else:
-        assert op == "end"
+        assert op in ("end", "ret")
     imm = None
     if dst is not None:
         word |= 1 << (32 + _reg(dst))
@@ -541,8 +549,11 @@ def ola_encode(ins):
     return [word] if imm is None else [word, imm]
 
 
-def cpu_vm_trace(program, log_n, max_steps=1 << 20):
-    """Run `program` (a list of instruction tuples, jump targets = word addresses) and return the [94][2^log_n] CPU table."""
+def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False):
+    """Run `program` (a list of instruction tuples, jump targets = word addresses) and return the [94][2^log_n] CPU table
+    and the executed steps; with want_side_tables also the (op0, op1) pairs of the gte rows (Cmp table), their
+    |op0 - op1| (RangeCheck rows looked by Cmp) and the operands of the range rows (RangeCheck rows looked by the CPU)."""
+    cmp_pairs, rc_cmp, rc_cpu, mem = [], [], [], {}
     words, at_pc = [], {}
     for ins in program:
         enc = ola_encode(ins)
@@ -589,6 +600,56 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20):
             regs[_reg(ins[1])] = r
             row["dst"], row["s_dst"] = r, _reg(ins[1])
             pc += step
+        elif op == "gte":  # execute_inst_gte, lib.rs:1107-1185
+            a = regs[_reg(ins[2])]
+            row["op0"], row["s_op0"] = a, _reg(ins[2])
+            b = val(ins[3])
+            row["op1"] = b
+            r = int(a >= b)
+            d = (a - b) % P if r else (b - a) % P
+            assert d <= 0xFFFFFFFF, "U32RangeCheckFail"
+            regs[_reg(ins[1])] = r
+            row["dst"], row["s_dst"] = r, _reg(ins[1])
+            cmp_pairs.append((a, b))
+            rc_cmp.append(d)
+            pc += step
+        elif op == "range":  # execute_inst_range, lib.rs:998-1039
+            v = regs[_reg(ins[1])]
+            assert v <= 0xFFFFFFFF, "U32RangeCheckFail"
+            row["op1"], row["s_op1"] = v, _reg(ins[1])
+            rc_cpu.append(v)
+            pc += step
+        elif op == "mstore":  # execute_inst_mstore (offset form), lib.rs:868-933
+            base = regs[_reg(ins[1])]
+            off = int(ins[2]) % P
+            row["op0"], row["s_op0"], row["op1"] = base, _reg(ins[1]), off
+            v = regs[_reg(ins[3])]
+            row["dst"], row["s_dst"] = v, _reg(ins[3])
+            row["aux1"] = (base + off) % P
+            mem[row["aux1"]] = v
+            pc += step
+        elif op == "mload":  # execute_inst_mload (offset form), lib.rs:935-996
+            base = regs[_reg(ins[2])]
+            off = int(ins[3]) % P
+            row["op0"], row["s_op0"], row["op1"] = base, _reg(ins[2]), off
+            row["aux1"] = (base + off) % P
+            regs[_reg(ins[1])] = mem[row["aux1"]]
+            row["dst"], row["s_dst"] = regs[_reg(ins[1])], _reg(ins[1])
+            pc += step
+        elif op == "call":  # execute_inst_call, lib.rs:816-849 (immediate target)
+            assert not isinstance(ins[1], str)
+            fp = regs[9]
+            mem[(fp - 1) % P] = pc + step
+            row["op0"], row["dst"], row["op1"] = (fp - 1) % P, pc + step, int(ins[1]) % P
+            row["aux0"] = (fp - 2) % P
+            row["aux1"] = mem[(fp - 2) % P]
+            pc = int(ins[1])
+        elif op == "ret":  # execute_inst_ret, lib.rs:851-866
+            fp = regs[9]
+            row["op0"], row["aux0"] = (fp - 1) % P, (fp - 2) % P
+            pc = mem[(fp - 1) % P]
+            regs[9] = mem[(fp - 2) % P]
+            row["dst"], row["aux1"] = pc, regs[9]
         elif op == "assert":
             v = val(ins[1])
             assert v == 1, "assert failed in the VM"
@@ -627,7 +688,7 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20):
         t[85, i] = 1                                  # is_entry_sc: env_idx == 0
         t[86, i] = 1                                  # is_next_line_diff_inst: ext_length (0) == ext_cnt (0)
         t[87, i] = 0 if s["op"] == "end" else 1        # is_next_line_same_tx
-        t[92, i] = s["op1_imm"]                        # filter_looking_prog_imm (no mload / mstore here)
+        t[92, i] = s["op1_imm"]                        # filter_looking_prog_imm: mload / mstore / any immediate operand
     k = len(steps)
     if k != n:  # padding, generation/cpu.rs:180-208
         t[26, k:] = t[26, k - 1]
@@ -637,7 +698,44 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20):
         t[86, k:] = 1
         t[87, k:] = 0
         t[93, k:] = 1
+    if want_side_tables:
+        return t, steps, cmp_pairs, rc_cmp, rc_cpu
     return t, steps
+
+
+def calls_program(n_iter):
+    """Exercises memory and builtin opcodes on top of fib_program's set: a stack frame (mstore / mload relative to r9), a
+    call / ret pair, gte comparisons in both directions and u32 range checks.  Word addresses in the comments."""
+    return [
+        ("mov", "r9", 100),               # 0   frame pointer
+        ("mov", "r0", 0),                 # 2
+        ("mov", "r1", 1),                 # 4
+        ("mov", "r2", 0),                 # 6
+        # loop (8):
+        ("mstore", "r9", -2, "r9"),       # 8   [fp-2] = fp   (what call / ret read back into r9)
+        ("call", 30),                     # 10  -> step function; return address 12 stored at [fp-1]
+        ("add", "r2", "r2", 1),           # 12
+        ("gte", "r4", "r2", n_iter),      # 14  r4 = (r2 >= n_iter)
+        ("gte", "r5", "r1", "r0"),        # 16  fib pair is non-decreasing: r5 = 1
+        ("assert", "r5"),                 # 17
+        ("not", "r6", "r4"),              # 18  r6 = p - 1 - r4
+        ("add", "r6", "r6", 2),           # 19  r6 = 1 - r4  (+ p)
+        ("cjmp", "r6", 8),                # 21  loop while r2 < n_iter
+        ("range", "r2"),                  # 23
+        ("mload", "r7", "r9", -3),        # 24  last sum the callee spilled
+        ("eq", "r8", "r7", "r1"),         # 26
+        ("assert", "r8"),                 # 27
+        ("jmp", 38),                      # 28
+        # step function (30): (r0, r1) <- (r1, r0 + r1); spills the sum to [fp-3]
+        ("add", "r3", "r0", "r1"),        # 30
+        ("mov", "r0", "r1"),              # 31
+        ("mov", "r1", "r3"),              # 32
+        ("mstore", "r9", -3, "r3"),       # 33
+        ("range", "r3"),                  # 35
+        ("ret",),                         # 36
+        ("end",),                         # 37 (never reached)
+        ("end",),                         # 38
+    ]
 
 
 def fib_program(n_iter):

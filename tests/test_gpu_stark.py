@@ -127,6 +127,36 @@ def test_cpu_cmp_rangecheck_real_program(ctx, orc):
     assert not olavm_b200.verify_proof([CPU, CMP, RC], short)[0]
 
 
+def test_cpu_memory_cmp_rangecheck_real_program(ctx, orc):
+    """[Cpu, Memory, Cmp, RangeCheck] of a real program (tests/tracegen.py: VM + gen_memory_table restatement): degree check
+    on, GPU proof bytes equal the oracle's, both verifiers accept; a read that returns another value than was written is
+    rejected by the Memory AIR on the GPU as well."""
+    cpu_t, steps, cmp_pairs, rc_cmp, rc_cpu, mem_log = tracegen.cpu_vm_trace(tracegen.calls_program(12), 9, want_side_tables="memory")
+    mem_t, rc_sort = tracegen.memory_trace_from_log(mem_log, 7)
+    cmp_t = tracegen.cmp_trace(cmp_pairs, 6)
+    rc_t = tracegen.rangecheck_trace(rc_cmp, cpu_vals=rc_cpu, mem_sort_vals=rc_sort)
+    ids = [CPU, 1, CMP, RC]
+    got = olavm_b200.prove_with_traces(ctx, ids, [cpu_t, mem_t, cmp_t, rc_t])
+    assert got == orc.stark_prove(ids, [cpu_t, mem_t, cmp_t, rc_t])
+    ok, msg = orc.stark_verify(ids, got)
+    assert ok, msg
+    ok, msg = olavm_b200.verify_proof(ids, got)
+    assert ok, msg
+    m = mem_t.copy()
+    k = next(i for i in range(1, m.shape[1]) if m[23, i] == 1 and m[17, i] == 0)
+    m[18, k] = (int(m[18, k]) + 1) % tracegen.P
+    with pytest.raises(olavm_b200.OlaError, match="Quotient has failed") as e:
+        olavm_b200.prove_with_traces(ctx, ids, [cpu_t, m, cmp_t, rc_t])
+    assert e.value.code == -5
+    # a longer run: 2^13 CPU rows, 2^11 memory rows
+    cpu_t, steps, cmp_pairs, rc_cmp, rc_cpu, mem_log = tracegen.cpu_vm_trace(tracegen.calls_program(300, linear=True), 13, want_side_tables="memory")
+    mem_t, rc_sort = tracegen.memory_trace_from_log(mem_log, 11)
+    big = olavm_b200.prove_with_traces(ctx, ids, [cpu_t, mem_t, tracegen.cmp_trace(cmp_pairs, 10),
+                                                   tracegen.rangecheck_trace(rc_cmp, cpu_vals=rc_cpu, mem_sort_vals=rc_sort)])
+    ok, msg = orc.stark_verify(ids, big)
+    assert ok, msg
+
+
 @pytest.mark.parametrize("log_n", [4, 8, 11])
 def test_cpu_table_pipeline_parity(ctx, orc, log_n):
     """The 94-column CPU table with its 39 CTL instances (78 Z columns, 12 quotient chunks) on random columns with

@@ -553,7 +553,7 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False):
     """Run `program` (a list of instruction tuples, jump targets = word addresses) and return the [94][2^log_n] CPU table
     and the executed steps; with want_side_tables also the (op0, op1) pairs of the gte rows (Cmp table), their
     |op0 - op1| (RangeCheck rows looked by Cmp) and the operands of the range rows (RangeCheck rows looked by the CPU)."""
-    cmp_pairs, rc_cmp, rc_cpu, mem = [], [], [], {}
+    cmp_pairs, rc_cmp, rc_cpu, mem, mem_log = [], [], [], {}, []
     words, at_pc = [], {}
     for ins in program:
         enc = ola_encode(ins)
@@ -627,6 +627,7 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False):
             row["dst"], row["s_dst"] = v, _reg(ins[3])
             row["aux1"] = (base + off) % P
             mem[row["aux1"]] = v
+            mem_log.append((row["aux1"], clk, 1 << 21, 1, v))
             pc += step
         elif op == "mload":  # execute_inst_mload (offset form), lib.rs:935-996
             base = regs[_reg(ins[2])]
@@ -635,6 +636,7 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False):
             row["aux1"] = (base + off) % P
             regs[_reg(ins[1])] = mem[row["aux1"]]
             row["dst"], row["s_dst"] = regs[_reg(ins[1])], _reg(ins[1])
+            mem_log.append((row["aux1"], clk, 1 << 22, 0, regs[_reg(ins[1])]))
             pc += step
         elif op == "call":  # execute_inst_call, lib.rs:816-849 (immediate target)
             assert not isinstance(ins[1], str)
@@ -643,6 +645,8 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False):
             row["op0"], row["dst"], row["op1"] = (fp - 1) % P, pc + step, int(ins[1]) % P
             row["aux0"] = (fp - 2) % P
             row["aux1"] = mem[(fp - 2) % P]
+            mem_log.append(((fp - 1) % P, clk, 1 << 24, 1, row["dst"]))
+            mem_log.append(((fp - 2) % P, clk, 1 << 24, 0, row["aux1"]))
             pc = int(ins[1])
         elif op == "ret":  # execute_inst_ret, lib.rs:851-866
             fp = regs[9]
@@ -650,6 +654,8 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False):
             pc = mem[(fp - 1) % P]
             regs[9] = mem[(fp - 2) % P]
             row["dst"], row["aux1"] = pc, regs[9]
+            mem_log.append(((fp - 1) % P, clk, 1 << 23, 0, pc))
+            mem_log.append(((fp - 2) % P, clk, 1 << 23, 0, regs[9]))
         elif op == "assert":
             v = val(ins[1])
             assert v == 1, "assert failed in the VM"
@@ -698,14 +704,82 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False):
         t[86, k:] = 1
         t[87, k:] = 0
         t[93, k:] = 1
+    if want_side_tables == "memory":
+        return t, steps, cmp_pairs, rc_cmp, rc_cpu, mem_log
     if want_side_tables:
         return t, steps, cmp_pairs, rc_cmp, rc_cpu
     return t, steps
 
 
-def calls_program(n_iter):
+MEM_OP_SELECTOR = {1 << 22: 6, 1 << 21: 7, 1 << 24: 8, 1 << 23: 9}  # mload, mstore, call, ret (memory/columns.rs:16-19)
+
+
+def memory_trace_from_log(mem_log, log_n):
+    """Memory table of a VM run whose accesses all fall in the read-write (stack) region: gen_memory_table
+    (executor/src/trace.rs:20-199: cells grouped by address in ascending order, access order inside an address, diff_addr /
+    diff_clk and the value each non-first row sends to the RangeCheck table) + generate_memory_trace
+    (circuits/src/generation/memory.rs:8-155, padding with write-once rows from p - (2^32 - 1) upwards).
+    Returns (table [29][2^log_n], mem_sort range-check values)."""
+    SPAN = (1 << 32) - 1
+    by_addr = {}
+    for addr, clk, op, is_write, value in mem_log:
+        assert addr < P - 2 * SPAN, "only the read-write region is modelled"
+        by_addr.setdefault(addr, []).append((clk, op, is_write, value))
+    cells, rc_sort = [], []
+    origin_addr = origin_clk = 0
+    first_row = True
+    for addr in sorted(by_addr):
+        new_addr = True
+        for clk, op, is_write, value in by_addr[addr]:
+            c = {"addr": addr, "clk": clk, "op": op, "is_write": is_write, "value": value, "diff_addr": 0, "diff_addr_inv": 0,
+                 "diff_clk": 0, "rw_addr_unchanged": 0, "rc_value": 0}
+            if first_row:
+                first_row = new_addr = False
+            elif new_addr:
+                c["diff_addr"] = addr - origin_addr
+                c["diff_addr_inv"] = _finv(c["diff_addr"])
+                c["rc_value"] = c["diff_addr"]
+                rc_sort.append(c["rc_value"])
+                new_addr = False
+            else:
+                c["diff_clk"] = clk - origin_clk
+                c["rw_addr_unchanged"] = 1
+                c["rc_value"] = c["diff_clk"]
+                rc_sort.append(c["rc_value"])
+            assert c["rc_value"] <= 0xFFFFFFFF, "U32RangeCheckFail"
+            cells.append(c)
+            origin_clk = clk
+        origin_addr = addr
+    n = 1 << log_n
+    k = len(cells)
+    assert 2 <= k <= n
+    t = np.zeros((29, n), dtype=np.uint64)
+    for i, c in enumerate(cells):
+        t[2, i], t[3, i], t[4, i], t[5, i] = 1, c["addr"], c["clk"], c["op"]
+        t[MEM_OP_SELECTOR[c["op"]], i] = 1
+        t[17, i], t[18, i] = c["is_write"], c["value"]
+        t[19, i], t[20, i], t[21, i] = c["diff_addr"], c["diff_addr_inv"], c["diff_clk"]
+        t[23, i], t[26, i] = c["rw_addr_unchanged"], c["rc_value"]
+        t[27, i] = 0 if i == 0 else 1
+    if k != n:  # memory.rs:113-146 (the last filled row is read-write: padding starts at p - span)
+        addr = P - SPAN
+        for i in range(k, n):
+            t[16, i] = 1
+            t[3, i] = addr
+            t[17, i] = 1
+            d = (addr - int(t[3, k - 1])) % P if i == k else 1
+            t[19, i], t[20, i] = d, _finv(d)
+            t[22, i] = (P - addr) % P
+            t[24, i] = 1
+            t[26, i] = t[22, i]
+            addr += 1
+    return t, rc_sort
+
+
+def calls_program(n_iter, linear=False):
     """Exercises memory and builtin opcodes on top of fib_program's set: a stack frame (mstore / mload relative to r9), a
-    call / ret pair, gte comparisons in both directions and u32 range checks.  Word addresses in the comments."""
+    call / ret pair, gte comparisons in both directions and u32 range checks.  Word addresses in the comments.
+    linear=True replaces the Fibonacci step by r1 + r2 (the loop counter) so that long runs stay inside the u32 range checks."""
     return [
         ("mov", "r9", 100),               # 0   frame pointer
         ("mov", "r0", 0),                 # 2
@@ -727,7 +801,7 @@ def calls_program(n_iter):
         ("assert", "r8"),                 # 27
         ("jmp", 38),                      # 28
         # step function (30): (r0, r1) <- (r1, r0 + r1); spills the sum to [fp-3]
-        ("add", "r3", "r0", "r1"),        # 30
+        ("add", "r3", "r1", "r2") if linear else ("add", "r3", "r0", "r1"),  # 30
         ("mov", "r0", "r1"),              # 31
         ("mov", "r1", "r3"),              # 32
         ("mstore", "r9", -3, "r3"),       # 33

@@ -157,6 +157,24 @@ def test_cpu_memory_cmp_rangecheck_real_program(ctx, orc):
     assert ok, msg
 
 
+def test_eight_table_system_of_a_real_program_run(ctx, orc):
+    """tracegen.real_program_system ([Cpu, Memory, Cmp, RangeCheck, Poseidon, StorageAccess, Program, ProgChunk] of one
+    program run, thirteen lookups with real data): GPU proof bytes equal the oracle's, both verifiers accept; a longer run
+    (2^13 CPU rows) verifies as well."""
+    ids, traces, cc = tracegen.real_program_system(orc, np.random.default_rng(5))
+    got = olavm_b200.prove_with_traces(ctx, ids, traces, compress_challenges=cc)
+    assert got == orc.stark_prove(ids, traces, compress_challenges=cc)
+    ok, msg = orc.stark_verify(ids, got)
+    assert ok, msg
+    ok, msg = olavm_b200.verify_proof(ids, got)
+    assert ok, msg
+    ids, traces, cc = tracegen.real_program_system(orc, np.random.default_rng(6), n_iter=300, linear=True, cpu_log=13, mem_log_n=11,
+                                                   cmp_log=10, prog_log=13)
+    big = olavm_b200.prove_with_traces(ctx, ids, traces, compress_challenges=cc)
+    ok, msg = orc.stark_verify(ids, big)
+    assert ok, msg
+
+
 @pytest.mark.parametrize("log_n", [4, 8, 11])
 def test_cpu_table_pipeline_parity(ctx, orc, log_n):
     """The 94-column CPU table with its 39 CTL instances (78 Z columns, 12 quotient chunks) on random columns with

@@ -371,3 +371,22 @@ def test_real_memory_table_binds(orc, case):
             return  # the forged register is read by later rows (eq / assert): rejected even earlier
         ok, msg = orc.stark_verify(ids, proof)
         assert not ok
+
+
+def test_eight_table_system_of_a_real_program_run(orc):
+    """tracegen.real_program_system: CPU, Memory, Cmp, RangeCheck, Poseidon, StorageAccess, Program and ProgChunk tables of
+    one program run, thirteen lookups carrying real data; degree check on, verifier accepts; an executed instruction
+    word that the program does not contain breaks the Program table's own lookup argument."""
+    rng = np.random.default_rng(5)
+    ids, traces, cc = tracegen.real_program_system(orc, rng)
+    proof = orc.stark_prove(ids, traces, compress_challenges=cc)
+    ok, msg = orc.stark_verify(ids, proof)
+    assert ok, msg
+    bad = [t.copy() for t in traces]
+    prog_t = bad[6]
+    prog_t[13, 3] = int(prog_t[13, 3]) ^ 1          # exec_inst of one fetched line
+    beta = cc[6]
+    prog_t[14, 3] = tracegen._horner(prog_t[8:14, 3], beta)
+    # ProgramStark has quotient_degree_factor 2 = 2^qdb, so trim_to_len cannot notice (prover.rs:463-473); the verifier does
+    ok, msg = orc.stark_verify(ids, orc.stark_prove(ids, bad, compress_challenges=cc))
+    assert not ok and "ProgramStark" in msg

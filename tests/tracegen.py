@@ -244,10 +244,11 @@ def _horner(vals, beta):
     return acc
 
 
-def program_valid_trace(rng, log_n, beta, prog_rows=None, n_exec=None):
+def program_valid_trace(rng, log_n, beta, prog_rows=None, n_exec=None, exec_rows=None):
     """Program table (program/columns.rs:3-16).  prog_rows: list of (addr0..3, pc, inst) program lines (default random);
-    the executed lines are drawn from them.  comp = sum_i x_i beta^i (program_stark.rs:70-88); the permuted columns by
-    lookup.rs permuted_cols."""
+    the executed lines are exec_rows when given (generate_prog_trace, generation/prog.rs:56-104: one row per executed
+    instruction word and one per immediate), else drawn from the program lines.  comp = sum_i x_i beta^i
+    (program_stark.rs:70-88); the permuted columns by lookup.rs permuted_cols."""
     n = 1 << log_n
     if prog_rows is None:
         prog_rows = [tuple(int(x) for x in _rand(rng, 6)) for _ in range(n // 2)]
@@ -258,8 +259,11 @@ def program_valid_trace(rng, log_n, beta, prog_rows=None, n_exec=None):
         t[0:6, i] = r
         t[6, i] = _horner(r, beta)
         t[17, i] = 1
+    if exec_rows is not None:
+        assert len(exec_rows) <= n
+        n_exec = len(exec_rows)
     for i in range(n_exec):
-        r = prog_rows[int(rng.integers(0, len(prog_rows)))]
+        r = exec_rows[i] if exec_rows is not None else prog_rows[int(rng.integers(0, len(prog_rows)))]
         t[8:14, i] = r
         t[14, i] = _horner(r, beta)
         t[16, i] = 1
@@ -313,7 +317,7 @@ def poseidon_valid_trace(orc, log_n, rows):
     return t
 
 
-def prog_chunk_valid_trace(orc, rng, log_n, line_counts=(1, 3, 2)):
+def prog_chunk_valid_trace(orc, rng, log_n, line_counts=(1, 3, 2), programs=None):
     """ProgChunk table (program/columns.rs:47-62): per program, lines of 8 instructions absorbed by a Poseidon sponge
     (cap = previous line's hash[8..12]).  Returns (trace, poseidon_rows, program_lines, prog_hashes):
     poseidon_rows = the (input, output) pairs the lines look up; program_lines = (addr0..3, pc, inst) with filter 1."""
@@ -322,13 +326,19 @@ def prog_chunk_valid_trace(orc, rng, log_n, line_counts=(1, 3, 2)):
     t[39] = 1
     row = 0
     psdn, lines, roots = [], [], []
-    for L in line_counts:
-        addr = [int(x) for x in _rand(rng, 4)]
+    # programs = [(code address [4], instruction words)]: real programs instead of random lines
+    todo = [(None, None, L) for L in line_counts] if programs is None else [(a, w, (len(w) + 7) // 8) for a, w in programs]
+    for paddr, pwords, L in todo:
+        addr = [int(x) for x in _rand(rng, 4)] if paddr is None else [int(x) for x in paddr]
         cap = [0, 0, 0, 0]
         for j in range(L):
             last = j == L - 1
-            cnt = int(rng.integers(1, 9)) if last else 8
-            inst = [int(x) for x in _rand(rng, 8)]
+            if pwords is None:
+                cnt = int(rng.integers(1, 9)) if last else 8
+                inst = [int(x) for x in _rand(rng, 8)]
+            else:
+                cnt = min(8, len(pwords) - 8 * j)
+                inst = [int(x) for x in pwords[8 * j:8 * j + cnt]] + [0] * (8 - cnt)
             for k in range(cnt, 8):
                 inst[k] = 0
             h = [int(x) for x in orc.poseidon(np.array(inst + cap, dtype=np.uint64))]
@@ -711,6 +721,22 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False):
     return t, steps
 
 
+def program_rows_of_run(program, steps):
+    """(program lines, executed lines) of a VM run for the Program table: every word of the program at code address 0
+    (generate_prog_trace, generation/prog.rs:106-131) and, per executed step, (pc, instruction) plus (pc + 1, immediate)
+    when the instruction carries one (:56-104)."""
+    words = []
+    for ins in program:
+        words += ola_encode(ins)
+    prog_rows = [(0, 0, 0, 0, pc, w) for pc, w in enumerate(words)]
+    exec_rows = []
+    for s in steps:
+        exec_rows.append((0, 0, 0, 0, s["pc"], s["inst"]))
+        if s["op1_imm"] == 1 or s["op"] in ("mload", "mstore"):
+            exec_rows.append((0, 0, 0, 0, s["pc"] + 1, s["imm"]))
+    return prog_rows, exec_rows
+
+
 MEM_OP_SELECTOR = {1 << 22: 6, 1 << 21: 7, 1 << 24: 8, 1 << 23: 9}  # mload, mstore, call, ret (memory/columns.rs:16-19)
 
 
@@ -836,3 +862,31 @@ def fib_program(n_iter):
         ("jmp", 28),                 # pc 26
         ("end",),                    # pc 28
     ]
+
+
+def real_program_system(orc, rng, n_iter=12, linear=False, cpu_log=9, mem_log_n=7, cmp_log=6, prog_log=9, beta=0x1234567890ABCDEF % P):
+    """An eight-table system produced by RUNNING a program: [Cpu, Memory, Cmp, RangeCheck, Poseidon, StorageAccess, Program,
+    ProgChunk].  The VM (cpu_vm_trace) fills the CPU table and logs memory accesses, comparisons and range checks; the
+    Memory / Cmp / RangeCheck tables are generated from those logs the way the executor does; the Program table holds the
+    program's words and one executed line per fetched word; ProgChunk hashes the program (Poseidon sponge over lines of
+    8 words), its digest is read from the storage tree at code address 0, and every sponge / Merkle hash is a Poseidon
+    row.  Lookups with real data: cpu->memory (x3), memory->rangecheck, cpu->cmp, cmp->rangecheck, cpu->rangecheck,
+    cpu->program (instruction and immediate), prog_chunk->program, prog_chunk->poseidon, prog_chunk->storage,
+    storage->poseidon.  Returns (table_ids, traces, compress_challenges)."""
+    prog = calls_program(n_iter, linear=linear)
+    cpu_t, steps, cmp_pairs, rc_cmp, rc_cpu, mlog = cpu_vm_trace(prog, cpu_log, want_side_tables="memory")
+    mem_t, rc_sort = memory_trace_from_log(mlog, mem_log_n)
+    cmp_t = cmp_trace(cmp_pairs, cmp_log)
+    rc_t = rangecheck_trace(rc_cmp, cpu_vals=rc_cpu, mem_sort_vals=rc_sort)
+    prog_rows, exec_rows = program_rows_of_run(prog, steps)
+    words = [r[5] for r in prog_rows]
+    pc_t, psdn_prog, lines, roots = prog_chunk_valid_trace(orc, rng, 3, programs=[([0, 0, 0, 0], words)])
+    assert lines == prog_rows
+    _, leaf = roots[0]
+    st, psdn_st = storage_valid_trace(orc, rng, 8, [dict(addr_bits=[0] * 256, leaf=leaf, pre_leaf=leaf, is_write=0, for_prog=1)])
+    rows = [(inp, [1, 0, 0, 0]) for inp, _ in psdn_prog]
+    rows += [(inp, [0, 0, 1, 0] if is_leaf else [0, 0, 0, 1]) for inp, _, is_leaf in psdn_st]
+    ps = poseidon_valid_trace(orc, 10, rows)
+    pt = program_valid_trace(rng, prog_log, beta, prog_rows=prog_rows, exec_rows=exec_rows)
+    ids = [0, 1, 3, 4, 5, 7, 10, 11]
+    return ids, [cpu_t, mem_t, cmp_t, rc_t, ps, st, pt, pc_t], [0, 0, 0, 0, 0, 0, beta, 0]

@@ -157,7 +157,7 @@ def test_cpu_memory_cmp_rangecheck_real_program(ctx, orc):
     assert ok, msg
 
 
-def test_eight_table_system_of_a_real_program_run(ctx, orc):
+def test_real_program_run_systems(ctx, orc):
     """tracegen.real_program_system ([Cpu, Memory, Cmp, RangeCheck, Poseidon, StorageAccess, Program, ProgChunk] of one
     program run, thirteen lookups with real data): GPU proof bytes equal the oracle's, both verifiers accept; a longer run
     (2^13 CPU rows) verifies as well."""
@@ -172,6 +172,12 @@ def test_eight_table_system_of_a_real_program_run(ctx, orc):
                                                    cmp_log=10, prog_log=13)
     big = olavm_b200.prove_with_traces(ctx, ids, traces, compress_challenges=cc)
     ok, msg = orc.stark_verify(ids, big)
+    assert ok, msg
+    # nine tables: and / or / xor rows and the Bitwise table behind them
+    ids, traces, cc = tracegen.real_program_system(orc, np.random.default_rng(7), bitwise=True)
+    got = olavm_b200.prove_with_traces(ctx, ids, traces, compress_challenges=cc)
+    assert got == orc.stark_prove(ids, traces, compress_challenges=cc)
+    ok, msg = olavm_b200.verify_proof(ids, got)
     assert ok, msg
 
 

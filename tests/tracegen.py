@@ -271,17 +271,21 @@ def program_valid_trace(rng, log_n, beta, prog_rows=None, n_exec=None, exec_rows
     return t
 
 
-def bitwise_valid_trace(rng, log_n, beta, n_ops=None):
+def bitwise_valid_trace(rng, log_n, beta, n_ops=None, ops=None):
     """Bitwise table (bitwise/columns.rs:23-48): byte-limb decompositions, beta-compressed (tag, a, b, r) byte triples
-    looked up in FIX_COMPRESS, byte range checks against FIX_RANGE_CHECK_U8."""
+    looked up in FIX_COMPRESS, byte range checks against FIX_RANGE_CHECK_U8.  ops = [(tag, a, b)] uses the operations of a
+    VM run (insert_bitwise_combined, executor lib.rs:1095-1100) instead of random ones."""
     n = 1 << log_n
     assert n >= 256
-    n_ops = min(n // 8, 60) if n_ops is None else n_ops
+    n_ops = (min(n // 8, 60) if n_ops is None else n_ops) if ops is None else len(ops)
     t = np.zeros((59, n), dtype=np.uint64)
     fixed = {(0, 0, 0, 0)}
     for i in range(n_ops):
-        tag = [OP_AND, OP_OR, OP_XOR][int(rng.integers(0, 3))]
-        a, b = int(rng.integers(0, 1 << 32)), int(rng.integers(0, 1 << 32))
+        if ops is not None:
+            tag, a, b = ops[i]
+        else:
+            tag = [OP_AND, OP_OR, OP_XOR][int(rng.integers(0, 3))]
+            a, b = int(rng.integers(0, 1 << 32)), int(rng.integers(0, 1 << 32))
         r = a & b if tag == OP_AND else (a | b if tag == OP_OR else a ^ b)
         t[0:5, i] = [1, tag, a, b, r]
         for j in range(4):
@@ -509,9 +513,9 @@ def hash_system_valid(orc, rng, beta=0x1234567890ABCDEF % P):
 # them with the quotient-degree check on tests the transcription against the reference's own trace semantics.
 # ---------------------------------------------------------------------------------------------------------------------
 OPCODE_SHIFT = {"add": 31, "mul": 30, "eq": 29, "assert": 28, "mov": 27, "jmp": 26, "cjmp": 25, "call": 24, "ret": 23, "mload": 22,
-                "mstore": 21, "end": 20, "range": 19, "not": 15, "neq": 14, "gte": 13}
+                "mstore": 21, "end": 20, "range": 19, "and": 18, "or": 17, "xor": 16, "not": 15, "neq": 14, "gte": 13}
 CPU_SELECTOR_COL = {"add": 66, "mul": 66, "eq": 66, "assert": 66, "neq": 66, "mov": 67, "jmp": 68, "cjmp": 69, "call": 70, "ret": 71,
-                    "mload": 72, "mstore": 73, "end": 74, "range": 75, "not": 77, "gte": 78}
+                    "mload": 72, "mstore": 73, "end": 74, "range": 75, "and": 76, "or": 76, "xor": 76, "not": 77, "gte": 78}
 
 
 def _finv(x):
@@ -531,7 +535,7 @@ def ola_encode(ins):
     op = ins[0]
     word = 1 << OPCODE_SHIFT[op]
     dst = op0 = op1 = None
-    if op in ("add", "mul", "eq", "neq", "gte"):
+    if op in ("add", "mul", "eq", "neq", "gte", "and", "or", "xor"):
         dst, op0, op1 = ins[1], ins[2], ins[3]
     elif op in ("mov", "not"):
         dst, op1 = ins[1], ins[2]
@@ -563,7 +567,7 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False):
     """Run `program` (a list of instruction tuples, jump targets = word addresses) and return the [94][2^log_n] CPU table
     and the executed steps; with want_side_tables also the (op0, op1) pairs of the gte rows (Cmp table), their
     |op0 - op1| (RangeCheck rows looked by Cmp) and the operands of the range rows (RangeCheck rows looked by the CPU)."""
-    cmp_pairs, rc_cmp, rc_cpu, mem, mem_log = [], [], [], {}, []
+    cmp_pairs, rc_cmp, rc_cpu, mem, mem_log, bit_ops = [], [], [], {}, [], []
     words, at_pc = [], {}
     for ins in program:
         enc = ola_encode(ins)
@@ -609,6 +613,17 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False):
                 r = int(a == b) if op == "eq" else int(a != b)
             regs[_reg(ins[1])] = r
             row["dst"], row["s_dst"] = r, _reg(ins[1])
+            pc += step
+        elif op in ("and", "or", "xor"):  # execute_inst_bitwise, lib.rs:1041-1105
+            a = regs[_reg(ins[2])]
+            row["op0"], row["s_op0"] = a, _reg(ins[2])
+            b = val(ins[3])
+            row["op1"] = b
+            assert a < (1 << 32) and b < (1 << 32), "the Bitwise table works on u32 operands"
+            r = a & b if op == "and" else (a | b if op == "or" else a ^ b)
+            regs[_reg(ins[1])] = r
+            row["dst"], row["s_dst"] = r, _reg(ins[1])
+            bit_ops.append((1 << OPCODE_SHIFT[op], a, b))
             pc += step
         elif op == "gte":  # execute_inst_gte, lib.rs:1107-1185
             a = regs[_reg(ins[2])]
@@ -714,6 +729,9 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False):
         t[86, k:] = 1
         t[87, k:] = 0
         t[93, k:] = 1
+    if want_side_tables == "all":
+        return t, steps, cmp_pairs, rc_cmp, rc_cpu, mem_log, bit_ops
+    assert not bit_ops or not want_side_tables, "bitwise rows are only returned with want_side_tables='all'"
     if want_side_tables == "memory":
         return t, steps, cmp_pairs, rc_cmp, rc_cpu, mem_log
     if want_side_tables:
@@ -802,40 +820,53 @@ def memory_trace_from_log(mem_log, log_n):
     return t, rc_sort
 
 
-def calls_program(n_iter, linear=False):
+def calls_program(n_iter, linear=False, bitwise=False):
     """Exercises memory and builtin opcodes on top of fib_program's set: a stack frame (mstore / mload relative to r9), a
-    call / ret pair, gte comparisons in both directions and u32 range checks.  Word addresses in the comments.
-    linear=True replaces the Fibonacci step by r1 + r2 (the loop counter) so that long runs stay inside the u32 range checks."""
-    return [
-        ("mov", "r9", 100),               # 0   frame pointer
-        ("mov", "r0", 0),                 # 2
-        ("mov", "r1", 1),                 # 4
-        ("mov", "r2", 0),                 # 6
-        # loop (8):
-        ("mstore", "r9", -2, "r9"),       # 8   [fp-2] = fp   (what call / ret read back into r9)
-        ("call", 30),                     # 10  -> step function; return address 12 stored at [fp-1]
-        ("add", "r2", "r2", 1),           # 12
-        ("gte", "r4", "r2", n_iter),      # 14  r4 = (r2 >= n_iter)
-        ("gte", "r5", "r1", "r0"),        # 16  fib pair is non-decreasing: r5 = 1
-        ("assert", "r5"),                 # 17
-        ("not", "r6", "r4"),              # 18  r6 = p - 1 - r4
-        ("add", "r6", "r6", 2),           # 19  r6 = 1 - r4  (+ p)
-        ("cjmp", "r6", 8),                # 21  loop while r2 < n_iter
-        ("range", "r2"),                  # 23
-        ("mload", "r7", "r9", -3),        # 24  last sum the callee spilled
-        ("eq", "r8", "r7", "r1"),         # 26
-        ("assert", "r8"),                 # 27
-        ("jmp", 38),                      # 28
-        # step function (30): (r0, r1) <- (r1, r0 + r1); spills the sum to [fp-3]
-        ("add", "r3", "r1", "r2") if linear else ("add", "r3", "r0", "r1"),  # 30
-        ("mov", "r0", "r1"),              # 31
-        ("mov", "r1", "r3"),              # 32
-        ("mstore", "r9", -3, "r3"),       # 33
-        ("range", "r3"),                  # 35
-        ("ret",),                         # 36
-        ("end",),                         # 37 (never reached)
-        ("end",),                         # 38
+    call / ret pair, gte comparisons in both directions and u32 range checks; with bitwise=True also and / or / xor in the
+    callee.  linear=True replaces the Fibonacci step by r1 + r2 (the loop counter) so that long runs stay inside the u32
+    range checks.  Jump targets are word addresses, resolved from labels below."""
+    body = [
+        ("mov", "r9", 100),               # frame pointer
+        ("mov", "r0", 0),
+        ("mov", "r1", 1),
+        ("mov", "r2", 0),
+        "loop",
+        ("mstore", "r9", -2, "r9"),       # [fp-2] = fp   (what call / ret read back into r9)
+        ("call", "step"),                 # return address stored at [fp-1]
+        ("add", "r2", "r2", 1),
+        ("gte", "r4", "r2", n_iter),      # r4 = (r2 >= n_iter)
+        ("gte", "r5", "r1", "r0"),        # the pair is non-decreasing: r5 = 1
+        ("assert", "r5"),
+        ("not", "r6", "r4"),              # r6 = p - 1 - r4
+        ("add", "r6", "r6", 2),           # r6 = 1 - r4  (+ p)
+        ("cjmp", "r6", "loop"),           # loop while r2 < n_iter
+        ("range", "r2"),
+        ("mload", "r7", "r9", -3),        # last sum the callee spilled
+        ("eq", "r8", "r7", "r1"),
+        ("assert", "r8"),
+        ("jmp", "done"),
+        "step",                           # (r0, r1) <- (r1, r0 + r1); spills the sum to [fp-3]
+        ("add", "r3", "r1", "r2") if linear else ("add", "r3", "r0", "r1"),
+        ("mov", "r0", "r1"),
+        ("mov", "r1", "r3"),
+        ("mstore", "r9", -3, "r3"),
+        ("range", "r3"),
     ]
+    if bitwise:
+        body += [
+            ("and", "r7", "r3", 0xFF0F),
+            ("or", "r8", "r7", "r2"),
+            ("xor", "r7", "r8", "r3"),
+        ]
+    body += [("ret",), ("end",), "done", ("end",)]
+    # resolve labels to word addresses
+    labels, pc = {}, 0
+    for x in body:
+        if isinstance(x, str):
+            labels[x] = pc
+        else:
+            pc += len(ola_encode(tuple(0 if (isinstance(a, str) and a in ("loop", "step", "done")) else a for a in x)))
+    return [tuple(labels[a] if (isinstance(a, str) and a in labels) else a for a in x) for x in body if not isinstance(x, str)]
 
 
 def fib_program(n_iter):
@@ -864,17 +895,19 @@ def fib_program(n_iter):
     ]
 
 
-def real_program_system(orc, rng, n_iter=12, linear=False, cpu_log=9, mem_log_n=7, cmp_log=6, prog_log=9, beta=0x1234567890ABCDEF % P):
+def real_program_system(orc, rng, n_iter=12, linear=False, cpu_log=9, mem_log_n=7, cmp_log=6, prog_log=9, beta=0x1234567890ABCDEF % P,
+                        bitwise=False, beta_bitwise=0x0FEDCBA987654321 % P, bitwise_log=9):
     """An eight-table system produced by RUNNING a program: [Cpu, Memory, Cmp, RangeCheck, Poseidon, StorageAccess, Program,
-    ProgChunk].  The VM (cpu_vm_trace) fills the CPU table and logs memory accesses, comparisons and range checks; the
+    ProgChunk]; with bitwise=True the program also executes and / or / xor and the Bitwise table (with its own compress
+    challenge) joins as a ninth table behind the cpu->bitwise lookup.  The VM (cpu_vm_trace) fills the CPU table and logs memory accesses, comparisons and range checks; the
     Memory / Cmp / RangeCheck tables are generated from those logs the way the executor does; the Program table holds the
     program's words and one executed line per fetched word; ProgChunk hashes the program (Poseidon sponge over lines of
     8 words), its digest is read from the storage tree at code address 0, and every sponge / Merkle hash is a Poseidon
     row.  Lookups with real data: cpu->memory (x3), memory->rangecheck, cpu->cmp, cmp->rangecheck, cpu->rangecheck,
     cpu->program (instruction and immediate), prog_chunk->program, prog_chunk->poseidon, prog_chunk->storage,
     storage->poseidon.  Returns (table_ids, traces, compress_challenges)."""
-    prog = calls_program(n_iter, linear=linear)
-    cpu_t, steps, cmp_pairs, rc_cmp, rc_cpu, mlog = cpu_vm_trace(prog, cpu_log, want_side_tables="memory")
+    prog = calls_program(n_iter, linear=linear, bitwise=bitwise)
+    cpu_t, steps, cmp_pairs, rc_cmp, rc_cpu, mlog, bit_ops = cpu_vm_trace(prog, cpu_log, want_side_tables="all")
     mem_t, rc_sort = memory_trace_from_log(mlog, mem_log_n)
     cmp_t = cmp_trace(cmp_pairs, cmp_log)
     rc_t = rangecheck_trace(rc_cmp, cpu_vals=rc_cpu, mem_sort_vals=rc_sort)
@@ -888,5 +921,8 @@ def real_program_system(orc, rng, n_iter=12, linear=False, cpu_log=9, mem_log_n=
     rows += [(inp, [0, 0, 1, 0] if is_leaf else [0, 0, 0, 1]) for inp, _, is_leaf in psdn_st]
     ps = poseidon_valid_trace(orc, 10, rows)
     pt = program_valid_trace(rng, prog_log, beta, prog_rows=prog_rows, exec_rows=exec_rows)
+    if bitwise:
+        bw = bitwise_valid_trace(rng, bitwise_log, beta_bitwise, ops=bit_ops)
+        return [0, 1, 2, 3, 4, 5, 7, 10, 11], [cpu_t, mem_t, bw, cmp_t, rc_t, ps, st, pt, pc_t], [0, 0, beta_bitwise, 0, 0, 0, 0, beta, 0]
     ids = [0, 1, 3, 4, 5, 7, 10, 11]
     return ids, [cpu_t, mem_t, cmp_t, rc_t, ps, st, pt, pc_t], [0, 0, 0, 0, 0, 0, beta, 0]

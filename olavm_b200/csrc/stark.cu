@@ -804,9 +804,12 @@ std::vector<uint8_t> prove_all(ola_ctx* ctx, const std::vector<int>& table_ids, 
     std::vector<std::unique_ptr<DevBuf>> d_vals(T);
     std::vector<std::unique_ptr<BatchHolder>> commits(T);
     Challenger ch;
-    // single GPU, host traces: every table's upload is queued on the copy stream up front, so table i+1 crosses PCIe
-    // while table i is being committed (LDE + Poseidon) on the context stream
-    const bool prefetch = ctx->world == 1 && !on_device;
+    // host traces: every table's upload is queued on the copy stream up front, so table i+1 crosses PCIe while table i is
+    // being committed (LDE + Poseidon) on the context stream.  With several ranks each uploads 1/world of the columns
+    // over its own PCIe link (into `slices`) and one all-gather over NVLink replicates the table.
+    const bool prefetch = !on_device;
+    const bool sharded_upload = prefetch && ctx->world > 1;
+    std::vector<std::unique_ptr<DevBuf>> slices(T);
     // The 12 trace commitments are independent (their caps are observed afterwards, in table order), so they are
     // uploaded and committed smallest first: the first commit starts after a short copy and the big tables cross
     // PCIe behind the hashing of the small ones instead of in front of everything (the CPU table alone is 57 ms of copy).
@@ -830,7 +833,16 @@ std::vector<uint8_t> prove_all(ola_ctx* ctx, const std::vector<int>& table_ids, 
         OLA_CUDA(cudaEventCreateWithFlags(&allocated, cudaEventDisableTiming));
         for (size_t i = 0; i < T; ++i) {
             OLA_CHECK(log_ns[i] + Config::rate_bits <= 32, OLA_ERR_INVALID_ARG, "trace too long for the field's two-adicity");
-            d_vals[i].reset(new DevBuf(((size_t)1 << log_ns[i]) * sys.tables[i].columns));
+            const size_t n = (size_t)1 << log_ns[i], cols = (size_t)sys.tables[i].columns;
+            if (sharded_upload) {
+                const size_t per = (cols + ctx->world - 1) / ctx->world;  // padded to equal contributions
+                d_vals[i].reset(new DevBuf(per * ctx->world * n));
+                slices[i].reset(new DevBuf(per * n));
+                const size_t lo = std::min(cols, (size_t)ctx->rank * per), hi = std::min(cols, lo + per);
+                if (hi - lo < per) OLA_CUDA(cudaMemsetAsync(slices[i]->p, 0, per * n * 8, ctx->stream));
+            } else {
+                d_vals[i].reset(new DevBuf(n * cols));
+            }
         }
         cudaError_t e = cudaEventRecord(allocated, ctx->stream);  // the stream-ordered allocations above precede the copies
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, allocated, 0);
@@ -838,8 +850,14 @@ std::vector<uint8_t> prove_all(ola_ctx* ctx, const std::vector<int>& table_ids, 
         OLA_CUDA(e);
         for (size_t oi = 0; oi < T; ++oi) {
             const size_t i = order[oi];
-            const size_t cnt = ((size_t)1 << log_ns[i]) * sys.tables[i].columns;
-            OLA_CUDA(cudaMemcpyAsync(d_vals[i]->p, traces[i], cnt * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+            const size_t n = (size_t)1 << log_ns[i], cols = (size_t)sys.tables[i].columns;
+            if (sharded_upload) {
+                const size_t per = (cols + ctx->world - 1) / ctx->world;
+                const size_t lo = std::min(cols, (size_t)ctx->rank * per), hi = std::min(cols, lo + per);
+                if (hi > lo) OLA_CUDA(cudaMemcpyAsync(slices[i]->p, traces[i] + lo * n, (hi - lo) * n * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+            } else {
+                OLA_CUDA(cudaMemcpyAsync(d_vals[i]->p, traces[i], n * cols * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+            }
             OLA_CUDA(cudaEventCreateWithFlags(&uploaded[i], cudaEventDisableTiming));
             OLA_CUDA(cudaEventRecord(uploaded[i], ctx->copy_stream));
         }
@@ -849,18 +867,11 @@ std::vector<uint8_t> prove_all(ola_ctx* ctx, const std::vector<int>& table_ids, 
             const size_t i = order[oi];
             const size_t n = (size_t)1 << log_ns[i], cnt = n * sys.tables[i].columns;
             OLA_CHECK(log_ns[i] + Config::rate_bits <= 32, OLA_ERR_INVALID_ARG, "trace too long for the field's two-adicity");
-            if (ctx->world > 1 && !on_device) {
-                // every rank holds the same host trace: each uploads 1/world of the columns over its own PCIe link and one
-                // all-gather over NVLink replicates the table (padded to equal contributions)
-                const size_t cols = (size_t)sys.tables[i].columns, per = (cols + ctx->world - 1) / ctx->world;
-                const size_t lo = std::min(cols, (size_t)ctx->rank * per), hi = std::min(cols, lo + per);
-                d_vals[i].reset(new DevBuf(per * ctx->world * n));
-                DevBuf send(per * n);
-                if (hi - lo < per) OLA_CUDA(cudaMemsetAsync(send.p, 0, per * n * 8, ctx->stream));
-                if (hi > lo) OLA_CUDA(cudaMemcpyAsync(send.p, traces[i] + lo * n, (hi - lo) * n * 8, cudaMemcpyHostToDevice, ctx->stream));
-                canon_copy(ctx, send.p, send.p, per * n);
-                comm_allgather(ctx, send.p, d_vals[i]->p, per * n * 8);
-                OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (sharded_upload) {
+                const size_t per = ((size_t)sys.tables[i].columns + ctx->world - 1) / ctx->world;
+                OLA_CUDA(cudaStreamWaitEvent(ctx->stream, uploaded[i], 0));
+                canon_copy(ctx, slices[i]->p, slices[i]->p, per * n);
+                comm_allgather(ctx, slices[i]->p, d_vals[i]->p, per * n * 8);
             } else if (prefetch) {
                 OLA_CUDA(cudaStreamWaitEvent(ctx->stream, uploaded[i], 0));
                 canon_copy(ctx, d_vals[i]->p, d_vals[i]->p, cnt);  // the Z kernels read these values with canonical-input arithmetic
@@ -875,6 +886,10 @@ std::vector<uint8_t> prove_all(ola_ctx* ctx, const std::vector<int>& table_ids, 
     } catch (...) {
         if (prefetch) cudaStreamSynchronize(ctx->copy_stream);  // no copy may outlive the buffers released by unwinding
         throw;
+    }
+    if (sharded_upload) {
+        OLA_CUDA(cudaStreamSynchronize(ctx->stream));  // the all-gathers have consumed the slices
+        slices.clear();
     }
     for (size_t i = 0; i < T; ++i) ch.observe_cap(batch_cap(ctx, commits[i]->b));
     // cross_table_lookup_data: challenges, then Z instances per table in registry order

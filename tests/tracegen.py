@@ -513,9 +513,9 @@ def hash_system_valid(orc, rng, beta=0x1234567890ABCDEF % P):
 # them with the quotient-degree check on tests the transcription against the reference's own trace semantics.
 # ---------------------------------------------------------------------------------------------------------------------
 OPCODE_SHIFT = {"add": 31, "mul": 30, "eq": 29, "assert": 28, "mov": 27, "jmp": 26, "cjmp": 25, "call": 24, "ret": 23, "mload": 22,
-                "mstore": 21, "end": 20, "range": 19, "and": 18, "or": 17, "xor": 16, "not": 15, "neq": 14, "gte": 13}
+                "mstore": 21, "end": 20, "range": 19, "and": 18, "or": 17, "xor": 16, "not": 15, "neq": 14, "gte": 13, "poseidon": 12}
 CPU_SELECTOR_COL = {"add": 66, "mul": 66, "eq": 66, "assert": 66, "neq": 66, "mov": 67, "jmp": 68, "cjmp": 69, "call": 70, "ret": 71,
-                    "mload": 72, "mstore": 73, "end": 74, "range": 75, "and": 76, "or": 76, "xor": 76, "not": 77, "gte": 78}
+                    "mload": 72, "mstore": 73, "end": 74, "range": 75, "and": 76, "or": 76, "xor": 76, "not": 77, "gte": 78, "poseidon": 79}
 
 
 def _finv(x):
@@ -535,7 +535,7 @@ def ola_encode(ins):
     op = ins[0]
     word = 1 << OPCODE_SHIFT[op]
     dst = op0 = op1 = None
-    if op in ("add", "mul", "eq", "neq", "gte", "and", "or", "xor"):
+    if op in ("add", "mul", "eq", "neq", "gte", "and", "or", "xor", "poseidon"):
         dst, op0, op1 = ins[1], ins[2], ins[3]
     elif op in ("mov", "not"):
         dst, op1 = ins[1], ins[2]
@@ -563,11 +563,11 @@ def ola_encode(ins):
     return [word] if imm is None else [word, imm]
 
 
-def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False):
+def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False, orc=None):
     """Run `program` (a list of instruction tuples, jump targets = word addresses) and return the [94][2^log_n] CPU table
     and the executed steps; with want_side_tables also the (op0, op1) pairs of the gte rows (Cmp table), their
     |op0 - op1| (RangeCheck rows looked by Cmp) and the operands of the range rows (RangeCheck rows looked by the CPU)."""
-    cmp_pairs, rc_cmp, rc_cpu, mem, mem_log, bit_ops = [], [], [], {}, [], []
+    cmp_pairs, rc_cmp, rc_cpu, mem, mem_log, bit_ops, psdn_calls = [], [], [], {}, [], [], []
     words, at_pc = [], {}
     for ins in program:
         enc = ola_encode(ins)
@@ -613,6 +613,40 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False):
                 r = int(a == b) if op == "eq" else int(a != b)
             regs[_reg(ins[1])] = r
             row["dst"], row["s_dst"] = r, _reg(ins[1])
+            pc += step
+        elif op == "poseidon":  # execute_inst_poseidon, lib.rs:1547-1685: hash `len` memory words at [op0] into 4 words at [dst]
+            assert orc is not None, "the poseidon opcode needs the oracle's permutation"
+            src = regs[_reg(ins[2])]
+            row["op0"], row["s_op0"] = src, _reg(ins[2])
+            ln = val(ins[3])
+            row["op1"] = ln
+            dst_addr = regs[_reg(ins[1])]
+            row["dst"], row["s_dst"] = dst_addr, _reg(ins[1])
+            assert ln > 0
+            chunk_rows = [dict(op0=src, acc=0, value=[0] * 8, cap=[0] * 4, hash=[0] * 12, ext=0)]  # the main line
+            state, hash_pre, read_ptr, perm_rows = [0] * 12, [0] * 12, 0, []
+            while True:
+                cnt = min(8, ln - read_ptr)
+                if cnt <= 0:
+                    break
+                for k in range(cnt):
+                    state[k] = mem[(src + read_ptr + k) % P]
+                    mem_log.append(((src + read_ptr + k) % P, clk, 1 << 12, 0, state[k]))
+                out = [int(x) for x in orc.poseidon(np.array(state, dtype=np.uint64))]
+                perm_rows.append((list(state), out))
+                chunk_rows.append(dict(op0=(src + read_ptr) % P, acc=read_ptr + cnt, value=list(state[0:8]), cap=list(hash_pre[8:12]),
+                                       hash=out, ext=1))
+                hash_pre = out
+                read_ptr += cnt
+                if read_ptr + 8 > ln:   # the next chunk is the (possibly empty) tail: positions past it keep the previous output
+                    tail = ln - read_ptr
+                    state = list(out) if tail == 0 else state[:0] + [0] * tail + out[tail:]
+                else:
+                    state = [0] * 8 + out[8:12]
+            for k in range(4):
+                mem[(dst_addr + k) % P] = hash_pre[k]
+                mem_log.append(((dst_addr + k) % P, clk, 1 << 12, 1, hash_pre[k]))
+            psdn_calls.append(dict(clk=clk, dst=dst_addr, op0=src, op1=ln, rows=chunk_rows, perms=perm_rows))
             pc += step
         elif op in ("and", "or", "xor"):  # execute_inst_bitwise, lib.rs:1041-1105
             a = regs[_reg(ins[2])]
@@ -729,6 +763,9 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False):
         t[86, k:] = 1
         t[87, k:] = 0
         t[93, k:] = 1
+    if want_side_tables == "all+poseidon":
+        return t, steps, cmp_pairs, rc_cmp, rc_cpu, mem_log, bit_ops, psdn_calls
+    assert not psdn_calls, "poseidon calls are only returned with want_side_tables='all+poseidon'"
     if want_side_tables == "all":
         return t, steps, cmp_pairs, rc_cmp, rc_cpu, mem_log, bit_ops
     assert not bit_ops or not want_side_tables, "bitwise rows are only returned with want_side_tables='all'"
@@ -755,7 +792,37 @@ def program_rows_of_run(program, steps):
     return prog_rows, exec_rows
 
 
-MEM_OP_SELECTOR = {1 << 22: 6, 1 << 21: 7, 1 << 24: 8, 1 << 23: 9}  # mload, mstore, call, ret (memory/columns.rs:16-19)
+MEM_OP_SELECTOR = {1 << 22: 6, 1 << 21: 7, 1 << 24: 8, 1 << 23: 9, 1 << 12: 13}  # mload, mstore, call, ret, poseidon (memory/columns.rs:16-23)
+
+
+def poseidon_chunk_trace_from_calls(calls, log_n):
+    """PoseidonChunk table of a VM run (insert_poseidon_chunk rows of execute_inst_poseidon + generate_poseidon_chunk_trace,
+    generation/poseidon_chunk.rs:7-88): per call one main line and one ext line per absorbed chunk.  Returns (table [53][n],
+    poseidon rows (input[12], output[12]))."""
+    n = 1 << log_n
+    t = np.zeros((53, n), dtype=np.uint64)
+    row, psdn = 0, []
+    for c in calls:
+        for r in c["rows"]:
+            t[0:8, row] = [0, 0, c["clk"], OP_POSEIDON, r["op0"], c["op1"], c["dst"], r["acc"]]
+            t[8:16, row] = r["value"]
+            t[16:20, row] = r["cap"]
+            t[20:32, row] = r["hash"]
+            t[32, row] = r["ext"]
+            result = c["op1"] == r["acc"]
+            t[33, row] = 1 if result else 0
+            pad = c["op1"] % 8 if result else 0
+            if pad:
+                t[34 + pad, row] = 1
+            t[42, row] = 1 - r["ext"]
+            if r["ext"]:
+                t[43:51, row] = [1 if (pad == 0 or k < pad) else 0 for k in range(8)]
+            t[51, row] = r["ext"]
+            row += 1
+        psdn += c["perms"]
+    assert 2 <= row <= n
+    t[52, row:] = 1
+    return t, psdn
 
 
 def memory_trace_from_log(mem_log, log_n):
@@ -820,7 +887,7 @@ def memory_trace_from_log(mem_log, log_n):
     return t, rc_sort
 
 
-def calls_program(n_iter, linear=False, bitwise=False):
+def calls_program(n_iter, linear=False, bitwise=False, poseidon=False):
     """Exercises memory and builtin opcodes on top of fib_program's set: a stack frame (mstore / mload relative to r9), a
     call / ret pair, gte comparisons in both directions and u32 range checks; with bitwise=True also and / or / xor in the
     callee.  linear=True replaces the Fibonacci step by r1 + r2 (the loop counter) so that long runs stay inside the u32
@@ -844,6 +911,22 @@ def calls_program(n_iter, linear=False, bitwise=False):
         ("mload", "r7", "r9", -3),        # last sum the callee spilled
         ("eq", "r8", "r7", "r1"),
         ("assert", "r8"),
+    ] + ([
+        # poseidon=True: spill 11 words at [40..51) and hash them (one full chunk + a tail of 3) into [60..64), then a second
+        # call over exactly 8 words (a single full chunk) into [64..68) and a short one (5 words) into [68..72)
+        ("mov", "r3", 40),
+        ("mstore", "r3", 0, "r0"), ("mstore", "r3", 1, "r1"), ("mstore", "r3", 2, "r2"), ("mstore", "r3", 3, "r7"),
+        ("mstore", "r3", 4, "r9"), ("mstore", "r3", 5, "r1"), ("mstore", "r3", 6, "r0"), ("mstore", "r3", 7, "r2"),
+        ("mstore", "r3", 8, "r8"), ("mstore", "r3", 9, "r7"), ("mstore", "r3", 10, "r1"),
+        ("mov", "r4", 60),
+        ("poseidon", "r4", "r3", 11),
+        ("mov", "r4", 64),
+        ("mov", "r5", 8),
+        ("poseidon", "r4", "r3", "r5"),
+        ("mov", "r4", 68),
+        ("poseidon", "r4", "r3", 5),
+        ("mload", "r6", "r4", 0),         # read one digest word back
+    ] if poseidon else []) + [
         ("jmp", "done"),
         "step",                           # (r0, r1) <- (r1, r0 + r1); spills the sum to [fp-3]
         ("add", "r3", "r1", "r2") if linear else ("add", "r3", "r0", "r1"),
@@ -896,31 +979,42 @@ def fib_program(n_iter):
 
 
 def real_program_system(orc, rng, n_iter=12, linear=False, cpu_log=9, mem_log_n=7, cmp_log=6, prog_log=9, beta=0x1234567890ABCDEF % P,
-                        bitwise=False, beta_bitwise=0x0FEDCBA987654321 % P, bitwise_log=9):
+                        bitwise=False, beta_bitwise=0x0FEDCBA987654321 % P, bitwise_log=9, poseidon=False):
     """An eight-table system produced by RUNNING a program: [Cpu, Memory, Cmp, RangeCheck, Poseidon, StorageAccess, Program,
     ProgChunk]; with bitwise=True the program also executes and / or / xor and the Bitwise table (with its own compress
-    challenge) joins as a ninth table behind the cpu->bitwise lookup.  The VM (cpu_vm_trace) fills the CPU table and logs memory accesses, comparisons and range checks; the
+    challenge) joins as a ninth table behind the cpu->bitwise lookup; with poseidon=True the program also hashes memory
+    ranges with the poseidon opcode and PoseidonChunk joins (cpu->poseidon_chunk, poseidon_chunk->memory x12,
+    poseidon_chunk->poseidon).  The VM (cpu_vm_trace) fills the CPU table and logs memory accesses, comparisons and range checks; the
     Memory / Cmp / RangeCheck tables are generated from those logs the way the executor does; the Program table holds the
     program's words and one executed line per fetched word; ProgChunk hashes the program (Poseidon sponge over lines of
     8 words), its digest is read from the storage tree at code address 0, and every sponge / Merkle hash is a Poseidon
     row.  Lookups with real data: cpu->memory (x3), memory->rangecheck, cpu->cmp, cmp->rangecheck, cpu->rangecheck,
     cpu->program (instruction and immediate), prog_chunk->program, prog_chunk->poseidon, prog_chunk->storage,
     storage->poseidon.  Returns (table_ids, traces, compress_challenges)."""
-    prog = calls_program(n_iter, linear=linear, bitwise=bitwise)
-    cpu_t, steps, cmp_pairs, rc_cmp, rc_cpu, mlog, bit_ops = cpu_vm_trace(prog, cpu_log, want_side_tables="all")
+    prog = calls_program(n_iter, linear=linear, bitwise=bitwise, poseidon=poseidon)
+    cpu_t, steps, cmp_pairs, rc_cmp, rc_cpu, mlog, bit_ops, psdn_calls = cpu_vm_trace(prog, cpu_log, want_side_tables="all+poseidon", orc=orc)
     mem_t, rc_sort = memory_trace_from_log(mlog, mem_log_n)
     cmp_t = cmp_trace(cmp_pairs, cmp_log)
     rc_t = rangecheck_trace(rc_cmp, cpu_vals=rc_cpu, mem_sort_vals=rc_sort)
     prog_rows, exec_rows = program_rows_of_run(prog, steps)
     words = [r[5] for r in prog_rows]
-    pc_t, psdn_prog, lines, roots = prog_chunk_valid_trace(orc, rng, 3, programs=[([0, 0, 0, 0], words)])
+    chunk_log = max(3, ((len(words) + 7) // 8 - 1).bit_length())
+    pc_t, psdn_prog, lines, roots = prog_chunk_valid_trace(orc, rng, chunk_log, programs=[([0, 0, 0, 0], words)])
     assert lines == prog_rows
     _, leaf = roots[0]
     st, psdn_st = storage_valid_trace(orc, rng, 8, [dict(addr_bits=[0] * 256, leaf=leaf, pre_leaf=leaf, is_write=0, for_prog=1)])
     rows = [(inp, [1, 0, 0, 0]) for inp, _ in psdn_prog]
     rows += [(inp, [0, 0, 1, 0] if is_leaf else [0, 0, 0, 1]) for inp, _, is_leaf in psdn_st]
+    if poseidon:
+        assert bitwise, "the ten-table system includes the Bitwise table"
+        pch, psdn_chunk = poseidon_chunk_trace_from_calls(psdn_calls, 4)
+        rows += [(inp, [1, 0, 0, 0]) for inp, _ in psdn_chunk]
     ps = poseidon_valid_trace(orc, 10, rows)
     pt = program_valid_trace(rng, prog_log, beta, prog_rows=prog_rows, exec_rows=exec_rows)
+    if poseidon:
+        bw = bitwise_valid_trace(rng, bitwise_log, beta_bitwise, ops=bit_ops)
+        return ([0, 1, 2, 3, 4, 5, 6, 7, 10, 11], [cpu_t, mem_t, bw, cmp_t, rc_t, ps, pch, st, pt, pc_t],
+                [0, 0, beta_bitwise, 0, 0, 0, 0, 0, beta, 0])
     if bitwise:
         bw = bitwise_valid_trace(rng, bitwise_log, beta_bitwise, ops=bit_ops)
         return [0, 1, 2, 3, 4, 5, 7, 10, 11], [cpu_t, mem_t, bw, cmp_t, rc_t, ps, st, pt, pc_t], [0, 0, beta_bitwise, 0, 0, 0, 0, beta, 0]

@@ -173,9 +173,9 @@ def test_real_program_run_systems(ctx, orc):
     big = olavm_b200.prove_with_traces(ctx, ids, traces, compress_challenges=cc)
     ok, msg = orc.stark_verify(ids, big)
     assert ok, msg
-    # ten tables: and / or / xor rows with the Bitwise table, poseidon calls with PoseidonChunk
-    ids, traces, cc = tracegen.real_program_system(orc, np.random.default_rng(7), bitwise=True, poseidon=True, mem_log_n=8)
-    assert len(ids) == 10
+    # eleven tables: and / or / xor rows with the Bitwise table, poseidon calls with PoseidonChunk, tstore / tload with Tape
+    ids, traces, cc = tracegen.real_program_system(orc, np.random.default_rng(7), bitwise=True, poseidon=True, tape=True, mem_log_n=8)
+    assert len(ids) == 11
     got = olavm_b200.prove_with_traces(ctx, ids, traces, compress_challenges=cc)
     assert got == orc.stark_prove(ids, traces, compress_challenges=cc)
     ok, msg = olavm_b200.verify_proof(ids, got)

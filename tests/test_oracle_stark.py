@@ -349,27 +349,37 @@ def test_real_memory_table_binds(orc, case):
         assert not ok
 
 
-def test_ten_table_system_of_a_real_program_run(orc):
-    """tracegen.real_program_system(bitwise=True, poseidon=True): CPU, Memory, Bitwise, Cmp, RangeCheck, Poseidon,
-    PoseidonChunk, StorageAccess, Program and ProgChunk tables of ONE program run (stack frames, call / ret, comparisons,
-    range checks, and / or / xor, three poseidon calls over memory ranges of 11, 8 and 5 words, the program hashed by
-    ProgChunk and its digest read from the storage tree); every lookup between these tables carries real data; degree
-    check on, the verifier accepts."""
-    ids, traces, cc = tracegen.real_program_system(orc, np.random.default_rng(5), bitwise=True, poseidon=True, mem_log_n=8)
-    assert ids == [0, 1, 2, 3, 4, 5, 6, 7, 10, 11]
+def test_eleven_table_system_of_a_real_program_run(orc):
+    """tracegen.real_program_system(bitwise, poseidon, tape): CPU, Memory, Bitwise, Cmp, RangeCheck, Poseidon, PoseidonChunk,
+    StorageAccess, Tape, Program and ProgChunk tables of ONE program run (stack frames, call / ret, comparisons, range
+    checks, and / or / xor, three poseidon calls over memory ranges of 11, 8 and 5 words, tstore / tload with their CPU
+    ext lines, the program hashed by ProgChunk and its digest read from the storage tree) -- every table except SCCall,
+    which needs a second contract; every lookup between these tables carries real data; degree check on, the verifier
+    accepts."""
+    ids, traces, cc = tracegen.real_program_system(orc, np.random.default_rng(5), bitwise=True, poseidon=True, tape=True, mem_log_n=8)
+    assert ids == [0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 11]
     proof = orc.stark_prove(ids, traces, compress_challenges=cc)
     ok, msg = orc.stark_verify(ids, proof)
     assert ok, msg
     # the tables whose quotient_degree_factor is a power of two cannot be checked by trim_to_len (prover.rs:463-473):
     # a broken cell in them is the verifier's to catch.  Program: a fetched word the program does not contain;
     # Bitwise: a wrong result byte.  (Each proven alone: their lookups into absent tables are dropped.)
-    prog_t = traces[8].copy()
+    prog_t = traces[9].copy()
     prog_t[13, 3] = int(prog_t[13, 3]) ^ 1
-    prog_t[14, 3] = tracegen._horner(prog_t[8:14, 3], cc[8])
-    ok, msg = orc.stark_verify([10], orc.stark_prove([10], [prog_t], compress_challenges=[cc[8]]))
+    prog_t[14, 3] = tracegen._horner(prog_t[8:14, 3], cc[9])
+    ok, msg = orc.stark_verify([10], orc.stark_prove([10], [prog_t], compress_challenges=[cc[9]]))
     assert not ok and "ProgramStark" in msg
-    ok, msg = orc.stark_verify([10], orc.stark_prove([10], [traces[8]], compress_challenges=[cc[8]]))
+    ok, msg = orc.stark_verify([10], orc.stark_prove([10], [traces[9]], compress_challenges=[cc[9]]))
     assert ok, msg
+    # Tape: a tload that returns another value than the tstore wrote
+    tape_t = traces[8].copy()
+    k = next(i for i in range(tape_t.shape[1]) if tape_t[2, i] == 1 << 9 and tape_t[5, i] == 1)
+    tape_t[4, k] = (int(tape_t[4, k]) + 1) % tracegen.P
+    try:
+        ok, msg = orc.stark_verify([8], orc.stark_prove([8], [tape_t]))
+    except orc.StarkError:
+        ok = False
+    assert not ok
     # PoseidonChunk + Poseidon + Memory: a digest word written to memory that is not the hash output
     ids3, mem_t = [1, 5, 6], traces[1].copy()
     k = next(i for i in range(mem_t.shape[1]) if mem_t[13, i] == 1 and mem_t[17, i] == 1)  # a poseidon write

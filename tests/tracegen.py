@@ -513,9 +513,9 @@ def hash_system_valid(orc, rng, beta=0x1234567890ABCDEF % P):
 # them with the quotient-degree check on tests the transcription against the reference's own trace semantics.
 # ---------------------------------------------------------------------------------------------------------------------
 OPCODE_SHIFT = {"add": 31, "mul": 30, "eq": 29, "assert": 28, "mov": 27, "jmp": 26, "cjmp": 25, "call": 24, "ret": 23, "mload": 22,
-                "mstore": 21, "end": 20, "range": 19, "and": 18, "or": 17, "xor": 16, "not": 15, "neq": 14, "gte": 13, "poseidon": 12}
+                "mstore": 21, "end": 20, "range": 19, "and": 18, "or": 17, "xor": 16, "not": 15, "neq": 14, "gte": 13, "poseidon": 12, "tload": 9, "tstore": 8}
 CPU_SELECTOR_COL = {"add": 66, "mul": 66, "eq": 66, "assert": 66, "neq": 66, "mov": 67, "jmp": 68, "cjmp": 69, "call": 70, "ret": 71,
-                    "mload": 72, "mstore": 73, "end": 74, "range": 75, "and": 76, "or": 76, "xor": 76, "not": 77, "gte": 78, "poseidon": 79}
+                    "mload": 72, "mstore": 73, "end": 74, "range": 75, "and": 76, "or": 76, "xor": 76, "not": 77, "gte": 78, "poseidon": 79, "tload": 82, "tstore": 83}
 
 
 def _finv(x):
@@ -535,8 +535,10 @@ def ola_encode(ins):
     op = ins[0]
     word = 1 << OPCODE_SHIFT[op]
     dst = op0 = op1 = None
-    if op in ("add", "mul", "eq", "neq", "gte", "and", "or", "xor", "poseidon"):
+    if op in ("add", "mul", "eq", "neq", "gte", "and", "or", "xor", "poseidon", "tload"):
         dst, op0, op1 = ins[1], ins[2], ins[3]
+    elif op == "tstore":
+        op0, op1 = ins[1], ins[2]
     elif op in ("mov", "not"):
         dst, op1 = ins[1], ins[2]
     elif op == "cjmp":
@@ -568,6 +570,7 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False, orc=
     and the executed steps; with want_side_tables also the (op0, op1) pairs of the gte rows (Cmp table), their
     |op0 - op1| (RangeCheck rows looked by Cmp) and the operands of the range rows (RangeCheck rows looked by the CPU)."""
     cmp_pairs, rc_cmp, rc_cpu, mem, mem_log, bit_ops, psdn_calls = [], [], [], {}, [], [], []
+    tp, tape, tape_log = 0, {}, {}   # tape pointer, tape contents, per-address access log (gen_tape_table order)
     words, at_pc = [], {}
     for ins in program:
         enc = ola_encode(ins)
@@ -579,7 +582,7 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False, orc=
         assert pc in at_pc, f"pc {pc} is not an instruction boundary"
         ins, enc = at_pc[pc]
         op, step = ins[0], len(enc)
-        row = {"clk": clk, "pc": pc, "regs": list(regs), "inst": enc[0], "imm": enc[1] if step == 2 else 0,
+        row = {"clk": clk, "pc": pc, "tp": tp, "regs": list(regs), "inst": enc[0], "imm": enc[1] if step == 2 else 0,
                "op1_imm": 1 if step == 2 else 0, "opcode": 1 << OPCODE_SHIFT[op], "op": op,
                "op0": 0, "op1": 0, "dst": 0, "aux0": 0, "aux1": 0, "s_op0": None, "s_op1": None, "s_dst": None}
 
@@ -614,6 +617,52 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False, orc=
             regs[_reg(ins[1])] = r
             row["dst"], row["s_dst"] = r, _reg(ins[1])
             pc += step
+        elif op in ("tstore", "tload"):  # execute_inst_tstore / _tload + tape_copy!, lib.rs:153-181, :1687-1846
+            ext_rows = []
+            if op == "tstore":   # copy `len` memory words at [op0] to the tape at tp, then tp += len
+                base = regs[_reg(ins[1])]
+                row["op0"], row["s_op0"] = base, _reg(ins[1])
+                ln = val(ins[2])
+                row["op1"] = ln
+                tape_base, mask = tp, 1 << 8
+            else:                # tload dst flag op1: flag 1 -> the last `op1` tape words, flag 0 -> the single word at tape address op1
+                base = regs[_reg(ins[1])]
+                row["dst"], row["s_dst"] = base, _reg(ins[1])
+                flag = regs[_reg(ins[2])]
+                row["aux1"], row["s_op0"] = flag, _reg(ins[2])
+                v1 = val(ins[3])
+                row["op1"] = v1
+                assert flag in (0, 1), "TloadFlagInvalid"
+                row["op0"] = flag
+                tape_base, ln, mask = ((tp - v1) % P, v1, 1 << 9) if flag == 1 else (v1, 1, 1 << 9)
+            for k in range(ln):
+                maddr, taddr = (base + k) % P, tape_base + k
+                e = dict(row)
+                e["regs"] = list(row["regs"])
+                e["is_ext"], e["ext_cnt"], e["filter_tape_looking"] = 1, k + 1, 1
+                e["aux0"], e["s_op0_0"] = maddr, taddr
+                if op == "tstore":
+                    v = mem[maddr]
+                    mem_log.append((maddr, clk, mask, 0, v))
+                    tape[taddr] = v
+                    tape_log.setdefault(taddr, []).append((0, mask, v, 1))
+                else:
+                    v = tape[taddr]
+                    tape_log[taddr].append((tape_log[taddr][-1][0], mask, v, 1))
+                    mem[maddr] = v
+                    mem_log.append((maddr, clk, mask, 1, v))
+                e["aux1"] = v
+                ext_rows.append(e)
+            row["ext_len"] = ln
+            for e in ext_rows:
+                e["ext_len"] = ln
+            steps.append(row)
+            steps.extend(ext_rows)
+            if op == "tstore":
+                tp += ln
+            pc += step
+            clk += 1
+            continue
         elif op == "poseidon":  # execute_inst_poseidon, lib.rs:1547-1685: hash `len` memory words at [op0] into 4 words at [dst]
             assert orc is not None, "the poseidon opcode needs the oracle's permutation"
             src = regs[_reg(ins[2])]
@@ -739,7 +788,8 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False, orc=
     assert len(steps) <= n, f"{len(steps)} steps do not fit 2^{log_n} rows"
     t = np.zeros((94, n), dtype=np.uint64)
     for i, s in enumerate(steps):  # generation/cpu.rs:62-178
-        t[12, i], t[13, i] = s["clk"], s["pc"]
+        t[11, i], t[12, i], t[13, i] = s["tp"], s["clk"], s["pc"]
+        t[14, i], t[15, i] = s.get("is_ext", 0), s.get("ext_cnt", 0)
         t[16:26, i] = s["regs"]
         t[26, i], t[27, i], t[28, i], t[29, i] = s["inst"], s["op1_imm"], s["opcode"], s["imm"]
         t[30, i], t[31, i], t[32, i], t[33, i], t[34, i] = s["op0"], s["op1"], s["dst"], s["aux0"], s["aux1"]
@@ -749,11 +799,14 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False, orc=
             t[46 + s["s_op1"], i] = 1
         if s["s_dst"] is not None:
             t[56 + s["s_dst"], i] = 1
+        if "s_op0_0" in s:
+            t[36, i] = s["s_op0_0"]                     # ext lines of tload / tstore keep the tape address in s_op0[0]
         t[CPU_SELECTOR_COL[s["op"]], i] = 1
         t[85, i] = 1                                  # is_entry_sc: env_idx == 0
-        t[86, i] = 1                                  # is_next_line_diff_inst: ext_length (0) == ext_cnt (0)
+        t[86, i] = 1 if s.get("ext_len", 0) == s.get("ext_cnt", 0) else 0   # is_next_line_diff_inst: ext_length == ext_cnt
         t[87, i] = 0 if s["op"] == "end" else 1        # is_next_line_same_tx
-        t[92, i] = s["op1_imm"]                        # filter_looking_prog_imm: mload / mstore / any immediate operand
+        t[88, i] = s.get("filter_tape_looking", 0)
+        t[92, i] = 0 if s.get("is_ext", 0) else s["op1_imm"]   # filter_looking_prog_imm: mload / mstore / any immediate operand
     k = len(steps)
     if k != n:  # padding, generation/cpu.rs:180-208
         t[26, k:] = t[26, k - 1]
@@ -763,6 +816,9 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False, orc=
         t[86, k:] = 1
         t[87, k:] = 0
         t[93, k:] = 1
+    if want_side_tables == "all+tape":
+        return t, steps, cmp_pairs, rc_cmp, rc_cpu, mem_log, bit_ops, psdn_calls, tape_log
+    assert not tape_log, "tape rows are only returned with want_side_tables='all+tape'"
     if want_side_tables == "all+poseidon":
         return t, steps, cmp_pairs, rc_cmp, rc_cpu, mem_log, bit_ops, psdn_calls
     assert not psdn_calls, "poseidon calls are only returned with want_side_tables='all+poseidon'"
@@ -786,13 +842,32 @@ def program_rows_of_run(program, steps):
     prog_rows = [(0, 0, 0, 0, pc, w) for pc, w in enumerate(words)]
     exec_rows = []
     for s in steps:
+        if s.get("is_ext", 0):
+            continue  # ext lines fetch nothing (generate_prog_trace skips them, prog.rs:58-60)
         exec_rows.append((0, 0, 0, 0, s["pc"], s["inst"]))
         if s["op1_imm"] == 1 or s["op"] in ("mload", "mstore"):
             exec_rows.append((0, 0, 0, 0, s["pc"] + 1, s["imm"]))
     return prog_rows, exec_rows
 
 
-MEM_OP_SELECTOR = {1 << 22: 6, 1 << 21: 7, 1 << 24: 8, 1 << 23: 9, 1 << 12: 13}  # mload, mstore, call, ret, poseidon (memory/columns.rs:16-23)
+MEM_OP_SELECTOR = {1 << 22: 6, 1 << 21: 7, 1 << 24: 8, 1 << 23: 9, 1 << 9: 10, 1 << 8: 11, 1 << 12: 13}  # mload, mstore, call, ret, tload, tstore, poseidon (memory/columns.rs:16-23)
+
+
+def tape_trace_from_log(tape_log, log_n):
+    """Tape table of a VM run: gen_tape_table (executor/src/trace.rs:400-414: cells grouped by tape address in ascending
+    order, access order inside an address) + generate_tape_trace (generation/tape.rs:10-73: padding repeats the last row
+    as an unlooked tload).  Columns (tape/columns.rs:3-9): tx_idx, is_init_seg, opcode, addr, value, filter_looked."""
+    n = 1 << log_n
+    t = np.zeros((6, n), dtype=np.uint64)
+    row = 0
+    for addr in sorted(tape_log):
+        for is_init, op, value, looked in tape_log[addr]:
+            t[:, row] = [0, is_init, op, addr, value, looked]
+            row += 1
+    assert 2 <= row <= n
+    if row != n:
+        t[1, row:], t[2, row:], t[3, row:], t[4, row:] = t[1, row - 1], 1 << 9, t[3, row - 1], t[4, row - 1]
+    return t
 
 
 def poseidon_chunk_trace_from_calls(calls, log_n):
@@ -887,7 +962,7 @@ def memory_trace_from_log(mem_log, log_n):
     return t, rc_sort
 
 
-def calls_program(n_iter, linear=False, bitwise=False, poseidon=False):
+def calls_program(n_iter, linear=False, bitwise=False, poseidon=False, tape=False):
     """Exercises memory and builtin opcodes on top of fib_program's set: a stack frame (mstore / mload relative to r9), a
     call / ret pair, gte comparisons in both directions and u32 range checks; with bitwise=True also and / or / xor in the
     callee.  linear=True replaces the Fibonacci step by r1 + r2 (the loop counter) so that long runs stay inside the u32
@@ -926,7 +1001,21 @@ def calls_program(n_iter, linear=False, bitwise=False, poseidon=False):
         ("mov", "r4", 68),
         ("poseidon", "r4", "r3", 5),
         ("mload", "r6", "r4", 0),         # read one digest word back
-    ] if poseidon else []) + [
+    ] if poseidon else []) + ([
+        # tape=True: copy three stack words to the tape (tp 0 -> 3), read the last two back (flag 1) and then the word at
+        # tape address 0 (flag 0) into another stack range, and check one of them
+        ("mstore", "r9", -8, "r1"), ("mstore", "r9", -7, "r2"), ("mstore", "r9", -6, "r7"),
+        ("add", "r4", "r9", -8),
+        ("tstore", "r4", 3),
+        ("add", "r5", "r9", -12),
+        ("mov", "r6", 1),
+        ("tload", "r5", "r6", 2),
+        ("mov", "r6", 0),
+        ("tload", "r5", "r6", 0),
+        ("mload", "r3", "r9", -12),
+        ("eq", "r8", "r3", "r1"),
+        ("assert", "r8"),
+    ] if tape else []) + [
         ("jmp", "done"),
         "step",                           # (r0, r1) <- (r1, r0 + r1); spills the sum to [fp-3]
         ("add", "r3", "r1", "r2") if linear else ("add", "r3", "r0", "r1"),
@@ -979,20 +1068,21 @@ def fib_program(n_iter):
 
 
 def real_program_system(orc, rng, n_iter=12, linear=False, cpu_log=9, mem_log_n=7, cmp_log=6, prog_log=9, beta=0x1234567890ABCDEF % P,
-                        bitwise=False, beta_bitwise=0x0FEDCBA987654321 % P, bitwise_log=9, poseidon=False):
+                        bitwise=False, beta_bitwise=0x0FEDCBA987654321 % P, bitwise_log=9, poseidon=False, tape=False):
     """An eight-table system produced by RUNNING a program: [Cpu, Memory, Cmp, RangeCheck, Poseidon, StorageAccess, Program,
     ProgChunk]; with bitwise=True the program also executes and / or / xor and the Bitwise table (with its own compress
     challenge) joins as a ninth table behind the cpu->bitwise lookup; with poseidon=True the program also hashes memory
     ranges with the poseidon opcode and PoseidonChunk joins (cpu->poseidon_chunk, poseidon_chunk->memory x12,
-    poseidon_chunk->poseidon).  The VM (cpu_vm_trace) fills the CPU table and logs memory accesses, comparisons and range checks; the
+    poseidon_chunk->poseidon); with tape=True also tstore / tload (CPU ext lines) and the Tape table: eleven of the twelve
+    tables -- only SCCall, which needs a second contract, is not reached by a run.  The VM (cpu_vm_trace) fills the CPU table and logs memory accesses, comparisons and range checks; the
     Memory / Cmp / RangeCheck tables are generated from those logs the way the executor does; the Program table holds the
     program's words and one executed line per fetched word; ProgChunk hashes the program (Poseidon sponge over lines of
     8 words), its digest is read from the storage tree at code address 0, and every sponge / Merkle hash is a Poseidon
     row.  Lookups with real data: cpu->memory (x3), memory->rangecheck, cpu->cmp, cmp->rangecheck, cpu->rangecheck,
     cpu->program (instruction and immediate), prog_chunk->program, prog_chunk->poseidon, prog_chunk->storage,
     storage->poseidon.  Returns (table_ids, traces, compress_challenges)."""
-    prog = calls_program(n_iter, linear=linear, bitwise=bitwise, poseidon=poseidon)
-    cpu_t, steps, cmp_pairs, rc_cmp, rc_cpu, mlog, bit_ops, psdn_calls = cpu_vm_trace(prog, cpu_log, want_side_tables="all+poseidon", orc=orc)
+    prog = calls_program(n_iter, linear=linear, bitwise=bitwise, poseidon=poseidon, tape=tape)
+    cpu_t, steps, cmp_pairs, rc_cmp, rc_cpu, mlog, bit_ops, psdn_calls, tape_log = cpu_vm_trace(prog, cpu_log, want_side_tables="all+tape", orc=orc)
     mem_t, rc_sort = memory_trace_from_log(mlog, mem_log_n)
     cmp_t = cmp_trace(cmp_pairs, cmp_log)
     rc_t = rangecheck_trace(rc_cmp, cpu_vals=rc_cpu, mem_sort_vals=rc_sort)
@@ -1011,6 +1101,12 @@ def real_program_system(orc, rng, n_iter=12, linear=False, cpu_log=9, mem_log_n=
         rows += [(inp, [1, 0, 0, 0]) for inp, _ in psdn_chunk]
     ps = poseidon_valid_trace(orc, 10, rows)
     pt = program_valid_trace(rng, prog_log, beta, prog_rows=prog_rows, exec_rows=exec_rows)
+    if tape:
+        assert poseidon and bitwise, "the eleven-table system includes Bitwise and PoseidonChunk"
+        bw = bitwise_valid_trace(rng, bitwise_log, beta_bitwise, ops=bit_ops)
+        tp_t = tape_trace_from_log(tape_log, 3)
+        return ([0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 11], [cpu_t, mem_t, bw, cmp_t, rc_t, ps, pch, st, tp_t, pt, pc_t],
+                [0, 0, beta_bitwise, 0, 0, 0, 0, 0, 0, beta, 0])
     if poseidon:
         bw = bitwise_valid_trace(rng, bitwise_log, beta_bitwise, ops=bit_ops)
         return ([0, 1, 2, 3, 4, 5, 6, 7, 10, 11], [cpu_t, mem_t, bw, cmp_t, rc_t, ps, pch, st, pt, pc_t],

@@ -29,7 +29,7 @@ for line in open(log):
     ins = kern[k]
     loop = None
     for a, t in ins:
-        mm = re.search(r"BRA\s+(?:!?U?P\d+,\s*)?0x([0-9a-f]+)", t)
+        mm = re.search(r"BRA(?:\.U)?\s+(?:!?U?P\d+,\s*)?0x([0-9a-f]+)", t)
         if mm and int(mm.group(1), 16) < a:
             loop = (int(mm.group(1), 16), a)
     body = [t for a, t in ins if loop and loop[0] <= a <= loop[1] and not t.startswith("NOP")]

@@ -39,5 +39,8 @@ for line in open(log):
     unroll = max(1, round(main_ops / 8)) if main_ops >= 8 else 1
     per_iter = {op: v / unroll for op, v in mix.items() if v / unroll >= 0.5}
     total = sum(mix.values()) / unroll
+    if cyc <= 0 or not body:
+        print(f"KIND {k:2d} {name:34s} (loop optimised away by ptxas)")
+        continue
     print(f"KIND {k:2d} {name:34s} cycles/iter {cyc:8.2f}  instr/iter {total:6.1f}  IPC/SMSP {8 * total / cyc:5.3f}   " +
           " ".join(f"{op}:{v:.0f}" for op, v in sorted(per_iter.items(), key=lambda kv: -kv[1])[:6]))

@@ -1,5 +1,7 @@
 """GPU parity tests (-m gpu) of the STARK prover: proof BYTES from the CUDA path (through the C ABI) must equal the
 oracle's for the same traces, and the oracle's restated verify_proof must accept them."""
+import os
+
 import numpy as np
 import pytest
 
@@ -176,6 +178,20 @@ def test_real_program_run_systems(ctx, orc):
     # eleven tables: and / or / xor rows with the Bitwise table, poseidon calls with PoseidonChunk, tstore / tload with Tape
     ids, traces, cc = tracegen.real_program_system(orc, np.random.default_rng(7), bitwise=True, poseidon=True, tape=True, mem_log_n=8)
     assert len(ids) == 11
+    got = olavm_b200.prove_with_traces(ctx, ids, traces, compress_challenges=cc)
+    assert got == orc.stark_prove(ids, traces, compress_challenges=cc)
+    ok, msg = olavm_b200.verify_proof(ids, got)
+    assert ok, msg
+
+
+@pytest.mark.parametrize("name", ["fibo_recursive", "call", "tape", "bitwise", "comparison", "range_check"])
+def test_reference_programs_run_and_prove(ctx, orc, name):
+    """The reference's own assembly test programs (tests/golden/ola_programs.json) run through the restated VM: the GPU
+    prover's quotients pass the degree check, the proof bytes equal the oracle's and the product verifier accepts."""
+    import json
+
+    text = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ola_programs.json")))["programs"][name]
+    ids, traces, cc, steps = tracegen.run_system(orc, np.random.default_rng(3), tracegen.parse_ola_asm(text))
     got = olavm_b200.prove_with_traces(ctx, ids, traces, compress_challenges=cc)
     assert got == orc.stark_prove(ids, traces, compress_challenges=cc)
     ok, msg = olavm_b200.verify_proof(ids, got)

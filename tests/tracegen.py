@@ -1116,3 +1116,90 @@ def real_program_system(orc, rng, n_iter=12, linear=False, cpu_log=9, mem_log_n=
         return [0, 1, 2, 3, 4, 5, 7, 10, 11], [cpu_t, mem_t, bw, cmp_t, rc_t, ps, st, pt, pc_t], [0, 0, beta_bitwise, 0, 0, 0, 0, beta, 0]
     ids = [0, 1, 3, 4, 5, 7, 10, 11]
     return ids, [cpu_t, mem_t, cmp_t, rc_t, ps, st, pt, pc_t], [0, 0, 0, 0, 0, 0, beta, 0]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Running the reference's own assembly test programs (assembler/test_data/asm/*.json, committed as
+# tests/golden/ola_programs.json by tools/extract_encoding_golden.py) through the VM above.
+# ---------------------------------------------------------------------------------------------------------------------
+def parse_ola_asm(text):
+    """Assembly text -> the VM's instruction tuples.  As the reference assembler does (assembler/src/relocate.rs:21-86,
+    encoder.rs): the scope labelled `main` moves to the front, an instruction occupies two words when its last operand is an
+    immediate or a label or when it is mload / mstore, labels resolve to word addresses.  Memory operands [rN], [rN,off]."""
+    import re
+
+    lines = [l.strip() for l in text.split("\n") if l.strip()]
+    scopes, cur = [], None
+    for l in lines:
+        if l.endswith(":") and not l.startswith("."):
+            cur = [l]
+            scopes.append(cur)
+        else:
+            assert cur is not None, "instruction before the first scope label"
+            cur.append(l)
+    scopes.sort(key=lambda sc: 0 if sc[0] == "main:" else 1)
+    assert scopes[0][0] == "main:", "no main scope"
+    is_reg = lambda a: re.fullmatch(r"r\d", a) is not None
+    labels, pc, insts = {}, 0, []
+    for l in (x for sc in scopes for x in sc):
+        if l.endswith(":"):
+            labels[l[:-1]] = pc
+            continue
+        parts = l.replace(", ", ",").split()
+        op, args = parts[0], parts[1:]
+        insts.append((op, args))
+        two = op in ("mload", "mstore") or (bool(args) and not (is_reg(args[-1]) or args[-1].startswith("[")))
+        pc += 2 if two else 1
+    out = []
+    for op, args in insts:
+        res = []
+        for a in args:
+            m = re.fullmatch(r"\[(r\d)(?:,([+-]?\d+))?\]", a)
+            if m:
+                res.append((m.group(1), int(m.group(2) or 0)))
+            elif is_reg(a):
+                res.append(a)
+            elif re.fullmatch(r"[+-]?\d+", a):
+                res.append(int(a))
+            else:
+                res.append(labels[a])
+        if op == "mstore":
+            (base, off), v = res
+            out.append(("mstore", base, off, v))
+        elif op == "mload":
+            dst, (base, off) = res
+            out.append(("mload", dst, base, off))
+        else:
+            out.append((op, *res))
+    return out
+
+
+def run_system(orc, rng, program, cpu_log=None, beta=0x1234567890ABCDEF % P, beta_bitwise=0x0FEDCBA987654321 % P):
+    """Run `program` (VM tuples) and build every table its run touches: always Cpu, Cmp, RangeCheck, Program; Memory, Bitwise,
+    Tape, Poseidon + PoseidonChunk when the run produced rows for them.  Returns (table_ids, traces, compress_challenges,
+    steps)."""
+    nsteps = len(cpu_vm_trace(program, 20, want_side_tables="all+tape", orc=orc)[1]) if cpu_log is None else None
+    if cpu_log is None:
+        cpu_log = max(4, (nsteps - 1).bit_length())
+    cpu_t, steps, cmp_pairs, rc_cmp, rc_cpu, mlog, bit_ops, psdn_calls, tape_log = cpu_vm_trace(program, cpu_log, want_side_tables="all+tape", orc=orc)
+    lg = lambda k, lo: max(lo, (max(k, 1) - 1).bit_length())
+    tabs = {0: cpu_t}
+    cc = {}
+    rc_sort = []
+    if len(mlog) >= 2:
+        tabs[1], rc_sort = memory_trace_from_log(mlog, lg(len(mlog) + 1, 2))
+    if bit_ops:
+        tabs[2] = bitwise_valid_trace(rng, 9, beta_bitwise, ops=bit_ops)
+        cc[2] = beta_bitwise
+    tabs[3] = cmp_trace(cmp_pairs, lg(len(cmp_pairs) + 1, 4))
+    tabs[4] = rangecheck_trace(rc_cmp, cpu_vals=rc_cpu, mem_sort_vals=rc_sort)
+    if psdn_calls:
+        tabs[6], psdn_rows = poseidon_chunk_trace_from_calls(psdn_calls, lg(sum(len(c["rows"]) for c in psdn_calls) + 1, 2))
+        tabs[5] = poseidon_valid_trace(orc, lg(len(psdn_rows) + 1, 4), [(inp, [1, 0, 0, 0]) for inp, _ in psdn_rows])
+    if tape_log:
+        tabs[8] = tape_trace_from_log(tape_log, lg(sum(len(v) for v in tape_log.values()) + 1, 2))
+    prog_rows, exec_rows = program_rows_of_run(program, steps)
+    tabs[10] = program_valid_trace(rng, lg(max(len(prog_rows), len(exec_rows)) + 1, 2), beta, prog_rows=prog_rows, exec_rows=exec_rows)
+    cc[10] = beta
+    ids = sorted(tabs)
+    return ids, [tabs[i] for i in ids], [cc.get(i, 0) for i in ids], steps

@@ -116,6 +116,16 @@ def main():
     path = os.path.join(ROOT, "tests/golden/ola_encoding.json")
     json.dump(out, open(path, "w"), indent=0)
     print(path, len(pairs), "distinct pairs from", sum(per_contract.values()), "instructions", os.path.getsize(path), "bytes")
+    # the reference's prophet-free assembly test programs that only use modelled opcodes (executor/src/tests.rs runs them):
+    # inputs of tests/test_oracle_stark.py::test_reference_programs_run_and_prove
+    progs = {}
+    for name in ("bitwise", "range_check", "comparison", "fibo_recursive", "tape", "call"):
+        d = json.load(open(os.path.join(REF, "asm", name + ".json")))
+        assert not d.get("prophets")
+        progs[name] = d["program"]
+    path = os.path.join(ROOT, "tests/golden/ola_programs.json")
+    json.dump({"source": "assembler/test_data/asm/<name>.json, field program", "programs": progs}, open(path, "w"), indent=0)
+    print(path, os.path.getsize(path), "bytes")
 
 
 if __name__ == "__main__":

@@ -67,6 +67,14 @@ def _set_sigs(L):
     L.orc_hash_no_pad.argtypes = [_u64p, _sz, _u64p]
     L.orc_two_to_one.argtypes = [_u64p, _u64p, _u64p]
     L.orc_hash_rows.argtypes = [_u64p, _sz, _sz, _u64p]
+    L.orc_set_hasher.argtypes = [_int]
+    L.orc_get_hasher.restype = _int
+    L.orc_challenger_permute.argtypes = [_u64p]
+    L.orc_blake3.argtypes = [ctypes.c_char_p, _sz, ctypes.POINTER(ctypes.c_uint8)]
+    L.orc_blake3_hash_no_pad.argtypes = [_u64p, _sz, _u64p]
+    L.orc_blake3_two_to_one.argtypes = [_u64p, _u64p, _u64p]
+    L.orc_blake3_permute.argtypes = [_u64p]
+    L.orc_bytes_hash_to_fields.argtypes = [_u64p, _u64p]
     L.orc_build_merkle_nodes.argtypes = [_u64p, _sz, _u64p]
     L.orc_merkle_new_v2.argtypes = [_u64p, _sz, _sz, _u32, _u64p, _u64p]
     L.orc_merkle_new_v2.restype = _int
@@ -156,6 +164,48 @@ def lde_batch(coeffs, shift=7, blowup=8):
     c = np.ascontiguousarray(coeffs, dtype=np.uint64)
     out = np.empty((c.shape[0], c.shape[1] * blowup), dtype=np.uint64)
     lib().orc_lde_batch(_p(c), c.shape[0], c.shape[1], int(shift), blowup, _p(out))
+    return out
+
+
+# ---------------------------------------------------------------- Hasher selection (GenericConfig::Hasher)
+POSEIDON, BLAKE3 = 0, 1
+
+
+class hasher:
+    """with oracle.hasher(oracle.BLAKE3): ...  -- C::Hasher = Blake3_256<32> (Blake3GoldilocksConfig, plonk/config.rs:153-161)
+    for leaf / node hashing, the challenger's permutation and the hash wire format; Poseidon (the default) otherwise."""
+
+    def __init__(self, hid):
+        self.hid = int(hid)
+
+    def __enter__(self):
+        self.prev = lib().orc_get_hasher()
+        lib().orc_set_hasher(self.hid)
+        return self
+
+    def __exit__(self, *exc):
+        lib().orc_set_hasher(self.prev)
+        return False
+
+
+def blake3(data):
+    out = (ctypes.c_uint8 * 32)()
+    data = bytes(data)
+    lib().orc_blake3(data, len(data), out)
+    return bytes(out)
+
+
+def blake3_permute(state):
+    s = np.ascontiguousarray(state, dtype=np.uint64).copy()
+    assert s.size == 12
+    lib().orc_blake3_permute(_p(s))
+    return s
+
+
+def bytes_hash_to_fields(h):
+    a = np.ascontiguousarray(h, dtype=np.uint64)
+    out = np.empty(5, dtype=np.uint64)
+    lib().orc_bytes_hash_to_fields(_p(a), _p(out))
     return out
 
 
@@ -251,8 +301,11 @@ def poseidon_table_row(inp):
     return row
 
 
-def stark_prove(table_ids, traces, check_degree=True, max_bytes=1 << 26, compress_challenges=None):
+def stark_prove(table_ids, traces, check_degree=True, max_bytes=1 << 26, compress_challenges=None, hasher_id=None):
     """prove_with_traces + Buffer::write_all_proof -> bytes.  traces[i]: [columns_i, 2^k_i] uint64 column-major."""
+    if hasher_id is not None:
+        with hasher(hasher_id):
+            return stark_prove(table_ids, traces, check_degree, max_bytes, compress_challenges)
     k = len(table_ids)
     trs = [np.ascontiguousarray(t, dtype=np.uint64) for t in traces]
     ids = (ctypes.c_int * k)(*[int(x) for x in table_ids])
@@ -272,8 +325,11 @@ def stark_prove(table_ids, traces, check_degree=True, max_bytes=1 << 26, compres
     return bytes(bytearray(out)[: n.value])
 
 
-def stark_verify(table_ids, proof):
+def stark_verify(table_ids, proof, hasher_id=None):
     """Buffer::read_all_proof + verify_proof -> (ok, message)."""
+    if hasher_id is not None:
+        with hasher(hasher_id):
+            return stark_verify(table_ids, proof)
     k = len(table_ids)
     ids = (ctypes.c_int * k)(*[int(x) for x in table_ids])
     buf = (ctypes.c_uint8 * len(proof)).from_buffer_copy(proof)

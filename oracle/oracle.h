@@ -26,9 +26,22 @@ void orc_poseidon(uint64_t state[12]);
 void orc_poseidon_naive(uint64_t state[12]);
 /* one row of the Poseidon table (134 columns, filters 0) for a permutation input (generation/poseidon.rs:18-80) */
 void orc_poseidon_table_row(const uint64_t in[12], uint64_t row[134]);
+void orc_poseidon_hash_no_pad(const uint64_t *in, size_t n, uint64_t out[4]);
+void orc_poseidon_two_to_one(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]);
+/* the Hasher in force (0 PoseidonHash, 1 Blake3_256<32>): leaf / node hashing and the challenger's permutation */
+void orc_set_hasher(int id);
+int orc_get_hasher(void);
 void orc_hash_no_pad(const uint64_t *in, size_t n, uint64_t out[4]);
 void orc_two_to_one(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]);
+void orc_challenger_permute(uint64_t state[12]);
 void orc_hash_rows(const uint64_t *rows, size_t nrows, size_t ncols, uint64_t *digests);
+
+/* blake3.c */
+void orc_blake3(const uint8_t *in, size_t len, uint8_t out[32]);
+void orc_blake3_hash_no_pad(const uint64_t *in, size_t n, uint64_t out[4]);
+void orc_blake3_two_to_one(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]);
+void orc_blake3_permute(uint64_t state[12]);
+void orc_bytes_hash_to_fields(const uint64_t h[4], uint64_t out[5]);
 
 /* merkle.c */
 void orc_build_merkle_nodes(const uint64_t *leaf_hashes, size_t nleaves, uint64_t *nodes);

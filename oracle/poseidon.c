@@ -153,7 +153,7 @@ void orc_poseidon_naive(uint64_t state[12]) {
 }
 
 /* hashing.rs:84-108, num_outputs = 4 */
-void orc_hash_no_pad(const uint64_t *in, size_t n, uint64_t out[4]) {
+void orc_poseidon_hash_no_pad(const uint64_t *in, size_t n, uint64_t out[4]) {
     uint64_t st[W];
     memset(st, 0, sizeof(st));
     for (size_t off = 0; off < n; off += 8) {
@@ -166,13 +166,38 @@ void orc_hash_no_pad(const uint64_t *in, size_t n, uint64_t out[4]) {
 }
 
 /* hashing.rs:66-74 */
-void orc_two_to_one(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]) {
+void orc_poseidon_two_to_one(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]) {
     uint64_t st[W];
     memset(st, 0, sizeof(st));
     memcpy(st, l, 32);
     memcpy(st + 4, r, 32);
     orc_poseidon(st);
     memcpy(out, st, 32);
+}
+
+/* C::Hasher of the GenericConfig in force (plonk/config.rs:115-122 PoseidonGoldilocksConfig, :153-161
+ * Blake3GoldilocksConfig): 0 = PoseidonHash, 1 = Blake3_256<32>.  Process-wide, set between calls (test tooling). */
+static int orc_hasher_id = 0;
+void orc_set_hasher(int id) { orc_hasher_id = id; }
+int orc_get_hasher(void) { return orc_hasher_id; }
+void orc_hash_no_pad(const uint64_t *in, size_t n, uint64_t out[4]) {
+    if (orc_hasher_id == 1)
+        orc_blake3_hash_no_pad(in, n, out);
+    else
+        orc_poseidon_hash_no_pad(in, n, out);
+}
+void orc_two_to_one(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]) {
+    if (orc_hasher_id == 1)
+        orc_blake3_two_to_one(l, r, out);
+    else
+        orc_poseidon_two_to_one(l, r, out);
+}
+/* H::Permutation of the Challenger (challenger.rs:137-152): PoseidonPermutation or Blake3Permutation */
+void orc_challenger_permute(uint64_t state[12]) {
+    if (orc_hasher_id == 1)
+        orc_blake3_permute(state);
+    else
+        orc_poseidon(state);
 }
 
 /* rows-major leaf hashing of a [nrows][ncols] matrix (MerkleTree::new_v2 leaf loop,

@@ -354,7 +354,9 @@ struct Writer {
     void ext(E x) { field(x.c0); field(x.c1); }
     void field_vec(const VF& v) { u32((uint32_t)v.size()); for (F x : v) field(x); }
     void ext_vec(const VE& v) { u32((uint32_t)v.size()); for (E x : v) ext(x); }
-    void hash(const Hash& h) { for (int i = 0; i < 4; i++) field(h.e[i]); }
+    void raw64(uint64_t x) { for (int i = 0; i < 8; i++) buf.push_back((uint8_t)(x >> (8 * i))); }
+    /* write_hash = h.to_bytes() (serialization.rs:115-117): HashOut -> canonical u64s; BytesHash<32> -> its 32 bytes */
+    void hash(const Hash& h) { for (int i = 0; i < 4; i++) { if (orc_get_hasher() == 1) raw64(h.e[i]); else field(h.e[i]); } }
     void cap(const Cap& c) { u32((uint32_t)c.size()); for (auto& h : c) hash(h); }
     void merkle_proof(const std::vector<Hash>& s) { u8((uint8_t)s.size()); for (auto& h : s) hash(h); }
     void proof(const StarkProof& p) {

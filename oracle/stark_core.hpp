@@ -86,7 +86,7 @@ struct Challenger {
     void duplexing() { /* :137-152 */
         for (size_t i = 0; i < in.size(); i++) state[i] = in[i];
         in.clear();
-        orc_poseidon(state);
+        orc_challenger_permute(state); /* H::Permutation: Poseidon, or Blake3Permutation (hash/blake3.rs:165-199) */
         out.assign(state, state + 8);
     }
     void observe(F x) { /* :47-56 */
@@ -95,7 +95,15 @@ struct Challenger {
         if (in.size() == 8) duplexing();
     }
     void observe_ext(E x) { observe(x.c0); observe(x.c1); }
-    void observe_hash(const Hash& h) { for (int i = 0; i < 4; i++) observe(h.e[i]); }
+    void observe_hash(const Hash& h) { /* :79-81 observes hash.to_vec(): HashOut -> its 4 elements; BytesHash<32> -> 5
+                                          elements of 7 bytes each (hash_types.rs:142-152) */
+        if (orc_get_hasher() == 1) {
+            F f[5];
+            orc_bytes_hash_to_fields(h.e, f);
+            for (int i = 0; i < 5; i++) observe(f[i]);
+        } else
+            for (int i = 0; i < 4; i++) observe(h.e[i]);
+    }
     void observe_cap(const Cap& c) { for (auto& h : c) observe_hash(h); }
     F get_challenge() { /* :86-99 */
         if (!in.empty() || out.empty()) duplexing();
@@ -260,7 +268,7 @@ inline F fri_pow(const Hash& h, const Config& c) { /* smallest valid nonce (SURV
     for (uint64_t i = 0;; i++) {
         F in[5] = {h.e[0], h.e[1], h.e[2], h.e[3], i};
         F out[4];
-        orc_hash_no_pad(in, 5, out);
+        orc_poseidon_hash_no_pad(in, 5, out); /* C::InnerHasher = PoseidonHash in every config (plonk/config.rs:121,159) */
         if (__builtin_clzll(out[0] | 1) >= (int)c.pow_bits && (out[0] >> (64 - c.pow_bits)) == 0) return i;
     }
 }
@@ -359,7 +367,7 @@ inline FriChallenges fri_challenges(Challenger& ch, const FriProof& p, uint32_t 
     Hash h = ch.get_hash();
     F in[5] = {h.e[0], h.e[1], h.e[2], h.e[3], p.pow_witness};
     F out[4];
-    orc_hash_no_pad(in, 5, out);
+    orc_poseidon_hash_no_pad(in, 5, out); /* C::InnerHasher = PoseidonHash in every config (plonk/config.rs:121,159) */
     fc.pow_response = out[0];
     size_t L = (size_t)1 << (degree_bits + c.rate_bits);
     for (uint32_t i = 0; i < c.num_queries; i++) fc.indices.push_back((size_t)(ch.get_challenge() % L));

@@ -55,6 +55,20 @@ uint64_t ola_gpu_kernel_launches(const ola_ctx* ctx);
 /* the cudaStream_t every kernel of this context is launched on (for CUDA-event timing by the caller) */
 void* ola_gpu_stream(ola_ctx* ctx);
 
+/* C::Hasher of the GenericConfig (plonky2/plonky2/src/plonk/config.rs:96-111) this context commits and proves with:
+ *   OLA_HASH_POSEIDON  PoseidonGoldilocksConfig (config.rs:115-122; the default; `ola prove`, client/src/main.rs:31)
+ *   OLA_HASH_BLAKE3    Blake3GoldilocksConfig   (config.rs:153-161; the reference's criterion benches,
+ *                      circuits/benches/fibo_loop.rs:26, and integration tests, circuits/src/stark/ola_stark.rs:684)
+ * It selects leaf hashing (H::hash_no_pad), node hashing (H::two_to_one), the challenger's permutation (H::Permutation)
+ * and the hash wire format (a BytesHash<32> is its 32 bytes, 4 little-endian u64 here, never reduced) of ola_hash_rows,
+ * ola_merkle_rows, ola_commit*, ola_prove.  C::InnerHasher (the FRI proof-of-work hash) is Poseidon in both.
+ * Under BLAKE3 the canonical u64 of each element is hashed (hash/blake3.rs:210-213 hashes the in-memory word, which is
+ * a non-canonical representative with probability ~2^-32 per element); leaves are limited to 2048 elements. */
+#define OLA_HASH_POSEIDON 0
+#define OLA_HASH_BLAKE3 1
+int ola_set_hasher(ola_ctx* ctx, int hasher);
+int ola_get_hasher(const ola_ctx* ctx);
+
 /* Per-kernel CUDA-event tracing on the context's stream (device analogue of the reference's TimingTree,
  * plonky2/plonky2/src/util/timing.rs).  begin: start recording an event pair around every launch;
  * end: synchronise, stop recording and write {"kernel": {"ms": total, "launches": n}, ...} as JSON text. */
@@ -191,6 +205,9 @@ int ola_set_comm(ola_ctx* ctx, int rank, int world, ola_allgather_fn allgather, 
  * context needed.  table_ids as for ola_prove (the system the proof was made for).  Returns OLA_OK when the proof is
  * accepted; OLA_ERR_INVALID_ARG with the reason in err (NUL-terminated, truncated to errcap) when it is rejected. */
 int ola_verify(const int* table_ids, uint32_t ntables, const uint8_t* proof, size_t proof_len, char* err, size_t errcap);
+/* the same for a proof made under `hasher` (OLA_HASH_*): verify_proof::<F, C, D> with C = Blake3GoldilocksConfig */
+int ola_verify_cfg(int hasher, const int* table_ids, uint32_t ntables, const uint8_t* proof, size_t proof_len, char* err,
+                   size_t errcap);
 /* number of trace columns of a table (S::COLUMNS), or -1 if its constraint kernel is not compiled in */
 int ola_table_columns(int table_id);
 

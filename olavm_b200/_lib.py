@@ -68,6 +68,9 @@ SIGNATURES = {
                          ctypes.POINTER(_sz)]),
     "ola_table_columns": (_int, [_int]),
     "ola_verify": (_int, [ctypes.POINTER(_int), _u32, _vp, _sz, ctypes.c_char_p, _sz]),
+    "ola_verify_cfg": (_int, [_int, ctypes.POINTER(_int), _u32, _vp, _sz, ctypes.c_char_p, _sz]),
+    "ola_set_hasher": (_int, [_vp, _int]),
+    "ola_get_hasher": (_int, [_vp]),
     "ola_set_comm": (_int, [_vp, _int, _int, _vp, _vp, _vp]),
     "ola_batch_free": (_int, [_vp, _vp]),
     "ola_batch_ncols": (_sz, [_vp]),

@@ -24,6 +24,15 @@ class Context:
             raise _lib.OlaError(rc, msg.decode() if msg else "")
         return rc
 
+    # ---- C::Hasher of the GenericConfig (plonk/config.rs:115-122 Poseidon, :153-161 Blake3)
+    @property
+    def hasher(self):
+        return int(self._lib.ola_get_hasher(self.handle))
+
+    @hasher.setter
+    def hasher(self, hasher_id):
+        self.check(self._lib.ola_set_hasher(self.handle, int(hasher_id)))
+
     def sync(self):
         self.check(self._lib.ola_gpu_sync(self.handle))
 

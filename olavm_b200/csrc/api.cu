@@ -8,6 +8,7 @@
 #include "common.h"
 #include "gl.cuh"
 #include "ntt.h"
+#include "hasher.h"
 #include "poseidon.cuh"
 #include "stark.h"
 #include "verify.h"
@@ -338,11 +339,11 @@ int ola_hash_rows(ola_ctx* ctx, const uint64_t* rows, uint64_t* digests, int on_
     if (!ctx || !digests || (!rows && nrows * ncols)) return OLA_ERR_INVALID_ARG;
     return guarded(ctx, [&] {
         if (on_device) {
-            ola::poseidon::hash_rows_rowmajor(ctx, rows, nrows, ncols, digests);
+            ola::hasher::hash_rows_rowmajor(ctx, rows, nrows, ncols, digests);
         } else {
             DevBuf d(nrows * ncols), o(nrows * 4);
             to_device(ctx, d.p, rows, nrows * ncols);
-            ola::poseidon::hash_rows_rowmajor(ctx, d.p, nrows, ncols, o.p);
+            ola::hasher::hash_rows_rowmajor(ctx, d.p, nrows, ncols, o.p);
             to_host(ctx, digests, o.p, nrows * 4);
         }
     });
@@ -363,8 +364,8 @@ int ola_merkle_rows(ola_ctx* ctx, const uint64_t* rows, int on_device, size_t nr
         }
         DevBuf nodes(2 * nrows * 4);
         OLA_CUDA(cudaMemsetAsync(nodes.p, 0, 2 * nrows * 32, ctx->stream));
-        ola::poseidon::hash_rows_rowmajor(ctx, src, nrows, ncols, nodes.p + 4 * nrows);
-        ola::poseidon::merkle_levels(ctx, nodes.p, nrows, nodes_out_host ? 1 : ((size_t)1 << cap_height));
+        ola::hasher::hash_rows_rowmajor(ctx, src, nrows, ncols, nodes.p + 4 * nrows);
+        ola::hasher::merkle_levels(ctx, nodes.p, nrows, nodes_out_host ? 1 : ((size_t)1 << cap_height));
         const size_t ncap = (size_t)1 << cap_height;
         to_host(ctx, cap_out_host, nodes.p + 4 * ncap, ncap * 4);
         if (nodes_out_host) to_host(ctx, nodes_out_host, nodes.p, 2 * nrows * 4);
@@ -432,7 +433,18 @@ int ola_set_comm(ola_ctx* ctx, int rank, int world, ola_allgather_fn allgather, 
         ctx->comm_user = user;
     });
 }
+int ola_set_hasher(ola_ctx* ctx, int hasher) {
+    if (!ctx) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        OLA_CHECK(hasher == OLA_HASH_POSEIDON || hasher == OLA_HASH_BLAKE3, OLA_ERR_INVALID_ARG, "unknown hasher id");
+        ctx->hasher = hasher;
+    });
+}
+int ola_get_hasher(const ola_ctx* ctx) { return ctx ? ctx->hasher : OLA_ERR_INVALID_ARG; }
 int ola_verify(const int* table_ids, uint32_t ntables, const uint8_t* proof, size_t proof_len, char* err, size_t errcap) {
+    return ola_verify_cfg(OLA_HASH_POSEIDON, table_ids, ntables, proof, proof_len, err, errcap);
+}
+int ola_verify_cfg(int hasher, const int* table_ids, uint32_t ntables, const uint8_t* proof, size_t proof_len, char* err, size_t errcap) {
     auto put = [&](const std::string& m) {
         if (err && errcap) snprintf(err, errcap, "%s", m.c_str());
     };
@@ -440,8 +452,12 @@ int ola_verify(const int* table_ids, uint32_t ntables, const uint8_t* proof, siz
         put("null argument");
         return OLA_ERR_INVALID_ARG;
     }
+    if (hasher != OLA_HASH_POSEIDON && hasher != OLA_HASH_BLAKE3) {
+        put("unknown hasher id");
+        return OLA_ERR_INVALID_ARG;
+    }
     try {
-        const std::string e = ola::stark::verify::verify_all(proof, proof_len, std::vector<int>(table_ids, table_ids + ntables));
+        const std::string e = ola::stark::verify::verify_all(proof, proof_len, std::vector<int>(table_ids, table_ids + ntables), hasher);
         put(e);
         return e.empty() ? OLA_OK : OLA_ERR_INVALID_ARG;
     } catch (const std::exception& ex) {

@@ -16,6 +16,7 @@
 
 #include "gl.cuh"
 #include "ntt.h"
+#include "hasher.h"
 #include "poseidon.cuh"
 
 namespace ola {
@@ -118,8 +119,8 @@ static void lde_columns(ola_ctx* ctx, ola_batch* b, size_t c0, size_t cnt, int c
 // MerkleTree::new_v2 over the LDE: leaf digests and the level reduction down to the cap
 static void hash_commit(ola_ctx* ctx, ola_batch* b) {
     const size_t n = (size_t)1 << b->log_n, L = n << b->shard_bits;
-    poseidon::hash_rows_colmajor(ctx, b->d_lde, L, L, b->ncols, b->d_nodes + 4 * L);
-    poseidon::merkle_levels(ctx, b->d_nodes, L, (size_t)1 << b->local_cap_height());
+    hasher::hash_rows_colmajor(ctx, b->d_lde, L, L, b->ncols, b->d_nodes + 4 * L);
+    hasher::merkle_levels(ctx, b->d_nodes, L, (size_t)1 << b->local_cap_height());
 }
 static void finish_commit(ola_ctx* ctx, ola_batch* b, int coset_first, int coset_count) {
     lde_columns(ctx, b, 0, b->ncols, coset_first, coset_count);

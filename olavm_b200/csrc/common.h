@@ -58,6 +58,7 @@ struct ola_ctx {
     std::vector<ola::ProfRecord> prof_pending;
     std::map<std::string, std::pair<double, uint64_t>> prof_totals;  // name -> (ms, launches)
     int device = 0;
+    int hasher = 0;  // OLA_HASH_POSEIDON / OLA_HASH_BLAKE3: C::Hasher of the commitments and the transcript (ola_set_hasher)
     cudaStream_t stream = nullptr;
     // second stream + events for uploads that overlap the transforms of the previous chunk (batch.cu ingest_host_columns)
     cudaStream_t copy_stream = nullptr;

@@ -12,6 +12,7 @@
 // and reuses the batched kernels of ntt.cu unchanged.  The transcript stays on the host (stark_types.h);
 // only caps, the final polynomial, the PoW nonce and the opened rows ever cross PCIe.
 #include "fri.h"
+#include "hasher.h"
 
 #include "batch.h"
 #include "ntt.h"
@@ -376,14 +377,16 @@ stark::FriProof prove_openings(ola_ctx* ctx, const Instance& inst, const std::ve
         }
         const size_t nleaves = ly->len / arity;
         ly->nodes.alloc(2 * nleaves * 4);
-        {
+        if (ctx->hasher == OLA_HASH_BLAKE3) {
+            blake3::fri_leaves(ctx, ly->vals.p, ly->len, arity, ly->nodes.p + 4 * nleaves);
+        } else {
             Launch lz(ctx, "fri_leaves");
             fri_leaves_kernel<<<(unsigned)((nleaves + 127) / 128), 128, 0, st>>>(ly->vals.p, ly->len, arity, ly->nodes.p + 4 * nleaves);
         }
         check_launch("fri_leaves_kernel");
         const size_t ncap = (size_t)1 << Config::cap_height;
         OLA_CHECK(nleaves >= ncap, OLA_ERR_INTERNAL, "FRI layer smaller than the Merkle cap");
-        poseidon::merkle_levels(ctx, ly->nodes.p, nleaves, ncap);
+        hasher::merkle_levels(ctx, ly->nodes.p, nleaves, ncap);
         stark::Cap cap(ncap);
         OLA_CUDA(cudaMemcpyAsync(cap.data(), ly->nodes.p + 4 * ncap, ncap * 32, cudaMemcpyDeviceToHost, st));
         OLA_CUDA(cudaStreamSynchronize(st));

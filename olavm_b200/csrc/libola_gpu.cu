@@ -4,6 +4,7 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -shared -Xcompiler -fPIC
 #include "ntt.cu"
 #include "poseidon.cu"
+#include "blake3.cu"
 #include "batch.cu"
 #include "fri.cu"
 #include "stark.cu"

@@ -803,7 +803,7 @@ std::vector<uint8_t> prove_all(ola_ctx* ctx, const std::vector<int>& table_ids, 
     OLA_CHECK(traces.size() == T && log_ns.size() == T, OLA_ERR_INVALID_ARG, "one trace per table");
     std::vector<std::unique_ptr<DevBuf>> d_vals(T);
     std::vector<std::unique_ptr<BatchHolder>> commits(T);
-    Challenger ch;
+    Challenger ch(ctx->hasher);
     // host traces: every table's upload is queued on the copy stream up front, so table i+1 crosses PCIe while table i is
     // being committed (LDE + Poseidon) on the context stream.  With several ranks each uploads 1/world of the columns
     // over its own PCIe link (into `slices`) and one all-gather over NVLink replicates the table.
@@ -906,6 +906,7 @@ std::vector<uint8_t> prove_all(ola_ctx* ctx, const std::vector<int>& table_ids, 
             if (ctl.has_looked) per_table[ctl.looked.table].push_back({c, &ctl.looked});
         }
     Writer w;
+    w.raw_hashes = ctx->hasher == OLA_HASH_BLAKE3;
     w.u32((uint32_t)T);
     for (size_t i = 0; i < T; ++i) {
         StarkProof p = prove_single_table(ctx, sys.tables[i], cfg, d_vals[i]->p, log_ns[i], commits[i]->b, per_table[i], ch);

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "gl.cuh"
+#include "blake3.cuh"
 #include "poseidon.cuh"
 
 namespace ola {
@@ -48,14 +49,21 @@ inline std::vector<uint32_t> fri_arities(uint32_t degree_bits) {
 }
 
 // ---- Fiat-Shamir transcript (iop/challenger.rs:18-162): host side, exact and sequential ----
+// Generic over H: H::Permutation is the Poseidon permutation or Blake3Permutation (hash/blake3.rs:165-199), and
+// observe_hash absorbs hash.to_vec() -- 4 elements of a HashOut, 5 seven-byte elements of a BytesHash<32>
+// (challenger.rs:79-81, hash/hash_types.rs:142-152).
 struct Challenger {
     F state[12];
     std::vector<F> in, out;
-    Challenger() { memset(state, 0, sizeof(state)); }
+    int hasher;  // OLA_HASH_POSEIDON (0) / OLA_HASH_BLAKE3 (1)
+    explicit Challenger(int hasher_id = 0) : hasher(hasher_id) { memset(state, 0, sizeof(state)); }
     void duplexing() {
         for (size_t i = 0; i < in.size(); i++) state[i] = in[i];
         in.clear();
-        poseidon::permute_host(state);
+        if (hasher == 1)
+            blake3::permute_host(state);
+        else
+            poseidon::permute_host(state);
         out.assign(state, state + 8);
     }
     void observe(F x) {
@@ -68,8 +76,15 @@ struct Challenger {
         observe(x.c1);
     }
     void observe_cap(const Cap& c) {
-        for (auto& h : c)
-            for (int i = 0; i < 4; i++) observe(h.e[i]);
+        for (auto& h : c) {
+            if (hasher == 1) {
+                F f[5];
+                blake3::hash_to_fields(h.e, f);
+                for (int i = 0; i < 5; i++) observe(f[i]);
+            } else {
+                for (int i = 0; i < 4; i++) observe(h.e[i]);
+            }
+        }
     }
     F get_challenge() {
         if (!in.empty() || out.empty()) duplexing();
@@ -201,6 +216,7 @@ struct StarkProof {
 // u8 Merkle-path length; PublicValues are not written ----
 struct Writer {
     std::vector<uint8_t> buf;
+    bool raw_hashes = false;  // BytesHash<32>: write_hash = the 32 digest bytes (serialization.rs:115-117), never reduced
     void u8(uint8_t x) { buf.push_back(x); }
     void u32(uint32_t x) {
         for (int i = 0; i < 4; i++) buf.push_back((uint8_t)(x >> (8 * i)));
@@ -222,7 +238,12 @@ struct Writer {
         for (E x : v) ext(x);
     }
     void hash(const Hash& h) {
-        for (int i = 0; i < 4; i++) field(h.e[i]);
+        for (int i = 0; i < 4; i++) {
+            if (raw_hashes)
+                for (int k = 0; k < 8; k++) buf.push_back((uint8_t)(h.e[i] >> (8 * k)));
+            else
+                field(h.e[i]);
+        }
     }
     void cap(const Cap& c) {
         u32((uint32_t)c.size());

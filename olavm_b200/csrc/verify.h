@@ -157,6 +157,17 @@ inline void eval_table(const TableInfo& t, const XRow& lv, const XRow& nv, XCons
     }
 }
 
+// C::Hasher the proof under verification was made with (set by verify_all for its duration; one per host thread)
+inline int& current_hasher() {
+    static thread_local int h = 0;
+    return h;
+}
+struct HasherScope {
+    int prev;
+    explicit HasherScope(int h) : prev(current_hasher()) { current_hasher() = h; }
+    ~HasherScope() { current_hasher() = prev; }
+};
+
 // ---- wire format reader (the inverse of Writer, stark_types.h) ----
 struct Reader {
     const uint8_t* p;
@@ -204,6 +215,14 @@ struct Reader {
     }
     Hash hash() {
         Hash h;
+        if (current_hasher() == 1) {  // BytesHash<32>::from_bytes: any 32 bytes
+            for (int i = 0; i < 4; ++i) {
+                h.e[i] = 0;
+                if (need(8))
+                    for (int k = 0; k < 8; ++k) h.e[i] |= (uint64_t)p[pos++] << (8 * k);
+            }
+            return h;
+        }
         for (int i = 0; i < 4; ++i) h.e[i] = field();
         return h;
     }
@@ -257,7 +276,7 @@ struct Reader {
 };
 
 // ---- hashing on the host (hashing.rs:84-108 hash_n_to_hash_no_pad, :66-74 two_to_one) ----
-inline Hash hash_no_pad(const F* in, size_t n) {
+inline Hash poseidon_hash_no_pad(const F* in, size_t n) {
     F st[12] = {0};
     for (size_t i = 0; i < n; i += 8) {
         for (size_t k = 0; k < 8 && i + k < n; ++k) st[k] = in[i + k];
@@ -267,7 +286,23 @@ inline Hash hash_no_pad(const F* in, size_t n) {
     for (int i = 0; i < 4; ++i) h.e[i] = st[i];
     return h;
 }
+inline Hash hash_no_pad(const F* in, size_t n) {
+    if (current_hasher() == 1) {  // Blake3_256::hash_no_pad (hash/blake3.rs:205-218)
+        Hash h;
+        if (n > blake3::MAX_U64S) throw Error(OLA_ERR_INVALID_ARG, "leaf too wide");
+        std::vector<F> c(in, in + n);
+        for (auto& x : c) x = gl::canon(x);
+        blake3::hash_host(c.data(), n, h.e);
+        return h;
+    }
+    return poseidon_hash_no_pad(in, n);
+}
 inline Hash two_to_one(const Hash& l, const Hash& r) {
+    if (current_hasher() == 1) {  // Blake3_256::two_to_one (hash/blake3.rs:220-233)
+        Hash h;
+        blake3::two_to_one(l.e, r.e, h.e);
+        return h;
+    }
     F st[12] = {l.e[0], l.e[1], l.e[2], l.e[3], r.e[0], r.e[1], r.e[2], r.e[3], 0, 0, 0, 0};
     poseidon::permute_host(st);
     Hash h;
@@ -281,8 +316,9 @@ inline bool merkle_verify(const F* leaf, size_t nleaf, size_t index, const Cap& 
         index >>= 1;
     }
     if (index >= cap.size()) return false;
-    for (int i = 0; i < 4; ++i)
-        if (gl::canon(cur.e[i]) != gl::canon(cap[index].e[i])) return false;
+    for (int i = 0; i < 4; ++i) {
+        if (current_hasher() == 1 ? cur.e[i] != cap[index].e[i] : gl::canon(cur.e[i]) != gl::canon(cap[index].e[i])) return false;
+    }
     return true;
 }
 
@@ -315,7 +351,7 @@ inline FriChallenges fri_challenges(Challenger& ch, const FriProof& p, uint32_t 
     for (auto& x : p.final_poly) ch.observe_ext(x);
     Hash h = ch.get_hash();
     F in[5] = {h.e[0], h.e[1], h.e[2], h.e[3], p.pow_witness};
-    fc.pow_response = gl::canon(hash_no_pad(in, 5).e[0]);
+    fc.pow_response = gl::canon(poseidon_hash_no_pad(in, 5).e[0]);  // C::InnerHasher = PoseidonHash in every config
     const size_t L = (size_t)1 << (degree_bits + Config::rate_bits);
     for (uint32_t i = 0; i < Config::num_queries; ++i) fc.indices.push_back((size_t)(ch.get_challenge() % L));
     return fc;
@@ -424,7 +460,8 @@ inline XE eval_column(const Column& c, const XRow& row) {
 }
 
 // verify_proof over the given system; returns "" when the proof is accepted, else the reason
-inline std::string verify_all(const uint8_t* bytes, size_t len, const std::vector<int>& table_ids) {
+inline std::string verify_all(const uint8_t* bytes, size_t len, const std::vector<int>& table_ids, int hasher = 0) {
+    HasherScope scope(hasher);
     Reader rd(bytes, len);
     const size_t T = rd.count(1);
     if (!rd.ok || T != table_ids.size()) return "wrong number of proofs";
@@ -441,7 +478,7 @@ inline std::string verify_all(const uint8_t* bytes, size_t len, const std::vecto
         for (auto& c : p.fri.commit_caps)
             if (c.size() != ncap) return "cap shape";
     }
-    Challenger ch;
+    Challenger ch(current_hasher());
     for (auto& p : proofs) ch.observe_cap(p.trace_cap);
     std::vector<Challenge> ctl_ch;
     for (uint32_t k = 0; k < Config::num_challenges; ++k) {

@@ -184,10 +184,12 @@ def prove_sharded_local(device, world, table_ids, traces, **kw):
 
     comm = LocalComm(world)
     out, err = [None] * world, [None] * world
+    hasher = kw.pop("hasher", 0)
 
     def run(rank):
         try:
             ctx = Context(device)
+            ctx.hasher = hasher
             comm.attach(ctx, rank)
             out[rank] = prove_with_traces(ctx, table_ids, traces, **kw)
             ctx.close()

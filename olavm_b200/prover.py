@@ -6,6 +6,7 @@ import numpy as np
 
 from . import _lib
 
+POSEIDON, BLAKE3 = 0, 1  # OLA_HASH_* of include/ola_gpu.h: C::Hasher (Context.hasher, verify_proof(hasher=))
 TABLES = dict(cpu=0, memory=1, bitwise=2, cmp=3, rangecheck=4, poseidon=5, poseidon_chunk=6, storage_access=7, tape=8, sccall=9,
               program=10, prog_chunk=11)
 
@@ -44,13 +45,14 @@ def prove_with_traces(ctx, table_ids, trace_poly_values, check_quotient_degree=T
     return out[: n.value].tobytes()
 
 
-def verify_proof(table_ids, proof):
+def verify_proof(table_ids, proof, hasher=0):
     """`circuits::stark::verifier::verify_proof` over `Buffer::read_all_proof`'s bytes (verifier.rs:32-212,
-    serialization.rs:395-411) -> (accepted, reason).  Host code: needs the library but no GPU."""
+    serialization.rs:395-411) -> (accepted, reason).  Host code: needs the library but no GPU.
+    hasher: POSEIDON (PoseidonGoldilocksConfig) or BLAKE3 (Blake3GoldilocksConfig), the config the proof was made under."""
     lib = _lib.load()
     k = len(table_ids)
     ids = (ctypes.c_int * k)(*[int(x) for x in table_ids])
     buf = np.frombuffer(bytes(proof), dtype=np.uint8)
     err = ctypes.create_string_buffer(512)
-    rc = lib.ola_verify(ids, k, buf.ctypes.data_as(ctypes.c_void_p), buf.size, err, 512)
+    rc = lib.ola_verify_cfg(int(hasher), ids, k, buf.ctypes.data_as(ctypes.c_void_p), buf.size, err, 512)
     return rc == 0, err.value.decode()

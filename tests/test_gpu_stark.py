@@ -184,7 +184,7 @@ def test_real_program_run_systems(ctx, orc):
     assert ok, msg
 
 
-@pytest.mark.parametrize("name", ["fibo_recursive", "call", "tape", "bitwise", "comparison", "range_check"])
+@pytest.mark.parametrize("name", ["fibo_recursive", "call", "tape", "bitwise", "comparison", "range_check", "memory", "mem_gep"])
 def test_reference_programs_run_and_prove(ctx, orc, name):
     """The reference's own assembly test programs (tests/golden/ola_programs.json) run through the restated VM: the GPU
     prover's quotients pass the degree check, the proof bytes equal the oracle's and the product verifier accepts."""

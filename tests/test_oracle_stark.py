@@ -395,6 +395,8 @@ def _reference_program(name):
 
 @pytest.mark.parametrize("name,tables,r0,min_steps", [
     ("fibo_recursive", [0, 1, 3, 4, 10], 55, 2000),      # fib(10) by recursion: 2150 executed rows, 176 call / ret pairs
+    ("memory", [0, 1, 3, 4, 10], 2, 17),                 # mstore / mload through [r9,r3,-1]: address = anchor + factor * register
+    ("mem_gep", [0, 1, 3, 4, 10], 3, 30),                # array_index(2) of {1, 2, 3} through mload r0 [r9,r6] (factor 1)
 ])  # call, tape, bitwise, comparison and range_check run in the GPU suite (tests/test_gpu_stark.py) and inside the eleven-table system
 def test_reference_programs_run_and_prove(orc, name, tables, r0, min_steps):
     prog = _reference_program(name)
@@ -403,3 +405,31 @@ def test_reference_programs_run_and_prove(orc, name, tables, r0, min_steps):
     proof = orc.stark_prove(ids, traces, compress_challenges=cc)
     ok, msg = orc.stark_verify(ids, proof)
     assert ok, msg
+
+
+@pytest.mark.parametrize("case", ["factor_is_not_the_immediate_word", "address_ignores_the_factor", "offset_register_value", "imm_fetch_filter"])
+def test_register_scaled_memory_operand_binds(orc, case):
+    """mload / mstore with op1_imm = 0 (`[anchor, register, factor]`, circuits/src/cpu/{mload,mstore}.rs: aux0 = immediate
+    word, aux1 = op0 + aux0 * op1): the reference's `memory` program proves, and each cell of that branch is bound."""
+    prog = _reference_program("memory")
+    ids, traces, cc, steps = tracegen.run_system(orc, np.random.default_rng(3), prog)
+    rows = [i for i, s in enumerate(steps) if s["op"] in ("mload", "mstore") and s["op1_imm"] == 0]
+    assert len(rows) == 2 and all(steps[i]["aux0"] == P - 1 and steps[i]["op1"] == 1 for i in rows)   # factor -1, r3 = 1
+    i = rows[0]
+    b = traces[0].copy()
+    if case == "factor_is_not_the_immediate_word":
+        b[33, i] = 1                                                    # aux0 != imm_val
+    elif case == "address_ignores_the_factor":
+        b[34, i] = int(b[30, i])                                        # aux1 = op0 instead of op0 + aux0 * op1
+    elif case == "offset_register_value":
+        b[31, i] = 2                                                    # op1 is not the selected register's value
+    else:
+        b[92, i] = 0                                                    # mstore must fetch its second word from the program
+    bad = list(traces)
+    bad[0] = b
+    try:
+        proof = orc.stark_prove(ids, bad, compress_challenges=cc)
+    except orc.StarkError as e:
+        assert "Quotient has failed" in str(e)
+        return
+    assert not orc.stark_verify(ids, proof)[0]

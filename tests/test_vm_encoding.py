@@ -10,12 +10,13 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ola
 
 
 def _to_tuple(op, args):
+    fix = lambda off: tuple(off) if isinstance(off, list) else off  # [offset register, factor]: the register-scaled form
     if op == "mstore":
         (base, off), val = args
-        return ("mstore", base, off, val)
+        return ("mstore", base, fix(off), val)
     if op == "mload":
         dst, (base, off) = args
-        return ("mload", dst, base, off)
+        return ("mload", dst, base, fix(off))
     return (op, *args)
 
 

@@ -546,12 +546,20 @@ def ola_encode(ins):
     elif op in ("jmp", "assert", "call", "range"):
         op1 = ins[1]
     elif op == "mstore":
-        op0, op1, dst = ins[1], int(ins[2]), ins[3]
+        op0, op1, dst = ins[1], ins[2], ins[3]
     elif op == "mload":
-        dst, op0, op1 = ins[1], ins[2], int(ins[3])
+        dst, op0, op1 = ins[1], ins[2], ins[3]
     else:
         assert op in ("end", "ret")
     imm = None
+    if op in ("mstore", "mload") and isinstance(op1, tuple):
+        # [anchor, offset register, factor]: op1 = the offset register, the immediate word carries the factor and the
+        # op1_imm flag stays 0 (OlaOperand::RegisterWithFactor, core/src/program/binary_program.rs:150-153)
+        reg, factor = op1
+        word |= (1 << (32 + _reg(dst))) | (1 << (52 + _reg(op0))) | (1 << (42 + _reg(reg)))
+        return [word, int(factor) % P]
+    if op in ("mstore", "mload"):
+        op1 = int(op1)
     if dst is not None:
         word |= 1 << (32 + _reg(dst))
     if op0 is not None:
@@ -727,20 +735,32 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False, orc=
             row["op1"], row["s_op1"] = v, _reg(ins[1])
             rc_cpu.append(v)
             pc += step
-        elif op == "mstore":  # execute_inst_mstore (offset form), lib.rs:868-933
+        elif op == "mstore":  # execute_inst_mstore, lib.rs:868-933
             base = regs[_reg(ins[1])]
-            off = int(ins[2]) % P
-            row["op0"], row["s_op0"], row["op1"] = base, _reg(ins[1]), off
+            if isinstance(ins[2], tuple):  # [anchor, reg, factor] (ops.len() == 5): addr = anchor + factor * reg, op1_imm = 0
+                reg, factor = ins[2]
+                row["op1"], row["s_op1"], row["aux0"], row["op1_imm"] = regs[_reg(reg)], _reg(reg), int(factor) % P, 0
+                off = row["aux0"] * row["op1"] % P
+                row["op0"], row["s_op0"] = base, _reg(ins[1])
+            else:                          # [anchor, offset] (ops.len() == 4): addr = anchor + offset, op1_imm = 1
+                off = int(ins[2]) % P
+                row["op0"], row["s_op0"], row["op1"] = base, _reg(ins[1]), off
             v = regs[_reg(ins[3])]
             row["dst"], row["s_dst"] = v, _reg(ins[3])
             row["aux1"] = (base + off) % P
             mem[row["aux1"]] = v
             mem_log.append((row["aux1"], clk, 1 << 21, 1, v))
             pc += step
-        elif op == "mload":  # execute_inst_mload (offset form), lib.rs:935-996
+        elif op == "mload":  # execute_inst_mload, lib.rs:935-996 (the two operand forms as for mstore)
             base = regs[_reg(ins[2])]
-            off = int(ins[3]) % P
-            row["op0"], row["s_op0"], row["op1"] = base, _reg(ins[2]), off
+            if isinstance(ins[3], tuple):
+                reg, factor = ins[3]
+                row["op1"], row["s_op1"], row["aux0"], row["op1_imm"] = regs[_reg(reg)], _reg(reg), int(factor) % P, 0
+                off = row["aux0"] * row["op1"] % P
+                row["op0"], row["s_op0"] = base, _reg(ins[2])
+            else:
+                off = int(ins[3]) % P
+                row["op0"], row["s_op0"], row["op1"] = base, _reg(ins[2]), off
             row["aux1"] = (base + off) % P
             regs[_reg(ins[1])] = mem[row["aux1"]]
             row["dst"], row["s_dst"] = regs[_reg(ins[1])], _reg(ins[1])
@@ -806,7 +826,8 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False, orc=
         t[86, i] = 1 if s.get("ext_len", 0) == s.get("ext_cnt", 0) else 0   # is_next_line_diff_inst: ext_length == ext_cnt
         t[87, i] = 0 if s["op"] == "end" else 1        # is_next_line_same_tx
         t[88, i] = s.get("filter_tape_looking", 0)
-        t[92, i] = 0 if s.get("is_ext", 0) else s["op1_imm"]   # filter_looking_prog_imm: mload / mstore / any immediate operand
+        # filter_looking_prog_imm (generation/cpu.rs:168-177): mload / mstore always fetch their second word, others when op1 is an immediate
+        t[92, i] = 0 if s.get("is_ext", 0) else (1 if s["op"] in ("mload", "mstore") else s["op1_imm"])
     k = len(steps)
     if k != n:  # padding, generation/cpu.rs:180-208
         t[26, k:] = t[26, k - 1]
@@ -1155,7 +1176,10 @@ def parse_ola_asm(text):
         res = []
         for a in args:
             m = re.fullmatch(r"\[(r\d)(?:,([+-]?\d+))?\]", a)
-            if m:
+            mf = re.fullmatch(r"\[(r\d),(r\d)(?:,([+-]?\d+))?\]", a)  # [anchor, offset reg(, factor = 1)]: operands.rs:80-114
+            if mf:
+                res.append((mf.group(1), (mf.group(2), int(mf.group(3) or 1))))
+            elif m:
                 res.append((m.group(1), int(m.group(2) or 0)))
             elif is_reg(a):
                 res.append(a)

@@ -37,12 +37,13 @@ def length(op, args):
 
 
 def vm_tuple(op, args):
+    fix = lambda off: tuple(off) if isinstance(off, list) else off  # [offset register, factor] -> the VM's tuple form
     if op == "mstore":
         (base, off), val = args
-        return ("mstore", base, off, val)
+        return ("mstore", base, fix(off), val)
     if op == "mload":
         dst, (base, off) = args
-        return ("mload", dst, base, off)
+        return ("mload", dst, base, fix(off))
     return (op, *args)
 
 
@@ -81,12 +82,15 @@ def main():
         for pc, op, args in insts:
             if op not in MODELLED:
                 continue
-            if any(a == "psp" or re.fullmatch(r"\[r\d,r\d\]", a) for a in args):
-                continue  # prophet stack pointer / register-scaled offsets are not modelled
+            if any(a == "psp" for a in args):
+                continue  # the prophet stack pointer is not modelled
             res = []
             for a in args:
                 m = re.fullmatch(r"\[(r\d)(?:,([+-]?\d+))?\]", a)
-                if m:
+                mf = re.fullmatch(r"\[(r\d),(r\d)(?:,([+-]?\d+))?\]", a)  # [anchor, offset register(, factor = 1)]
+                if mf:
+                    res.append([mf.group(1), [mf.group(2), int(mf.group(3) or 1)]])
+                elif m:
                     res.append([m.group(1), int(m.group(2) or 0)])
                 elif is_reg(a):
                     res.append(a)
@@ -102,7 +106,7 @@ def main():
                 continue
             seen.add(key)
             # a small fixture: at most 4 distinct examples per (opcode, operand shape, registers used)
-            shape = (op, tuple("m" if isinstance(a, list) else ("r" if isinstance(a, str) else "i") for a in res),
+            shape = (op, tuple(("M" if isinstance(a[1], list) else "m") if isinstance(a, list) else ("r" if isinstance(a, str) else "i") for a in res),
                      tuple(a if isinstance(a, str) else (a[0] if isinstance(a, list) else "") for a in res))
             per_shape[shape] = per_shape.get(shape, 0) + 1
             if per_shape[shape] > 4:
@@ -119,10 +123,11 @@ def main():
     # the reference's prophet-free assembly test programs that only use modelled opcodes (executor/src/tests.rs runs them):
     # inputs of tests/test_oracle_stark.py::test_reference_programs_run_and_prove
     progs = {}
-    for name in ("bitwise", "range_check", "comparison", "fibo_recursive", "tape", "call"):
+    for name in ("bitwise", "range_check", "comparison", "fibo_recursive", "tape", "call", "memory", "mem_gep"):
         d = json.load(open(os.path.join(REF, "asm", name + ".json")))
         assert not d.get("prophets")
         progs[name] = d["program"]
+        tracegen.parse_ola_asm(d["program"])  # (the reference ships assembled binaries only for its system contracts, above)
     path = os.path.join(ROOT, "tests/golden/ola_programs.json")
     json.dump({"source": "assembler/test_data/asm/<name>.json, field program", "programs": progs}, open(path, "w"), indent=0)
     print(path, os.path.getsize(path), "bytes")

@@ -90,6 +90,7 @@ def _set_sigs(L):
     L.orc_stark_verify.argtypes = [ctypes.POINTER(_int), _u32, ctypes.POINTER(ctypes.c_uint8), _sz, ctypes.c_char_p, _sz]
     L.orc_stark_verify.restype = _int
     L.orc_table_columns.argtypes = [_int]
+    L.orc_air_first_failure.argtypes = [_int, _u64p, _u32, _u64, ctypes.POINTER(_u64), ctypes.POINTER(_int)]
     L.orc_table_columns.restype = _int
 
 
@@ -290,6 +291,19 @@ class StarkError(RuntimeError):
 
 def table_columns(table_id):
     return lib().orc_table_columns(int(table_id))
+
+
+def air_first_failure(table_id, trace, compress_challenge=0):
+    """The reference's per-table acceptance test (cpu_stark.rs:974-1105 and siblings): evaluate the table's AIR on every
+    row pair of `trace` ([columns, 2^k]).  None when all constraints vanish, else (row, position of the first non-zero
+    constraint in evaluation order)."""
+    t = np.ascontiguousarray(trace, dtype=np.uint64)
+    row, idx = _u64(0), _int(0)
+    rc = lib().orc_air_first_failure(int(table_id), _p(t), int(t.shape[1]).bit_length() - 1, int(compress_challenge), ctypes.byref(row),
+                                     ctypes.byref(idx))
+    if rc < 0:
+        raise StarkError("air_first_failure: unknown table or bad trace")
+    return None if rc == 0 else (int(row.value), int(idx.value))
 
 
 def poseidon_table_row(inp):

@@ -14,7 +14,13 @@ struct Consumer {
     std::vector<T> accs;
     T z_last, lagrange_first, lagrange_last;
     Consumer(const VF& a, T zl, T lf, T ll) : alphas(a), accs(a.size(), T::zero()), z_last(zl), lagrange_first(lf), lagrange_last(ll) {}
+    /* test hook (orc_air_first_failure): position, in evaluation order, of the first constraint that is non-zero */
+    int seen = 0, first_nonzero = -1;
+    static bool is_zero(F x) { return gl_canon(x) == 0; }
+    static bool is_zero(E x) { return gl_canon(x.c0) == 0 && gl_canon(x.c1) == 0; }
     void constraint(T c) {
+        if (first_nonzero < 0 && !is_zero(c.v)) first_nonzero = seen;
+        seen++;
         for (size_t i = 0; i < alphas.size(); i++) accs[i] = accs[i] * alphas[i] + c;
     }
     void constraint_transition(T c) { constraint(c * z_last); }

@@ -61,6 +61,39 @@ int orc_stark_verify(const int* table_ids, uint32_t ntables, const uint8_t* proo
     }
 }
 
+/* The reference's per-table acceptance test ("all constraints vanish on a real trace", e.g. cpu_stark.rs:974-1105,
+ * memory_stark.rs tests): evaluate the table's AIR (eval_packed_generic) on every row pair (i, i+1 mod n) over the base
+ * field with the row flags a ConstraintConsumer gets there (z_last = 0 on the last row, lagrange_first / _last on the
+ * first / last).  Returns 0 when every constraint vanishes; 1 and the first offending (row, position of the constraint
+ * in evaluation order) otherwise; -1 on error.  CTL / permutation checks are not part of it. */
+int orc_air_first_failure(int table_id, const uint64_t* trace, uint32_t log_n, uint64_t compress_challenge, uint64_t* row_out,
+                          int* constraint_out) {
+    try {
+        VF cc(1, compress_challenge);
+        System sys = make_system(std::vector<int>(1, table_id), cc);
+        const Table& t = sys.tables[0];
+        const size_t n = (size_t)1 << log_n;
+        std::vector<P<FOps>> lv(t.columns), nv(t.columns);
+        for (size_t i = 0; i < n; i++) {
+            const size_t j = (i + 1) % n;
+            for (int c = 0; c < t.columns; c++) {
+                lv[c] = P<FOps>(gl_canon(trace[(size_t)c * n + i]));
+                nv[c] = P<FOps>(gl_canon(trace[(size_t)c * n + j]));
+            }
+            Consumer<FOps> cons(VF(1, 1), P<FOps>::c(i + 1 == n ? 0 : 1), P<FOps>::c(i == 0 ? 1 : 0), P<FOps>::c(i + 1 == n ? 1 : 0));
+            t.eval_base(lv.data(), nv.data(), cons);
+            if (cons.first_nonzero >= 0) {
+                *row_out = i;
+                *constraint_out = cons.first_nonzero;
+                return 1;
+            }
+        }
+        return 0;
+    } catch (...) {
+        return -1;
+    }
+}
+
 int orc_table_columns(int table_id) {
     try { return table_by_id(table_id).columns; } catch (...) { return -1; }
 }

@@ -433,3 +433,29 @@ def test_register_scaled_memory_operand_binds(orc, case):
         assert "Quotient has failed" in str(e)
         return
     assert not orc.stark_verify(ids, proof)[0]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's per-table acceptance test restated directly: "all constraints vanish on a real trace" (cpu_stark.rs:974-1105
+# and the `test_*_stark` functions of every table): orc.air_first_failure evaluates a table's AIR on every row pair with the
+# row flags a ConstraintConsumer gets there.  No proving involved, so it also says WHICH constraint a broken cell violates.
+# ---------------------------------------------------------------------------------------------------------------------
+def test_all_constraints_vanish_on_the_traces_of_a_real_run(orc):
+    ids, traces, cc = tracegen.real_program_system(orc, np.random.default_rng(5), bitwise=True, poseidon=True, tape=True, mem_log_n=8)
+    assert ids == [0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 11]
+    for tid, t, c in zip(ids, traces, cc):
+        assert orc.air_first_failure(tid, t, c) is None, tid
+    for name in ("memory", "mem_gep", "call", "tape", "bitwise", "comparison", "range_check"):
+        pids, ptraces, pcc, _ = tracegen.run_system(orc, np.random.default_rng(3), _reference_program(name))
+        for tid, t, c in zip(pids, ptraces, pcc):
+            assert orc.air_first_failure(tid, t, c) is None, (name, tid)
+    # a broken cell is located: row and the position of the violated constraint in evaluation order
+    cpu_t = traces[0].copy()
+    cpu_t[32, 5] = (int(cpu_t[32, 5]) + 1) % P        # dst of row 5
+    row, idx = orc.air_first_failure(0, cpu_t)
+    assert row in (4, 5) and idx >= 0
+    mem_t = traces[1].copy()
+    mem_t[3, 2] = (int(mem_t[3, 2]) + 1) % P
+    assert orc.air_first_failure(1, mem_t) is not None
+    # random columns satisfy nothing
+    assert orc.air_first_failure(3, tracegen.cmp_random_trace(np.random.default_rng(1), 4)) is not None

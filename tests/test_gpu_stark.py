@@ -345,3 +345,15 @@ def test_sharded_prover_five_table_system_and_cpu_table(ctx, orc):
     single = olavm_b200.prove_with_traces(ctx, [CPU], [t], check_quotient_degree=False)
     proofs = odist.prove_sharded_local(0, 4, [CPU], [t], check_quotient_degree=False)
     assert all(p == single for p in proofs)
+
+
+def test_storage_opcodes_real_run(ctx, orc):
+    """sstore / sload run through the VM (tests/tracegen.py::storage_program): Cpu storage ext lines, Memory, StorageAccess
+    walking one consistent sparse Merkle tree, the tree-key / leaf / branch Poseidon rows: the GPU proof passes the degree
+    check, equals the oracle's bytes and verifies."""
+    ids, traces, cc, _ = tracegen.run_system(orc, np.random.default_rng(4), tracegen.storage_program())
+    assert ids == [0, 1, 3, 4, 5, 7, 10]
+    got = olavm_b200.prove_with_traces(ctx, ids, traces, compress_challenges=cc)
+    assert got == orc.stark_prove(ids, traces, compress_challenges=cc)
+    ok, msg = olavm_b200.verify_proof(ids, got)
+    assert ok, msg

@@ -459,3 +459,54 @@ def test_all_constraints_vanish_on_the_traces_of_a_real_run(orc):
     assert orc.air_first_failure(1, mem_t) is not None
     # random columns satisfy nothing
     assert orc.air_first_failure(3, tracegen.cmp_random_trace(np.random.default_rng(1), 4)) is not None
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# sstore / sload (executor/src/lib.rs:1263-1530): the StorageAccess table and the storage ext lines of the CPU table come
+# from a RUN -- one consistent sparse Merkle tree walked access by access -- so cpu->memory (8 cells per ext line),
+# cpu->poseidon (tree key), cpu->storage_access and storage_access->poseidon all carry real data.
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def storage_run(orc):
+    ids, traces, cc, steps = tracegen.run_system(orc, np.random.default_rng(4), tracegen.storage_program())
+    return ids, traces, cc, steps
+
+
+def test_storage_opcodes_run_and_prove(orc, storage_run):
+    ids, traces, cc, steps = storage_run
+    assert ids == [0, 1, 3, 4, 5, 7, 10]
+    regs = steps[-1]["regs"]
+    assert (regs[4], regs[0], regs[2]) == (13, 24, 0)     # first read of A, A after the overwrite, the absent slot
+    ext = [s for s in steps if s.get("is_ext") and s["op"] in ("sstore", "sload")]
+    assert [e["idx_storage"] for e in ext] == [1, 2, 3, 4, 5, 6]
+    for tid, t, c in zip(ids, traces, cc):
+        assert orc.air_first_failure(tid, t, c) is None, tid
+    st = traces[ids.index(7)]
+    roots = [tuple(int(x) for x in st[5:9, 256 * k]) for k in range(6)]
+    assert roots[0] == roots[1] and roots[1] != roots[2] and roots[2] != roots[3] and roots[3] == roots[4] == roots[5]   # reads keep the root
+    proof = orc.stark_prove(ids, traces, compress_challenges=cc)
+    ok, msg = orc.stark_verify(ids, proof)
+    assert ok, msg
+    import olavm_b200
+
+    ok, msg = olavm_b200.verify_proof(ids, proof)
+    assert ok, msg
+
+
+@pytest.mark.parametrize("case", ["sload_returns_another_value", "tree_key_of_another_slot"])
+def test_storage_accesses_bind_to_the_tree(orc, storage_run, case):
+    ids, traces, cc, steps = storage_run
+    i = next(k for k, s in enumerate(steps) if s.get("is_ext") and s["op"] == "sload")
+    cpu_t = traces[0].copy()
+    if case == "sload_returns_another_value":
+        cpu_t[46 + 4, i] = 99        # the value word the CPU claims the tree returned (and never wrote to memory)
+    else:
+        cpu_t[56, i] = (int(cpu_t[56, i]) + 1) % P   # tree key limb 0: neither Poseidon's output nor the walked path
+    bad = [cpu_t] + list(traces[1:])
+    assert orc.air_first_failure(0, cpu_t) is None     # the CPU table alone cannot tell: the lookups do
+    try:
+        proof = orc.stark_prove(ids, bad, compress_challenges=cc)
+    except orc.StarkError:
+        return
+    ok, msg = orc.stark_verify(ids, proof)
+    assert not ok and "Cross-table lookup" in msg

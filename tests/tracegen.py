@@ -420,7 +420,7 @@ def storage_valid_trace(orc, rng, log_n, accesses):
     row0 = 0
     for ai, acc in enumerate(accesses):
         bits = acc["addr_bits"]
-        sib = [[int(x) for x in _rand(rng, 4)] for _ in range(256)]
+        sib = acc["sib"] if "sib" in acc else [[int(x) for x in _rand(rng, 4)] for _ in range(256)]
         # bottom-up: path_l = hash of the child at layer l + 1 (the leaf value at layer 256)
         path = [None] * 257
         pre_path = [None] * 257
@@ -452,7 +452,7 @@ def storage_valid_trace(orc, rng, log_n, accesses):
             b = bits[l - 1]
             accv = b if l % 64 == 1 else (2 * accv + b) % P
             marker += 1 if l in (1, 64, 128, 192, 256) else 0
-            t[0, r] = ai + 1
+            t[0, r] = acc.get("idx", ai + 1)
             t[1:5, r] = pre_root
             t[5:9, r] = root
             t[9, r] = acc["is_write"]
@@ -477,6 +477,76 @@ def storage_valid_trace(orc, rng, log_n, accesses):
         t[47, r] = 1
         t[5:9, r] = prev_root
     return t, psdn
+
+
+class SparseMerkleTree:
+    """The account tree the storage opcodes walk, as far as the StorageAccess AIR sees it: depth 256, a node is
+    Poseidon(left | right | hash_type, 0, 0, 0)[0..4] with hash_type 1 when the children are leaves (layer 256) and 0
+    above, an absent leaf is [0; 4] (tree_key_default).  Only the populated paths are materialised."""
+
+    def __init__(self, orc):
+        self.orc, self.leaves = orc, {}
+        self.default = [None] * 257
+        self.default[256] = [0, 0, 0, 0]
+        for d in range(255, -1, -1):
+            self.default[d] = self._h(self.default[d + 1], self.default[d + 1], d + 1 == 256)
+
+    def _h(self, left, right, children_are_leaves):
+        inp = list(left) + list(right) + [1 if children_are_leaves else 0, 0, 0, 0]
+        return [int(x) for x in self.orc.poseidon(np.array(inp, dtype=np.uint64))[:4]]
+
+    def _subtree(self, depth, prefix, keys):
+        if not keys:
+            return self.default[depth]
+        if depth == 256:
+            return self.leaves[keys[0]]
+        zero = [k for k in keys if k[depth] == 0]
+        one = [k for k in keys if k[depth] == 1]
+        return self._h(self._subtree(depth + 1, prefix + (0,), zero), self._subtree(depth + 1, prefix + (1,), one), depth + 1 == 256)
+
+    def root(self):
+        return self._subtree(0, (), list(self.leaves))
+
+    def siblings(self, bits):
+        """sib[l - 1] = the sibling of the path node at layer l = 1..256 (layer 256 = the leaves)."""
+        bits = tuple(bits)
+        out = []
+        for l in range(1, 257):
+            pre = bits[: l - 1] + (1 - bits[l - 1],)
+            out.append(self._subtree(l, pre, [k for k in self.leaves if k[:l] == pre]))
+        return out
+
+    def set(self, bits, leaf):
+        self.leaves[tuple(bits)] = list(leaf)
+
+
+def tree_key_bits(tree_key):
+    """TreeKey (4 field elements) -> the 256 path bits, layer 1 first: limb k is bits [64k, 64k + 64), most significant first."""
+    return [(int(tree_key[k]) >> (63 - j)) & 1 for k in range(4) for j in range(64)]
+
+
+def storage_tables_from_log(orc, rng, st_log, extra_accesses=()):
+    """StorageAccess table + its Poseidon rows for the sstore / sload accesses a VM run logged (cpu_vm_trace, st_log), in
+    access order (storage_access_idx 1, 2, ...), walking ONE consistent sparse Merkle tree: every access's pre_root is the
+    previous access's root.  extra_accesses (e.g. ProgChunk's code-root read, for_prog=1) follow the run's.  Returns
+    (table, poseidon rows as (input, filters)) with the tree-key hashes (filter_looked_treekey) first."""
+    tree = SparseMerkleTree(orc)
+    accesses, rows = [], []
+    for a in st_log:
+        bits = tree_key_bits(a["tree_key"])
+        assert tree.leaves.get(tuple(bits), [0, 0, 0, 0]) == list(a["pre_leaf"])
+        sib = tree.siblings(bits)
+        accesses.append(dict(idx=a["idx"], addr_bits=bits, leaf=a["leaf"], pre_leaf=a["pre_leaf"], is_write=a["is_write"], sib=sib))
+        if a["is_write"]:
+            tree.set(bits, a["leaf"])
+        rows.append((a["hash_input"], [0, 1, 0, 0]))
+    for k, a in enumerate(extra_accesses):
+        bits = a["addr_bits"]
+        accesses.append(dict(a, idx=len(st_log) + k + 1, sib=tree.siblings(bits)))
+    log_n = max(8, (256 * len(accesses)).bit_length() - (1 if (256 * len(accesses)) & (256 * len(accesses) - 1) == 0 else 0))
+    st, psdn_st = storage_valid_trace(orc, rng, log_n, accesses)
+    rows += [(inp, [0, 0, 1, 0] if is_leaf else [0, 0, 0, 1]) for inp, _, is_leaf in psdn_st]
+    return st, rows
 
 
 def hash_system_valid(orc, rng, beta=0x1234567890ABCDEF % P):
@@ -513,9 +583,11 @@ def hash_system_valid(orc, rng, beta=0x1234567890ABCDEF % P):
 # them with the quotient-degree check on tests the transcription against the reference's own trace semantics.
 # ---------------------------------------------------------------------------------------------------------------------
 OPCODE_SHIFT = {"add": 31, "mul": 30, "eq": 29, "assert": 28, "mov": 27, "jmp": 26, "cjmp": 25, "call": 24, "ret": 23, "mload": 22,
-                "mstore": 21, "end": 20, "range": 19, "and": 18, "or": 17, "xor": 16, "not": 15, "neq": 14, "gte": 13, "poseidon": 12, "tload": 9, "tstore": 8}
+                "mstore": 21, "end": 20, "range": 19, "and": 18, "or": 17, "xor": 16, "not": 15, "neq": 14, "gte": 13, "poseidon": 12, "sload": 11,
+                "sstore": 10, "tload": 9, "tstore": 8}
 CPU_SELECTOR_COL = {"add": 66, "mul": 66, "eq": 66, "assert": 66, "neq": 66, "mov": 67, "jmp": 68, "cjmp": 69, "call": 70, "ret": 71,
-                    "mload": 72, "mstore": 73, "end": 74, "range": 75, "and": 76, "or": 76, "xor": 76, "not": 77, "gte": 78, "poseidon": 79, "tload": 82, "tstore": 83}
+                    "mload": 72, "mstore": 73, "end": 74, "range": 75, "and": 76, "or": 76, "xor": 76, "not": 77, "gte": 78, "poseidon": 79, "sload": 80, "sstore": 81,
+                    "tload": 82, "tstore": 83}
 
 
 def _finv(x):
@@ -537,7 +609,7 @@ def ola_encode(ins):
     dst = op0 = op1 = None
     if op in ("add", "mul", "eq", "neq", "gte", "and", "or", "xor", "poseidon", "tload"):
         dst, op0, op1 = ins[1], ins[2], ins[3]
-    elif op == "tstore":
+    elif op in ("tstore", "sstore", "sload"):
         op0, op1 = ins[1], ins[2]
     elif op in ("mov", "not"):
         dst, op1 = ins[1], ins[2]
@@ -579,6 +651,7 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False, orc=
     |op0 - op1| (RangeCheck rows looked by Cmp) and the operands of the range rows (RangeCheck rows looked by the CPU)."""
     cmp_pairs, rc_cmp, rc_cpu, mem, mem_log, bit_ops, psdn_calls = [], [], [], {}, [], [], []
     tp, tape, tape_log = 0, {}, {}   # tape pointer, tape contents, per-address access log (gen_tape_table order)
+    st_idx, st_cache, st_log = 0, {}, []   # storage_access_idx, tx storage cache (tree key -> value), access log
     words, at_pc = [], {}
     for ins in program:
         enc = ola_encode(ins)
@@ -592,7 +665,7 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False, orc=
         op, step = ins[0], len(enc)
         row = {"clk": clk, "pc": pc, "tp": tp, "regs": list(regs), "inst": enc[0], "imm": enc[1] if step == 2 else 0,
                "op1_imm": 1 if step == 2 else 0, "opcode": 1 << OPCODE_SHIFT[op], "op": op,
-               "op0": 0, "op1": 0, "dst": 0, "aux0": 0, "aux1": 0, "s_op0": None, "s_op1": None, "s_dst": None}
+               "op0": 0, "op1": 0, "dst": 0, "aux0": 0, "aux1": 0, "s_op0": None, "s_op1": None, "s_dst": None, "idx_storage": st_idx}
 
         def val(x):  # get_index_value (lib.rs:297-320)
             if isinstance(x, str):
@@ -625,6 +698,47 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False, orc=
             regs[_reg(ins[1])] = r
             row["dst"], row["s_dst"] = r, _reg(ins[1])
             pc += step
+        elif op in ("sstore", "sload"):  # execute_inst_sstore / _sload, lib.rs:1263-1403, :1405-1530 (contract address 0)
+            assert orc is not None, "storage opcodes hash the tree key: pass orc"
+            mask = 1 << OPCODE_SHIFT[op]
+            key_addr = regs[_reg(ins[1])]
+            row["op0"], row["s_op0"] = key_addr, _reg(ins[1])
+            val_addr = val(ins[2])
+            row["op1"] = val_addr
+            e = dict(row)                      # the ext line (aux_insert!, lib.rs:128-150): same clk / pc / instruction / registers,
+            e["regs"] = list(row["regs"])      # a fresh RegisterSelector holding the operands, the 4 + 4 memory cells and the tree key
+            e["is_ext"], e["ext_cnt"], e["ext_len"], e["s_op0"], e["s_op1"], e["s_dst"] = 1, 1, 1, None, None, None
+            slot_key = [mem[(key_addr + i) % P] for i in range(4)]
+            for i in range(4):                 # sstore interleaves key / value reads, sload reads the key first: same log per cell
+                mem_log.append(((key_addr + i) % P, clk, mask, 0, slot_key[i]))
+                if op == "sstore":
+                    mem_log.append(((val_addr + i) % P, clk, mask, 0, mem[(val_addr + i) % P]))
+            hin = [0, 0, 0, 0] + slot_key + [0, 0, 0, 0]   # StorageKey::raw_hashed_key (core/src/types/storage/mod.rs:37-46)
+            tree_key = [int(x) for x in orc.poseidon(np.array(hin, dtype=np.uint64))[:4]]
+            pre = st_cache.get(tuple(tree_key), [0, 0, 0, 0])
+            if op == "sstore":
+                value = [mem[(val_addr + i) % P] for i in range(4)]
+                st_cache[tuple(tree_key)] = value
+            else:
+                value = pre
+                for i in range(4):
+                    mem[(val_addr + i) % P] = value[i]
+                    mem_log.append(((val_addr + i) % P, clk, mask, 1, value[i]))
+            st_idx += 1
+            e["idx_storage"] = st_idx
+            raw = {}
+            for i in range(4):
+                raw[36 + i], raw[36 + 4 + i] = (key_addr + i) % P, slot_key[i]
+                raw[46 + i], raw[46 + 4 + i] = (val_addr + i) % P, value[i]
+                raw[56 + i] = tree_key[i]
+            e["sel_raw"] = raw
+            st_log.append(dict(idx=st_idx, is_write=int(op == "sstore"), tree_key=tree_key, pre_leaf=pre, leaf=value, hash_input=hin))
+            row["ext_len"] = 1
+            steps.append(row)
+            steps.append(e)
+            pc += step
+            clk += 1
+            continue
         elif op in ("tstore", "tload"):  # execute_inst_tstore / _tload + tape_copy!, lib.rs:153-181, :1687-1846
             ext_rows = []
             if op == "tstore":   # copy `len` memory words at [op0] to the tape at tp, then tp += len
@@ -813,6 +927,7 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False, orc=
         t[16:26, i] = s["regs"]
         t[26, i], t[27, i], t[28, i], t[29, i] = s["inst"], s["op1_imm"], s["opcode"], s["imm"]
         t[30, i], t[31, i], t[32, i], t[33, i], t[34, i] = s["op0"], s["op1"], s["dst"], s["aux0"], s["aux1"]
+        t[35, i] = s["idx_storage"]
         if s["s_op0"] is not None:
             t[36 + s["s_op0"], i] = 1
         if s["s_op1"] is not None:
@@ -821,6 +936,9 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False, orc=
             t[56 + s["s_dst"], i] = 1
         if "s_op0_0" in s:
             t[36, i] = s["s_op0_0"]                     # ext lines of tload / tstore keep the tape address in s_op0[0]
+        for col, v in s.get("sel_raw", {}).items():     # ext lines of sstore / sload: cell addresses, cell values, tree key
+            t[col, i] = v
+        t[90, i] = 1 if (s.get("is_ext", 0) and s["op"] in ("sstore", "sload")) else 0   # is_storage_ext_line
         t[CPU_SELECTOR_COL[s["op"]], i] = 1
         t[85, i] = 1                                  # is_entry_sc: env_idx == 0
         t[86, i] = 1 if s.get("ext_len", 0) == s.get("ext_cnt", 0) else 0   # is_next_line_diff_inst: ext_length == ext_cnt
@@ -831,12 +949,16 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False, orc=
     k = len(steps)
     if k != n:  # padding, generation/cpu.rs:180-208
         t[26, k:] = t[26, k - 1]
+        t[35, k:] = t[35, k - 1]
         t[28, k:] = 1 << 20
         t[74, k:] = 1
         t[85, k:] = 1
         t[86, k:] = 1
         t[87, k:] = 0
         t[93, k:] = 1
+    if want_side_tables == "all+storage":
+        return t, steps, cmp_pairs, rc_cmp, rc_cpu, mem_log, bit_ops, psdn_calls, tape_log, st_log
+    assert not st_log, "storage accesses are only returned with want_side_tables='all+storage'"
     if want_side_tables == "all+tape":
         return t, steps, cmp_pairs, rc_cmp, rc_cpu, mem_log, bit_ops, psdn_calls, tape_log
     assert not tape_log, "tape rows are only returned with want_side_tables='all+tape'"
@@ -871,7 +993,7 @@ def program_rows_of_run(program, steps):
     return prog_rows, exec_rows
 
 
-MEM_OP_SELECTOR = {1 << 22: 6, 1 << 21: 7, 1 << 24: 8, 1 << 23: 9, 1 << 9: 10, 1 << 8: 11, 1 << 12: 13}  # mload, mstore, call, ret, tload, tstore, poseidon (memory/columns.rs:16-23)
+MEM_OP_SELECTOR = {1 << 22: 6, 1 << 21: 7, 1 << 24: 8, 1 << 23: 9, 1 << 9: 10, 1 << 8: 11, 1 << 12: 13, 1 << 10: 14, 1 << 11: 15}  # mload, mstore, call, ret, tload, tstore, poseidon, sstore, sload (memory/columns.rs:16-25)
 
 
 def tape_trace_from_log(tape_log, log_n):
@@ -1062,6 +1184,30 @@ def calls_program(n_iter, linear=False, bitwise=False, poseidon=False, tape=Fals
     return [tuple(labels[a] if (isinstance(a, str) and a in labels) else a for a in x) for x in body if not isinstance(x, str)]
 
 
+def storage_program():
+    """sstore / sload over two slots of contract 0: write slot A, read it back, overwrite it (a repeated write), write slot
+    B, read an absent slot C (all-zero value), read A again; every loaded word is then pulled into a register through
+    mload so that the values the storage tree returned reach the register file.  Memory layout: keys at 200 / 210 / 220
+    (4 words each), values at 300 / 310, read buffers at 400...; r9 stays 0 (no stack frame is needed)."""
+    prog = [("mov", "r1", 200), ("mov", "r2", 300), ("mov", "r3", 400), ("mov", "r5", 210), ("mov", "r6", 310), ("mov", "r7", 220)]
+    cells = {200: [1, 2, 3, 4], 210: [5, 6, 7, 8], 220: [9, 9, 9, 9], 300: [11, 12, 13, 14], 310: [21, 22, 23, 24]}
+    for base, words in cells.items():
+        prog.append(("mov", "r8", base))
+        for i, w in enumerate(words):
+            prog += [("mov", "r0", w), ("mstore", "r8", i, "r0")]
+    prog += [("sstore", "r1", "r2"),            # A := (11, 12, 13, 14)      initial write
+             ("sload", "r1", "r3"),             # [400..404) := A
+             ("mload", "r4", "r3", 2),          # r4 = 13
+             ("sstore", "r1", "r6"),            # A := (21, 22, 23, 24)      repeated write
+             ("sstore", "r5", "r2"),            # B := (11, 12, 13, 14)
+             ("sload", "r7", 410),              # [410..414) := C = 0        (immediate buffer address)
+             ("sload", "r1", 420),              # [420..424) := A
+             ("mov", "r8", 420), ("mload", "r0", "r8", 3),   # r0 = 24
+             ("mov", "r8", 410), ("mload", "r2", "r8", 0),   # r2 = 0
+             ("end",)]
+    return prog
+
+
 def fib_program(n_iter):
     """r0, r1 = fib pair; r2 = loop counter; loops n_iter times, checks the result bookkeeping with eq / assert / neq / not."""
     return [
@@ -1202,10 +1348,10 @@ def run_system(orc, rng, program, cpu_log=None, beta=0x1234567890ABCDEF % P, bet
     """Run `program` (VM tuples) and build every table its run touches: always Cpu, Cmp, RangeCheck, Program; Memory, Bitwise,
     Tape, Poseidon + PoseidonChunk when the run produced rows for them.  Returns (table_ids, traces, compress_challenges,
     steps)."""
-    nsteps = len(cpu_vm_trace(program, 20, want_side_tables="all+tape", orc=orc)[1]) if cpu_log is None else None
+    nsteps = len(cpu_vm_trace(program, 20, want_side_tables="all+storage", orc=orc)[1]) if cpu_log is None else None
     if cpu_log is None:
         cpu_log = max(4, (nsteps - 1).bit_length())
-    cpu_t, steps, cmp_pairs, rc_cmp, rc_cpu, mlog, bit_ops, psdn_calls, tape_log = cpu_vm_trace(program, cpu_log, want_side_tables="all+tape", orc=orc)
+    cpu_t, steps, cmp_pairs, rc_cmp, rc_cpu, mlog, bit_ops, psdn_calls, tape_log, st_log = cpu_vm_trace(program, cpu_log, want_side_tables="all+storage", orc=orc)
     lg = lambda k, lo: max(lo, (max(k, 1) - 1).bit_length())
     tabs = {0: cpu_t}
     cc = {}
@@ -1217,9 +1363,15 @@ def run_system(orc, rng, program, cpu_log=None, beta=0x1234567890ABCDEF % P, bet
         cc[2] = beta_bitwise
     tabs[3] = cmp_trace(cmp_pairs, lg(len(cmp_pairs) + 1, 4))
     tabs[4] = rangecheck_trace(rc_cmp, cpu_vals=rc_cpu, mem_sort_vals=rc_sort)
+    hash_rows = []
     if psdn_calls:
         tabs[6], psdn_rows = poseidon_chunk_trace_from_calls(psdn_calls, lg(sum(len(c["rows"]) for c in psdn_calls) + 1, 2))
-        tabs[5] = poseidon_valid_trace(orc, lg(len(psdn_rows) + 1, 4), [(inp, [1, 0, 0, 0]) for inp, _ in psdn_rows])
+        hash_rows += [(inp, [1, 0, 0, 0]) for inp, _ in psdn_rows]
+    if st_log:  # sstore / sload: StorageAccess walks one consistent tree; tree-key, leaf and branch hashes join the Poseidon table
+        tabs[7], st_rows = storage_tables_from_log(orc, rng, st_log)
+        hash_rows += st_rows
+    if hash_rows:
+        tabs[5] = poseidon_valid_trace(orc, lg(len(hash_rows) + 1, 4), hash_rows)
     if tape_log:
         tabs[8] = tape_trace_from_log(tape_log, lg(sum(len(v) for v in tape_log.values()) + 1, 2))
     prog_rows, exec_rows = program_rows_of_run(program, steps)

@@ -184,14 +184,15 @@ def test_real_program_run_systems(ctx, orc):
     assert ok, msg
 
 
-@pytest.mark.parametrize("name", ["fibo_recursive", "call", "tape", "bitwise", "comparison", "range_check", "memory", "mem_gep"])
+@pytest.mark.parametrize("name", ["fibo_recursive", "call", "tape", "bitwise", "comparison", "range_check", "memory", "mem_gep", "context_fetch"])
 def test_reference_programs_run_and_prove(ctx, orc, name):
     """The reference's own assembly test programs (tests/golden/ola_programs.json) run through the restated VM: the GPU
     prover's quotients pass the degree check, the proof bytes equal the oracle's and the product verifier accepts."""
     import json
 
     text = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ola_programs.json")))["programs"][name]
-    ids, traces, cc, steps = tracegen.run_system(orc, np.random.default_rng(3), tracegen.parse_ola_asm(text))
+    ids, traces, cc, steps = tracegen.run_system(orc, np.random.default_rng(3), tracegen.parse_ola_asm(text),
+                                                 init_tape=tracegen.CONTEXT_TAPE if name == "context_fetch" else ())
     got = olavm_b200.prove_with_traces(ctx, ids, traces, compress_challenges=cc)
     assert got == orc.stark_prove(ids, traces, compress_challenges=cc)
     ok, msg = olavm_b200.verify_proof(ids, got)

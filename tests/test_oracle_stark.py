@@ -397,10 +397,11 @@ def _reference_program(name):
     ("fibo_recursive", [0, 1, 3, 4, 10], 55, 2000),      # fib(10) by recursion: 2150 executed rows, 176 call / ret pairs
     ("memory", [0, 1, 3, 4, 10], 2, 17),                 # mstore / mload through [r9,r3,-1]: address = anchor + factor * register
     ("mem_gep", [0, 1, 3, 4, 10], 3, 30),                # array_index(2) of {1, 2, 3} through mload r0 [r9,r6] (factor 1)
+    ("context_fetch", [0, 1, 3, 4, 8, 10], 1027, 18),    # chain_id(): tload of cell 7 of the transaction's INITIAL tape (is_init_seg rows)
 ])  # call, tape, bitwise, comparison and range_check run in the GPU suite (tests/test_gpu_stark.py) and inside the eleven-table system
 def test_reference_programs_run_and_prove(orc, name, tables, r0, min_steps):
     prog = _reference_program(name)
-    ids, traces, cc, steps = tracegen.run_system(orc, np.random.default_rng(3), prog)
+    ids, traces, cc, steps = tracegen.run_system(orc, np.random.default_rng(3), prog, init_tape=tracegen.CONTEXT_TAPE if name == "context_fetch" else ())
     assert ids == tables and len(steps) >= min_steps and steps[-1]["regs"][0] == r0
     proof = orc.stark_prove(ids, traces, compress_challenges=cc)
     ok, msg = orc.stark_verify(ids, proof)
@@ -445,8 +446,9 @@ def test_all_constraints_vanish_on_the_traces_of_a_real_run(orc):
     assert ids == [0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 11]
     for tid, t, c in zip(ids, traces, cc):
         assert orc.air_first_failure(tid, t, c) is None, tid
-    for name in ("memory", "mem_gep", "call", "tape", "bitwise", "comparison", "range_check"):
-        pids, ptraces, pcc, _ = tracegen.run_system(orc, np.random.default_rng(3), _reference_program(name))
+    for name in ("memory", "mem_gep", "call", "tape", "bitwise", "comparison", "range_check", "context_fetch"):
+        pids, ptraces, pcc, _ = tracegen.run_system(orc, np.random.default_rng(3), _reference_program(name),
+                                                    init_tape=tracegen.CONTEXT_TAPE if name == "context_fetch" else ())
         for tid, t, c in zip(pids, ptraces, pcc):
             assert orc.air_first_failure(tid, t, c) is None, (name, tid)
     # a broken cell is located: row and the position of the violated constraint in evaluation order

@@ -645,13 +645,17 @@ def ola_encode(ins):
     return [word] if imm is None else [word, imm]
 
 
-def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False, orc=None):
+def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False, orc=None, init_tape=()):
     """Run `program` (a list of instruction tuples, jump targets = word addresses) and return the [94][2^log_n] CPU table
     and the executed steps; with want_side_tables also the (op0, op1) pairs of the gte rows (Cmp table), their
     |op0 - op1| (RangeCheck rows looked by Cmp) and the operands of the range rows (RangeCheck rows looked by the CPU)."""
     cmp_pairs, rc_cmp, rc_cpu, mem, mem_log, bit_ops, psdn_calls = [], [], [], {}, [], [], []
     tp, tape, tape_log = 0, {}, {}   # tape pointer, tape contents, per-address access log (gen_tape_table order)
     st_idx, st_cache, st_log = 0, {}, []   # storage_access_idx, tx storage cache (tree key -> value), access log
+    for v in init_tape:                    # init_tape (executor/src/load_tx.rs:89-132): tx context, calldata, addresses; is_init cells
+        tape[tp] = int(v) % P
+        tape_log[tp] = [(1, 0, tape[tp], 0)]
+        tp += 1
     words, at_pc = [], {}
     for ins in program:
         enc = ola_encode(ins)
@@ -1289,6 +1293,12 @@ def real_program_system(orc, rng, n_iter=12, linear=False, cpu_log=9, mem_log_n=
 # Running the reference's own assembly test programs (assembler/test_data/asm/*.json, committed as
 # tests/golden/ola_programs.json by tools/extract_encoding_golden.py) through the VM above.
 # ---------------------------------------------------------------------------------------------------------------------
+# A transaction's initial tape as init_tape lays it out (executor/src/load_tx.rs:89-117): block_number, block_timestamp,
+# sequencer_address[4], version, chain_id (address 7), caller_address[4], nonce, signature_r[4], signature_s[4], tx_hash[4],
+# calldata (here one word: length 0), caller / callee / callee-code addresses.
+CONTEXT_TAPE = [5, 1700000000, 1, 2, 3, 4, 3, 1027, 9, 9, 9, 9, 1, 11, 12, 13, 14, 21, 22, 23, 24, 31, 32, 33, 34] + [0] + [0, 0, 0, 1] + [0, 0, 0, 2] * 2
+
+
 def parse_ola_asm(text):
     """Assembly text -> the VM's instruction tuples.  As the reference assembler does (assembler/src/relocate.rs:21-86,
     encoder.rs): the scope labelled `main` moves to the front, an instruction occupies two words when its last operand is an
@@ -1344,14 +1354,14 @@ def parse_ola_asm(text):
     return out
 
 
-def run_system(orc, rng, program, cpu_log=None, beta=0x1234567890ABCDEF % P, beta_bitwise=0x0FEDCBA987654321 % P):
+def run_system(orc, rng, program, cpu_log=None, beta=0x1234567890ABCDEF % P, beta_bitwise=0x0FEDCBA987654321 % P, init_tape=()):
     """Run `program` (VM tuples) and build every table its run touches: always Cpu, Cmp, RangeCheck, Program; Memory, Bitwise,
     Tape, Poseidon + PoseidonChunk when the run produced rows for them.  Returns (table_ids, traces, compress_challenges,
     steps)."""
-    nsteps = len(cpu_vm_trace(program, 20, want_side_tables="all+storage", orc=orc)[1]) if cpu_log is None else None
+    nsteps = len(cpu_vm_trace(program, 20, want_side_tables="all+storage", orc=orc, init_tape=init_tape)[1]) if cpu_log is None else None
     if cpu_log is None:
         cpu_log = max(4, (nsteps - 1).bit_length())
-    cpu_t, steps, cmp_pairs, rc_cmp, rc_cpu, mlog, bit_ops, psdn_calls, tape_log, st_log = cpu_vm_trace(program, cpu_log, want_side_tables="all+storage", orc=orc)
+    cpu_t, steps, cmp_pairs, rc_cmp, rc_cpu, mlog, bit_ops, psdn_calls, tape_log, st_log = cpu_vm_trace(program, cpu_log, want_side_tables="all+storage", orc=orc, init_tape=init_tape)
     lg = lambda k, lo: max(lo, (max(k, 1) - 1).bit_length())
     tabs = {0: cpu_t}
     cc = {}

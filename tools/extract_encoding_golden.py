@@ -123,7 +123,7 @@ def main():
     # the reference's prophet-free assembly test programs that only use modelled opcodes (executor/src/tests.rs runs them):
     # inputs of tests/test_oracle_stark.py::test_reference_programs_run_and_prove
     progs = {}
-    for name in ("bitwise", "range_check", "comparison", "fibo_recursive", "tape", "call", "memory", "mem_gep"):
+    for name in ("bitwise", "range_check", "comparison", "fibo_recursive", "tape", "call", "memory", "mem_gep", "context_fetch"):
         d = json.load(open(os.path.join(REF, "asm", name + ".json")))
         assert not d.get("prophets")
         progs[name] = d["program"]

@@ -358,3 +358,16 @@ def test_storage_opcodes_real_run(ctx, orc):
     assert got == orc.stark_prove(ids, traces, compress_challenges=cc)
     ok, msg = olavm_b200.verify_proof(ids, got)
     assert ok, msg
+
+
+@pytest.mark.parametrize("name", ["malloc", "storage", "poseidon_hash"])
+def test_reference_prophet_programs_run_and_prove(ctx, orc, name):
+    """The reference's malloc-prophet test programs (heap and write-once memory regions; `storage` = its own sstore / sload
+    program, `poseidon_hash` = its poseidon-opcode program with calldata on the initial tape): GPU proof bytes = oracle's."""
+    from test_oracle_stark import _reference_run
+
+    ids, traces, cc, _ = _reference_run(orc, name)
+    got = olavm_b200.prove_with_traces(ctx, ids, traces, compress_challenges=cc)
+    assert got == orc.stark_prove(ids, traces, compress_challenges=cc)
+    ok, msg = olavm_b200.verify_proof(ids, got)
+    assert ok, msg

@@ -393,6 +393,18 @@ def _reference_program(name):
     return tracegen.parse_ola_asm(json.load(open(path))["programs"][name])
 
 
+def _reference_run(orc, name):
+    """Run one of the reference's test programs the way executor/src/tests.rs does (its calldata on the initial tape, its
+    malloc prophets) -> (table ids, traces, compress challenges, steps)."""
+    import json
+    import os
+
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ola_programs.json")))
+    prog, prophets = tracegen.parse_ola_prophets({"program": g["programs"][name], "prophets": g["prophets"].get(name, [])})
+    tape = tracegen.reference_test_tape(tracegen.REFERENCE_CALLDATA[name]) if name in tracegen.REFERENCE_CALLDATA else ()
+    return tracegen.run_system(orc, np.random.default_rng(3), prog, prophets=prophets, init_tape=tape)
+
+
 @pytest.mark.parametrize("name,tables,r0,min_steps", [
     ("fibo_recursive", [0, 1, 3, 4, 10], 55, 2000),      # fib(10) by recursion: 2150 executed rows, 176 call / ret pairs
     ("memory", [0, 1, 3, 4, 10], 2, 17),                 # mstore / mload through [r9,r3,-1]: address = anchor + factor * register
@@ -512,3 +524,53 @@ def test_storage_accesses_bind_to_the_tree(orc, storage_run, case):
         return
     ok, msg = orc.stark_verify(ids, proof)
     assert not ok and "Cross-table lookup" in msg
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's test programs that use the prophet (hint) mechanism, for the one built-in they share -- `malloc`: the
+# prophet stack pointer (`mov r0 psp`), outputs in the write-once region, heap cells, i.e. all three regions of the Memory
+# table (gen_memory_table's region logic, diff_addr_cond and the MemRegion range checks).  `storage`, `storage_multi_keys`
+# and `storage_u32` are the reference's own sstore / sload programs, `poseidon` / `poseidon_hash` its poseidon-opcode ones;
+# the ones with calldata get the initial tape executor/src/tests.rs gives them.
+# ---------------------------------------------------------------------------------------------------------------------
+PROPHET_PROGRAMS = ["malloc", "mem_gep_vector", "poseidon", "poseidon_hash", "ptr_call", "storage", "storage_multi_keys", "storage_u32"]
+
+
+@pytest.mark.parametrize("name", PROPHET_PROGRAMS)
+def test_prophet_programs_satisfy_every_table(orc, name):
+    ids, traces, cc, steps = _reference_run(orc, name)
+    assert 1 in ids and steps[-1]["op"] == "end"
+    for tid, t, c in zip(ids, traces, cc):
+        assert orc.air_first_failure(tid, t, c) is None, (name, tid)
+    mem_t = traces[ids.index(1)]
+    assert mem_t[24].any() and mem_t[25].any()          # prophet-region and heap rows are present
+    if name.startswith("storage"):
+        assert 7 in ids and 5 in ids                    # StorageAccess + the tree-key / leaf / branch hashes
+    if name.startswith("poseidon"):
+        assert 6 in ids                                 # PoseidonChunk
+
+
+@pytest.mark.parametrize("name", ["storage", "poseidon_hash"])
+def test_prophet_programs_prove(orc, name):
+    ids, traces, cc, _ = _reference_run(orc, name)
+    proof = orc.stark_prove(ids, traces, compress_challenges=cc)
+    ok, msg = orc.stark_verify(ids, proof)
+    assert ok, msg
+
+
+def test_memory_regions_bind(orc):
+    """A heap cell that reads a value nobody wrote, and a prophet cell written twice, are rejected by the Memory AIR."""
+    ids, traces, cc, _ = _reference_run(orc, "malloc")
+    mem_t = traces[ids.index(1)]
+    heap_reads = [i for i in range(mem_t.shape[1]) if mem_t[25, i] == 1 and mem_t[17, i] == 0]
+    b = mem_t.copy()
+    if heap_reads:
+        b[18, heap_reads[0]] = (int(b[18, heap_reads[0]]) + 1) % P
+    else:  # malloc.json only writes its block: corrupt the value the program read back from the prophet cell instead
+        i = next(i for i in range(mem_t.shape[1]) if mem_t[24, i] == 1 and mem_t[17, i] == 0 and mem_t[16, i] == 0)
+        b[18, i] = (int(b[18, i]) + 1) % P
+    assert orc.air_first_failure(1, b) is not None
+    b = mem_t.copy()
+    i = next(i for i in range(mem_t.shape[1]) if mem_t[24, i] == 1 and mem_t[17, i] == 0 and mem_t[16, i] == 0)
+    b[17, i] = 1                                        # a second WRITE to a write-once cell by mload's row
+    assert orc.air_first_failure(1, b) is not None

@@ -637,7 +637,9 @@ def ola_encode(ins):
     if op0 is not None:
         word |= 1 << (52 + _reg(op0))
     if op1 is not None:
-        if isinstance(op1, str):
+        if op1 == "psp":
+            pass  # the prophet stack pointer: neither an op1 register bit nor the immediate flag (binary_program.rs:286-290)
+        elif isinstance(op1, str):
             word |= 1 << (42 + _reg(op1))
         else:
             word |= 1 << 62
@@ -645,13 +647,20 @@ def ola_encode(ins):
     return [word] if imm is None else [word, imm]
 
 
-def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False, orc=None, init_tape=()):
+PSP_START_ADDR = P - 0xFFFFFFFF        # core/src/vm/memory.rs:8-10: prophet (write-once) region [p - span, p), heap [p - 2 span, p - span)
+HP_START_ADDR = P - 2 * 0xFFFFFFFF
+
+
+def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False, orc=None, init_tape=(), prophets=None):
     """Run `program` (a list of instruction tuples, jump targets = word addresses) and return the [94][2^log_n] CPU table
     and the executed steps; with want_side_tables also the (op0, op1) pairs of the gte rows (Cmp table), their
     |op0 - op1| (RangeCheck rows looked by Cmp) and the operands of the range rows (RangeCheck rows looked by the CPU)."""
     cmp_pairs, rc_cmp, rc_cpu, mem, mem_log, bit_ops, psdn_calls = [], [], [], {}, [], [], []
     tp, tape, tape_log = 0, {}, {}   # tape pointer, tape contents, per-address access log (gen_tape_table order)
     st_idx, st_cache, st_log = 0, {}, []   # storage_access_idx, tx storage cache (tree key -> value), access log
+    psp = psp_start = PSP_START_ADDR       # Process::new (executor/src/lib.rs:267-269); hp starts one past the heap-pointer cell
+    hp = HP_START_ADDR + 1
+    prophets = prophets or {}
     for v in init_tape:                    # init_tape (executor/src/load_tx.rs:89-132): tx context, calldata, addresses; is_init cells
         tape[tp] = int(v) % P
         tape_log[tp] = [(1, 0, tape[tp], 0)]
@@ -672,10 +681,26 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False, orc=
                "op0": 0, "op1": 0, "dst": 0, "aux0": 0, "aux1": 0, "s_op0": None, "s_op1": None, "s_dst": None, "idx_storage": st_idx}
 
         def val(x):  # get_index_value (lib.rs:297-320)
+            if x == "psp":
+                return psp_start
             if isinstance(x, str):
                 row["s_op1"] = _reg(x)
                 return regs[_reg(x)]
             return int(x) % P
+
+
+        def run_prophet(at_pc_):  # Process::prophet (lib.rs:369-444) for the one built-in the prophet-using test programs share
+            nonlocal psp, psp_start, hp
+            spec = prophets.get(at_pc_)
+            if spec is None:
+                return
+            assert spec["fn"] == "malloc" and spec["inputs"] == 1, "only `cid.addr = malloc(cid.len)` prophets are modelled"
+            ln = regs[1]                       # the first prophet input comes from r1 (PROPHET_INPUT_REG_START_INDEX)
+            hp = (hp + ln) % P                 # travel_malloc (interpreter/src/interpreter/executor.rs:656-671): hp += len, returns the NEW hp
+            psp_start = psp
+            mem[psp] = hp                      # outputs go to the write-once region at psp, clk 0, opcode 0
+            mem_log.append((psp, 0, 0, 1, hp))
+            psp += 1
 
         if op == "end":
             steps.append(row)
@@ -919,6 +944,7 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False, orc=
             pc = t
         else:
             raise ValueError(op)
+        run_prophet(row["pc"])                 # lib.rs:2255-2257: the prophet labelled at this pc runs after its instruction
         steps.append(row)
         clk += 1
         assert len(steps) < max_steps, "program does not terminate"
@@ -1048,38 +1074,50 @@ def poseidon_chunk_trace_from_calls(calls, log_n):
 
 
 def memory_trace_from_log(mem_log, log_n):
-    """Memory table of a VM run whose accesses all fall in the read-write (stack) region: gen_memory_table
-    (executor/src/trace.rs:20-199: cells grouped by address in ascending order, access order inside an address, diff_addr /
-    diff_clk and the value each non-first row sends to the RangeCheck table) + generate_memory_trace
-    (circuits/src/generation/memory.rs:8-155, padding with write-once rows from p - (2^32 - 1) upwards).
-    Returns (table [29][2^log_n], mem_sort range-check values)."""
+    """Memory table of a VM run: gen_memory_table (executor/src/trace.rs:20-199: cells grouped by address in ascending
+    order, access order inside an address; diff_addr / diff_clk / diff_addr_cond and the values each row sends to the
+    RangeCheck table, by region: read-write stack below p - 2 span, read-write heap [p - 2 span, p - span), write-once
+    prophet region [p - span, p)) + generate_memory_trace (circuits/src/generation/memory.rs:8-155: the two range-check
+    filters, padding with write-once rows).  Log entries: (addr, clk, opcode mask or 0 for a prophet write, is_write,
+    value).  Returns (table [29][2^log_n], mem_sort range-check values, mem_region range-check values) -- the second
+    list only when a heap / prophet cell was touched (the two-value form is kept for runs that stay on the stack)."""
     SPAN = (1 << 32) - 1
     by_addr = {}
     for addr, clk, op, is_write, value in mem_log:
-        assert addr < P - 2 * SPAN, "only the read-write region is modelled"
         by_addr.setdefault(addr, []).append((clk, op, is_write, value))
-    cells, rc_sort = [], []
+    cells = []
     origin_addr = origin_clk = 0
-    first_row = True
+    first_row = first_heap_row = True
     for addr in sorted(by_addr):
         new_addr = True
+        prophet, heap = int(addr >= P - SPAN), int(P - 2 * SPAN <= addr < P - SPAN)
+        cond = (P - addr) if prophet else ((P - SPAN - addr) if heap else 0)
         for clk, op, is_write, value in by_addr[addr]:
-            c = {"addr": addr, "clk": clk, "op": op, "is_write": is_write, "value": value, "diff_addr": 0, "diff_addr_inv": 0,
-                 "diff_clk": 0, "rw_addr_unchanged": 0, "rc_value": 0}
+            c = {"addr": addr, "clk": clk, "op": op, "is_write": is_write, "value": value, "is_rw": 1 - prophet, "prophet": prophet,
+                 "heap": heap, "cond": cond, "diff_addr": 0, "diff_addr_inv": 0, "diff_clk": 0, "rw_addr_unchanged": 0, "rc_value": 0}
             if first_row:
                 first_row = new_addr = False
+                if heap:
+                    first_heap_row = False
             elif new_addr:
                 c["diff_addr"] = addr - origin_addr
-                c["diff_addr_inv"] = _finv(c["diff_addr"])
-                c["rc_value"] = c["diff_addr"]
-                rc_sort.append(c["rc_value"])
+                if prophet:                       # write-once region: the row is ordered by its distance to p, not by diff_addr
+                    c["rc_value"] = cond
+                elif heap and first_heap_row:     # the first heap cell: nothing to compare with
+                    c["diff_addr"] = 0
+                    first_heap_row = False
+                else:
+                    c["diff_addr_inv"] = _finv(c["diff_addr"])
+                    c["rc_value"] = c["diff_addr"]
                 new_addr = False
             else:
                 c["diff_clk"] = clk - origin_clk
-                c["rw_addr_unchanged"] = 1
-                c["rc_value"] = c["diff_clk"]
-                rc_sort.append(c["rc_value"])
-            assert c["rc_value"] <= 0xFFFFFFFF, "U32RangeCheckFail"
+                if prophet:
+                    c["rc_value"] = cond
+                else:
+                    c["rw_addr_unchanged"] = 1
+                    c["rc_value"] = c["diff_clk"]
+            assert c["rc_value"] <= 0xFFFFFFFF and cond <= 0xFFFFFFFF, "U32RangeCheckFail"
             cells.append(c)
             origin_clk = clk
         origin_addr = addr
@@ -1087,16 +1125,24 @@ def memory_trace_from_log(mem_log, log_n):
     k = len(cells)
     assert 2 <= k <= n
     t = np.zeros((29, n), dtype=np.uint64)
+    rc_sort, rc_region = [], []
     for i, c in enumerate(cells):
-        t[2, i], t[3, i], t[4, i], t[5, i] = 1, c["addr"], c["clk"], c["op"]
-        t[MEM_OP_SELECTOR[c["op"]], i] = 1
+        t[2, i], t[3, i], t[4, i], t[5, i] = c["is_rw"], c["addr"], c["clk"], c["op"]
+        t[16 if c["op"] == 0 else MEM_OP_SELECTOR[c["op"]], i] = 1     # opcode 0 = a prophet write (COL_MEM_S_PROPHET)
         t[17, i], t[18, i] = c["is_write"], c["value"]
-        t[19, i], t[20, i], t[21, i] = c["diff_addr"], c["diff_addr_inv"], c["diff_clk"]
-        t[23, i], t[26, i] = c["rw_addr_unchanged"], c["rc_value"]
-        t[27, i] = 0 if i == 0 else 1
-    if k != n:  # memory.rs:113-146 (the last filled row is read-write: padding starts at p - span)
-        addr = P - SPAN
+        t[19, i], t[20, i], t[21, i], t[22, i] = c["diff_addr"], c["diff_addr_inv"], c["diff_clk"], c["cond"]
+        t[23, i], t[24, i], t[25, i], t[26, i] = c["rw_addr_unchanged"], c["prophet"], c["heap"], c["rc_value"]
+        looking = not (i == 0 or c["prophet"] or (c["heap"] and not cells[i - 1]["heap"]))
+        t[27, i] = int(looking)
+        t[28, i] = int(c["heap"] or c["prophet"])
+        if looking:
+            rc_sort.append(c["rc_value"])
+        if t[28, i]:
+            rc_region.append(c["cond"])
+    if k != n:  # memory.rs:113-146: padding continues the write-once region (from p - span when the last filled row is read-write)
+        addr = P - SPAN if cells[-1]["is_rw"] else cells[-1]["addr"] + 1
         for i in range(k, n):
+            assert addr < P, "the prophet region is full"
             t[16, i] = 1
             t[3, i] = addr
             t[17, i] = 1
@@ -1106,6 +1152,8 @@ def memory_trace_from_log(mem_log, log_n):
             t[24, i] = 1
             t[26, i] = t[22, i]
             addr += 1
+    if rc_region:
+        return t, rc_sort, rc_region
     return t, rc_sort
 
 
@@ -1299,7 +1347,37 @@ def real_program_system(orc, rng, n_iter=12, linear=False, cpu_log=9, mem_log_n=
 CONTEXT_TAPE = [5, 1700000000, 1, 2, 3, 4, 3, 1027, 9, 9, 9, 9, 1, 11, 12, 13, 14, 21, 22, 23, 24, 31, 32, 33, 34] + [0] + [0, 0, 0, 1] + [0, 0, 0, 2] * 2
 
 
-def parse_ola_asm(text):
+def reference_test_tape(calldata):
+    """The initial tape executor/src/tests.rs::executor_run_test_program builds for a test with calldata: init_tape
+    (load_tx.rs:89-117) over init_tx_context_mock (core/src/vm/transaction.rs:18-56), the calldata, then the caller /
+    callee / callee-code addresses the test fixes (tests.rs:69-86)."""
+    ctx = [3, 1692846754, 1, 2, 3, 4, 3, 1, 5, 6, 7, 8, 25, 129, 130, 131, 132, 133, 134, 135, 136, 137, 138, 139, 140]
+    return ctx + [int(x) for x in calldata] + [17, 18, 19, 20] + [9, 10, 11, 12] + [13, 14, 15, 16]
+
+
+# calldata of the reference's own executor tests (executor/src/tests.rs), by program
+REFERENCE_CALLDATA = {"fibo_loop": [10, 1, 2, 1015130275], "ptr_call": [0, 2657046596], "sc_input": [10, 20, 2, 253268590],
+                      "storage_u32": [0, 2364819430], "poseidon_hash": [0, 1239976900], "context_fetch": [0, 3458276513]}
+
+
+def parse_ola_prophets(doc):
+    """(program tuples, {pc: prophet spec}) of an assembler/test_data/asm/<name>.json document: a prophet is keyed by the word
+    address of its `.PROPHETn_0` label (relocate.rs) and runs after the instruction there.  Only the `malloc` built-in is
+    modelled (cpu_vm_trace.run_prophet); anything else raises."""
+    import re
+
+    prog, labels = parse_ola_asm(doc["program"], want_labels=True)
+    out = {}
+    for p in doc.get("prophets", []):
+        code = re.sub(r"\s+", "", p["code"])
+        if code != "%{entry(){cid.addr=malloc(cid.len);}%}":
+            raise NotImplementedError("prophet: " + p["code"])
+        assert len(p["inputs"]) == 1 and p["inputs"][0]["length"] == 1 and not p["inputs"][0]["is_ref"] and len(p["outputs"]) == 1
+        out[labels[p["label"]]] = {"fn": "malloc", "inputs": 1}
+    return prog, out
+
+
+def parse_ola_asm(text, want_labels=False):
     """Assembly text -> the VM's instruction tuples.  As the reference assembler does (assembler/src/relocate.rs:21-86,
     encoder.rs): the scope labelled `main` moves to the front, an instruction occupies two words when its last operand is an
     immediate or a label or when it is mload / mstore, labels resolve to word addresses.  Memory operands [rN], [rN,off]."""
@@ -1325,7 +1403,7 @@ def parse_ola_asm(text):
         parts = l.replace(", ", ",").split()
         op, args = parts[0], parts[1:]
         insts.append((op, args))
-        two = op in ("mload", "mstore") or (bool(args) and not (is_reg(args[-1]) or args[-1].startswith("[")))
+        two = op in ("mload", "mstore") or (bool(args) and not (is_reg(args[-1]) or args[-1] == "psp" or args[-1].startswith("[")))
         pc += 2 if two else 1
     out = []
     for op, args in insts:
@@ -1337,7 +1415,7 @@ def parse_ola_asm(text):
                 res.append((mf.group(1), (mf.group(2), int(mf.group(3) or 1))))
             elif m:
                 res.append((m.group(1), int(m.group(2) or 0)))
-            elif is_reg(a):
+            elif is_reg(a) or a == "psp":
                 res.append(a)
             elif re.fullmatch(r"[+-]?\d+", a):
                 res.append(int(a))
@@ -1351,28 +1429,30 @@ def parse_ola_asm(text):
             out.append(("mload", dst, base, off))
         else:
             out.append((op, *res))
-    return out
+    return (out, labels) if want_labels else out
 
 
-def run_system(orc, rng, program, cpu_log=None, beta=0x1234567890ABCDEF % P, beta_bitwise=0x0FEDCBA987654321 % P, init_tape=()):
+def run_system(orc, rng, program, cpu_log=None, beta=0x1234567890ABCDEF % P, beta_bitwise=0x0FEDCBA987654321 % P, init_tape=(), prophets=None):
     """Run `program` (VM tuples) and build every table its run touches: always Cpu, Cmp, RangeCheck, Program; Memory, Bitwise,
     Tape, Poseidon + PoseidonChunk when the run produced rows for them.  Returns (table_ids, traces, compress_challenges,
     steps)."""
-    nsteps = len(cpu_vm_trace(program, 20, want_side_tables="all+storage", orc=orc, init_tape=init_tape)[1]) if cpu_log is None else None
+    nsteps = len(cpu_vm_trace(program, 20, want_side_tables="all+storage", orc=orc, init_tape=init_tape, prophets=prophets)[1]) if cpu_log is None else None
     if cpu_log is None:
         cpu_log = max(4, (nsteps - 1).bit_length())
-    cpu_t, steps, cmp_pairs, rc_cmp, rc_cpu, mlog, bit_ops, psdn_calls, tape_log, st_log = cpu_vm_trace(program, cpu_log, want_side_tables="all+storage", orc=orc, init_tape=init_tape)
+    cpu_t, steps, cmp_pairs, rc_cmp, rc_cpu, mlog, bit_ops, psdn_calls, tape_log, st_log = cpu_vm_trace(program, cpu_log, want_side_tables="all+storage", orc=orc, init_tape=init_tape, prophets=prophets)
     lg = lambda k, lo: max(lo, (max(k, 1) - 1).bit_length())
     tabs = {0: cpu_t}
     cc = {}
-    rc_sort = []
+    rc_sort, rc_region = [], []
     if len(mlog) >= 2:
-        tabs[1], rc_sort = memory_trace_from_log(mlog, lg(len(mlog) + 1, 2))
+        out = memory_trace_from_log(mlog, lg(len(mlog) + 1, 2))
+        tabs[1], rc_sort = out[0], out[1]
+        rc_region = out[2] if len(out) == 3 else []
     if bit_ops:
         tabs[2] = bitwise_valid_trace(rng, 9, beta_bitwise, ops=bit_ops)
         cc[2] = beta_bitwise
     tabs[3] = cmp_trace(cmp_pairs, lg(len(cmp_pairs) + 1, 4))
-    tabs[4] = rangecheck_trace(rc_cmp, cpu_vals=rc_cpu, mem_sort_vals=rc_sort)
+    tabs[4] = rangecheck_trace(rc_cmp, cpu_vals=rc_cpu, mem_sort_vals=rc_sort, mem_region_vals=rc_region)
     hash_rows = []
     if psdn_calls:
         tabs[6], psdn_rows = poseidon_chunk_trace_from_calls(psdn_calls, lg(sum(len(c["rows"]) for c in psdn_calls) + 1, 2))

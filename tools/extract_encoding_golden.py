@@ -82,8 +82,6 @@ def main():
         for pc, op, args in insts:
             if op not in MODELLED:
                 continue
-            if any(a == "psp" for a in args):
-                continue  # the prophet stack pointer is not modelled
             res = []
             for a in args:
                 m = re.fullmatch(r"\[(r\d)(?:,([+-]?\d+))?\]", a)
@@ -92,7 +90,7 @@ def main():
                     res.append([mf.group(1), [mf.group(2), int(mf.group(3) or 1)]])
                 elif m:
                     res.append([m.group(1), int(m.group(2) or 0)])
-                elif is_reg(a):
+                elif is_reg(a) or a == "psp":  # psp: the prophet stack pointer special register (mov only)
                     res.append(a)
                 elif re.fullmatch(r"[+-]?\d+", a):
                     res.append(int(a))
@@ -122,14 +120,21 @@ def main():
     print(path, len(pairs), "distinct pairs from", sum(per_contract.values()), "instructions", os.path.getsize(path), "bytes")
     # the reference's prophet-free assembly test programs that only use modelled opcodes (executor/src/tests.rs runs them):
     # inputs of tests/test_oracle_stark.py::test_reference_programs_run_and_prove
-    progs = {}
+    progs, prophets = {}, {}
     for name in ("bitwise", "range_check", "comparison", "fibo_recursive", "tape", "call", "memory", "mem_gep", "context_fetch"):
         d = json.load(open(os.path.join(REF, "asm", name + ".json")))
         assert not d.get("prophets")
         progs[name] = d["program"]
         tracegen.parse_ola_asm(d["program"])  # (the reference ships assembled binaries only for its system contracts, above)
+    # programs whose only prophets are `cid.addr = malloc(cid.len)` (the one built-in the VM models): program + prophets
+    for name in ("malloc", "mem_gep_vector", "poseidon", "poseidon_hash", "ptr_call", "storage", "storage_multi_keys", "storage_u32"):
+        d = json.load(open(os.path.join(REF, "asm", name + ".json")))
+        tracegen.parse_ola_prophets(d)
+        progs[name] = d["program"]
+        prophets[name] = d["prophets"]
     path = os.path.join(ROOT, "tests/golden/ola_programs.json")
-    json.dump({"source": "assembler/test_data/asm/<name>.json, field program", "programs": progs}, open(path, "w"), indent=0)
+    json.dump({"source": "assembler/test_data/asm/<name>.json, fields program and prophets", "programs": progs, "prophets": prophets},
+              open(path, "w"), indent=0)
     print(path, os.path.getsize(path), "bytes")
 
 

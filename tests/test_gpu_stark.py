@@ -360,7 +360,7 @@ def test_storage_opcodes_real_run(ctx, orc):
     assert ok, msg
 
 
-@pytest.mark.parametrize("name", ["malloc", "storage", "poseidon_hash"])
+@pytest.mark.parametrize("name", ["malloc", "storage", "poseidon_hash", "fibo_loop"])
 def test_reference_prophet_programs_run_and_prove(ctx, orc, name):
     """The reference's malloc-prophet test programs (heap and write-once memory regions; `storage` = its own sstore / sload
     program, `poseidon_hash` = its poseidon-opcode program with calldata on the initial tape): GPU proof bytes = oracle's."""

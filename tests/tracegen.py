@@ -694,7 +694,10 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False, orc=
             spec = prophets.get(at_pc_)
             if spec is None:
                 return
-            assert spec["fn"] == "malloc" and spec["inputs"] == 1, "only `cid.addr = malloc(cid.len)` prophets are modelled"
+            if spec["fn"] == "printf":         # no outputs: the interpreter returns only the heap pointer; psp_start catches up
+                psp_start = psp
+                return
+            assert spec["fn"] == "malloc" and spec["inputs"] == 1, "only the malloc and printf built-ins are modelled"
             ln = regs[1]                       # the first prophet input comes from r1 (PROPHET_INPUT_REG_START_INDEX)
             hp = (hp + ln) % P                 # travel_malloc (interpreter/src/interpreter/executor.rs:656-671): hp += len, returns the NEW hp
             psp_start = psp
@@ -1362,14 +1365,19 @@ REFERENCE_CALLDATA = {"fibo_loop": [10, 1, 2, 1015130275], "ptr_call": [0, 26570
 
 def parse_ola_prophets(doc):
     """(program tuples, {pc: prophet spec}) of an assembler/test_data/asm/<name>.json document: a prophet is keyed by the word
-    address of its `.PROPHETn_0` label (relocate.rs) and runs after the instruction there.  Only the `malloc` built-in is
+    address of the instruction BEFORE its `.PROPHETn_m` label (relocate.rs:151-159) and runs after that instruction, so that the
+    `mov rX psp` behind the label already sees its outputs.  Only the `malloc` built-in is
     modelled (cpu_vm_trace.run_prophet); anything else raises."""
     import re
 
-    prog, labels = parse_ola_asm(doc["program"], want_labels=True)
+    prog, labels = parse_ola_asm(doc["program"], want_labels="hosts")
     out = {}
     for p in doc.get("prophets", []):
         code = re.sub(r"\s+", "", p["code"])
+        if code == "%{entry(){printf(cid.base,cid.flag);}%}":
+            assert not p["outputs"]
+            out[labels[p["label"]]] = {"fn": "printf", "inputs": 2}
+            continue
         if code != "%{entry(){cid.addr=malloc(cid.len);}%}":
             raise NotImplementedError("prophet: " + p["code"])
         assert len(p["inputs"]) == 1 and p["inputs"][0]["length"] == 1 and not p["inputs"][0]["is_ref"] and len(p["outputs"]) == 1
@@ -1395,14 +1403,16 @@ def parse_ola_asm(text, want_labels=False):
     scopes.sort(key=lambda sc: 0 if sc[0] == "main:" else 1)
     assert scopes[0][0] == "main:", "no main scope"
     is_reg = lambda a: re.fullmatch(r"r\d", a) is not None
-    labels, pc, insts = {}, 0, []
+    labels, pc, insts, last_pc, label_host = {}, 0, [], 0, {}
     for l in (x for sc in scopes for x in sc):
         if l.endswith(":"):
             labels[l[:-1]] = pc
+            label_host[l[:-1]] = last_pc     # a prophet label's host is the instruction BEFORE it (relocate.rs:151-159, ori_counter)
             continue
         parts = l.replace(", ", ",").split()
         op, args = parts[0], parts[1:]
         insts.append((op, args))
+        last_pc = pc
         two = op in ("mload", "mstore") or (bool(args) and not (is_reg(args[-1]) or args[-1] == "psp" or args[-1].startswith("[")))
         pc += 2 if two else 1
     out = []
@@ -1429,7 +1439,7 @@ def parse_ola_asm(text, want_labels=False):
             out.append(("mload", dst, base, off))
         else:
             out.append((op, *res))
-    return (out, labels) if want_labels else out
+    return (out, label_host) if want_labels == "hosts" else ((out, labels) if want_labels else out)
 
 
 def run_system(orc, rng, program, cpu_log=None, beta=0x1234567890ABCDEF % P, beta_bitwise=0x0FEDCBA987654321 % P, init_tape=(), prophets=None):

@@ -1360,7 +1360,8 @@ def reference_test_tape(calldata):
 
 # calldata of the reference's own executor tests (executor/src/tests.rs), by program
 REFERENCE_CALLDATA = {"fibo_loop": [10, 1, 2, 1015130275], "ptr_call": [0, 2657046596], "sc_input": [10, 20, 2, 253268590],
-                      "storage_u32": [0, 2364819430], "poseidon_hash": [0, 1239976900], "context_fetch": [0, 3458276513]}
+                      "storage_u32": [0, 2364819430], "poseidon_hash": [0, 1239976900], "context_fetch": [0, 3458276513],
+                      "printf": [5, 111, 108, 97, 118, 109, 11, 12, 8, 3238128773]}
 
 
 def parse_ola_prophets(doc):

@@ -532,7 +532,7 @@ def test_storage_accesses_bind_to_the_tree(orc, storage_run, case):
 # the ones with calldata get the initial tape executor/src/tests.rs gives them.
 # ---------------------------------------------------------------------------------------------------------------------
 PROPHET_PROGRAMS = ["malloc", "mem_gep_vector", "poseidon", "poseidon_hash", "ptr_call", "storage", "storage_multi_keys", "storage_u32",
-                    "fibo_loop", "printf"]  # fibo_loop: the program of the reference's criterion bench (circuits/benches/fibo_loop.rs), malloc + printf prophets
+                    "fibo_loop", "printf", "global"]  # global: div / mod helper prophets and reads of the heap-pointer cell; fibo_loop: the program of the reference's criterion bench (circuits/benches/fibo_loop.rs), malloc + printf prophets
 
 
 @pytest.mark.parametrize("name", PROPHET_PROGRAMS)

@@ -660,7 +660,8 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False, orc=
     st_idx, st_cache, st_log = 0, {}, []   # storage_access_idx, tx storage cache (tree key -> value), access log
     psp = psp_start = PSP_START_ADDR       # Process::new (executor/src/lib.rs:267-269); hp starts one past the heap-pointer cell
     hp = HP_START_ADDR + 1
-    prophets = prophets or {}
+    mem[HP_START_ADDR] = HP_START_ADDR + 1   # "init heap ptr" (lib.rs:2088-2100); gen_memory_table drops that row (trace.rs:33-38), the
+    prophets = prophets or {}               # Memory AIR pins the cell's first value instead (memory_stark.rs, ADDR_HEAP_PTR)
     for v in init_tape:                    # init_tape (executor/src/load_tx.rs:89-132): tx context, calldata, addresses; is_init cells
         tape[tp] = int(v) % P
         tape_log[tp] = [(1, 0, tape[tp], 0)]
@@ -697,7 +698,15 @@ def cpu_vm_trace(program, log_n, max_steps=1 << 20, want_side_tables=False, orc=
             if spec["fn"] == "printf":         # no outputs: the interpreter returns only the heap pointer; psp_start catches up
                 psp_start = psp
                 return
-            assert spec["fn"] == "malloc" and spec["inputs"] == 1, "only the malloc and printf built-ins are modelled"
+            if spec["fn"] in ("mod", "div", "split_hi", "split_lo"):   # one-line integer helpers written in the prophet language itself
+                x, y = regs[1], regs[2]                                  # inputs: r1, r2 (read_prophet_input, lib.rs:322-367)
+                v = {"mod": lambda: x % y, "div": lambda: x // y, "split_hi": lambda: x >> 32, "split_lo": lambda: x & 0xFFFFFFFF}[spec["fn"]]()
+                psp_start = psp
+                mem[psp] = v
+                mem_log.append((psp, 0, 0, 1, v))
+                psp += 1
+                return
+            assert spec["fn"] == "malloc" and spec["inputs"] == 1, "only malloc, printf and the integer helpers are modelled"
             ln = regs[1]                       # the first prophet input comes from r1 (PROPHET_INPUT_REG_START_INDEX)
             hp = (hp + ln) % P                 # travel_malloc (interpreter/src/interpreter/executor.rs:656-671): hp += len, returns the NEW hp
             psp_start = psp
@@ -1361,7 +1370,7 @@ def reference_test_tape(calldata):
 # calldata of the reference's own executor tests (executor/src/tests.rs), by program
 REFERENCE_CALLDATA = {"fibo_loop": [10, 1, 2, 1015130275], "ptr_call": [0, 2657046596], "sc_input": [10, 20, 2, 253268590],
                       "storage_u32": [0, 2364819430], "poseidon_hash": [0, 1239976900], "context_fetch": [0, 3458276513],
-                      "printf": [5, 111, 108, 97, 118, 109, 11, 12, 8, 3238128773]}
+                      "printf": [5, 111, 108, 97, 118, 109, 11, 12, 8, 3238128773], "global": [0, 4171824493]}
 
 
 def parse_ola_prophets(doc):
@@ -1378,6 +1387,14 @@ def parse_ola_prophets(doc):
         if code == "%{entry(){printf(cid.base,cid.flag);}%}":
             assert not p["outputs"]
             out[labels[p["label"]]] = {"fn": "printf", "inputs": 2}
+            continue
+        helpers = {"%{functionmod(feltx,felty)->felt{returnx%y;}entry(){cid.r=mod(cid.x,cid.y);}%}": ("mod", 2),
+                   "%{functiondiv(feltx,felty)->felt{returnx/y;}entry(){cid.q=div(cid.x,cid.y);}%}": ("div", 2),
+                   "%{functionsplit_hi(feltin)->felt{returnin/4294967296;}entry(){cid.out=split_hi(cid.in);}%}": ("split_hi", 1),
+                   "%{functionsplit_lo(feltin)->felt{returnin%4294967296;}entry(){cid.out=split_lo(cid.in);}%}": ("split_lo", 1)}
+        if code in helpers:
+            assert len(p["inputs"]) == helpers[code][1] and len(p["outputs"]) == 1 and all(i["length"] == 1 and not i["is_ref"] for i in p["inputs"])
+            out[labels[p["label"]]] = {"fn": helpers[code][0], "inputs": helpers[code][1]}
             continue
         if code != "%{entry(){cid.addr=malloc(cid.len);}%}":
             raise NotImplementedError("prophet: " + p["code"])

@@ -128,7 +128,7 @@ def main():
         tracegen.parse_ola_asm(d["program"])  # (the reference ships assembled binaries only for its system contracts, above)
     # programs whose only prophets are `cid.addr = malloc(cid.len)` / `printf(...)` (the built-ins the VM models): program + prophets
     for name in ("malloc", "mem_gep_vector", "poseidon", "poseidon_hash", "ptr_call", "storage", "storage_multi_keys", "storage_u32",
-                 "fibo_loop", "printf"):
+                 "fibo_loop", "printf", "global"):
         d = json.load(open(os.path.join(REF, "asm", name + ".json")))
         tracegen.parse_ola_prophets(d)
         progs[name] = d["program"]

@@ -14,7 +14,8 @@ uniform Goldilocks columns.  A "step" is one pass of that path over the whole 20
                all host cores) on a bounded column sample of the same workload
   coset_shard_commit (every N) : one 94-column 2^20-row commitment strong-scaled over the ranks by LDE cosets, cap
                assembled by one NCCL all-gather
-  prove_all_tables (N = 1)     : wall time of one 12-table proof with a 2^22-row CPU table from pinned host traces
+  prove_all_tables             : wall time of one 12-table proof with a 2^22-row CPU table from pinned host traces (coset-sharded
+               over the ranks at N > 1); at N = 1 also under Blake3GoldilocksConfig (key "blake3")
 
 Multi-GPU (torchrun, one rank per GPU): columns are independent, so ranks shard by column with no data-path
 collective (weak scaling: 200 columns per GPU); time = max over ranks.

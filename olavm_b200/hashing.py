@@ -1,5 +1,6 @@
-"""Mirror of plonky2's Poseidon hashing entry points used by the prover
-(plonky2/plonky2/src/hash/poseidon.rs:640-652 `PoseidonHash`, hashing.rs:66-108, merkle_tree/mod.rs:180)."""
+"""Mirror of plonky2's hashing entry points used by the prover: `Hasher::hash_no_pad` / `MerkleTree::new_v2` under the
+context's hasher (`ctx.hasher`: PoseidonHash, plonky2/plonky2/src/hash/poseidon.rs:640-652 + hashing.rs:66-108, or
+Blake3_256<32>, hash/blake3.rs:201-234) and the raw Poseidon permutation (merkle_tree/mod.rs:180)."""
 import numpy as np
 
 from . import _lib
@@ -15,7 +16,8 @@ def poseidon(ctx, states):
 
 
 def hash_no_pad_rows(ctx, rows):
-    """PoseidonHash::hash_no_pad of every row of a row-major [nrows, ncols] matrix -> [nrows, 4]."""
+    """H::hash_no_pad of every row of a row-major [nrows, ncols] matrix -> [nrows, 4] (H = ctx.hasher; a BLAKE3 digest is its
+    32 bytes as 4 little-endian u64, not field elements)."""
     a = np.ascontiguousarray(rows, dtype=np.uint64)
     out = np.empty((a.shape[0], 4), dtype=np.uint64)
     ctx.check(ctx._lib.ola_hash_rows(ctx.handle, _lib.hptr(a), _lib.hptr(out), 0, a.shape[0], a.shape[1]))

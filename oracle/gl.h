@@ -31,15 +31,16 @@
 
 typedef unsigned __int128 u128;
 
-static inline uint64_t gl_canon(uint64_t x) { return x >= GL_P ? x - GL_P : x; }
+/* (the conditional corrections are written as masks: on random field elements the branches are coin flips, and the
+ * mispredictions, not the arithmetic, were most of the oracle's run time) */
+static inline uint64_t gl_canon(uint64_t x) { return x - ((0 - (uint64_t)(x >= GL_P)) & GL_P); }
 
 static inline uint64_t gl_add(uint64_t a, uint64_t b) {
     /* a, b canonical */
     uint64_t s = a + b;
-    if (s < a || s >= GL_P) s -= GL_P;
-    return s;
+    return s - ((0 - (uint64_t)((s < a) | (s >= GL_P))) & GL_P);
 }
-static inline uint64_t gl_sub(uint64_t a, uint64_t b) { return a >= b ? a - b : a + (GL_P - b); }
+static inline uint64_t gl_sub(uint64_t a, uint64_t b) { return (a - b) + ((0 - (uint64_t)(a < b)) & GL_P); }
 static inline uint64_t gl_neg(uint64_t a) { return a ? GL_P - a : 0; }
 
 /* goldilocks_field.rs:342-355 reduce128, then canonicalised */
@@ -47,10 +48,10 @@ static inline uint64_t gl_reduce128(u128 x) {
     uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
     uint64_t hi_hi = hi >> 32, hi_lo = hi & GL_EPS;
     uint64_t t0 = lo - hi_hi;
-    if (lo < hi_hi) t0 -= GL_EPS;
+    t0 -= (0 - (uint64_t)(lo < hi_hi)) & GL_EPS;
     uint64_t t1 = hi_lo * GL_EPS;
     uint64_t t2 = t0 + t1;
-    if (t2 < t0) t2 += GL_EPS;
+    t2 += (0 - (uint64_t)(t2 < t0)) & GL_EPS;
     return gl_canon(t2);
 }
 static inline uint64_t gl_mul(uint64_t a, uint64_t b) { return gl_reduce128((u128)a * b); }

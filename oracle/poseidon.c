@@ -35,12 +35,20 @@ static void sbox_layer(uint64_t *s) {
 }
 /* poseidon.rs:168-189 + :236-257: out[r] = sum_i v[(i+r)%12]*CIRC[i] + v[r]*DIAG[r] */
 static void mds_layer(uint64_t *s) {
-    uint64_t out[W];
+    /* the same sums, accumulated the way poseidon.rs:236-257 does: 32-bit halves of the state in u64 accumulators (the
+     * coefficients are < 2^6, 13 terms: no overflow), recombined as lo + (hi << 32) and reduced once */
+    uint64_t lo[2 * W], hi[2 * W], out[W];
+    for (int i = 0; i < W; i++) {
+        lo[i] = lo[i + W] = s[i] & 0xFFFFFFFFULL;
+        hi[i] = hi[i + W] = s[i] >> 32;
+    }
     for (int r = 0; r < W; r++) {
-        u128 acc = 0;
-        for (int i = 0; i < W; i++) acc += (u128)s[(i + r) % W] * ORC_MDS_MATRIX_CIRC[i];
-        acc += (u128)s[r] * ORC_MDS_MATRIX_DIAG[r];
-        out[r] = gl_reduce128(acc);
+        uint64_t al = lo[r] * ORC_MDS_MATRIX_DIAG[r], ah = hi[r] * ORC_MDS_MATRIX_DIAG[r];
+        for (int i = 0; i < W; i++) {
+            al += lo[i + r] * ORC_MDS_MATRIX_CIRC[i];
+            ah += hi[i + r] * ORC_MDS_MATRIX_CIRC[i];
+        }
+        out[r] = gl_reduce128((u128)al + ((u128)ah << 32));
     }
     memcpy(s, out, sizeof(out));
 }

@@ -55,3 +55,15 @@ def test_accepts_valid_trace_of_a_wide_and_a_narrow_table(orc, name):
     ok, msg = olavm_b200.verify_proof(ids, proof, hasher=B3)
     assert ok, msg
     assert orc.stark_verify(ids, proof, hasher_id=orc.BLAKE3)[0]
+
+
+def test_accepts_the_reference_storage_program_under_blake3(orc):
+    """The reference's own sstore / sload program (seven tables of one run, the 134-column Poseidon table among them: two
+    BLAKE3 chunks and a parent per leaf) proven by the oracle under Blake3GoldilocksConfig: the product verifier accepts."""
+    from test_oracle_stark import _reference_run
+
+    ids, traces, cc, _ = _reference_run(orc, "storage")
+    proof = orc.stark_prove(ids, traces, compress_challenges=cc, hasher_id=orc.BLAKE3)
+    ok, msg = olavm_b200.verify_proof(ids, proof, hasher=B3)
+    assert ok, msg
+    assert not olavm_b200.verify_proof(ids, proof)[0]

@@ -14,3 +14,8 @@ python bench.py 2>gpurun_out/r02a_bench.err | tee gpurun_out/r02a_bench_n1.json 
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02a_launches_bench.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --prove-log-n 18 > /dev/null 2>&1
 tail -2 gpurun_out/r02a_launches_bench.csv
+# (6) one full ncu capture of the constraint-quotient kernel (profiles/r01t_quotient_static_analysis.md, candidate 4):
+#     the per-line stall page decides between the shared-memory staging and the lazy-primitive leads
+ncu --set full --clock-control none --import-source on -k regex:quotient_kernel -s 2 -c 1 -o gpurun_out/r02a_quotient -f \
+    python tools/bench_prove.py --blake3 20 > gpurun_out/r02a_quotient_ncu.log 2>&1
+tail -2 gpurun_out/r02a_quotient_ncu.log

@@ -51,7 +51,7 @@ def test_merkle_tree_nodes_and_cap_equal_oracle(b3ctx, orc):
             assert (sib == orc.merkle_prove(digests, 256, 3, i)).all()
 
 
-@pytest.mark.parametrize("ncols,log_n", [(12, 10), (94, 8), (134, 6)])
+@pytest.mark.parametrize("ncols,log_n", [(12, 10), (94, 8), (134, 6), (94, 14)])
 def test_commitment_equals_oracle(b3ctx, orc, ncols, log_n):
     vals = orc.rand_elems(5 + ncols, (ncols, 1 << log_n))
     batch = olavm_b200.PolynomialBatch.from_values(b3ctx, vals, 3, False, 4)

@@ -208,6 +208,21 @@ int ola_verify(const int* table_ids, uint32_t ntables, const uint8_t* proof, siz
 /* the same for a proof made under `hasher` (OLA_HASH_*): verify_proof::<F, C, D> with C = Blake3GoldilocksConfig */
 int ola_verify_cfg(int hasher, const int* table_ids, uint32_t ntables, const uint8_t* proof, size_t proof_len, char* err,
                    size_t errcap);
+/* ---- trace-generation tail: what sits directly in front of prove_with_traces ----
+ * generate_poseidon_trace (circuits/src/generation/poseidon.rs:5-130) together with the per-round states the executor
+ * records for each hash (core/src/util/poseidon_utils.rs:289-420): `inputs` [nrows][12] permutation inputs and `filters`
+ * [nrows][4] (looked_normal, looked_treekey, looked_storage_leaf, looked_storage_branch; NULL = all 0) -> the
+ * column-major Poseidon table `out` [134][2^log_n] (builtins/poseidon/columns.rs:6-42); rows past nrows are the
+ * zero-input padding row (POSEIDON_ZERO_HASH_*).  One GPU thread per row.  on_device: all three pointers are device
+ * pointers. */
+int ola_generate_poseidon_trace(ola_ctx* ctx, const uint64_t* inputs, const uint64_t* filters, size_t nrows, uint32_t log_n, uint64_t* out,
+                                int on_device);
+/* The compress challenge of the Bitwise / Program tables: a fresh Poseidon Challenger observes `ncols` HOST columns of n
+ * elements, column after column, and squeezes one element (generate_bitwise_trace, generation/builtin.rs:118-131: the 12
+ * limb columns; generate_prog_trace, generation/prog.rs:23-29: the 8 interleaved root limbs as one column).  A duplex
+ * sponge is sequential: host code on the library's own transcript, no context needed. */
+int ola_compress_challenge(const uint64_t* const* cols, uint32_t ncols, size_t n, uint64_t* beta_out);
+
 /* number of trace columns of a table (S::COLUMNS), or -1 if its constraint kernel is not compiled in */
 int ola_table_columns(int table_id);
 

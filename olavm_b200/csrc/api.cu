@@ -18,7 +18,12 @@ namespace {
 template <typename F>
 int guarded(ola_ctx* ctx, F&& f) {
     try {
-        if (ctx) ola::set_alloc_stream(ctx->stream);
+        if (ctx) {
+            // a context is bound to its device: callers may come from any host thread / after switching devices
+            int cur = -1;
+            if (cudaGetDevice(&cur) != cudaSuccess || cur != ctx->device) OLA_CUDA(cudaSetDevice(ctx->device));
+            ola::set_alloc_stream(ctx->stream);
+        }
         f();
         return OLA_OK;
     } catch (const ola::Error& e) {
@@ -468,6 +473,38 @@ int ola_verify_cfg(int hasher, const int* table_ids, uint32_t ntables, const uin
         return OLA_ERR_INTERNAL;
     }
 }
+// ---- trace-generation tail (generation.cu) ----
+int ola_generate_poseidon_trace(ola_ctx* ctx, const uint64_t* inputs, const uint64_t* filters, size_t nrows, uint32_t log_n, uint64_t* out,
+                                int on_device) {
+    if (!ctx || (!inputs && nrows) || !out || log_n > 28 || nrows > ((size_t)1 << log_n)) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        const size_t n = (size_t)1 << log_n;
+        if (on_device) {
+            ola::generation::poseidon_trace(ctx, inputs, filters, nrows, log_n, out);
+            return;
+        }
+        DevBuf d_in(std::max<size_t>(nrows * 12, 1)), d_f(std::max<size_t>(nrows * 4, 1)), d_out(134 * n);
+        if (nrows) to_device(ctx, d_in.p, inputs, nrows * 12);
+        if (nrows && filters) to_device(ctx, d_f.p, filters, nrows * 4);
+        ola::generation::poseidon_trace(ctx, d_in.p, filters ? d_f.p : nullptr, nrows, log_n, d_out.p);
+        to_host(ctx, out, d_out.p, 134 * n);
+    });
+}
+int ola_compress_challenge(const uint64_t* const* cols, uint32_t ncols, size_t n, uint64_t* beta_out) {
+    if ((!cols && ncols) || !beta_out) return OLA_ERR_INVALID_ARG;
+    try {
+        ola::stark::Challenger ch(OLA_HASH_POSEIDON);
+        for (uint32_t c = 0; c < ncols; ++c) {
+            if (!cols[c] && n) return OLA_ERR_INVALID_ARG;
+            for (size_t i = 0; i < n; ++i) ch.observe(cols[c][i]);
+        }
+        *beta_out = ch.get_challenge();
+        return OLA_OK;
+    } catch (...) {
+        return OLA_ERR_INTERNAL;
+    }
+}
+
 int ola_table_columns(int table_id) {
     try {
         return ola::stark::table_available(table_id) ? ola::stark::table_info(table_id).columns : -1;

@@ -8,4 +8,5 @@
 #include "batch.cu"
 #include "fri.cu"
 #include "stark.cu"
+#include "generation.cu"
 #include "api.cu"

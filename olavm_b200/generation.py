@@ -1,0 +1,57 @@
+"""Mirror of the trace-generation tail (circuits/src/generation), the step directly in front of prove_with_traces:
+`generate_poseidon_trace` (generation/poseidon.rs:5-130, the round states of core/src/util/poseidon_utils.rs included)
+on the GPU, and the Bitwise / Program compress challenge (generation/builtin.rs:118-131, generation/prog.rs:23-29)."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+
+def generate_poseidon_trace(ctx, inputs, filters=None, log_n=None):
+    """inputs [k, 12] permutation inputs, filters [k, 4] (looked_normal, looked_treekey, looked_storage_leaf,
+    looked_storage_branch; default all 0) -> the Poseidon table [134, 2^log_n]; rows past k are zero-input padding rows."""
+    a = np.ascontiguousarray(inputs, dtype=np.uint64).reshape(-1, 12)
+    k = a.shape[0]
+    if log_n is None:
+        log_n = max(1, (max(k, 1) - 1).bit_length())
+    if k > (1 << log_n):
+        raise ValueError("more rows than 2^log_n")
+    f = None
+    if filters is not None:
+        f = np.ascontiguousarray(filters, dtype=np.uint64).reshape(-1, 4)
+        if f.shape[0] != k:
+            raise ValueError("one filter quadruple per input")
+    out = np.empty((134, 1 << log_n), dtype=np.uint64)
+    ctx.check(ctx._lib.ola_generate_poseidon_trace(ctx.handle, _lib.hptr(a) if k else None, _lib.hptr(f), k, log_n, _lib.hptr(out), 0))
+    return out
+
+
+def compress_challenge(columns):
+    """Challenger::new(); observe_elements(column) for every column; get_challenge()."""
+    cols = [np.ascontiguousarray(c, dtype=np.uint64).reshape(-1) for c in columns]
+    n = cols[0].shape[0] if cols else 0
+    if any(c.shape[0] != n for c in cols):
+        raise ValueError("columns of one length")
+    ptrs = (ctypes.c_void_p * max(len(cols), 1))(*[c.ctypes.data for c in cols])
+    beta = ctypes.c_uint64(0)
+    rc = _lib.load().ola_compress_challenge(ptrs, len(cols), n, ctypes.byref(beta))
+    if rc != 0:
+        raise _lib.OlaError(rc, "ola_compress_challenge")
+    return int(beta.value)
+
+
+class Hasher:
+    """The two Poseidon services workload generators need (`poseidon(state)`, `poseidon_table_row(input)`), served by the
+    library's device entry points."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def poseidon(self, state):
+        from . import hashing
+
+        return hashing.poseidon(self.ctx, state)
+
+    def poseidon_table_row(self, inp):
+        return generate_poseidon_trace(self.ctx, np.asarray(inp, dtype=np.uint64).reshape(1, 12), log_n=1)[:, 0].copy()

@@ -25,10 +25,22 @@ def prove_with_traces(ctx, table_ids, trace_poly_values, check_quotient_degree=T
     "Quotient has failed, ..." and OlaError(OLA_ERR_INVALID_ARG, "Non-binary filter?") like partial_products' assert."""
     k = len(table_ids)
     trs = [np.ascontiguousarray(t, dtype=np.uint64) for t in trace_poly_values]
-    for t in trs:
+    if len(trs) != k:
+        raise ValueError("one trace per table id")
+    for tid, t in zip(table_ids, trs):
+        if t.ndim != 2:
+            raise ValueError("a trace is a [columns, rows] matrix")
+        cols = table_columns(ctx, tid)
+        if cols < 0:
+            raise ValueError(f"unknown table id {tid}")
+        if t.shape[0] != cols:   # the C ABI reads columns * rows elements from each pointer
+            raise ValueError(f"table {tid} has {cols} columns, the trace has {t.shape[0]}")
         n = t.shape[1]
         if n == 0 or n & (n - 1):
             raise ValueError("trace length must be a power of 2")
+    if compress_challenges is None and any(int(t) in (TABLES["bitwise"], TABLES["program"]) for t in table_ids):
+        # generation/mod.rs:183-188 always sets both; proving with beta = 0 would make the compress lookups degenerate
+        raise ValueError("the Bitwise and Program tables need their compress challenges (compress_challenges=...)")
     ids = (ctypes.c_int * k)(*[int(x) for x in table_ids])
     ptrs = (ctypes.c_void_p * k)(*[t.ctypes.data for t in trs])
     logs = (ctypes.c_uint32 * k)(*[int(t.shape[1]).bit_length() - 1 for t in trs])

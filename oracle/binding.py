@@ -92,6 +92,8 @@ def _set_sigs(L):
     L.orc_table_columns.argtypes = [_int]
     L.orc_air_first_failure.argtypes = [_int, _u64p, _u32, _u64, ctypes.POINTER(_u64), ctypes.POINTER(_int)]
     L.orc_table_columns.restype = _int
+    L.orc_compress_challenge.argtypes = [ctypes.POINTER(ctypes.c_void_p), _u32, _sz]
+    L.orc_compress_challenge.restype = _u64
 
 
 # ---------------------------------------------------------------- helpers
@@ -304,6 +306,15 @@ def air_first_failure(table_id, trace, compress_challenge=0):
     if rc < 0:
         raise StarkError("air_first_failure: unknown table or bad trace")
     return None if rc == 0 else (int(row.value), int(idx.value))
+
+
+def compress_challenge(columns):
+    """The Bitwise / Program compress challenge (generation/builtin.rs:118-131, generation/prog.rs:23-29): a fresh
+    Challenger observes every column in turn and squeezes one element."""
+    cols = [np.ascontiguousarray(c, dtype=np.uint64).reshape(-1) for c in columns]
+    n = cols[0].shape[0] if cols else 0
+    ptrs = (ctypes.c_void_p * max(len(cols), 1))(*[c.ctypes.data for c in cols])
+    return int(lib().orc_compress_challenge(ptrs, len(cols), n))
 
 
 def poseidon_table_row(inp):

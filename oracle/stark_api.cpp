@@ -94,6 +94,15 @@ int orc_air_first_failure(int table_id, const uint64_t* trace, uint32_t log_n, u
     }
 }
 
+/* The compress challenge of generate_bitwise_trace (circuits/src/generation/builtin.rs:118-131) / generate_prog_trace
+ * (generation/prog.rs:23-29): Challenger::new(), observe_elements(column) column after column, get_challenge(). */
+uint64_t orc_compress_challenge(const uint64_t* const* cols, uint32_t ncols, size_t n) {
+    Challenger ch;
+    for (uint32_t c = 0; c < ncols; c++)
+        for (size_t i = 0; i < n; i++) ch.observe(gl_canon(cols[c][i]));
+    return ch.get_challenge();
+}
+
 int orc_table_columns(int table_id) {
     try { return table_by_id(table_id).columns; } catch (...) { return -1; }
 }

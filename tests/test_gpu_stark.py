@@ -371,3 +371,22 @@ def test_reference_prophet_programs_run_and_prove(ctx, orc, name):
     assert got == orc.stark_prove(ids, traces, compress_challenges=cc)
     ok, msg = olavm_b200.verify_proof(ids, got)
     assert ok, msg
+
+
+def test_fib_loop_2p18_proof_bytes_equal_oracle(ctx, orc):
+    """BASELINE configs[2] at a size the oracle finishes in about a minute: the vectorised fib-loop system
+    (workload/fibloop.py; satisfying traces, all 12 tables, all 19 lookups, CPU table 2^18 rows, Program 2^19,
+    Memory / RangeCheck 2^18), quotient-degree check ON: GPU proof bytes == oracle proof bytes, both verifiers accept."""
+    from olavm_b200 import generation
+    from workload import fibloop
+
+    n = fibloop.bound_for_rows(18)
+    ids, traces, cc, info = fibloop.fib_loop_system(n, generation.Hasher(ctx), log_n_cpu=18)
+    assert info["table_log_n"][0] == 18 and ids == list(range(12))
+    got = olavm_b200.prove_with_traces(ctx, ids, traces, compress_challenges=cc)
+    ok, msg = olavm_b200.verify_proof(ids, got)
+    assert ok, msg
+    ok, msg = orc.stark_verify(ids, got)
+    assert ok, msg
+    ref = orc.stark_prove(ids, traces, check_degree=True, compress_challenges=cc)
+    assert len(got) == len(ref) and got == ref

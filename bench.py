@@ -102,77 +102,87 @@ def cpu_lde(oracle, ncols, log_n, reps=1):
     return 80.0 * n * ncols / best / 1e9, best, os.cpu_count()
 
 
-def table_log_sizes(k):
-    """Row counts (log2) of the 12 tables for a proof whose CPU table has 2^k rows: the other tables at plausible natural
-    sizes (Table enum order, ola_stark.rs:104-119); RangeCheck is at least 2^16 (its fixed u16 column)."""
-    return [k, k - 1, max(k - 4, 8), max(k - 4, 4), max(16, k - 3), max(k - 6, 3), max(k - 6, 3), max(k - 5, 8), max(k - 8, 3),
-            max(k - 10, 2), max(k - 2, 4), max(k - 5, 3)]
+def fib_workload(ctx, log_n, pinned=True):
+    """The 12-table system of BASELINE configs[2]: one run of the fib-loop program (workload/fibloop.py) whose CPU table has
+    2^log_n rows; satisfying traces of all 12 tables, every cross-table lookup balanced.  Generated on the host (numpy) with
+    the library's own Poseidon entry points; no oracle involved."""
+    import torch
+
+    from olavm_b200 import generation
+    from workload import fibloop
+
+    t0 = time.perf_counter()
+    ids, traces, cc, info = fibloop.fib_loop_system(fibloop.bound_for_rows(log_n), generation.Hasher(ctx), log_n_cpu=log_n)
+    info["generation_seconds"] = time.perf_counter() - t0
+    keep = []
+    if pinned:
+        out = []
+        for t in traces:
+            buf = torch.empty(t.shape, dtype=torch.int64).pin_memory()
+            v = buf.numpy().view(np.uint64)
+            v[:] = t
+            keep.append(buf)
+            out.append(v)
+        traces = out
+    return ids, traces, cc, info, keep
 
 
-def prove_all_tables(ctx, log_n, world=1, rank=0, odist=None, device=None):
-    """Second half of BASELINE.json's metric (configs[2]; at N > 1 strong-scaled by cosets, configs[4]): wall time of one 12-table proof whose CPU table has 2^log_n rows
-    (94 trace + 78 CTL-Z + 12 quotient columns), through the C ABI from PINNED HOST traces to proof bytes on the host.
-    Synthetic random traces with binary filters, quotient-degree check off ("pipeline parity": no executor exists here
-    to make a satisfying trace -- every kernel of the proof runs on the same shapes); all 19 cross-table lookups."""
+def prove_all_tables(ctx, log_n, world=1, rank=0, odist=None, device=None, cpu_sample_log=18, with_cpu=True):
+    """Second half of BASELINE.json's metric (configs[2]; at N > 1 strong-scaled by cosets, configs[4]): wall time of one
+    12-table proof of the fib-loop program whose CPU table has 2^log_n rows, through the C ABI from PINNED HOST traces to
+    proof bytes on the host, quotient-degree check ON; the bytes are then checked by the library's verifier and by the
+    oracle's (the checker, outside the timed region)."""
+    import hashlib
+
     import torch
 
     import olavm_b200
 
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import tracegen as tg
-
     dist = None
-
-    rng = np.random.default_rng(22)
-    gens = [tg.cpu_random_trace, tg.memory_random_trace, tg.bitwise_random_trace, tg.cmp_random_trace, None, tg.poseidon_random_trace,
-            tg.poseidon_chunk_random_trace, tg.storage_random_trace, tg.tape_random_trace, tg.sccall_random_trace, tg.program_random_trace,
-            tg.prog_chunk_random_trace]
-    logs = table_log_sizes(log_n)
-    traces, keep = [], []
-    for tid, (g, lg) in enumerate(zip(gens, logs)):
-        t = tg.rangecheck_random_trace(rng, lg) if tid == 4 else g(rng, lg)
-        pinned = torch.empty(t.shape, dtype=torch.int64).pin_memory()
-        v = pinned.numpy().view(np.uint64)
-        v[:] = t
-        keep.append(pinned)
-        traces.append(v)
-    ids = list(range(12))
-    cc = [int(x) for x in rng.integers(0, 0xFFFFFFFF00000001, size=12, dtype=np.uint64)]
-    small = [np.ascontiguousarray(t[:, : min(t.shape[1], 1 << 16 if i == 4 else 1 << 10)]) for i, t in enumerate(traces)]
+    ids, traces, cc, info, keep = fib_workload(ctx, log_n)
+    logs = info["table_log_n"]
+    small_ids, small, small_cc, _, _ = fib_workload(ctx, 10, pinned=False)
     if world > 1:
-        # coset-sharded prover (ola_set_comm): every rank holds the same traces (same seed) and proves collectively;
-        # collectives = NCCL through torch.distributed on the library's stream
+        # coset-sharded prover (ola_set_comm): every rank holds the same traces and proves collectively
         import torch.distributed as dist_mod
 
         dist = dist_mod
-        odist.set_comm_torch(ctx)
+        odist.set_comm(ctx)
 
     def sync_all():
         ctx.sync()
         if world > 1:
             dist.barrier()
 
-    olavm_b200.prove_with_traces(ctx, ids, small, check_quotient_degree=False, compress_challenges=cc)  # warm-up (module load, pool)
+    def prove(tr=traces, c=cc):
+        return olavm_b200.prove_with_traces(ctx, ids, tr, check_quotient_degree=True, compress_challenges=c)
+
+    prove(small, small_cc)  # warm-up (module load, pool)
     sync_all()
     t0 = time.perf_counter()
-    olavm_b200.prove_with_traces(ctx, ids, traces, check_quotient_degree=False, compress_challenges=cc)  # grows the memory pool
+    proof = prove()  # grows the memory pool
     first = time.perf_counter() - t0
     sync_all()
-    # the reported time is an un-instrumented call; a second call with per-launch CUDA events gives the kernel breakdown
-    t0 = time.perf_counter()
-    proof = olavm_b200.prove_with_traces(ctx, ids, traces, check_quotient_degree=False, compress_challenges=cc)
-    dt = time.perf_counter() - t0
-    sync_all()
+    # the reported time is the best of three un-instrumented calls (max over ranks each); a further call with per-launch
+    # CUDA events gives the kernel breakdown
+    runs = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        p2 = prove()
+        dt_i = time.perf_counter() - t0
+        sync_all()
+        assert p2 == proof, "two proofs of the same traces differ"
+        runs.append(odist.max_over_ranks(dt_i, device=device) if world > 1 else dt_i)
+    dt = min(runs)
+    comm0 = odist.comm_bytes(ctx) if world > 1 else 0
     ctx.profile_begin()
     t0 = time.perf_counter()
-    proof2 = olavm_b200.prove_with_traces(ctx, ids, traces, check_quotient_degree=False, compress_challenges=cc)
+    proof2 = prove()
     dt_prof = time.perf_counter() - t0
     prof = ctx.profile_end()
+    comm_bytes = (odist.comm_bytes(ctx) - comm0) if world > 1 else 0
     assert proof2 == proof, "two proofs of the same traces differ"
     if world > 1:
-        dt = odist.max_over_ranks(dt, device=device)  # every rank returns the same proof; the slowest one defines the time
-        import hashlib
-
         digest = torch.tensor(list(hashlib.sha256(proof).digest()[:8]), dtype=torch.int64, device=device)
         lo, hi = digest.clone(), digest.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
@@ -182,62 +192,75 @@ def prove_all_tables(ctx, log_n, world=1, rank=0, odist=None, device=None):
     rows = sum(1 << lg for lg in logs)
     if rank != 0:
         return None
+    ok, why = olavm_b200.verify_proof(ids, proof)
+    out = {"log_n_cpu": log_n, "program": "fib loop (workload/fibloop.py: the inner loop of the reference's fibo_loop benchmark program)",
+           "workload": {k: info[k] for k in ("loop_bound", "cpu_steps", "memory_accesses", "cmp_rows", "bitwise_rows", "fetched_words", "generation_seconds")},
+           "table_log_n": logs, "seconds": dt, "seconds_runs": runs, "first_call_seconds": first, "proof_bytes": len(proof),
+           "proof_sha256_16": hashlib.sha256(proof).hexdigest()[:16], "tables": 12, "ctls": 19, "trace_rows_total": rows,
+           "constraint_rows_per_s": rows / dt, "cpu_table_columns": {"trace": 94, "ctl_z": 78, "quotient": 12},
+           "mode": "satisfying traces of a program run, quotient-degree check ON; pinned host traces in, proof bytes out",
+           "verified_by_ola_verify": bool(ok), "kernel_ms": {k: round(v["ms"], 1) for k, v in top},
+           "kernel_ms_total": round(sum(v["ms"] for v in prof.values()), 1), "seconds_with_event_tracing": dt_prof,
+           "launches": int(sum(v["launches"] for v in prof.values())), "h2d_bytes": int(sum(t.nbytes for t in traces))}
+    if not ok:
+        out["verify_error"] = why
     if world > 1:
-        import hashlib
-
-        return {"log_n_cpu": log_n, "table_log_n": logs, "seconds": dt, "first_call_seconds": first, "proof_bytes": len(proof),
-                "proof_sha256_16": hashlib.sha256(proof).hexdigest()[:16], "tables": 12, "ctls": 19, "trace_rows_total": rows,
-                "constraint_rows_per_s": rows / dt, "parallelism": f"coset-shard x{world} (ola_set_comm over NCCL)", "scaling": "strong",
-                "mode": "synthetic random traces, binary filters, quotient-degree check off; pinned host traces in, proof bytes out",
-                "kernel_ms_rank0": {k: round(v["ms"], 1) for k, v in top}, "kernel_ms_total_rank0": round(sum(v["ms"] for v in prof.values()), 1),
-                "seconds_with_event_tracing": dt_prof, "launches_rank0": int(sum(v["launches"] for v in prof.values()))}
-    # bounded CPU sample of the same path: the oracle port proving a 2^14-row CPU table alone, all host threads
+        out.update({"parallelism": f"coset-shard x{world} (ola_set_comm, NCCL)", "scaling": "strong", "comm_bytes_rank0": int(comm_bytes)})
+        out["kernel_ms_rank0"] = out.pop("kernel_ms")
+    if not with_cpu:
+        out["verified"] = bool(ok)
+        return out
     host_threads()
     import oracle
 
-    sample = tg.cpu_random_trace(np.random.default_rng(14), 14)
-    t0 = time.perf_counter()
-    oracle.stark_prove([0], [sample], check_degree=False)
-    cpu_dt = time.perf_counter() - t0
-    cpu_port = {"kind": "port", "cores": os.cpu_count(), "sample": "oracle port, CPU table alone, 2^14 rows (94 trace + 78 Z + 12 quotient columns)",
-                "seconds": cpu_dt, "constraint_rows_per_s": (1 << 14) / cpu_dt,
-                "context": "reference README.md:69 quotes 39.767 s for a 2^20-row proof on 64 cores (other hardware)"}
-    import hashlib
-
-    # the same proof under Blake3GoldilocksConfig (the config of the reference's own criterion benches,
-    # circuits/benches/fibo_loop.rs:26): last, and fenced, so that nothing it does can cost the numbers above
-    blake3_leg = None
-    try:
-        ctx.hasher = olavm_b200.BLAKE3
-        olavm_b200.prove_with_traces(ctx, ids, small, check_quotient_degree=False, compress_challenges=cc)
-        ctx.sync()
+    ok2, why2 = oracle.stark_verify(ids, proof)   # the checker: the oracle's restated verify_proof on the GPU's bytes
+    out["verified_by_oracle"] = bool(ok2)
+    out["verified"] = bool(ok and ok2)
+    if not ok2:
+        out["oracle_verify_error"] = why2
+    if world == 1:
+        # bounded CPU sample of the SAME path: the oracle port proving the same program's 12-table system with a
+        # 2^cpu_sample_log-row CPU table, all host threads
+        s_ids, s_tr, s_cc, s_info, _ = fib_workload(ctx, cpu_sample_log, pinned=False)
         t0 = time.perf_counter()
-        proof_b3 = olavm_b200.prove_with_traces(ctx, ids, traces, check_quotient_degree=False, compress_challenges=cc)
-        dt_b3 = time.perf_counter() - t0
-        ctx.profile_begin()
-        proof_b3_2 = olavm_b200.prove_with_traces(ctx, ids, traces, check_quotient_degree=False, compress_challenges=cc)
-        prof_b3 = ctx.profile_end()
-        assert proof_b3_2 == proof_b3 and proof_b3 != proof and len(proof_b3) == len(proof)
-        top_b3 = sorted(prof_b3.items(), key=lambda kv: -kv[1]["ms"])[:10]
-        blake3_leg = {"config": "Blake3GoldilocksConfig (C::Hasher = Blake3_256<32>; PoW stays Poseidon)", "seconds": dt_b3,
-                      "constraint_rows_per_s": rows / dt_b3, "proof_sha256_16": hashlib.sha256(proof_b3).hexdigest()[:16],
-                      "kernel_ms": {k: round(v["ms"], 1) for k, v in top_b3},
-                      "kernel_ms_total": round(sum(v["ms"] for v in prof_b3.values()), 1)}
-    except Exception as e:  # noqa: BLE001
-        blake3_leg = {"error": repr(e)[:300]}
-    finally:
+        ref = oracle.stark_prove(s_ids, s_tr, check_degree=True, compress_challenges=s_cc)
+        cpu_dt = time.perf_counter() - t0
+        s_rows = sum(1 << lg for lg in s_info["table_log_n"])
+        got = prove(s_tr, s_cc)
+        out["cpu_baseline"] = {"kind": "port", "cores": os.cpu_count(),
+                               "sample": f"oracle port (naive radix-2 cfft, OpenMP), same 12-table fib-loop system with a 2^{cpu_sample_log}-row CPU table, degree check on",
+                               "table_log_n": s_info["table_log_n"], "seconds": cpu_dt, "constraint_rows_per_s": s_rows / cpu_dt,
+                               "gpu_bytes_equal_oracle_bytes": bool(got == ref),
+                               "context": "reference README.md:69 quotes 39.767 s for a 2^20-row proof on 64 cores (other hardware)"}
+        # the same proof under Blake3GoldilocksConfig (the config of the reference's own criterion benches,
+        # circuits/benches/fibo_loop.rs:26): last, and fenced, so that nothing it does can cost the numbers above
         try:
-            ctx.hasher = olavm_b200.POSEIDON
-        except Exception:  # noqa: BLE001
-            pass
-
-    return {"log_n_cpu": log_n, "blake3": blake3_leg, "cpu_baseline": cpu_port, "proof_sha256_16": hashlib.sha256(proof).hexdigest()[:16], "table_log_n": logs, "seconds": dt, "first_call_seconds": first, "proof_bytes": len(proof), "tables": 12, "ctls": 19,
-            "cpu_table_columns": {"trace": 94, "ctl_z": 78, "quotient": 12}, "trace_rows_total": rows,
-            "constraint_rows_per_s": rows / dt,
-            "mode": "synthetic random traces, binary filters, quotient-degree check off; pinned host traces in, proof bytes out",
-            "kernel_ms": {k: round(v["ms"], 1) for k, v in top}, "kernel_ms_total": round(sum(v["ms"] for v in prof.values()), 1),
-            "seconds_with_event_tracing": dt_prof, "launches": int(sum(v["launches"] for v in prof.values())),
-            "h2d_bytes": int(sum(t.nbytes for t in traces))}
+            ctx.hasher = olavm_b200.BLAKE3
+            prove(small, small_cc)
+            ctx.sync()
+            b3 = []
+            for _ in range(2):
+                t0 = time.perf_counter()
+                proof_b3 = prove()
+                b3.append(time.perf_counter() - t0)
+            ctx.profile_begin()
+            proof_b3_2 = prove()
+            prof_b3 = ctx.profile_end()
+            assert proof_b3_2 == proof_b3 and proof_b3 != proof
+            okb, whyb = olavm_b200.verify_proof(ids, proof_b3, hasher=olavm_b200.BLAKE3)
+            top_b3 = sorted(prof_b3.items(), key=lambda kv: -kv[1]["ms"])[:10]
+            out["blake3"] = {"config": "Blake3GoldilocksConfig (C::Hasher = Blake3_256<32>; PoW stays Poseidon)", "seconds": min(b3),
+                             "constraint_rows_per_s": rows / min(b3), "proof_sha256_16": hashlib.sha256(proof_b3).hexdigest()[:16],
+                             "verified_by_ola_verify": bool(okb), "kernel_ms": {k: round(v["ms"], 1) for k, v in top_b3},
+                             "kernel_ms_total": round(sum(v["ms"] for v in prof_b3.values()), 1)}
+        except Exception as e:  # noqa: BLE001
+            out["blake3"] = {"error": repr(e)[:300]}
+        finally:
+            try:
+                ctx.hasher = olavm_b200.POSEIDON
+            except Exception:  # noqa: BLE001
+                pass
+    return out
 
 
 def coset_shard_commit(ctx, torch, dist, odist, world, rank, device, stream, log_n=20, ncols=94, reps=3):
@@ -325,6 +348,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-prove-log-n", type=int, default=18, help="CPU-table rows (log2) of the oracle-port proof sample")
     ap.add_argument("--prove-log-n", type=int, default=22, help="also time one 12-table proof whose CPU table has 2^k rows (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -453,7 +477,14 @@ def main():
     # extra legs (not the headline): strong-scaled coset-shard commit at every N, the full 12-table proof at N = 1
     extra = {"coset_shard_commit": coset_shard_commit(ctx, torch, dist, odist, world, rank, torch.device("cuda", local_rank), stream)}
     if args.prove_log_n:
-        extra["prove_all_tables"] = prove_all_tables(ctx, args.prove_log_n, world, rank, odist, torch.device("cuda", local_rank))
+        extra["prove_all_tables"] = prove_all_tables(ctx, args.prove_log_n, world, rank, odist, torch.device("cuda", local_rank),
+                                                     cpu_sample_log=args.cpu_prove_log_n, with_cpu=not args.no_cpu_baseline)
+        if rank == 0:
+            pa = extra["prove_all_tables"]
+            # the strong-scaling curve of the metric's first half (one proof, fixed size, N GPUs), surfaced at top level
+            extra["strong_scaling"] = {"metric": f"seconds per 12-table proof, fib-loop program, 2^{args.prove_log_n}-row CPU table (BASELINE configs[2]/[4])",
+                                       "n_gpus": world, "seconds": pa["seconds"], "proof_sha256_16": pa["proof_sha256_16"], "verified": pa.get("verified"),
+                                       "comm_bytes_rank0": pa.get("comm_bytes_rank0", 0), "higher_is_better": False}
     if rank == 0:
         line.update(extra)
         _emit(json.dumps(line))

@@ -201,6 +201,15 @@ typedef int (*ola_allgather_fn)(void* user, const void* send_dev, void* recv_dev
 typedef int (*ola_allreduce_u64_fn)(void* user, void* buf_dev, size_t count_u64, void* stream); /* in place, wrapping sum */
 int ola_set_comm(ola_ctx* ctx, int rank, int world, ola_allgather_fn allgather, ola_allreduce_u64_fn allreduce_sum, void* user);
 
+/* The same communicator bound natively: the library dlopens libnccl (libnccl_path, or NULL = the copy already loaded in
+ * the process / the default search path) and issues ncclAllGather / ncclAllReduce on the context's stream itself, so
+ * that no host-language callback sits on the proving path.  Rank 0 calls ola_nccl_unique_id and hands the 128 bytes to
+ * the other ranks over any side channel; then every rank calls ola_set_comm_nccl (collective: ncclCommInitRank). */
+int ola_nccl_unique_id(const char* libnccl_path, uint8_t id_out[128]);
+int ola_set_comm_nccl(ola_ctx* ctx, const char* libnccl_path, int rank, int world, const uint8_t id[128]);
+/* bytes this rank has received through its communicator so far (all-gathers: world * bytes_per_rank; all-reduces: 8 * count) */
+uint64_t ola_comm_bytes(const ola_ctx* ctx);
+
 /* verify_proof (circuits/src/stark/verifier.rs:32-212) over Buffer::read_all_proof's bytes: host code, no GPU or
  * context needed.  table_ids as for ola_prove (the system the proof was made for).  Returns OLA_OK when the proof is
  * accepted; OLA_ERR_INVALID_ARG with the reason in err (NUL-terminated, truncated to errcap) when it is rejected. */

@@ -74,6 +74,9 @@ SIGNATURES = {
     "ola_set_hasher": (_int, [_vp, _int]),
     "ola_get_hasher": (_int, [_vp]),
     "ola_set_comm": (_int, [_vp, _int, _int, _vp, _vp, _vp]),
+    "ola_nccl_unique_id": (_int, [ctypes.c_char_p, _vp]),
+    "ola_set_comm_nccl": (_int, [_vp, ctypes.c_char_p, _int, _int, _vp]),
+    "ola_comm_bytes": (_u64, [_vp]),
     "ola_batch_free": (_int, [_vp, _vp]),
     "ola_batch_ncols": (_sz, [_vp]),
     "ola_batch_degree_log": (_u32, [_vp]),

@@ -13,6 +13,15 @@
 #include "stark.h"
 #include "verify.h"
 
+namespace ola {
+namespace nccl {
+void release(ola_ctx* ctx);  // nccl_comm.cu
+}
+namespace generation {
+void poseidon_trace(ola_ctx* ctx, const uint64_t* d_inputs, const uint64_t* d_filters, size_t nrows, uint32_t log_n, uint64_t* d_out);
+}
+}  // namespace ola
+
 namespace {
 
 template <typename F>
@@ -128,6 +137,7 @@ void ola_gpu_destroy(ola_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    ola::nccl::release(ctx);
     ola::ntt::free_twiddles(ctx);
     ola::set_alloc_stream(ctx->stream);
     if (ctx->scratch) ola::dev_free(ctx->scratch);

@@ -74,6 +74,8 @@ struct ola_ctx {
     ola_allgather_fn comm_allgather = nullptr;
     ola_allreduce_u64_fn comm_allreduce = nullptr;
     void* comm_user = nullptr;
+    void* nccl_state = nullptr;   // ola_set_comm_nccl: the library's own NCCL communicator (nccl_comm.cu)
+    uint64_t comm_bytes = 0;      // bytes this rank received through the communicator (ola_comm_bytes)
 };
 
 namespace ola {
@@ -111,10 +113,12 @@ inline void ensure_copy_stream(ola_ctx* ctx) {
 }
 inline void comm_allgather(ola_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank) {
     OLA_CHECK(ctx->comm_allgather != nullptr, OLA_ERR_INTERNAL, "no communicator");
+    ctx->comm_bytes += bytes_per_rank * (size_t)ctx->world;
     OLA_CHECK(ctx->comm_allgather(ctx->comm_user, send, recv, bytes_per_rank, (void*)ctx->stream) == 0, OLA_ERR_INTERNAL, "all-gather callback failed");
 }
 inline void comm_allreduce(ola_ctx* ctx, void* buf, size_t count) {
     OLA_CHECK(ctx->comm_allreduce != nullptr, OLA_ERR_INTERNAL, "no communicator");
+    ctx->comm_bytes += count * 8;
     OLA_CHECK(ctx->comm_allreduce(ctx->comm_user, buf, count, (void*)ctx->stream) == 0, OLA_ERR_INTERNAL, "all-reduce callback failed");
 }
 inline void check_launch(const char* what) {

@@ -9,4 +9,5 @@
 #include "fri.cu"
 #include "stark.cu"
 #include "generation.cu"
+#include "nccl_comm.cu"
 #include "api.cu"

@@ -827,6 +827,7 @@ std::vector<uint8_t> prove_all(ola_ctx* ctx, const std::vector<int>& table_ids, 
                 if (e) cudaEventDestroy(e);
         }
     } event_guard{uploaded};
+    try {  // from the first queued copy on: no copy may outlive the buffers released by unwinding
     if (prefetch) {
         ensure_copy_stream(ctx);
         cudaEvent_t allocated;
@@ -862,7 +863,7 @@ std::vector<uint8_t> prove_all(ola_ctx* ctx, const std::vector<int>& table_ids, 
             OLA_CUDA(cudaEventRecord(uploaded[i], ctx->copy_stream));
         }
     }
-    try {
+    {
         for (size_t oi = 0; oi < T; ++oi) {
             const size_t i = order[oi];
             const size_t n = (size_t)1 << log_ns[i], cnt = n * sys.tables[i].columns;
@@ -883,6 +884,7 @@ std::vector<uint8_t> prove_all(ola_ctx* ctx, const std::vector<int>& table_ids, 
             commits[i].reset(new BatchHolder());
             commits[i]->b = commit(ctx, d_vals[i]->p, sys.tables[i].columns, log_ns[i], false);
         }
+    }
     } catch (...) {
         if (prefetch) cudaStreamSynchronize(ctx->copy_stream);  // no copy may outlive the buffers released by unwinding
         throw;

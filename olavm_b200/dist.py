@@ -126,6 +126,35 @@ def set_comm_torch(ctx, group=None):
     return rank, world
 
 
+def set_comm(ctx, group=None, libnccl_path=None):
+    """Bind the library's collectives to ITS OWN NCCL communicator (ola_set_comm_nccl: libnccl is dlopened by the library,
+    the collectives are issued from C++ on the context's stream).  torch.distributed only carries the 128-byte
+    ncclUniqueId from rank 0 to the others.  OLA_COMM=torch selects the callback binding (set_comm_torch) instead."""
+    import os
+
+    import numpy as np
+
+    if os.environ.get("OLA_COMM", "nccl") == "torch":
+        return set_comm_torch(ctx, group)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    uid = np.zeros(128, dtype=np.uint8)
+    path = libnccl_path.encode() if libnccl_path else None
+    if rank == 0:
+        ctx.check(ctx._lib.ola_nccl_unique_id(path, uid.ctypes.data_as(ctypes.c_void_p)))
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", ctx.device) if backend == "nccl" else torch.device("cpu")
+    t = torch.from_numpy(uid.copy()).to(dev)
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    uid = t.cpu().numpy()
+    ctx.check(ctx._lib.ola_set_comm_nccl(ctx.handle, path, rank, world, uid.ctypes.data_as(ctypes.c_void_p)))
+    return rank, world
+
+
+def comm_bytes(ctx):
+    """Bytes this rank received through the library's communicator so far (ola_comm_bytes)."""
+    return int(ctx._lib.ola_comm_bytes(ctx.handle))
+
+
 class LocalComm:
     """In-process communicator for `world` host threads that each own a Context on the SAME GPU (test harness for the
     sharded prover on a one-GPU box): collectives go through host staging buffers and a threading.Barrier.

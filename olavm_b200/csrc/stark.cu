@@ -21,6 +21,8 @@
 #include "batch.h"
 #include "fri.h"
 #include "ntt.h"
+#include "tma.cuh"
+#include "verify.h"
 
 namespace ola {
 namespace stark {
@@ -62,7 +64,28 @@ struct DevPermInst {
 struct DevPermBatch {
     int inst_off, inst_cnt;
 };
+// The quotient kernel's view of the CTL section: one DevSide per lookup side of this table (a TableWithColumns,
+// cross_table_lookup.rs:173-194) with its two challenge instances.  GrandProductChallenge::combine is sum_q beta^q col_q +
+// gamma and a Column is sum_t coef_t trace[col_t] + const, so an instance's combination is ONE dot product over trace
+// columns: the host folds beta^q coef_t into per-term weights (w0 / w1 for the two challenges) and the constants into c0 / c1.
+struct DevTerm {
+    int col, pad_;
+    uint64_t w0, w1;
+};
+struct DevSide {
+    int term_off, term_cnt;  // into terms[]
+    int filt_off, filt_cnt;  // into fterms[] (w0 = coefficient); filt_cnt < 0: no filter (the filter is 1)
+    uint64_t c0, c1;         // sum_q beta_j^q const_q + gamma_j
+    uint64_t filt_const;
+    int z0, z1;              // Z columns of the two instances (index into zs, permutation Zs included); z1 < 0: none
+    int k0, k1;              // index of each instance's first-row constraint among the table's constraints (transition: + 1)
+    int filt_single, pad_;   // >= 0: the filter is exactly that trace column
+};
 struct DevTables {  // all arrays live in one device allocation
+    const DevSide* sides;
+    const DevTerm* terms;
+    const DevTerm* fterms;
+    int nsides, nterms, nfterms;
     const DevLc* lcs;
     const int* lc_col;
     const uint64_t* lc_coef;
@@ -202,7 +225,8 @@ struct QuotArgs {
     DevTables d;
     int num_perm_zs;
     uint64_t compress_challenge;  // Bitwise / Program only (canonical)
-    const uint64_t* apow;         // [2][2*nctl + 1]: alpha_j^k, weights of the CTL section's constraints
+    const uint64_t* weights;      // [K][2]: alpha_0^(K-1-k), alpha_1^(K-1-k) for the table's K constraints (AIR, permutation, CTL)
+    int nweights;                 // K
     // coset shard: this rank evaluates points [r_offset, r_offset + npoints) of the quotient domain; its LDE buffers
     // start at leaf r_offset (row r of the domain is local row r - r_offset); out[j][r - r_offset], j-stride out_stride
     size_t r_offset, npoints, out_stride;
@@ -214,12 +238,53 @@ __device__ __forceinline__ uint64_t pow_omega_fwd(const uint64_t* __restrict__ p
     return gl::mul(r, __ldg(pw + (E & 2047u)));
 }
 
+// Shared-memory image of what every thread of a CTA reads uniformly: the constraint weights and the CTL descriptors.
+// One elected thread stages it with 1-D bulk copies (TMA engine, tma.cuh) while the others compute their row addresses.
+struct QuotSmem {
+    static __host__ __device__ size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+    static __host__ __device__ size_t weights_off() { return 16; }  // [0,8): mbarrier
+    static __host__ __device__ size_t sides_off(int K) { return weights_off() + align16((size_t)K * 16); }
+    static __host__ __device__ size_t terms_off(int K, int nsides) { return sides_off(K) + align16((size_t)nsides * sizeof(DevSide)); }
+    static __host__ __device__ size_t fterms_off(int K, int nsides, int nterms) { return terms_off(K, nsides) + align16((size_t)nterms * sizeof(DevTerm)); }
+    static __host__ __device__ size_t bytes(int K, int nsides, int nterms, int nfterms) {
+        return fterms_off(K, nsides, nterms) + align16((size_t)nfterms * sizeof(DevTerm));
+    }
+};
+
 template <class Air, int MINB = 3>
 __global__ void __launch_bounds__(128, MINB) quotient_kernel(const QuotArgs a) {
-    const size_t r_raw = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r_raw >= a.npoints) return;
-    const size_t rg = r_raw + a.r_offset;  // index in the quotient domain (leaf order)
+    extern __shared__ __align__(16) unsigned char q_smem[];
+    const DevTables& d = a.d;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(q_smem);
+    const uint64_t* s_w = reinterpret_cast<const uint64_t*>(q_smem + QuotSmem::weights_off());
+    const DevSide* s_sides = reinterpret_cast<const DevSide*>(q_smem + QuotSmem::sides_off(a.nweights));
+    const DevTerm* s_terms = reinterpret_cast<const DevTerm*>(q_smem + QuotSmem::terms_off(a.nweights, d.nsides));
+    const DevTerm* s_fterms = reinterpret_cast<const DevTerm*>(q_smem + QuotSmem::fterms_off(a.nweights, d.nsides, d.nterms));
+    if (threadIdx.x == 0) {
+        tma::mbar_init(bar, 1);
+        tma::fence_barrier_init();
+        const uint32_t b_w = (uint32_t)QuotSmem::align16((size_t)a.nweights * 16), b_s = (uint32_t)QuotSmem::align16((size_t)d.nsides * sizeof(DevSide)),
+                       b_t = (uint32_t)QuotSmem::align16((size_t)d.nterms * sizeof(DevTerm)), b_f = (uint32_t)QuotSmem::align16((size_t)d.nfterms * sizeof(DevTerm));
+        tma::mbar_arrive_expect_tx(bar, b_w + b_s + b_t + b_f);
+        tma::bulk_g2s((void*)s_w, a.weights, b_w, bar);
+        if (b_s) tma::bulk_g2s((void*)s_sides, d.sides, b_s, bar);
+        if (b_t) tma::bulk_g2s((void*)s_terms, d.terms, b_t, bar);
+        if (b_f) tma::bulk_g2s((void*)s_fterms, d.fterms, b_f, bar);
+    }
+    // Row mapping.  Warp w of the launch handles the 32 rows whose natural indices are j = lane' * (n/32) + m for the block
+    // counter m = w mod (n/32): consecutive warps hold consecutive m, and the NEXT rows of block m are the rows of block
+    // m + 1 -- so a CTA's next-row loads are its neighbour warp's local-row loads (L1), and the CTA after it reuses the
+    // last block through L2.  In leaf order those 32 rows are the consecutive positions (bitrev(m) << 5 | lane).
+    const size_t r_lin = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = r_lin < a.npoints;
     const uint32_t nmask = (1u << a.log_n) - 1;
+    uint32_t pos_lin = (uint32_t)r_lin & nmask;
+    if (a.log_n > 5) {
+        const uint32_t m = pos_lin >> 5, lane = pos_lin & 31u;
+        pos_lin = (gl::bitrev32(m, a.log_n - 5) << 5) | lane;
+    }
+    const size_t r_raw = (r_lin & ~(size_t)nmask) | pos_lin;  // local row (leaf order) in this rank's buffers
+    const size_t rg = r_raw + a.r_offset;                      // index in the quotient domain (leaf order)
     const uint32_t coset = (uint32_t)(rg >> a.log_n), pos = (uint32_t)rg & nmask;
     const uint32_t j = gl::bitrev32(pos, a.log_n);
     const uint32_t pos_next = gl::bitrev32((j + 1) & nmask, a.log_n);
@@ -227,26 +292,27 @@ __global__ void __launch_bounds__(128, MINB) quotient_kernel(const QuotArgs a) {
     const size_t r = r_raw, r_next = (((size_t)coset << a.log_n) | pos_next) - a.r_offset;
     // natural LDE index k = bitrev_{log_n+3}(r) = j*8 + bitrev3(coset); x = 7 * omega_{8n}^k
     const uint32_t cb = gl::bitrev32(coset, 3);
-    const uint32_t k = (j << 3) | cb;
+    const uint32_t kk = (j << 3) | cb;
     const int lde_bits = a.log_n + 3;
-    const uint32_t E = lde_bits >= 32 ? k : (k << (32 - lde_bits));
+    const uint32_t E = lde_bits >= 32 ? kk : (kk << (32 - lde_bits));
     const uint64_t x = gl::mul(gl::GEN, pow_omega_fwd(a.pw, E));
     const uint32_t zi = cb >> (3 - a.qdb);  // (k / step) mod 2^qdb
     // L_0(x) = Z_H(x) / (n (x - 1)),  L_last(x) = Z_H(x) / (n (g x - 1))   (verifier.rs:380-396); x is never in H
     const uint64_t d0 = gl::mul(a.n_field, gl::sub(x, 1)), d1 = gl::mul(a.n_field, gl::sub(gl::mul(a.g, x), 1));
     const uint64_t inv01 = gl::inv(gl::mul(d0, d1));
+    tma::mbar_wait(bar, 0);
+    if (!active) return;
     Consumer yc;
-    yc.alpha0 = Fp(a.alpha0);
-    yc.alpha1 = Fp(a.alpha1);
-    yc.acc0 = Fp(0);
-    yc.acc1 = Fp(0);
+    yc.acc0.clear();
+    yc.acc1.clear();
+    yc.w = s_w;
+    yc.k = 0;
     yc.z_last = Fp(gl::sub(x, a.g_inv));
     yc.lagrange_first = Fp(gl::mul(a.zh[zi], gl::mul(inv01, d1)));
     yc.lagrange_last = Fp(gl::mul(a.zh[zi], gl::mul(inv01, d0)));
     const Row lv{a.trace_lde, a.L, r}, nv{a.trace_lde, a.L, r_next};
     Air::eval(lv, nv, yc, Fp(a.compress_challenge));
 
-    const DevTables& d = a.d;
     // eval_permutation_checks (permutation.rs:302-360)
     if (a.num_perm_zs > 0) {
         for (int i = 0; i < a.num_perm_zs; ++i) yc.constraint_first_row(Fp(a.zs_lde[(size_t)i * a.L + r]) - air::one());
@@ -267,52 +333,83 @@ __global__ void __launch_bounds__(128, MINB) quotient_kernel(const QuotArgs a) {
             yc.constraint(zn * rhs - zl * lhs);
         }
     }
-    // eval_cross_table_lookup_checks (cross_table_lookup.rs:380-419).  The consumer is Horner in alpha, so constraint
-    // k of this section (2i: first-row check of instance i, 2i+1: its transition check) carries weight
-    // alpha^(2 nctl - 1 - k); accumulating with explicit weights makes the order free, which lets the two instances
-    // of one lookup side (same columns and filter, the two challenge pairs) share every column evaluation.
-    if (d.nctl > 0) {
-        const int K = 2 * d.nctl;
-        const uint64_t* __restrict__ ap0 = a.apow;
-        const uint64_t* __restrict__ ap1 = a.apow + (K + 1);
-        Fp s0 = yc.acc0 * Fp(ap0[K]), s1 = yc.acc1 * Fp(ap1[K]);
-        for (int i = 0; i < d.nctl; ++i) {
-            const DevCtl c = d.ctls[i];
-            if (c.is_twin) continue;
-            const int j = c.twin;
-            const Fp lf = c.filter >= 0 ? eval_lc(d, c.filter, a.trace_lde, a.L, r) : air::one();
-            const Fp nf = c.filter >= 0 ? eval_lc(d, c.filter, a.trace_lde, a.L, r_next) : air::one();
-            const Fp b0(c.beta), b1(j >= 0 ? d.ctls[j].beta : 0);
-            Fp l0(0), n0(0), l1(0), n1(0);
-            for (int q = c.col_cnt - 1; q >= 0; --q) {  // GrandProductChallenge::combine, Horner from the last column
-                const Fp v = eval_lc(d, c.col_off + q, a.trace_lde, a.L, r), w = eval_lc(d, c.col_off + q, a.trace_lde, a.L, r_next);
-                l0 = l0 * b0 + v;
-                n0 = n0 * b0 + w;
-                if (j >= 0) {
-                    l1 = l1 * b1 + v;
-                    n1 = n1 * b1 + w;
-                }
-            }
-            const Fp one_lf = air::one() - lf, one_nf = air::one() - nf;
-            for (int h = 0; h < 2; ++h) {
-                const int inst = h == 0 ? i : j;
-                if (inst < 0) break;
-                const Fp lc = (h == 0 ? l0 : l1) + Fp(h == 0 ? c.gamma : d.ctls[j].gamma);
-                const Fp nc = (h == 0 ? n0 : n1) + Fp(h == 0 ? c.gamma : d.ctls[j].gamma);
-                const Fp local_z(a.zs_lde[(size_t)(a.num_perm_zs + inst) * a.L + r]), next_z(a.zs_lde[(size_t)(a.num_perm_zs + inst) * a.L + r_next]);
-                // select(filter, x) = filter * x + 1 - filter
-                const Fp c_first = (local_z - (lf * lc + one_lf)) * yc.lagrange_first;
-                const Fp c_trans = (next_z - local_z * (nf * nc + one_nf)) * yc.z_last;
-                const int w = K - 1 - 2 * inst;
-                s0 = s0 + c_first * Fp(ap0[w]) + c_trans * Fp(ap0[w - 1]);
-                s1 = s1 + c_first * Fp(ap1[w]) + c_trans * Fp(ap1[w - 1]);
-            }
+    // eval_cross_table_lookup_checks (cross_table_lookup.rs:380-419): per instance a first-row constraint
+    // (local_z - select(filter, combined)) and a transition constraint (next_z - local_z select(next filter, next
+    // combined)), at positions k and k + 1 of the consumer's sequence.  Because every constraint carries its explicit
+    // weight the order of evaluation is free: the two challenge instances of a side share every trace load, their
+    // combinations are dot products accumulated unreduced, and the transition constraints of all instances are summed
+    // (weighted) before the single multiplication by z_last.
+    air::Wide t0, t1;  // sum of weighted transition constraints, per alpha
+    t0.clear();
+    t1.clear();
+    const uint64_t* __restrict__ tr = a.trace_lde;
+    for (int s = 0; s < d.nsides; ++s) {
+        const DevSide sd = s_sides[s];
+        air::Wide l0, l1, n0, n1;
+        l0.clear();
+        l1.clear();
+        n0.clear();
+        n1.clear();
+#pragma unroll 2
+        for (int t = 0; t < sd.term_cnt; ++t) {
+            const DevTerm tm = s_terms[sd.term_off + t];
+            const uint64_t* col = tr + (size_t)tm.col * a.L;
+            const uint64_t v = __ldg(col + r), vn = __ldg(col + r_next);
+            l0.mac(v, tm.w0);
+            l1.mac(v, tm.w1);
+            n0.mac(vn, tm.w0);
+            n1.mac(vn, tm.w1);
         }
-        yc.acc0 = s0;
-        yc.acc1 = s1;
+        Fp lf(1), nf(1);
+        if (sd.filt_single >= 0) {
+            const uint64_t* col = tr + (size_t)sd.filt_single * a.L;
+            lf = Fp(__ldg(col + r));
+            nf = Fp(__ldg(col + r_next));
+        } else if (sd.filt_cnt >= 0) {
+            air::Wide fl, fn;
+            fl.clear();
+            fn.clear();
+            for (int t = 0; t < sd.filt_cnt; ++t) {
+                const DevTerm tm = s_fterms[sd.filt_off + t];
+                const uint64_t* col = tr + (size_t)tm.col * a.L;
+                fl.mac(__ldg(col + r), tm.w0);
+                fn.mac(__ldg(col + r_next), tm.w0);
+            }
+            lf = Fp(fl.reduce()) + Fp(sd.filt_const);
+            nf = Fp(fn.reduce()) + Fp(sd.filt_const);
+        }
+        const bool filtered = sd.filt_cnt >= 0;
+        const Fp one_lf = air::one() - lf, one_nf = air::one() - nf;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int z = h == 0 ? sd.z0 : sd.z1;
+            if (z < 0) break;
+            Fp lc = Fp((h == 0 ? l0 : l1).reduce()) + Fp(h == 0 ? sd.c0 : sd.c1);
+            Fp nc = Fp((h == 0 ? n0 : n1).reduce()) + Fp(h == 0 ? sd.c0 : sd.c1);
+            if (filtered) {  // select(filter, x) = filter * x + 1 - filter
+                lc = lf * lc + one_lf;
+                nc = nf * nc + one_nf;
+            }
+            const uint64_t* zcol = a.zs_lde + (size_t)z * a.L;
+            const Fp local_z(__ldg(zcol + r)), next_z(__ldg(zcol + r_next));
+            const Fp c_first = (local_z - lc) * yc.lagrange_first;
+            const Fp c_trans = next_z - local_z * nc;
+            const int k = h == 0 ? sd.k0 : sd.k1;
+            const ulonglong2 wf = *reinterpret_cast<const ulonglong2*>(s_w + 2 * k);
+            const ulonglong2 wt = *reinterpret_cast<const ulonglong2*>(s_w + 2 * k + 2);
+            yc.acc0.mac(c_first.v, wf.x);
+            yc.acc1.mac(c_first.v, wf.y);
+            t0.mac(c_trans.v, wt.x);
+            t1.mac(c_trans.v, wt.y);
+        }
     }
-    a.out[r] = gl::mul(yc.acc0.v, a.zh_inv[zi]);
-    a.out[a.out_stride + r] = gl::mul(yc.acc1.v, a.zh_inv[zi]);
+    Fp acc0(yc.acc0.reduce()), acc1(yc.acc1.reduce());
+    if (d.nsides > 0) {
+        acc0 = acc0 + Fp(t0.reduce()) * yc.z_last;
+        acc1 = acc1 + Fp(t1.reduce()) * yc.z_last;
+    }
+    a.out[r] = gl::mul(acc0.v, a.zh_inv[zi]);
+    a.out[a.out_stride + r] = gl::mul(acc1.v, a.zh_inv[zi]);
 }
 
 static void launch_quotient(ola_ctx* ctx, int table_id, QuotArgs a) {
@@ -322,6 +419,8 @@ static void launch_quotient(ola_ctx* ctx, int table_id, QuotArgs a) {
     // instruction stream both measured slower (profiles/quotient_r01h_summary.md)
     const int threads = 128;
     const unsigned blocks = (unsigned)((size + threads - 1) / threads);
+    const size_t smem = QuotSmem::bytes(a.nweights, a.d.nsides, a.d.nterms, a.d.nfterms);
+    OLA_CHECK(smem <= 48 * 1024, OLA_ERR_INTERNAL, "quotient descriptors exceed the default shared-memory window");
     Launch lz(ctx, "quotient");
     switch (table_id) {
         case T_CPU: {
@@ -329,28 +428,28 @@ static void launch_quotient(ola_ctx* ctx, int table_id, QuotArgs a) {
             // profiles/r01m_quotient_minb_sweep.txt (2^20 rows: 89.9 / 64.1 / 51.0 ms for 2 / 3 / 4)
             static const int minb = [] { const char* e = getenv("OLA_QUOT_MINB"); return e ? atoi(e) : 4; }();
             if (minb == 4)
-                quotient_kernel<air::Cpu, 4><<<blocks, threads, 0, ctx->stream>>>(a);
+                quotient_kernel<air::Cpu, 4><<<blocks, threads, smem, ctx->stream>>>(a);
             else if (minb == 5)
-                quotient_kernel<air::Cpu, 5><<<blocks, threads, 0, ctx->stream>>>(a);
+                quotient_kernel<air::Cpu, 5><<<blocks, threads, smem, ctx->stream>>>(a);
             else if (minb == 6)
-                quotient_kernel<air::Cpu, 6><<<blocks, threads, 0, ctx->stream>>>(a);
+                quotient_kernel<air::Cpu, 6><<<blocks, threads, smem, ctx->stream>>>(a);
             else if (minb == 2)
-                quotient_kernel<air::Cpu, 2><<<blocks, threads, 0, ctx->stream>>>(a);
+                quotient_kernel<air::Cpu, 2><<<blocks, threads, smem, ctx->stream>>>(a);
             else
-                quotient_kernel<air::Cpu, 3><<<blocks, threads, 0, ctx->stream>>>(a);
+                quotient_kernel<air::Cpu, 3><<<blocks, threads, smem, ctx->stream>>>(a);
             break;
         }
-        case T_MEMORY: quotient_kernel<air::Memory><<<blocks, threads, 0, ctx->stream>>>(a); break;
-        case T_CMP: quotient_kernel<air::Cmp><<<blocks, threads, 0, ctx->stream>>>(a); break;
-        case T_RANGECHECK: quotient_kernel<air::RangeCheck><<<blocks, threads, 0, ctx->stream>>>(a); break;
-        case T_BITWISE: quotient_kernel<air::Bitwise><<<blocks, threads, 0, ctx->stream>>>(a); break;
-        case T_POSEIDON: quotient_kernel<air::Poseidon><<<blocks, threads, 0, ctx->stream>>>(a); break;
-        case T_POSEIDON_CHUNK: quotient_kernel<air::PoseidonChunk><<<blocks, threads, 0, ctx->stream>>>(a); break;
-        case T_STORAGE: quotient_kernel<air::StorageAccess><<<blocks, threads, 0, ctx->stream>>>(a); break;
-        case T_TAPE: quotient_kernel<air::Tape><<<blocks, threads, 0, ctx->stream>>>(a); break;
-        case T_SCCALL: quotient_kernel<air::SCCall><<<blocks, threads, 0, ctx->stream>>>(a); break;
-        case T_PROGRAM: quotient_kernel<air::Program><<<blocks, threads, 0, ctx->stream>>>(a); break;
-        case T_PROG_CHUNK: quotient_kernel<air::ProgChunk><<<blocks, threads, 0, ctx->stream>>>(a); break;
+        case T_MEMORY: quotient_kernel<air::Memory><<<blocks, threads, smem, ctx->stream>>>(a); break;
+        case T_CMP: quotient_kernel<air::Cmp><<<blocks, threads, smem, ctx->stream>>>(a); break;
+        case T_RANGECHECK: quotient_kernel<air::RangeCheck><<<blocks, threads, smem, ctx->stream>>>(a); break;
+        case T_BITWISE: quotient_kernel<air::Bitwise><<<blocks, threads, smem, ctx->stream>>>(a); break;
+        case T_POSEIDON: quotient_kernel<air::Poseidon><<<blocks, threads, smem, ctx->stream>>>(a); break;
+        case T_POSEIDON_CHUNK: quotient_kernel<air::PoseidonChunk><<<blocks, threads, smem, ctx->stream>>>(a); break;
+        case T_STORAGE: quotient_kernel<air::StorageAccess><<<blocks, threads, smem, ctx->stream>>>(a); break;
+        case T_TAPE: quotient_kernel<air::Tape><<<blocks, threads, smem, ctx->stream>>>(a); break;
+        case T_SCCALL: quotient_kernel<air::SCCall><<<blocks, threads, smem, ctx->stream>>>(a); break;
+        case T_PROGRAM: quotient_kernel<air::Program><<<blocks, threads, smem, ctx->stream>>>(a); break;
+        case T_PROG_CHUNK: quotient_kernel<air::ProgChunk><<<blocks, threads, smem, ctx->stream>>>(a); break;
         default: throw Error(OLA_ERR_INVALID_ARG, "no constraint kernel for table " + std::to_string(table_id));
     }
 }
@@ -491,6 +590,59 @@ struct DescBuilder {
         ctl_sides.push_back(ci.twc);
         ctls.push_back(c);
     }
+    // the quotient kernel's flattened CTL section (DevSide / DevTerm); base_k = number of constraints in front of it
+    std::vector<DevSide> sides;
+    std::vector<DevTerm> terms, fterms;
+    void build_sides(int base_k, int num_perm_zs) {
+        for (size_t i = 0; i < ctls.size(); ++i) {
+            const DevCtl& c = ctls[i];
+            if (c.is_twin) continue;
+            const int j = c.twin;
+            DevSide sd;
+            memset(&sd, 0, sizeof(sd));
+            sd.term_off = (int)terms.size();
+            F b0 = 1, b1 = 1, c0 = 0, c1 = 0;
+            for (int q = 0; q < c.col_cnt; ++q) {
+                const DevLc& lc = lcs[c.col_off + q];
+                for (int t = 0; t < lc.cnt; ++t) {
+                    DevTerm tm;
+                    tm.col = lc_col[lc.off + t];
+                    tm.pad_ = 0;
+                    tm.w0 = gl::mul(b0, lc_coef[lc.off + t]);
+                    tm.w1 = gl::mul(b1, lc_coef[lc.off + t]);
+                    terms.push_back(tm);
+                }
+                c0 = gl::add(c0, gl::mul(b0, lc.constant));
+                c1 = gl::add(c1, gl::mul(b1, lc.constant));
+                b0 = gl::mul(b0, c.beta);
+                if (j >= 0) b1 = gl::mul(b1, ctls[j].beta);
+            }
+            sd.term_cnt = (int)terms.size() - sd.term_off;
+            sd.c0 = gl::add(c0, c.gamma);
+            sd.c1 = j >= 0 ? gl::add(c1, ctls[j].gamma) : 0;
+            sd.filt_single = -1;
+            if (c.filter >= 0) {
+                const DevLc& lc = lcs[c.filter];
+                if (lc.single >= 0) {
+                    sd.filt_single = lc.single;
+                    sd.filt_off = 0;
+                    sd.filt_cnt = 0;
+                } else {
+                    sd.filt_off = (int)fterms.size();
+                    for (int t = 0; t < lc.cnt; ++t) fterms.push_back(DevTerm{lc_col[lc.off + t], 0, lc_coef[lc.off + t], 0});
+                    sd.filt_cnt = lc.cnt;
+                    sd.filt_const = lc.constant;
+                }
+            } else {
+                sd.filt_cnt = -1;
+            }
+            sd.z0 = num_perm_zs + (int)i;
+            sd.z1 = j >= 0 ? num_perm_zs + j : -1;
+            sd.k0 = base_k + 2 * (int)i;
+            sd.k1 = j >= 0 ? base_k + 2 * j : -1;
+            sides.push_back(sd);
+        }
+    }
 };
 struct DevDesc {
     uint64_t* mem = nullptr;
@@ -499,19 +651,28 @@ struct DevDesc {
         if (mem) ola::dev_free(mem);
     }
     void upload(ola_ctx* ctx, const DescBuilder& b) {
-        auto a8 = [](size_t bytes) { return (bytes + 7) / 8; };
+        // every array starts on a 16-byte boundary and is followed by slack: the quotient kernel stages the side / term
+        // arrays with bulk copies whose size is rounded up to 16 bytes
+        auto a8 = [](size_t bytes) { return ((bytes + 15) / 16) * 2; };
         size_t o_lcs = 0, o_col = o_lcs + a8(b.lcs.size() * sizeof(DevLc)), o_coef = o_col + a8(b.lc_col.size() * 4),
-               o_ctl = o_coef + b.lc_coef.size(), o_inst = o_ctl + a8(b.ctls.size() * sizeof(DevCtl)),
+               o_ctl = o_coef + a8(b.lc_coef.size() * 8), o_inst = o_ctl + a8(b.ctls.size() * sizeof(DevCtl)),
                o_bat = o_inst + a8(b.insts.size() * sizeof(DevPermInst)), o_pair = o_bat + a8(b.batches.size() * sizeof(DevPermBatch)),
-               total = o_pair + a8(b.pairs.size() * 4) + 1;
+               o_side = o_pair + a8(b.pairs.size() * 4), o_term = o_side + a8(b.sides.size() * sizeof(DevSide)),
+               o_fterm = o_term + a8(b.terms.size() * sizeof(DevTerm)), total = o_fterm + a8(b.fterms.size() * sizeof(DevTerm)) + 2;
         std::vector<uint64_t> h(total, 0);
-        memcpy(&h[o_lcs], b.lcs.data(), b.lcs.size() * sizeof(DevLc));
-        memcpy(&h[o_col], b.lc_col.data(), b.lc_col.size() * 4);
-        memcpy(&h[o_coef], b.lc_coef.data(), b.lc_coef.size() * 8);
-        memcpy(&h[o_ctl], b.ctls.data(), b.ctls.size() * sizeof(DevCtl));
-        memcpy(&h[o_inst], b.insts.data(), b.insts.size() * sizeof(DevPermInst));
-        memcpy(&h[o_bat], b.batches.data(), b.batches.size() * sizeof(DevPermBatch));
-        memcpy(&h[o_pair], b.pairs.data(), b.pairs.size() * 4);
+        auto put = [&](size_t off, const void* src, size_t bytes) {
+            if (bytes) memcpy(&h[off], src, bytes);
+        };
+        put(o_lcs, b.lcs.data(), b.lcs.size() * sizeof(DevLc));
+        put(o_col, b.lc_col.data(), b.lc_col.size() * 4);
+        put(o_coef, b.lc_coef.data(), b.lc_coef.size() * 8);
+        put(o_ctl, b.ctls.data(), b.ctls.size() * sizeof(DevCtl));
+        put(o_inst, b.insts.data(), b.insts.size() * sizeof(DevPermInst));
+        put(o_bat, b.batches.data(), b.batches.size() * sizeof(DevPermBatch));
+        put(o_pair, b.pairs.data(), b.pairs.size() * 4);
+        put(o_side, b.sides.data(), b.sides.size() * sizeof(DevSide));
+        put(o_term, b.terms.data(), b.terms.size() * sizeof(DevTerm));
+        put(o_fterm, b.fterms.data(), b.fterms.size() * sizeof(DevTerm));
         dev_alloc(&mem, total);
         OLA_CUDA(cudaMemcpyAsync(mem, h.data(), total * 8, cudaMemcpyHostToDevice, ctx->stream));
         OLA_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -524,6 +685,12 @@ struct DevDesc {
         t.perm_batches = (const DevPermBatch*)(mem + o_bat);
         t.perm_pairs = (const int*)(mem + o_pair);
         t.nperm_batches = (int)b.batches.size();
+        t.sides = (const DevSide*)(mem + o_side);
+        t.terms = (const DevTerm*)(mem + o_term);
+        t.fterms = (const DevTerm*)(mem + o_fterm);
+        t.nsides = (int)b.sides.size();
+        t.nterms = (int)b.terms.size();
+        t.nfterms = (int)b.fterms.size();
     }
 };
 
@@ -631,6 +798,11 @@ static StarkProof prove_single_table(ola_ctx* ctx, const TableInfo& t, const Con
     }
     for (auto& ci : ctl) db.add_ctl(ci);
     const size_t num_perm_zs = db.batches.size();
+    // the table's constraints in consumer order: the AIR's, then per permutation Z a first-row check and per batch a
+    // transition check, then two per CTL instance (vanishing_poly.rs:20-47)
+    const int k_air = verify::air_constraint_count(t);
+    const int k_total = k_air + 2 * (int)num_perm_zs + 2 * (int)ctl.size();
+    db.build_sides(k_air + 2 * (int)num_perm_zs, (int)num_perm_zs);
     const size_t nzs = num_perm_zs + ctl.size();
     OLA_CHECK(nzs > 0, OLA_ERR_INVALID_ARG, "No CTL?");
     DevDesc desc;
@@ -709,23 +881,23 @@ static StarkProof prove_single_table(ola_ctx* ctx, const TableInfo& t, const Con
         a.d = desc.t;
         a.num_perm_zs = (int)num_perm_zs;
         a.compress_challenge = t.compress_challenge;
-        // alpha_j^k, k = 0 .. 2*nctl: weights of the cross-table-lookup section (see quotient_kernel)
-        const size_t K1 = 2 * (size_t)desc.t.nctl + 1;
-        std::vector<uint64_t> h_apow(2 * K1);
+        // weights of the consumer's Horner accumulation: constraint k of K carries alpha_j^(K-1-k)
+        std::vector<uint64_t> h_w(2 * (size_t)k_total + 2, 0);
         for (int j = 0; j < 2; ++j) {
             const F al = j == 0 ? alpha0 : alpha1;
             F pw = 1;
-            for (size_t k = 0; k < K1; ++k) {
-                h_apow[j * K1 + k] = pw;
+            for (int k = k_total - 1; k >= 0; --k) {
+                h_w[2 * (size_t)k + j] = pw;
                 pw = gl::mul(pw, al);
             }
         }
-        DevBuf d_apow(2 * K1);
-        OLA_CUDA(cudaMemcpyAsync(d_apow.p, h_apow.data(), h_apow.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-        a.apow = d_apow.p;
+        DevBuf d_w(h_w.size());
+        OLA_CUDA(cudaMemcpyAsync(d_w.p, h_w.data(), h_w.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        a.weights = d_w.p;
+        a.nweights = k_total;
         launch_quotient(ctx, t.id, a);
         check_launch("quotient_kernel");
-        OLA_CUDA(cudaStreamSynchronize(ctx->stream));  // h_apow / d_apow go out of scope
+        OLA_CUDA(cudaStreamSynchronize(ctx->stream));  // h_w / d_w go out of scope
     }
     if (ctx->world > 1)
         for (int j = 0; j < 2; ++j) comm_allgather(ctx, d_qsend.p + (size_t)j * per * n, d_q.p + (size_t)j * qstride, (size_t)per * n * 8);

@@ -125,12 +125,13 @@ namespace stark {
 namespace verify {
 
 // the table's eval_packed_generic at (local, next) over the extension
-inline void eval_table(const TableInfo& t, const XRow& lv, const XRow& nv, XConsumer& yc) {
+template <class YC>
+inline void eval_table_t(const TableInfo& t, const XRow& lv, const XRow& nv, YC& yc) {
     const XE beta(t.compress_challenge);
     switch (t.id) {
-        case T_CPU: air::cpu::eval<XE, XRow, XConsumer>(lv, nv, yc); break;
-        case T_MEMORY: air::mem::eval<XE, XRow, XConsumer>(lv, nv, yc); break;
-        case T_BITWISE: air::bitwise::eval<XE, XRow, XConsumer>(lv, nv, yc, beta); break;
+        case T_CPU: air::cpu::eval<XE, XRow, YC>(lv, nv, yc); break;
+        case T_MEMORY: air::mem::eval<XE, XRow, YC>(lv, nv, yc); break;
+        case T_BITWISE: air::bitwise::eval<XE, XRow, YC>(lv, nv, yc, beta); break;
         case T_CMP: {  // cmp_stark.rs:21-45
             const XE one((F)1), op0 = lv[0], op1 = lv[1], gte = lv[2], abs_diff = lv[3], abs_diff_inv = lv[4];
             yc.constraint(gte * (one - gte));
@@ -142,19 +143,36 @@ inline void eval_table(const TableInfo& t, const XRow& lv, const XRow& nv, XCons
         case T_RANGECHECK: {  // rangecheck_stark.rs:27-67
             const XE val = lv[4], limb_lo = lv[5], limb_hi = lv[6];
             yc.constraint(val - (limb_lo + limb_hi * XE((F)(1 << 16))));
-            air::eval_lookups_t<XE, XRow, XConsumer>(lv, nv, yc, 7, 10);
-            air::eval_lookups_t<XE, XRow, XConsumer>(lv, nv, yc, 8, 11);
+            air::eval_lookups_t<XE, XRow, YC>(lv, nv, yc, 7, 10);
+            air::eval_lookups_t<XE, XRow, YC>(lv, nv, yc, 8, 11);
             break;
         }
-        case T_POSEIDON: air::psdn::eval<XE, XRow, XConsumer, HostPoseidonParams>(lv, nv, yc); break;
-        case T_POSEIDON_CHUNK: air::psdn_chunk::eval<XE, XRow, XConsumer>(lv, nv, yc); break;
-        case T_STORAGE: air::storage::eval<XE, XRow, XConsumer>(lv, nv, yc); break;
-        case T_TAPE: air::tape::eval<XE, XRow, XConsumer>(lv, nv, yc); break;
-        case T_SCCALL: air::sccall::eval<XE, XRow, XConsumer>(lv, nv, yc); break;
-        case T_PROGRAM: air::program::eval<XE, XRow, XConsumer>(lv, nv, yc, beta); break;
-        case T_PROG_CHUNK: air::prog_chunk::eval<XE, XRow, XConsumer>(lv, nv, yc); break;
+        case T_POSEIDON: air::psdn::eval<XE, XRow, YC, HostPoseidonParams>(lv, nv, yc); break;
+        case T_POSEIDON_CHUNK: air::psdn_chunk::eval<XE, XRow, YC>(lv, nv, yc); break;
+        case T_STORAGE: air::storage::eval<XE, XRow, YC>(lv, nv, yc); break;
+        case T_TAPE: air::tape::eval<XE, XRow, YC>(lv, nv, yc); break;
+        case T_SCCALL: air::sccall::eval<XE, XRow, YC>(lv, nv, yc); break;
+        case T_PROGRAM: air::program::eval<XE, XRow, YC>(lv, nv, yc, beta); break;
+        case T_PROG_CHUNK: air::prog_chunk::eval<XE, XRow, YC>(lv, nv, yc); break;
         default: throw Error(OLA_ERR_INVALID_ARG, "unknown table id");
     }
+}
+
+inline void eval_table(const TableInfo& t, const XRow& lv, const XRow& nv, XConsumer& yc) { eval_table_t<XConsumer>(t, lv, nv, yc); }
+// number of constraints the table's eval_packed_generic emits (independent of the row: no constraint is conditional)
+struct CountingConsumer {
+    int n = 0;
+    void constraint(XE) { ++n; }
+    void constraint_transition(XE) { ++n; }
+    void constraint_first_row(XE) { ++n; }
+    void constraint_last_row(XE) { ++n; }
+};
+inline int air_constraint_count(const TableInfo& t) {
+    std::vector<XE> zeros((size_t)t.columns, XE((F)0));
+    XRow row{zeros.data()};
+    CountingConsumer cc;
+    eval_table_t<CountingConsumer>(t, row, row, cc);
+    return cc.n;
 }
 
 // C::Hasher the proof under verification was made with (set by verify_all for its duration; one per host thread)

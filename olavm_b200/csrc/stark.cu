@@ -69,7 +69,7 @@ struct DevPermBatch {
 // gamma and a Column is sum_t coef_t trace[col_t] + const, so an instance's combination is ONE dot product over trace
 // columns: the host folds beta^q coef_t into per-term weights (w0 / w1 for the two challenges) and the constants into c0 / c1.
 struct DevTerm {
-    int col, pad_;
+    uint64_t off;  // byte offset of the trace column inside the LDE buffer (column * column stride * 8)
     uint64_t w0, w1;
 };
 struct DevSide {
@@ -305,6 +305,8 @@ __global__ void __launch_bounds__(128, MINB) quotient_kernel(const QuotArgs a) {
     Consumer yc;
     yc.acc0.clear();
     yc.acc1.clear();
+    yc.tr0.clear();
+    yc.tr1.clear();
     yc.w = s_w;
     yc.k = 0;
     yc.z_last = Fp(gl::sub(x, a.g_inv));
@@ -339,10 +341,8 @@ __global__ void __launch_bounds__(128, MINB) quotient_kernel(const QuotArgs a) {
     // weight the order of evaluation is free: the two challenge instances of a side share every trace load, their
     // combinations are dot products accumulated unreduced, and the transition constraints of all instances are summed
     // (weighted) before the single multiplication by z_last.
-    air::Wide t0, t1;  // sum of weighted transition constraints, per alpha
-    t0.clear();
-    t1.clear();
-    const uint64_t* __restrict__ tr = a.trace_lde;
+    const char* __restrict__ tr_r = reinterpret_cast<const char*>(a.trace_lde + r);
+    const char* __restrict__ tr_n = reinterpret_cast<const char*>(a.trace_lde + r_next);
     for (int s = 0; s < d.nsides; ++s) {
         const DevSide sd = s_sides[s];
         air::Wide l0, l1, n0, n1;
@@ -353,8 +353,7 @@ __global__ void __launch_bounds__(128, MINB) quotient_kernel(const QuotArgs a) {
 #pragma unroll 2
         for (int t = 0; t < sd.term_cnt; ++t) {
             const DevTerm tm = s_terms[sd.term_off + t];
-            const uint64_t* col = tr + (size_t)tm.col * a.L;
-            const uint64_t v = __ldg(col + r), vn = __ldg(col + r_next);
+            const uint64_t v = __ldg(reinterpret_cast<const uint64_t*>(tr_r + tm.off)), vn = __ldg(reinterpret_cast<const uint64_t*>(tr_n + tm.off));
             l0.mac(v, tm.w0);
             l1.mac(v, tm.w1);
             n0.mac(vn, tm.w0);
@@ -362,7 +361,7 @@ __global__ void __launch_bounds__(128, MINB) quotient_kernel(const QuotArgs a) {
         }
         Fp lf(1), nf(1);
         if (sd.filt_single >= 0) {
-            const uint64_t* col = tr + (size_t)sd.filt_single * a.L;
+            const uint64_t* col = a.trace_lde + (size_t)sd.filt_single * a.L;
             lf = Fp(__ldg(col + r));
             nf = Fp(__ldg(col + r_next));
         } else if (sd.filt_cnt >= 0) {
@@ -371,9 +370,8 @@ __global__ void __launch_bounds__(128, MINB) quotient_kernel(const QuotArgs a) {
             fn.clear();
             for (int t = 0; t < sd.filt_cnt; ++t) {
                 const DevTerm tm = s_fterms[sd.filt_off + t];
-                const uint64_t* col = tr + (size_t)tm.col * a.L;
-                fl.mac(__ldg(col + r), tm.w0);
-                fn.mac(__ldg(col + r_next), tm.w0);
+                fl.mac(__ldg(reinterpret_cast<const uint64_t*>(tr_r + tm.off)), tm.w0);
+                fn.mac(__ldg(reinterpret_cast<const uint64_t*>(tr_n + tm.off)), tm.w0);
             }
             lf = Fp(fl.reduce()) + Fp(sd.filt_const);
             nf = Fp(fn.reduce()) + Fp(sd.filt_const);
@@ -399,15 +397,12 @@ __global__ void __launch_bounds__(128, MINB) quotient_kernel(const QuotArgs a) {
             const ulonglong2 wt = *reinterpret_cast<const ulonglong2*>(s_w + 2 * k + 2);
             yc.acc0.mac(c_first.v, wf.x);
             yc.acc1.mac(c_first.v, wf.y);
-            t0.mac(c_trans.v, wt.x);
-            t1.mac(c_trans.v, wt.y);
+            yc.tr0.mac(c_trans.v, wt.x);
+            yc.tr1.mac(c_trans.v, wt.y);
         }
     }
-    Fp acc0(yc.acc0.reduce()), acc1(yc.acc1.reduce());
-    if (d.nsides > 0) {
-        acc0 = acc0 + Fp(t0.reduce()) * yc.z_last;
-        acc1 = acc1 + Fp(t1.reduce()) * yc.z_last;
-    }
+    Fp acc0, acc1;
+    yc.finish(acc0, acc1);
     a.out[r] = gl::mul(acc0.v, a.zh_inv[zi]);
     a.out[a.out_stride + r] = gl::mul(acc1.v, a.zh_inv[zi]);
 }
@@ -593,7 +588,7 @@ struct DescBuilder {
     // the quotient kernel's flattened CTL section (DevSide / DevTerm); base_k = number of constraints in front of it
     std::vector<DevSide> sides;
     std::vector<DevTerm> terms, fterms;
-    void build_sides(int base_k, int num_perm_zs) {
+    void build_sides(int base_k, int num_perm_zs, uint64_t col_stride_bytes) {
         for (size_t i = 0; i < ctls.size(); ++i) {
             const DevCtl& c = ctls[i];
             if (c.is_twin) continue;
@@ -606,8 +601,7 @@ struct DescBuilder {
                 const DevLc& lc = lcs[c.col_off + q];
                 for (int t = 0; t < lc.cnt; ++t) {
                     DevTerm tm;
-                    tm.col = lc_col[lc.off + t];
-                    tm.pad_ = 0;
+                    tm.off = (uint64_t)lc_col[lc.off + t] * col_stride_bytes;
                     tm.w0 = gl::mul(b0, lc_coef[lc.off + t]);
                     tm.w1 = gl::mul(b1, lc_coef[lc.off + t]);
                     terms.push_back(tm);
@@ -629,7 +623,7 @@ struct DescBuilder {
                     sd.filt_cnt = 0;
                 } else {
                     sd.filt_off = (int)fterms.size();
-                    for (int t = 0; t < lc.cnt; ++t) fterms.push_back(DevTerm{lc_col[lc.off + t], 0, lc_coef[lc.off + t], 0});
+                    for (int t = 0; t < lc.cnt; ++t) fterms.push_back(DevTerm{(uint64_t)lc_col[lc.off + t] * col_stride_bytes, lc_coef[lc.off + t], 0});
                     sd.filt_cnt = lc.cnt;
                     sd.filt_const = lc.constant;
                 }
@@ -802,7 +796,7 @@ static StarkProof prove_single_table(ola_ctx* ctx, const TableInfo& t, const Con
     // transition check, then two per CTL instance (vanishing_poly.rs:20-47)
     const int k_air = verify::air_constraint_count(t);
     const int k_total = k_air + 2 * (int)num_perm_zs + 2 * (int)ctl.size();
-    db.build_sides(k_air + 2 * (int)num_perm_zs, (int)num_perm_zs);
+    db.build_sides(k_air + 2 * (int)num_perm_zs, (int)num_perm_zs, ((uint64_t)8 << trace_commit->leaf_bits()));
     const size_t nzs = num_perm_zs + ctl.size();
     OLA_CHECK(nzs > 0, OLA_ERR_INVALID_ARG, "No CTL?");
     DevDesc desc;

@@ -302,6 +302,107 @@ def coset_shard_commit(ctx, torch, dist, odist, world, rank, device, stream, log
             "cap_word0": int(cap0[0, 0])}
 
 
+def merkle_commit_config4(ctx, torch, dist, odist, world, rank, device, stream, log_l=24, ncols=64, reps=2):
+    """BASELINE configs[3]: Merkle commit (MerkleTree::new_v2, cap height 4) of 2^24 leaves x 64 columns resident in HBM,
+    under Poseidon and BLAKE3; at N > 1 the leaves are sharded by leaf range = LDE cosets = whole cap subtrees and the cap is
+    assembled by one all-gather.  Times are the hashing kernels' (leaf sponge + level reduction), max over ranks; the
+    transform that produces the leaves is not part of this config."""
+    import olavm_b200
+    from olavm_b200.pcs import PolynomialBatch
+
+    log_n = log_l - RATE_BITS
+    rng = np.random.Generator(np.random.PCG64(4))
+    vals = rng.integers(0, 0xFFFFFFFF00000001, size=(ncols, 1 << log_n), dtype=np.uint64)
+    d_vals = ctx.upload(vals)
+    lo, hi = odist.coset_range(RATE_BITS, rank, world)
+    L = 1 << log_l
+    out = {"config": f"Merkle commit of 2^{log_l} leaves x {ncols} columns (BASELINE configs[3])", "leaves_per_gpu": L // world,
+           "parallelism": f"leaf-range (coset) shard x{world}, cap all-gather"}
+    for name, hid, leaf_key, level_key in (("poseidon", olavm_b200.POSEIDON, "poseidon_leaves", "merkle_level"),
+                                           ("blake3", olavm_b200.BLAKE3, "blake3_leaves", "blake3_merkle_level")):
+        ctx.hasher = hid
+        try:
+            b = PolynomialBatch._commit(ctx, d_vals, False, RATE_BITS, 4, on_device=True, ncols=ncols, degree_log=log_n, coset_first=lo, coset_count=hi - lo)
+            b.free()
+            ctx.sync()
+            if world > 1:
+                dist.barrier()
+            ctx.profile_begin()
+            for _ in range(reps):
+                b = PolynomialBatch._commit(ctx, d_vals, False, RATE_BITS, 4, on_device=True, ncols=ncols, degree_log=log_n, coset_first=lo, coset_count=hi - lo)
+                if world > 1:
+                    with torch.cuda.stream(stream):
+                        odist.allgather_cap(b.merkle_cap.hashes.view(np.int64), RATE_BITS, 4, device=device)
+                b.free()
+            prof = ctx.profile_end()
+            leaf_ms = odist.max_over_ranks(prof[leaf_key]["ms"] / reps, device=device)
+            level_ms = odist.max_over_ranks(prof[level_key]["ms"] / reps, device=device)
+            calls = L * ((ncols + 7) // 8) + (L - 16)  # Poseidon permutations (BLAKE3: compressions, one chunk per leaf)
+            total_s = (leaf_ms + level_ms) * 1e-3
+            out[name] = {"leaf_ms": leaf_ms, "levels_ms": level_ms, "leaf_hashes_per_s": L / (leaf_ms * 1e-3), "hash_calls_per_s": calls / total_s,
+                         "algorithmic_GBps": ((8 * ncols + 32) * L + 96 * (L - 16)) / total_s / 1e9}
+        finally:
+            ctx.hasher = olavm_b200.POSEIDON
+    # roofline note: the Poseidon commit is bound by the integer-multiply pipe (DESIGN.md section 3.2); the model ceiling is
+    # 1.09e9 permutations/s per GPU (34.1k fmaheavy cycles per warp-permutation)
+    if "poseidon" in out:
+        out["poseidon"]["int_pipe_ceiling_perms_per_s"] = 1.09e9 * world
+        out["poseidon"]["frac_of_int_pipe_ceiling"] = out["poseidon"]["hash_calls_per_s"] / (1.09e9 * world)
+    ctx.free(d_vals)
+    return out
+
+
+def poseidon_table_config5(ctx, torch, dist, odist, world, rank, device, log_n):
+    """BASELINE configs[4] stand-in (the reference has no sha256 builtin: SURVEY.md 8d): the widest builtin table, PoseidonStark
+    (134 columns, constraint degree 7), with 2^log_n rows generated ON the device (ola_generate_poseidon_trace) and proven
+    coset-sharded over the ranks from device-resident traces; the cap of every commitment is assembled by an NCCL
+    all-gather.  2^24 rows need 144 GB of LDE: they fit from 2 GPUs up (72 GB each); one GPU runs 2^23."""
+    import hashlib
+
+    import olavm_b200
+
+    n = 1 << log_n
+    rng = np.random.Generator(np.random.PCG64(5))
+    block = rng.integers(0, 0xFFFFFFFF00000001, size=(1 << 16, 12), dtype=np.uint64)
+    block[:, 8:12] = 0
+    inputs = np.ascontiguousarray(np.tile(block, (n >> 16, 1)) if log_n >= 16 else block[:n])
+    d_in = ctx.upload(inputs)
+    del inputs
+    d_trace = ctx.alloc(134 * n)
+    ctx.sync()
+    t0 = time.perf_counter()
+    ctx.check(ctx._lib.ola_generate_poseidon_trace(ctx.handle, d_in, None, n, log_n, d_trace, 1))
+    ctx.sync()
+    gen_s = time.perf_counter() - t0
+    ctx.free(d_in)
+
+    def prove():
+        return olavm_b200.prove_with_device_traces(ctx, [5], [d_trace], [log_n])
+
+    def sync_all():
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+
+    prove()
+    sync_all()
+    runs = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        proof = prove()
+        dt_i = time.perf_counter() - t0
+        sync_all()
+        runs.append(odist.max_over_ranks(dt_i, device=device) if world > 1 else dt_i)
+    ctx.free(d_trace)
+    if rank != 0:
+        return None
+    ok, why = olavm_b200.verify_proof([5], proof)
+    dt = min(runs)
+    return {"config": f"PoseidonStark table, 2^{log_n} rows x 134 columns, generated on the device, coset-sharded prove x{world} (BASELINE configs[4] stand-in)",
+            "log_n": log_n, "seconds": dt, "seconds_runs": runs, "rows_per_s": n / dt, "generation_seconds": gen_s, "lde_bytes_per_gpu": 134 * n * 8 * 8 // world,
+            "proof_bytes": len(proof), "proof_sha256_16": hashlib.sha256(proof).hexdigest()[:16], "verified_by_ola_verify": bool(ok), "verify_error": why if not ok else ""}
+
+
 def host_threads():
     """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm uses all host cores (set before libgomp loads)."""
     if "TORCHELASTIC_RUN_ID" in os.environ or os.environ.get("OMP_NUM_THREADS") == "1":
@@ -348,6 +449,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--merkle-log-l", type=int, default=24, help="BASELINE configs[3]: Merkle commit of 2^k leaves x 64 columns (0 = skip)")
+    ap.add_argument("--poseidon-table-log-n", type=int, default=0,
+                    help="BASELINE configs[4] stand-in: prove a 2^k-row PoseidonStark table (0 = 24 from 2 GPUs up, 23 on one; -1 = skip)")
     ap.add_argument("--cpu-prove-log-n", type=int, default=18, help="CPU-table rows (log2) of the oracle-port proof sample")
     ap.add_argument("--prove-log-n", type=int, default=22, help="also time one 12-table proof whose CPU table has 2^k rows (0 = skip)")
     args = ap.parse_args()
@@ -485,6 +589,18 @@ def main():
             extra["strong_scaling"] = {"metric": f"seconds per 12-table proof, fib-loop program, 2^{args.prove_log_n}-row CPU table (BASELINE configs[2]/[4])",
                                        "n_gpus": world, "seconds": pa["seconds"], "proof_sha256_16": pa["proof_sha256_16"], "verified": pa.get("verified"),
                                        "comm_bytes_rank0": pa.get("comm_bytes_rank0", 0), "higher_is_better": False}
+    dev = torch.device("cuda", local_rank)
+    if args.merkle_log_l:
+        try:
+            extra["merkle_commit"] = merkle_commit_config4(ctx, torch, dist, odist, world, rank, dev, stream, log_l=args.merkle_log_l)
+        except Exception as e:  # noqa: BLE001
+            extra["merkle_commit"] = {"error": repr(e)[:300]}
+    if args.poseidon_table_log_n >= 0:
+        k5 = args.poseidon_table_log_n or (24 if world >= 2 else 23)
+        try:
+            extra["poseidon_table_prove"] = poseidon_table_config5(ctx, torch, dist, odist, world, rank, dev, k5)
+        except Exception as e:  # noqa: BLE001
+            extra["poseidon_table_prove"] = {"error": repr(e)[:300]}
     if rank == 0:
         line.update(extra)
         _emit(json.dumps(line))

@@ -64,12 +64,12 @@ __global__ void __launch_bounds__(256) merkle_level_kernel(uint64_t* nodes, size
     o[1] = make_ulonglong2(h[2], h[3]);
 }
 
-__global__ void __launch_bounds__(256) fri_leaves_kernel(const uint64_t* __restrict__ vals /* [2][len] */, size_t len, int arity,
-                                                         uint64_t* __restrict__ digests) {
+__global__ void __launch_bounds__(256) fri_leaves_kernel(const uint64_t* __restrict__ vals /* [2][len] */, size_t len, int arity, size_t leaf_first,
+                                                         size_t leaf_count, uint64_t* __restrict__ digests) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= len / arity) return;
+    if (i >= leaf_count) return;
     uint64_t h[4];
-    hash_u64s<false>((size_t)2 * arity, FriLoad{vals + i * arity, vals + len + i * arity}, h);
+    hash_u64s<false>((size_t)2 * arity, FriLoad{vals + (leaf_first + i) * arity, vals + len + (leaf_first + i) * arity}, h);
     ulonglong2* d = reinterpret_cast<ulonglong2*>(digests + 4 * i);
     d[0] = make_ulonglong2(h[0], h[1]);
     d[1] = make_ulonglong2(h[2], h[3]);
@@ -115,13 +115,12 @@ void merkle_levels(ola_ctx* ctx, uint64_t* d_nodes, size_t nleaves, size_t stop)
         if (first == 1) break;
     }
 }
-void fri_leaves(ola_ctx* ctx, const uint64_t* d_vals, size_t len, int arity, uint64_t* d_digests) {
-    const size_t nleaves = len / arity;
+void fri_leaves(ola_ctx* ctx, const uint64_t* d_vals, size_t len, int arity, size_t leaf_first, size_t nleaves, uint64_t* d_digests) {
     if (!nleaves) return;
     OLA_CHECK(2 * (size_t)arity <= 128, OLA_ERR_INVALID_ARG, "FRI arity too large for a one-chunk leaf");
     {
         Launch lz(ctx, "blake3_fri_leaves");
-        fri_leaves_kernel<<<(unsigned)((nleaves + 255) / 256), 256, 0, ctx->stream>>>(d_vals, len, arity, d_digests);
+        fri_leaves_kernel<<<(unsigned)((nleaves + 255) / 256), 256, 0, ctx->stream>>>(d_vals, len, arity, leaf_first, nleaves, d_digests);
     }
     check_launch("blake3 fri_leaves_kernel");
 }

@@ -159,15 +159,17 @@ __global__ void __launch_bounds__(QL_THREADS) ql_emit_kernel(const uint64_t* __r
 }
 
 // ---- FRI layer leaves: leaf i = flatten(values[16 i .. 16 i + 16)) -> digest (hash_no_pad of 32 elements) ----
-__global__ void __launch_bounds__(128, 5) fri_leaves_kernel(const uint64_t* __restrict__ vals /* [2][len] */, size_t len, int arity, uint64_t* __restrict__ digests) {
+// (leaves [leaf_first, leaf_first + leaf_count) of the layer; digests[4 i] is the digest of leaf leaf_first + i: a rank of
+// the leaf-range-sharded commit phase hashes its own range)
+__global__ void __launch_bounds__(128, 5) fri_leaves_kernel(const uint64_t* __restrict__ vals /* [2][len] */, size_t len, int arity, size_t leaf_first,
+                                                            size_t leaf_count, uint64_t* __restrict__ digests) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t nleaves = len / arity;
-    if (i >= nleaves) return;
+    if (i >= leaf_count) return;
     uint64_t s[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) s[k] = 0;
-    const uint64_t* c0 = vals + i * arity;
-    const uint64_t* c1 = vals + len + i * arity;
+    const uint64_t* c0 = vals + (leaf_first + i) * arity;
+    const uint64_t* c1 = vals + len + (leaf_first + i) * arity;
     for (int e = 0; e < arity; e += 4) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -344,8 +346,9 @@ stark::FriProof prove_openings(ola_ctx* ctx, const Instance& inst, const std::ve
 
     // ---- commit phase (fri_committed_trees, prover.rs:72-121)
     struct Layer {
-        DevMem vals, nodes;
-        size_t len = 0;
+        DevMem vals, nodes;  // nodes: heap-ordered tree over leaves [leaf_lo, leaf_lo + nloc)
+        size_t len = 0, nloc = 0, leaf_lo = 0;
+        bool sharded = false;
     };
     std::vector<std::unique_ptr<Layer>> layers;
     stark::FriProof proof;
@@ -376,20 +379,36 @@ stark::FriProof prove_openings(ola_ctx* ctx, const Instance& inst, const std::ve
             ntt::forward(ctx, d);
         }
         const size_t nleaves = ly->len / arity;
-        ly->nodes.alloc(2 * nleaves * 4);
-        if (ctx->hasher == OLA_HASH_BLAKE3) {
-            blake3::fri_leaves(ctx, ly->vals.p, ly->len, arity, ly->nodes.p + 4 * nleaves);
-        } else {
-            Launch lz(ctx, "fri_leaves");
-            fri_leaves_kernel<<<(unsigned)((nleaves + 127) / 128), 128, 0, st>>>(ly->vals.p, ly->len, arity, ly->nodes.p + 4 * nleaves);
-        }
-        check_launch("fri_leaves_kernel");
         const size_t ncap = (size_t)1 << Config::cap_height;
         OLA_CHECK(nleaves >= ncap, OLA_ERR_INTERNAL, "FRI layer smaller than the Merkle cap");
-        hasher::merkle_levels(ctx, ly->nodes.p, nleaves, ncap);
+        // Multi-GPU: a large layer's tree is sharded by leaf range (rank r hashes leaves [r nleaves / world, ...) and reduces
+        // the ncap / world cap subtrees above them; one all-gather assembles the cap); small layers are replicated.
+        // (OLA_FRI_SHARD_MIN_LEAVES lowers the threshold so that tests reach the sharded path with small tables)
+        const char* env_min = getenv("OLA_FRI_SHARD_MIN_LEAVES");
+        const size_t shard_min = env_min ? (size_t)atoll(env_min) : ((size_t)1 << 14);
+        ly->sharded = ctx->world > 1 && nleaves >= shard_min && nleaves >= ncap * (size_t)ctx->world && ncap % (size_t)ctx->world == 0;
+        ly->nloc = ly->sharded ? nleaves / (size_t)ctx->world : nleaves;
+        ly->leaf_lo = ly->sharded ? (size_t)ctx->rank * ly->nloc : 0;
+        const size_t ncap_loc = ly->sharded ? ncap / (size_t)ctx->world : ncap;
+        ly->nodes.alloc(2 * ly->nloc * 4);
+        if (ctx->hasher == OLA_HASH_BLAKE3) {
+            blake3::fri_leaves(ctx, ly->vals.p, ly->len, arity, ly->leaf_lo, ly->nloc, ly->nodes.p + 4 * ly->nloc);
+        } else {
+            Launch lz(ctx, "fri_leaves");
+            fri_leaves_kernel<<<(unsigned)((ly->nloc + 127) / 128), 128, 0, st>>>(ly->vals.p, ly->len, arity, ly->leaf_lo, ly->nloc, ly->nodes.p + 4 * ly->nloc);
+        }
+        check_launch("fri_leaves_kernel");
+        hasher::merkle_levels(ctx, ly->nodes.p, ly->nloc, ncap_loc);
         stark::Cap cap(ncap);
-        OLA_CUDA(cudaMemcpyAsync(cap.data(), ly->nodes.p + 4 * ncap, ncap * 32, cudaMemcpyDeviceToHost, st));
-        OLA_CUDA(cudaStreamSynchronize(st));
+        if (ly->sharded) {
+            DevMem d_cap(ncap * 4);
+            comm_allgather(ctx, ly->nodes.p + 4 * ncap_loc, d_cap.p, ncap_loc * 32);
+            OLA_CUDA(cudaMemcpyAsync(cap.data(), d_cap.p, ncap * 32, cudaMemcpyDeviceToHost, st));
+            OLA_CUDA(cudaStreamSynchronize(st));
+        } else {
+            OLA_CUDA(cudaMemcpyAsync(cap.data(), ly->nodes.p + 4 * ncap, ncap * 32, cudaMemcpyDeviceToHost, st));
+            OLA_CUDA(cudaStreamSynchronize(st));
+        }
         ch.observe_cap(cap);
         proof.commit_caps.push_back(cap);
         E beta = ch.get_ext();
@@ -453,6 +472,8 @@ stark::FriProof prove_openings(ola_ctx* ctx, const Instance& inst, const std::ve
         off_paths[o] = total;
         total += (size_t)nq * nsib0 * 4;
     }
+    // the layers' Merkle paths come next (owner-answered like the oracle openings when a layer's tree is sharded), the
+    // layers' rows last (the layer values are replicated: every rank reads them locally)
     std::vector<size_t> off_lrows(layers.size()), off_lpaths(layers.size());
     std::vector<int> lshift(layers.size()), lnsib(layers.size());
     {
@@ -463,13 +484,17 @@ stark::FriProof prove_openings(ola_ctx* ctx, const Instance& inst, const std::ve
             bits -= arities[li];
             lshift[li] = sh;
             lnsib[li] = (int)bits - (int)Config::cap_height;
-            off_lrows[li] = total;
-            total += (size_t)nq * 2 * (1 << arities[li]);
             off_lpaths[li] = total;
             total += (size_t)nq * lnsib[li] * 4;
         }
     }
+    const size_t exchanged_words = total;
+    for (size_t li = 0; li < layers.size(); ++li) {
+        off_lrows[li] = total;
+        total += (size_t)nq * 2 * (1 << arities[li]);
+    }
     DevMem d_out(total);
+    if (ctx->world > 1) OLA_CUDA(cudaMemsetAsync(d_out.p, 0, total * 8, st));
     bool sharded = false;
     for (size_t o = 0; o < oracles.size(); ++o) {
         size_t cnt = (size_t)nq * oracles[o]->ncols;
@@ -488,11 +513,6 @@ stark::FriProof prove_openings(ola_ctx* ctx, const Instance& inst, const std::ve
                                                                                   leaf_lo, d_out.p + off_paths[o]);
         }
     }
-    if (sharded) {
-        // owner-answered openings: every rank holds zeros for the leaves it does not own -> wrapping sum = the answer
-        const size_t oracle_words = layers.empty() ? total : off_lrows[0];
-        comm_allreduce(ctx, d_out.p, oracle_words);
-    }
     for (size_t li = 0; li < layers.size(); ++li) {
         const int arity = 1 << arities[li];
         size_t cnt = (size_t)nq * 2 * arity;
@@ -501,12 +521,18 @@ stark::FriProof prove_openings(ola_ctx* ctx, const Instance& inst, const std::ve
             gather_query_ext_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(layers[li]->vals.p, layers[li]->len, arity, (const uint32_t*)d_idx.p, lshift[li],
                                                                                 nq, d_out.p + off_lrows[li]);
         }
-        if (lnsib[li] > 0) {
+        // paths: the owner of the leaf answers; a replicated layer is answered by rank 0 alone when the buffer is exchanged
+        const bool answer = layers[li]->sharded || !sharded || ctx->rank == 0;
+        if (lnsib[li] > 0 && answer) {
             Launch lz(ctx, "fri_query_paths");
             size_t pc = (size_t)nq * lnsib[li] * 4;
-            gather_query_paths_kernel<<<(unsigned)((pc + 127) / 128), 128, 0, st>>>(layers[li]->nodes.p, layers[li]->len / arity, (const uint32_t*)d_idx.p,
-                                                                                  lshift[li], nq, lnsib[li], 0, d_out.p + off_lpaths[li]);
+            gather_query_paths_kernel<<<(unsigned)((pc + 127) / 128), 128, 0, st>>>(layers[li]->nodes.p, layers[li]->nloc, (const uint32_t*)d_idx.p, lshift[li], nq,
+                                                                                  lnsib[li], layers[li]->leaf_lo, d_out.p + off_lpaths[li]);
         }
+    }
+    if (sharded) {
+        // owner-answered openings: every rank holds zeros for the leaves it does not own -> wrapping sum = the answer
+        comm_allreduce(ctx, d_out.p, exchanged_words);
     }
     check_launch("fri query gathers");
     std::vector<uint64_t> hout(total);

@@ -12,7 +12,7 @@ void hash_rows_rowmajor(ola_ctx* ctx, const uint64_t* d_rows, size_t nrows, size
 void hash_rows_colmajor(ola_ctx* ctx, const uint64_t* d_cols, size_t col_stride, size_t nrows, size_t ncols, uint64_t* d_digests);
 void merkle_levels(ola_ctx* ctx, uint64_t* d_nodes, size_t nleaves, size_t stop);
 // digests[i] = hash_no_pad(flatten(vals[arity i .. arity (i + 1)))) of a planar [2][len] extension vector
-void fri_leaves(ola_ctx* ctx, const uint64_t* d_vals, size_t len, int arity, uint64_t* d_digests);
+void fri_leaves(ola_ctx* ctx, const uint64_t* d_vals, size_t len, int arity, size_t leaf_first, size_t nleaves, uint64_t* d_digests);
 }  // namespace blake3
 namespace hasher {
 void hash_rows_rowmajor(ola_ctx* ctx, const uint64_t* d_rows, size_t nrows, size_t ncols, uint64_t* d_digests);

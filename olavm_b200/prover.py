@@ -57,6 +57,30 @@ def prove_with_traces(ctx, table_ids, trace_poly_values, check_quotient_degree=T
     return out[: n.value].tobytes()
 
 
+def prove_with_device_traces(ctx, table_ids, device_ptrs, log_ns, check_quotient_degree=True, max_bytes=1 << 26, compress_challenges=None):
+    """prove_with_traces for traces already resident in HBM (ola_prove with on_device = 1): device_ptrs[i] points at table
+    i's column-major [columns_i][2^log_ns[i]] u64 block (Context.alloc / Context.upload / generation on the device)."""
+    k = len(table_ids)
+    if len(device_ptrs) != k or len(log_ns) != k:
+        raise ValueError("one device pointer and one log size per table id")
+    if compress_challenges is None and any(int(t) in (TABLES["bitwise"], TABLES["program"]) for t in table_ids):
+        raise ValueError("the Bitwise and Program tables need their compress challenges (compress_challenges=...)")
+    ids = (ctypes.c_int * k)(*[int(x) for x in table_ids])
+    ptrs = (ctypes.c_void_p * k)(*[p.value if isinstance(p, ctypes.c_void_p) else int(p) for p in device_ptrs])
+    logs = (ctypes.c_uint32 * k)(*[int(x) for x in log_ns])
+    out = np.empty(max_bytes, dtype=np.uint8)
+    n = ctypes.c_size_t(0)
+    cc = None
+    if compress_challenges is not None:
+        cc_arr = np.ascontiguousarray(compress_challenges, dtype=np.uint64)
+        if cc_arr.shape != (k,):
+            raise ValueError("one compress challenge per table")
+        cc = cc_arr.ctypes.data_as(ctypes.c_void_p)
+    ctx.check(ctx._lib.ola_prove(ctx.handle, ids, k, ptrs, 1, logs, cc, 1 if check_quotient_degree else 0, out.ctypes.data_as(ctypes.c_void_p),
+                                 max_bytes, ctypes.byref(n)))
+    return out[: n.value].tobytes()
+
+
 def verify_proof(table_ids, proof, hasher=0):
     """`circuits::stark::verifier::verify_proof` over `Buffer::read_all_proof`'s bytes (verifier.rs:32-212,
     serialization.rs:395-411) -> (accepted, reason).  Host code: needs the library but no GPU.

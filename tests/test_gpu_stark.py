@@ -333,6 +333,26 @@ def test_sharded_prover_equals_single_gpu(ctx, orc, world):
     assert ok, msg
 
 
+@pytest.mark.parametrize("hasher", [0, 1])
+def test_sharded_prover_with_leaf_range_sharded_fri_layers(ctx, orc, hasher, monkeypatch):
+    """Large FRI layers are committed by leaf range across the ranks (cap all-gathered, Merkle paths answered by the leaf's
+    owner); the threshold is lowered so that this small system takes that path.  Same bytes as one GPU, both hashers."""
+    from olavm_b200 import dist as odist
+
+    monkeypatch.setenv("OLA_FRI_SHARD_MIN_LEAVES", "64")
+    cmp_t, rc_t = _valid_cmp_rc(8, 9)   # RangeCheck 2^16 rows: first FRI layer 2^15 leaves, second 2^11, third 2^7
+    ctx.hasher = hasher
+    try:
+        single = olavm_b200.prove_with_traces(ctx, [CMP, RC], [cmp_t, rc_t])
+    finally:
+        ctx.hasher = 0
+    for world in (2, 4, 8):
+        proofs = odist.prove_sharded_local(0, world, [CMP, RC], [cmp_t, rc_t], hasher=hasher)
+        assert all(p == single for p in proofs), world
+    ok, msg = orc.stark_verify([CMP, RC], single, hasher_id=hasher)
+    assert ok, msg
+
+
 def test_sharded_prover_five_table_system_and_cpu_table(ctx, orc):
     from olavm_b200 import dist as odist
 

@@ -232,6 +232,14 @@ int ola_generate_poseidon_trace(ola_ctx* ctx, const uint64_t* inputs, const uint
  * sponge is sequential: host code on the library's own transcript, no context needed. */
 int ola_compress_challenge(const uint64_t* const* cols, uint32_t ncols, size_t n, uint64_t* beta_out);
 
+/* Diagnostic (host code, no context): the individual constraint values of a table's eval_packed_generic (e.g.
+ * CpuStark, circuits/src/cpu/cpu_stark.rs:871-946) on ONE (local, next) row pair over the base field, in emission order and
+ * before the ConstraintConsumer weighs them -- vals_out[k] is the argument of the k-th yield_constr call, kinds_out[k] = 0
+ * constraint, 1 constraint_transition, 2 constraint_first_row, 3 constraint_last_row.  These are the same constraint
+ * transcriptions the quotient kernels and ola_verify compile.  Returns the number of constraints (at most cap are
+ * written) or a negative error. */
+int ola_air_constraints(int table_id, const uint64_t* lv, const uint64_t* nv, uint64_t compress_challenge, uint64_t* vals_out, int* kinds_out,
+                        int cap);
 /* number of trace columns of a table (S::COLUMNS), or -1 if its constraint kernel is not compiled in */
 int ola_table_columns(int table_id);
 

@@ -515,6 +515,32 @@ int ola_compress_challenge(const uint64_t* const* cols, uint32_t ncols, size_t n
     }
 }
 
+int ola_air_constraints(int table_id, const uint64_t* lv, const uint64_t* nv, uint64_t compress_challenge, uint64_t* vals_out, int* kinds_out, int cap) {
+    if (!lv || !nv || (cap > 0 && (!vals_out || !kinds_out))) return OLA_ERR_INVALID_ARG;
+    try {
+        if (!ola::stark::table_available(table_id)) return OLA_ERR_INVALID_ARG;
+        ola::stark::TableInfo t = ola::stark::table_info(table_id);
+        t.compress_challenge = gl::canon(compress_challenge);
+        using ola::stark::verify::XE;
+        std::vector<XE> l((size_t)t.columns), n((size_t)t.columns);
+        for (int c = 0; c < t.columns; ++c) {
+            l[c] = XE((ola::stark::F)lv[c]);
+            n[c] = XE((ola::stark::F)nv[c]);
+        }
+        ola::stark::verify::XRow lrow{l.data()}, nrow{n.data()};
+        ola::stark::verify::RecordingConsumer rc;
+        ola::stark::verify::eval_table_t(t, lrow, nrow, rc);
+        const int k = (int)rc.vals.size();
+        for (int i = 0; i < k && i < cap; ++i) {
+            vals_out[i] = gl::canon(rc.vals[i].v.c0);  // base-field rows: the extension component stays 0
+            kinds_out[i] = rc.kinds[i];
+        }
+        return k;
+    } catch (...) {
+        return OLA_ERR_INTERNAL;
+    }
+}
+
 int ola_table_columns(int table_id) {
     try {
         return ola::stark::table_available(table_id) ? ola::stark::table_info(table_id).columns : -1;

@@ -167,6 +167,15 @@ struct CountingConsumer {
     void constraint_first_row(XE) { ++n; }
     void constraint_last_row(XE) { ++n; }
 };
+// the raw argument and the kind (0 constraint, 1 transition, 2 first row, 3 last row) of every yield, in order
+struct RecordingConsumer {
+    std::vector<XE> vals;
+    std::vector<int> kinds;
+    void constraint(XE c) { vals.push_back(c); kinds.push_back(0); }
+    void constraint_transition(XE c) { vals.push_back(c); kinds.push_back(1); }
+    void constraint_first_row(XE c) { vals.push_back(c); kinds.push_back(2); }
+    void constraint_last_row(XE c) { vals.push_back(c); kinds.push_back(3); }
+};
 inline int air_constraint_count(const TableInfo& t) {
     std::vector<XE> zeros((size_t)t.columns, XE((F)0));
     XRow row{zeros.data()};

@@ -57,6 +57,25 @@ def prove_with_traces(ctx, table_ids, trace_poly_values, check_quotient_degree=T
     return out[: n.value].tobytes()
 
 
+def air_constraints(table_id, lv, nv, compress_challenge=0):
+    """The individual constraint values the table's eval_packed_generic emits for one (local, next) row pair over the base
+    field, in order, with their kinds (0 constraint, 1 transition, 2 first row, 3 last row): the constraint code of the
+    quotient kernels and of verify_proof, evaluated on the host.  -> (values uint64[K], kinds int32[K])."""
+    lib = _lib.load()
+    lv = np.ascontiguousarray(lv, dtype=np.uint64)
+    nv = np.ascontiguousarray(nv, dtype=np.uint64)
+    cols = int(lib.ola_table_columns(int(table_id)))
+    if cols < 0 or lv.shape != (cols,) or nv.shape != (cols,):
+        raise ValueError("unknown table or wrong row width")
+    cap = 4096
+    vals = np.zeros(cap, dtype=np.uint64)
+    kinds = np.zeros(cap, dtype=np.int32)
+    k = lib.ola_air_constraints(int(table_id), _lib.hptr(lv), _lib.hptr(nv), int(compress_challenge), _lib.hptr(vals), kinds.ctypes.data_as(ctypes.c_void_p), cap)
+    if k < 0 or k > cap:
+        raise _lib.OlaError(k, "ola_air_constraints")
+    return vals[:k].copy(), kinds[:k].copy()
+
+
 def prove_with_device_traces(ctx, table_ids, device_ptrs, log_ns, check_quotient_degree=True, max_bytes=1 << 26, compress_challenges=None):
     """prove_with_traces for traces already resident in HBM (ola_prove with on_device = 1): device_ptrs[i] points at table
     i's column-major [columns_i][2^log_ns[i]] u64 block (Context.alloc / Context.upload / generation on the device)."""

@@ -92,6 +92,8 @@ def _set_sigs(L):
     L.orc_table_columns.argtypes = [_int]
     L.orc_air_first_failure.argtypes = [_int, _u64p, _u32, _u64, ctypes.POINTER(_u64), ctypes.POINTER(_int)]
     L.orc_table_columns.restype = _int
+    L.orc_air_constraints.argtypes = [_int, _u64p, _u64p, _u64, _u64p, ctypes.POINTER(_int), _int]
+    L.orc_air_constraints.restype = _int
     L.orc_compress_challenge.argtypes = [ctypes.POINTER(ctypes.c_void_p), _u32, _sz]
     L.orc_compress_challenge.restype = _u64
 
@@ -306,6 +308,20 @@ def air_first_failure(table_id, trace, compress_challenge=0):
     if rc < 0:
         raise StarkError("air_first_failure: unknown table or bad trace")
     return None if rc == 0 else (int(row.value), int(idx.value))
+
+
+def air_constraints(table_id, lv, nv, compress_challenge=0):
+    """The individual constraint values the table's eval_packed_generic emits for one (local, next) row pair, in order,
+    with their kinds (0 constraint, 1 transition, 2 first row, 3 last row): (values uint64[K], kinds int32[K])."""
+    lv = np.ascontiguousarray(lv, dtype=np.uint64)
+    nv = np.ascontiguousarray(nv, dtype=np.uint64)
+    cap = 4096
+    vals = np.zeros(cap, dtype=np.uint64)
+    kinds = np.zeros(cap, dtype=np.int32)
+    n = lib().orc_air_constraints(int(table_id), _p(lv), _p(nv), int(compress_challenge), _p(vals), kinds.ctypes.data_as(ctypes.POINTER(_int)), cap)
+    if n < 0 or n > cap:
+        raise StarkError("air_constraints: unknown table")
+    return vals[:n].copy(), kinds[:n].copy()
 
 
 def compress_challenge(columns):

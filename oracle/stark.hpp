@@ -18,14 +18,25 @@ struct Consumer {
     int seen = 0, first_nonzero = -1;
     static bool is_zero(F x) { return gl_canon(x) == 0; }
     static bool is_zero(E x) { return gl_canon(x.c0) == 0 && gl_canon(x.c1) == 0; }
-    void constraint(T c) {
+    /* test hook (orc_air_constraints): the raw argument and the kind of every yield, in order */
+    bool record = false;
+    std::vector<typename O::T> rec_raw;
+    std::vector<int> rec_kinds;
+    void note(T c, int kind) {
+        if (record) {
+            rec_raw.push_back(c.v);
+            rec_kinds.push_back(kind);
+        }
+    }
+    void weigh(T c) {
         if (first_nonzero < 0 && !is_zero(c.v)) first_nonzero = seen;
         seen++;
         for (size_t i = 0; i < alphas.size(); i++) accs[i] = accs[i] * alphas[i] + c;
     }
-    void constraint_transition(T c) { constraint(c * z_last); }
-    void constraint_first_row(T c) { constraint(c * lagrange_first); }
-    void constraint_last_row(T c) { constraint(c * lagrange_last); }
+    void constraint(T c) { note(c, 0); weigh(c); }
+    void constraint_transition(T c) { note(c, 1); weigh(c * z_last); }
+    void constraint_first_row(T c) { note(c, 2); weigh(c * lagrange_first); }
+    void constraint_last_row(T c) { note(c, 3); weigh(c * lagrange_last); }
 };
 
 /* ------------------------------------------------------------------ Column / CTL (cross_table_lookup.rs) */

@@ -103,6 +103,35 @@ uint64_t orc_compress_challenge(const uint64_t* const* cols, uint32_t ncols, siz
     return ch.get_challenge();
 }
 
+/* The individual constraint values of a table's eval_packed_generic on one (local, next) row pair over the base field, in
+ * emission order, BEFORE the consumer weighs them: vals[k] = the argument of the k-th yield_constr call, kinds[k] = 0
+ * constraint, 1 constraint_transition, 2 constraint_first_row, 3 constraint_last_row.  Returns the number of constraints (or
+ * -1); writes at most cap of them.  Lets a test pin order AND value of every constraint of another transcription. */
+int orc_air_constraints(int table_id, const uint64_t* lv_in, const uint64_t* nv_in, uint64_t compress_challenge, uint64_t* vals, int* kinds, int cap) {
+    try {
+        VF cc(1, compress_challenge);
+        System sys = make_system(std::vector<int>(1, table_id), cc);
+        const Table& t = sys.tables[0];
+        std::vector<P<FOps>> lv(t.columns), nv(t.columns);
+        for (int c = 0; c < t.columns; c++) {
+            lv[c] = P<FOps>(gl_canon(lv_in[c]));
+            nv[c] = P<FOps>(gl_canon(nv_in[c]));
+        }
+        /* z_last = lagrange_first = lagrange_last = 1 and alpha = 0 would lose the values: record them instead */
+        Consumer<FOps> cons(VF(1, 1), P<FOps>::c(1), P<FOps>::c(1), P<FOps>::c(1));
+        cons.record = true;
+        t.eval_base(lv.data(), nv.data(), cons);
+        const int n = (int)cons.rec_raw.size();
+        for (int k = 0; k < n && k < cap; k++) {
+            vals[k] = gl_canon(cons.rec_raw[k]);
+            kinds[k] = cons.rec_kinds[k];
+        }
+        return n;
+    } catch (...) {
+        return -1;
+    }
+}
+
 int orc_table_columns(int table_id) {
     try { return table_by_id(table_id).columns; } catch (...) { return -1; }
 }

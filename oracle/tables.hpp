@@ -12,9 +12,9 @@
 #define ORC_TABLES_HPP
 #include "stark.hpp"
 #include "poseidon_constants.h"
-/* The CPU table's constraint body and the CTL registry are a single transcription shared with the product
- * (olavm_b200/csrc/air/{cpu_air,ctl_registry}.h); see the note at the top of cpu_air.h and DESIGN.md section 4. */
-#include "../olavm_b200/csrc/air/ctl_registry.h"
+/* every table's AIR and the CTL registry are restated in this directory from the Rust (air_*.hpp, ctl_registry.hpp); nothing
+ * under olavm_b200/ is included */
+#include "ctl_registry.hpp"
 
 namespace orc {
 
@@ -61,58 +61,15 @@ void eval(const P<O>* lv, const P<O>* nv, Consumer<O>& yc) {
 }
 }  // namespace rangecheck
 
-}  // namespace orc
-namespace ola {
-namespace air {
-template <> inline orc::P<orc::FOps> kc<orc::P<orc::FOps>>(uint64_t k) { return orc::P<orc::FOps>::c(k); }
-template <> inline orc::P<orc::EOps> kc<orc::P<orc::EOps>>(uint64_t k) { return orc::P<orc::EOps>::c(k); }
-template <> inline bool is_zero<orc::P<orc::FOps>>(const orc::P<orc::FOps>& x) { return x.v == 0; }
-template <> inline bool is_zero<orc::P<orc::EOps>>(const orc::P<orc::EOps>& x) { return x.v.c0 == 0 && x.v.c1 == 0; }
-}  // namespace air
-}  // namespace ola
-namespace orc {
-/* ---- Cpu (cpu_stark.rs:871-946, shared transcription) ---- */
-namespace cpu_t {
-template <class O>
-void eval(const P<O>* lv, const P<O>* nv, Consumer<O>& yc) {
-    ola::air::cpu::eval<P<O>, const P<O>*, Consumer<O>>(lv, nv, yc);
-}
-}  // namespace cpu_t
-/* ---- Memory (memory_stark.rs:92-340, shared transcription) ---- */
-namespace mem_t {
-template <class O>
-void eval(const P<O>* lv, const P<O>* nv, Consumer<O>& yc) {
-    ola::air::mem::eval<P<O>, const P<O>*, Consumer<O>>(lv, nv, yc);
-}
-}  // namespace mem_t
-
-/* ---- shared transcriptions of builtins_air.h / hash_air.h ---- */
-#define ORC_SHARED_TABLE(NS_T, NS)                                                                     \
-    namespace NS_T {                                                                                   \
-    template <class O>                                                                                 \
-    void eval(const P<O>* lv, const P<O>* nv, Consumer<O>& yc) { ola::air::NS::eval<P<O>, const P<O>*, Consumer<O>>(lv, nv, yc); } \
-    }
-ORC_SHARED_TABLE(tape_t, tape)
-ORC_SHARED_TABLE(sccall_t, sccall)
-ORC_SHARED_TABLE(prog_chunk_t, prog_chunk)
-ORC_SHARED_TABLE(storage_t, storage)
-ORC_SHARED_TABLE(psdn_chunk_t, psdn_chunk)
-#undef ORC_SHARED_TABLE
-/* Poseidon table: parameter tables from the oracle's own generated constants */
-struct PoseidonParams {
-    static uint64_t round(int i) { return ORC_ALL_ROUND_CONSTANTS[i]; }
-    static uint64_t circ(int i) { return ORC_MDS_MATRIX_CIRC[i]; }
-    static uint64_t diag(int i) { return ORC_MDS_MATRIX_DIAG[i]; }
-    static uint64_t first(int i) { return ORC_FAST_PARTIAL_FIRST_ROUND_CONSTANT[i]; }
-    static uint64_t partial(int r) { return ORC_FAST_PARTIAL_ROUND_CONSTANTS[r]; }
-    static uint64_t init(int r, int c) { return ORC_FAST_PARTIAL_ROUND_INITIAL_MATRIX[r][c]; }
-    static uint64_t what(int r, int i) { return ORC_FAST_PARTIAL_ROUND_W_HATS[r][i]; }
-    static uint64_t vs(int r, int i) { return ORC_FAST_PARTIAL_ROUND_VS[r][i]; }
-};
-namespace psdn_t {
-template <class O>
-void eval(const P<O>* lv, const P<O>* nv, Consumer<O>& yc) { ola::air::psdn::eval<P<O>, const P<O>*, Consumer<O>, PoseidonParams>(lv, nv, yc); }
-}  // namespace psdn_t
+/* ---- the other ten tables: air_cpu.hpp, air_memory.hpp, air_builtins.hpp, air_storage_program.hpp ---- */
+namespace cpu_t { template <class O> void eval(const P<O>* lv, const P<O>* nv, Consumer<O>& yc) { cpu_air::eval<O>(lv, nv, yc); } }
+namespace mem_t { template <class O> void eval(const P<O>* lv, const P<O>* nv, Consumer<O>& yc) { memory_air::eval<O>(lv, nv, yc); } }
+namespace tape_t { template <class O> void eval(const P<O>* lv, const P<O>* nv, Consumer<O>& yc) { tape_air::eval<O>(lv, nv, yc); } }
+namespace sccall_t { template <class O> void eval(const P<O>* lv, const P<O>* nv, Consumer<O>& yc) { sccall_air::eval<O>(lv, nv, yc); } }
+namespace prog_chunk_t { template <class O> void eval(const P<O>* lv, const P<O>* nv, Consumer<O>& yc) { prog_chunk_air::eval<O>(lv, nv, yc); } }
+namespace storage_t { template <class O> void eval(const P<O>* lv, const P<O>* nv, Consumer<O>& yc) { storage_air::eval<O>(lv, nv, yc); } }
+namespace psdn_chunk_t { template <class O> void eval(const P<O>* lv, const P<O>* nv, Consumer<O>& yc) { poseidon_chunk_air::eval<O>(lv, nv, yc); } }
+namespace psdn_t { template <class O> void eval(const P<O>* lv, const P<O>* nv, Consumer<O>& yc) { poseidon_air::eval<O>(lv, nv, yc); } }
 
 template <class EvalB, class EvalE>
 Table make_table(const char* name, int cols, int degree, EvalB eb, EvalE ee, std::vector<PermutationPair> pp = {}) {
@@ -132,8 +89,8 @@ inline bool table_available(int id) { return id >= 0 && id < T_NUM; }
 /* beta: the table's compress challenge (Bitwise / Program only; verifier.rs:78-86 takes it from the proof) */
 inline Table table_by_id(int id, F beta = 0) {
     switch (id) {
-        case T_CPU: return ORC_TABLE("CpuStark", cpu_t, ola::air::cpu::NUM_CPU_COLS, 7);
-        case T_MEMORY: return ORC_TABLE("MemoryStark", mem_t, ola::air::mem::NUM_MEM_COLS, 8);
+        case T_CPU: return ORC_TABLE("CpuStark", cpu_t, cpu_air::NUM_COLS, 7);
+        case T_MEMORY: return ORC_TABLE("MemoryStark", mem_t, memory_air::NUM_COLS, 8);
         case T_CMP: return ORC_TABLE("CmpStark", cmp, cmp::NUM, 3);
         case T_RANGECHECK:
             return ORC_TABLE("RangeCheckStark", rangecheck, rangecheck::NUM, 3,
@@ -141,42 +98,34 @@ inline Table table_by_id(int id, F beta = 0) {
                               PermutationPair{{{rangecheck::LIMB_HI, rangecheck::LIMB_HI_PERMUTED}}},
                               PermutationPair{{{rangecheck::FIX_RANGE_CHECK_U16, rangecheck::FIX_RANGE_CHECK_U16_PERMUTED_LO}}},
                               PermutationPair{{{rangecheck::FIX_RANGE_CHECK_U16, rangecheck::FIX_RANGE_CHECK_U16_PERMUTED_HI}}}});
-        case T_POSEIDON: return ORC_TABLE("PoseidonStark", psdn_t, ola::air::psdn::NUM_POSEIDON_COLS, 7);
-        case T_POSEIDON_CHUNK: return ORC_TABLE("PoseidonChunkStark", psdn_chunk_t, ola::air::psdn_chunk::NUM_POSEIDON_CHUNK_COLS, 3);
-        case T_STORAGE: return ORC_TABLE("StorageAccessStark", storage_t, ola::air::storage::NUM_COL_ST, 4);
-        case T_TAPE: return ORC_TABLE("TapeStark", tape_t, ola::air::tape::NUM_COL_TAPE, 5);
-        case T_SCCALL: return ORC_TABLE("SCCallStark", sccall_t, ola::air::sccall::NUM_COL_SCCALL, 1);
-        case T_PROG_CHUNK: return ORC_TABLE("ProgChunkStark", prog_chunk_t, ola::air::prog_chunk::NUM_PROG_CHUNK_COLS, 4);
+        case T_POSEIDON: return ORC_TABLE("PoseidonStark", psdn_t, poseidon_air::NUM_COLS, 7);
+        case T_POSEIDON_CHUNK: return ORC_TABLE("PoseidonChunkStark", psdn_chunk_t, poseidon_chunk_air::NUM_COLS, 3);
+        case T_STORAGE: return ORC_TABLE("StorageAccessStark", storage_t, storage_air::NUM_COLS, 4);
+        case T_TAPE: return ORC_TABLE("TapeStark", tape_t, tape_air::NUM_COLS, 5);
+        case T_SCCALL: return ORC_TABLE("SCCallStark", sccall_t, sccall_air::NUM_COLS, 1);
+        case T_PROG_CHUNK: return ORC_TABLE("ProgChunkStark", prog_chunk_t, prog_chunk_air::NUM_COLS, 4);
         case T_BITWISE: {
-            namespace B = ola::air::bitwise;
-            std::vector<PermutationPair> pp;
+            namespace B = bitwise_air;
+            std::vector<PermutationPair> pp; /* bitwise_stark.rs:352-363 */
             for (int i = 0; i < 4; ++i) pp.push_back(PermutationPair{{{B::COMPRESS_LIMBS + i, B::COMPRESS_PERMUTED + i}}});
             for (int i = 0; i < 4; ++i) pp.push_back(PermutationPair{{{B::FIX_COMPRESS, B::FIX_COMPRESS_PERMUTED + i}}});
-            return make_table("BitwiseStark", B::COL_NUM_BITWISE, 3,
-                              [beta](const P<FOps>* lv, const P<FOps>* nv, Consumer<FOps>& yc) { B::eval<P<FOps>, const P<FOps>*, Consumer<FOps>>(lv, nv, yc, P<FOps>::c(beta)); },
-                              [beta](const P<EOps>* lv, const P<EOps>* nv, Consumer<EOps>& yc) { B::eval<P<EOps>, const P<EOps>*, Consumer<EOps>>(lv, nv, yc, P<EOps>::c(beta)); }, pp);
+            return make_table("BitwiseStark", B::NUM_COLS, 3,
+                              [beta](const P<FOps>* lv, const P<FOps>* nv, Consumer<FOps>& yc) { B::eval<FOps>(lv, nv, yc, P<FOps>::c(beta)); },
+                              [beta](const P<EOps>* lv, const P<EOps>* nv, Consumer<EOps>& yc) { B::eval<EOps>(lv, nv, yc, P<EOps>::c(beta)); }, pp);
         }
         case T_PROGRAM: {
-            namespace G = ola::air::program;
-            return make_table("ProgramStark", G::NUM_PROG_COLS, 3,
-                              [beta](const P<FOps>* lv, const P<FOps>* nv, Consumer<FOps>& yc) { G::eval<P<FOps>, const P<FOps>*, Consumer<FOps>>(lv, nv, yc, P<FOps>::c(beta)); },
-                              [beta](const P<EOps>* lv, const P<EOps>* nv, Consumer<EOps>& yc) { G::eval<P<EOps>, const P<EOps>*, Consumer<EOps>>(lv, nv, yc, P<EOps>::c(beta)); },
-                              {PermutationPair{{{G::COL_PROG_COMP_PROG, G::COL_PROG_COMP_PROG_PERM}}}, PermutationPair{{{G::COL_PROG_EXEC_COMP_PROG, G::COL_PROG_EXEC_COMP_PROG_PERM}}}});
+            namespace G = program_air;
+            return make_table("ProgramStark", G::NUM_COLS, 3,
+                              [beta](const P<FOps>* lv, const P<FOps>* nv, Consumer<FOps>& yc) { G::eval<FOps>(lv, nv, yc, P<FOps>::c(beta)); },
+                              [beta](const P<EOps>* lv, const P<EOps>* nv, Consumer<EOps>& yc) { G::eval<EOps>(lv, nv, yc, P<EOps>::c(beta)); },
+                              {PermutationPair{{{G::COMP_PROG, G::COMP_PROG_PERM}}}, PermutationPair{{{G::EXEC_COMP_PROG, G::EXEC_COMP_PROG_PERM}}}}); /* program_stark.rs:110-115 */
         }
         default: throw std::runtime_error("unknown table id");
     }
 }
 
-/* all_cross_table_lookups (ola_stark.rs:121-143) via the shared registry */
-struct RegPolicy {
-    typedef orc::Column Column;
-    typedef TableWithColumns Twc;
-    typedef CrossTableLookup Ctl;
-    static Column single(int c) { return Column::single(c); }
-    static Column linear(std::vector<std::pair<int, uint64_t>> v, uint64_t k) { return Column::linear(std::vector<std::pair<int, F>>(v.begin(), v.end()), k); }
-    static Twc twc(int table, std::vector<Column> cols, Column filter) { return orc::twc(table, std::move(cols), std::move(filter)); }
-};
-inline std::vector<CrossTableLookup> all_cross_table_lookups() { return ola::air::build_ctl_registry<RegPolicy>(); }
+/* all_cross_table_lookups (ola_stark.rs:121-143): ctl_registry.hpp */
+inline std::vector<CrossTableLookup> all_cross_table_lookups() { return ctl::all_cross_table_lookups(); }
 
 /* A proving system = an ordered subset of the 12 tables (proof order = enum order) plus every registered CTL side
  * whose table is inside the subset (table ids remapped to positions).  CTLs losing a side become partial. */

@@ -186,6 +186,55 @@ int ola_batch_prove_leaf(ola_ctx* ctx, const ola_batch* b, size_t leaf_index, ui
 int ola_prove(ola_ctx* ctx, const int* table_ids, uint32_t ntables, const uint64_t* const* traces, int on_device,
               const uint32_t* log_ns, const uint64_t* compress_challenges, int check_quotient_degree, uint8_t* proof_out,
               size_t proof_cap, size_t* proof_len);
+/* ---- the same proof with the Fiat-Shamir transcript kept by the CALLER (the staged seams) ----
+ * A Rust host that wants to keep its own `Challenger` (plonky2/plonky2/src/iop/challenger.rs) -- to bind the proof to more
+ * public data, to share one transcript between provers, or to audit the prover's transcript -- drives the proof as a
+ * sequence of transcript events instead of handing the transcript to the library.  ola_prove_session_begin starts the prover
+ * (on a worker thread of the library); the caller then loops on ola_prove_session_next:
+ *   OLA_EV_OBSERVE    absorb elems[0..count) in order (challenger.observe_elements); then call next again
+ *   OLA_EV_CHALLENGE  squeeze `count` elements (challenger.get_n_challenges(count)) and hand them over with
+ *                     ola_prove_session_supply; then call next again
+ *   OLA_EV_COMPACT    challenger.compact() (prover.rs:344); then call next again
+ *   OLA_EV_DONE       collect the proof with ola_prove_session_finish
+ * `stage` names the seam of prove_with_traces / prove_single_table / fri_proof the event belongs to (OLA_STAGE_*, the
+ * reference line it mirrors is listed with each) and `table` the Table id being proven (-1 outside prove_single_table):
+ * OLA_STAGE_ZS_CAP is the boundary SURVEY 8b calls ola_ctl_z, OLA_STAGE_ALPHAS .. QUOTIENT_CAP ola_quotient, OLA_STAGE_ZETA ..
+ * OPENINGS ola_open, OLA_STAGE_FRI_* ola_fri_*.  With the reference's own Challenger on the other side the bytes equal
+ * ola_prove's.  The elems pointer is valid until the next call.  No callback enters the host; finish may be called early to
+ * abandon a proof.  Single-GPU contexts only; the context must not be used by other calls while a session is open. */
+typedef struct ola_session ola_session;
+typedef struct {
+    int kind;              /* OLA_EV_* */
+    int stage;             /* OLA_STAGE_* */
+    int table;             /* Table id, or -1 */
+    const uint64_t* elems; /* OLA_EV_OBSERVE: canonical field elements to absorb */
+    size_t count;          /* OBSERVE: number of elems; CHALLENGE: number of elements to supply */
+} ola_transcript_event;
+#define OLA_EV_OBSERVE 1
+#define OLA_EV_CHALLENGE 2
+#define OLA_EV_COMPACT 3
+#define OLA_EV_DONE 4
+#define OLA_EV_FAILED 5
+#define OLA_STAGE_TRACE_CAPS 1        /* prover.rs:147-150 */
+#define OLA_STAGE_CTL_CHALLENGES 2    /* prover.rs:152-158, get_grand_product_challenge_set */
+#define OLA_STAGE_TABLE_BEGIN 3       /* prover.rs:344-372: compact, permutation challenges */
+#define OLA_STAGE_ZS_CAP 4            /* prover.rs:411-413 */
+#define OLA_STAGE_ALPHAS 5            /* prover.rs:415 */
+#define OLA_STAGE_QUOTIENT_CAP 6      /* prover.rs:489-491 */
+#define OLA_STAGE_ZETA 7              /* prover.rs:493 */
+#define OLA_STAGE_OPENINGS 8          /* prover.rs:530, proof.rs:248-283 */
+#define OLA_STAGE_FRI_ALPHA 9         /* fri/oracle.rs:176 */
+#define OLA_STAGE_FRI_LAYER_CAP 10    /* fri/prover.rs:94 */
+#define OLA_STAGE_FRI_BETA 11         /* fri/prover.rs:96 */
+#define OLA_STAGE_FRI_FINAL_POLY 12   /* fri/prover.rs:118 */
+#define OLA_STAGE_FRI_POW 13          /* fri/prover.rs:131: get_hash */
+#define OLA_STAGE_FRI_QUERY_INDICES 14 /* fri/prover.rs:157-160 */
+int ola_prove_session_begin(ola_ctx* ctx, const int* table_ids, uint32_t ntables, const uint64_t* const* traces, int on_device,
+                            const uint32_t* log_ns, const uint64_t* compress_challenges, int check_quotient_degree, ola_session** out);
+int ola_prove_session_next(ola_session* s, ola_transcript_event* ev);
+int ola_prove_session_supply(ola_session* s, const uint64_t* challenges, size_t count);
+int ola_prove_session_finish(ola_session* s, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+
 /* ---- multi-GPU: one process (or thread) per GPU, the proof coset-sharded across the ranks ----
  * After ola_set_comm, ola_prove called COLLECTIVELY by every rank with the SAME arguments shards the three dominant
  * costs by LDE cosets -- commitments (coset LDE + leaf hashing + subtree reduction), constraint-quotient evaluation
@@ -211,12 +260,18 @@ int ola_set_comm_nccl(ola_ctx* ctx, const char* libnccl_path, int rank, int worl
 uint64_t ola_comm_bytes(const ola_ctx* ctx);
 
 /* verify_proof (circuits/src/stark/verifier.rs:32-212) over Buffer::read_all_proof's bytes: host code, no GPU or
- * context needed.  table_ids as for ola_prove (the system the proof was made for).  Returns OLA_OK when the proof is
- * accepted; OLA_ERR_INVALID_ARG with the reason in err (NUL-terminated, truncated to errcap) when it is rejected. */
+ * context needed.  Like the reference's, it is fixed at the full system: table_ids must be the 12 ids 0..11 in order, and
+ * every cross-table lookup is checked.  Returns OLA_OK when the proof is accepted; OLA_ERR_INVALID_ARG with the reason in err
+ * (NUL-terminated, truncated to errcap) when it is rejected. */
 int ola_verify(const int* table_ids, uint32_t ntables, const uint8_t* proof, size_t proof_len, char* err, size_t errcap);
 /* the same for a proof made under `hasher` (OLA_HASH_*): verify_proof::<F, C, D> with C = Blake3GoldilocksConfig */
 int ola_verify_cfg(int hasher, const int* table_ids, uint32_t ntables, const uint8_t* proof, size_t proof_len, char* err,
                    size_t errcap);
+/* WEAKER, for tests and for proofs of a subsystem made by ola_prove with fewer tables: verifies an ordered subset of the
+ * tables.  A cross-table lookup with a side outside the subset cannot be balanced and is NOT checked (its Z columns are
+ * still checked against the table's own constraints), so acceptance says nothing about those lookups. */
+int ola_verify_subsystem_cfg(int hasher, const int* table_ids, uint32_t ntables, const uint8_t* proof, size_t proof_len, char* err,
+                             size_t errcap);
 /* ---- trace-generation tail: what sits directly in front of prove_with_traces ----
  * generate_poseidon_trace (circuits/src/generation/poseidon.rs:5-130) together with the per-round states the executor
  * records for each hash (core/src/util/poseidon_utils.rs:289-420): `inputs` [nrows][12] permutation inputs and `filters`

@@ -8,7 +8,7 @@ from ._lib import OlaError, load  # noqa: F401
 from .context import Context  # noqa: F401
 from .pcs import MerkleCap, PolynomialBatch  # noqa: F401
 from . import cfft, generation, hashing, prover  # noqa: F401
-from .prover import BLAKE3, POSEIDON, prove_with_device_traces, prove_with_traces, verify_proof  # noqa: F401
+from .prover import BLAKE3, POSEIDON, prove_with_device_traces, prove_with_traces, verify_proof, verify_subsystem_proof  # noqa: F401
 
 GOLDILOCKS_P = 0xFFFFFFFF00000001
 COSET_SHIFT = 7

@@ -72,9 +72,14 @@ SIGNATURES = {
     "ola_compress_challenge": (_int, [ctypes.POINTER(_vp), _u32, _sz, ctypes.POINTER(_u64)]),
     "ola_verify": (_int, [ctypes.POINTER(_int), _u32, _vp, _sz, ctypes.c_char_p, _sz]),
     "ola_verify_cfg": (_int, [_int, ctypes.POINTER(_int), _u32, _vp, _sz, ctypes.c_char_p, _sz]),
+    "ola_verify_subsystem_cfg": (_int, [_int, ctypes.POINTER(_int), _u32, _vp, _sz, ctypes.c_char_p, _sz]),
     "ola_set_hasher": (_int, [_vp, _int]),
     "ola_get_hasher": (_int, [_vp]),
     "ola_set_comm": (_int, [_vp, _int, _int, _vp, _vp, _vp]),
+    "ola_prove_session_begin": (_int, [_vp, ctypes.POINTER(_int), _u32, ctypes.POINTER(_vp), _int, ctypes.POINTER(_u32), _vp, _int, ctypes.POINTER(_vp)]),
+    "ola_prove_session_next": (_int, [_vp, _vp]),
+    "ola_prove_session_supply": (_int, [_vp, _vp, _sz]),
+    "ola_prove_session_finish": (_int, [_vp, _vp, _sz, ctypes.POINTER(_sz)]),
     "ola_nccl_unique_id": (_int, [ctypes.c_char_p, _vp]),
     "ola_set_comm_nccl": (_int, [_vp, ctypes.c_char_p, _int, _int, _vp]),
     "ola_comm_bytes": (_u64, [_vp]),

@@ -435,6 +435,119 @@ int ola_prove(ola_ctx* ctx, const int* table_ids, uint32_t ntables, const uint64
         memcpy(proof_out, bytes.data(), bytes.size());
     });
 }
+// ---- ola_prove with the transcript kept by the caller (ola_prove_session_*) ----
+}  // extern "C"
+#include <thread>
+struct ola_session {
+    ola_ctx* ctx = nullptr;
+    ola::stark::TranscriptHost host;
+    std::thread worker;
+    std::vector<uint8_t> proof;
+    int rc = OLA_OK;
+    std::string error;
+    bool finished = false;  // the worker has published DONE / FAILED
+    std::vector<int> ids;
+    std::vector<const uint64_t*> traces;
+    std::vector<uint32_t> log_ns;
+    std::vector<uint64_t> cc;
+    bool on_device = false;
+    ola::stark::Config cfg;
+};
+extern "C" {
+int ola_prove_session_begin(ola_ctx* ctx, const int* table_ids, uint32_t ntables, const uint64_t* const* traces, int on_device, const uint32_t* log_ns,
+                            const uint64_t* compress_challenges, int check_quotient_degree, ola_session** out) {
+    if (!ctx || !table_ids || !traces || !log_ns || !out) return OLA_ERR_INVALID_ARG;
+    if (ctx->world != 1) {
+        ctx->last_error = "ola_prove_session_*: single-GPU contexts only";
+        return OLA_ERR_INVALID_ARG;
+    }
+    ola_session* s = nullptr;
+    try {
+        s = new ola_session();
+    } catch (...) {
+        return OLA_ERR_OOM;
+    }
+    s->ctx = ctx;
+    s->ids.assign(table_ids, table_ids + ntables);
+    s->traces.assign(traces, traces + ntables);
+    s->log_ns.assign(log_ns, log_ns + ntables);
+    if (compress_challenges) s->cc.assign(compress_challenges, compress_challenges + ntables);
+    s->on_device = on_device != 0;
+    s->cfg.check_quotient_degree = check_quotient_degree != 0;
+    s->worker = std::thread([s] {
+        using TH = ola::stark::TranscriptHost;
+        TH::Kind last = TH::DONE;
+        s->rc = guarded(s->ctx, [&] { s->proof = ola::stark::prove_all(s->ctx, s->ids, s->traces, s->on_device, s->log_ns, s->cc, s->cfg, &s->host); });
+        if (s->rc != OLA_OK) {
+            s->error = s->ctx->last_error;
+            last = TH::FAILED;
+        }
+        std::lock_guard<std::mutex> lk(s->host.m);
+        s->host.pending = last;
+        s->finished = true;
+        s->host.cv.notify_all();
+    });
+    *out = s;
+    return OLA_OK;
+}
+int ola_prove_session_next(ola_session* s, ola_transcript_event* ev) {
+    if (!s || !ev) return OLA_ERR_INVALID_ARG;
+    using TH = ola::stark::TranscriptHost;
+    std::unique_lock<std::mutex> lk(s->host.m);
+    // the previous OBSERVE / COMPACT event is consumed by asking for the next one
+    if (!s->finished && s->host.pending != TH::NONE && s->host.pending != TH::CHALLENGE && s->host.delivered) {
+        s->host.consumed = true;
+        s->host.delivered = false;
+        s->host.pending = TH::NONE;
+        s->host.cv.notify_all();
+    }
+    if (!s->finished && s->host.pending == TH::CHALLENGE && s->host.delivered) return OLA_ERR_INVALID_ARG;  // supply the challenges first
+    s->host.cv.wait(lk, [&] { return s->finished || (s->host.pending != TH::NONE && !s->host.delivered); });
+    ev->kind = (int)s->host.pending;
+    ev->stage = s->host.stage;
+    ev->table = s->host.table;
+    ev->elems = s->host.pending == TH::OBSERVE ? s->host.elems.data() : nullptr;
+    ev->count = s->host.pending == TH::OBSERVE ? s->host.elems.size() : (s->host.pending == TH::CHALLENGE ? s->host.want : 0);
+    if (!s->finished) s->host.delivered = true;
+    return s->host.pending == TH::FAILED ? s->rc : OLA_OK;
+}
+int ola_prove_session_supply(ola_session* s, const uint64_t* challenges, size_t count) {
+    if (!s || (!challenges && count)) return OLA_ERR_INVALID_ARG;
+    using TH = ola::stark::TranscriptHost;
+    std::lock_guard<std::mutex> lk(s->host.m);
+    if (s->finished || s->host.pending != TH::CHALLENGE || !s->host.delivered || count != s->host.want) return OLA_ERR_INVALID_ARG;
+    s->host.elems.assign(challenges, challenges + count);
+    s->host.supplied = true;
+    s->host.delivered = false;
+    s->host.pending = TH::NONE;
+    s->host.cv.notify_all();
+    return OLA_OK;
+}
+int ola_prove_session_finish(ola_session* s, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+    if (!s) return OLA_ERR_INVALID_ARG;
+    {
+        std::lock_guard<std::mutex> lk(s->host.m);
+        if (!s->finished) {  // abandoned: unblock the prover, which unwinds
+            s->host.abort = true;
+            s->host.cv.notify_all();
+        }
+    }
+    if (s->worker.joinable()) s->worker.join();
+    int rc = s->rc;
+    if (rc == OLA_OK && s->host.abort) rc = OLA_ERR_INVALID_ARG;
+    if (proof_len) *proof_len = s->proof.size();
+    if (rc == OLA_OK) {
+        if (!proof_out || s->proof.size() > proof_cap)
+            rc = OLA_ERR_INVALID_ARG;
+        else
+            memcpy(proof_out, s->proof.data(), s->proof.size());
+    } else if (!s->error.empty()) {
+        s->ctx->last_error = s->error;
+    }
+    delete s;
+    return rc;
+}
+
 int ola_set_comm(ola_ctx* ctx, int rank, int world, ola_allgather_fn allgather, ola_allreduce_u64_fn allreduce_sum, void* user) {
     if (!ctx) return OLA_ERR_INVALID_ARG;
     return guarded(ctx, [&] {
@@ -456,10 +569,7 @@ int ola_set_hasher(ola_ctx* ctx, int hasher) {
     });
 }
 int ola_get_hasher(const ola_ctx* ctx) { return ctx ? ctx->hasher : OLA_ERR_INVALID_ARG; }
-int ola_verify(const int* table_ids, uint32_t ntables, const uint8_t* proof, size_t proof_len, char* err, size_t errcap) {
-    return ola_verify_cfg(OLA_HASH_POSEIDON, table_ids, ntables, proof, proof_len, err, errcap);
-}
-int ola_verify_cfg(int hasher, const int* table_ids, uint32_t ntables, const uint8_t* proof, size_t proof_len, char* err, size_t errcap) {
+static int verify_impl(int hasher, const int* table_ids, uint32_t ntables, const uint8_t* proof, size_t proof_len, char* err, size_t errcap, bool full_system) {
     auto put = [&](const std::string& m) {
         if (err && errcap) snprintf(err, errcap, "%s", m.c_str());
     };
@@ -469,6 +579,17 @@ int ola_verify_cfg(int hasher, const int* table_ids, uint32_t ntables, const uin
     }
     if (hasher != OLA_HASH_POSEIDON && hasher != OLA_HASH_BLAKE3) {
         put("unknown hasher id");
+        return OLA_ERR_INVALID_ARG;
+    }
+    for (uint32_t i = 0; i < ntables; ++i)
+        if (table_ids[i] < 0 || table_ids[i] >= ola::stark::T_NUM || (i > 0 && table_ids[i] <= table_ids[i - 1])) {
+            put("table ids must be distinct ids of the Table enum in ascending order");
+            return OLA_ERR_INVALID_ARG;
+        }
+    if (full_system && ntables != (uint32_t)ola::stark::T_NUM) {
+        // verify_proof (verifier.rs:32-212) is fixed at the 12 tables and checks every cross-table lookup; a subset would
+        // silently skip the lookups whose other side is missing
+        put("verify_proof covers the full 12-table system (ids 0..11); ola_verify_subsystem_cfg verifies a subsystem, with weaker guarantees");
         return OLA_ERR_INVALID_ARG;
     }
     try {
@@ -482,6 +603,15 @@ int ola_verify_cfg(int hasher, const int* table_ids, uint32_t ntables, const uin
         put("unknown error");
         return OLA_ERR_INTERNAL;
     }
+}
+int ola_verify(const int* table_ids, uint32_t ntables, const uint8_t* proof, size_t proof_len, char* err, size_t errcap) {
+    return verify_impl(OLA_HASH_POSEIDON, table_ids, ntables, proof, proof_len, err, errcap, true);
+}
+int ola_verify_cfg(int hasher, const int* table_ids, uint32_t ntables, const uint8_t* proof, size_t proof_len, char* err, size_t errcap) {
+    return verify_impl(hasher, table_ids, ntables, proof, proof_len, err, errcap, true);
+}
+int ola_verify_subsystem_cfg(int hasher, const int* table_ids, uint32_t ntables, const uint8_t* proof, size_t proof_len, char* err, size_t errcap) {
+    return verify_impl(hasher, table_ids, ntables, proof, proof_len, err, errcap, false);
 }
 // ---- trace-generation tail (generation.cu) ----
 int ola_generate_poseidon_trace(ola_ctx* ctx, const uint64_t* inputs, const uint64_t* filters, size_t nrows, uint32_t log_n, uint64_t* out,

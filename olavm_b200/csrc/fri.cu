@@ -274,6 +274,7 @@ stark::FriProof prove_openings(ola_ctx* ctx, const Instance& inst, const std::ve
     OLA_CHECK(inst.batches.size() <= 3 && !inst.batches.empty(), OLA_ERR_INTERNAL, "FRI instance: 1..3 opening batches supported");
     cudaStream_t st = ctx->stream;
 
+    ch.at(stark::STAGE_FRI_ALPHA);
     E alpha = ch.get_ext();
 
     // ---- polynomial list and per-batch alpha-power indices
@@ -409,8 +410,10 @@ stark::FriProof prove_openings(ola_ctx* ctx, const Instance& inst, const std::ve
             OLA_CUDA(cudaMemcpyAsync(cap.data(), ly->nodes.p + 4 * ncap, ncap * 32, cudaMemcpyDeviceToHost, st));
             OLA_CUDA(cudaStreamSynchronize(st));
         }
+        ch.at(stark::STAGE_FRI_LAYER_CAP);
         ch.observe_cap(cap);
         proof.commit_caps.push_back(cap);
+        ch.at(stark::STAGE_FRI_BETA);
         E beta = ch.get_ext();
         DevMem folded(2 * (m / arity));
         {
@@ -431,6 +434,7 @@ stark::FriProof prove_openings(ola_ctx* ctx, const Instance& inst, const std::ve
         std::vector<uint64_t> h(2 * m);
         OLA_CUDA(cudaMemcpyAsync(h.data(), coeffs.p, 2 * m * 8, cudaMemcpyDeviceToHost, st));
         OLA_CUDA(cudaStreamSynchronize(st));
+        ch.at(stark::STAGE_FRI_FINAL_POLY);
         for (size_t i = 0; i < m; ++i) {
             proof.final_poly.push_back(gl::make2(h[i], h[m + i]));
             ch.observe_ext(proof.final_poly.back());
@@ -438,6 +442,7 @@ stark::FriProof prove_openings(ola_ctx* ctx, const Instance& inst, const std::ve
     }
     // ---- proof of work
     {
+        ch.at(stark::STAGE_FRI_POW);
         stark::Hash h = ch.get_hash();
         DevMem d_best(1);
         unsigned long long init = ~0ULL;
@@ -459,7 +464,11 @@ stark::FriProof prove_openings(ola_ctx* ctx, const Instance& inst, const std::ve
     // ---- query phase (fri_prover_query_rounds, prover.rs:150-204): one batched gather per tree
     const int nq = (int)Config::num_queries;
     std::vector<uint32_t> idx(nq);
-    for (int q = 0; q < nq; ++q) idx[q] = (uint32_t)(ch.get_challenge() % L);
+    ch.at(stark::STAGE_FRI_QUERY_INDICES);
+    {
+        const std::vector<stark::F> qs = ch.get_challenges((size_t)nq);
+        for (int q = 0; q < nq; ++q) idx[q] = (uint32_t)(qs[q] % L);
+    }
     DevMem d_idx((nq + 1) / 2 + 1);
     OLA_CUDA(cudaMemcpyAsync(d_idx.p, idx.data(), nq * 4, cudaMemcpyHostToDevice, st));
     // output layout: per oracle [nq][ncols] rows then [nq][nsib][4] paths; per layer [nq][2*arity] then paths

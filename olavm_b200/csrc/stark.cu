@@ -751,6 +751,7 @@ static StarkProof prove_single_table(ola_ctx* ctx, const TableInfo& t, const Con
     uint32_t total_ar = 0;
     for (auto a : arities) total_ar += a;
     OLA_CHECK(total_ar <= degree_bits + Config::rate_bits - Config::cap_height, OLA_ERR_INVALID_ARG, "FRI total reduction arity is too large.");
+    ch.at(STAGE_TABLE_BEGIN);
     ch.compact();
 
     // permutation challenges and instances (get_n_grand_product_challenge_sets, get_permutation_batches)
@@ -830,8 +831,11 @@ static StarkProof prove_single_table(ola_ctx* ctx, const TableInfo& t, const Con
     StarkProof proof;
     proof.trace_cap = batch_cap(ctx, trace_commit);
     proof.zs_cap = batch_cap(ctx, zs_commit.b);
+    ch.at(STAGE_ZS_CAP);
     ch.observe_cap(proof.zs_cap);
-    const F alpha0 = ch.get_challenge(), alpha1 = ch.get_challenge();
+    ch.at(STAGE_ALPHAS);
+    const std::vector<F> alphas = ch.get_challenges(2);
+    const F alpha0 = alphas[0], alpha1 = alphas[1];
 
     // ---- compute_quotient_polys
     const int qdf = t.quotient_degree_factor();
@@ -914,8 +918,10 @@ static StarkProof prove_single_table(ola_ctx* ctx, const TableInfo& t, const Con
     BatchHolder q_commit;
     q_commit.b = commit(ctx, d_chunks.p, (size_t)2 * qdf, degree_bits, true);
     proof.quotient_cap = batch_cap(ctx, q_commit.b);
+    ch.at(STAGE_QUOTIENT_CAP);
     ch.observe_cap(proof.quotient_cap);
 
+    ch.at(STAGE_ZETA);
     const E zeta = ch.get_ext();
     const F g = gl::root_of_unity((int)degree_bits);
     {
@@ -934,6 +940,7 @@ static StarkProof prove_single_table(ola_ctx* ctx, const TableInfo& t, const Con
     for (auto& e : eval_batch_at(ctx, zs_commit.b, num_perm_zs, nzs - num_perm_zs, gl::make2(g_inv, 0))) os.ctl_zs_last.push_back(e.c0);
     os.quotient = eval_batch_at(ctx, q_commit.b, 0, (size_t)2 * qdf, zeta);
     // observe_openings(to_fri_openings) (proof.rs:248-283)
+    ch.at(STAGE_OPENINGS);
     for (auto& v : os.local_values) ch.observe_ext(v);
     for (auto& v : os.zs) ch.observe_ext(v);
     for (auto& v : os.quotient) ch.observe_ext(v);
@@ -959,7 +966,8 @@ static StarkProof prove_single_table(ola_ctx* ctx, const TableInfo& t, const Con
 
 // prove_with_traces (prover.rs:79-327) + Buffer::write_all_proof (serialization.rs:377-393)
 std::vector<uint8_t> prove_all(ola_ctx* ctx, const std::vector<int>& table_ids, const std::vector<const uint64_t*>& traces, bool on_device,
-                               const std::vector<uint32_t>& log_ns, const std::vector<uint64_t>& compress_challenges, const Config& cfg) {
+                               const std::vector<uint32_t>& log_ns, const std::vector<uint64_t>& compress_challenges, const Config& cfg,
+                               TranscriptHost* transcript_host) {
     System sys = make_system(table_ids);
     OLA_CHECK(compress_challenges.empty() || compress_challenges.size() == sys.tables.size(), OLA_ERR_INVALID_ARG, "one compress challenge per table");
     for (size_t i = 0; i < compress_challenges.size(); ++i)
@@ -969,7 +977,7 @@ std::vector<uint8_t> prove_all(ola_ctx* ctx, const std::vector<int>& table_ids, 
     OLA_CHECK(traces.size() == T && log_ns.size() == T, OLA_ERR_INVALID_ARG, "one trace per table");
     std::vector<std::unique_ptr<DevBuf>> d_vals(T);
     std::vector<std::unique_ptr<BatchHolder>> commits(T);
-    Challenger ch(ctx->hasher);
+    Challenger ch(ctx->hasher, transcript_host);
     // host traces: every table's upload is queued on the copy stream up front, so table i+1 crosses PCIe while table i is
     // being committed (LDE + Poseidon) on the context stream.  With several ranks each uploads 1/world of the columns
     // over its own PCIe link (into `slices`) and one all-gather over NVLink replicates the table.
@@ -1059,7 +1067,9 @@ std::vector<uint8_t> prove_all(ola_ctx* ctx, const std::vector<int>& table_ids, 
         OLA_CUDA(cudaStreamSynchronize(ctx->stream));  // the all-gathers have consumed the slices
         slices.clear();
     }
+    ch.at(STAGE_TRACE_CAPS);
     for (size_t i = 0; i < T; ++i) ch.observe_cap(batch_cap(ctx, commits[i]->b));
+    ch.at(STAGE_CTL_CHALLENGES);
     // cross_table_lookup_data: challenges, then Z instances per table in registry order
     std::vector<Challenge> ctl_ch;
     for (uint32_t k = 0; k < Config::num_challenges; ++k) {
@@ -1077,6 +1087,7 @@ std::vector<uint8_t> prove_all(ola_ctx* ctx, const std::vector<int>& table_ids, 
     w.raw_hashes = ctx->hasher == OLA_HASH_BLAKE3;
     w.u32((uint32_t)T);
     for (size_t i = 0; i < T; ++i) {
+        ch.table = sys.tables[i].id;
         StarkProof p = prove_single_table(ctx, sys.tables[i], cfg, d_vals[i]->p, log_ns[i], commits[i]->b, per_table[i], ch);
         w.proof(p);
         commits[i].reset();  // tables are proven sequentially: free this table's HBM before the next

@@ -5,6 +5,9 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <condition_variable>
+#include <mutex>
+#include <stdexcept>
 #include <string>
 #include <utility>
 #include <vector>
@@ -52,11 +55,81 @@ inline std::vector<uint32_t> fri_arities(uint32_t degree_bits) {
 // Generic over H: H::Permutation is the Poseidon permutation or Blake3Permutation (hash/blake3.rs:165-199), and
 // observe_hash absorbs hash.to_vec() -- 4 elements of a HashOut, 5 seven-byte elements of a BytesHash<32>
 // (challenger.rs:79-81, hash/hash_types.rs:142-152).
+// ---- an EXTERNAL transcript: the host application keeps its own Challenger (ola_prove_session_*) ----
+// The prover runs on a worker thread and, instead of hashing, hands every transcript operation to the API caller as an
+// event -- OBSERVE (elements to absorb, in order), CHALLENGE (n elements to squeeze), COMPACT (Challenger::compact) -- and
+// blocks until the caller has consumed it (and, for CHALLENGE, supplied the values).  Stage labels say which seam of
+// prove_with_traces / prove_single_table / fri_proof the event belongs to.
+enum TranscriptStage {
+    STAGE_TRACE_CAPS = 1,      // prover.rs:147-150: observe every table's trace cap
+    STAGE_CTL_CHALLENGES = 2,  // cross_table_lookup_data's beta / gamma pairs (prover.rs:152-158)
+    STAGE_TABLE_BEGIN = 3,     // prove_single_table: challenger.compact() + permutation challenges (prover.rs:344-372)
+    STAGE_ZS_CAP = 4,          // permutation / CTL Z commitment (prover.rs:411-413)
+    STAGE_ALPHAS = 5,          // get_n_challenges(num_challenges) (prover.rs:415)
+    STAGE_QUOTIENT_CAP = 6,    // prover.rs:489-491
+    STAGE_ZETA = 7,            // get_extension_challenge (prover.rs:493)
+    STAGE_OPENINGS = 8,        // observe_openings (prover.rs:530)
+    STAGE_FRI_ALPHA = 9,       // prove_openings: alpha (fri/oracle.rs:176)
+    STAGE_FRI_LAYER_CAP = 10,  // fri_committed_trees: layer cap (fri/prover.rs:94)
+    STAGE_FRI_BETA = 11,       // fri/prover.rs:96
+    STAGE_FRI_FINAL_POLY = 12, // fri/prover.rs:118
+    STAGE_FRI_POW = 13,        // fri_proof_of_work: challenger.get_hash() (fri/prover.rs:131)
+    STAGE_FRI_QUERY_INDICES = 14  // fri_prover_query_rounds (fri/prover.rs:157-160)
+};
+struct TranscriptHost {
+    enum Kind { NONE = 0, OBSERVE = 1, CHALLENGE = 2, COMPACT = 3, DONE = 4, FAILED = 5 };
+    std::mutex m;
+    std::condition_variable cv;
+    Kind pending = NONE;     // event published by the prover, not yet consumed by the caller
+    int stage = 0, table = -1;
+    std::vector<F> elems;    // OBSERVE: the elements; CHALLENGE: filled by the caller
+    size_t want = 0;         // CHALLENGE: how many
+    bool supplied = false, consumed = false, abort = false;
+    bool delivered = false;  // the caller has been handed the pending event (ola_prove_session_next)
+    struct Aborted {};
+    // prover side: publish an event and wait until the caller has dealt with it
+    void publish(Kind k, int stg, int tbl, std::vector<F>&& data, size_t n_want) {
+        std::unique_lock<std::mutex> lk(m);
+        pending = k;
+        stage = stg;
+        table = tbl;
+        elems = std::move(data);
+        want = n_want;
+        supplied = consumed = delivered = false;
+        cv.notify_all();
+        cv.wait(lk, [&] { return abort || (k == CHALLENGE ? supplied : consumed); });
+        if (abort) throw Aborted();
+        pending = NONE;
+    }
+};
+
 struct Challenger {
     F state[12];
     std::vector<F> in, out;
     int hasher;  // OLA_HASH_POSEIDON (0) / OLA_HASH_BLAKE3 (1)
-    explicit Challenger(int hasher_id = 0) : hasher(hasher_id) { memset(state, 0, sizeof(state)); }
+    TranscriptHost* host = nullptr;  // non-null: every operation is forwarded to the caller's Challenger instead
+    int stage = 0, table = -1;       // labels of the forwarded events
+    explicit Challenger(int hasher_id = 0, TranscriptHost* h = nullptr) : hasher(hasher_id), host(h) { memset(state, 0, sizeof(state)); }
+    void at(int stg) { stage = stg; }
+    void flush_to_host() {
+        if (!in.empty()) {
+            std::vector<F> data;
+            data.swap(in);
+            host->publish(TranscriptHost::OBSERVE, stage, table, std::move(data), 0);
+        }
+    }
+    std::vector<F> ask_host(size_t n) {
+        flush_to_host();
+        host->publish(TranscriptHost::CHALLENGE, stage, table, std::vector<F>(), n);
+        std::vector<F> r;
+        {
+            std::lock_guard<std::mutex> lk(host->m);
+            r = host->elems;
+        }
+        if (r.size() != n) throw std::runtime_error("transcript host supplied a wrong number of challenges");
+        for (auto& x : r) x = gl::canon(x);
+        return r;
+    }
     void duplexing() {
         for (size_t i = 0; i < in.size(); i++) state[i] = in[i];
         in.clear();
@@ -67,6 +140,10 @@ struct Challenger {
         out.assign(state, state + 8);
     }
     void observe(F x) {
+        if (host) {
+            in.push_back(gl::canon(x));  // buffered: forwarded as one OBSERVE event before the next challenge
+            return;
+        }
         out.clear();
         in.push_back(gl::canon(x));
         if (in.size() == 8) duplexing();
@@ -87,22 +164,44 @@ struct Challenger {
         }
     }
     F get_challenge() {
+        if (host) return ask_host(1)[0];
         if (!in.empty() || out.empty()) duplexing();
         F r = out.back();  // pops from the END (challenger.rs:97-99)
         out.pop_back();
         return r;
     }
+    std::vector<F> get_challenges(size_t n) {  // get_n_challenges (challenger.rs:101-103)
+        if (host) return ask_host(n);
+        std::vector<F> r;
+        for (size_t i = 0; i < n; i++) r.push_back(get_challenge());
+        return r;
+    }
     E get_ext() {
+        if (host) {
+            std::vector<F> r = ask_host(2);
+            return gl::make2(r[0], r[1]);
+        }
         F a = get_challenge();
         F b = get_challenge();
         return gl::make2(a, b);
     }
     Hash get_hash() {
+        if (host) {
+            std::vector<F> r = ask_host(4);
+            Hash hh;
+            for (int i = 0; i < 4; i++) hh.e[i] = r[i];
+            return hh;
+        }
         Hash h;
         for (int i = 0; i < 4; i++) h.e[i] = get_challenge();
         return h;
     }
     void compact() {
+        if (host) {
+            flush_to_host();
+            host->publish(TranscriptHost::COMPACT, stage, table, std::vector<F>(), 0);
+            return;
+        }
         if (!in.empty()) duplexing();
         out.clear();
     }

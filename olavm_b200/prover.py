@@ -100,14 +100,80 @@ def prove_with_device_traces(ctx, table_ids, device_ptrs, log_ns, check_quotient
     return out[: n.value].tobytes()
 
 
-def verify_proof(table_ids, proof, hasher=0):
-    """`circuits::stark::verifier::verify_proof` over `Buffer::read_all_proof`'s bytes (verifier.rs:32-212,
-    serialization.rs:395-411) -> (accepted, reason).  Host code: needs the library but no GPU.
-    hasher: POSEIDON (PoseidonGoldilocksConfig) or BLAKE3 (Blake3GoldilocksConfig), the config the proof was made under."""
+class TranscriptEvent(ctypes.Structure):
+    """ola_transcript_event of include/ola_gpu.h."""
+    _fields_ = [("kind", ctypes.c_int), ("stage", ctypes.c_int), ("table", ctypes.c_int), ("elems", ctypes.POINTER(ctypes.c_uint64)), ("count", ctypes.c_size_t)]
+
+
+EV_OBSERVE, EV_CHALLENGE, EV_COMPACT, EV_DONE, EV_FAILED = 1, 2, 3, 4, 5
+
+
+def prove_with_challenger(ctx, table_ids, trace_poly_values, challenger, check_quotient_degree=True, max_bytes=1 << 26, compress_challenges=None,
+                          log=None):
+    """prove_with_traces with the Fiat-Shamir transcript kept by the CALLER (ola_prove_session_*): `challenger` is the host's
+    own plonky2 `Challenger` -- any object with observe_elements(list of int), get_n_challenges(n) -> list of int and
+    compact().  The library reports every transcript operation as an event; `log`, if a list, receives (kind, stage, table,
+    count) per event.  With a faithful Challenger the bytes equal prove_with_traces'."""
+    k = len(table_ids)
+    trs = [np.ascontiguousarray(t, dtype=np.uint64) for t in trace_poly_values]
+    for tid, t in zip(table_ids, trs):
+        if t.ndim != 2 or t.shape[0] != table_columns(ctx, tid) or t.shape[1] & (t.shape[1] - 1):
+            raise ValueError(f"bad trace for table {tid}")
+    ids = (ctypes.c_int * k)(*[int(x) for x in table_ids])
+    ptrs = (ctypes.c_void_p * k)(*[t.ctypes.data for t in trs])
+    logs = (ctypes.c_uint32 * k)(*[int(t.shape[1]).bit_length() - 1 for t in trs])
+    cc = None
+    if compress_challenges is not None:
+        cc_arr = np.ascontiguousarray(compress_challenges, dtype=np.uint64)
+        cc = cc_arr.ctypes.data_as(ctypes.c_void_p)
+    sess = ctypes.c_void_p()
+    lib = ctx._lib
+    ctx.check(lib.ola_prove_session_begin(ctx.handle, ids, k, ptrs, 0, logs, cc, 1 if check_quotient_degree else 0, ctypes.byref(sess)))
+    ev = TranscriptEvent()
+    rc = 0
+    try:
+        while True:
+            rc = lib.ola_prove_session_next(sess, ctypes.byref(ev))
+            if log is not None:
+                log.append((ev.kind, ev.stage, ev.table, int(ev.count)))
+            if rc != 0 or ev.kind in (EV_DONE, EV_FAILED):
+                break
+            if ev.kind == EV_OBSERVE:
+                challenger.observe_elements([int(ev.elems[i]) for i in range(ev.count)])
+            elif ev.kind == EV_CHALLENGE:
+                vals = np.array([int(x) for x in challenger.get_n_challenges(int(ev.count))], dtype=np.uint64)
+                r = lib.ola_prove_session_supply(sess, vals.ctypes.data_as(ctypes.c_void_p), vals.size)
+                if r != 0:
+                    raise _lib.OlaError(r, "ola_prove_session_supply")
+            elif ev.kind == EV_COMPACT:
+                challenger.compact()
+    finally:
+        out = np.empty(max_bytes, dtype=np.uint8)
+        n = ctypes.c_size_t(0)
+        frc = lib.ola_prove_session_finish(sess, out.ctypes.data_as(ctypes.c_void_p), max_bytes, ctypes.byref(n))
+    ctx.check(frc)
+    return out[: n.value].tobytes()
+
+
+def _verify(entry, table_ids, proof, hasher):
     lib = _lib.load()
     k = len(table_ids)
     ids = (ctypes.c_int * k)(*[int(x) for x in table_ids])
     buf = np.frombuffer(bytes(proof), dtype=np.uint8)
     err = ctypes.create_string_buffer(512)
-    rc = lib.ola_verify_cfg(int(hasher), ids, k, buf.ctypes.data_as(ctypes.c_void_p), buf.size, err, 512)
+    rc = getattr(lib, entry)(int(hasher), ids, k, buf.ctypes.data_as(ctypes.c_void_p), buf.size, err, 512)
     return rc == 0, err.value.decode()
+
+
+def verify_proof(table_ids, proof, hasher=0):
+    """`circuits::stark::verifier::verify_proof` over `Buffer::read_all_proof`'s bytes (verifier.rs:32-212,
+    serialization.rs:395-411) -> (accepted, reason).  Host code: needs the library but no GPU.  Like the reference's it is
+    fixed at the full 12-table system (table_ids = 0..11) and checks every cross-table lookup.
+    hasher: POSEIDON (PoseidonGoldilocksConfig) or BLAKE3 (Blake3GoldilocksConfig), the config the proof was made under."""
+    return _verify("ola_verify_cfg", table_ids, proof, hasher)
+
+
+def verify_subsystem_proof(table_ids, proof, hasher=0):
+    """WEAKER than verify_proof: verifies a proof of an ordered SUBSET of the tables (what prove_with_traces makes when given
+    fewer tables).  Lookups with a side outside the subset are not checked.  For tests of subsystems."""
+    return _verify("ola_verify_subsystem_cfg", table_ids, proof, hasher)

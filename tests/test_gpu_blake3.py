@@ -79,9 +79,9 @@ def test_proof_bytes_equal_oracle_and_verify(b3ctx, orc, seed, log_cmp):
     assert got == ref
     ok, msg = orc.stark_verify([CMP, RC], got, hasher_id=orc.BLAKE3)
     assert ok, msg
-    ok, msg = olavm_b200.verify_proof([CMP, RC], got, hasher=B3)
+    ok, msg = olavm_b200.verify_subsystem_proof([CMP, RC], got, hasher=B3)
     assert ok, msg
-    assert not olavm_b200.verify_proof([CMP, RC], got)[0]  # not a PoseidonGoldilocksConfig proof
+    assert not olavm_b200.verify_subsystem_proof([CMP, RC], got)[0]  # not a PoseidonGoldilocksConfig proof
 
 
 def test_hasher_switch_leaves_the_poseidon_path_unchanged(ctx, orc):

@@ -93,7 +93,7 @@ def test_cpu_table_real_trace(ctx, orc):
     assert got == orc.stark_prove([CPU, CMP, RC], [cpu_t, cmp_t, rc_t])
     ok, msg = orc.stark_verify([CPU, CMP, RC], got)
     assert ok, msg
-    ok, msg = olavm_b200.verify_proof([CPU, CMP, RC], got)
+    ok, msg = olavm_b200.verify_subsystem_proof([CPU, CMP, RC], got)
     assert ok, msg
     bad = cpu_t.copy()
     i_add = next(i for i, s in enumerate(steps) if s["op"] == "add")
@@ -120,13 +120,13 @@ def test_cpu_cmp_rangecheck_real_program(ctx, orc):
     assert got == orc.stark_prove([CPU, CMP, RC], [cpu_t, cmp_t, rc_t])
     ok, msg = orc.stark_verify([CPU, CMP, RC], got)
     assert ok, msg
-    ok, msg = olavm_b200.verify_proof([CPU, CMP, RC], got)
+    ok, msg = olavm_b200.verify_subsystem_proof([CPU, CMP, RC], got)
     assert ok, msg
     # a Cmp row withheld: the proof is produced (each table is consistent) and both verifiers reject the lookup
     short = olavm_b200.prove_with_traces(ctx, [CPU, CMP, RC], [cpu_t, tracegen.cmp_trace(cmp_pairs[:-1], 6),
                                                                tracegen.rangecheck_trace(rc_cmp[:-1], cpu_vals=rc_cpu)])
     assert not orc.stark_verify([CPU, CMP, RC], short)[0]
-    assert not olavm_b200.verify_proof([CPU, CMP, RC], short)[0]
+    assert not olavm_b200.verify_subsystem_proof([CPU, CMP, RC], short)[0]
 
 
 def test_cpu_memory_cmp_rangecheck_real_program(ctx, orc):
@@ -142,7 +142,7 @@ def test_cpu_memory_cmp_rangecheck_real_program(ctx, orc):
     assert got == orc.stark_prove(ids, [cpu_t, mem_t, cmp_t, rc_t])
     ok, msg = orc.stark_verify(ids, got)
     assert ok, msg
-    ok, msg = olavm_b200.verify_proof(ids, got)
+    ok, msg = olavm_b200.verify_subsystem_proof(ids, got)
     assert ok, msg
     m = mem_t.copy()
     k = next(i for i in range(1, m.shape[1]) if m[23, i] == 1 and m[17, i] == 0)
@@ -168,7 +168,7 @@ def test_real_program_run_systems(ctx, orc):
     assert got == orc.stark_prove(ids, traces, compress_challenges=cc)
     ok, msg = orc.stark_verify(ids, got)
     assert ok, msg
-    ok, msg = olavm_b200.verify_proof(ids, got)
+    ok, msg = olavm_b200.verify_subsystem_proof(ids, got)
     assert ok, msg
     ids, traces, cc = tracegen.real_program_system(orc, np.random.default_rng(6), n_iter=300, linear=True, cpu_log=13, mem_log_n=11,
                                                    cmp_log=10, prog_log=13)
@@ -180,7 +180,7 @@ def test_real_program_run_systems(ctx, orc):
     assert len(ids) == 11
     got = olavm_b200.prove_with_traces(ctx, ids, traces, compress_challenges=cc)
     assert got == orc.stark_prove(ids, traces, compress_challenges=cc)
-    ok, msg = olavm_b200.verify_proof(ids, got)
+    ok, msg = olavm_b200.verify_subsystem_proof(ids, got)
     assert ok, msg
 
 
@@ -195,7 +195,7 @@ def test_reference_programs_run_and_prove(ctx, orc, name):
                                                  init_tape=tracegen.CONTEXT_TAPE if name == "context_fetch" else ())
     got = olavm_b200.prove_with_traces(ctx, ids, traces, compress_challenges=cc)
     assert got == orc.stark_prove(ids, traces, compress_challenges=cc)
-    ok, msg = olavm_b200.verify_proof(ids, got)
+    ok, msg = olavm_b200.verify_subsystem_proof(ids, got)
     assert ok, msg
 
 
@@ -250,7 +250,7 @@ def test_valid_trace_of_each_remaining_table(ctx, orc, name):
     assert got == ref
     ok, msg = orc.stark_verify(ids, got)
     assert ok, msg
-    ok, msg = olavm_b200.verify_proof(ids, got)  # product prover -> product verifier
+    ok, msg = olavm_b200.verify_subsystem_proof(ids, got)  # product prover -> product verifier
     assert ok, msg
 
 
@@ -280,7 +280,7 @@ def test_five_table_hash_system(ctx, orc):
     assert got == ref
     ok, msg = orc.stark_verify(ids, got)
     assert ok, msg
-    ok, msg = olavm_b200.verify_proof(ids, got)
+    ok, msg = olavm_b200.verify_subsystem_proof(ids, got)
     assert ok, msg
     # a broken Poseidon round witness is caught by the device-side degree check like the reference's panic
     bad = [t.copy() for t in traces]
@@ -376,7 +376,7 @@ def test_storage_opcodes_real_run(ctx, orc):
     assert ids == [0, 1, 3, 4, 5, 7, 10]
     got = olavm_b200.prove_with_traces(ctx, ids, traces, compress_challenges=cc)
     assert got == orc.stark_prove(ids, traces, compress_challenges=cc)
-    ok, msg = olavm_b200.verify_proof(ids, got)
+    ok, msg = olavm_b200.verify_subsystem_proof(ids, got)
     assert ok, msg
 
 
@@ -389,7 +389,7 @@ def test_reference_prophet_programs_run_and_prove(ctx, orc, name):
     ids, traces, cc, _ = _reference_run(orc, name)
     got = olavm_b200.prove_with_traces(ctx, ids, traces, compress_challenges=cc)
     assert got == orc.stark_prove(ids, traces, compress_challenges=cc)
-    ok, msg = olavm_b200.verify_proof(ids, got)
+    ok, msg = olavm_b200.verify_subsystem_proof(ids, got)
     assert ok, msg
 
 
@@ -410,3 +410,60 @@ def test_fib_loop_2p18_proof_bytes_equal_oracle(ctx, orc):
     assert ok, msg
     ref = orc.stark_prove(ids, traces, check_degree=True, compress_challenges=cc)
     assert len(got) == len(ref) and got == ref
+
+
+class _HostChallenger:
+    """plonky2's Challenger (iop/challenger.rs:18-162) as the HOST application would keep it: duplex sponge over the Poseidon
+    permutation, rate 8, overwrite mode, output popped from the end.  Written against the Rust, independent of the library."""
+
+    def __init__(self, permute):
+        self.permute, self.state, self.inp, self.out = permute, [0] * 12, [], []
+
+    def _duplex(self):
+        for i, x in enumerate(self.inp):
+            self.state[i] = x
+        self.inp = []
+        self.state = [int(x) for x in self.permute(np.array(self.state, dtype=np.uint64))]
+        self.out = self.state[:8]
+
+    def observe_elements(self, xs):
+        for x in xs:
+            self.out = []
+            self.inp.append(int(x) % P)
+            if len(self.inp) == 8:
+                self._duplex()
+
+    def get_n_challenges(self, n):
+        r = []
+        for _ in range(n):
+            if self.inp or not self.out:
+                self._duplex()
+            r.append(self.out.pop())
+        return r
+
+    def compact(self):
+        if self.inp:
+            self._duplex()
+        self.out = []
+
+
+def test_prove_session_with_the_hosts_own_challenger(ctx, orc):
+    """ola_prove_session_*: the transcript is kept by the caller.  With plonky2's Challenger on the host side the bytes equal
+    ola_prove's; every seam of prove_single_table / fri_proof shows up as a stage; a host that perturbs its transcript gets a
+    different (still self-consistent) proof."""
+    cmp_t, rc_t = _valid_cmp_rc(5, 6)
+    single = olavm_b200.prove_with_traces(ctx, [CMP, RC], [cmp_t, rc_t])
+    log = []
+    got = olavm_b200.prover.prove_with_challenger(ctx, [CMP, RC], [cmp_t, rc_t], _HostChallenger(orc.poseidon), log=log)
+    assert got == single
+    stages = {stage for kind, stage, table, count in log}
+    assert stages >= set(range(1, 15)) - {3} or stages >= set(range(1, 15))   # every stage label occurs (3 only with compact events)
+    assert any(kind == 3 for kind, *_ in log) and log[-1][0] == 4
+    assert {table for _, stage, table, _ in log if stage >= 4} == {CMP, RC}
+    # a different transcript (one extra absorbed element up front) still yields a proof, and a different one
+    ch = _HostChallenger(orc.poseidon)
+    ch.observe_elements([42])
+    other = olavm_b200.prover.prove_with_challenger(ctx, [CMP, RC], [cmp_t, rc_t], ch)
+    assert other != single and len(other) == len(single)
+    # the context is usable afterwards
+    assert olavm_b200.prove_with_traces(ctx, [CMP, RC], [cmp_t, rc_t]) == single

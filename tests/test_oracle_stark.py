@@ -501,7 +501,7 @@ def test_storage_opcodes_run_and_prove(orc, storage_run):
     assert ok, msg
     import olavm_b200
 
-    ok, msg = olavm_b200.verify_proof(ids, proof)
+    ok, msg = olavm_b200.verify_subsystem_proof(ids, proof)
     assert ok, msg
 
 

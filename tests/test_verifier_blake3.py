@@ -24,11 +24,11 @@ def cmp_rc_b3(orc):
 
 def test_accepts_blake3_proof_and_only_under_blake3(orc, cmp_rc_b3):
     cmp_t, rc_t, proof = cmp_rc_b3
-    ok, msg = olavm_b200.verify_proof([CMP, RC], proof, hasher=B3)
+    ok, msg = olavm_b200.verify_subsystem_proof([CMP, RC], proof, hasher=B3)
     assert ok, msg
-    assert not olavm_b200.verify_proof([CMP, RC], proof)[0]  # Poseidon verifier
-    assert not olavm_b200.verify_proof([CMP, RC], orc.stark_prove([CMP, RC], [cmp_t, rc_t]), hasher=B3)[0]
-    assert not olavm_b200.verify_proof([CMP, RC], proof, hasher=7)[0]  # unknown hasher id
+    assert not olavm_b200.verify_subsystem_proof([CMP, RC], proof)[0]  # Poseidon verifier
+    assert not olavm_b200.verify_subsystem_proof([CMP, RC], orc.stark_prove([CMP, RC], [cmp_t, rc_t]), hasher=B3)[0]
+    assert not olavm_b200.verify_subsystem_proof([CMP, RC], proof, hasher=7)[0]  # unknown hasher id
 
 
 def test_decides_like_the_oracle_verifier_on_tampered_blake3_proofs(orc, cmp_rc_b3):
@@ -39,12 +39,12 @@ def test_decides_like_the_oracle_verifier_on_tampered_blake3_proofs(orc, cmp_rc_
     for off in offsets:
         bad = bytearray(proof)
         bad[off] ^= 1
-        ok, _ = olavm_b200.verify_proof([CMP, RC], bytes(bad), hasher=B3)
+        ok, _ = olavm_b200.verify_subsystem_proof([CMP, RC], bytes(bad), hasher=B3)
         ok_ref, _ = orc.stark_verify([CMP, RC], bytes(bad), hasher_id=orc.BLAKE3)
         assert ok == ok_ref, off
         rejected += not ok
     assert rejected >= len(offsets) - 2
-    assert not olavm_b200.verify_proof([CMP, RC], proof[:-1], hasher=B3)[0]
+    assert not olavm_b200.verify_subsystem_proof([CMP, RC], proof[:-1], hasher=B3)[0]
 
 
 @pytest.mark.parametrize("name", ["poseidon", "tape"])
@@ -52,7 +52,7 @@ def test_accepts_valid_trace_of_a_wide_and_a_narrow_table(orc, name):
     # the Poseidon table's rows are 134 columns = 1072 bytes: two BLAKE3 chunks and a parent node per leaf
     ids, traces, cc = _valid_single(orc, name)
     proof = orc.stark_prove(ids, traces, True, compress_challenges=cc, hasher_id=orc.BLAKE3)
-    ok, msg = olavm_b200.verify_proof(ids, proof, hasher=B3)
+    ok, msg = olavm_b200.verify_subsystem_proof(ids, proof, hasher=B3)
     assert ok, msg
     assert orc.stark_verify(ids, proof, hasher_id=orc.BLAKE3)[0]
 
@@ -64,6 +64,6 @@ def test_accepts_the_reference_storage_program_under_blake3(orc):
 
     ids, traces, cc, _ = _reference_run(orc, "storage")
     proof = orc.stark_prove(ids, traces, compress_challenges=cc, hasher_id=orc.BLAKE3)
-    ok, msg = olavm_b200.verify_proof(ids, proof, hasher=B3)
+    ok, msg = olavm_b200.verify_subsystem_proof(ids, proof, hasher=B3)
     assert ok, msg
-    assert not olavm_b200.verify_proof(ids, proof)[0]
+    assert not olavm_b200.verify_subsystem_proof(ids, proof)[0]

@@ -12,6 +12,8 @@
 // and reuses the batched kernels of ntt.cu unchanged.  The transcript stays on the host (stark_types.h);
 // only caps, the final polynomial, the PoW nonce and the opened rows ever cross PCIe.
 #include "fri.h"
+
+#include "air/air_common.cuh"
 #include "hasher.h"
 
 #include "batch.h"
@@ -31,26 +33,34 @@ struct ComposeDesc {
     const uint64_t* ptr[MAX_POLYS];  // coefficient column of polynomial p
     int16_t idx[3][MAX_POLYS];       // position of p inside batch b, or -1
 };
-__global__ void compose_kernel(const ComposeDesc* __restrict__ d, int npolys, size_t n, const uint64_t* __restrict__ apow /* [2][maxlen] */,
-                               size_t apow_stride, uint64_t* __restrict__ comp /* [3][2][n] */) {
+// Each batch's sum is accumulated UNREDUCED (air::Wide: 6 instructions per multiply-accumulate instead of the 28 of a reduced
+// multiply + add) and reduced once per output: the kernel reads every committed coefficient once and was bound by the
+// integer pipes, not by HBM (10.6 ms for 10.4 GB before).
+__global__ void __launch_bounds__(128) compose_kernel(const ComposeDesc* __restrict__ d, int npolys, size_t n, const uint64_t* __restrict__ apow /* [2][maxlen] */,
+                                                      size_t apow_stride, uint64_t* __restrict__ comp /* [3][2][n] */) {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    gl::ext2 acc[3] = {gl::make2(0, 0), gl::make2(0, 0), gl::make2(0, 0)};
+    air::Wide acc[3][2];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        acc[b][0].clear();
+        acc[b][1].clear();
+    }
     for (int p = 0; p < npolys; ++p) {
-        uint64_t v = d->ptr[p][j];
+        const uint64_t v = __ldg(d->ptr[p] + j);
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
-            int k = d->idx[b][p];
+            const int k = d->idx[b][p];
             if (k >= 0) {
-                gl::ext2 a = gl::make2(__ldg(apow + k), __ldg(apow + apow_stride + k));
-                acc[b] = gl::add(acc[b], gl::mul(a, v));
+                acc[b][0].mac(v, __ldg(apow + k));
+                acc[b][1].mac(v, __ldg(apow + apow_stride + k));
             }
         }
     }
 #pragma unroll
     for (int b = 0; b < 3; ++b) {
-        comp[((size_t)b * 2) * n + j] = acc[b].c0;
-        comp[((size_t)b * 2 + 1) * n + j] = acc[b].c1;
+        comp[((size_t)b * 2) * n + j] = acc[b][0].reduce();
+        comp[((size_t)b * 2 + 1) * n + j] = acc[b][1].reduce();
     }
 }
 
@@ -95,20 +105,47 @@ __global__ void __launch_bounds__(QL_THREADS) ql_chunk_kernel(const uint64_t* __
     }
 }
 // phase 2: carry T_s = S[(s+1)*CHUNK] = C_{s+1} + z^CHUNK * T_{s+1}; one thread per batch
-__global__ void ql_carry_kernel(uint64_t* chunkv, size_t nchunks, QlParams p) {
-    int b = threadIdx.x;
-    if (b >= p.nbatches) return;
+// carries between chunks: T_s = sum_{u > s} C_u zc^(u - s - 1) (zc = z^CHUNK), written over C_s.  One CTA per batch: every
+// thread owns a run of consecutive chunks, the runs are combined by a suffix scan over the affine maps
+// carry -> A + M carry (A = the run's own Horner value, M = zc^run length), then each thread replays its run with the carry
+// that enters it.  (A single thread per batch walking all chunks took 0.7 ms per 2^22-row table: pure latency.)
+static constexpr int QLC_THREADS = 1024;
+__global__ void __launch_bounds__(QLC_THREADS) ql_carry_kernel(uint64_t* chunkv, size_t nchunks, QlParams p) {
+    __shared__ gl::ext2 sm[QLC_THREADS], sa[QLC_THREADS];
+    const int b = blockIdx.x, t = threadIdx.x;
     uint64_t* c0 = chunkv + ((size_t)b * 2) * nchunks;
     uint64_t* c1 = c0 + nchunks;
-    gl::ext2 carry = gl::make2(0, 0);
-    for (size_t s = nchunks; s-- > 0;) {
-        gl::ext2 cs = gl::make2(c0[s], c1[s]);
+    const gl::ext2 zc = p.zchunk[b];
+    const size_t per = (nchunks + QLC_THREADS - 1) / QLC_THREADS;
+    const size_t lo = (size_t)t * per < nchunks ? (size_t)t * per : nchunks, hi = lo + per < nchunks ? lo + per : nchunks;
+    gl::ext2 A = gl::make2(0, 0), M = gl::make2(1, 0);
+    for (size_t s = hi; s-- > lo;) {
+        A = gl::add(gl::make2(c0[s], c1[s]), gl::mul(zc, A));
+        M = gl::mul(M, zc);
+    }
+    sm[t] = M;
+    sa[t] = A;
+    __syncthreads();
+    // inclusive suffix scan: (M, A)[t] <- composition of the runs t, t + 1, ... (the lower run is applied last)
+    for (int d = 1; d < QLC_THREADS; d <<= 1) {
+        gl::ext2 m = sm[t], a = sa[t];
+        if (t + d < QLC_THREADS) {
+            a = gl::add(a, gl::mul(m, sa[t + d]));
+            m = gl::mul(m, sm[t + d]);
+        }
+        __syncthreads();
+        sm[t] = m;
+        sa[t] = a;
+        __syncthreads();
+    }
+    gl::ext2 carry = t + 1 < QLC_THREADS ? sa[t + 1] : gl::make2(0, 0);  // what the runs above hand down (they start from 0)
+    for (size_t s = hi; s-- > lo;) {
+        const gl::ext2 cs = gl::make2(c0[s], c1[s]);
         c0[s] = carry.c0;  // overwrite C_s with T_s
         c1[s] = carry.c1;
-        carry = gl::add(cs, gl::mul(p.zchunk[b], carry));
+        carry = gl::add(cs, gl::mul(zc, carry));
     }
 }
-// phase 3: in-chunk suffix scan with the carry, emit final[m] = sum_b w_b S_b[m]
 __global__ void __launch_bounds__(QL_THREADS) ql_emit_kernel(const uint64_t* __restrict__ comp, size_t n, QlParams p, const uint64_t* __restrict__ carry,
                                                           size_t nchunks, uint64_t* __restrict__ final_poly /* [2][n] */) {
     __shared__ gl::ext2 sh[QL_THREADS + 1];
@@ -220,13 +257,19 @@ __global__ void gather_query_rows_kernel(const uint64_t* __restrict__ m, size_t 
     out[i] = (leaf >= leaf_lo && leaf - leaf_lo < stride) ? m[c * stride + (leaf - leaf_lo)] : 0;
 }
 // FRI layer leaf (arity ext values interleaved) at idx[q] >> shift: out[q][2*e + comp]
+// (vals = the layer values of leaves [leaf_lo, leaf_lo + nleaves_local), planes `len` apart; leaves of other ranks -> 0)
 __global__ void gather_query_ext_kernel(const uint64_t* __restrict__ vals, size_t len, int arity, const uint32_t* __restrict__ idx, int shift, int nq,
-                                        uint64_t* __restrict__ out) {
+                                        size_t leaf_lo, size_t nleaves_local, uint64_t* __restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)nq * arity * 2) return;
     size_t q = i / (2 * arity), r = i % (2 * arity);
     size_t e = r / 2, comp = r % 2;
-    out[i] = vals[comp * len + (size_t)(idx[q] >> shift) * arity + e];
+    size_t leaf = idx[q] >> shift;
+    if (leaf < leaf_lo || leaf - leaf_lo >= nleaves_local) {
+        out[i] = 0;
+        return;
+    }
+    out[i] = vals[comp * len + (leaf - leaf_lo) * arity + e];
 }
 // Merkle paths: out[q][j][w] = nodes[(((nleaves + leaf) >> j) ^ 1) * 4 + w], leaf = idx[q] >> shift
 // (nodes = the heap-ordered subtree over leaves [leaf_lo, leaf_lo + nleaves); paths stop at the cap, inside the subtree)
@@ -335,7 +378,7 @@ stark::FriProof prove_openings(ola_ctx* ctx, const Instance& inst, const std::ve
     check_launch("ql_chunk_kernel");
     {
         Launch lz(ctx, "fri_divide_carry");
-        ql_carry_kernel<<<1, 32, 0, st>>>(d_chunk.p, nchunks, qp);
+        ql_carry_kernel<<<(unsigned)qp.nbatches, QLC_THREADS, 0, st>>>(d_chunk.p, nchunks, qp);
     }
     check_launch("ql_carry_kernel");
     {
@@ -348,7 +391,7 @@ stark::FriProof prove_openings(ola_ctx* ctx, const Instance& inst, const std::ve
     // ---- commit phase (fri_committed_trees, prover.rs:72-121)
     struct Layer {
         DevMem vals, nodes;  // nodes: heap-ordered tree over leaves [leaf_lo, leaf_lo + nloc)
-        size_t len = 0, nloc = 0, leaf_lo = 0;
+        size_t len = 0, len_loc = 0, nloc = 0, leaf_lo = 0;  // vals: [2][len_loc], the values of this rank's leaves
         bool sharded = false;
     };
     std::vector<std::unique_ptr<Layer>> layers;
@@ -363,40 +406,48 @@ stark::FriProof prove_openings(ola_ctx* ctx, const Instance& inst, const std::ve
         std::unique_ptr<Layer> ly(new Layer());
         const uint32_t mbits = (uint32_t)__builtin_ctzll(m);
         ly->len = m << Config::rate_bits;
-        ly->vals.alloc(2 * ly->len);
+        const size_t nleaves = ly->len / arity;
+        const size_t ncap = (size_t)1 << Config::cap_height;
+        OLA_CHECK(nleaves >= ncap, OLA_ERR_INTERNAL, "FRI layer smaller than the Merkle cap");
+        // Multi-GPU: a large layer is sharded by leaf range = LDE cosets: rank r evaluates cosets [r 8 / world, ...) of the
+        // layer polynomial, hashes those leaves and reduces the ncap / world cap subtrees above them; one all-gather
+        // assembles the cap, and query openings are answered by the owner of the leaf.  Small layers are replicated.
+        // (OLA_FRI_SHARD_MIN_LEAVES lowers the threshold so that tests reach the sharded path with small tables)
+        const char* env_min = getenv("OLA_FRI_SHARD_MIN_LEAVES");
+        const size_t shard_min = env_min ? (size_t)atoll(env_min) : ((size_t)1 << 14);
+        const int ncosets = 1 << Config::rate_bits;
+        ly->sharded = ctx->world > 1 && nleaves >= shard_min && nleaves >= ncap * (size_t)ctx->world && ncap % (size_t)ctx->world == 0 &&
+                      ncosets % ctx->world == 0 && (m % (size_t)arity) == 0;
+        ly->nloc = ly->sharded ? nleaves / (size_t)ctx->world : nleaves;
+        ly->leaf_lo = ly->sharded ? (size_t)ctx->rank * ly->nloc : 0;
+        ly->len_loc = ly->sharded ? ly->len / (size_t)ctx->world : ly->len;
+        const size_t ncap_loc = ly->sharded ? ncap / (size_t)ctx->world : ncap;
+        ly->vals.alloc(2 * ly->len_loc);
         {
             ntt::FwdDesc d;
             d.src = coeffs.p;
             d.src_col_stride = m;
             d.dst = ly->vals.p;
-            d.dst_col_stride = ly->len;
+            d.dst_col_stride = ly->len_loc;
             d.dst_coset_stride = m;
             d.ncols = 2;
             d.log_n = (int)mbits;
             d.coset_bits = (int)Config::rate_bits;
+            if (ly->sharded) {
+                d.coset_count = ncosets / ctx->world;
+                d.coset_first = ctx->rank * d.coset_count;
+            }
             d.shift = shift;
             d.tag_strided = "fri_lde_strided";
             d.tag_contig = "fri_lde_contig";
             ntt::forward(ctx, d);
         }
-        const size_t nleaves = ly->len / arity;
-        const size_t ncap = (size_t)1 << Config::cap_height;
-        OLA_CHECK(nleaves >= ncap, OLA_ERR_INTERNAL, "FRI layer smaller than the Merkle cap");
-        // Multi-GPU: a large layer's tree is sharded by leaf range (rank r hashes leaves [r nleaves / world, ...) and reduces
-        // the ncap / world cap subtrees above them; one all-gather assembles the cap); small layers are replicated.
-        // (OLA_FRI_SHARD_MIN_LEAVES lowers the threshold so that tests reach the sharded path with small tables)
-        const char* env_min = getenv("OLA_FRI_SHARD_MIN_LEAVES");
-        const size_t shard_min = env_min ? (size_t)atoll(env_min) : ((size_t)1 << 14);
-        ly->sharded = ctx->world > 1 && nleaves >= shard_min && nleaves >= ncap * (size_t)ctx->world && ncap % (size_t)ctx->world == 0;
-        ly->nloc = ly->sharded ? nleaves / (size_t)ctx->world : nleaves;
-        ly->leaf_lo = ly->sharded ? (size_t)ctx->rank * ly->nloc : 0;
-        const size_t ncap_loc = ly->sharded ? ncap / (size_t)ctx->world : ncap;
         ly->nodes.alloc(2 * ly->nloc * 4);
         if (ctx->hasher == OLA_HASH_BLAKE3) {
-            blake3::fri_leaves(ctx, ly->vals.p, ly->len, arity, ly->leaf_lo, ly->nloc, ly->nodes.p + 4 * ly->nloc);
+            blake3::fri_leaves(ctx, ly->vals.p, ly->len_loc, arity, 0, ly->nloc, ly->nodes.p + 4 * ly->nloc);
         } else {
             Launch lz(ctx, "fri_leaves");
-            fri_leaves_kernel<<<(unsigned)((ly->nloc + 127) / 128), 128, 0, st>>>(ly->vals.p, ly->len, arity, ly->leaf_lo, ly->nloc, ly->nodes.p + 4 * ly->nloc);
+            fri_leaves_kernel<<<(unsigned)((ly->nloc + 127) / 128), 128, 0, st>>>(ly->vals.p, ly->len_loc, arity, 0, ly->nloc, ly->nodes.p + 4 * ly->nloc);
         }
         check_launch("fri_leaves_kernel");
         hasher::merkle_levels(ctx, ly->nodes.p, ly->nloc, ncap_loc);
@@ -481,8 +532,7 @@ stark::FriProof prove_openings(ola_ctx* ctx, const Instance& inst, const std::ve
         off_paths[o] = total;
         total += (size_t)nq * nsib0 * 4;
     }
-    // the layers' Merkle paths come next (owner-answered like the oracle openings when a layer's tree is sharded), the
-    // layers' rows last (the layer values are replicated: every rank reads them locally)
+    // the layers' rows and Merkle paths follow: owner-answered like the oracle openings when the layer is sharded
     std::vector<size_t> off_lrows(layers.size()), off_lpaths(layers.size());
     std::vector<int> lshift(layers.size()), lnsib(layers.size());
     {
@@ -493,15 +543,13 @@ stark::FriProof prove_openings(ola_ctx* ctx, const Instance& inst, const std::ve
             bits -= arities[li];
             lshift[li] = sh;
             lnsib[li] = (int)bits - (int)Config::cap_height;
+            off_lrows[li] = total;
+            total += (size_t)nq * 2 * (1 << arities[li]);
             off_lpaths[li] = total;
             total += (size_t)nq * lnsib[li] * 4;
         }
     }
     const size_t exchanged_words = total;
-    for (size_t li = 0; li < layers.size(); ++li) {
-        off_lrows[li] = total;
-        total += (size_t)nq * 2 * (1 << arities[li]);
-    }
     DevMem d_out(total);
     if (ctx->world > 1) OLA_CUDA(cudaMemsetAsync(d_out.p, 0, total * 8, st));
     bool sharded = false;
@@ -525,14 +573,15 @@ stark::FriProof prove_openings(ola_ctx* ctx, const Instance& inst, const std::ve
     for (size_t li = 0; li < layers.size(); ++li) {
         const int arity = 1 << arities[li];
         size_t cnt = (size_t)nq * 2 * arity;
+        // the owner of the leaf answers; a replicated layer is answered by rank 0 alone when the buffer is exchanged
+        const bool answer = layers[li]->sharded || !sharded || ctx->rank == 0;
+        if (!answer) continue;
         {
             Launch lz(ctx, "fri_query_rows");
-            gather_query_ext_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(layers[li]->vals.p, layers[li]->len, arity, (const uint32_t*)d_idx.p, lshift[li],
-                                                                                nq, d_out.p + off_lrows[li]);
+            gather_query_ext_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(layers[li]->vals.p, layers[li]->len_loc, arity, (const uint32_t*)d_idx.p, lshift[li],
+                                                                                nq, layers[li]->leaf_lo, layers[li]->nloc, d_out.p + off_lrows[li]);
         }
-        // paths: the owner of the leaf answers; a replicated layer is answered by rank 0 alone when the buffer is exchanged
-        const bool answer = layers[li]->sharded || !sharded || ctx->rank == 0;
-        if (lnsib[li] > 0 && answer) {
+        if (lnsib[li] > 0) {
             Launch lz(ctx, "fri_query_paths");
             size_t pc = (size_t)nq * lnsib[li] * 4;
             gather_query_paths_kernel<<<(unsigned)((pc + 127) / 128), 128, 0, st>>>(layers[li]->nodes.p, layers[li]->nloc, (const uint32_t*)d_idx.p, lshift[li], nq,

@@ -20,6 +20,7 @@ typedef int (*CommDestroy_t)(void*);
 typedef const char* (*GetErrorString_t)(int);
 typedef int (*AllGather_t)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef int (*AllReduce_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*CommSplit_t)(void*, int, int, void**, void*);
 enum { kUint8 = 1, kUint64 = 5, kSum = 0 };  // ncclDataType_t / ncclRedOp_t values (nccl.h)
 
 struct Api {
@@ -30,6 +31,7 @@ struct Api {
     GetErrorString_t error_string = nullptr;
     AllGather_t all_gather = nullptr;
     AllReduce_t all_reduce = nullptr;
+    CommSplit_t comm_split = nullptr;  // optional (NCCL >= 2.18)
 };
 
 static bool load_api(const char* path, Api& api, std::string& err) {
@@ -52,6 +54,7 @@ static bool load_api(const char* path, Api& api, std::string& err) {
     api.error_string = (GetErrorString_t)dlsym(h, "ncclGetErrorString");
     api.all_gather = (AllGather_t)dlsym(h, "ncclAllGather");
     api.all_reduce = (AllReduce_t)dlsym(h, "ncclAllReduce");
+    api.comm_split = (CommSplit_t)dlsym(h, "ncclCommSplit");
     if (!api.get_unique_id || !api.comm_init_rank || !api.comm_destroy || !api.all_gather || !api.all_reduce) {
         err = "libnccl lacks a required symbol";
         return false;
@@ -62,6 +65,8 @@ static bool load_api(const char* path, Api& api, std::string& err) {
 struct Comm {
     Api api;
     void* comm = nullptr;
+    void* comm2 = nullptr;  // a second communicator over the same ranks, for collectives on the copy stream that overlap
+                            // the proving stream's (collectives of ONE communicator are serialised by NCCL)
 };
 
 static int cb_allgather(void* user, const void* send, void* recv, size_t bytes_per_rank, void* stream) {
@@ -73,9 +78,23 @@ static int cb_allreduce(void* user, void* buf, size_t count, void* stream) {
     return c->api.all_reduce(buf, buf, count, kUint64, kSum, c->comm, (cudaStream_t)stream);
 }
 
+// all-gather on the second communicator, on `stream`; false when there is none (the caller falls back to the first)
+bool allgather_side(ola_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank, cudaStream_t stream) {
+    Comm* c = (Comm*)ctx->nccl_state;
+    if (!c || !c->comm2) return false;
+    ctx->comm_bytes += bytes_per_rank * (size_t)ctx->world;
+    if (c->api.all_gather(send, recv, bytes_per_rank, kUint8, c->comm2, stream) != 0) throw ola::Error(OLA_ERR_INTERNAL, "ncclAllGather (side communicator) failed");
+    return true;
+}
+bool has_side_comm(const ola_ctx* ctx) {
+    const Comm* c = (const Comm*)ctx->nccl_state;
+    return c && c->comm2;
+}
+
 void release(ola_ctx* ctx) {
     Comm* c = (Comm*)ctx->nccl_state;
     if (!c) return;
+    if (c->comm2) c->api.comm_destroy(c->comm2);
     if (c->comm) c->api.comm_destroy(c->comm);
     delete c;
     ctx->nccl_state = nullptr;
@@ -117,6 +136,11 @@ int ola_set_comm_nccl(ola_ctx* ctx, const char* libnccl_path, int rank, int worl
             std::string m = std::string("ncclCommInitRank: ") + (c->api.error_string ? c->api.error_string(rc) : "error");
             delete c;
             throw ola::Error(OLA_ERR_INTERNAL, m);
+        }
+        // OLA_NCCL_SIDE_COMM=0 disables the second communicator (no overlap of the trace all-gathers with the commits)
+        const char* side = getenv("OLA_NCCL_SIDE_COMM");
+        if (world > 1 && c->api.comm_split && !(side && side[0] == '0')) {
+            if (c->api.comm_split(c->comm, 0, rank, &c->comm2, nullptr) != 0) c->comm2 = nullptr;
         }
         ctx->nccl_state = c;
         ctx->rank = rank;

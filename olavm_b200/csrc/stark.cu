@@ -25,6 +25,12 @@
 #include "verify.h"
 
 namespace ola {
+namespace nccl {
+bool allgather_side(ola_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank, cudaStream_t stream);
+bool has_side_comm(const ola_ctx* ctx);
+}  // namespace nccl
+// batch.cu
+__global__ void canon_copy_kernel(uint64_t* dst, const uint64_t* src, size_t n);
 namespace stark {
 
 using air::Consumer;
@@ -460,22 +466,28 @@ __global__ void nonzero_kernel(const uint64_t* __restrict__ data, size_t col_str
 static constexpr int EV_RUN = 16, EV_THREADS = 256, EV_CHUNK = EV_RUN * EV_THREADS;
 struct EvParams {
     gl::ext2 z;
-    gl::ext2 zr[8];  // z^(RUN * 2^k)
+    gl::ext2 zk[EV_RUN];  // z^k, k < RUN
+    gl::ext2 zr[8];       // z^(RUN * 2^k)
 };
+// A thread's run is a dot product of RUN base-field coefficients with the powers z^k: accumulated unreduced (air::Wide, two
+// multiply-accumulates per coefficient) instead of RUN dependent extension-field Horner steps.
 __global__ void __launch_bounds__(EV_THREADS) eval_partial_kernel(const uint64_t* __restrict__ coeffs, size_t n, EvParams p, uint64_t* __restrict__ partial /* [ncols][nchunks][2] */,
                                                                size_t nchunks) {
     __shared__ gl::ext2 sh[EV_THREADS];
     const uint64_t* c = coeffs + (size_t)blockIdx.y * n;
     const int t = threadIdx.x;
     size_t start = (size_t)blockIdx.x * EV_CHUNK + (size_t)t * EV_RUN;
-    gl::ext2 acc = gl::make2(0, 0);
-    for (int k = EV_RUN - 1; k >= 0; --k) {
-        size_t j = start + k;
-        uint64_t v = j < n ? c[j] : 0;
-        acc = gl::mul(acc, p.z);
-        acc.c0 = gl::add(acc.c0, v);
+    air::Wide a0, a1;
+    a0.clear();
+    a1.clear();
+#pragma unroll
+    for (int k = 0; k < EV_RUN; ++k) {
+        const size_t j = start + k;
+        const uint64_t v = j < n ? __ldg(c + j) : 0;
+        a0.mac(v, p.zk[k].c0);
+        a1.mac(v, p.zk[k].c1);
     }
-    sh[t] = acc;
+    sh[t] = gl::make2(a0.reduce(), a1.reduce());
     __syncthreads();
     for (int k = 0; (1 << k) < EV_THREADS; ++k) {
         gl::ext2 v = sh[t];
@@ -498,6 +510,13 @@ static std::vector<E> eval_batch_at(ola_ctx* ctx, const ola_batch* b, size_t fir
     const size_t nchunks = (n + EV_CHUNK - 1) / EV_CHUNK;
     EvParams p;
     p.z = z;
+    {
+        E zk = gl::make2(1, 0);
+        for (int k = 0; k < EV_RUN; ++k) {
+            p.zk[k] = zk;
+            zk = gl::mul(zk, z);
+        }
+    }
     E zr = gl::pow(z, (uint64_t)EV_RUN);
     for (int k = 0; k < 8; ++k) {
         p.zr[k] = zr;
@@ -983,6 +1002,7 @@ std::vector<uint8_t> prove_all(ola_ctx* ctx, const std::vector<int>& table_ids, 
     // over its own PCIe link (into `slices`) and one all-gather over NVLink replicates the table.
     const bool prefetch = !on_device;
     const bool sharded_upload = prefetch && ctx->world > 1;
+    const bool side_comm = sharded_upload && nccl::has_side_comm(ctx);
     std::vector<std::unique_ptr<DevBuf>> slices(T);
     // The 12 trace commitments are independent (their caps are observed afterwards, in table order), so they are
     // uploaded and committed smallest first: the first commit starts after a short copy and the big tables cross
@@ -1030,6 +1050,15 @@ std::vector<uint8_t> prove_all(ola_ctx* ctx, const std::vector<int>& table_ids, 
                 const size_t per = (cols + ctx->world - 1) / ctx->world;
                 const size_t lo = std::min(cols, (size_t)ctx->rank * per), hi = std::min(cols, lo + per);
                 if (hi > lo) OLA_CUDA(cudaMemcpyAsync(slices[i]->p, traces[i] + lo * n, (hi - lo) * n * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+                if (side_comm) {
+                    // canonicalise and replicate the table right behind its upload, on the copy stream and the second NCCL
+                    // communicator: these all-gathers overlap the commitments of the tables in front
+                    const unsigned blocks = (unsigned)std::min<size_t>((per * n + 255) / 256, 148 * 16);
+                    canon_copy_kernel<<<blocks, 256, 0, ctx->copy_stream>>>(slices[i]->p, slices[i]->p, per * n);
+                    check_launch("canon_copy_kernel");
+                    count_launch(ctx);
+                    nccl::allgather_side(ctx, slices[i]->p, d_vals[i]->p, per * n * 8, ctx->copy_stream);
+                }
             } else {
                 OLA_CUDA(cudaMemcpyAsync(d_vals[i]->p, traces[i], n * cols * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
             }
@@ -1042,7 +1071,9 @@ std::vector<uint8_t> prove_all(ola_ctx* ctx, const std::vector<int>& table_ids, 
             const size_t i = order[oi];
             const size_t n = (size_t)1 << log_ns[i], cnt = n * sys.tables[i].columns;
             OLA_CHECK(log_ns[i] + Config::rate_bits <= 32, OLA_ERR_INVALID_ARG, "trace too long for the field's two-adicity");
-            if (sharded_upload) {
+            if (sharded_upload && side_comm) {
+                OLA_CUDA(cudaStreamWaitEvent(ctx->stream, uploaded[i], 0));  // uploaded, canonicalised and all-gathered
+            } else if (sharded_upload) {
                 const size_t per = ((size_t)sys.tables[i].columns + ctx->world - 1) / ctx->world;
                 OLA_CUDA(cudaStreamWaitEvent(ctx->stream, uploaded[i], 0));
                 canon_copy(ctx, slices[i]->p, slices[i]->p, per * n);
@@ -1065,6 +1096,7 @@ std::vector<uint8_t> prove_all(ola_ctx* ctx, const std::vector<int>& table_ids, 
     }
     if (sharded_upload) {
         OLA_CUDA(cudaStreamSynchronize(ctx->stream));  // the all-gathers have consumed the slices
+        if (side_comm) OLA_CUDA(cudaStreamSynchronize(ctx->copy_stream));
         slices.clear();
     }
     ch.at(STAGE_TRACE_CAPS);

@@ -1,0 +1,183 @@
+/* A C host of libola_gpu.so (no Python, no ctypes): what a Rust / C maintainer's program does through the C ABI.
+ *   gcc -O2 -I include tests/c/abi_smoke.c -o abi_smoke -L olavm_b200 -lola_gpu -Wl,-rpath,$PWD/olavm_b200
+ * Without a GPU it checks that ola_gpu_init fails loudly (OLA_ERR_NO_DEVICE, no CPU fallback) and exercises the host-only
+ * entry points; with one it commits a batch, proves a Cmp + RangeCheck system built in C, verifies the proof with
+ * ola_verify_subsystem_cfg, and drives the same proof through ola_prove_session_* with a replaying transcript.
+ * Exit code 0 = every check passed; prints one line per check. */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "ola_gpu.h"
+
+#define P 0xFFFFFFFF00000001ULL
+static int failures = 0;
+#define CHECK(cond, what)                                   \
+    do {                                                    \
+        if (cond)                                           \
+            printf("ok   %s\n", what);                      \
+        else {                                              \
+            printf("FAIL %s\n", what);                      \
+            failures++;                                     \
+        }                                                   \
+    } while (0)
+
+static uint64_t mulmod(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) % P); }
+static uint64_t powmod(uint64_t b, uint64_t e) {
+    uint64_t r = 1;
+    while (e) {
+        if (e & 1) r = mulmod(r, b);
+        b = mulmod(b, b);
+        e >>= 1;
+    }
+    return r;
+}
+static uint64_t rng_state = 88172645463325252ULL;
+static uint64_t rnd(void) {
+    rng_state ^= rng_state << 13;
+    rng_state ^= rng_state >> 7;
+    rng_state ^= rng_state << 17;
+    return rng_state;
+}
+static int cmp_u64(const void* a, const void* b) {
+    uint64_t x = *(const uint64_t*)a, y = *(const uint64_t*)b;
+    return x < y ? -1 : x > y;
+}
+/* Halo2-style permuted (input, table) columns, circuits/src/stark/lookup.rs:68-131 (unused table values in ascending order) */
+static void permuted_cols(const uint64_t* in, const uint64_t* tab, size_t n, uint64_t* pin, uint64_t* ptab) {
+    uint64_t* st = malloc(n * 8);
+    unsigned char* used = calloc(n, 1);
+    memcpy(pin, in, n * 8);
+    memcpy(st, tab, n * 8);
+    qsort(pin, n, 8, cmp_u64);
+    qsort(st, n, 8, cmp_u64);
+    size_t j = 0;
+    unsigned char* matched = calloc(n, 1);
+    for (size_t i = 0; i < n; i++) { /* r-th occurrence of a value pairs with the r-th occurrence in the table */
+        while (j < n && st[j] < pin[i]) j++;
+        if (j < n && st[j] == pin[i] && !used[j]) {
+            ptab[i] = st[j];
+            used[j] = matched[i] = 1;
+            j++;
+        }
+    }
+    size_t u = 0;
+    for (size_t i = 0; i < n; i++)
+        if (!matched[i]) {
+            while (used[u]) u++;
+            ptab[i] = st[u];
+            used[u++] = 1;
+        }
+    free(st);
+    free(used);
+    free(matched);
+}
+
+int main(void) {
+    /* ---- host-only entry points: work without a GPU */
+    CHECK(ola_table_columns(0) == 94 && ola_table_columns(4) == 12 && ola_table_columns(12) < 0, "ola_table_columns");
+    uint64_t col[8] = {1, 2, 3, 4, 5, 6, 7, 8}, beta = 0;
+    const uint64_t* cols1[1] = {col};
+    CHECK(ola_compress_challenge(cols1, 1, 8, &beta) == OLA_OK && beta != 0 && beta < P, "ola_compress_challenge");
+    {
+        uint64_t lv[6] = {9, 5, 1, 4, 0, 1}, nv[6] = {0}, vals[8];
+        int kinds[8];
+        lv[4] = powmod(4, P - 2);
+        int k = ola_air_constraints(3, lv, nv, 0, vals, kinds, 8); /* Cmp row 9 >= 5, |diff| 4: all four constraints vanish */
+        CHECK(k == 4 && !vals[0] && !vals[1] && !vals[2] && !vals[3], "ola_air_constraints (Cmp row)");
+    }
+    char err[256];
+    int ids2[2] = {3, 4};
+    uint8_t junk[16] = {0};
+    CHECK(ola_verify(ids2, 2, junk, sizeof junk, err, sizeof err) == OLA_ERR_INVALID_ARG && strstr(err, "12-table"), "ola_verify refuses a subsystem");
+    CHECK(ola_verify_subsystem_cfg(OLA_HASH_POSEIDON, ids2, 2, junk, sizeof junk, err, sizeof err) == OLA_ERR_INVALID_ARG, "malformed proof rejected");
+
+    ola_ctx* ctx = NULL;
+    int rc = ola_gpu_init(0, &ctx);
+    if (rc != OLA_OK) {
+        CHECK(rc == OLA_ERR_NO_DEVICE && ctx == NULL, "no GPU: ola_gpu_init fails with OLA_ERR_NO_DEVICE (no CPU fallback)");
+        printf("%s\n", failures ? "FAILED" : "PASSED (host-only part; no GPU here)");
+        return failures != 0;
+    }
+    /* ---- commit: PolynomialBatch::from_values */
+    const uint32_t log_n = 10;
+    const size_t n = (size_t)1 << log_n, ncols = 5;
+    uint64_t* vals = malloc(ncols * n * 8);
+    for (size_t i = 0; i < ncols * n; i++) vals[i] = rnd() % P;
+    ola_batch* b = NULL;
+    uint64_t cap[16 * 4], cap2[16 * 4];
+    CHECK(ola_commit(ctx, vals, 0, ncols, log_n, 0, 3, 4, &b, cap) == OLA_OK && b, "ola_commit");
+    CHECK(ola_batch_get_cap(ctx, b, cap2) == OLA_OK && !memcmp(cap, cap2, sizeof cap), "ola_batch_get_cap");
+    uint64_t* co = malloc(ncols * n * 8);
+    CHECK(ola_batch_get_coeffs(ctx, b, co) == OLA_OK, "ola_batch_get_coeffs");
+    CHECK(ola_ntt_forward(ctx, co, 0, ncols, log_n) == OLA_OK && !memcmp(co, vals, ncols * n * 8), "coefficients evaluate back to the values");
+    uint64_t sib[32 * 4];
+    CHECK(ola_batch_prove_leaf(ctx, b, 77, sib) == (int)(log_n + 3 - 4), "ola_batch_prove_leaf");
+    CHECK(ola_batch_free(ctx, b) == OLA_OK, "ola_batch_free");
+
+    /* ---- a valid Cmp (2^5 rows) + RangeCheck (2^16 rows) system built in C */
+    const size_t nc = 32, nr = (size_t)1 << 16;
+    uint64_t* cmp = calloc(6 * nc, 8);
+    uint64_t* rc_t = calloc(12 * nr, 8);
+    for (size_t i = 0; i < nc; i++) cmp[2 * nc + i] = 1; /* padding rows: gte = 1 */
+    for (size_t i = 0; i < 20; i++) {
+        uint64_t a = rnd() & 0xFFFFFFFF, bb = rnd() & 0xFFFFFFFF, d = a >= bb ? a - bb : bb - a;
+        cmp[0 * nc + i] = a;
+        cmp[1 * nc + i] = bb;
+        cmp[2 * nc + i] = a >= bb;
+        cmp[3 * nc + i] = d;
+        cmp[4 * nc + i] = d ? powmod(d, P - 2) : 0;
+        cmp[5 * nc + i] = 1;
+        rc_t[3 * nr + i] = 1; /* cmp filter */
+        rc_t[4 * nr + i] = d;
+        rc_t[5 * nr + i] = d & 0xFFFF;
+        rc_t[6 * nr + i] = d >> 16;
+    }
+    for (size_t i = 0; i < nr; i++) rc_t[9 * nr + i] = i;
+    permuted_cols(rc_t + 5 * nr, rc_t + 9 * nr, nr, rc_t + 7 * nr, rc_t + 10 * nr);
+    permuted_cols(rc_t + 6 * nr, rc_t + 9 * nr, nr, rc_t + 8 * nr, rc_t + 11 * nr);
+    const uint64_t* traces[2] = {cmp, rc_t};
+    uint32_t logs[2] = {5, 16};
+    uint8_t* proof = malloc(1 << 22);
+    uint8_t* proof2 = malloc(1 << 22);
+    size_t plen = 0, plen2 = 0;
+    rc = ola_prove(ctx, ids2, 2, traces, 0, logs, NULL, 1, proof, 1 << 22, &plen);
+    if (rc != OLA_OK) printf("     ola_prove: %s\n", ola_gpu_last_error(ctx));
+    CHECK(rc == OLA_OK && plen > 1000, "ola_prove (Cmp + RangeCheck, quotient-degree check on)");
+    CHECK(ola_verify_subsystem_cfg(OLA_HASH_POSEIDON, ids2, 2, proof, plen, err, sizeof err) == OLA_OK, "ola_verify_subsystem_cfg accepts it");
+    proof[plen / 2] ^= 1;
+    CHECK(ola_verify_subsystem_cfg(OLA_HASH_POSEIDON, ids2, 2, proof, plen, err, sizeof err) != OLA_OK, "a flipped bit is rejected");
+    proof[plen / 2] ^= 1;
+    cmp[3 * nc + 2] ^= 1; /* a wrong |a - b| */
+    CHECK(ola_prove(ctx, ids2, 2, traces, 0, logs, NULL, 1, proof2, 1 << 22, &plen2) == OLA_ERR_QUOTIENT_DEGREE, "a broken trace fails with OLA_ERR_QUOTIENT_DEGREE");
+    cmp[3 * nc + 2] ^= 1;
+
+    /* ---- the same proof with the transcript on THIS side: a host challenger that absorbs nothing and answers every
+     * challenge request with fixed values still drives a complete session (the proof differs from ola_prove's) */
+    ola_session* s = NULL;
+    CHECK(ola_prove_session_begin(ctx, ids2, 2, traces, 0, logs, NULL, 1, &s) == OLA_OK && s, "ola_prove_session_begin");
+    ola_transcript_event ev;
+    size_t nobs = 0, nchal = 0, ncompact = 0;
+    int stages_seen = 0;
+    for (;;) {
+        rc = ola_prove_session_next(s, &ev);
+        if (rc != OLA_OK || ev.kind == OLA_EV_DONE || ev.kind == OLA_EV_FAILED) break;
+        stages_seen |= 1 << ev.stage;
+        if (ev.kind == OLA_EV_OBSERVE) nobs += ev.count;
+        if (ev.kind == OLA_EV_COMPACT) ncompact++;
+        if (ev.kind == OLA_EV_CHALLENGE) {
+            uint64_t c[64];
+            for (size_t i = 0; i < ev.count; i++) c[i] = 0x1234567 + 977 * (nchal + i); /* this host's "challenger" */
+            nchal += ev.count;
+            if (ola_prove_session_supply(s, c, ev.count) != OLA_OK) break;
+        }
+    }
+    CHECK(rc == OLA_OK && ev.kind == OLA_EV_DONE && nobs > 100 && nchal > 60 && ncompact == 2, "session events: observe / challenge / compact / done");
+    CHECK((stages_seen & 0x7FFE) == 0x7FFE, "every stage label 1..14 occurred");
+    CHECK(ola_prove_session_finish(s, proof2, 1 << 22, &plen2) == OLA_OK && plen2 == plen && memcmp(proof, proof2, plen) != 0, "session proof (other transcript, same shape)");
+    CHECK(ola_prove(ctx, ids2, 2, traces, 0, logs, NULL, 1, proof2, 1 << 22, &plen2) == OLA_OK && plen2 == plen && !memcmp(proof, proof2, plen), "context reusable; ola_prove deterministic");
+    CHECK(ola_gpu_kernel_launches(ctx) > 0, "kernels were launched");
+    ola_gpu_destroy(ctx);
+    printf("%s\n", failures ? "FAILED" : "PASSED");
+    return failures != 0;
+}

@@ -46,3 +46,17 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "libola_oracle" not in text, f
+
+
+def test_rust_ffi_block_is_current():
+    """integration/ola_gpu.rs (the extern "C" block a maintainer drops into the reference) is generated from the header."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    assert subprocess.call([sys.executable, os.path.join(root, "tools", "gen_rust_ffi.py"), "--check"]) == 0, "run tools/gen_rust_ffi.py"
+    rs = open(os.path.join(root, "integration", "ola_gpu.rs")).read()
+    from olavm_b200 import _lib
+
+    for name in _lib.header_symbols():
+        assert f"pub fn {name}(" in rs, name

@@ -403,7 +403,7 @@ def poseidon_table_config5(ctx, torch, dist, odist, world, rank, device, log_n):
     ctx.free(d_trace)
     if rank != 0:
         return None
-    ok, why = olavm_b200.verify_proof([5], proof)
+    ok, why = olavm_b200.verify_subsystem_proof([5], proof)   # one table of the system: the subsystem verifier
     dt = min(runs)
     return {"config": f"PoseidonStark table, 2^{log_n} rows x 134 columns, generated on the device, coset-sharded prove x{world} (BASELINE configs[4] stand-in)",
             "log_n": log_n, "seconds": dt, "seconds_runs": runs, "rows_per_s": n / dt, "generation_seconds": gen_s, "lde_bytes_per_gpu": 134 * n * 8 * 8 // world,
@@ -574,6 +574,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "coset-LDE forward network (lde_strided + lde_contig)", "achieved": ach,
                          "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None, "traffic": traffic,
+                         "traffic_source": "static: dram__bytes_read + dram__bytes_write of the two LDE launches from one ncu --set full capture (profiles/lde_traffic.json), not re-measured in this run",
                          "peak_source": how,
                          "note": "64-bit modular butterflies are INT-pipe bound on B200; see DESIGN.md section 5"},
             "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},

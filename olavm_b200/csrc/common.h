@@ -114,11 +114,13 @@ inline void ensure_copy_stream(ola_ctx* ctx) {
 inline void comm_allgather(ola_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank) {
     OLA_CHECK(ctx->comm_allgather != nullptr, OLA_ERR_INTERNAL, "no communicator");
     ctx->comm_bytes += bytes_per_rank * (size_t)ctx->world;
+    Launch lz(ctx, "comm_allgather");  // event-timed like a kernel: transfer time plus the wait for the slowest rank
     OLA_CHECK(ctx->comm_allgather(ctx->comm_user, send, recv, bytes_per_rank, (void*)ctx->stream) == 0, OLA_ERR_INTERNAL, "all-gather callback failed");
 }
 inline void comm_allreduce(ola_ctx* ctx, void* buf, size_t count) {
     OLA_CHECK(ctx->comm_allreduce != nullptr, OLA_ERR_INTERNAL, "no communicator");
     ctx->comm_bytes += count * 8;
+    Launch lz(ctx, "comm_allreduce");
     OLA_CHECK(ctx->comm_allreduce(ctx->comm_user, buf, count, (void*)ctx->stream) == 0, OLA_ERR_INTERNAL, "all-reduce callback failed");
 }
 inline void check_launch(const char* what) {

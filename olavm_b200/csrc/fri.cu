@@ -46,7 +46,29 @@ __global__ void __launch_bounds__(128) compose_kernel(const ComposeDesc* __restr
         acc[b][0].clear();
         acc[b][1].clear();
     }
-    for (int p = 0; p < npolys; ++p) {
+    // four polynomials per trip: the pointer fetch and the coefficient load of a polynomial are dependent loads, so the
+    // loads of a group are issued together before any of them is consumed (memory-level parallelism; the kernel streams
+    // every committed coefficient once)
+    int p = 0;
+    for (; p + 4 <= npolys; p += 4) {
+        const uint64_t* q0 = d->ptr[p];
+        const uint64_t* q1 = d->ptr[p + 1];
+        const uint64_t* q2 = d->ptr[p + 2];
+        const uint64_t* q3 = d->ptr[p + 3];
+        const uint64_t v[4] = {__ldg(q0 + j), __ldg(q1 + j), __ldg(q2 + j), __ldg(q3 + j)};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                const int k = d->idx[b][p + u];
+                if (k >= 0) {
+                    acc[b][0].mac(v[u], __ldg(apow + k));
+                    acc[b][1].mac(v[u], __ldg(apow + apow_stride + k));
+                }
+            }
+        }
+    }
+    for (; p < npolys; ++p) {
         const uint64_t v = __ldg(d->ptr[p] + j);
 #pragma unroll
         for (int b = 0; b < 3; ++b) {

@@ -136,23 +136,47 @@ __global__ void ctl_values_kernel(DevTables d, const uint64_t* __restrict__ trac
 }
 
 // permutation Z factors: prod_inst lhs / prod_inst rhs  (compute_permutation_z_poly, permutation.rs:129-160)
+// Each thread handles PV_ROWS rows a grid-stride apart (coalesced) and shares ONE field inversion between them
+// (Montgomery's trick: 3 (PV_ROWS - 1) multiplications instead of PV_ROWS - 1 further ~95-multiplication inversions).
+static constexpr int PV_ROWS = 4;
 __global__ void perm_values_kernel(DevTables d, const uint64_t* __restrict__ trace, size_t n, uint64_t* __restrict__ zs) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const DevPermBatch b = d.perm_batches[blockIdx.y];
-    Fp num(1), den(1);
-    for (int k = 0; k < b.inst_cnt; ++k) {
-        const DevPermInst in = d.perm_insts[b.inst_off + k];
-        Fp l(in.gamma), r(in.gamma), w(1), beta(in.beta);
-        for (int p = 0; p < in.pair_cnt; ++p) {
-            l += Fp(trace[(size_t)d.perm_pairs[2 * (in.pair_off + p)] * n + i]) * w;
-            r += Fp(trace[(size_t)d.perm_pairs[2 * (in.pair_off + p) + 1] * n + i]) * w;
-            w *= beta;
+    uint64_t num[PV_ROWS], den[PV_ROWS];
+#pragma unroll
+    for (int r = 0; r < PV_ROWS; ++r) {
+        const size_t i = i0 + (size_t)r * stride;
+        Fp nm(1), dn(1);
+        if (i < n) {
+            for (int k = 0; k < b.inst_cnt; ++k) {
+                const DevPermInst in = d.perm_insts[b.inst_off + k];
+                Fp l(in.gamma), rr(in.gamma), w(1), beta(in.beta);
+                for (int p = 0; p < in.pair_cnt; ++p) {
+                    l += Fp(trace[(size_t)d.perm_pairs[2 * (in.pair_off + p)] * n + i]) * w;
+                    rr += Fp(trace[(size_t)d.perm_pairs[2 * (in.pair_off + p) + 1] * n + i]) * w;
+                    w *= beta;
+                }
+                nm *= l;
+                dn *= rr;
+            }
         }
-        num *= l;
-        den *= r;
+        num[r] = nm.v;
+        den[r] = dn.v;
     }
-    zs[(size_t)blockIdx.y * n + i] = gl::mul(num.v, gl::inv(den.v));
+    // prefix products of the denominators, one inversion, then peel the inverses off from the back
+    uint64_t pre[PV_ROWS];
+    pre[0] = den[0];
+#pragma unroll
+    for (int r = 1; r < PV_ROWS; ++r) pre[r] = gl::mul(pre[r - 1], den[r]);
+    uint64_t inv = gl::inv(pre[PV_ROWS - 1]);
+#pragma unroll
+    for (int r = PV_ROWS - 1; r >= 0; --r) {
+        const uint64_t inv_r = r ? gl::mul(inv, pre[r - 1]) : inv;
+        if (r) inv = gl::mul(inv, den[r]);
+        const size_t i = i0 + (size_t)r * stride;
+        if (i < n) zs[(size_t)blockIdx.y * n + i] = gl::mul(num[r], inv_r);
+    }
 }
 
 // ---- prefix products over columns [ncols][n], in place.  exclusive: out[i] = prod_{j<i}; else prod_{j<=i}
@@ -828,7 +852,7 @@ static StarkProof prove_single_table(ola_ctx* ctx, const TableInfo& t, const Con
     if (num_perm_zs) {
         {
             Launch lz(ctx, "perm_values");
-            perm_values_kernel<<<dim3((unsigned)((n + 127) / 128), (unsigned)num_perm_zs), 128, 0, ctx->stream>>>(desc.t, d_trace, n, d_zs.p);
+            perm_values_kernel<<<dim3((unsigned)((n + 128 * PV_ROWS - 1) / (128 * PV_ROWS)), (unsigned)num_perm_zs), 128, 0, ctx->stream>>>(desc.t, d_trace, n, d_zs.p);
         }
         check_launch("perm_values_kernel");
         prefix_products(ctx, d_zs.p, num_perm_zs, n, true);

@@ -110,7 +110,10 @@ struct Challenger {
     TranscriptHost* host = nullptr;  // non-null: every operation is forwarded to the caller's Challenger instead
     int stage = 0, table = -1;       // labels of the forwarded events
     explicit Challenger(int hasher_id = 0, TranscriptHost* h = nullptr) : hasher(hasher_id), host(h) { memset(state, 0, sizeof(state)); }
-    void at(int stg) { stage = stg; }
+    void at(int stg) {
+        if (host && stg != stage) flush_to_host();  // elements observed under the previous label are delivered with it
+        stage = stg;
+    }
     void flush_to_host() {
         if (!in.empty()) {
             std::vector<F> data;

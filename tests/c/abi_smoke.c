@@ -148,9 +148,15 @@ int main(void) {
     proof[plen / 2] ^= 1;
     CHECK(ola_verify_subsystem_cfg(OLA_HASH_POSEIDON, ids2, 2, proof, plen, err, sizeof err) != OLA_OK, "a flipped bit is rejected");
     proof[plen / 2] ^= 1;
-    cmp[3 * nc + 2] ^= 1; /* a wrong |a - b| */
-    CHECK(ola_prove(ctx, ids2, 2, traces, 0, logs, NULL, 1, proof2, 1 << 22, &plen2) == OLA_ERR_QUOTIENT_DEGREE, "a broken trace fails with OLA_ERR_QUOTIENT_DEGREE");
+    cmp[3 * nc + 2] ^= 1; /* a wrong |a - b|: Cmp's quotient_degree_factor is a power of two, so -- as in the reference,
+                             prover.rs:463-478 -- no coefficient is left over for the prover's own degree check; the proof is
+                             made and the verifier rejects it */
+    rc = ola_prove(ctx, ids2, 2, traces, 0, logs, NULL, 1, proof2, 1 << 22, &plen2);
+    CHECK(rc == OLA_OK && ola_verify_subsystem_cfg(OLA_HASH_POSEIDON, ids2, 2, proof2, plen2, err, sizeof err) != OLA_OK, "the proof of a broken trace is rejected");
     cmp[3 * nc + 2] ^= 1;
+    cmp[5 * nc + 3] = 2; /* a filter that is neither 0 nor 1: partial_products asserts (cross_table_lookup.rs:305) */
+    CHECK(ola_prove(ctx, ids2, 2, traces, 0, logs, NULL, 1, proof2, 1 << 22, &plen2) == OLA_ERR_INVALID_ARG && strstr(ola_gpu_last_error(ctx), "Non-binary filter"), "a non-binary filter fails like the reference's assert");
+    cmp[5 * nc + 3] = 1;
 
     /* ---- the same proof with the transcript on THIS side: a host challenger that absorbs nothing and answers every
      * challenge request with fixed values still drives a complete session (the proof differs from ola_prove's) */

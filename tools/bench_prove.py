@@ -11,9 +11,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 import olavm_b200
-import tracegen
+from workload import tracegen
 
 BLAKE3 = "--blake3" in sys.argv  # C::Hasher = Blake3_256<32> (Blake3GoldilocksConfig) instead of Poseidon
 logs = [int(x) for x in sys.argv[1:] if not x.startswith("--")] or [16, 18, 20]

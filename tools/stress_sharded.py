@@ -8,9 +8,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 import olavm_b200
-import tracegen
+from workload import tracegen
 from olavm_b200 import dist as odist
 
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 5

@@ -54,6 +54,7 @@ struct PassArgs {
     int lazy_out;         // tile kernels: leave the outputs un-canonicalised (an intermediate pass; every pass accepts lazy input)
     size_t ncols;         // tile_contig: columns in the batch (the last column group may be partial)
     uint64_t scale;
+    int inv_roots;        // pw / brs hold the inverse roots (the shift form of the tile kernels needs to know which powers of two they are)
     uint64_t s_last[MAX_COSETS];  // per coset: (shift_i)^(2^(M-l)), or its inverse for the GS network
 };
 
@@ -481,6 +482,15 @@ static int tune_variant() {
     }();
     return v;
 }
+// OLA_NTT_SHIFT=0 runs the forward tile passes as radix-2 butterflies on canonical products (the round-1 form) instead
+// of the shift-twiddle form of ntt_shift.cuh (A/B measurements: profiles/r02m_*)
+static bool tune_shift() {
+    static bool v = [] {
+        const char* e = getenv("OLA_NTT_SHIFT");
+        return !(e && atoi(e) == 0);
+    }();
+    return v;
+}
 static bool tune_contig_c4() {
     static bool v = [] {
         const char* e = getenv("OLA_NTT_CONTIG_C4");
@@ -494,6 +504,15 @@ static void tile_optin(int max_optin) {
     OLA_CUDA(cudaFuncSetAttribute(tile::tile_strided<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     OLA_CUDA(cudaFuncSetAttribute(tile::tile_contig<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     OLA_CUDA(cudaFuncSetAttribute(tile::tile_contig<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+}
+template <typename G>
+static void tile_optin_shift(int max_optin, bool strided) {
+    if (strided) {
+        OLA_CUDA(cudaFuncSetAttribute(tile::tile_strided<G, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+        OLA_CUDA(cudaFuncSetAttribute(tile::tile_strided<G, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    }
+    OLA_CUDA(cudaFuncSetAttribute(tile::tile_contig<G, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    OLA_CUDA(cudaFuncSetAttribute(tile::tile_contig<G, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
 }
 template <typename G>
 static void tile_optin_contig(int max_optin) {
@@ -531,6 +550,19 @@ static void tile_optin_all(int max_optin) {
     tile_optin_contig<tile::Cfg<9, 2>>(max_optin);
     tile_optin_contig<tile::Cfg<10, 2>>(max_optin);
     tile_optin_contig<tile::Cfg<11, 2>>(max_optin);
+    tile_optin_shift<T6>(max_optin, true);
+    tile_optin_shift<T7>(max_optin, true);
+    tile_optin_shift<T8>(max_optin, true);
+    tile_optin_shift<T9>(max_optin, true);
+    tile_optin_shift<T10v2>(max_optin, true);
+    tile_optin_shift<T10c4>(max_optin, false);
+    tile_optin_shift<T11v2>(max_optin, true);
+    tile_optin_shift<tile::Cfg<6, 2>>(max_optin, false);
+    tile_optin_shift<tile::Cfg<7, 2>>(max_optin, false);
+    tile_optin_shift<tile::Cfg<8, 2>>(max_optin, false);
+    tile_optin_shift<tile::Cfg<9, 2>>(max_optin, false);
+    tile_optin_shift<tile::Cfg<10, 2>>(max_optin, false);
+    tile_optin_shift<tile::Cfg<11, 2>>(max_optin, false);
 }
 
 // tiles per CTA: long enough to amortise the twiddle prologue, short enough to keep >= ~8 waves of CTAs in flight
@@ -540,7 +572,7 @@ static size_t pick_tiles_per_cta(const ola_ctx* ctx, size_t total_tiles, size_t 
     t = std::min<size_t>(std::max<size_t>(t, 1), 32);
     return std::min(t, per_table);
 }
-template <typename G, bool GS>
+template <typename G, bool GS, int MODE = 0>
 static void tile_strided_launch(ola_ctx* ctx, const PassArgs& a, size_t ncols, int ncosets) {
     PassArgs b = a;
     b.ncols = ncols;
@@ -553,9 +585,9 @@ static void tile_strided_launch(ola_ctx* ctx, const PassArgs& a, size_t ncols, i
         chunks = (per_q + b.tiles_per_cta - 1) / b.tiles_per_cta;
     }
     const dim3 g((unsigned)ncosets, (unsigned)(nsub * chunks));
-    tile::tile_strided<G, GS><<<g, G::NT, G::SMEM, ctx->stream>>>(b);
+    tile::tile_strided<G, GS, MODE><<<g, G::NT, G::SMEM, ctx->stream>>>(b);
 }
-template <typename G, bool GS>
+template <typename G, bool GS, int MODE = 0>
 static void tile_contig_launch(ola_ctx* ctx, const PassArgs& a, size_t ncols, int ncosets) {
     PassArgs b = a;
     b.ncols = ncols;
@@ -568,24 +600,47 @@ static void tile_contig_launch(ola_ctx* ctx, const PassArgs& a, size_t ncols, in
         chunks = (groups + b.tiles_per_cta - 1) / b.tiles_per_cta;
     }
     const dim3 g((unsigned)nsub, (unsigned)chunks, (unsigned)ncosets);
-    tile::tile_contig<G, GS><<<g, G::NT, G::SMEM, ctx->stream>>>(b);
+    tile::tile_contig<G, GS, MODE><<<g, G::NT, G::SMEM, ctx->stream>>>(b);
+}
+// the default configurations also exist in the shift form (forward network; MODE 1 / 2 = forward / inverse roots)
+template <typename G, bool GS>
+static void tile_strided_launch_m(ola_ctx* ctx, const PassArgs& a, size_t ncols, int ncosets) {
+    if constexpr (!GS) {
+        if (tune_shift()) {
+            if (a.inv_roots) tile_strided_launch<G, false, 2>(ctx, a, ncols, ncosets);
+            else tile_strided_launch<G, false, 1>(ctx, a, ncols, ncosets);
+            return;
+        }
+    }
+    tile_strided_launch<G, GS>(ctx, a, ncols, ncosets);
+}
+template <typename G, bool GS>
+static void tile_contig_launch_m(ola_ctx* ctx, const PassArgs& a, size_t ncols, int ncosets) {
+    if constexpr (!GS) {
+        if (tune_shift()) {
+            if (a.inv_roots) tile_contig_launch<G, false, 2>(ctx, a, ncols, ncosets);
+            else tile_contig_launch<G, false, 1>(ctx, a, ncols, ncosets);
+            return;
+        }
+    }
+    tile_contig_launch<G, GS>(ctx, a, ncols, ncosets);
 }
 template <bool GS>
 static void tile_strided_dispatch(ola_ctx* ctx, const PassArgs& a, size_t ncols, int ncosets) {
     const int v = tune_variant();
     switch (a.l) {
-        case 6: tile_strided_launch<T6, GS>(ctx, a, ncols, ncosets); break;
-        case 7: tile_strided_launch<T7, GS>(ctx, a, ncols, ncosets); break;
-        case 8: tile_strided_launch<T8, GS>(ctx, a, ncols, ncosets); break;
-        case 9: tile_strided_launch<T9, GS>(ctx, a, ncols, ncosets); break;
+        case 6: tile_strided_launch_m<T6, GS>(ctx, a, ncols, ncosets); break;
+        case 7: tile_strided_launch_m<T7, GS>(ctx, a, ncols, ncosets); break;
+        case 8: tile_strided_launch_m<T8, GS>(ctx, a, ncols, ncosets); break;
+        case 9: tile_strided_launch_m<T9, GS>(ctx, a, ncols, ncosets); break;
         case 10:
             if (v == 1) tile_strided_launch<T10v1, GS>(ctx, a, ncols, ncosets);
-            else if (v == 2) tile_strided_launch<T10v2, GS>(ctx, a, ncols, ncosets);
+            else if (v == 2) tile_strided_launch_m<T10v2, GS>(ctx, a, ncols, ncosets);
             else if (v == 3) tile_strided_launch<T10v3, GS>(ctx, a, ncols, ncosets);
             else tile_strided_launch<T10, GS>(ctx, a, ncols, ncosets);
             break;
         case 11:
-            if (v == 2) tile_strided_launch<T11v2, GS>(ctx, a, ncols, ncosets);
+            if (v == 2) tile_strided_launch_m<T11v2, GS>(ctx, a, ncols, ncosets);
             else if (v == 3) tile_strided_launch<T11v3, GS>(ctx, a, ncols, ncosets);
             else tile_strided_launch<T11, GS>(ctx, a, ncols, ncosets);
             break;
@@ -597,30 +652,30 @@ static void tile_contig_dispatch(ola_ctx* ctx, const PassArgs& a, size_t ncols, 
     const int v = tune_variant();
     if (ncols <= 2) {  // one or two columns (quotient, FRI): 2-lane tiles
         switch (a.l) {
-            case 6: tile_contig_launch<tile::Cfg<6, 2>, GS>(ctx, a, ncols, ncosets); break;
-            case 7: tile_contig_launch<tile::Cfg<7, 2>, GS>(ctx, a, ncols, ncosets); break;
-            case 8: tile_contig_launch<tile::Cfg<8, 2>, GS>(ctx, a, ncols, ncosets); break;
-            case 9: tile_contig_launch<tile::Cfg<9, 2>, GS>(ctx, a, ncols, ncosets); break;
-            case 10: tile_contig_launch<tile::Cfg<10, 2>, GS>(ctx, a, ncols, ncosets); break;
-            case 11: tile_contig_launch<tile::Cfg<11, 2>, GS>(ctx, a, ncols, ncosets); break;
+            case 6: tile_contig_launch_m<tile::Cfg<6, 2>, GS>(ctx, a, ncols, ncosets); break;
+            case 7: tile_contig_launch_m<tile::Cfg<7, 2>, GS>(ctx, a, ncols, ncosets); break;
+            case 8: tile_contig_launch_m<tile::Cfg<8, 2>, GS>(ctx, a, ncols, ncosets); break;
+            case 9: tile_contig_launch_m<tile::Cfg<9, 2>, GS>(ctx, a, ncols, ncosets); break;
+            case 10: tile_contig_launch_m<tile::Cfg<10, 2>, GS>(ctx, a, ncols, ncosets); break;
+            case 11: tile_contig_launch_m<tile::Cfg<11, 2>, GS>(ctx, a, ncols, ncosets); break;
             default: OLA_CHECK(false, OLA_ERR_INTERNAL, "no tiled contiguous pass of that length");
         }
         return;
     }
     switch (a.l) {
-        case 6: tile_contig_launch<T6, GS>(ctx, a, ncols, ncosets); break;
-        case 7: tile_contig_launch<T7, GS>(ctx, a, ncols, ncosets); break;
-        case 8: tile_contig_launch<T8, GS>(ctx, a, ncols, ncosets); break;
-        case 9: tile_contig_launch<T9, GS>(ctx, a, ncols, ncosets); break;
+        case 6: tile_contig_launch_m<T6, GS>(ctx, a, ncols, ncosets); break;
+        case 7: tile_contig_launch_m<T7, GS>(ctx, a, ncols, ncosets); break;
+        case 8: tile_contig_launch_m<T8, GS>(ctx, a, ncols, ncosets); break;
+        case 9: tile_contig_launch_m<T9, GS>(ctx, a, ncols, ncosets); break;
         case 10:
-            if (tune_contig_c4()) tile_contig_launch<T10c4, GS>(ctx, a, ncols, ncosets);
+            if (tune_contig_c4()) tile_contig_launch_m<T10c4, GS>(ctx, a, ncols, ncosets);
             else if (v == 1) tile_contig_launch<T10v1, GS>(ctx, a, ncols, ncosets);
             else if (v == 2) tile_contig_launch<T10v2, GS>(ctx, a, ncols, ncosets);
             else if (v == 3) tile_contig_launch<T10v3, GS>(ctx, a, ncols, ncosets);
             else tile_contig_launch<T10, GS>(ctx, a, ncols, ncosets);
             break;
         case 11:
-            if (v == 2) tile_contig_launch<T11v2, GS>(ctx, a, ncols, ncosets);
+            if (v == 2) tile_contig_launch_m<T11v2, GS>(ctx, a, ncols, ncosets);
             else if (v == 3) tile_contig_launch<T11v3, GS>(ctx, a, ncols, ncosets);
             else tile_contig_launch<T11, GS>(ctx, a, ncols, ncosets);
             break;
@@ -791,6 +846,7 @@ void forward(ola_ctx* ctx, const FwdDesc& d) {
         a.dst_coset_stride = last ? d.dst_coset_stride : work_coset;
         a.pw = ctx->tw.pw[dir];
         a.brs = ctx->tw.brs[dir];
+        a.inv_roots = dir;
         a.L = L;
         a.M = M;
         a.l = plan[pi];

@@ -18,6 +18,7 @@
 //     are bank-conflict-free.
 //   * Inputs may be any u64 representatives ("lazy"); only the last pass of a transform canonicalises its output.
 #pragma once
+#include "ntt_shift.cuh"
 
 namespace ola {
 namespace ntt {
@@ -78,6 +79,24 @@ __device__ __forceinline__ void build_twiddles(uint64_t* tw, const uint64_t* cu,
         const int u = 31 - __clz(i), q = i - (1 << u);
         scatter_twiddle<l, 0>(tw, u, q, gl::mul(cu[u], __ldg(brs + q)));
     }
+}
+
+// shift form (ntt_shift.cuh): the table of round RHO holds theta^m, m = 1 .. 2^K - 1, at tw[OFF + ((m - 1) << U0) + qh] with
+// theta = the twiddle of (stage U0 + K - 1, block qh << (K - 1)) -- the same 2^K - 1 slots per qh as the radix-2 form
+template <int l, int RHO>
+__device__ __forceinline__ void build_twiddles_pow_round(uint64_t* tw, const uint64_t* cu, const uint64_t* __restrict__ brs, int tid, int nt) {
+    using rd = Rd<l, RHO>;
+    for (int qh = tid; qh < (1 << rd::U0); qh += nt) {
+        const uint64_t theta = gl::mul(cu[rd::U0 + rd::K - 1], __ldg(brs + (qh << (rd::K - 1))));
+        uint64_t p = theta;
+        tw[rd::OFF + qh] = p;
+#pragma unroll 1
+        for (int m = 2; m < (1 << rd::K); ++m) {
+            p = gl::mul(p, theta);
+            tw[rd::OFF + ((m - 1) << rd::U0) + qh] = p;
+        }
+    }
+    if constexpr (RHO + 1 < Sched<l>::NR) build_twiddles_pow_round<l, RHO + 1>(tw, cu, brs, tid, nt);
 }
 
 // K stages on 2^K rows x LN lanes in registers; t = tw + OFF + qh
@@ -144,7 +163,9 @@ __device__ __forceinline__ constexpr int row_off(int m) {
     return (m << SH) + (SH >= P ? (m << (SH >= P ? SH - P : 0)) : (m >> (SH < P ? P - SH : 0)));
 }
 
-template <typename G, bool GS, bool CONTIG, int I>
+// MODE (forward network only): 0 = radix-2 butterflies on canonical products, 1 = shift form with the forward roots,
+// 2 = shift form with the inverse roots (the plain iNTT runs the forward network on inverse roots)
+template <typename G, bool GS, bool CONTIG, int MODE, int I>
 __device__ __forceinline__ void run_step(const Io<CONTIG>& io, uint64_t* __restrict__ x, const uint64_t* __restrict__ tw, int tid) {
     constexpr int l = G::l, C = G::C, P = G::PADLOG;
     constexpr int NR = Sched<l>::NR;
@@ -211,7 +232,10 @@ __device__ __forceinline__ void run_step(const Io<CONTIG>& io, uint64_t* __restr
                 }
             }
         }
-        bfly_regs<K, U0, GS, LN>(v, tw + rd::OFF + qh);
+        if constexpr (MODE == 0)
+            bfly_regs<K, U0, GS, LN>(v, tw + rd::OFF + qh);
+        else
+            bfly_shift<K, U0, LN, MODE == 2>(v, tw + rd::OFF + qh);
         if (LAST) {
 #pragma unroll
             for (int m = 0; m < NE; ++m) {
@@ -260,10 +284,11 @@ __device__ __forceinline__ void run_step(const Io<CONTIG>& io, uint64_t* __restr
     if (!LAST) __syncthreads();
 }
 
-template <typename G, bool GS, bool CONTIG, int I>
+template <typename G, bool GS, bool CONTIG, int MODE, int I>
 __device__ __forceinline__ void run_steps(const Io<CONTIG>& io, uint64_t* x, const uint64_t* tw, int tid) {
-    run_step<G, GS, CONTIG, I>(io, x, tw, tid);
-    if constexpr (I + 1 < Sched<G::l>::NR) run_steps<G, GS, CONTIG, I + 1>(io, x, tw, tid);
+    static_assert(!(GS && MODE != 0), "the shift form exists for the forward network only");
+    run_step<G, GS, CONTIG, MODE, I>(io, x, tw, tid);
+    if constexpr (I + 1 < Sched<G::l>::NR) run_steps<G, GS, CONTIG, MODE, I + 1>(io, x, tw, tid);
 }
 
 // Both kernels are persistent over tiles that share one twiddle table (same sub-block Q, same coset): the table is
@@ -273,7 +298,7 @@ __device__ __forceinline__ void run_steps(const Io<CONTIG>& io, uint64_t* x, con
 // strided pass: tile = (sub-block Q, C adjacent inner indices) x all 2^l rows.  grid (cosets, sub-blocks x chunks):
 // the cosets of one chunk are resident together and walk the same tiles, so the shared input of a coset LDE
 // (src_coset_stride == 0) comes from HBM once and from L2 for the other cosets.
-template <typename G, bool GS>
+template <typename G, bool GS, int MODE = 0>
 __global__ void __launch_bounds__(G::NT, G::MINB) tile_strided(const PassArgs a) {
     extern __shared__ __align__(16) uint64_t sm[];
     constexpr int l = G::l, C = G::C, R = 1 << l;
@@ -298,20 +323,23 @@ __global__ void __launch_bounds__(G::NT, G::MINB) tile_strided(const PassArgs a)
     io.scale = a.scale;
     if (tid == 0) row_constants(a, a.s_last[coset], Q, cu);
     __syncthreads();
-    build_twiddles<l>(tw, cu, a.brs, tid, G::NT);
+    if constexpr (MODE == 0)
+        build_twiddles<l>(tw, cu, a.brs, tid, G::NT);
+    else
+        build_twiddles_pow_round<l, 0>(tw, cu, a.brs, tid, G::NT);
     __syncthreads();
     for (size_t t = t0; t < t1; ++t) {
         const size_t col = t / tiles_per_sub, c0 = (t % tiles_per_sub) * C;
         io.in = a.src + col * a.src_col_stride + coset * a.src_coset_stride + ((size_t)Q << a.M) + c0;
         io.out = a.dst + col * a.dst_col_stride + coset * a.dst_coset_stride + ((size_t)Q << a.M) + c0;
-        run_steps<G, GS, false, 0>(io, x, tw, tid);
+        run_steps<G, GS, false, MODE, 0>(io, x, tw, tid);
         if (Sched<l>::NR > 1 && t + 1 < t1) __syncthreads();  // the next tile's first round overwrites the staging rows
     }
 }
 
 // contiguous pass (M == l): tile = sub-block Q (2^l consecutive elements) of C columns.  grid (sub-blocks, chunks of
 // column groups, cosets)
-template <typename G, bool GS>
+template <typename G, bool GS, int MODE = 0>
 __global__ void __launch_bounds__(G::NT, G::MINB) tile_contig(const PassArgs a) {
     extern __shared__ __align__(16) uint64_t sm[];
     constexpr int l = G::l, C = G::C, R = 1 << l;
@@ -333,14 +361,17 @@ __global__ void __launch_bounds__(G::NT, G::MINB) tile_contig(const PassArgs a) 
     io.scale = a.scale;
     if (tid == 0) row_constants(a, a.s_last[coset], Q, cu);
     __syncthreads();
-    build_twiddles<l>(tw, cu, a.brs, tid, G::NT);
+    if constexpr (MODE == 0)
+        build_twiddles<l>(tw, cu, a.brs, tid, G::NT);
+    else
+        build_twiddles_pow_round<l, 0>(tw, cu, a.brs, tid, G::NT);
     __syncthreads();
     for (size_t g = g0; g < g1; ++g) {
         const size_t col0 = g * C;
         io.in = a.src + col0 * a.src_col_stride + coset * a.src_coset_stride + ((size_t)Q << l);
         io.out = a.dst + col0 * a.dst_col_stride + coset * a.dst_coset_stride + ((size_t)Q << l);
         io.lanes_valid = (int)((a.ncols - col0) < (size_t)C ? (a.ncols - col0) : (size_t)C);
-        run_steps<G, GS, true, 0>(io, x, tw, tid);
+        run_steps<G, GS, true, MODE, 0>(io, x, tw, tid);
         if (Sched<l>::NR > 1 && g + 1 < g1) __syncthreads();
     }
 }

@@ -1,0 +1,14 @@
+#!/bin/bash
+# Round-2 GPU call m: the shift-twiddle register rounds inside the tile kernels.  Parity first (every NTT / commit / proof
+# test against the oracle), then the headline leg A/B (OLA_NTT_SHIFT=0: radix-2 butterflies on canonical products).
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_stark.py -m gpu -x -q 2>&1 | tail -6 | tee gpurun_out/r02m_pytest.txt
+run() {
+  env "$@" python bench.py --steps 10 --warmup 3 --no-cpu-baseline --prove-log-n 0 --merkle-log-l 0 2>gpurun_out/r02m_bench.err | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); k=d['kernels_ms_per_step']
+print('$*', 'step_ms=%.2f e2e_ms=%.2f GB/s=%.1f frac=%.4f'%(d['ms_per_step'], d['e2e']['ms_per_step'], d['value'], d['roofline']['frac']), {a:round(b,2) for a,b in k.items()})"
+}
+run OLA_NTT_SHIFT=0 | tee gpurun_out/r02m_ab.txt
+run OLA_NTT_SHIFT=1 | tee -a gpurun_out/r02m_ab.txt
+tail -3 gpurun_out/r02m_bench.err

@@ -410,6 +410,41 @@ def poseidon_table_config5(ctx, torch, dist, odist, world, rank, device, log_n):
             "proof_bytes": len(proof), "proof_sha256_16": hashlib.sha256(proof).hexdigest()[:16], "verified_by_ola_verify": bool(ok), "verify_error": why if not ok else ""}
 
 
+def pin_to_gpu_numa(torch, local_rank):
+    """Bind this rank's CPU threads and (preferred) host-memory node to the NUMA node of its GPU before the pinned
+    buffers are allocated: with 8 ranks streaming 1.7 GB per step each, a trace that sits on the far socket crosses the
+    inter-socket link on its way to PCIe.  Reports what it found; a box that exposes one node is left as it is."""
+    info = {"node": None, "nodes_online": None, "cpus": None, "bound": False}
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        node = int(open(base + "/numa_node").read().strip())
+        online = open("/sys/devices/system/node/online").read().strip()
+        info.update(node=node, nodes_online=online, pci=bdf)
+        if node < 0 or online in ("0", ""):
+            return info
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        info["cpus"] = len(use)
+        if use:
+            os.sched_setaffinity(0, use)
+            import ctypes
+            libc = ctypes.CDLL(None, use_errno=True)
+            mask = ctypes.c_ulong(1 << node)
+            # set_mempolicy(MPOL_PREFERRED = 1, nodemask, maxnode): x86_64 syscall 238
+            rc = libc.syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(64))
+            info["bound"] = True
+            info["mempolicy_rc"] = int(rc)
+    except Exception as e:  # sysfs not exposed in the container, unknown PCI id, ...
+        info["error"] = str(e)[:80]
+    return info
+
+
 def host_threads():
     """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm uses all host cores (set before libgomp loads)."""
     if "TORCHELASTIC_RUN_ID" in os.environ or os.environ.get("OMP_NUM_THREADS") == "1":
@@ -482,6 +517,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
+    numa = pin_to_gpu_numa(torch, local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -572,11 +608,12 @@ def main():
                     "d2h_bytes_per_step": N_QUERIES * NCOLS * 8 * world},
             "gpu_launches": launches,
             "clocks": clocks,
+            "numa_rank0": numa,
             "roofline": {"bound": "hbm", "kernel": "coset-LDE forward network (lde_strided + lde_contig)", "achieved": ach,
                          "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None, "traffic": traffic,
                          "traffic_source": "static: dram__bytes_read + dram__bytes_write of the two LDE launches from one ncu --set full capture (profiles/lde_traffic.json), not re-measured in this run",
                          "peak_source": how,
-                         "note": "64-bit modular butterflies are INT-pipe bound on B200; see DESIGN.md section 5"},
+                         "note": "64-bit modular butterflies are INT-pipe bound on B200 (issue slots ~80 % busy in isolation, tools/microbench/bfly16.cu); see DESIGN.md section 5"},
             "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
         }
         if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N = 1 only

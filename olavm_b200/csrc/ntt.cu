@@ -491,6 +491,17 @@ static bool tune_shift() {
     }();
     return v;
 }
+// natural-order (bit-reversed store) last passes.  OLA_NTT_NAT = 2 (default): tile_nat, C sub-blocks per tile so that
+// stores fill whole sectors; 1: tile_contig with single-element scattered stores (measured no better than 0,
+// profiles/r02n_*); 0: the generic kernels of round 1 (16-byte pieces)
+static int tune_nat() {
+    static int v = [] {
+        const char* e = getenv("OLA_NTT_NAT");
+        const int t = e ? atoi(e) : 2;
+        return (t >= 0 && t <= 2) ? t : 2;
+    }();
+    return v;
+}
 static bool tune_contig_c4() {
     static bool v = [] {
         const char* e = getenv("OLA_NTT_CONTIG_C4");
@@ -683,6 +694,52 @@ static void tile_contig_dispatch(ola_ctx* ctx, const PassArgs& a, size_t ncols, 
     }
 }
 
+// natural-order last pass (tile_nat): C sub-blocks per tile; needs at least C sub-blocks (t = L - l >= log2 C)
+using N6 = tile::Cfg<6, 8, 2, 1, 4, 1>;
+using N7 = tile::Cfg<7, 8, 2, 1, 4, 1>;
+using N8 = tile::Cfg<8, 8, 2, 1, 4, 1>;
+using N9 = tile::Cfg<9, 8, 2, 1, 4, 1>;
+using N10 = tile::Cfg<10, 8, 2, 1, 4, 1>;
+using N11 = tile::Cfg<11, 4, 2, 1, 4, 1>;
+template <typename G>
+static constexpr size_t tile_nat_smem() {
+    return ((size_t)G::C * G::R + (size_t)G::C * 16 + 16 + (size_t)G::RP * G::C) * sizeof(uint64_t);
+}
+template <typename G>
+static void tile_nat_launch(ola_ctx* ctx, const PassArgs& a, size_t ncols, int ncosets) {
+    PassArgs b = a;
+    b.ncols = ncols;
+    const size_t groups = (((size_t)1 << a.L) >> G::l) / G::C;
+    b.tiles_per_cta = pick_tiles_per_cta(ctx, groups * ncols * (size_t)ncosets, ncols, 1);
+    size_t chunks = (ncols + b.tiles_per_cta - 1) / b.tiles_per_cta;
+    while (chunks > 65535) {
+        b.tiles_per_cta *= 2;
+        chunks = (ncols + b.tiles_per_cta - 1) / b.tiles_per_cta;
+    }
+    const dim3 g((unsigned)groups, (unsigned)chunks, (unsigned)ncosets);
+    if (a.inv_roots) tile::tile_nat<G, 2><<<g, G::NT, tile_nat_smem<G>(), ctx->stream>>>(b);
+    else tile::tile_nat<G, 1><<<g, G::NT, tile_nat_smem<G>(), ctx->stream>>>(b);
+}
+static bool tile_nat_dispatch(ola_ctx* ctx, const PassArgs& a, size_t ncols, int ncosets, const char* name) {
+    const int t = a.L - a.l;
+    if (t < 3) return false;  // fewer than eight sub-blocks: the generic pass handles it
+    Launch lz(ctx, name);
+    switch (a.l) {
+        case 6: tile_nat_launch<N6>(ctx, a, ncols, ncosets); break;
+        case 7: tile_nat_launch<N7>(ctx, a, ncols, ncosets); break;
+        case 8: tile_nat_launch<N8>(ctx, a, ncols, ncosets); break;
+        case 9: tile_nat_launch<N9>(ctx, a, ncols, ncosets); break;
+        case 10: tile_nat_launch<N10>(ctx, a, ncols, ncosets); break;
+        default: tile_nat_launch<N11>(ctx, a, ncols, ncosets); break;
+    }
+    return true;
+}
+template <typename G>
+static void tile_nat_optin(int max_optin) {
+    OLA_CUDA(cudaFuncSetAttribute(tile::tile_nat<G, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    OLA_CUDA(cudaFuncSetAttribute(tile::tile_nat<G, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Opt every pass kernel into the device's maximum dynamic shared memory once, with the same value from every context
 // (a per-launch cudaFuncSetAttribute with the launch's own size races when several host threads drive one GPU).
@@ -698,6 +755,12 @@ static void opt_in_shared_memory(int device) {
     OLA_CUDA(cudaFuncSetAttribute(pass_contig<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     OLA_CUDA(cudaFuncSetAttribute(pass_contig<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     tile_optin_all(max_optin);
+    tile_nat_optin<N6>(max_optin);
+    tile_nat_optin<N7>(max_optin);
+    tile_nat_optin<N8>(max_optin);
+    tile_nat_optin<N9>(max_optin);
+    tile_nat_optin<N10>(max_optin);
+    tile_nat_optin<N11>(max_optin);
 }
 
 void init_twiddles(ola_ctx* ctx) {
@@ -793,7 +856,9 @@ static void launch_contig(ola_ctx* ctx, const PassArgs& a, size_t ncols, int nco
     const int R = 1 << a.l;
     size_t blocks = (((size_t)1 << a.L) >> a.l) / a.G;
     dim3 grid((unsigned)blocks, (unsigned)ncols, (unsigned)ncosets);
-    if (a.l >= 6 && a.l <= 11 && !a.bitrev_store && tune_tile()) {
+    if (a.bitrev_store && a.l >= 6 && a.l <= 11 && tune_tile() && tune_shift() && tune_nat() == 2 && tile_nat_dispatch(ctx, a, ncols, ncosets, name)) {
+        // done by tile_nat
+    } else if (a.l >= 6 && a.l <= 11 && (!a.bitrev_store || tune_nat() == 1) && tune_tile()) {
         Launch lz(ctx, name);
         tile_contig_dispatch<GS>(ctx, a, ncols, ncosets);
     } else if (a.l >= 6) {

@@ -34,10 +34,11 @@ GL_HD gl::W96 mul_pow2_sel(gl::W96 v, int e /* 0 < e < 96, a multiple of 12 */) 
     }
 }
 
-// t[(m - 1) << U0] = theta^m for m = 1 .. 2^K - 1.  Inputs and outputs are lazy u64 representatives.
+// t[(m - 1) << U0] = theta^m for m = 1 .. 2^K - 1 (lane ln reads its own table lane_stride elements further on when the
+// lanes are different sub-blocks, tile_nat).  Inputs and outputs are lazy u64 representatives.
 // INV: the table holds inverse roots (the plain iNTT runs the forward network on omega^-1): omega^-1 = 2^(192 - 39 j)
 template <int K, int U0, int LN, bool INV = false>
-GL_HD void bfly_shift(uint64_t (&v)[1 << K][LN], const uint64_t* __restrict__ t) {
+GL_HD void bfly_shift(uint64_t (&v)[1 << K][LN], const uint64_t* __restrict__ t, size_t lane_stride = 0) {
     static_assert(K >= 1 && K <= 4, "shift rounds cover up to sixteen rows (omega_16 = 2^156)");
     constexpr int NE = 1 << K;
 #pragma unroll
@@ -45,7 +46,7 @@ GL_HD void bfly_shift(uint64_t (&v)[1 << K][LN], const uint64_t* __restrict__ t)
         gl::W96 x[NE];
         x[0] = gl::w96_bias(gl::w96_from_u64(v[0][ln]));  // every output contains row 0 once: all of them end up non-negative
 #pragma unroll
-        for (int m = 1; m < NE; ++m) x[m] = gl::w96_mul(v[m][ln], t[(m - 1) << U0]);
+        for (int m = 1; m < NE; ++m) x[m] = gl::w96_mul(v[m][ln], t[ln * lane_stride + ((m - 1) << U0)]);
 #pragma unroll
         for (int s = 0; s < K; ++s) {
             const int half = (NE >> 1) >> s;

@@ -155,7 +155,20 @@ struct Io {
     int lanes_valid;           // contig: columns of this group that exist (lanes >= lanes_valid are skipped)
     int apply_scale, lazy_out;
     uint64_t scale;
+    // contig, natural-order output: row r of the sub-block goes to out[lane * out_lane + ((bitrev_l(r) << br_t) * br_mul) + br_off]
+    int br_t;                  // -1: positions stay as they are
+    size_t br_mul, br_off;
+    // tile_nat: the lanes are C sub-blocks (not columns): their input offsets come from a table and each has its own
+    // twiddle table, twl elements after the previous lane's (0 = one table for all lanes)
+    const size_t* lane_in;
+    size_t twl;
 };
+
+__device__ __forceinline__ constexpr uint32_t brev_const(uint32_t m, int bits) {
+    uint32_t r = 0;
+    for (int i = 0; i < bits; ++i) r |= ((m >> i) & 1u) << (bits - 1 - i);
+    return r;
+}
 
 // row offset (in padded rows) of register-block element m relative to the block's first row
 template <int SH, int P>
@@ -205,7 +218,7 @@ __device__ __forceinline__ void run_step(const Io<CONTIG>& io, uint64_t* __restr
 #pragma unroll
                 for (int ln = 0; ln < LN; ++ln) {
                     const bool ok = lane0 + ln < io.lanes_valid;
-                    const uint64_t* p = io.in + (size_t)(lane0 + ln) * io.in_lane + rbase;
+                    const uint64_t* p = io.in + (io.lane_in ? io.lane_in[lane0 + ln] : (size_t)(lane0 + ln) * io.in_lane) + rbase;
                     if (SH == 0) {
 #pragma unroll
                         for (int m = 0; m < NE; m += 2) {
@@ -235,7 +248,7 @@ __device__ __forceinline__ void run_step(const Io<CONTIG>& io, uint64_t* __restr
         if constexpr (MODE == 0)
             bfly_regs<K, U0, GS, LN>(v, tw + rd::OFF + qh);
         else
-            bfly_shift<K, U0, LN, MODE == 2>(v, tw + rd::OFF + qh);
+            bfly_shift<K, U0, LN, MODE == 2>(v, tw + rd::OFF + qh + (CONTIG ? (size_t)lane0 * io.twl : 0), CONTIG ? io.twl : 0);
         if (LAST) {
 #pragma unroll
             for (int m = 0; m < NE; ++m) {
@@ -256,6 +269,19 @@ __device__ __forceinline__ void run_step(const Io<CONTIG>& io, uint64_t* __restr
                         *reinterpret_cast<ulonglong2*>(p + (size_t)m * step) = make_ulonglong2(v[m][0], v[m][LN - 1]);
                     else
                         p[(size_t)m * step] = v[m][0];
+                }
+            } else if (io.br_t >= 0) {
+                // natural-order output: bitrev_l(rbase + (m << SH)) = bitrev_l(rbase) | (bitrev_K(m) << (l - K - SH)); the 8-byte
+                // stores of one CTA are 2^br_t elements apart and meet those of the CTAs running beside it (sub-blocks in
+                // bit-reversed order, tile_contig) in L2
+                const size_t rb = (size_t)(__brev((uint32_t)rbase) >> (32 - l));
+#pragma unroll
+                for (int ln = 0; ln < LN; ++ln) {
+                    if (lane0 + ln >= io.lanes_valid) continue;
+                    uint64_t* p = io.out + (size_t)(lane0 + ln) * io.out_lane + io.br_off;
+#pragma unroll
+                    for (int m = 0; m < NE; ++m)
+                        p[((rb | ((size_t)brev_const((uint32_t)m, K) << (l - K - SH))) << io.br_t) * io.br_mul] = v[m][ln];
                 }
             } else {
 #pragma unroll
@@ -318,6 +344,10 @@ __global__ void __launch_bounds__(G::NT, G::MINB) tile_strided(const PassArgs a)
     io.in_row = io.out_row = inner;
     io.in_lane = io.out_lane = 1;
     io.lanes_valid = C;
+    io.br_t = -1;
+    io.br_mul = io.br_off = 0;
+    io.lane_in = nullptr;
+    io.twl = 0;
     io.apply_scale = a.apply_scale;
     io.lazy_out = a.lazy_out;
     io.scale = a.scale;
@@ -348,7 +378,10 @@ __global__ void __launch_bounds__(G::NT, G::MINB) tile_contig(const PassArgs a) 
     uint64_t* x = sm + R + 16;
     const int tid = threadIdx.x;
     const uint32_t coset = blockIdx.z;
-    const uint32_t Q = blockIdx.x;
+    // natural-order output (bitrev_store): CTA x takes the sub-block whose bit-reversed index is x, so that the CTAs in
+    // flight together write neighbouring addresses (row kk of sub-block Q lands at (kk << t) + bitrev_t(Q))
+    const int t_done = a.L - l;
+    const uint32_t Q = a.bitrev_store ? gl::bitrev32(blockIdx.x, t_done) : blockIdx.x;
     const size_t groups = (a.ncols + C - 1) / C;
     const size_t g0 = (size_t)blockIdx.y * a.tiles_per_cta;
     const size_t g1 = g0 + a.tiles_per_cta < groups ? g0 + a.tiles_per_cta : groups;
@@ -356,6 +389,11 @@ __global__ void __launch_bounds__(G::NT, G::MINB) tile_contig(const PassArgs a) 
     io.in_row = io.out_row = 1;
     io.in_lane = a.src_col_stride;
     io.out_lane = a.dst_col_stride;
+    io.br_t = a.bitrev_store ? t_done : -1;
+    io.br_mul = a.out_mul;
+    io.br_off = (size_t)blockIdx.x * a.out_mul + (a.coset_bits ? gl::bitrev32(coset, a.coset_bits) : 0);
+    io.lane_in = nullptr;
+    io.twl = 0;
     io.apply_scale = a.apply_scale;
     io.lazy_out = a.lazy_out;
     io.scale = a.scale;
@@ -369,10 +407,61 @@ __global__ void __launch_bounds__(G::NT, G::MINB) tile_contig(const PassArgs a) 
     for (size_t g = g0; g < g1; ++g) {
         const size_t col0 = g * C;
         io.in = a.src + col0 * a.src_col_stride + coset * a.src_coset_stride + ((size_t)Q << l);
-        io.out = a.dst + col0 * a.dst_col_stride + coset * a.dst_coset_stride + ((size_t)Q << l);
+        io.out = a.bitrev_store ? a.dst + col0 * a.dst_col_stride : a.dst + col0 * a.dst_col_stride + coset * a.dst_coset_stride + ((size_t)Q << l);
         io.lanes_valid = (int)((a.ncols - col0) < (size_t)C ? (a.ncols - col0) : (size_t)C);
         run_steps<G, GS, true, MODE, 0>(io, x, tw, tid);
         if (Sched<l>::NR > 1 && g + 1 < g1) __syncthreads();
+    }
+}
+
+// last pass with NATURAL-ORDER output (the plain iNTT: coefficients; a natural-order LDE): tile = C sub-blocks x all 2^l
+// rows of ONE column, the sub-blocks being those whose bit-reversed indices are consecutive (k0 .. k0 + C - 1): row r of
+// sub-block bitrev_t(k) belongs at natural index (bitrev_l(r) << t) + k, so the C lanes of a row are neighbours in the
+// output and every store instruction of a warp fills whole 32-byte sectors (the generic bit-reversed store writes 16-byte
+// pieces; writing one sub-block per CTA scatters single elements: 2.2x DRAM write traffic, profiles/r02n_*).  The price
+// is one twiddle table per lane (the sub-blocks' row constants differ), built once per CTA and amortised over the
+// columns it streams.  Shift form only (MODE 1 / 2).  grid (2^t / C, column chunks, cosets)
+template <typename G, int MODE>
+__global__ void __launch_bounds__(G::NT, 1) tile_nat(const PassArgs a) {
+    extern __shared__ __align__(16) uint64_t sm[];
+    constexpr int l = G::l, C = G::C, R = 1 << l;
+    uint64_t* tw = sm;                                          // [C][R]
+    uint64_t* cu = sm + (size_t)C * R;                          // [C][16]
+    size_t* lane_in = reinterpret_cast<size_t*>(cu + C * 16);   // [C] (16 slots reserved)
+    uint64_t* x = cu + C * 16 + 16;
+    const int tid = threadIdx.x;
+    const uint32_t coset = blockIdx.z;
+    const int t_done = a.L - l;
+    const uint32_t k0 = blockIdx.x * C;
+    const size_t g0 = (size_t)blockIdx.y * a.tiles_per_cta;
+    const size_t g1 = g0 + a.tiles_per_cta < a.ncols ? g0 + a.tiles_per_cta : a.ncols;
+    if (tid < C) {
+        const uint32_t Q = gl::bitrev32(k0 + tid, t_done);
+        row_constants(a, a.s_last[coset], Q, cu + tid * 16);
+        lane_in[tid] = (size_t)Q << l;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int g = 0; g < C; ++g) build_twiddles_pow_round<l, 0>(tw + (size_t)g * R, cu + g * 16, a.brs, tid, G::NT);
+    __syncthreads();
+    Io<true> io;
+    io.in_row = io.out_row = 1;
+    io.in_lane = 0;
+    io.out_lane = a.out_mul;
+    io.lanes_valid = C;
+    io.br_t = t_done;
+    io.br_mul = a.out_mul;
+    io.br_off = (size_t)k0 * a.out_mul + (a.coset_bits ? gl::bitrev32(coset, a.coset_bits) : 0);
+    io.lane_in = lane_in;
+    io.twl = R;
+    io.apply_scale = a.apply_scale;
+    io.lazy_out = a.lazy_out;
+    io.scale = a.scale;
+    for (size_t col = g0; col < g1; ++col) {
+        io.in = a.src + col * a.src_col_stride + coset * a.src_coset_stride;
+        io.out = a.dst + col * a.dst_col_stride;
+        run_steps<G, false, true, MODE, 0>(io, x, tw, tid);
+        if (Sched<l>::NR > 1 && col + 1 < g1) __syncthreads();
     }
 }
 

@@ -54,6 +54,7 @@ struct PassArgs {
     int lazy_out;         // tile kernels: leave the outputs un-canonicalised (an intermediate pass; every pass accepts lazy input)
     size_t ncols;         // tile_contig: columns in the batch (the last column group may be partial)
     uint64_t scale;
+    int prefetch;         // contiguous tile passes: bulk-prefetch the tile this many groups ahead into L2 (0 = off)
     int inv_roots;        // pw / brs hold the inverse roots (the shift form of the tile kernels needs to know which powers of two they are)
     uint64_t s_last[MAX_COSETS];  // per coset: (shift_i)^(2^(M-l)), or its inverse for the GS network
 };
@@ -502,6 +503,22 @@ static int tune_nat() {
     }();
     return v;
 }
+// OLA_NTT_PREFETCH = tiles ahead whose columns the contiguous tile passes pull into L2 with cp.async.bulk.prefetch (0 = off)
+static int tune_prefetch() {
+    static int v = [] {
+        const char* e = getenv("OLA_NTT_PREFETCH");
+        const int t = e ? atoi(e) : 1;
+        return (t >= 0 && t <= 4) ? t : 1;
+    }();
+    return v;
+}
+static int tune_contig_minb() {
+    static int v = [] {
+        const char* e = getenv("OLA_NTT_CONTIG_MINB");
+        return e ? atoi(e) : 4;
+    }();
+    return v;
+}
 static bool tune_contig_c4() {
     static bool v = [] {
         const char* e = getenv("OLA_NTT_CONTIG_C4");
@@ -539,6 +556,7 @@ using T10v1 = tile::Cfg<10, 8, 2, 2, 5, 3>;
 using T10v2 = tile::Cfg<10, 8, 2, 1, 4, 2>;
 using T10v3 = tile::Cfg<10, 8, 1, 1, 4, 2>;
 using T10c4 = tile::Cfg<10, 4, 2, 1, 4, 4>;  // contiguous pass, 4-column tiles: 43 KB, 4-5 CTAs / SM (OLA_NTT_CONTIG_C4=0 disables)
+using T10c4m3 = tile::Cfg<10, 4, 2, 1, 4, 3>;  // the same with the register cap of 3 CTAs / SM (85 registers, no spills): OLA_NTT_CONTIG_MINB=3
 using T11 = tile::Cfg<11, 4>;
 using T11v2 = tile::Cfg<11, 4, 2, 1, 4, 2>;
 using T11v3 = tile::Cfg<11, 4, 1, 1, 4, 2>;
@@ -552,6 +570,7 @@ static void tile_optin_all(int max_optin) {
     tile_optin<T10v2>(max_optin);
     tile_optin<T10v3>(max_optin);
     tile_optin_contig<T10c4>(max_optin);
+    tile_optin_contig<T10c4m3>(max_optin);
     tile_optin<T11>(max_optin);
     tile_optin<T11v2>(max_optin);
     tile_optin<T11v3>(max_optin);
@@ -567,6 +586,7 @@ static void tile_optin_all(int max_optin) {
     tile_optin_shift<T9>(max_optin, true);
     tile_optin_shift<T10v2>(max_optin, true);
     tile_optin_shift<T10c4>(max_optin, false);
+    tile_optin_shift<T10c4m3>(max_optin, false);
     tile_optin_shift<T11v2>(max_optin, true);
     tile_optin_shift<tile::Cfg<6, 2>>(max_optin, false);
     tile_optin_shift<tile::Cfg<7, 2>>(max_optin, false);
@@ -602,6 +622,7 @@ template <typename G, bool GS, int MODE = 0>
 static void tile_contig_launch(ola_ctx* ctx, const PassArgs& a, size_t ncols, int ncosets) {
     PassArgs b = a;
     b.ncols = ncols;
+    b.prefetch = tune_prefetch();
     const size_t nsub = ((size_t)1 << a.L) >> G::l;
     const size_t groups = (ncols + G::C - 1) / G::C;
     b.tiles_per_cta = pick_tiles_per_cta(ctx, groups * nsub * (size_t)ncosets, groups, G::MINB);
@@ -679,7 +700,8 @@ static void tile_contig_dispatch(ola_ctx* ctx, const PassArgs& a, size_t ncols, 
         case 8: tile_contig_launch_m<T8, GS>(ctx, a, ncols, ncosets); break;
         case 9: tile_contig_launch_m<T9, GS>(ctx, a, ncols, ncosets); break;
         case 10:
-            if (tune_contig_c4()) tile_contig_launch_m<T10c4, GS>(ctx, a, ncols, ncosets);
+            if (tune_contig_c4() && tune_contig_minb() == 3) tile_contig_launch_m<T10c4m3, GS>(ctx, a, ncols, ncosets);
+            else if (tune_contig_c4()) tile_contig_launch_m<T10c4, GS>(ctx, a, ncols, ncosets);
             else if (v == 1) tile_contig_launch<T10v1, GS>(ctx, a, ncols, ncosets);
             else if (v == 2) tile_contig_launch<T10v2, GS>(ctx, a, ncols, ncosets);
             else if (v == 3) tile_contig_launch<T10v3, GS>(ctx, a, ncols, ncosets);
@@ -709,6 +731,7 @@ template <typename G>
 static void tile_nat_launch(ola_ctx* ctx, const PassArgs& a, size_t ncols, int ncosets) {
     PassArgs b = a;
     b.ncols = ncols;
+    b.prefetch = tune_prefetch();
     const size_t groups = (((size_t)1 << a.L) >> G::l) / G::C;
     b.tiles_per_cta = pick_tiles_per_cta(ctx, groups * ncols * (size_t)ncosets, ncols, 1);
     size_t chunks = (ncols + b.tiles_per_cta - 1) / b.tiles_per_cta;

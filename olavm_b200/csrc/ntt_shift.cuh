@@ -38,13 +38,16 @@ GL_HD gl::W96 mul_pow2_sel(gl::W96 v, int e /* 0 < e < 96, a multiple of 12 */) 
 // lanes are different sub-blocks, tile_nat).  Inputs and outputs are lazy u64 representatives.
 // INV: the table holds inverse roots (the plain iNTT runs the forward network on omega^-1): omega^-1 = 2^(192 - 39 j)
 template <int K, int U0, int LN, bool INV = false>
-GL_HD void bfly_shift(uint64_t (&v)[1 << K][LN], const uint64_t* __restrict__ t, size_t lane_stride = 0) {
+// scale0 != nullptr: the table holds theta^m * scale (an output scale folded into the twiddles: 1/n of the iNTT) and
+// row 0, which no twiddle multiplies, takes the factor explicitly -- one product per block instead of one per output.
+GL_HD void bfly_shift(uint64_t (&v)[1 << K][LN], const uint64_t* __restrict__ t, size_t lane_stride = 0, const uint64_t* scale0 = nullptr) {
     static_assert(K >= 1 && K <= 4, "shift rounds cover up to sixteen rows (omega_16 = 2^156)");
     constexpr int NE = 1 << K;
 #pragma unroll
     for (int ln = 0; ln < LN; ++ln) {
         gl::W96 x[NE];
-        x[0] = gl::w96_bias(gl::w96_from_u64(v[0][ln]));  // every output contains row 0 once: all of them end up non-negative
+        // every output contains row 0 once: a multiple of p added to it makes all of them non-negative
+        x[0] = gl::w96_bias(scale0 ? gl::w96_mul(v[0][ln], *scale0) : gl::w96_from_u64(v[0][ln]));
 #pragma unroll
         for (int m = 1; m < NE; ++m) x[m] = gl::w96_mul(v[m][ln], t[ln * lane_stride + ((m - 1) << U0)]);
 #pragma unroll

@@ -19,6 +19,7 @@
 //   * Inputs may be any u64 representatives ("lazy"); only the last pass of a transform canonicalises its output.
 #pragma once
 #include "ntt_shift.cuh"
+#include "tma.cuh"
 
 namespace ola {
 namespace ntt {
@@ -83,12 +84,13 @@ __device__ __forceinline__ void build_twiddles(uint64_t* tw, const uint64_t* cu,
 
 // shift form (ntt_shift.cuh): the table of round RHO holds theta^m, m = 1 .. 2^K - 1, at tw[OFF + ((m - 1) << U0) + qh] with
 // theta = the twiddle of (stage U0 + K - 1, block qh << (K - 1)) -- the same 2^K - 1 slots per qh as the radix-2 form
+// (the LAST round's table is theta^m * scale when the pass applies an output scale: bfly_shift's scale0)
 template <int l, int RHO>
-__device__ __forceinline__ void build_twiddles_pow_round(uint64_t* tw, const uint64_t* cu, const uint64_t* __restrict__ brs, int tid, int nt) {
+__device__ __forceinline__ void build_twiddles_pow_round(uint64_t* tw, const uint64_t* cu, const uint64_t* __restrict__ brs, int tid, int nt, uint64_t scale) {
     using rd = Rd<l, RHO>;
     for (int qh = tid; qh < (1 << rd::U0); qh += nt) {
         const uint64_t theta = gl::mul(cu[rd::U0 + rd::K - 1], __ldg(brs + (qh << (rd::K - 1))));
-        uint64_t p = theta;
+        uint64_t p = (RHO + 1 == Sched<l>::NR) ? gl::mul(theta, scale) : theta;
         tw[rd::OFF + qh] = p;
 #pragma unroll 1
         for (int m = 2; m < (1 << rd::K); ++m) {
@@ -96,7 +98,7 @@ __device__ __forceinline__ void build_twiddles_pow_round(uint64_t* tw, const uin
             tw[rd::OFF + ((m - 1) << rd::U0) + qh] = p;
         }
     }
-    if constexpr (RHO + 1 < Sched<l>::NR) build_twiddles_pow_round<l, RHO + 1>(tw, cu, brs, tid, nt);
+    if constexpr (RHO + 1 < Sched<l>::NR) build_twiddles_pow_round<l, RHO + 1>(tw, cu, brs, tid, nt, scale);
 }
 
 // K stages on 2^K rows x LN lanes in registers; t = tw + OFF + qh
@@ -248,14 +250,15 @@ __device__ __forceinline__ void run_step(const Io<CONTIG>& io, uint64_t* __restr
         if constexpr (MODE == 0)
             bfly_regs<K, U0, GS, LN>(v, tw + rd::OFF + qh);
         else
-            bfly_shift<K, U0, LN, MODE == 2>(v, tw + rd::OFF + qh + (CONTIG ? (size_t)lane0 * io.twl : 0), CONTIG ? io.twl : 0);
+            bfly_shift<K, U0, LN, MODE == 2>(v, tw + rd::OFF + qh + (CONTIG ? (size_t)lane0 * io.twl : 0), CONTIG ? io.twl : 0,
+                                             (LAST && io.apply_scale) ? &io.scale : nullptr);
         if (LAST) {
 #pragma unroll
             for (int m = 0; m < NE; ++m) {
 #pragma unroll
                 for (int ln = 0; ln < LN; ++ln) {
-                    if (io.apply_scale)
-                        v[m][ln] = gl::mul(v[m][ln], io.scale);
+                    if (MODE == 0 && io.apply_scale)
+                        v[m][ln] = gl::mul(v[m][ln], io.scale);  // (the shift form folds the scale into the last round's twiddles)
                     else if (!io.lazy_out)
                         v[m][ln] = gl::canon_fast(v[m][ln]);
                 }
@@ -356,7 +359,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) tile_strided(const PassArgs a)
     if constexpr (MODE == 0)
         build_twiddles<l>(tw, cu, a.brs, tid, G::NT);
     else
-        build_twiddles_pow_round<l, 0>(tw, cu, a.brs, tid, G::NT);
+        build_twiddles_pow_round<l, 0>(tw, cu, a.brs, tid, G::NT, a.apply_scale ? a.scale : 1);
     __syncthreads();
     for (size_t t = t0; t < t1; ++t) {
         const size_t col = t / tiles_per_sub, c0 = (t % tiles_per_sub) * C;
@@ -402,10 +405,14 @@ __global__ void __launch_bounds__(G::NT, G::MINB) tile_contig(const PassArgs a) 
     if constexpr (MODE == 0)
         build_twiddles<l>(tw, cu, a.brs, tid, G::NT);
     else
-        build_twiddles_pow_round<l, 0>(tw, cu, a.brs, tid, G::NT);
+        build_twiddles_pow_round<l, 0>(tw, cu, a.brs, tid, G::NT, a.apply_scale ? a.scale : 1);
     __syncthreads();
     for (size_t g = g0; g < g1; ++g) {
         const size_t col0 = g * C;
+        // the tile a.prefetch groups ahead is pulled into L2 by the copy engine (one bulk prefetch per column: 2^l contiguous
+        // elements) while this one is transformed: the first round's loads then wait for L2, not for HBM
+        if (a.prefetch && tid < C && g + a.prefetch < g1 && (g + a.prefetch) * C + tid < a.ncols)
+            tma::bulk_prefetch_l2(a.src + ((g + a.prefetch) * C + tid) * a.src_col_stride + coset * a.src_coset_stride + ((size_t)Q << l), (uint32_t)(R * sizeof(uint64_t)));
         io.in = a.src + col0 * a.src_col_stride + coset * a.src_coset_stride + ((size_t)Q << l);
         io.out = a.bitrev_store ? a.dst + col0 * a.dst_col_stride : a.dst + col0 * a.dst_col_stride + coset * a.dst_coset_stride + ((size_t)Q << l);
         io.lanes_valid = (int)((a.ncols - col0) < (size_t)C ? (a.ncols - col0) : (size_t)C);
@@ -442,7 +449,7 @@ __global__ void __launch_bounds__(G::NT, 1) tile_nat(const PassArgs a) {
     }
     __syncthreads();
 #pragma unroll 1
-    for (int g = 0; g < C; ++g) build_twiddles_pow_round<l, 0>(tw + (size_t)g * R, cu + g * 16, a.brs, tid, G::NT);
+    for (int g = 0; g < C; ++g) build_twiddles_pow_round<l, 0>(tw + (size_t)g * R, cu + g * 16, a.brs, tid, G::NT, a.apply_scale ? a.scale : 1);
     __syncthreads();
     Io<true> io;
     io.in_row = io.out_row = 1;
@@ -458,6 +465,8 @@ __global__ void __launch_bounds__(G::NT, 1) tile_nat(const PassArgs a) {
     io.lazy_out = a.lazy_out;
     io.scale = a.scale;
     for (size_t col = g0; col < g1; ++col) {
+        if (a.prefetch && tid < C && col + a.prefetch < g1)
+            tma::bulk_prefetch_l2(a.src + (col + a.prefetch) * a.src_col_stride + coset * a.src_coset_stride + lane_in[tid], (uint32_t)(R * sizeof(uint64_t)));
         io.in = a.src + col * a.src_col_stride + coset * a.src_coset_stride;
         io.out = a.dst + col * a.dst_col_stride;
         run_steps<G, false, true, MODE, 0>(io, x, tw, tid);

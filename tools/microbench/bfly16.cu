@@ -66,12 +66,17 @@ static int host_check(int trials) {
                 }
             }
         }
-        uint64_t pw = 1;
+        // every third trial folds an output scale into the table (the iNTT's 1/n): tw = theta^m * scale, row 0 scaled explicitly
+        const bool scaled = (tr % 3 == 1);
+        const uint64_t scale = gl::canon(rnd());
+        uint64_t pw = scaled ? scale : 1;
         for (int m = 1; m < NE; ++m) {
             pw = gl::mul(pw, theta);
             tw[m - 1] = pw;
         }
-        bfly_shift<K, 0, 1, INV>(v, tw);
+        if (scaled)
+            for (int m = 0; m < NE; ++m) ref[m] = gl::mul(ref[m], scale);
+        bfly_shift<K, 0, 1, INV>(v, tw, 0, scaled ? &scale : nullptr);
         for (int m = 0; m < NE; ++m)
             if (gl::canon(v[m][0]) != ref[m]) {
                 if (bad < 5) printf("K=%d trial %d row %d: got %016llx want %016llx\n", K, tr, m, (unsigned long long)gl::canon(v[m][0]), (unsigned long long)ref[m]);

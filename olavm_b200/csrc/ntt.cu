@@ -493,13 +493,13 @@ static bool tune_shift() {
     return v;
 }
 // natural-order (bit-reversed store) last passes.  OLA_NTT_NAT = 2 (default): tile_nat, C sub-blocks per tile so that
-// stores fill whole sectors; 1: tile_contig with single-element scattered stores (measured no better than 0,
-// profiles/r02n_*); 0: the generic kernels of round 1 (16-byte pieces)
+// stores fill whole sectors; 0: the generic kernels of round 1 (16-byte pieces).  (One sub-block per CTA with
+// single-element scattered stores was measured no better than the generic kernels and removed: profiles/r02n_*.)
 static int tune_nat() {
     static int v = [] {
         const char* e = getenv("OLA_NTT_NAT");
         const int t = e ? atoi(e) : 2;
-        return (t >= 0 && t <= 2) ? t : 2;
+        return (t == 0) ? 0 : 2;
     }();
     return v;
 }
@@ -509,6 +509,13 @@ static int tune_prefetch() {
         const char* e = getenv("OLA_NTT_PREFETCH");
         const int t = e ? atoi(e) : 1;
         return (t >= 0 && t <= 4) ? t : 1;
+    }();
+    return v;
+}
+static int tune_contig_ln3() {
+    static int v = [] {
+        const char* e = getenv("OLA_NTT_CONTIG_LN3");
+        return e ? atoi(e) : 2;
     }();
     return v;
 }
@@ -556,6 +563,7 @@ using T10v1 = tile::Cfg<10, 8, 2, 2, 5, 3>;
 using T10v2 = tile::Cfg<10, 8, 2, 1, 4, 2>;
 using T10v3 = tile::Cfg<10, 8, 1, 1, 4, 2>;
 using T10c4 = tile::Cfg<10, 4, 2, 1, 4, 4>;  // contiguous pass, 4-column tiles: 43 KB, 4-5 CTAs / SM (OLA_NTT_CONTIG_C4=0 disables)
+using T10c4l1 = tile::Cfg<10, 4, 1, 1, 4, 4>;  // one lane per thread in the radix-8 rounds too: OLA_NTT_CONTIG_LN3=1
 using T10c4m3 = tile::Cfg<10, 4, 2, 1, 4, 3>;  // the same with the register cap of 3 CTAs / SM (85 registers, no spills): OLA_NTT_CONTIG_MINB=3
 using T11 = tile::Cfg<11, 4>;
 using T11v2 = tile::Cfg<11, 4, 2, 1, 4, 2>;
@@ -571,6 +579,7 @@ static void tile_optin_all(int max_optin) {
     tile_optin<T10v3>(max_optin);
     tile_optin_contig<T10c4>(max_optin);
     tile_optin_contig<T10c4m3>(max_optin);
+    tile_optin_contig<T10c4l1>(max_optin);
     tile_optin<T11>(max_optin);
     tile_optin<T11v2>(max_optin);
     tile_optin<T11v3>(max_optin);
@@ -587,6 +596,8 @@ static void tile_optin_all(int max_optin) {
     tile_optin_shift<T10v2>(max_optin, true);
     tile_optin_shift<T10c4>(max_optin, false);
     tile_optin_shift<T10c4m3>(max_optin, false);
+    tile_optin_shift<T10c4l1>(max_optin, false);
+    tile_optin_shift<T10v3>(max_optin, true);
     tile_optin_shift<T11v2>(max_optin, true);
     tile_optin_shift<tile::Cfg<6, 2>>(max_optin, false);
     tile_optin_shift<tile::Cfg<7, 2>>(max_optin, false);
@@ -668,7 +679,7 @@ static void tile_strided_dispatch(ola_ctx* ctx, const PassArgs& a, size_t ncols,
         case 10:
             if (v == 1) tile_strided_launch<T10v1, GS>(ctx, a, ncols, ncosets);
             else if (v == 2) tile_strided_launch_m<T10v2, GS>(ctx, a, ncols, ncosets);
-            else if (v == 3) tile_strided_launch<T10v3, GS>(ctx, a, ncols, ncosets);
+            else if (v == 3) tile_strided_launch_m<T10v3, GS>(ctx, a, ncols, ncosets);
             else tile_strided_launch<T10, GS>(ctx, a, ncols, ncosets);
             break;
         case 11:
@@ -700,7 +711,8 @@ static void tile_contig_dispatch(ola_ctx* ctx, const PassArgs& a, size_t ncols, 
         case 8: tile_contig_launch_m<T8, GS>(ctx, a, ncols, ncosets); break;
         case 9: tile_contig_launch_m<T9, GS>(ctx, a, ncols, ncosets); break;
         case 10:
-            if (tune_contig_c4() && tune_contig_minb() == 3) tile_contig_launch_m<T10c4m3, GS>(ctx, a, ncols, ncosets);
+            if (tune_contig_c4() && tune_contig_ln3() == 1) tile_contig_launch_m<T10c4l1, GS>(ctx, a, ncols, ncosets);
+            else if (tune_contig_c4() && tune_contig_minb() == 3) tile_contig_launch_m<T10c4m3, GS>(ctx, a, ncols, ncosets);
             else if (tune_contig_c4()) tile_contig_launch_m<T10c4, GS>(ctx, a, ncols, ncosets);
             else if (v == 1) tile_contig_launch<T10v1, GS>(ctx, a, ncols, ncosets);
             else if (v == 2) tile_contig_launch<T10v2, GS>(ctx, a, ncols, ncosets);
@@ -881,7 +893,7 @@ static void launch_contig(ola_ctx* ctx, const PassArgs& a, size_t ncols, int nco
     dim3 grid((unsigned)blocks, (unsigned)ncols, (unsigned)ncosets);
     if (a.bitrev_store && a.l >= 6 && a.l <= 11 && tune_tile() && tune_shift() && tune_nat() == 2 && tile_nat_dispatch(ctx, a, ncols, ncosets, name)) {
         // done by tile_nat
-    } else if (a.l >= 6 && a.l <= 11 && (!a.bitrev_store || tune_nat() == 1) && tune_tile()) {
+    } else if (a.l >= 6 && a.l <= 11 && !a.bitrev_store && tune_tile()) {
         Launch lz(ctx, name);
         tile_contig_dispatch<GS>(ctx, a, ncols, ncosets);
     } else if (a.l >= 6) {

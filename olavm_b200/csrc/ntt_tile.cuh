@@ -180,7 +180,8 @@ __device__ __forceinline__ constexpr int row_off(int m) {
 
 // MODE (forward network only): 0 = radix-2 butterflies on canonical products, 1 = shift form with the forward roots,
 // 2 = shift form with the inverse roots (the plain iNTT runs the forward network on inverse roots)
-template <typename G, bool GS, bool CONTIG, int MODE, int I>
+// NAT: the lanes of a contiguous tile are sub-blocks with consecutive bit-reversed indices (tile_nat) instead of columns
+template <typename G, bool GS, bool CONTIG, int MODE, int I, bool NAT = false>
 __device__ __forceinline__ void run_step(const Io<CONTIG>& io, uint64_t* __restrict__ x, const uint64_t* __restrict__ tw, int tid) {
     constexpr int l = G::l, C = G::C, P = G::PADLOG;
     constexpr int NR = Sched<l>::NR;
@@ -220,7 +221,7 @@ __device__ __forceinline__ void run_step(const Io<CONTIG>& io, uint64_t* __restr
 #pragma unroll
                 for (int ln = 0; ln < LN; ++ln) {
                     const bool ok = lane0 + ln < io.lanes_valid;
-                    const uint64_t* p = io.in + (io.lane_in ? io.lane_in[lane0 + ln] : (size_t)(lane0 + ln) * io.in_lane) + rbase;
+                    const uint64_t* p = io.in + (NAT ? io.lane_in[lane0 + ln] : (size_t)(lane0 + ln) * io.in_lane) + rbase;
                     if (SH == 0) {
 #pragma unroll
                         for (int m = 0; m < NE; m += 2) {
@@ -250,7 +251,7 @@ __device__ __forceinline__ void run_step(const Io<CONTIG>& io, uint64_t* __restr
         if constexpr (MODE == 0)
             bfly_regs<K, U0, GS, LN>(v, tw + rd::OFF + qh);
         else
-            bfly_shift<K, U0, LN, MODE == 2>(v, tw + rd::OFF + qh + (CONTIG ? (size_t)lane0 * io.twl : 0), CONTIG ? io.twl : 0,
+            bfly_shift<K, U0, LN, MODE == 2>(v, tw + rd::OFF + qh + (NAT ? (size_t)lane0 * io.twl : 0), NAT ? io.twl : 0,
                                              (LAST && io.apply_scale) ? &io.scale : nullptr);
         if (LAST) {
 #pragma unroll
@@ -273,14 +274,12 @@ __device__ __forceinline__ void run_step(const Io<CONTIG>& io, uint64_t* __restr
                     else
                         p[(size_t)m * step] = v[m][0];
                 }
-            } else if (io.br_t >= 0) {
-                // natural-order output: bitrev_l(rbase + (m << SH)) = bitrev_l(rbase) | (bitrev_K(m) << (l - K - SH)); the 8-byte
-                // stores of one CTA are 2^br_t elements apart and meet those of the CTAs running beside it (sub-blocks in
-                // bit-reversed order, tile_contig) in L2
+            } else if constexpr (NAT) {
+                // natural-order output: bitrev_l(rbase + (m << SH)) = bitrev_l(rbase) | (bitrev_K(m) << (l - K - SH)); the lanes of
+                // a row are neighbours in the output
                 const size_t rb = (size_t)(__brev((uint32_t)rbase) >> (32 - l));
 #pragma unroll
                 for (int ln = 0; ln < LN; ++ln) {
-                    if (lane0 + ln >= io.lanes_valid) continue;
                     uint64_t* p = io.out + (size_t)(lane0 + ln) * io.out_lane + io.br_off;
 #pragma unroll
                     for (int m = 0; m < NE; ++m)
@@ -313,11 +312,11 @@ __device__ __forceinline__ void run_step(const Io<CONTIG>& io, uint64_t* __restr
     if (!LAST) __syncthreads();
 }
 
-template <typename G, bool GS, bool CONTIG, int MODE, int I>
+template <typename G, bool GS, bool CONTIG, int MODE, int I, bool NAT = false>
 __device__ __forceinline__ void run_steps(const Io<CONTIG>& io, uint64_t* x, const uint64_t* tw, int tid) {
     static_assert(!(GS && MODE != 0), "the shift form exists for the forward network only");
-    run_step<G, GS, CONTIG, MODE, I>(io, x, tw, tid);
-    if constexpr (I + 1 < Sched<G::l>::NR) run_steps<G, GS, CONTIG, MODE, I + 1>(io, x, tw, tid);
+    run_step<G, GS, CONTIG, MODE, I, NAT>(io, x, tw, tid);
+    if constexpr (I + 1 < Sched<G::l>::NR) run_steps<G, GS, CONTIG, MODE, I + 1, NAT>(io, x, tw, tid);
 }
 
 // Both kernels are persistent over tiles that share one twiddle table (same sub-block Q, same coset): the table is
@@ -381,10 +380,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) tile_contig(const PassArgs a) 
     uint64_t* x = sm + R + 16;
     const int tid = threadIdx.x;
     const uint32_t coset = blockIdx.z;
-    // natural-order output (bitrev_store): CTA x takes the sub-block whose bit-reversed index is x, so that the CTAs in
-    // flight together write neighbouring addresses (row kk of sub-block Q lands at (kk << t) + bitrev_t(Q))
-    const int t_done = a.L - l;
-    const uint32_t Q = a.bitrev_store ? gl::bitrev32(blockIdx.x, t_done) : blockIdx.x;
+    const uint32_t Q = blockIdx.x;
     const size_t groups = (a.ncols + C - 1) / C;
     const size_t g0 = (size_t)blockIdx.y * a.tiles_per_cta;
     const size_t g1 = g0 + a.tiles_per_cta < groups ? g0 + a.tiles_per_cta : groups;
@@ -392,9 +388,8 @@ __global__ void __launch_bounds__(G::NT, G::MINB) tile_contig(const PassArgs a) 
     io.in_row = io.out_row = 1;
     io.in_lane = a.src_col_stride;
     io.out_lane = a.dst_col_stride;
-    io.br_t = a.bitrev_store ? t_done : -1;
-    io.br_mul = a.out_mul;
-    io.br_off = (size_t)blockIdx.x * a.out_mul + (a.coset_bits ? gl::bitrev32(coset, a.coset_bits) : 0);
+    io.br_t = -1;
+    io.br_mul = io.br_off = 0;
     io.lane_in = nullptr;
     io.twl = 0;
     io.apply_scale = a.apply_scale;
@@ -414,7 +409,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) tile_contig(const PassArgs a) 
         if (a.prefetch && tid < C && g + a.prefetch < g1 && (g + a.prefetch) * C + tid < a.ncols)
             tma::bulk_prefetch_l2(a.src + ((g + a.prefetch) * C + tid) * a.src_col_stride + coset * a.src_coset_stride + ((size_t)Q << l), (uint32_t)(R * sizeof(uint64_t)));
         io.in = a.src + col0 * a.src_col_stride + coset * a.src_coset_stride + ((size_t)Q << l);
-        io.out = a.bitrev_store ? a.dst + col0 * a.dst_col_stride : a.dst + col0 * a.dst_col_stride + coset * a.dst_coset_stride + ((size_t)Q << l);
+        io.out = a.dst + col0 * a.dst_col_stride + coset * a.dst_coset_stride + ((size_t)Q << l);
         io.lanes_valid = (int)((a.ncols - col0) < (size_t)C ? (a.ncols - col0) : (size_t)C);
         run_steps<G, GS, true, MODE, 0>(io, x, tw, tid);
         if (Sched<l>::NR > 1 && g + 1 < g1) __syncthreads();
@@ -469,7 +464,7 @@ __global__ void __launch_bounds__(G::NT, 1) tile_nat(const PassArgs a) {
             tma::bulk_prefetch_l2(a.src + (col + a.prefetch) * a.src_col_stride + coset * a.src_coset_stride + lane_in[tid], (uint32_t)(R * sizeof(uint64_t)));
         io.in = a.src + col * a.src_col_stride + coset * a.src_coset_stride;
         io.out = a.dst + col * a.dst_col_stride;
-        run_steps<G, false, true, MODE, 0>(io, x, tw, tid);
+        run_steps<G, false, true, MODE, 0, true>(io, x, tw, tid);
         if (Sched<l>::NR > 1 && col + 1 < g1) __syncthreads();
     }
 }

@@ -512,20 +512,6 @@ static int tune_prefetch() {
     }();
     return v;
 }
-static int tune_contig_ln3() {
-    static int v = [] {
-        const char* e = getenv("OLA_NTT_CONTIG_LN3");
-        return e ? atoi(e) : 2;
-    }();
-    return v;
-}
-static int tune_contig_minb() {
-    static int v = [] {
-        const char* e = getenv("OLA_NTT_CONTIG_MINB");
-        return e ? atoi(e) : 4;
-    }();
-    return v;
-}
 static bool tune_contig_c4() {
     static bool v = [] {
         const char* e = getenv("OLA_NTT_CONTIG_C4");
@@ -548,6 +534,8 @@ static void tile_optin_shift(int max_optin, bool strided) {
     }
     OLA_CUDA(cudaFuncSetAttribute(tile::tile_contig<G, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
     OLA_CUDA(cudaFuncSetAttribute(tile::tile_contig<G, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    OLA_CUDA(cudaFuncSetAttribute(tile::tile_contig<G, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    OLA_CUDA(cudaFuncSetAttribute(tile::tile_contig<G, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
 }
 template <typename G>
 static void tile_optin_contig(int max_optin) {
@@ -563,8 +551,7 @@ using T10v1 = tile::Cfg<10, 8, 2, 2, 5, 3>;
 using T10v2 = tile::Cfg<10, 8, 2, 1, 4, 2>;
 using T10v3 = tile::Cfg<10, 8, 1, 1, 4, 2>;
 using T10c4 = tile::Cfg<10, 4, 2, 1, 4, 4>;  // contiguous pass, 4-column tiles: 43 KB, 4-5 CTAs / SM (OLA_NTT_CONTIG_C4=0 disables)
-using T10c4l1 = tile::Cfg<10, 4, 1, 1, 4, 4>;  // one lane per thread in the radix-8 rounds too: OLA_NTT_CONTIG_LN3=1
-using T10c4m3 = tile::Cfg<10, 4, 2, 1, 4, 3>;  // the same with the register cap of 3 CTAs / SM (85 registers, no spills): OLA_NTT_CONTIG_MINB=3
+// (one lane per thread in the radix-8 rounds, and a 3-CTA register cap, were measured and dropped: profiles/r02p_*, r02s_*)
 using T11 = tile::Cfg<11, 4>;
 using T11v2 = tile::Cfg<11, 4, 2, 1, 4, 2>;
 using T11v3 = tile::Cfg<11, 4, 1, 1, 4, 2>;
@@ -578,8 +565,7 @@ static void tile_optin_all(int max_optin) {
     tile_optin<T10v2>(max_optin);
     tile_optin<T10v3>(max_optin);
     tile_optin_contig<T10c4>(max_optin);
-    tile_optin_contig<T10c4m3>(max_optin);
-    tile_optin_contig<T10c4l1>(max_optin);
+
     tile_optin<T11>(max_optin);
     tile_optin<T11v2>(max_optin);
     tile_optin<T11v3>(max_optin);
@@ -595,9 +581,7 @@ static void tile_optin_all(int max_optin) {
     tile_optin_shift<T9>(max_optin, true);
     tile_optin_shift<T10v2>(max_optin, true);
     tile_optin_shift<T10c4>(max_optin, false);
-    tile_optin_shift<T10c4m3>(max_optin, false);
-    tile_optin_shift<T10c4l1>(max_optin, false);
-    tile_optin_shift<T10v3>(max_optin, true);
+
     tile_optin_shift<T11v2>(max_optin, true);
     tile_optin_shift<tile::Cfg<6, 2>>(max_optin, false);
     tile_optin_shift<tile::Cfg<7, 2>>(max_optin, false);
@@ -629,7 +613,7 @@ static void tile_strided_launch(ola_ctx* ctx, const PassArgs& a, size_t ncols, i
     const dim3 g((unsigned)ncosets, (unsigned)(nsub * chunks));
     tile::tile_strided<G, GS, MODE><<<g, G::NT, G::SMEM, ctx->stream>>>(b);
 }
-template <typename G, bool GS, int MODE = 0>
+template <typename G, bool GS, int MODE = 0, bool FULL = false>
 static void tile_contig_launch(ola_ctx* ctx, const PassArgs& a, size_t ncols, int ncosets) {
     PassArgs b = a;
     b.ncols = ncols;
@@ -643,7 +627,7 @@ static void tile_contig_launch(ola_ctx* ctx, const PassArgs& a, size_t ncols, in
         chunks = (groups + b.tiles_per_cta - 1) / b.tiles_per_cta;
     }
     const dim3 g((unsigned)nsub, (unsigned)chunks, (unsigned)ncosets);
-    tile::tile_contig<G, GS, MODE><<<g, G::NT, G::SMEM, ctx->stream>>>(b);
+    tile::tile_contig<G, GS, MODE, FULL><<<g, G::NT, G::SMEM, ctx->stream>>>(b);
 }
 // the default configurations also exist in the shift form (forward network; MODE 1 / 2 = forward / inverse roots)
 template <typename G, bool GS>
@@ -661,8 +645,14 @@ template <typename G, bool GS>
 static void tile_contig_launch_m(ola_ctx* ctx, const PassArgs& a, size_t ncols, int ncosets) {
     if constexpr (!GS) {
         if (tune_shift()) {
-            if (a.inv_roots) tile_contig_launch<G, false, 2>(ctx, a, ncols, ncosets);
-            else tile_contig_launch<G, false, 1>(ctx, a, ncols, ncosets);
+            const bool full = (ncols % G::C) == 0;  // no partial column group: the variant without per-lane predicates
+            if (a.inv_roots) {
+                if (full) tile_contig_launch<G, false, 2, true>(ctx, a, ncols, ncosets);
+                else tile_contig_launch<G, false, 2>(ctx, a, ncols, ncosets);
+            } else {
+                if (full) tile_contig_launch<G, false, 1, true>(ctx, a, ncols, ncosets);
+                else tile_contig_launch<G, false, 1>(ctx, a, ncols, ncosets);
+            }
             return;
         }
     }
@@ -679,7 +669,7 @@ static void tile_strided_dispatch(ola_ctx* ctx, const PassArgs& a, size_t ncols,
         case 10:
             if (v == 1) tile_strided_launch<T10v1, GS>(ctx, a, ncols, ncosets);
             else if (v == 2) tile_strided_launch_m<T10v2, GS>(ctx, a, ncols, ncosets);
-            else if (v == 3) tile_strided_launch_m<T10v3, GS>(ctx, a, ncols, ncosets);
+            else if (v == 3) tile_strided_launch<T10v3, GS>(ctx, a, ncols, ncosets);
             else tile_strided_launch<T10, GS>(ctx, a, ncols, ncosets);
             break;
         case 11:
@@ -711,9 +701,7 @@ static void tile_contig_dispatch(ola_ctx* ctx, const PassArgs& a, size_t ncols, 
         case 8: tile_contig_launch_m<T8, GS>(ctx, a, ncols, ncosets); break;
         case 9: tile_contig_launch_m<T9, GS>(ctx, a, ncols, ncosets); break;
         case 10:
-            if (tune_contig_c4() && tune_contig_ln3() == 1) tile_contig_launch_m<T10c4l1, GS>(ctx, a, ncols, ncosets);
-            else if (tune_contig_c4() && tune_contig_minb() == 3) tile_contig_launch_m<T10c4m3, GS>(ctx, a, ncols, ncosets);
-            else if (tune_contig_c4()) tile_contig_launch_m<T10c4, GS>(ctx, a, ncols, ncosets);
+            if (tune_contig_c4()) tile_contig_launch_m<T10c4, GS>(ctx, a, ncols, ncosets);
             else if (v == 1) tile_contig_launch<T10v1, GS>(ctx, a, ncols, ncosets);
             else if (v == 2) tile_contig_launch<T10v2, GS>(ctx, a, ncols, ncosets);
             else if (v == 3) tile_contig_launch<T10v3, GS>(ctx, a, ncols, ncosets);

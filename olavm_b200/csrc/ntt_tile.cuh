@@ -180,8 +180,9 @@ __device__ __forceinline__ constexpr int row_off(int m) {
 
 // MODE (forward network only): 0 = radix-2 butterflies on canonical products, 1 = shift form with the forward roots,
 // 2 = shift form with the inverse roots (the plain iNTT runs the forward network on inverse roots)
-// NAT: the lanes of a contiguous tile are sub-blocks with consecutive bit-reversed indices (tile_nat) instead of columns
-template <typename G, bool GS, bool CONTIG, int MODE, int I, bool NAT = false>
+// NAT: the lanes of a contiguous tile are sub-blocks with consecutive bit-reversed indices (tile_nat) instead of columns;
+// FULL: every lane of the tile exists (the column count is a multiple of C): no per-lane predicates
+template <typename G, bool GS, bool CONTIG, int MODE, int I, bool NAT = false, bool FULL = false>
 __device__ __forceinline__ void run_step(const Io<CONTIG>& io, uint64_t* __restrict__ x, const uint64_t* __restrict__ tw, int tid) {
     constexpr int l = G::l, C = G::C, P = G::PADLOG;
     constexpr int NR = Sched<l>::NR;
@@ -220,7 +221,7 @@ __device__ __forceinline__ void run_step(const Io<CONTIG>& io, uint64_t* __restr
             } else {
 #pragma unroll
                 for (int ln = 0; ln < LN; ++ln) {
-                    const bool ok = lane0 + ln < io.lanes_valid;
+                    const bool ok = FULL || NAT || lane0 + ln < io.lanes_valid;
                     const uint64_t* p = io.in + (NAT ? io.lane_in[lane0 + ln] : (size_t)(lane0 + ln) * io.in_lane) + rbase;
                     if (SH == 0) {
 #pragma unroll
@@ -254,14 +255,18 @@ __device__ __forceinline__ void run_step(const Io<CONTIG>& io, uint64_t* __restr
             bfly_shift<K, U0, LN, MODE == 2>(v, tw + rd::OFF + qh + (NAT ? (size_t)lane0 * io.twl : 0), NAT ? io.twl : 0,
                                              (LAST && io.apply_scale) ? &io.scale : nullptr);
         if (LAST) {
+            // forward network: a strided pass is never the last one (its outputs stay lazy, no scale), a contiguous pass always
+            // is (canonical outputs) -- ntt.cu forward(); the inverse network decides at run time
+            if constexpr (GS || CONTIG) {
 #pragma unroll
-            for (int m = 0; m < NE; ++m) {
+                for (int m = 0; m < NE; ++m) {
 #pragma unroll
-                for (int ln = 0; ln < LN; ++ln) {
-                    if (MODE == 0 && io.apply_scale)
-                        v[m][ln] = gl::mul(v[m][ln], io.scale);  // (the shift form folds the scale into the last round's twiddles)
-                    else if (!io.lazy_out)
-                        v[m][ln] = gl::canon_fast(v[m][ln]);
+                    for (int ln = 0; ln < LN; ++ln) {
+                        if (MODE == 0 && io.apply_scale)
+                            v[m][ln] = gl::mul(v[m][ln], io.scale);  // (the shift form folds the scale into the last round's twiddles)
+                        else if (!GS || !io.lazy_out)
+                            v[m][ln] = gl::canon_fast(v[m][ln]);
+                    }
                 }
             }
             if (!CONTIG) {
@@ -288,7 +293,7 @@ __device__ __forceinline__ void run_step(const Io<CONTIG>& io, uint64_t* __restr
             } else {
 #pragma unroll
                 for (int ln = 0; ln < LN; ++ln) {
-                    if (lane0 + ln >= io.lanes_valid) continue;
+                    if (!FULL && lane0 + ln >= io.lanes_valid) continue;
                     uint64_t* p = io.out + (size_t)(lane0 + ln) * io.out_lane + rbase;
                     if (SH == 0) {
 #pragma unroll
@@ -312,11 +317,11 @@ __device__ __forceinline__ void run_step(const Io<CONTIG>& io, uint64_t* __restr
     if (!LAST) __syncthreads();
 }
 
-template <typename G, bool GS, bool CONTIG, int MODE, int I, bool NAT = false>
+template <typename G, bool GS, bool CONTIG, int MODE, int I, bool NAT = false, bool FULL = false>
 __device__ __forceinline__ void run_steps(const Io<CONTIG>& io, uint64_t* x, const uint64_t* tw, int tid) {
     static_assert(!(GS && MODE != 0), "the shift form exists for the forward network only");
-    run_step<G, GS, CONTIG, MODE, I, NAT>(io, x, tw, tid);
-    if constexpr (I + 1 < Sched<G::l>::NR) run_steps<G, GS, CONTIG, MODE, I + 1, NAT>(io, x, tw, tid);
+    run_step<G, GS, CONTIG, MODE, I, NAT, FULL>(io, x, tw, tid);
+    if constexpr (I + 1 < Sched<G::l>::NR) run_steps<G, GS, CONTIG, MODE, I + 1, NAT, FULL>(io, x, tw, tid);
 }
 
 // Both kernels are persistent over tiles that share one twiddle table (same sub-block Q, same coset): the table is
@@ -336,7 +341,10 @@ __global__ void __launch_bounds__(G::NT, G::MINB) tile_strided(const PassArgs a)
     const int tid = threadIdx.x;
     const uint32_t coset = blockIdx.x;
     const size_t inner = (size_t)1 << (a.M - l);
-    const size_t tiles_per_sub = inner / C;
+    constexpr int C_LOG = (C == 8) ? 3 : (C == 4) ? 2 : (C == 2) ? 1 : 0;
+    static_assert((1 << C_LOG) == C, "C is 1, 2, 4 or 8");
+    const int tps_log = a.M - l - C_LOG;
+    const size_t tiles_per_sub = (size_t)1 << tps_log;
     const size_t per_q = a.ncols * tiles_per_sub;  // tiles of one sub-block: (column, tile) pairs
     const size_t chunks_per_q = (per_q + a.tiles_per_cta - 1) / a.tiles_per_cta;
     const uint32_t Q = (uint32_t)(blockIdx.y / chunks_per_q);
@@ -361,7 +369,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) tile_strided(const PassArgs a)
         build_twiddles_pow_round<l, 0>(tw, cu, a.brs, tid, G::NT, a.apply_scale ? a.scale : 1);
     __syncthreads();
     for (size_t t = t0; t < t1; ++t) {
-        const size_t col = t / tiles_per_sub, c0 = (t % tiles_per_sub) * C;
+        const size_t col = t >> tps_log, c0 = (t & (tiles_per_sub - 1)) * C;  // tiles_per_sub is a power of two: no 64-bit division per tile
         io.in = a.src + col * a.src_col_stride + coset * a.src_coset_stride + ((size_t)Q << a.M) + c0;
         io.out = a.dst + col * a.dst_col_stride + coset * a.dst_coset_stride + ((size_t)Q << a.M) + c0;
         run_steps<G, GS, false, MODE, 0>(io, x, tw, tid);
@@ -371,7 +379,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) tile_strided(const PassArgs a)
 
 // contiguous pass (M == l): tile = sub-block Q (2^l consecutive elements) of C columns.  grid (sub-blocks, chunks of
 // column groups, cosets)
-template <typename G, bool GS, int MODE = 0>
+template <typename G, bool GS, int MODE = 0, bool FULL = false>
 __global__ void __launch_bounds__(G::NT, G::MINB) tile_contig(const PassArgs a) {
     extern __shared__ __align__(16) uint64_t sm[];
     constexpr int l = G::l, C = G::C, R = 1 << l;
@@ -411,7 +419,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) tile_contig(const PassArgs a) 
         io.in = a.src + col0 * a.src_col_stride + coset * a.src_coset_stride + ((size_t)Q << l);
         io.out = a.dst + col0 * a.dst_col_stride + coset * a.dst_coset_stride + ((size_t)Q << l);
         io.lanes_valid = (int)((a.ncols - col0) < (size_t)C ? (a.ncols - col0) : (size_t)C);
-        run_steps<G, GS, true, MODE, 0>(io, x, tw, tid);
+        run_steps<G, GS, true, MODE, 0, false, FULL>(io, x, tw, tid);
         if (Sched<l>::NR > 1 && g + 1 < g1) __syncthreads();
     }
 }

@@ -1,0 +1,381 @@
+// Lookup-argument columns and the RangeCheck table on the GPU (trace generation next to the prover).
+//
+// Replaces
+//   circuits/src/stark/lookup.rs:68-131          permuted_cols: sort the input and the table column, then ONE sequential merge
+//                                                walk with a LIFO list of skipped table values and a FIFO list of unfilled rows
+//   circuits/src/generation/builtin.rs:249-316   generate_rc_trace (two permuted_cols calls over 2^16 .. 2^22+ rows)
+//
+// The walk is serial in the reference; here it is re-derived as data-parallel steps that produce the SAME columns:
+//   1. S = sort(canonical inputs), T = sort(canonical table)                   (bitonic network, shared-memory inner stages)
+//   2. input i (value v, rank r among the equal inputs) is paired with a table copy of v iff r < #{T == v}: permuted_table[i] = v.
+//      Table entry j (value w, rank r') is paired iff r' < #{S == w}.                                   (binary searches)
+//   3. The unpaired entries are the walk's events in increasing value: an unpaired table entry is PUSHED on the list of unused
+//      values, an unpaired input POPS the most recent one (pushes and pops never share a value: one side has the surplus).  The
+//      walk stops when the table is exhausted, so an unpaired input whose value is >= max(T) pops nothing.  The position of an
+//      event in that order needs no sort: (#pushes before it in T) + (#pops before it in S), two prefix sums.
+//   4. "pop takes the most recent unused push, a pop on an empty list waits" is bracket matching: with depth = running sum of
+//      +1 / -1, a push at depth d (after) and a pop at depth d (before) alternate inside every level, so after sorting the events
+//      by (level, position) each pop is matched by its predecessor iff that is a push of the same level.
+//   5. The unmatched inputs (in row order) receive the never-popped table values (in table order): two compactions.
+// Every step is exact integer work; tests compare with the oracle's statement-by-statement walk on valid lookups, missing
+// values, surplus on either side, duplicates in the table and random 64-bit columns.
+#include "batch.h"
+#include "common.h"
+#include "gl.cuh"
+
+namespace ola {
+namespace lookup {
+
+static constexpr int SORT_TILE = 2048;  // elements sorted per CTA in shared memory (1024 threads, two each)
+
+// ---- bitonic sort of 2^k u64 keys, ascending ----------------------------------------------------------------------------------
+__device__ __forceinline__ void cmp_swap(uint64_t& a, uint64_t& b, bool asc) {
+    if ((a > b) == asc) {
+        const uint64_t t = a;
+        a = b;
+        b = t;
+    }
+}
+// all stages k = 2 .. min(n, SORT_TILE) inside one tile
+__global__ void __launch_bounds__(SORT_TILE / 2) sort_tile_kernel(uint64_t* __restrict__ d, size_t n) {
+    __shared__ uint64_t s[SORT_TILE];
+    const size_t base = (size_t)blockIdx.x * SORT_TILE;
+    const int t = threadIdx.x;
+    const int m = (int)(n < (size_t)SORT_TILE ? n : (size_t)SORT_TILE);
+    for (int i = t; i < m; i += blockDim.x) s[i] = d[base + i];
+    __syncthreads();
+    for (int k = 2; k <= m; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int p = t; p < m / 2; p += blockDim.x) {
+                const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));  // the lower index of the pair
+                const bool asc = (((base + i) & (size_t)k) == 0);
+                cmp_swap(s[i], s[i + j], asc);
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = t; i < m; i += blockDim.x) d[base + i] = s[i];
+}
+// one global step (distance j >= SORT_TILE) of stage k
+__global__ void sort_global_step_kernel(uint64_t* __restrict__ d, size_t n, size_t k, size_t j) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n / 2) return;
+    const size_t i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+    uint64_t a = d[i], b = d[i + j];
+    const bool asc = ((i & k) == 0);
+    if ((a > b) == asc) {
+        d[i] = b;
+        d[i + j] = a;
+    }
+}
+// the steps j = SORT_TILE / 2 .. 1 of stage k (k > SORT_TILE) inside one tile
+__global__ void __launch_bounds__(SORT_TILE / 2) sort_tile_tail_kernel(uint64_t* __restrict__ d, size_t k) {
+    __shared__ uint64_t s[SORT_TILE];
+    const size_t base = (size_t)blockIdx.x * SORT_TILE;
+    const int t = threadIdx.x;
+    for (int i = t; i < SORT_TILE; i += blockDim.x) s[i] = d[base + i];
+    __syncthreads();
+    const bool asc = ((base & k) == 0);  // k > SORT_TILE: one direction for the whole tile
+    for (int j = SORT_TILE >> 1; j > 0; j >>= 1) {
+        for (int p = t; p < SORT_TILE / 2; p += blockDim.x) {
+            const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+            cmp_swap(s[i], s[i + j], asc);
+        }
+        __syncthreads();
+    }
+    for (int i = t; i < SORT_TILE; i += blockDim.x) d[base + i] = s[i];
+}
+static void sort_u64(ola_ctx* ctx, uint64_t* d, size_t n) {  // n a power of two
+    Launch lz(ctx, "lookup_sort");
+    const size_t tiles = n <= (size_t)SORT_TILE ? 1 : n / SORT_TILE;
+    sort_tile_kernel<<<(unsigned)tiles, SORT_TILE / 2, 0, ctx->stream>>>(d, n);
+    for (size_t k = (size_t)SORT_TILE * 2; k <= n; k <<= 1) {
+        for (size_t j = k >> 1; j >= (size_t)SORT_TILE; j >>= 1)
+            sort_global_step_kernel<<<(unsigned)((n / 2 + 255) / 256), 256, 0, ctx->stream>>>(d, n, k, j);
+        sort_tile_tail_kernel<<<(unsigned)tiles, SORT_TILE / 2, 0, ctx->stream>>>(d, k);
+    }
+    check_launch("lookup sort");
+}
+
+// ---- exclusive prefix sums of 32-bit counts (signed values wrap correctly) ---------------------------------------------------------
+static constexpr int SCAN_BLOCK = 1024;
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_block_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t* __restrict__ sums, size_t n) {
+    __shared__ uint32_t s[SCAN_BLOCK];
+    const size_t i = (size_t)blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    const uint32_t v = i < n ? in[i] : 0;
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < SCAN_BLOCK; off <<= 1) {
+        const uint32_t a = threadIdx.x >= off ? s[threadIdx.x - off] : 0;
+        __syncthreads();
+        s[threadIdx.x] += a;
+        __syncthreads();
+    }
+    if (i < n) out[i] = s[threadIdx.x] - v;  // exclusive
+    if (threadIdx.x == SCAN_BLOCK - 1) sums[blockIdx.x] = s[threadIdx.x];
+}
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_sums_kernel(uint32_t* __restrict__ sums, size_t nblocks, uint32_t* __restrict__ total) {
+    // one CTA walks the block sums in chunks of SCAN_BLOCK (at most 2^24 / 2^10 = 16384 of them)
+    __shared__ uint32_t s[SCAN_BLOCK];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (size_t base = 0; base < nblocks; base += SCAN_BLOCK) {
+        const size_t i = base + threadIdx.x;
+        const uint32_t v = i < nblocks ? sums[i] : 0;
+        s[threadIdx.x] = v;
+        __syncthreads();
+        for (int off = 1; off < SCAN_BLOCK; off <<= 1) {
+            const uint32_t a = threadIdx.x >= off ? s[threadIdx.x - off] : 0;
+            __syncthreads();
+            s[threadIdx.x] += a;
+            __syncthreads();
+        }
+        if (i < nblocks) sums[i] = carry + s[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == SCAN_BLOCK - 1) carry += s[threadIdx.x];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+__global__ void scan_add_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ sums, size_t n) {
+    const size_t i = (size_t)blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    if (i < n) out[i] += sums[blockIdx.x];
+}
+// out[i] = sum_{k < i} in[k];  *total (device) = the sum of all
+static void exclusive_scan(ola_ctx* ctx, const uint32_t* in, uint32_t* out, uint32_t* sums, uint32_t* total, size_t n) {
+    const size_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    scan_block_kernel<<<(unsigned)nb, SCAN_BLOCK, 0, ctx->stream>>>(in, out, sums, n);
+    scan_sums_kernel<<<1, SCAN_BLOCK, 0, ctx->stream>>>(sums, nb, total);
+    scan_add_kernel<<<(unsigned)nb, SCAN_BLOCK, 0, ctx->stream>>>(out, sums, n);
+    check_launch("lookup scan");
+}
+
+// ---- steps 2-5 ------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ size_t lower_bound(const uint64_t* __restrict__ a, size_t n, uint64_t v) {  // first index with a[i] >= v
+    size_t lo = 0, hi = n;
+    while (lo < hi) {
+        const size_t mid = (lo + hi) >> 1;
+        if (a[mid] < v)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ size_t upper_bound(const uint64_t* __restrict__ a, size_t n, uint64_t v) {  // first index with a[i] > v
+    size_t lo = 0, hi = n;
+    while (lo < hi) {
+        const size_t mid = (lo + hi) >> 1;
+        if (a[mid] <= v)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+__global__ void canon_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = gl::canon(in[i]);
+}
+
+// step 2: pairing.  pop[i] = 1: input i is unpaired and its value is below max(T) (it pops);  hole[i] = 1: unpaired at or above
+// max(T) (nothing to pop: the walk has ended).  push[j] = 1: table entry j is unpaired.  Paired inputs get their table value.
+__global__ void classify_kernel(const uint64_t* __restrict__ S, const uint64_t* __restrict__ T, size_t n, uint64_t* __restrict__ PT,
+                                uint32_t* __restrict__ pop, uint32_t* __restrict__ hole, uint32_t* __restrict__ push) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t tmax = T[n - 1];
+    {
+        const uint64_t v = S[i];
+        const size_t r = i - lower_bound(S, n, v);
+        const size_t cnt_t = upper_bound(T, n, v) - lower_bound(T, n, v);
+        const bool paired = r < cnt_t;
+        PT[i] = paired ? v : 0;
+        pop[i] = (!paired && v < tmax) ? 1u : 0u;
+        hole[i] = (!paired && v >= tmax) ? 1u : 0u;
+    }
+    {
+        const uint64_t w = T[i];
+        const size_t r = i - lower_bound(T, n, w);
+        const size_t cnt_s = upper_bound(S, n, w) - lower_bound(S, n, w);
+        push[i] = (r < cnt_s) ? 0u : 1u;
+    }
+}
+// step 3: the events in walk order.  ev_delta[e] = +1 (push) / -1 (pop), ev_ref[e] = j (push) or n + i (pop)
+__global__ void events_kernel(const uint64_t* __restrict__ S, const uint64_t* __restrict__ T, size_t n, const uint32_t* __restrict__ pop,
+                              const uint32_t* __restrict__ push, const uint32_t* __restrict__ cum_pop, const uint32_t* __restrict__ cum_push,
+                              uint32_t total_pop, uint32_t total_push, uint32_t* __restrict__ ev_delta, uint32_t* __restrict__ ev_ref) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (pop[i]) {  // pushes of smaller values come first (none has the same value)
+        const size_t lb = lower_bound(T, n, S[i]);
+        const uint32_t e = cum_pop[i] + (lb < n ? cum_push[lb] : total_push);
+        ev_delta[e] = 0xFFFFFFFFu;
+        ev_ref[e] = (uint32_t)(n + i);
+    }
+    if (push[i]) {
+        const size_t lb = lower_bound(S, n, T[i]);
+        const uint32_t e = cum_push[i] + (lb < n ? cum_pop[lb] : total_pop);
+        ev_delta[e] = 1u;
+        ev_ref[e] = (uint32_t)i;
+    }
+}
+// step 4a: sort keys (level, position).  depth_before[e] = exclusive sum of the deltas; a push sits at level depth_before + 1,
+// a pop at level depth_before; levels are offset by n_events so that they stay non-negative
+__global__ void level_keys_kernel(const uint32_t* __restrict__ ev_delta, const uint32_t* __restrict__ depth_before, uint32_t n_events, size_t cap,
+                                  uint64_t* __restrict__ keys) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= cap) return;
+    if (e >= n_events) {
+        keys[e] = ~0ULL;  // padding sorts last
+        return;
+    }
+    const int32_t level = (int32_t)depth_before[e] + (ev_delta[e] == 1u ? 1 : 0);
+    keys[e] = ((uint64_t)(uint32_t)(level + (int32_t)n_events) << 32) | (uint64_t)e;
+}
+// step 4b: a pop whose predecessor in (level, position) order is a push of the same level takes that push's table value
+__global__ void match_kernel(const uint64_t* __restrict__ keys, uint32_t n_events, const uint32_t* __restrict__ ev_delta, const uint32_t* __restrict__ ev_ref,
+                             const uint64_t* __restrict__ T, size_t n, uint64_t* __restrict__ PT, uint32_t* __restrict__ hole, uint32_t* __restrict__ left) {
+    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_events) return;
+    const uint64_t key = keys[s];
+    const uint32_t e = (uint32_t)key;
+    if (ev_delta[e] == 1u) {  // a push: it stays on the list unless the next event of its level pops it
+        bool popped = false;
+        if (s + 1 < n_events) {
+            const uint64_t nk = keys[s + 1];
+            popped = (nk >> 32) == (key >> 32) && ev_delta[(uint32_t)nk] != 1u;
+        }
+        left[ev_ref[e]] = popped ? 0u : 1u;
+        return;
+    }
+    const uint32_t i = ev_ref[e] - (uint32_t)n;
+    bool matched = false;
+    if (s > 0) {
+        const uint64_t pk = keys[s - 1];
+        if ((pk >> 32) == (key >> 32) && ev_delta[(uint32_t)pk] == 1u) {
+            PT[i] = T[ev_ref[(uint32_t)pk]];
+            matched = true;
+        }
+    }
+    if (!matched) hole[i] = 1u;  // popped an empty list: filled at the end
+}
+// step 5: the k-th unfilled row takes the k-th value left on the list
+__global__ void compact_left_kernel(const uint64_t* __restrict__ T, size_t n, const uint32_t* __restrict__ left, const uint32_t* __restrict__ cum_left,
+                                    uint64_t* __restrict__ left_vals) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n && left[j]) left_vals[cum_left[j]] = T[j];
+}
+__global__ void fill_holes_kernel(size_t n, const uint32_t* __restrict__ hole, const uint32_t* __restrict__ cum_hole, const uint64_t* __restrict__ left_vals,
+                                  uint64_t* __restrict__ PT) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && hole[i]) PT[i] = left_vals[cum_hole[i]];
+}
+__global__ void zero_u32_kernel(uint32_t* p, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0;
+}
+
+struct Buf {
+    uint64_t* p = nullptr;
+    explicit Buf(size_t n_u64) { dev_alloc(&p, n_u64 ? n_u64 : 1); }
+    ~Buf() {
+        if (p) dev_free(p);
+    }
+    Buf(const Buf&) = delete;
+    Buf& operator=(const Buf&) = delete;
+    uint32_t* u32() { return reinterpret_cast<uint32_t*>(p); }
+};
+
+// d_inputs, d_table: n elements each (any representatives); d_perm_inputs, d_perm_table: n each.  n a power of two >= 2.
+void permuted_cols(ola_ctx* ctx, const uint64_t* d_inputs, const uint64_t* d_table, size_t n, uint64_t* d_perm_inputs, uint64_t* d_perm_table) {
+    OLA_CHECK(n >= 2 && (n & (n - 1)) == 0 && n <= ((size_t)1 << 24), OLA_ERR_INVALID_ARG, "permuted_cols: the column length must be a power of two in [2, 2^24]");
+    const unsigned gb = (unsigned)((n + 255) / 256);
+    uint64_t* S = d_perm_inputs;  // the sorted inputs ARE the permuted inputs (lookup.rs:130)
+    Buf T(n);
+    canon_kernel<<<gb, 256, 0, ctx->stream>>>(d_inputs, S, n);
+    canon_kernel<<<gb, 256, 0, ctx->stream>>>(d_table, T.p, n);
+    sort_u64(ctx, S, n);
+    sort_u64(ctx, T.p, n);
+
+    Launch lz(ctx, "lookup_walk");
+    // 32-bit work arrays: pop, hole, push, left | cum_pop, cum_push, cum_x | block sums | totals
+    const size_t nb = (2 * n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    Buf w32((7 * n + nb + 16) / 2 + 8);
+    uint32_t* pop = w32.u32();
+    uint32_t* hole = pop + n;
+    uint32_t* push = hole + n;
+    uint32_t* left = push + n;
+    uint32_t* cum_a = left + n;
+    uint32_t* cum_b = cum_a + n;
+    uint32_t* cum_c = cum_b + n;
+    uint32_t* sums = cum_c + n;
+    uint32_t* totals = sums + nb;  // [0] pops, [1] pushes, [2] scratch
+    classify_kernel<<<gb, 256, 0, ctx->stream>>>(S, T.p, n, d_perm_table, pop, hole, push);
+    exclusive_scan(ctx, pop, cum_a, sums, totals + 0, n);
+    exclusive_scan(ctx, push, cum_b, sums, totals + 1, n);
+    uint32_t h_tot[2];
+    OLA_CUDA(cudaMemcpyAsync(h_tot, totals, sizeof(h_tot), cudaMemcpyDeviceToHost, ctx->stream));
+    OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+    const uint32_t n_pop = h_tot[0], n_push = h_tot[1], n_ev = n_pop + n_push;
+    zero_u32_kernel<<<gb, 256, 0, ctx->stream>>>(left, n);
+    if (n_ev) {
+        size_t cap = 2;
+        while (cap < n_ev) cap <<= 1;
+        Buf ev(cap + cap + cap);  // ev_delta | ev_ref | depth (u32 each, cap entries) + keys (u64, cap entries)
+        uint32_t* ev_delta = ev.u32();
+        uint32_t* ev_ref = ev_delta + cap;
+        uint32_t* depth = ev_ref + cap;
+        uint64_t* keys = ev.p + (3 * cap + 1) / 2 + 1;
+        Buf ev_sums((cap / SCAN_BLOCK + 2) / 2 + 2);
+        events_kernel<<<gb, 256, 0, ctx->stream>>>(S, T.p, n, pop, push, cum_a, cum_b, n_pop, n_push, ev_delta, ev_ref);
+        exclusive_scan(ctx, ev_delta, depth, ev_sums.u32(), totals + 2, n_ev);
+        level_keys_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, ctx->stream>>>(ev_delta, depth, n_ev, cap, keys);
+        sort_u64(ctx, keys, cap);
+        match_kernel<<<(unsigned)((n_ev + 255) / 256), 256, 0, ctx->stream>>>(keys, n_ev, ev_delta, ev_ref, T.p, n, d_perm_table, hole, left);
+        check_launch("lookup match");
+        OLA_CUDA(cudaStreamSynchronize(ctx->stream));  // ev / ev_sums are released below: the stream-ordered pool makes that safe, the sync keeps errors local
+    }
+    // a table entry that was never an event is paired; one that was pushed and never popped is left over
+    exclusive_scan(ctx, left, cum_c, sums, totals + 2, n);
+    Buf left_vals(n);
+    compact_left_kernel<<<gb, 256, 0, ctx->stream>>>(T.p, n, left, cum_c, left_vals.p);
+    exclusive_scan(ctx, hole, cum_a, sums, totals + 2, n);
+    fill_holes_kernel<<<gb, 256, 0, ctx->stream>>>(n, hole, cum_a, left_vals.p, d_perm_table);
+    check_launch("lookup fill");
+    OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+// ---- generate_rc_trace (builtin.rs:249-316) ---------------------------------------------------------------------------------------------
+// vals[nrows], kinds[nrows] in {0 cpu, 1 memory sort, 2 memory region, 3 comparison} (one u64 each); out = [12][n] column-major
+__global__ void rc_fill_kernel(const uint64_t* __restrict__ vals, const uint64_t* __restrict__ kinds, size_t nrows, size_t n, uint64_t* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool live = i < nrows;
+    const uint64_t v = live ? gl::canon(vals[i]) : 0;
+    const uint64_t k = live ? kinds[i] : 4;
+    out[0 * n + i] = k == 0;          // CPU_FILTER
+    out[1 * n + i] = k == 1;          // MEMORY_SORT_FILTER
+    out[2 * n + i] = k == 2;          // MEMORY_REGION_FILTER
+    out[3 * n + i] = k == 3;          // CMP_FILTER
+    out[4 * n + i] = v;               // VAL
+    out[5 * n + i] = v & 0xFFFF;      // LIMB_LO  (split_u16_limbs_from_field, trace.rs:414-418)
+    out[6 * n + i] = v >> 16;         // LIMB_HI
+    out[9 * n + i] = i < 65536 ? i : 65535;  // FIX_RANGE_CHECK_U16, padded with its last value (builtin.rs:278-293)
+}
+void rangecheck_trace(ola_ctx* ctx, const uint64_t* d_vals, const uint64_t* d_kinds, size_t nrows, uint32_t log_n, uint64_t* d_out) {
+    const size_t n = (size_t)1 << log_n;
+    OLA_CHECK(log_n >= 16 && nrows <= n, OLA_ERR_INVALID_ARG, "RangeCheck table: at least 2^16 rows (RANGE_CHECK_U16_SIZE) and room for every value");
+    {
+        Launch lz(ctx, "gen_rc_fill");
+        rc_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_vals, d_kinds, nrows, n, d_out);
+        check_launch("rc_fill_kernel");
+    }
+    permuted_cols(ctx, d_out + 5 * n, d_out + 9 * n, n, d_out + 7 * n, d_out + 10 * n);  // LIMB_LO_PERMUTED, FIX_..._PERMUTED_LO
+    permuted_cols(ctx, d_out + 6 * n, d_out + 9 * n, n, d_out + 8 * n, d_out + 11 * n);  // LIMB_HI_PERMUTED, FIX_..._PERMUTED_HI
+}
+
+}  // namespace lookup
+}  // namespace ola

@@ -119,8 +119,8 @@ GL_HD W96 w96_mul(uint64_t x, uint64_t w) {
 //     V 2^r = w0' + w1 t + w2 t^2   (mod p),  all three words unsigned.
 // Times t^q, folded with t^2 = t - 1, t^3 = -1:
 //   q = 0:  (w1:w0') + w2 (2^32 - 1)
-//   q = 1:  (w0' + w1) t - (w1 + w2)
-//   q = 2:  (w0' - w2) t - (w0' + w1)
+//   q = 1:  (w0' + w1) t - (w1 + w2)  =  w1 (2^32 - 1) + (w0' t - w2)
+//   q = 2:  (w0' - w2) t - (w0' + w1) =  w0' (2^32 - 1) - (w1 + w2 t)
 template <int E>
 GL_HD W96 w96_mul_pow2(W96 v) {
     static_assert(E > 0 && E < 96 && E % 32 != 0, "shift out of range");
@@ -139,31 +139,27 @@ GL_HD W96 w96_mul_pow2(W96 v) {
             : "r"(w0), "r"(w1), "r"(w2));
         return o;
     }
-    uint32_t p0, p1, q0, q1;
+    // q = 1:  w1 (t - 1) + (w0' t - w2);   q = 2:  w0' (t - 1) - (w1 + w2 t):  a negated two-word value, then one multiply-add
+    // chain by 2^32 - 1 (IADD3 + IMAD.HI with carry) into it
+    const uint32_t m = (q == 1) ? w1 : w0;
     if (q == 1) {
-        asm("add.cc.u32 %0, %2, %3;\n\t"
-            "addc.u32   %1, 0, 0;"
-            : "=r"(p0), "=r"(p1)
-            : "r"(w1), "r"(w2));
-        asm("add.cc.u32 %0, %2, %3;\n\t"
-            "addc.u32   %1, 0, 0;"
-            : "=r"(q0), "=r"(q1)
-            : "r"(w0), "r"(w1));
-    } else {
-        asm("add.cc.u32 %0, %2, %3;\n\t"
-            "addc.u32   %1, 0, 0;"
-            : "=r"(p0), "=r"(p1)
-            : "r"(w0), "r"(w1));
-        asm("sub.cc.u32 %0, %2, %3;\n\t"
-            "subc.u32   %1, 0, 0;"
-            : "=r"(q0), "=r"(q1)
+        asm("sub.cc.u32  %0, 0, %4;\n\t"
+            "subc.cc.u32 %1, %3, 0;\n\t"
+            "subc.u32    %2, 0, 0;"
+            : "=r"(o.a), "=r"(o.b), "=r"(o.c)
             : "r"(w0), "r"(w2));
+    } else {
+        asm("sub.cc.u32  %0, 0, %3;\n\t"
+            "subc.cc.u32 %1, 0, %4;\n\t"
+            "subc.u32    %2, 0, 0;"
+            : "=r"(o.a), "=r"(o.b), "=r"(o.c)
+            : "r"(w1), "r"(w2));
     }
-    asm("sub.cc.u32  %0, 0, %5;\n\t"
-        "subc.cc.u32 %1, %3, %6;\n\t"
-        "subc.u32    %2, %4, 0;"
-        : "=r"(o.a), "=r"(o.b), "=r"(o.c)
-        : "r"(q0), "r"(q1), "r"(p0), "r"(p1));
+    asm("mad.lo.cc.u32  %0, %3, 0xffffffff, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, 0xffffffff, %1;\n\t"
+        "addc.u32       %2, %2, 0;"
+        : "+r"(o.a), "+r"(o.b), "+r"(o.c)
+        : "r"(m));
     return o;
 #else
 #if defined(W96_CHECK_BOUNDS)

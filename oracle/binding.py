@@ -94,6 +94,10 @@ def _set_sigs(L):
     L.orc_table_columns.restype = _int
     L.orc_air_constraints.argtypes = [_int, _u64p, _u64p, _u64, _u64p, ctypes.POINTER(_int), _int]
     L.orc_air_constraints.restype = _int
+    L.orc_permuted_cols.argtypes = [_u64p, _u64p, _sz, _u64p, _u64p]
+    L.orc_permuted_cols.restype = None
+    L.orc_generate_rc_trace.argtypes = [_u64p, ctypes.POINTER(ctypes.c_uint8), _sz, _u64p, _sz]
+    L.orc_generate_rc_trace.restype = _sz
     L.orc_compress_challenge.argtypes = [ctypes.POINTER(ctypes.c_void_p), _u32, _sz]
     L.orc_compress_challenge.restype = _u64
 
@@ -322,6 +326,28 @@ def air_constraints(table_id, lv, nv, compress_challenge=0):
     if n < 0 or n > cap:
         raise StarkError("air_constraints: unknown table")
     return vals[:n].copy(), kinds[:n].copy()
+
+
+def permuted_cols(inputs, table):
+    """lookup.rs:68-131: (permuted inputs, permuted table) of the Halo2-style lookup argument."""
+    a = np.ascontiguousarray(inputs, dtype=np.uint64).reshape(-1)
+    t = np.ascontiguousarray(table, dtype=np.uint64).reshape(-1)
+    assert a.shape == t.shape
+    pi, pt = np.empty_like(a), np.empty_like(a)
+    lib().orc_permuted_cols(_p(a), _p(t), a.shape[0], _p(pi), _p(pt))
+    return pi, pt
+
+
+def generate_rc_trace(vals, kinds):
+    """generate_rc_trace (builtin.rs:249-316): the 12-column RangeCheck table of the given (value, looking table) rows."""
+    v = np.ascontiguousarray(vals, dtype=np.uint64).reshape(-1)
+    k = np.ascontiguousarray(kinds, dtype=np.uint8).reshape(-1)
+    assert v.shape == k.shape
+    kp = k.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
+    n = int(lib().orc_generate_rc_trace(_p(v), kp, v.shape[0], None, 0))
+    out = np.empty((12, n), dtype=np.uint64)
+    lib().orc_generate_rc_trace(_p(v), kp, v.shape[0], _p(out), n)
+    return out
 
 
 def compress_challenge(columns):

@@ -36,6 +36,10 @@ void orc_two_to_one(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]);
 void orc_challenger_permute(uint64_t state[12]);
 void orc_hash_rows(const uint64_t *rows, size_t nrows, size_t ncols, uint64_t *digests);
 
+/* lookup.c */
+void orc_permuted_cols(const uint64_t *inputs, const uint64_t *table, size_t n, uint64_t *permuted_inputs, uint64_t *permuted_table);
+size_t orc_generate_rc_trace(const uint64_t *vals, const uint8_t *kinds, size_t nrows, uint64_t *out, size_t out_cap_rows);
+
 /* blake3.c */
 void orc_blake3(const uint8_t *in, size_t len, uint8_t out[32]);
 void orc_blake3_hash_no_pad(const uint64_t *in, size_t n, uint64_t out[4]);

@@ -281,6 +281,22 @@ int ola_verify_subsystem_cfg(int hasher, const int* table_ids, uint32_t ntables,
  * pointers. */
 int ola_generate_poseidon_trace(ola_ctx* ctx, const uint64_t* inputs, const uint64_t* filters, size_t nrows, uint32_t log_n, uint64_t* out,
                                 int on_device);
+/* permuted_cols (circuits/src/stark/lookup.rs:68-131): the permuted input / permuted table pair of the Halo2-style lookup
+ * argument (eval_lookups, lookup.rs:13-35) for one input column and one table column of n elements, n a power of two in
+ * [2, 2^24].  permuted_inputs = the sorted canonical inputs; permuted_table = the reference's merge walk (matching table
+ * value on the first occurrence of an input value, otherwise the most recently skipped table value, unfilled rows taking the
+ * values never used, in order) -- computed here as sorts, prefix sums and a bracket matching on the GPU, same columns.
+ * on_device: all four pointers are device pointers. */
+int ola_permuted_cols(ola_ctx* ctx, const uint64_t* inputs, const uint64_t* table, size_t n, uint64_t* permuted_inputs, uint64_t* permuted_table,
+                      int on_device);
+/* generate_rc_trace (circuits/src/generation/builtin.rs:249-316) from the executor's RangeCheckRow list
+ * (core/src/trace/trace.rs:401-425): vals[nrows] and kinds[nrows] (which table looks the value up: 0 cpu, 1 memory sort,
+ * 2 memory region, 3 comparison -- the filter column that is 1 in that row) -> the column-major RangeCheck table
+ * out [12][2^log_n] (builtins/rangecheck/columns.rs:27-40: 4 filters, val, limb_lo, limb_hi, the two permuted limb columns,
+ * the fixed 0..2^16-1 column padded with its last value, its two permuted copies); log_n >= 16 and nrows <= 2^log_n.
+ * on_device: all three pointers are device pointers. */
+int ola_generate_rangecheck_trace(ola_ctx* ctx, const uint64_t* vals, const uint64_t* kinds, size_t nrows, uint32_t log_n, uint64_t* out,
+                                  int on_device);
 /* The compress challenge of the Bitwise / Program tables: a fresh Poseidon Challenger observes `ncols` HOST columns of n
  * elements, column after column, and squeezes one element (generate_bitwise_trace, generation/builtin.rs:118-131: the 12
  * limb columns; generate_prog_trace, generation/prog.rs:23-29: the 8 interleaved root limbs as one column).  A duplex

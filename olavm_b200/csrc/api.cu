@@ -630,6 +630,40 @@ int ola_generate_poseidon_trace(ola_ctx* ctx, const uint64_t* inputs, const uint
         to_host(ctx, out, d_out.p, 134 * n);
     });
 }
+int ola_permuted_cols(ola_ctx* ctx, const uint64_t* inputs, const uint64_t* table, size_t n, uint64_t* permuted_inputs, uint64_t* permuted_table,
+                      int on_device) {
+    if (!ctx || !inputs || !table || !permuted_inputs || !permuted_table) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        if (on_device) {
+            ola::lookup::permuted_cols(ctx, inputs, table, n, permuted_inputs, permuted_table);
+            return;
+        }
+        OLA_CHECK(n >= 2 && (n & (n - 1)) == 0 && n <= ((size_t)1 << 24), OLA_ERR_INVALID_ARG, "permuted_cols: the column length must be a power of two in [2, 2^24]");
+        DevBuf d_in(n), d_tab(n), d_pi(n), d_pt(n);
+        to_device(ctx, d_in.p, inputs, n);
+        to_device(ctx, d_tab.p, table, n);
+        ola::lookup::permuted_cols(ctx, d_in.p, d_tab.p, n, d_pi.p, d_pt.p);
+        to_host(ctx, permuted_inputs, d_pi.p, n);
+        to_host(ctx, permuted_table, d_pt.p, n);
+    });
+}
+int ola_generate_rangecheck_trace(ola_ctx* ctx, const uint64_t* vals, const uint64_t* kinds, size_t nrows, uint32_t log_n, uint64_t* out,
+                                  int on_device) {
+    if (!ctx || ((!vals || !kinds) && nrows) || !out || log_n < 16 || log_n > 24 || nrows > ((size_t)1 << log_n)) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        const size_t n = (size_t)1 << log_n;
+        if (on_device) {
+            ola::lookup::rangecheck_trace(ctx, vals, kinds, nrows, log_n, out);
+            return;
+        }
+        for (size_t i = 0; i < nrows; ++i) OLA_CHECK(kinds[i] <= 3, OLA_ERR_INVALID_ARG, "RangeCheck row kind must be 0 (cpu), 1 (memory sort), 2 (memory region) or 3 (comparison)");
+        DevBuf d_v(std::max<size_t>(nrows, 1)), d_k(std::max<size_t>(nrows, 1)), d_out(12 * n);
+        if (nrows) to_device(ctx, d_v.p, vals, nrows);
+        if (nrows) to_device(ctx, d_k.p, kinds, nrows);
+        ola::lookup::rangecheck_trace(ctx, d_v.p, d_k.p, nrows, log_n, d_out.p);
+        to_host(ctx, out, d_out.p, 12 * n);
+    });
+}
 int ola_compress_challenge(const uint64_t* const* cols, uint32_t ncols, size_t n, uint64_t* beta_out) {
     if ((!cols && ncols) || !beta_out) return OLA_ERR_INVALID_ARG;
     try {

@@ -9,5 +9,6 @@
 #include "fri.cu"
 #include "stark.cu"
 #include "generation.cu"
+#include "lookup.cu"
 #include "nccl_comm.cu"
 #include "api.cu"

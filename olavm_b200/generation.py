@@ -1,6 +1,7 @@
 """Mirror of the trace-generation tail (circuits/src/generation), the step directly in front of prove_with_traces:
 `generate_poseidon_trace` (generation/poseidon.rs:5-130, the round states of core/src/util/poseidon_utils.rs included)
-on the GPU, and the Bitwise / Program compress challenge (generation/builtin.rs:118-131, generation/prog.rs:23-29)."""
+on the GPU, `permuted_cols` (stark/lookup.rs:68-131) and `generate_rc_trace` (generation/builtin.rs:249-316) on the GPU,
+and the Bitwise / Program compress challenge (generation/builtin.rs:118-131, generation/prog.rs:23-29)."""
 import ctypes
 
 import numpy as np
@@ -24,6 +25,32 @@ def generate_poseidon_trace(ctx, inputs, filters=None, log_n=None):
             raise ValueError("one filter quadruple per input")
     out = np.empty((134, 1 << log_n), dtype=np.uint64)
     ctx.check(ctx._lib.ola_generate_poseidon_trace(ctx.handle, _lib.hptr(a) if k else None, _lib.hptr(f), k, log_n, _lib.hptr(out), 0))
+    return out
+
+
+def permuted_cols(ctx, inputs, table):
+    """permuted_cols (stark/lookup.rs:68-131): (permuted inputs, permuted table) of one lookup, on the GPU."""
+    a = np.ascontiguousarray(inputs, dtype=np.uint64).reshape(-1)
+    t = np.ascontiguousarray(table, dtype=np.uint64).reshape(-1)
+    if a.shape != t.shape:
+        raise ValueError("input and table columns of one length")
+    pi, pt = np.empty_like(a), np.empty_like(a)
+    ctx.check(ctx._lib.ola_permuted_cols(ctx.handle, _lib.hptr(a), _lib.hptr(t), a.shape[0], _lib.hptr(pi), _lib.hptr(pt), 0))
+    return pi, pt
+
+
+def generate_rc_trace(ctx, vals, kinds, log_n=None):
+    """generate_rc_trace (generation/builtin.rs:249-316): values and the table that looks each one up (0 cpu, 1 memory
+    sort, 2 memory region, 3 comparison) -> the RangeCheck table [12, 2^log_n] (log_n >= 16)."""
+    v = np.ascontiguousarray(vals, dtype=np.uint64).reshape(-1)
+    k = np.ascontiguousarray(kinds, dtype=np.uint64).reshape(-1)
+    if v.shape != k.shape:
+        raise ValueError("one kind per value")
+    if log_n is None:
+        log_n = max(16, (max(v.shape[0], 1) - 1).bit_length())
+    out = np.empty((12, 1 << log_n), dtype=np.uint64)
+    ctx.check(ctx._lib.ola_generate_rangecheck_trace(ctx.handle, _lib.hptr(v) if v.shape[0] else None, _lib.hptr(k) if v.shape[0] else None,
+                                                      v.shape[0], log_n, _lib.hptr(out), 0))
     return out
 
 

@@ -297,6 +297,21 @@ int ola_permuted_cols(ola_ctx* ctx, const uint64_t* inputs, const uint64_t* tabl
  * on_device: all three pointers are device pointers. */
 int ola_generate_rangecheck_trace(ola_ctx* ctx, const uint64_t* vals, const uint64_t* kinds, size_t nrows, uint32_t log_n, uint64_t* out,
                                   int on_device);
+/* generate_bitwise_trace (circuits/src/generation/builtin.rs:35-206) from the executor's BitwiseCombinedRow list
+ * (core/src/trace/trace.rs:368-399): tags[nrows] (c.opcode: 1 << Opcode::AND / OR / XOR), op0 / op1 / res[nrows] -> the
+ * column-major Bitwise table out [59][2^log_n] (builtins/bitwise/columns.rs:23-62), log_n >= 18 (3 * 2^16 fixed rows), and the
+ * table's compress challenge *beta_out (the (trace, beta) pair the reference returns; beta is ola_prove's
+ * compress_challenges entry for the Bitwise table).  Row fill, the beta-compressed limb triples and the sixteen permuted_cols
+ * run on the GPU; the challenge is the library's host transcript over the twelve limb columns.  The table is the one the
+ * reference produces, including its handling of the fourth limb (columns 8, 12 and 16 stay zero: builtin.rs:66, :71, :76
+ * write it to the first column of the next range, which is overwritten).  on_device: tags, op0, op1, res and out are device
+ * pointers (beta_out is always a host pointer). */
+int ola_generate_bitwise_trace(ola_ctx* ctx, const uint64_t* tags, const uint64_t* op0, const uint64_t* op1, const uint64_t* res, size_t nrows,
+                               uint32_t log_n, uint64_t* out, uint64_t* beta_out, int on_device);
+/* generate_cmp_trace (circuits/src/generation/builtin.rs:208-247): cells [nrows][6] = (op0, op1, gte, abs_diff, abs_diff_inv,
+ * filter_looking_rc) as the executor recorded them (CmpRow) -> the column-major Cmp table out [6][2^log_n]
+ * (builtins/cmp/columns.rs:16-22); padding rows are (1, 0, 1, 1, 1, 0). */
+int ola_generate_cmp_trace(ola_ctx* ctx, const uint64_t* cells, size_t nrows, uint32_t log_n, uint64_t* out, int on_device);
 /* The compress challenge of the Bitwise / Program tables: a fresh Poseidon Challenger observes `ncols` HOST columns of n
  * elements, column after column, and squeezes one element (generate_bitwise_trace, generation/builtin.rs:118-131: the 12
  * limb columns; generate_prog_trace, generation/prog.rs:23-29: the 8 interleaved root limbs as one column).  A duplex

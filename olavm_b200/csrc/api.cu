@@ -664,6 +664,42 @@ int ola_generate_rangecheck_trace(ola_ctx* ctx, const uint64_t* vals, const uint
         to_host(ctx, out, d_out.p, 12 * n);
     });
 }
+int ola_generate_bitwise_trace(ola_ctx* ctx, const uint64_t* tags, const uint64_t* op0, const uint64_t* op1, const uint64_t* res, size_t nrows,
+                               uint32_t log_n, uint64_t* out, uint64_t* beta_out, int on_device) {
+    if (!ctx || ((!tags || !op0 || !op1 || !res) && nrows) || !out || !beta_out || log_n < 18 || log_n > 24 || nrows > ((size_t)1 << log_n))
+        return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        const size_t n = (size_t)1 << log_n;
+        if (on_device) {
+            *beta_out = ola::lookup::bitwise_trace(ctx, tags, op0, op1, res, nrows, log_n, out);
+            return;
+        }
+        const size_t m = std::max<size_t>(nrows, 1);
+        DevBuf d_t(m), d_a(m), d_b(m), d_r(m), d_out(59 * n);
+        if (nrows) {
+            to_device(ctx, d_t.p, tags, nrows);
+            to_device(ctx, d_a.p, op0, nrows);
+            to_device(ctx, d_b.p, op1, nrows);
+            to_device(ctx, d_r.p, res, nrows);
+        }
+        *beta_out = ola::lookup::bitwise_trace(ctx, d_t.p, d_a.p, d_b.p, d_r.p, nrows, log_n, d_out.p);
+        to_host(ctx, out, d_out.p, 59 * n);
+    });
+}
+int ola_generate_cmp_trace(ola_ctx* ctx, const uint64_t* cells, size_t nrows, uint32_t log_n, uint64_t* out, int on_device) {
+    if (!ctx || (!cells && nrows) || !out || log_n < 1 || log_n > 28 || nrows > ((size_t)1 << log_n)) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        const size_t n = (size_t)1 << log_n;
+        if (on_device) {
+            ola::lookup::cmp_trace(ctx, cells, nrows, log_n, out);
+            return;
+        }
+        DevBuf d_c(std::max<size_t>(nrows * 6, 1)), d_out(6 * n);
+        if (nrows) to_device(ctx, d_c.p, cells, nrows * 6);
+        ola::lookup::cmp_trace(ctx, d_c.p, nrows, log_n, d_out.p);
+        to_host(ctx, out, d_out.p, 6 * n);
+    });
+}
 int ola_compress_challenge(const uint64_t* const* cols, uint32_t ncols, size_t n, uint64_t* beta_out) {
     if ((!cols && ncols) || !beta_out) return OLA_ERR_INVALID_ARG;
     try {

@@ -22,6 +22,9 @@
 #include "batch.h"
 #include "common.h"
 #include "gl.cuh"
+#include "stark_types.h"
+
+#include <vector>
 
 namespace ola {
 namespace lookup {
@@ -375,6 +378,101 @@ void rangecheck_trace(ola_ctx* ctx, const uint64_t* d_vals, const uint64_t* d_ki
     }
     permuted_cols(ctx, d_out + 5 * n, d_out + 9 * n, n, d_out + 7 * n, d_out + 10 * n);  // LIMB_LO_PERMUTED, FIX_..._PERMUTED_LO
     permuted_cols(ctx, d_out + 6 * n, d_out + 9 * n, n, d_out + 8 * n, d_out + 11 * n);  // LIMB_HI_PERMUTED, FIX_..._PERMUTED_HI
+}
+
+// ---- generate_bitwise_trace (builtin.rs:35-206) --------------------------------------------------------------------------------------
+// Column order builtins/bitwise/columns.rs:23-62 (59 columns).  The reference writes the FOURTH limb of op0 / op1 / res to
+// trace[OP0_LIMBS.end] / [OP1_LIMBS.end] / [RES_LIMBS.end] (builtin.rs:66, :71, :76) -- the first column of the NEXT range,
+// overwritten right after -- so columns 8, 12 and 16 stay zero in the table it produces; a drop-in generator reproduces that
+// table (operands below 2^24 satisfy the AIR, as in the reference).  Opcode::AND = 18, OR = 17, XOR = 16 (instruction.rs:44-46).
+__global__ void bitwise_fill_kernel(const uint64_t* __restrict__ tags, const uint64_t* __restrict__ op0, const uint64_t* __restrict__ op1,
+                                    const uint64_t* __restrict__ res, size_t nrows, size_t n, uint64_t* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    auto put = [&](int c, uint64_t v) { out[(size_t)c * n + i] = v; };
+    const bool live = i < nrows;
+    const uint64_t a = live ? gl::canon(op0[i]) : 0, b = live ? gl::canon(op1[i]) : 0, r = live ? gl::canon(res[i]) : 0;
+    put(0, live ? 1 : 0);
+    put(1, live ? tags[i] : 0);
+    put(2, a);
+    put(3, b);
+    put(4, r);
+    put(5, a & 255), put(6, (a >> 8) & 255), put(7, (a >> 16) & 255), put(8, 0);
+    put(9, b & 255), put(10, (b >> 8) & 255), put(11, (b >> 16) & 255), put(12, 0);
+    put(13, r & 255), put(14, (r >> 8) & 255), put(15, (r >> 16) & 255), put(16, 0);
+    put(37, i < 256 ? i : 0);  // FIX_RANGE_CHECK_U8: 0 .. 255, then zeros (builtin.rs:85; not padded with its last value)
+    const size_t blk = i >> 16, idx = i & 65535, x = idx >> 8, y = idx & 255;
+    const bool fixed = blk < 3;
+    put(50, fixed ? (1ull << (18 - blk)) : 0);  // FIX_TAG: AND, OR, XOR blocks of 2^16 rows
+    put(51, fixed ? x : 0);
+    put(52, fixed ? y : 0);
+    put(53, fixed ? (blk == 0 ? (x & y) : blk == 1 ? (x | y) : (x ^ y)) : 0);
+}
+// COMPRESS_LIMBS[k] = tag + op0_k beta + op1_k beta^2 + res_k beta^3;  FIX_COMPRESS likewise over the fixed columns (builtin.rs:133-159)
+__global__ void bitwise_compress_kernel(size_t n, uint64_t beta, uint64_t* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t b2 = gl::mul(beta, beta), b3 = gl::mul(b2, beta);
+    auto at = [&](int c) { return out[(size_t)c * n + i]; };
+    const uint64_t tag = gl::canon(at(1));
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        out[(size_t)(29 + k) * n + i] = gl::add(gl::add(gl::add(tag, gl::mul(at(5 + k), beta)), gl::mul(at(9 + k), b2)), gl::mul(at(13 + k), b3));
+    out[(size_t)54 * n + i] = gl::add(gl::add(gl::add(at(50), gl::mul(at(51), beta)), gl::mul(at(52), b2)), gl::mul(at(53), b3));
+}
+// returns beta.  d_out = [59][n]
+uint64_t bitwise_trace(ola_ctx* ctx, const uint64_t* d_tags, const uint64_t* d_op0, const uint64_t* d_op1, const uint64_t* d_res, size_t nrows, uint32_t log_n,
+                       uint64_t* d_out) {
+    const size_t n = (size_t)1 << log_n;
+    OLA_CHECK(log_n >= 18 && log_n <= 24 && nrows <= n, OLA_ERR_INVALID_ARG, "Bitwise table: at least 2^18 rows (3 * 2^16 fixed rows) and room for every operation");
+    const unsigned gb = (unsigned)((n + 255) / 256);
+    {
+        Launch lz(ctx, "gen_bitwise_fill");
+        bitwise_fill_kernel<<<gb, 256, 0, ctx->stream>>>(d_tags, d_op0, d_op1, d_res, nrows, n, d_out);
+        check_launch("bitwise_fill_kernel");
+    }
+    // the compress challenge: a fresh Challenger observes the twelve limb columns (builtin.rs:118-131) -- a duplex sponge is
+    // sequential, so the columns come to the host and the library's own transcript absorbs them
+    std::vector<uint64_t> limbs(12 * n);
+    OLA_CUDA(cudaMemcpyAsync(limbs.data(), d_out + 5 * n, 12 * n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+    stark::Challenger ch(OLA_HASH_POSEIDON);
+    for (size_t k = 0; k < 12 * n; ++k) ch.observe(limbs[k]);
+    const uint64_t beta = ch.get_challenge();
+    {
+        Launch lz(ctx, "gen_bitwise_compress");
+        bitwise_compress_kernel<<<gb, 256, 0, ctx->stream>>>(n, beta, d_out);
+        check_launch("bitwise_compress_kernel");
+    }
+    auto col = [&](int c) { return d_out + (size_t)c * n; };
+    for (int k = 0; k < 4; ++k) {  // builtin.rs:162-195
+        permuted_cols(ctx, col(5 + k), col(37), n, col(17 + k), col(38 + k));
+        permuted_cols(ctx, col(9 + k), col(37), n, col(21 + k), col(38 + 4 + k));
+        permuted_cols(ctx, col(13 + k), col(37), n, col(25 + k), col(38 + 8 + k));
+        permuted_cols(ctx, col(29 + k), col(54), n, col(33 + k), col(55 + k));
+    }
+    return beta;
+}
+
+// ---- generate_cmp_trace (builtin.rs:208-247) ------------------------------------------------------------------------------------------
+// cells [nrows][6] = (op0, op1, gte, abs_diff, abs_diff_inv, filter_looking_rc) as the executor recorded them; padding rows
+// (1, 0, 1, 1, 1, 0).  d_out = [6][n]
+__global__ void cmp_fill_kernel(const uint64_t* __restrict__ cells, size_t nrows, size_t n, uint64_t* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (i < nrows) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) out[(size_t)c * n + i] = gl::canon(cells[i * 6 + c]);
+    } else {
+        out[0 * n + i] = 1, out[1 * n + i] = 0, out[2 * n + i] = 1, out[3 * n + i] = 1, out[4 * n + i] = 1, out[5 * n + i] = 0;
+    }
+}
+void cmp_trace(ola_ctx* ctx, const uint64_t* d_cells, size_t nrows, uint32_t log_n, uint64_t* d_out) {
+    const size_t n = (size_t)1 << log_n;
+    OLA_CHECK(log_n >= 1 && nrows <= n, OLA_ERR_INVALID_ARG, "Cmp table: room for every comparison");
+    Launch lz(ctx, "gen_cmp_fill");
+    cmp_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_cells, nrows, n, d_out);
+    check_launch("cmp_fill_kernel");
 }
 
 }  // namespace lookup

@@ -54,6 +54,32 @@ def generate_rc_trace(ctx, vals, kinds, log_n=None):
     return out
 
 
+def generate_bitwise_trace(ctx, tags, op0, op1, res, log_n=None):
+    """generate_bitwise_trace (generation/builtin.rs:35-206): (the Bitwise table [59, 2^log_n], its compress challenge)."""
+    t, a, b, r = (np.ascontiguousarray(x, dtype=np.uint64).reshape(-1) for x in (tags, op0, op1, res))
+    k = t.shape[0]
+    if not (a.shape[0] == b.shape[0] == r.shape[0] == k):
+        raise ValueError("one tag, op0, op1 and res per operation")
+    if log_n is None:
+        log_n = max(18, (max(k, 1) - 1).bit_length())
+    out = np.empty((59, 1 << log_n), dtype=np.uint64)
+    beta = ctypes.c_uint64(0)
+    ptr = (lambda x: _lib.hptr(x) if k else None)
+    ctx.check(ctx._lib.ola_generate_bitwise_trace(ctx.handle, ptr(t), ptr(a), ptr(b), ptr(r), k, log_n, _lib.hptr(out), ctypes.byref(beta), 0))
+    return out, int(beta.value)
+
+
+def generate_cmp_trace(ctx, cells, log_n=None):
+    """generate_cmp_trace (generation/builtin.rs:208-247): cells [k, 6] -> the Cmp table [6, 2^log_n]."""
+    c = np.ascontiguousarray(cells, dtype=np.uint64).reshape(-1, 6)
+    k = c.shape[0]
+    if log_n is None:
+        log_n = max(1, (max(k, 1) - 1).bit_length())
+    out = np.empty((6, 1 << log_n), dtype=np.uint64)
+    ctx.check(ctx._lib.ola_generate_cmp_trace(ctx.handle, _lib.hptr(c) if k else None, k, log_n, _lib.hptr(out), 0))
+    return out
+
+
 def compress_challenge(columns):
     """Challenger::new(); observe_elements(column) for every column; get_challenge()."""
     cols = [np.ascontiguousarray(c, dtype=np.uint64).reshape(-1) for c in columns]

@@ -98,6 +98,10 @@ def _set_sigs(L):
     L.orc_permuted_cols.restype = None
     L.orc_generate_rc_trace.argtypes = [_u64p, ctypes.POINTER(ctypes.c_uint8), _sz, _u64p, _sz]
     L.orc_generate_rc_trace.restype = _sz
+    L.orc_generate_bitwise_trace.argtypes = [_u64p, _u64p, _u64p, _u64p, _sz, _u64p, _sz, _u64p]
+    L.orc_generate_bitwise_trace.restype = _sz
+    L.orc_generate_cmp_trace.argtypes = [_u64p, _sz, _u64p, _sz]
+    L.orc_generate_cmp_trace.restype = _sz
     L.orc_compress_challenge.argtypes = [ctypes.POINTER(ctypes.c_void_p), _u32, _sz]
     L.orc_compress_challenge.restype = _u64
 
@@ -347,6 +351,26 @@ def generate_rc_trace(vals, kinds):
     n = int(lib().orc_generate_rc_trace(_p(v), kp, v.shape[0], None, 0))
     out = np.empty((12, n), dtype=np.uint64)
     lib().orc_generate_rc_trace(_p(v), kp, v.shape[0], _p(out), n)
+    return out
+
+
+def generate_bitwise_trace(tags, op0, op1, res):
+    """generate_bitwise_trace (builtin.rs:35-206): (the 59-column Bitwise table, its compress challenge beta)."""
+    t, a, b, r = (np.ascontiguousarray(x, dtype=np.uint64).reshape(-1) for x in (tags, op0, op1, res))
+    k = t.shape[0]
+    n = int(lib().orc_generate_bitwise_trace(_p(t), _p(a), _p(b), _p(r), k, None, 0, None))
+    out = np.empty((59, n), dtype=np.uint64)
+    beta = np.zeros(1, dtype=np.uint64)
+    lib().orc_generate_bitwise_trace(_p(t), _p(a), _p(b), _p(r), k, _p(out), n, _p(beta))
+    return out, int(beta[0])
+
+
+def generate_cmp_trace(cells):
+    """generate_cmp_trace (builtin.rs:208-247): cells [k, 6] -> the Cmp table [6, n]."""
+    c = np.ascontiguousarray(cells, dtype=np.uint64).reshape(-1, 6)
+    n = int(lib().orc_generate_cmp_trace(_p(c), c.shape[0], None, 0))
+    out = np.empty((6, n), dtype=np.uint64)
+    lib().orc_generate_cmp_trace(_p(c), c.shape[0], _p(out), n)
     return out
 
 

@@ -39,6 +39,9 @@ void orc_hash_rows(const uint64_t *rows, size_t nrows, size_t ncols, uint64_t *d
 /* lookup.c */
 void orc_permuted_cols(const uint64_t *inputs, const uint64_t *table, size_t n, uint64_t *permuted_inputs, uint64_t *permuted_table);
 size_t orc_generate_rc_trace(const uint64_t *vals, const uint8_t *kinds, size_t nrows, uint64_t *out, size_t out_cap_rows);
+size_t orc_generate_bitwise_trace(const uint64_t *tags, const uint64_t *op0, const uint64_t *op1, const uint64_t *res, size_t nrows, uint64_t *out,
+                                  size_t out_cap_rows, uint64_t *beta_out);
+size_t orc_generate_cmp_trace(const uint64_t *cells, size_t nrows, uint64_t *out, size_t out_cap_rows);
 
 /* blake3.c */
 void orc_blake3(const uint8_t *in, size_t len, uint8_t out[32]);

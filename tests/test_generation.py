@@ -145,3 +145,78 @@ def test_generate_rc_trace_equals_oracle_and_satisfies_the_air(ctx, orc, nrows, 
         assert t.shape == ref.shape and (t == ref).all()
     # "all constraints vanish on a real trace" (rangecheck_stark.rs test) on the generated table: table id 4 = RangeCheck
     assert orc.air_first_failure(4, t) is None
+
+
+# ---- generate_bitwise_trace / generate_cmp_trace (generation/builtin.rs:35-247) ---------------------------------------------------
+def _bitwise_ops(rng, k, bits=24):
+    tags = np.array([1 << 18, 1 << 17, 1 << 16], dtype=np.uint64)[rng.integers(0, 3, size=k)]  # 1 << Opcode::{AND, OR, XOR}
+    a = rng.integers(0, 1 << bits, size=k, dtype=np.uint64)
+    b = rng.integers(0, 1 << bits, size=k, dtype=np.uint64)
+    r = np.where(tags == (1 << 18), a & b, np.where(tags == (1 << 17), a | b, a ^ b)).astype(np.uint64)
+    return tags, a, b, r
+
+
+def test_oracle_bitwise_trace_follows_the_reference_including_its_fourth_limb(orc):
+    """The reference writes limb 3 of op0 / op1 / res to the first column of the NEXT range (builtin.rs:66, :71, :76), where it
+    is overwritten: columns 8, 12, 16 stay zero.  The restated generator reproduces that table; with operands below 2^24 it
+    satisfies the Bitwise AIR (table id 2), with a 32-bit operand the limb sum check fails as it does in the reference."""
+    rng = np.random.default_rng(21)
+    tags, a, b, r = _bitwise_ops(rng, 300)
+    t, beta = orc.generate_bitwise_trace(tags, a, b, r)
+    assert t.shape == (59, 1 << 18)
+    assert not t[8].any() and not t[12].any() and not t[16].any()
+    assert (t[5, :300] == (a & 255)).all() and (t[11, :300] == ((b >> 16) & 255)).all() and (t[13, :300] == (r & 255)).all()
+    assert beta == orc.compress_challenge([t[c] for c in range(5, 17)])
+    assert orc.air_first_failure(2, t, compress_challenge=beta) is None
+    tags2, a2, b2, r2 = _bitwise_ops(rng, 4, bits=32)
+    a2[0] |= np.uint64(1 << 31)
+    r2 = np.where(tags2 == (1 << 18), a2 & b2, np.where(tags2 == (1 << 17), a2 | b2, a2 ^ b2)).astype(np.uint64)
+    t2, beta2 = orc.generate_bitwise_trace(tags2, a2, b2, r2)
+    assert orc.air_first_failure(2, t2, compress_challenge=beta2) is not None
+
+
+def test_oracle_cmp_trace(orc):
+    rng = np.random.default_rng(22)
+    cells = []
+    for _ in range(5):
+        x, y = int(rng.integers(0, 1 << 32)), int(rng.integers(0, 1 << 32))
+        d = abs(x - y)
+        cells.append([x, y, int(x >= y), d, pow(d, P - 2, P) if d else 0, 1])
+    t = orc.generate_cmp_trace(np.array(cells, dtype=np.uint64))
+    assert t.shape == (6, 8) and (t[:, 5:] == np.array([1, 0, 1, 1, 1, 0], dtype=np.uint64)[:, None]).all()
+    assert orc.air_first_failure(3, t) is None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [0, 1, 300, 5000])
+def test_generate_bitwise_trace_equals_oracle(ctx, orc, k):
+    from olavm_b200 import generation
+
+    rng = np.random.default_rng(30 + k)
+    tags, a, b, r = _bitwise_ops(rng, k, bits=32 if k == 300 else 24)
+    t, beta = generation.generate_bitwise_trace(ctx, tags, a, b, r)
+    ref, rbeta = orc.generate_bitwise_trace(tags, a, b, r)
+    assert beta == rbeta
+    assert t.shape == ref.shape
+    bad = [c for c in range(59) if not (t[c] == ref[c]).all()]
+    assert not bad, bad
+    if k != 300:
+        assert orc.air_first_failure(2, t, compress_challenge=beta) is None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,log_n", [(0, 1), (3, 2), (1000, 10), (1 << 16, 16)])
+def test_generate_cmp_trace_equals_oracle(ctx, orc, k, log_n):
+    from olavm_b200 import generation
+
+    rng = np.random.default_rng(40 + k)
+    x = rng.integers(0, 1 << 32, size=k, dtype=np.uint64)
+    y = rng.integers(0, 1 << 32, size=k, dtype=np.uint64)
+    d = np.where(x >= y, x - y, y - x).astype(np.uint64)
+    inv = np.array([pow(int(v), P - 2, P) if v else 0 for v in d[: min(k, 2000)]] + [1] * max(0, k - 2000), dtype=np.uint64)
+    cells = np.stack([x, y, (x >= y).astype(np.uint64), d, inv, np.ones(k, dtype=np.uint64)], axis=1) if k else np.zeros((0, 6), dtype=np.uint64)
+    t = generation.generate_cmp_trace(ctx, cells, log_n)
+    ref = orc.generate_cmp_trace(cells)
+    assert ref.shape[1] <= (1 << log_n)
+    assert (t[:, : ref.shape[1]] == ref).all()
+    assert (t[:, ref.shape[1]:] == np.array([1, 0, 1, 1, 1, 0], dtype=np.uint64)[:, None]).all()

@@ -96,6 +96,14 @@ static int poseidon_mode() {
     }();
     return v;
 }
+// OLA_MERKLE_SMALL: levels with at most this many nodes run the straight-line body (0 = never)
+static size_t merkle_small_threshold() {
+    static const size_t v = [] {
+        const char* e = getenv("OLA_MERKLE_SMALL");
+        return e ? (size_t)atoll(e) : (size_t)0;
+    }();
+    return v;
+}
 void permute_states(ola_ctx* ctx, uint64_t* d_states, size_t n) {
     if (!n) return;
     {
@@ -144,7 +152,11 @@ void merkle_levels(ola_ctx* ctx, uint64_t* d_nodes, size_t nleaves, size_t stop)
     for (size_t first = nleaves / 2; first >= stop && first >= 1; first /= 2) {
         {
             Launch lz(ctx, "merkle_level");
-            if (poseidon_mode() == 2)
+            // a level of a few thousand nodes is one permutation deep per thread and latency-bound (one warp per scheduler at
+            // most): the straight-line full rounds give that warp twelve independent S-box chains instead of three
+            if (first <= merkle_small_threshold())
+                merkle_level_kernel<2><<<(unsigned)((first + 127) / 128), 128, 0, ctx->stream>>>(d_nodes, first, first);
+            else if (poseidon_mode() == 2)
                 merkle_level_kernel<2><<<(unsigned)((first + 127) / 128), 128, 0, ctx->stream>>>(d_nodes, first, first);
             else if (poseidon_mode() == 3)
                 merkle_level_kernel<3><<<(unsigned)((first + 127) / 128), 128, 0, ctx->stream>>>(d_nodes, first, first);

@@ -220,3 +220,41 @@ def test_generate_cmp_trace_equals_oracle(ctx, orc, k, log_n):
     assert ref.shape[1] <= (1 << log_n)
     assert (t[:, : ref.shape[1]] == ref).all()
     assert (t[:, ref.shape[1]:] == np.array([1, 0, 1, 1, 1, 0], dtype=np.uint64)[:, None]).all()
+
+
+@pytest.mark.gpu
+def test_tables_generated_on_the_device_are_proven_where_they_lie(ctx, orc):
+    """generation -> prove without a host round trip: Cmp and RangeCheck tables are generated INTO device memory
+    (on_device = 1), ola_prove consumes them there (on_device = 1), the subsystem verifier accepts the proof, and the bytes
+    equal the oracle prover's on the host copies of the same tables.  The cmp -> rangecheck lookup carries real data: every
+    comparison's |a - b| is a RangeCheck row looked up by the Cmp table."""
+    import ctypes
+
+    import olavm_b200
+    from olavm_b200 import _lib
+
+    rng = np.random.default_rng(77)
+    k = 3000
+    x = rng.integers(0, 1 << 32, size=k, dtype=np.uint64)
+    y = rng.integers(0, 1 << 32, size=k, dtype=np.uint64)
+    d = np.where(x >= y, x - y, y - x).astype(np.uint64)
+    inv = np.array([pow(int(v), P - 2, P) if v else 0 for v in d], dtype=np.uint64)
+    cells = np.stack([x, y, (x >= y).astype(np.uint64), d, inv, np.ones(k, dtype=np.uint64)], axis=1)
+    kinds = np.full(k, 3, dtype=np.uint64)  # looked up by the comparison table
+    log_cmp, log_rc = 12, 16
+    lib = ctx._lib
+    d_cells, d_vals, d_kinds = ctx.upload(cells), ctx.upload(d), ctx.upload(kinds)
+    d_cmp, d_rc = ctx.alloc(6 << log_cmp), ctx.alloc(12 << log_rc)
+    try:
+        ctx.check(lib.ola_generate_cmp_trace(ctx.handle, d_cells, k, log_cmp, d_cmp, 1))
+        ctx.check(lib.ola_generate_rangecheck_trace(ctx.handle, d_vals, d_kinds, k, log_rc, d_rc, 1))
+        proof = olavm_b200.prove_with_device_traces(ctx, [3, 4], [d_cmp, d_rc], [log_cmp, log_rc])
+        cmp_host = ctx.download(d_cmp, (6, 1 << log_cmp))
+        rc_host = ctx.download(d_rc, (12, 1 << log_rc))
+    finally:
+        for p in (d_cells, d_vals, d_kinds, d_cmp, d_rc):
+            ctx.free(p)
+    ok, why = olavm_b200.verify_subsystem_proof([3, 4], proof)
+    assert ok, why
+    assert orc.air_first_failure(3, cmp_host) is None and orc.air_first_failure(4, rc_host) is None
+    assert proof == orc.stark_prove([3, 4], [cmp_host, rc_host], check_degree=True)

@@ -312,6 +312,15 @@ int ola_generate_bitwise_trace(ola_ctx* ctx, const uint64_t* tags, const uint64_
  * filter_looking_rc) as the executor recorded them (CmpRow) -> the column-major Cmp table out [6][2^log_n]
  * (builtins/cmp/columns.rs:16-22); padding rows are (1, 0, 1, 1, 1, 0). */
 int ola_generate_cmp_trace(ola_ctx* ctx, const uint64_t* cells, size_t nrows, uint32_t log_n, uint64_t* out, int on_device);
+/* generate_cpu_trace (circuits/src/generation/cpu.rs:11-218): the executor's Step list (core/src/trace/trace.rs) as one record
+ * of 66 u64 per executed row ->  the column-major CPU table out [94][2^log_n] (circuits/src/cpu/columns.rs), padding rows
+ * included (cpu.rs:180-208).  Record layout (field.0 of the Rust struct, in this order):
+ *    0 env_idx   1 call_sc_cnt   2..5 addr_storage[4]   6..9 addr_code[4]   10 tp   11 clk   12 pc   13 is_ext_line   14 ext_cnt
+ *   15..24 regs[10]   25 instruction   26 op1_imm   27 opcode   28 immediate_data
+ *   29 op0   30 op1   31 dst   32 aux0   33 aux1  (register_selector)   34 storage_access_idx
+ *   35..44 op0_reg_sel[10]   45..54 op1_reg_sel[10]   55..64 dst_reg_sel[10]   65 filter_tape_looking
+ * One GPU thread per table row.  on_device: steps and out are device pointers. */
+int ola_generate_cpu_trace(ola_ctx* ctx, const uint64_t* steps, size_t nrows, uint32_t log_n, uint64_t* out, int on_device);
 /* The compress challenge of the Bitwise / Program tables: a fresh Poseidon Challenger observes `ncols` HOST columns of n
  * elements, column after column, and squeezes one element (generate_bitwise_trace, generation/builtin.rs:118-131: the 12
  * limb columns; generate_prog_trace, generation/prog.rs:23-29: the 8 interleaved root limbs as one column).  A duplex

@@ -700,6 +700,20 @@ int ola_generate_cmp_trace(ola_ctx* ctx, const uint64_t* cells, size_t nrows, ui
         to_host(ctx, out, d_out.p, 6 * n);
     });
 }
+int ola_generate_cpu_trace(ola_ctx* ctx, const uint64_t* steps, size_t nrows, uint32_t log_n, uint64_t* out, int on_device) {
+    if (!ctx || (!steps && nrows) || !out || log_n > 26 || nrows > ((size_t)1 << log_n)) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        const size_t n = (size_t)1 << log_n;
+        if (on_device) {
+            ola::lookup::cpu_trace(ctx, steps, nrows, log_n, out);
+            return;
+        }
+        DevBuf d_s(std::max<size_t>(nrows * 66, 1)), d_out(94 * n);
+        if (nrows) to_device(ctx, d_s.p, steps, nrows * 66);
+        ola::lookup::cpu_trace(ctx, d_s.p, nrows, log_n, d_out.p);
+        to_host(ctx, out, d_out.p, 94 * n);
+    });
+}
 int ola_compress_challenge(const uint64_t* const* cols, uint32_t ncols, size_t n, uint64_t* beta_out) {
     if ((!cols && ncols) || !beta_out) return OLA_ERR_INVALID_ARG;
     try {

@@ -475,5 +475,93 @@ void cmp_trace(ola_ctx* ctx, const uint64_t* d_cells, size_t nrows, uint32_t log
     check_launch("cmp_fill_kernel");
 }
 
+// ---- generate_cpu_trace (circuits/src/generation/cpu.rs:11-218) -------------------------------------------------------------------------
+// One thread per table row: the executor's Step record (66 u64, layout in include/ola_gpu.h) is copied into the 94 columns
+// (cpu/columns.rs), the opcode picks its selector column (opcode_to_selector, cpu.rs:19-59), the derived flags follow
+// cpu.rs:111-177 on the raw u64 values, rows past nrows are padding rows (cpu.rs:180-208: END opcode, the last row's
+// instruction and storage index carried on).
+__device__ __forceinline__ int cpu_selector_of(uint64_t opcode) {
+    // binary_bit_mask = 1 << shift (core/src/vm/opcodes.rs): ADD 31, MUL 30, EQ 29, ASSERT 28, MOV 27, JMP 26, CJMP 25, CALL 24, RET 23,
+    // MLOAD 22, MSTORE 21, END 20, RC 19, AND 18, OR 17, XOR 16, NOT 15, NEQ 14, GTE 13, POSEIDON 12, SLOAD 11, SSTORE 10, TLOAD 9,
+    // TSTORE 8, SCCALL 7
+    if (opcode == 0 || (opcode & (opcode - 1)) != 0) return -1;
+    const int sh = 63 - __clzll((long long)opcode);
+    switch (sh) {
+        case 31: case 30: case 29: case 28: case 14: return 66;  // COL_S_SIMPLE_ARITHMATIC_OP
+        case 27: return 67;
+        case 26: return 68;
+        case 25: return 69;
+        case 24: return 70;
+        case 23: return 71;
+        case 22: return 72;
+        case 21: return 73;
+        case 20: return 74;
+        case 19: return 75;
+        case 18: case 17: case 16: return 76;  // COL_S_BITWISE
+        case 15: return 77;
+        case 13: return 78;
+        case 12: return 79;
+        case 11: return 80;
+        case 10: return 81;
+        case 9: return 82;
+        case 8: return 83;
+        case 7: return 84;
+        default: return -1;
+    }
+}
+__global__ void cpu_fill_kernel(const uint64_t* __restrict__ steps /* [nrows][66] */, size_t nrows, size_t n, uint64_t* __restrict__ out /* [94][n] */) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    auto put = [&](int c, uint64_t v) { out[(size_t)c * n + i] = v; };
+    constexpr uint64_t END = 1ull << 20, SLOAD = 1ull << 11, SSTORE = 1ull << 10, TLOAD = 1ull << 9, TSTORE = 1ull << 8, SCCALL = 1ull << 7,
+                       MLOAD = 1ull << 22, MSTORE = 1ull << 21;
+    if (i >= nrows) {  // padding
+        const uint64_t* last = nrows ? steps + (nrows - 1) * 66 : nullptr;
+        for (int c = 0; c < 94; ++c) put(c, 0);
+        put(26, last ? gl::canon(last[25]) : 1048576);  // COL_INST of the last executed row
+        put(28, END);
+        put(35, last ? gl::canon(last[34]) : 0);        // COL_IDX_STORAGE carried on
+        put(74, 1), put(85, 1), put(86, 1), put(93, 1);
+        return;
+    }
+    const uint64_t* s = steps + i * 66;
+    put(0, 0);
+    put(1, gl::canon(s[0])), put(2, gl::canon(s[1]));
+    for (int j = 0; j < 4; ++j) put(3 + j, gl::canon(s[2 + j])), put(7 + j, gl::canon(s[6 + j]));
+    put(11, gl::canon(s[10]));
+    put(12, (uint32_t)s[11]);
+    put(13, gl::canon(s[12])), put(14, gl::canon(s[13])), put(15, gl::canon(s[14]));
+    for (int j = 0; j < 10; ++j) put(16 + j, gl::canon(s[15 + j]));
+    for (int j = 0; j < 10; ++j) put(26 + j, gl::canon(s[25 + j]));  // inst, op1_imm, opcode, imm, op0, op1, dst, aux0, aux1, idx_storage
+    for (int j = 0; j < 30; ++j) put(36 + j, gl::canon(s[35 + j]));  // the three register-selector groups
+    const uint64_t opcode = s[27], op0 = s[29], op1 = s[30], ext_cnt = s[14], is_ext = s[13];
+    const bool env_zero = gl::canon(s[0]) == 0;
+    const int sel = cpu_selector_of(opcode);
+    for (int c = 66; c < 85; ++c) put(c, c == sel ? 1 : 0);
+    put(85, env_zero ? 1 : 0);
+    uint64_t ext_length = 0;  // cpu.rs:118-132: plain u64 arithmetic on the inner values
+    if (opcode == SLOAD || opcode == SSTORE || opcode == SCCALL || (opcode == END && !env_zero))
+        ext_length = 1;
+    else if (opcode == TLOAD)
+        ext_length = op0 * op1 + (1 - op0);
+    else if (opcode == TSTORE)
+        ext_length = op1;
+    put(86, ext_length == ext_cnt ? 1 : 0);
+    put(87, (env_zero && opcode == END) ? 0 : 1);
+    put(88, gl::canon(s[65]));
+    put(89, (opcode == SCCALL && ext_cnt == 1) ? 1 : 0);
+    put(90, ((opcode == SLOAD || opcode == SSTORE) && is_ext == 1) ? 1 : 0);
+    put(91, (opcode == END && is_ext == 1) ? 1 : 0);
+    put(92, is_ext == 1 ? 0 : ((opcode == MLOAD || opcode == MSTORE) ? 1 : (s[26] == 1 ? 1 : 0)));
+    put(93, 0);
+}
+void cpu_trace(ola_ctx* ctx, const uint64_t* d_steps, size_t nrows, uint32_t log_n, uint64_t* d_out) {
+    const size_t n = (size_t)1 << log_n;
+    OLA_CHECK(nrows <= n, OLA_ERR_INVALID_ARG, "CPU table: room for every executed row");
+    Launch lz(ctx, "gen_cpu_fill");
+    cpu_fill_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(d_steps, nrows, n, d_out);
+    check_launch("cpu_fill_kernel");
+}
+
 }  // namespace lookup
 }  // namespace ola

@@ -80,6 +80,18 @@ def generate_cmp_trace(ctx, cells, log_n=None):
     return out
 
 
+def generate_cpu_trace(ctx, steps, log_n=None):
+    """generate_cpu_trace (generation/cpu.rs:11-218): Step records [k, 66] (layout: include/ola_gpu.h) -> the CPU table
+    [94, 2^log_n]."""
+    r = np.ascontiguousarray(steps, dtype=np.uint64).reshape(-1, 66)
+    k = r.shape[0]
+    if log_n is None:
+        log_n = max(0, (max(k, 1) - 1).bit_length())
+    out = np.empty((94, 1 << log_n), dtype=np.uint64)
+    ctx.check(ctx._lib.ola_generate_cpu_trace(ctx.handle, _lib.hptr(r) if k else None, k, log_n, _lib.hptr(out), 0))
+    return out
+
+
 def compress_challenge(columns):
     """Challenger::new(); observe_elements(column) for every column; get_challenge()."""
     cols = [np.ascontiguousarray(c, dtype=np.uint64).reshape(-1) for c in columns]

@@ -102,6 +102,8 @@ def _set_sigs(L):
     L.orc_generate_bitwise_trace.restype = _sz
     L.orc_generate_cmp_trace.argtypes = [_u64p, _sz, _u64p, _sz]
     L.orc_generate_cmp_trace.restype = _sz
+    L.orc_generate_cpu_trace.argtypes = [_u64p, _sz, _sz, _u64p]
+    L.orc_generate_cpu_trace.restype = None
     L.orc_compress_challenge.argtypes = [ctypes.POINTER(ctypes.c_void_p), _u32, _sz]
     L.orc_compress_challenge.restype = _u64
 
@@ -371,6 +373,17 @@ def generate_cmp_trace(cells):
     n = int(lib().orc_generate_cmp_trace(_p(c), c.shape[0], None, 0))
     out = np.empty((6, n), dtype=np.uint64)
     lib().orc_generate_cmp_trace(_p(c), c.shape[0], _p(out), n)
+    return out
+
+
+def generate_cpu_trace(steps, log_n=None):
+    """generate_cpu_trace (generation/cpu.rs:11-218): step records [k, 66] (layout: oracle/generation_cpu.c) -> the CPU table [94, n]."""
+    r = np.ascontiguousarray(steps, dtype=np.uint64).reshape(-1, 66)
+    k = r.shape[0]
+    n = 1 << (log_n if log_n is not None else max(0, (max(k, 1) - 1).bit_length()))
+    assert n >= k
+    out = np.empty((94, n), dtype=np.uint64)
+    lib().orc_generate_cpu_trace(_p(r), k, n, _p(out))
     return out
 
 

@@ -1,0 +1,96 @@
+/* ORACLE (test infrastructure, NOT product code): generate_cpu_trace restated.
+ *
+ *   orc_generate_cpu_trace   circuits/src/generation/cpu.rs:11-218
+ *                            columns: circuits/src/cpu/columns.rs (94 columns); opcode masks: core/src/vm/opcodes.rs
+ *                            (binary_bit_mask = 1 << binary_bit_shift; ADD 31 ... SCCALL 7)
+ *
+ * The executor's Step (core/src/trace/trace.rs) enters as one record of 66 u64 per executed row:
+ *    0 env_idx   1 call_sc_cnt   2..5 addr_storage[4]   6..9 addr_code[4]   10 tp   11 clk   12 pc   13 is_ext_line   14 ext_cnt
+ *   15..24 regs[10]   25 instruction   26 op1_imm   27 opcode   28 immediate_data
+ *   29 op0   30 op1   31 dst   32 aux0   33 aux1 (register_selector)   34 storage_access_idx
+ *   35..44 op0_reg_sel[10]   45..54 op1_reg_sel[10]   55..64 dst_reg_sel[10]   65 filter_tape_looking */
+#include <string.h>
+
+#include "oracle.h"
+
+enum { OP_ADD = 31, OP_MUL = 30, OP_EQ = 29, OP_ASSERT = 28, OP_MOV = 27, OP_JMP = 26, OP_CJMP = 25, OP_CALL = 24, OP_RET = 23, OP_MLOAD = 22,
+       OP_MSTORE = 21, OP_END = 20, OP_RC = 19, OP_AND = 18, OP_OR = 17, OP_XOR = 16, OP_NOT = 15, OP_NEQ = 14, OP_GTE = 13, OP_POSEIDON = 12,
+       OP_SLOAD = 11, OP_SSTORE = 10, OP_TLOAD = 9, OP_TSTORE = 8, OP_SCCALL = 7 };
+#define MASK(op) (1ull << (op))
+
+/* opcode_to_selector (cpu.rs:19-59) */
+static int selector_of(uint64_t opcode) {
+    if (opcode == MASK(OP_ADD) || opcode == MASK(OP_MUL) || opcode == MASK(OP_EQ) || opcode == MASK(OP_ASSERT) || opcode == MASK(OP_NEQ)) return 66;
+    if (opcode == MASK(OP_MOV)) return 67;
+    if (opcode == MASK(OP_JMP)) return 68;
+    if (opcode == MASK(OP_CJMP)) return 69;
+    if (opcode == MASK(OP_CALL)) return 70;
+    if (opcode == MASK(OP_RET)) return 71;
+    if (opcode == MASK(OP_MLOAD)) return 72;
+    if (opcode == MASK(OP_MSTORE)) return 73;
+    if (opcode == MASK(OP_END)) return 74;
+    if (opcode == MASK(OP_RC)) return 75;
+    if (opcode == MASK(OP_AND) || opcode == MASK(OP_OR) || opcode == MASK(OP_XOR)) return 76;
+    if (opcode == MASK(OP_NOT)) return 77;
+    if (opcode == MASK(OP_GTE)) return 78;
+    if (opcode == MASK(OP_POSEIDON)) return 79;
+    if (opcode == MASK(OP_SLOAD)) return 80;
+    if (opcode == MASK(OP_SSTORE)) return 81;
+    if (opcode == MASK(OP_TLOAD)) return 82;
+    if (opcode == MASK(OP_TSTORE)) return 83;
+    if (opcode == MASK(OP_SCCALL)) return 84;
+    return -1;
+}
+
+/* steps [nrows][66]; out [94][n] column-major, n a power of two >= max(nrows, 1) (the reference takes the next power of two). */
+void orc_generate_cpu_trace(const uint64_t *steps, size_t nrows, size_t n, uint64_t *out) {
+    memset(out, 0, 94 * n * sizeof(uint64_t));
+#define T(c, i) out[(size_t)(c) * n + (i)]
+    for (size_t i = 0; i < nrows; ++i) { /* :61-178 */
+        const uint64_t *s = steps + i * 66;
+        T(0, i) = 0;                     /* COL_TX_IDX */
+        T(1, i) = gl_canon(s[0]);        /* COL_ENV_IDX */
+        T(2, i) = gl_canon(s[1]);        /* COL_CALL_SC_CNT */
+        for (int j = 0; j < 4; ++j) T(3 + j, i) = gl_canon(s[2 + j]), T(7 + j, i) = gl_canon(s[6 + j]);
+        T(11, i) = gl_canon(s[10]);      /* TP */
+        T(12, i) = (uint32_t)s[11];      /* CLK: from_canonical_u32 */
+        T(13, i) = gl_canon(s[12]);      /* PC */
+        T(14, i) = gl_canon(s[13]);      /* IS_EXT_LINE */
+        T(15, i) = gl_canon(s[14]);      /* EXT_CNT */
+        for (int j = 0; j < 10; ++j) T(16 + j, i) = gl_canon(s[15 + j]);
+        T(26, i) = gl_canon(s[25]), T(27, i) = gl_canon(s[26]), T(28, i) = gl_canon(s[27]), T(29, i) = gl_canon(s[28]);
+        T(30, i) = gl_canon(s[29]), T(31, i) = gl_canon(s[30]), T(32, i) = gl_canon(s[31]), T(33, i) = gl_canon(s[32]), T(34, i) = gl_canon(s[33]);
+        T(35, i) = gl_canon(s[34]);      /* IDX_STORAGE */
+        for (int j = 0; j < 10; ++j) T(36 + j, i) = gl_canon(s[35 + j]), T(46 + j, i) = gl_canon(s[45 + j]), T(56 + j, i) = gl_canon(s[55 + j]);
+        const uint64_t opcode = s[27], env = s[0], op0 = s[29], op1 = s[30], ext_cnt = s[14], is_ext = s[13];
+        const int sel = selector_of(opcode);
+        if (sel >= 0) T(sel, i) = 1;
+        const int env_zero = gl_canon(env) == 0;
+        T(85, i) = env_zero ? 1 : 0; /* IS_ENTRY_SC */
+        uint64_t ext_length; /* :118-132, plain u64 arithmetic on the inner values */
+        if (opcode == MASK(OP_SLOAD) || opcode == MASK(OP_SSTORE) || opcode == MASK(OP_SCCALL) || (opcode == MASK(OP_END) && !env_zero))
+            ext_length = 1;
+        else if (opcode == MASK(OP_TLOAD))
+            ext_length = op0 * op1 + (1 - op0);
+        else if (opcode == MASK(OP_TSTORE))
+            ext_length = op1;
+        else
+            ext_length = 0;
+        T(86, i) = ext_length == ext_cnt ? 1 : 0;                              /* IS_NEXT_LINE_DIFF_INST */
+        T(87, i) = (env_zero && opcode == MASK(OP_END)) ? 0 : 1;               /* IS_NEXT_LINE_SAME_TX */
+        T(88, i) = gl_canon(s[65]);                                            /* FILTER_TAPE_LOOKING */
+        T(89, i) = (opcode == MASK(OP_SCCALL) && ext_cnt == 1) ? 1 : 0;        /* IS_SCCALL_EXT_LINE */
+        T(90, i) = ((opcode == MASK(OP_SLOAD) || opcode == MASK(OP_SSTORE)) && is_ext == 1) ? 1 : 0; /* IS_STORAGE_EXT_LINE */
+        T(91, i) = (opcode == MASK(OP_END) && is_ext == 1) ? 1 : 0;            /* FILTER_SCCALL_END */
+        T(92, i) = is_ext == 1 ? 0 : ((opcode == MASK(OP_MLOAD) || opcode == MASK(OP_MSTORE)) ? 1 : (s[26] == 1 ? 1 : 0)); /* FILTER_LOOKING_PROG_IMM */
+    }
+    /* padding (:180-208) */
+    const uint64_t inst_end = nrows == 0 ? 1048576 : T(26, nrows - 1);
+    const uint64_t last_tx = nrows == 0 ? 0 : T(0, nrows - 1);
+    const uint64_t last_idx_storage = nrows == 0 ? 0 : T(35, nrows - 1);
+    for (size_t i = nrows; i < n; ++i) {
+        T(0, i) = last_tx, T(26, i) = inst_end, T(28, i) = MASK(OP_END), T(35, i) = last_idx_storage;
+        T(74, i) = 1, T(85, i) = 1, T(86, i) = 1, T(87, i) = 0, T(93, i) = 1;
+    }
+#undef T
+}

@@ -43,6 +43,9 @@ size_t orc_generate_bitwise_trace(const uint64_t *tags, const uint64_t *op0, con
                                   size_t out_cap_rows, uint64_t *beta_out);
 size_t orc_generate_cmp_trace(const uint64_t *cells, size_t nrows, uint64_t *out, size_t out_cap_rows);
 
+/* generation_cpu.c */
+void orc_generate_cpu_trace(const uint64_t *steps, size_t nrows, size_t n, uint64_t *out);
+
 /* blake3.c */
 void orc_blake3(const uint8_t *in, size_t len, uint8_t out[32]);
 void orc_blake3_hash_no_pad(const uint64_t *in, size_t n, uint64_t out[4]);

@@ -258,3 +258,76 @@ def test_tables_generated_on_the_device_are_proven_where_they_lie(ctx, orc):
     assert ok, why
     assert orc.air_first_failure(3, cmp_host) is None and orc.air_first_failure(4, rc_host) is None
     assert proof == orc.stark_prove([3, 4], [cmp_host, rc_host], check_degree=True)
+
+
+# ---- generate_cpu_trace (generation/cpu.rs:11-218) ---------------------------------------------------------------------------------
+_CPU_PROGRAMS = ("fibo_recursive", "memory", "mem_gep", "call", "tape", "bitwise", "comparison", "range_check", "context_fetch", "storage",
+                 "fibo_loop", "malloc", "poseidon_hash")
+
+
+def _vm_run(orc, name):
+    """One of the reference's assembly test programs through the restated VM -> (its CPU table, the Step records)."""
+    import json
+    import os
+
+    from workload import tracegen
+
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ola_programs.json")))
+    prog, prophets = tracegen.parse_ola_prophets({"program": g["programs"][name], "prophets": g["prophets"].get(name, [])})
+    if name in tracegen.REFERENCE_CALLDATA:
+        tape = tracegen.reference_test_tape(tracegen.REFERENCE_CALLDATA[name])
+    else:
+        tape = tracegen.CONTEXT_TAPE if name == "context_fetch" else ()
+    ids, traces, cc, steps = tracegen.run_system(orc, np.random.default_rng(3), prog, prophets=prophets, init_tape=tape)
+    return traces[0], tracegen.steps_to_records(steps)
+
+
+def _random_step_records(rng, k):
+    """Records with every opcode, ext lines, non-zero env / call counters: the branches of cpu.rs:111-177."""
+    r = rng.integers(0, P, size=(k, 66), dtype=np.uint64)
+    shifts = rng.integers(7, 32, size=k)
+    r[:, 27] = np.left_shift(np.uint64(1), shifts.astype(np.uint64))
+    r[:, 27][rng.random(k) < 0.05] = 12345          # an opcode that is no instruction: no selector
+    r[:, 0] = np.where(rng.random(k) < 0.5, 0, rng.integers(1, 5, size=k)).astype(np.uint64)   # env_idx
+    r[:, 13] = rng.integers(0, 2, size=k)           # is_ext_line
+    r[:, 14] = rng.integers(0, 3, size=k)           # ext_cnt
+    r[:, 26] = rng.integers(0, 2, size=k)           # op1_imm
+    r[:, 29] = rng.integers(0, 2, size=k)           # op0 (a flag on tload rows)
+    r[:, 30] = rng.integers(0, 4, size=k)           # op1 (a length on tload / tstore rows)
+    r[:, 11] = rng.integers(0, 1 << 32, size=k)     # clk is a u32
+    return r
+
+
+@pytest.mark.parametrize("name", _CPU_PROGRAMS)
+def test_oracle_cpu_trace_equals_the_vm_table(orc, name):
+    """Two restatements of generate_cpu_trace -- oracle/generation_cpu.c from the Rust, and the test VM's own table fill
+    (workload/tracegen.py, which carries its own ext_length bookkeeping) -- agree on the reference's assembly programs."""
+    table, records = _vm_run(orc, name)
+    got = orc.generate_cpu_trace(records, int(table.shape[1]).bit_length() - 1)
+    bad = [c for c in range(94) if not (got[c] == table[c]).all()]
+    assert not bad, bad
+    assert orc.air_first_failure(0, got) is None or name in ()  # the generated table satisfies the CPU AIR
+
+
+def test_oracle_cpu_trace_of_no_steps_is_the_padding_table(orc):
+    from workload import tracegen
+
+    assert (orc.generate_cpu_trace(np.zeros((0, 66), dtype=np.uint64), 4) == tracegen.cpu_padding_trace(4)).all()
+
+
+@pytest.mark.gpu
+def test_generate_cpu_trace_equals_oracle(ctx, orc):
+    from olavm_b200 import generation
+
+    for name in ("fibo_recursive", "tape", "storage", "fibo_loop"):
+        table, records = _vm_run(orc, name)
+        log_n = int(table.shape[1]).bit_length() - 1
+        got = generation.generate_cpu_trace(ctx, records, log_n)
+        assert (got == table).all(), name
+    rng = np.random.default_rng(8)
+    for k, log_n in ((0, 3), (1, 0), (777, 10), (1 << 14, 14), (50000, 16)):
+        rec = _random_step_records(rng, k)
+        got = generation.generate_cpu_trace(ctx, rec, log_n)
+        ref = orc.generate_cpu_trace(rec, log_n)
+        bad = [c for c in range(94) if not (got[c] == ref[c]).all()]
+        assert not bad, (k, bad)

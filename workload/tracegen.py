@@ -41,6 +41,32 @@ def permuted_cols(inputs, table):
     return np.array(si, dtype=np.uint64), np.array(perm, dtype=np.uint64)
 
 
+def steps_to_records(steps):
+    """The executed rows of cpu_vm_trace as the 66-u64 Step records generate_cpu_trace consumes (layout:
+    include/ola_gpu.h ola_generate_cpu_trace; core/src/trace/trace.rs Step).  Single-contract runs: env_idx = call_sc_cnt = 0,
+    zero storage / code addresses."""
+    r = np.zeros((len(steps), 66), dtype=np.uint64)
+    for i, s in enumerate(steps):
+        r[i, 10], r[i, 11], r[i, 12] = s["tp"], s["clk"], s["pc"]
+        r[i, 13], r[i, 14] = s.get("is_ext", 0), s.get("ext_cnt", 0)
+        r[i, 15:25] = s["regs"]
+        r[i, 25], r[i, 26], r[i, 27], r[i, 28] = s["inst"], s["op1_imm"], s["opcode"], s["imm"]
+        r[i, 29], r[i, 30], r[i, 31], r[i, 32], r[i, 33] = s["op0"], s["op1"], s["dst"], s["aux0"], s["aux1"]
+        r[i, 34] = s["idx_storage"]
+        if s["s_op0"] is not None:
+            r[i, 35 + s["s_op0"]] = 1
+        if s["s_op1"] is not None:
+            r[i, 45 + s["s_op1"]] = 1
+        if s["s_dst"] is not None:
+            r[i, 55 + s["s_dst"]] = 1
+        if "s_op0_0" in s:
+            r[i, 35] = s["s_op0_0"]
+        for col, v in s.get("sel_raw", {}).items():   # table columns 36..65 -> record fields 35..64
+            r[i, col - 1] = v
+        r[i, 65] = s.get("filter_tape_looking", 0)
+    return r
+
+
 def cmp_trace(pairs, log_n):
     """Cmp table (columns.rs:16-22): op0, op1, gte, abs_diff, abs_diff_inv, filter_looking_rc.
     Padding rows (0, 0, 1, 0, 0, 0) satisfy every constraint of cmp_stark.rs:36-44."""

@@ -321,6 +321,14 @@ int ola_generate_cmp_trace(ola_ctx* ctx, const uint64_t* cells, size_t nrows, ui
  *   35..44 op0_reg_sel[10]   45..54 op1_reg_sel[10]   55..64 dst_reg_sel[10]   65 filter_tape_looking
  * One GPU thread per table row.  on_device: steps and out are device pointers. */
 int ola_generate_cpu_trace(ola_ctx* ctx, const uint64_t* steps, size_t nrows, uint32_t log_n, uint64_t* out, int on_device);
+/* generate_memory_trace (circuits/src/generation/memory.rs:8-155): the executor's MemoryTraceCell list (core/src/trace/trace.rs;
+ * sorted by address and differenced by gen_memory_table) as one record of 15 u64 per cell -> the column-major Memory table
+ * out [29][2^log_n] (circuits/src/memory/columns.rs:12-45), log_n >= 1, padding rows continuing the write-once region
+ * (memory.rs:113-146).  Record layout:
+ *    0 env_idx   1 is_rw   2 addr   3 clk   4 op   5 is_write   6 value   7 diff_addr   8 diff_addr_inv   9 diff_clk
+ *   10 diff_addr_cond   11 rw_addr_unchanged   12 region_prophet   13 region_heap   14 rc_value
+ * on_device: cells and out are device pointers. */
+int ola_generate_memory_trace(ola_ctx* ctx, const uint64_t* cells, size_t ncells, uint32_t log_n, uint64_t* out, int on_device);
 /* The compress challenge of the Bitwise / Program tables: a fresh Poseidon Challenger observes `ncols` HOST columns of n
  * elements, column after column, and squeezes one element (generate_bitwise_trace, generation/builtin.rs:118-131: the 12
  * limb columns; generate_prog_trace, generation/prog.rs:23-29: the 8 interleaved root limbs as one column).  A duplex

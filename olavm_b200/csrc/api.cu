@@ -714,6 +714,20 @@ int ola_generate_cpu_trace(ola_ctx* ctx, const uint64_t* steps, size_t nrows, ui
         to_host(ctx, out, d_out.p, 94 * n);
     });
 }
+int ola_generate_memory_trace(ola_ctx* ctx, const uint64_t* cells, size_t ncells, uint32_t log_n, uint64_t* out, int on_device) {
+    if (!ctx || (!cells && ncells) || !out || log_n < 1 || log_n > 27 || ncells > ((size_t)1 << log_n)) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        const size_t n = (size_t)1 << log_n;
+        if (on_device) {
+            ola::lookup::memory_trace(ctx, cells, ncells, log_n, out);
+            return;
+        }
+        DevBuf d_c(std::max<size_t>(ncells * 15, 1)), d_out(29 * n);
+        if (ncells) to_device(ctx, d_c.p, cells, ncells * 15);
+        ola::lookup::memory_trace(ctx, d_c.p, ncells, log_n, d_out.p);
+        to_host(ctx, out, d_out.p, 29 * n);
+    });
+}
 int ola_compress_challenge(const uint64_t* const* cols, uint32_t ncols, size_t n, uint64_t* beta_out) {
     if ((!cols && ncols) || !beta_out) return OLA_ERR_INVALID_ARG;
     try {

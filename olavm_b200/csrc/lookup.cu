@@ -563,5 +563,70 @@ void cpu_trace(ola_ctx* ctx, const uint64_t* d_steps, size_t nrows, uint32_t log
     check_launch("cpu_fill_kernel");
 }
 
+// ---- generate_memory_trace (circuits/src/generation/memory.rs:8-155) -------------------------------------------------------------------
+// One thread per table row.  Filled rows copy the executor's MemoryTraceCell (15 u64, layout in include/ola_gpu.h; already
+// sorted and differenced by gen_memory_table), pick the selector of the accessing opcode and derive the two range-check
+// filters (the first needs the previous cell's region); padding rows continue the write-once region one address per row
+// (memory.rs:113-146), the first of them carrying the inverse of its distance to the last filled row.
+__device__ __forceinline__ int mem_selector_of(uint64_t op) {
+    if (op == 0) return 16;  // COL_MEM_S_PROPHET
+    if (op & (op - 1)) return -1;
+    switch (63 - __clzll((long long)op)) {
+        case 22: return 6;   // MLOAD
+        case 21: return 7;   // MSTORE
+        case 24: return 8;   // CALL
+        case 23: return 9;   // RET
+        case 9: return 10;   // TLOAD
+        case 8: return 11;   // TSTORE
+        case 7: return 12;   // SCCALL
+        case 12: return 13;  // POSEIDON
+        case 10: return 14;  // SSTORE
+        case 11: return 15;  // SLOAD
+        default: return -1;
+    }
+}
+__global__ void memory_fill_kernel(const uint64_t* __restrict__ cells /* [ncells][15] */, size_t ncells, size_t n, uint64_t* __restrict__ out /* [29][n] */) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    auto put = [&](int c, uint64_t v) { out[(size_t)c * n + i] = v; };
+    constexpr uint64_t SPAN = 0xFFFFFFFFull;  // 2^32 - 1
+    if (i < ncells) {
+        const uint64_t* c = cells + i * 15;
+        put(0, 0);
+        for (int j = 0; j < 5; ++j) put(1 + j, gl::canon(c[j]));  // env_idx, is_rw, addr, clk, op
+        const int sel = mem_selector_of(c[4]);
+        for (int k = 6; k <= 16; ++k) put(k, k == sel ? 1 : 0);
+        for (int j = 0; j < 10; ++j) put(17 + j, gl::canon(c[5 + j]));  // is_write, value, diff_addr, its inverse, diff_clk, cond, unchanged, prophet, heap, rc_value
+        const bool prophet = gl::canon(c[12]) == 1, heap = gl::canon(c[13]) == 1;
+        const bool last_is_not_heap = i > 0 && gl::canon(cells[(i - 1) * 15 + 13]) == 0;
+        put(27, (i == 0 || prophet || (heap && last_is_not_heap)) ? 0 : 1);
+        put(28, (heap || prophet) ? 1 : 0);
+        return;
+    }
+    // no cell at all: row 0 is the first address of the write-once region (memory.rs:101-112) and counts as filled
+    const size_t filled = ncells ? ncells : 1;
+    const uint64_t last_is_rw = ncells ? gl::canon(cells[(ncells - 1) * 15 + 1]) : 0;
+    const uint64_t last_addr = ncells ? gl::canon(cells[(ncells - 1) * 15 + 2]) : gl::sub(0, SPAN);
+    const uint64_t last_env = ncells ? gl::canon(cells[(ncells - 1) * 15 + 0]) : 0;
+    for (int k = 0; k < 29; ++k) put(k, 0);
+    if (i == 0) {  // only when ncells == 0
+        put(3, last_addr), put(17, 1), put(22, gl::sub(0, last_addr)), put(24, 1), put(26, gl::sub(0, last_addr));
+        return;
+    }
+    const uint64_t base = last_is_rw == 1 ? gl::sub(0, SPAN) : gl::add(last_addr, 1);
+    const uint64_t addr = gl::add(base, gl::canon((uint64_t)(i - filled)));
+    const uint64_t d = (i == filled) ? gl::sub(addr, last_addr) : 1;
+    put(16, 1), put(1, last_env), put(3, addr), put(17, 1);
+    put(19, d), put(20, (i == filled) ? gl::inv(d) : 1);
+    put(22, gl::sub(0, addr)), put(24, 1), put(26, gl::sub(0, addr));
+}
+void memory_trace(ola_ctx* ctx, const uint64_t* d_cells, size_t ncells, uint32_t log_n, uint64_t* d_out) {
+    const size_t n = (size_t)1 << log_n;
+    OLA_CHECK(log_n >= 1 && ncells <= n, OLA_ERR_INVALID_ARG, "Memory table: at least two rows and room for every cell");
+    Launch lz(ctx, "gen_memory_fill");
+    memory_fill_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(d_cells, ncells, n, d_out);
+    check_launch("memory_fill_kernel");
+}
+
 }  // namespace lookup
 }  // namespace ola

@@ -92,6 +92,18 @@ def generate_cpu_trace(ctx, steps, log_n=None):
     return out
 
 
+def generate_memory_trace(ctx, cells, log_n=None):
+    """generate_memory_trace (generation/memory.rs:8-155): MemoryTraceCell records [k, 15] (layout: include/ola_gpu.h) -> the
+    Memory table [29, 2^log_n]."""
+    r = np.ascontiguousarray(cells, dtype=np.uint64).reshape(-1, 15)
+    k = r.shape[0]
+    if log_n is None:
+        log_n = max(1, (max(k, 2) - 1).bit_length())
+    out = np.empty((29, 1 << log_n), dtype=np.uint64)
+    ctx.check(ctx._lib.ola_generate_memory_trace(ctx.handle, _lib.hptr(r) if k else None, k, log_n, _lib.hptr(out), 0))
+    return out
+
+
 def compress_challenge(columns):
     """Challenger::new(); observe_elements(column) for every column; get_challenge()."""
     cols = [np.ascontiguousarray(c, dtype=np.uint64).reshape(-1) for c in columns]

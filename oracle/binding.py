@@ -104,6 +104,8 @@ def _set_sigs(L):
     L.orc_generate_cmp_trace.restype = _sz
     L.orc_generate_cpu_trace.argtypes = [_u64p, _sz, _sz, _u64p]
     L.orc_generate_cpu_trace.restype = None
+    L.orc_generate_memory_trace.argtypes = [_u64p, _sz, _sz, _u64p]
+    L.orc_generate_memory_trace.restype = None
     L.orc_compress_challenge.argtypes = [ctypes.POINTER(ctypes.c_void_p), _u32, _sz]
     L.orc_compress_challenge.restype = _u64
 
@@ -384,6 +386,18 @@ def generate_cpu_trace(steps, log_n=None):
     assert n >= k
     out = np.empty((94, n), dtype=np.uint64)
     lib().orc_generate_cpu_trace(_p(r), k, n, _p(out))
+    return out
+
+
+def generate_memory_trace(cells, log_n=None):
+    """generate_memory_trace (generation/memory.rs:8-155): MemoryTraceCell records [k, 15] (layout: oracle/generation_cpu.c)
+    -> the Memory table [29, n]."""
+    r = np.ascontiguousarray(cells, dtype=np.uint64).reshape(-1, 15)
+    k = r.shape[0]
+    n = 1 << (log_n if log_n is not None else max(1, (max(k, 2) - 1).bit_length()))
+    assert n >= max(k, 2)
+    out = np.empty((29, n), dtype=np.uint64)
+    lib().orc_generate_memory_trace(_p(r), k, n, _p(out))
     return out
 
 

@@ -94,3 +94,64 @@ void orc_generate_cpu_trace(const uint64_t *steps, size_t nrows, size_t n, uint6
     }
 #undef T
 }
+
+/* ---- generate_memory_trace (circuits/src/generation/memory.rs:8-155) -----------------------------------------------------------
+ * The executor's MemoryTraceCell list (core/src/trace/trace.rs; already sorted and differenced by gen_memory_table) enters as
+ * one record of 15 u64 per cell:
+ *    0 env_idx   1 is_rw   2 addr   3 clk   4 op   5 is_write   6 value   7 diff_addr   8 diff_addr_inv   9 diff_clk
+ *   10 diff_addr_cond   11 rw_addr_unchanged   12 region_prophet   13 region_heap   14 rc_value
+ * Columns: circuits/src/memory/columns.rs:12-45 (29 columns).  out [29][n], n a power of two >= max(ncells, 2). */
+static int mem_selector_of(uint64_t op) {
+    if (op == 0) return 16;                 /* COL_MEM_S_PROPHET */
+    if (op == MASK(OP_MLOAD)) return 6;
+    if (op == MASK(OP_MSTORE)) return 7;
+    if (op == MASK(OP_CALL)) return 8;
+    if (op == MASK(OP_RET)) return 9;
+    if (op == MASK(OP_TLOAD)) return 10;
+    if (op == MASK(OP_TSTORE)) return 11;
+    if (op == MASK(OP_SCCALL)) return 12;
+    if (op == MASK(OP_POSEIDON)) return 13;
+    if (op == MASK(OP_SSTORE)) return 14;
+    if (op == MASK(OP_SLOAD)) return 15;
+    return -1;
+}
+void orc_generate_memory_trace(const uint64_t *cells, size_t ncells, size_t n, uint64_t *out) {
+    const uint64_t SPAN = 0xFFFFFFFFull; /* 2^32 - 1 */
+    memset(out, 0, 29 * n * sizeof(uint64_t));
+#define T(c, i) out[(size_t)(c) * n + (i)]
+    size_t filled = ncells;
+    for (size_t i = 0; i < ncells; ++i) { /* :51-99 */
+        const uint64_t *c = cells + i * 15;
+        T(0, i) = 0;
+        T(1, i) = gl_canon(c[0]), T(2, i) = gl_canon(c[1]), T(3, i) = gl_canon(c[2]), T(4, i) = gl_canon(c[3]), T(5, i) = gl_canon(c[4]);
+        const int sel = mem_selector_of(c[4]);
+        if (sel >= 0) T(sel, i) = 1;
+        T(17, i) = gl_canon(c[5]), T(18, i) = gl_canon(c[6]), T(19, i) = gl_canon(c[7]), T(20, i) = gl_canon(c[8]), T(21, i) = gl_canon(c[9]);
+        T(22, i) = gl_canon(c[10]), T(23, i) = gl_canon(c[11]), T(24, i) = gl_canon(c[12]), T(25, i) = gl_canon(c[13]), T(26, i) = gl_canon(c[14]);
+        const int prophet = gl_canon(c[12]) == 1, heap = gl_canon(c[13]) == 1;
+        const int last_is_not_heap = i > 0 && gl_canon(cells[(i - 1) * 15 + 13]) == 0;
+        T(27, i) = (i == 0 || prophet || (heap && last_is_not_heap)) ? 0 : 1;   /* FILTER_LOOKING_RC */
+        T(28, i) = (heap || prophet) ? 1 : 0;                                    /* FILTER_LOOKING_RC_COND */
+    }
+    if (filled == 0) { /* :101-112 */
+        const uint64_t addr = gl_sub(0, SPAN);
+        T(3, 0) = addr, T(17, 0) = 1, T(22, 0) = gl_sub(0, addr), T(24, 0) = 1, T(26, 0) = gl_sub(0, addr);
+        filled = 1;
+    }
+    if (n != filled) { /* :115-146 */
+        uint64_t addr = T(2, filled - 1) == 1 ? gl_sub(0, SPAN) : gl_add(T(3, filled - 1), 1);
+        const uint64_t tx_idx = T(0, filled - 1), env_idx = T(1, filled - 1);
+        int first = 1;
+        for (size_t i = filled; i < n; ++i) {
+            T(16, i) = 1, T(0, i) = tx_idx, T(1, i) = env_idx, T(3, i) = addr, T(17, i) = 1;
+            T(19, i) = first ? gl_sub(addr, T(3, filled - 1)) : 1;
+            T(20, i) = gl_inv(T(19, i));
+            T(22, i) = gl_sub(0, addr);
+            T(24, i) = 1;
+            T(26, i) = T(22, i);
+            addr = gl_add(addr, 1);
+            first = 0;
+        }
+    }
+#undef T
+}

@@ -331,3 +331,67 @@ def test_generate_cpu_trace_equals_oracle(ctx, orc):
         ref = orc.generate_cpu_trace(rec, log_n)
         bad = [c for c in range(94) if not (got[c] == ref[c]).all()]
         assert not bad, (k, bad)
+
+
+# ---- generate_memory_trace (generation/memory.rs:8-155) ----------------------------------------------------------------------------
+_MEM_PROGRAMS = ("fibo_recursive", "memory", "mem_gep", "call", "storage", "malloc", "poseidon_hash", "fibo_loop", "global")
+
+
+def _vm_memory(orc, name):
+    """A reference program through the restated VM -> (its Memory table, the MemoryTraceCell records, log_n)."""
+    import json
+    import os
+
+    from workload import tracegen
+
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ola_programs.json")))
+    prog, prophets = tracegen.parse_ola_prophets({"program": g["programs"][name], "prophets": g["prophets"].get(name, [])})
+    tape = tracegen.reference_test_tape(tracegen.REFERENCE_CALLDATA[name]) if name in tracegen.REFERENCE_CALLDATA else ()
+    mem_log = tracegen.cpu_vm_trace(prog, 13, want_side_tables="all+storage", orc=orc, init_tape=tape, prophets=prophets)[5]
+    log_n = max(1, (len(mem_log) - 1).bit_length())
+    table, cells = tracegen.memory_trace_from_log(mem_log, log_n, want_cells=True)
+    return table, tracegen.memory_cells_to_records(cells), log_n
+
+
+@pytest.mark.parametrize("name", _MEM_PROGRAMS)
+def test_oracle_memory_trace_equals_the_vm_table(orc, name):
+    """oracle/generation_cpu.c's generate_memory_trace (from the Rust) against the test VM's own Memory table (stack, heap and
+    write-once regions, padding that continues the write-once region), and against the Memory AIR."""
+    table, records, log_n = _vm_memory(orc, name)
+    got = orc.generate_memory_trace(records, log_n)
+    bad = [c for c in range(29) if not (got[c] == table[c]).all()]
+    assert not bad, bad
+    assert orc.air_first_failure(1, got) is None
+
+
+def test_oracle_memory_trace_of_no_cells(orc):
+    t = orc.generate_memory_trace(np.zeros((0, 15), dtype=np.uint64), 2)
+    span = (1 << 32) - 1
+    assert t[3].tolist() == [P - span, P - span + 1, P - span + 2, P - span + 3] and t[24].tolist() == [1, 1, 1, 1]
+    assert t[16].tolist() == [0, 1, 1, 1] and t[19].tolist() == [0, 1, 1, 1] and t[26].tolist() == [span, span - 1, span - 2, span - 3]
+
+
+@pytest.mark.gpu
+def test_generate_memory_trace_equals_oracle(ctx, orc):
+    from olavm_b200 import generation
+
+    for name in ("fibo_recursive", "storage", "malloc", "global"):
+        table, records, log_n = _vm_memory(orc, name)
+        for extra in (0, 1):  # also with a larger table: more padding rows
+            got = generation.generate_memory_trace(ctx, records, log_n + extra)
+            assert (got == orc.generate_memory_trace(records, log_n + extra)).all(), (name, extra)
+            if not extra:
+                assert (got == table).all(), name
+    assert (generation.generate_memory_trace(ctx, np.zeros((0, 15), dtype=np.uint64), 3) == orc.generate_memory_trace(np.zeros((0, 15), dtype=np.uint64), 3)).all()
+    rng = np.random.default_rng(9)
+    for k, log_n in ((1, 1), (5, 3), (4000, 12), (1 << 15, 15)):
+        rec = rng.integers(0, P, size=(k, 15), dtype=np.uint64)
+        ops = np.array([0, 1 << 22, 1 << 21, 1 << 24, 1 << 23, 1 << 9, 1 << 8, 1 << 7, 1 << 12, 1 << 10, 1 << 11, 12345], dtype=np.uint64)
+        rec[:, 4] = ops[rng.integers(0, len(ops), size=k)]
+        rec[:, 1] = rng.integers(0, 2, size=k)
+        rec[:, 12] = rng.integers(0, 2, size=k)
+        rec[:, 13] = rng.integers(0, 2, size=k)
+        got = generation.generate_memory_trace(ctx, rec, log_n)
+        ref = orc.generate_memory_trace(rec, log_n)
+        bad = [c for c in range(29) if not (got[c] == ref[c]).all()]
+        assert not bad, (k, bad)

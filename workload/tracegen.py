@@ -1111,7 +1111,17 @@ def poseidon_chunk_trace_from_calls(calls, log_n):
     return t, psdn
 
 
-def memory_trace_from_log(mem_log, log_n):
+def memory_cells_to_records(cells):
+    """The MemoryTraceCell list of memory_trace_from_log as the 15-u64 records generate_memory_trace consumes (layout:
+    include/ola_gpu.h ola_generate_memory_trace; core/src/trace/trace.rs MemoryTraceCell).  Single-contract runs: env_idx 0."""
+    r = np.zeros((len(cells), 15), dtype=np.uint64)
+    for i, c in enumerate(cells):
+        r[i] = [0, c["is_rw"], c["addr"], c["clk"], c["op"], c["is_write"], c["value"], c["diff_addr"], c["diff_addr_inv"], c["diff_clk"],
+                c["cond"], c["rw_addr_unchanged"], c["prophet"], c["heap"], c["rc_value"]]
+    return r
+
+
+def memory_trace_from_log(mem_log, log_n, want_cells=False):
     """Memory table of a VM run: gen_memory_table (executor/src/trace.rs:20-199: cells grouped by address in ascending
     order, access order inside an address; diff_addr / diff_clk / diff_addr_cond and the values each row sends to the
     RangeCheck table, by region: read-write stack below p - 2 span, read-write heap [p - 2 span, p - span), write-once
@@ -1190,6 +1200,8 @@ def memory_trace_from_log(mem_log, log_n):
             t[24, i] = 1
             t[26, i] = t[22, i]
             addr += 1
+    if want_cells:
+        return t, cells
     if rc_region:
         return t, rc_sort, rc_region
     return t, rc_sort

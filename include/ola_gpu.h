@@ -329,6 +329,15 @@ int ola_generate_cpu_trace(ola_ctx* ctx, const uint64_t* steps, size_t nrows, ui
  *   10 diff_addr_cond   11 rw_addr_unchanged   12 region_prophet   13 region_heap   14 rc_value
  * on_device: cells and out are device pointers. */
 int ola_generate_memory_trace(ola_ctx* ctx, const uint64_t* cells, size_t ncells, uint32_t log_n, uint64_t* out, int on_device);
+/* generate_prog_trace (circuits/src/generation/prog.rs:18-157): the Step records of ola_generate_cpu_trace (executed side: one
+ * row per fetched instruction word and one per immediate, ext lines skipped), prog_rows [nprog_rows][6] = (code address 0..3, pc,
+ * word) for every word of every program in the order the Rust walks `progs`, and roots[8] = start_root[4], end_root[4] (HOST
+ * pointer) -> the column-major Program table out [18][2^log_n] (circuits/src/program/columns.rs:3-16) and its compress challenge
+ * *beta_out (the (trace, beta) pair the reference returns).  2^log_n must hold max(fetched words, program words).  The beta-
+ * compression, the placement of the executed rows (a prefix sum) and the table's permuted_cols run on the GPU.  on_device:
+ * steps, prog_rows and out are device pointers (roots and beta_out stay on the host). */
+int ola_generate_program_trace(ola_ctx* ctx, const uint64_t* steps, size_t nsteps, const uint64_t* prog_rows, size_t nprog_rows, const uint64_t* roots,
+                               uint32_t log_n, uint64_t* out, uint64_t* beta_out, int on_device);
 /* The compress challenge of the Bitwise / Program tables: a fresh Poseidon Challenger observes `ncols` HOST columns of n
  * elements, column after column, and squeezes one element (generate_bitwise_trace, generation/builtin.rs:118-131: the 12
  * limb columns; generate_prog_trace, generation/prog.rs:23-29: the 8 interleaved root limbs as one column).  A duplex

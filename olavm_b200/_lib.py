@@ -75,6 +75,7 @@ SIGNATURES = {
     "ola_generate_cmp_trace": (_int, [_vp, _vp, _sz, _u32, _vp, _int]),
     "ola_generate_cpu_trace": (_int, [_vp, _vp, _sz, _u32, _vp, _int]),
     "ola_generate_memory_trace": (_int, [_vp, _vp, _sz, _u32, _vp, _int]),
+    "ola_generate_program_trace": (_int, [_vp, _vp, _sz, _vp, _sz, _vp, _u32, _vp, ctypes.POINTER(_u64), _int]),
     "ola_compress_challenge": (_int, [ctypes.POINTER(_vp), _u32, _sz, ctypes.POINTER(_u64)]),
     "ola_verify": (_int, [ctypes.POINTER(_int), _u32, _vp, _sz, ctypes.c_char_p, _sz]),
     "ola_verify_cfg": (_int, [_int, ctypes.POINTER(_int), _u32, _vp, _sz, ctypes.c_char_p, _sz]),

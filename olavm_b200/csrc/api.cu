@@ -728,6 +728,22 @@ int ola_generate_memory_trace(ola_ctx* ctx, const uint64_t* cells, size_t ncells
         to_host(ctx, out, d_out.p, 29 * n);
     });
 }
+int ola_generate_program_trace(ola_ctx* ctx, const uint64_t* steps, size_t nsteps, const uint64_t* prog_rows, size_t nprog_rows, const uint64_t* roots,
+                               uint32_t log_n, uint64_t* out, uint64_t* beta_out, int on_device) {
+    if (!ctx || (!steps && nsteps) || (!prog_rows && nprog_rows) || !roots || !out || !beta_out || log_n < 1 || log_n > 24) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        const size_t n = (size_t)1 << log_n;
+        if (on_device) {
+            *beta_out = ola::lookup::program_trace(ctx, steps, nsteps, prog_rows, nprog_rows, roots, log_n, out);
+            return;
+        }
+        DevBuf d_s(std::max<size_t>(nsteps * 66, 1)), d_p(std::max<size_t>(nprog_rows * 6, 1)), d_out(18 * n);
+        if (nsteps) to_device(ctx, d_s.p, steps, nsteps * 66);
+        if (nprog_rows) to_device(ctx, d_p.p, prog_rows, nprog_rows * 6);
+        *beta_out = ola::lookup::program_trace(ctx, d_s.p, nsteps, d_p.p, nprog_rows, roots, log_n, d_out.p);
+        to_host(ctx, out, d_out.p, 18 * n);
+    });
+}
 int ola_compress_challenge(const uint64_t* const* cols, uint32_t ncols, size_t n, uint64_t* beta_out) {
     if ((!cols && ncols) || !beta_out) return OLA_ERR_INVALID_ARG;
     try {

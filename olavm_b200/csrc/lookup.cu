@@ -628,5 +628,94 @@ void memory_trace(ola_ctx* ctx, const uint64_t* d_cells, size_t ncells, uint32_t
     check_launch("memory_fill_kernel");
 }
 
+// ---- generate_prog_trace (circuits/src/generation/prog.rs:18-157) ----------------------------------------------------------------------
+// The Program table: one row per fetched program word on the executed side (one or two per executed main line: the instruction
+// and, when it carries one, its immediate -- a prefix sum places them), one row per word of every program on the other side, the
+// beta-compressed (code address, pc, word) of both, and the permuted pair of the lookup between them (permuted_cols at the
+// table's full size: 2^23 rows for the benchmark's run).
+__device__ __forceinline__ uint64_t prog_compress(const uint64_t v[6], uint64_t beta) {  // sum_k v[k] beta^k (prog.rs:149-156)
+    uint64_t acc = 0;
+#pragma unroll
+    for (int k = 5; k >= 0; --k) acc = gl::add(gl::mul(acc, beta), gl::canon(v[k]));
+    return acc;
+}
+__device__ __forceinline__ bool step_fetches_imm(const uint64_t* s) { return s[26] == 1 || s[27] == (1ull << 22) || s[27] == (1ull << 21); }
+__global__ void prog_count_kernel(const uint64_t* __restrict__ steps, size_t nsteps, uint32_t* __restrict__ w) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsteps) return;
+    const uint64_t* s = steps + i * 66;
+    w[i] = s[13] == 1 ? 0u : (step_fetches_imm(s) ? 2u : 1u);  // ext lines fetch nothing (prog.rs:58-60)
+}
+__global__ void prog_exec_fill_kernel(const uint64_t* __restrict__ steps, size_t nsteps, const uint32_t* __restrict__ at, uint64_t beta, size_t n,
+                                      uint64_t* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsteps) return;
+    const uint64_t* s = steps + i * 66;
+    if (s[13] == 1) return;
+    size_t e = at[i];
+    uint64_t v[6] = {s[6], s[7], s[8], s[9], s[12], s[25]};
+    for (int rep = 0; rep < 2; ++rep) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) out[(size_t)(8 + k) * n + e] = gl::canon(v[k]);
+        out[(size_t)14 * n + e] = prog_compress(v, beta);
+        out[(size_t)16 * n + e] = 1;
+        if (rep == 1 || !step_fetches_imm(s)) break;
+        v[4] = s[12] + 1;  // pc + 1: the immediate word
+        v[5] = s[28];
+        ++e;
+    }
+}
+__global__ void prog_rows_fill_kernel(const uint64_t* __restrict__ rows /* [m][6] */, size_t m, uint64_t beta, size_t n, uint64_t* __restrict__ out) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    uint64_t v[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        v[k] = rows[j * 6 + k];
+        out[(size_t)k * n + j] = gl::canon(v[k]);
+    }
+    out[(size_t)6 * n + j] = prog_compress(v, beta);
+    out[(size_t)17 * n + j] = 1;
+}
+// roots[8] (host) = start_root[4], end_root[4]; returns beta.  d_out = [18][n]
+uint64_t program_trace(ola_ctx* ctx, const uint64_t* d_steps, size_t nsteps, const uint64_t* d_prog_rows, size_t m, const uint64_t* roots, uint32_t log_n,
+                       uint64_t* d_out) {
+    const size_t n = (size_t)1 << log_n;
+    OLA_CHECK(log_n >= 1 && log_n <= 24 && m <= n, OLA_ERR_INVALID_ARG, "Program table: a power of two of at least 2 rows with room for every program word");
+    stark::Challenger ch(OLA_HASH_POSEIDON);  // observe start[i], end[i] for i in 0..4 (prog.rs:23-29)
+    for (int i = 0; i < 4; ++i) {
+        ch.observe(gl::canon(roots[i]));
+        ch.observe(gl::canon(roots[4 + i]));
+    }
+    const uint64_t beta = ch.get_challenge();
+    OLA_CUDA(cudaMemsetAsync(d_out, 0, 18 * n * sizeof(uint64_t), ctx->stream));
+    if (nsteps) {
+        const size_t nb = (nsteps + SCAN_BLOCK - 1) / SCAN_BLOCK;
+        Buf w32((2 * nsteps + nb + 8) / 2 + 4);
+        uint32_t* w = w32.u32();
+        uint32_t* at = w + nsteps;
+        uint32_t* sums = at + nsteps;
+        uint32_t* total = sums + nb;
+        Launch lz(ctx, "gen_prog_fill");
+        const unsigned gs = (unsigned)((nsteps + 255) / 256);
+        prog_count_kernel<<<gs, 256, 0, ctx->stream>>>(d_steps, nsteps, w);
+        exclusive_scan(ctx, w, at, sums, total, nsteps);
+        uint32_t exec_len = 0;
+        OLA_CUDA(cudaMemcpyAsync(&exec_len, total, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+        OLA_CHECK(exec_len <= n, OLA_ERR_INVALID_ARG, "Program table: the executed lines fetch more words than the table has rows");
+        prog_exec_fill_kernel<<<gs, 256, 0, ctx->stream>>>(d_steps, nsteps, at, beta, n, d_out);
+        check_launch("prog_exec_fill_kernel");
+        OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    if (m) {
+        Launch lz(ctx, "gen_prog_fill");
+        prog_rows_fill_kernel<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(d_prog_rows, m, beta, n, d_out);
+        check_launch("prog_rows_fill_kernel");
+    }
+    permuted_cols(ctx, d_out + 14 * n, d_out + 6 * n, n, d_out + 15 * n, d_out + 7 * n);  // prog.rs:132-135
+    return beta;
+}
+
 }  // namespace lookup
 }  // namespace ola

@@ -104,6 +104,19 @@ def generate_memory_trace(ctx, cells, log_n=None):
     return out
 
 
+def generate_prog_trace(ctx, steps, prog_rows, roots, log_n):
+    """generate_prog_trace (generation/prog.rs:18-157): Step records [k, 66], program lines [m, 6], roots[8] = start_root,
+    end_root -> (the Program table [18, 2^log_n], its compress challenge)."""
+    r = np.ascontiguousarray(steps, dtype=np.uint64).reshape(-1, 66)
+    pr = np.ascontiguousarray(prog_rows, dtype=np.uint64).reshape(-1, 6)
+    ro = np.ascontiguousarray(roots, dtype=np.uint64).reshape(8)
+    out = np.empty((18, 1 << log_n), dtype=np.uint64)
+    beta = ctypes.c_uint64(0)
+    ctx.check(ctx._lib.ola_generate_program_trace(ctx.handle, _lib.hptr(r) if r.shape[0] else None, r.shape[0], _lib.hptr(pr) if pr.shape[0] else None,
+                                                   pr.shape[0], _lib.hptr(ro), log_n, _lib.hptr(out), ctypes.byref(beta), 0))
+    return out, int(beta.value)
+
+
 def compress_challenge(columns):
     """Challenger::new(); observe_elements(column) for every column; get_challenge()."""
     cols = [np.ascontiguousarray(c, dtype=np.uint64).reshape(-1) for c in columns]

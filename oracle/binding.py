@@ -106,6 +106,8 @@ def _set_sigs(L):
     L.orc_generate_cpu_trace.restype = None
     L.orc_generate_memory_trace.argtypes = [_u64p, _sz, _sz, _u64p]
     L.orc_generate_memory_trace.restype = None
+    L.orc_generate_prog_trace.argtypes = [_u64p, _sz, _u64p, _sz, _u64p, _u64p, _sz, _u64p]
+    L.orc_generate_prog_trace.restype = _sz
     L.orc_compress_challenge.argtypes = [ctypes.POINTER(ctypes.c_void_p), _u32, _sz]
     L.orc_compress_challenge.restype = _u64
 
@@ -399,6 +401,22 @@ def generate_memory_trace(cells, log_n=None):
     out = np.empty((29, n), dtype=np.uint64)
     lib().orc_generate_memory_trace(_p(r), k, n, _p(out))
     return out
+
+
+def generate_prog_trace(steps, prog_rows, roots, log_n=None):
+    """generate_prog_trace (generation/prog.rs:18-157): Step records [k, 66], program lines [m, 6] = (addr0..3, pc, inst),
+    roots[8] = start_root, end_root -> (the Program table [18, n], its compress challenge beta)."""
+    r = np.ascontiguousarray(steps, dtype=np.uint64).reshape(-1, 66)
+    pr = np.ascontiguousarray(prog_rows, dtype=np.uint64).reshape(-1, 6)
+    ro = np.ascontiguousarray(roots, dtype=np.uint64).reshape(8)
+    n = int(lib().orc_generate_prog_trace(_p(r), r.shape[0], _p(pr), pr.shape[0], _p(ro), None, 0, None))
+    if log_n is not None:
+        assert (1 << log_n) >= n
+        n = 1 << log_n
+    out = np.empty((18, n), dtype=np.uint64)
+    beta = np.zeros(1, dtype=np.uint64)
+    lib().orc_generate_prog_trace(_p(r), r.shape[0], _p(pr), pr.shape[0], _p(ro), _p(out), n, _p(beta))
+    return out, int(beta[0])
 
 
 def compress_challenge(columns):

@@ -155,3 +155,61 @@ void orc_generate_memory_trace(const uint64_t *cells, size_t ncells, size_t n, u
     }
 #undef T
 }
+
+/* ---- generate_prog_trace (circuits/src/generation/prog.rs:18-157) -----------------------------------------------------------------
+ * steps: the 66-u64 Step records of orc_generate_cpu_trace (is_ext_line 13, op1_imm 26, opcode 27, addr_code 6..9, pc 12,
+ * instruction 25, immediate_data 28); prog_rows [m][6] = (addr0..3, pc, inst), the lines of every program in order (the Rust
+ * flattens `progs` in the same order, prog.rs:106-131); roots[8] = start_root[4], end_root[4].  Columns program/columns.rs:3-16
+ * (18).  Returns the number of rows n = max(next_power_of_two(max(exec_len, m)), 2) when out == NULL or too small. */
+uint64_t orc_compress_challenge(const uint64_t *const *cols, uint32_t ncols, size_t n); /* stark_api.cpp */
+static uint64_t prog_compress(const uint64_t v[6], uint64_t beta) { /* prog.rs:149-156 */
+    uint64_t acc = 0;
+    for (int k = 5; k >= 0; --k) acc = gl_add(gl_mul(acc, beta), gl_canon(v[k]));
+    return acc;
+}
+size_t orc_generate_prog_trace(const uint64_t *steps, size_t nsteps, const uint64_t *prog_rows, size_t m, const uint64_t roots[8], uint64_t *out,
+                               size_t out_cap_rows, uint64_t *beta_out) {
+    uint64_t inter[8]; /* observe start[i], end[i] for i in 0..4 (prog.rs:25-28) */
+    for (int i = 0; i < 4; ++i) inter[2 * i] = roots[i], inter[2 * i + 1] = roots[4 + i];
+    const uint64_t *col = inter;
+    const uint64_t beta = orc_compress_challenge(&col, 1, 8);
+    size_t exec_len = 0;
+    for (size_t i = 0; i < nsteps; ++i) {
+        const uint64_t *s = steps + i * 66;
+        if (s[13] == 1) continue;
+        exec_len += (s[26] == 1 || s[27] == MASK(OP_MLOAD) || s[27] == MASK(OP_MSTORE)) ? 2 : 1;
+    }
+    size_t filled = exec_len > m ? exec_len : m, n = 2;
+    while (n < filled) n <<= 1;
+    if (out == NULL || out_cap_rows < n) return n;
+    n = out_cap_rows; /* a caller may ask for a larger power of two */
+    memset(out, 0, 18 * n * sizeof(uint64_t));
+#define T(c, i) out[(size_t)(c) * n + (i)]
+    size_t e = 0;
+    for (size_t i = 0; i < nsteps; ++i) { /* :56-104 */
+        const uint64_t *s = steps + i * 66;
+        if (s[13] == 1) continue;
+        uint64_t v[6] = {s[6], s[7], s[8], s[9], s[12], s[25]};
+        for (int k = 0; k < 6; ++k) T(8 + k, e) = gl_canon(v[k]);
+        T(16, e) = 1;
+        T(14, e) = prog_compress(v, beta);
+        e++;
+        if (s[26] == 1 || s[27] == MASK(OP_MLOAD) || s[27] == MASK(OP_MSTORE)) {
+            uint64_t w[6] = {s[6], s[7], s[8], s[9], s[12] + 1, s[28]};
+            for (int k = 0; k < 6; ++k) T(8 + k, e) = gl_canon(w[k]);
+            T(16, e) = 1;
+            T(14, e) = prog_compress(w, beta);
+            e++;
+        }
+    }
+    for (size_t j = 0; j < m; ++j) { /* :106-131 */
+        const uint64_t *r = prog_rows + j * 6;
+        for (int k = 0; k < 6; ++k) T(k, j) = gl_canon(r[k]);
+        T(17, j) = 1;
+        T(6, j) = prog_compress(r, beta);
+    }
+    orc_permuted_cols(&T(14, 0), &T(6, 0), n, &T(15, 0), &T(7, 0)); /* :132-135 */
+#undef T
+    if (beta_out) *beta_out = beta;
+    return n;
+}

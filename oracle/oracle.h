@@ -46,6 +46,8 @@ size_t orc_generate_cmp_trace(const uint64_t *cells, size_t nrows, uint64_t *out
 /* generation_cpu.c */
 void orc_generate_cpu_trace(const uint64_t *steps, size_t nrows, size_t n, uint64_t *out);
 void orc_generate_memory_trace(const uint64_t *cells, size_t ncells, size_t n, uint64_t *out);
+size_t orc_generate_prog_trace(const uint64_t *steps, size_t nsteps, const uint64_t *prog_rows, size_t m, const uint64_t roots[8], uint64_t *out,
+                               size_t out_cap_rows, uint64_t *beta_out);
 
 /* blake3.c */
 void orc_blake3(const uint8_t *in, size_t len, uint8_t out[32]);

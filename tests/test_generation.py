@@ -395,3 +395,67 @@ def test_generate_memory_trace_equals_oracle(ctx, orc):
         ref = orc.generate_memory_trace(rec, log_n)
         bad = [c for c in range(29) if not (got[c] == ref[c]).all()]
         assert not bad, (k, bad)
+
+
+# ---- generate_prog_trace (generation/prog.rs:18-157) --------------------------------------------------------------------------------
+def _vm_program(orc, name):
+    """A reference program through the restated VM -> (Step records, program lines, executed lines, program)."""
+    import json
+    import os
+
+    from workload import tracegen
+
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ola_programs.json")))
+    prog, prophets = tracegen.parse_ola_prophets({"program": g["programs"][name], "prophets": g["prophets"].get(name, [])})
+    tape = tracegen.reference_test_tape(tracegen.REFERENCE_CALLDATA[name]) if name in tracegen.REFERENCE_CALLDATA else ()
+    steps = tracegen.cpu_vm_trace(prog, 13, want_side_tables="all+storage", orc=orc, init_tape=tape, prophets=prophets)[1]
+    prog_rows, exec_rows = tracegen.program_rows_of_run(prog, steps)
+    return tracegen.steps_to_records(steps), np.array(prog_rows, dtype=np.uint64), exec_rows
+
+
+_ROOTS = np.arange(11, 19, dtype=np.uint64)
+
+
+@pytest.mark.parametrize("name", ("fibo_recursive", "memory", "call", "tape", "storage", "fibo_loop", "poseidon_hash"))
+def test_oracle_prog_trace_equals_the_python_generator(orc, name):
+    from workload import tracegen
+
+    records, prog_rows, exec_rows = _vm_program(orc, name)
+    got, beta = orc.generate_prog_trace(records, prog_rows, _ROOTS)
+    inter = np.empty(8, dtype=np.uint64)
+    inter[0::2], inter[1::2] = _ROOTS[:4], _ROOTS[4:]
+    assert beta == orc.compress_challenge([inter])   # start[i], end[i] interleaved (prog.rs:25-28)
+    ref = tracegen.program_valid_trace(np.random.default_rng(0), int(got.shape[1]).bit_length() - 1, beta,
+                                       prog_rows=[tuple(int(x) for x in r) for r in prog_rows], exec_rows=exec_rows)
+    bad = [c for c in range(18) if not (got[c] == ref[c]).all()]
+    assert not bad, bad
+    assert orc.air_first_failure(10, got, compress_challenge=beta) is None
+
+
+@pytest.mark.gpu
+def test_generate_prog_trace_equals_oracle(ctx, orc):
+    from olavm_b200 import generation
+
+    for name in ("fibo_recursive", "storage", "fibo_loop"):
+        records, prog_rows, _ = _vm_program(orc, name)
+        ref, rbeta = orc.generate_prog_trace(records, prog_rows, _ROOTS)
+        log_n = int(ref.shape[1]).bit_length() - 1
+        got, beta = generation.generate_prog_trace(ctx, records, prog_rows, _ROOTS, log_n)
+        assert beta == rbeta
+        bad = [c for c in range(18) if not (got[c] == ref[c]).all()]
+        assert not bad, (name, bad)
+    # a long run: many executed words over a short program, the lookup at 2^17 rows
+    rng = np.random.default_rng(10)
+    prog_rows = np.stack([np.zeros(500, dtype=np.uint64)] * 4 + [np.arange(500, dtype=np.uint64), rng.integers(0, P, size=500, dtype=np.uint64)], axis=1)
+    k = 90000
+    rec = np.zeros((k, 66), dtype=np.uint64)
+    pcs = rng.integers(0, 499, size=k)
+    rec[:, 12] = pcs
+    rec[:, 25] = prog_rows[pcs, 5]
+    rec[:, 26] = rng.integers(0, 2, size=k)            # op1_imm: a second fetched word
+    rec[:, 28] = prog_rows[pcs + 1, 5]
+    rec[:, 27] = np.uint64(1 << 31)
+    rec[:, 13] = (rng.random(k) < 0.1).astype(np.uint64)  # ext lines fetch nothing
+    ref, rbeta = orc.generate_prog_trace(rec, prog_rows, _ROOTS)
+    got, beta = generation.generate_prog_trace(ctx, rec, prog_rows, _ROOTS, int(ref.shape[1]).bit_length() - 1)
+    assert beta == rbeta and (got == ref).all()

@@ -723,6 +723,16 @@ using N8 = tile::Cfg<8, 8, 2, 1, 4, 1>;
 using N9 = tile::Cfg<9, 8, 2, 1, 4, 1>;
 using N10 = tile::Cfg<10, 8, 2, 1, 4, 1>;
 using N11 = tile::Cfg<11, 4, 2, 1, 4, 1>;
+// four sub-blocks per tile (whole 32-byte sectors per store), 256 threads, register cap and 68 KB of shared memory for 3 CTAs / SM:
+// 1.43 ms against 1.95 ms for the eight-lane tile at one 512-thread CTA / SM (profiles/r03h_nat_c4_ab.txt); OLA_NTT_NAT_C4=0 selects the latter
+using N10c4 = tile::Cfg<10, 4, 2, 1, 4, 3>;
+static bool tune_nat_c4() {
+    static bool v = [] {
+        const char* e = getenv("OLA_NTT_NAT_C4");
+        return !(e && atoi(e) == 0);
+    }();
+    return v;
+}
 template <typename G>
 static constexpr size_t tile_nat_smem() {
     return ((size_t)G::C * G::R + (size_t)G::C * 16 + 16 + (size_t)G::RP * G::C) * sizeof(uint64_t);
@@ -733,7 +743,7 @@ static void tile_nat_launch(ola_ctx* ctx, const PassArgs& a, size_t ncols, int n
     b.ncols = ncols;
     b.prefetch = tune_prefetch();
     const size_t groups = (((size_t)1 << a.L) >> G::l) / G::C;
-    b.tiles_per_cta = pick_tiles_per_cta(ctx, groups * ncols * (size_t)ncosets, ncols, 1);
+    b.tiles_per_cta = pick_tiles_per_cta(ctx, groups * ncols * (size_t)ncosets, ncols, G::MINB);
     size_t chunks = (ncols + b.tiles_per_cta - 1) / b.tiles_per_cta;
     while (chunks > 65535) {
         b.tiles_per_cta *= 2;
@@ -752,7 +762,10 @@ static bool tile_nat_dispatch(ola_ctx* ctx, const PassArgs& a, size_t ncols, int
         case 7: tile_nat_launch<N7>(ctx, a, ncols, ncosets); break;
         case 8: tile_nat_launch<N8>(ctx, a, ncols, ncosets); break;
         case 9: tile_nat_launch<N9>(ctx, a, ncols, ncosets); break;
-        case 10: tile_nat_launch<N10>(ctx, a, ncols, ncosets); break;
+        case 10:
+            if (tune_nat_c4()) tile_nat_launch<N10c4>(ctx, a, ncols, ncosets);
+            else tile_nat_launch<N10>(ctx, a, ncols, ncosets);
+            break;
         default: tile_nat_launch<N11>(ctx, a, ncols, ncosets); break;
     }
     return true;
@@ -784,6 +797,7 @@ static void opt_in_shared_memory(int device) {
     tile_nat_optin<N9>(max_optin);
     tile_nat_optin<N10>(max_optin);
     tile_nat_optin<N11>(max_optin);
+    tile_nat_optin<N10c4>(max_optin);
 }
 
 void init_twiddles(ola_ctx* ctx) {

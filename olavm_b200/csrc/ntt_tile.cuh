@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) tile_contig(const PassArgs a) 
 // is one twiddle table per lane (the sub-blocks' row constants differ), built once per CTA and amortised over the
 // columns it streams.  Shift form only (MODE 1 / 2).  grid (2^t / C, column chunks, cosets)
 template <typename G, int MODE>
-__global__ void __launch_bounds__(G::NT, 1) tile_nat(const PassArgs a) {
+__global__ void __launch_bounds__(G::NT, G::MINB) tile_nat(const PassArgs a) {
     extern __shared__ __align__(16) uint64_t sm[];
     constexpr int l = G::l, C = G::C, R = 1 << l;
     uint64_t* tw = sm;                                          // [C][R]

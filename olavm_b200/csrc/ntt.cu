@@ -512,6 +512,14 @@ static int tune_prefetch() {
     }();
     return v;
 }
+// OLA_NTT_STRIDED_C4=1: four-lane tiles (32-byte row segments, 256 threads, 4 CTAs / SM) in the strided 10-stage pass too
+static bool tune_strided_c4() {
+    static bool v = [] {
+        const char* e = getenv("OLA_NTT_STRIDED_C4");
+        return e && atoi(e) == 1;
+    }();
+    return v;
+}
 static bool tune_contig_c4() {
     static bool v = [] {
         const char* e = getenv("OLA_NTT_CONTIG_C4");
@@ -580,7 +588,9 @@ static void tile_optin_all(int max_optin) {
     tile_optin_shift<T8>(max_optin, true);
     tile_optin_shift<T9>(max_optin, true);
     tile_optin_shift<T10v2>(max_optin, true);
-    tile_optin_shift<T10c4>(max_optin, false);
+    tile_optin_shift<T10c4>(max_optin, true);
+    OLA_CUDA(cudaFuncSetAttribute(tile::tile_strided<T10c4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    OLA_CUDA(cudaFuncSetAttribute(tile::tile_strided<T10c4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
 
     tile_optin_shift<T11v2>(max_optin, true);
     tile_optin_shift<tile::Cfg<6, 2>>(max_optin, false);
@@ -668,6 +678,7 @@ static void tile_strided_dispatch(ola_ctx* ctx, const PassArgs& a, size_t ncols,
         case 9: tile_strided_launch_m<T9, GS>(ctx, a, ncols, ncosets); break;
         case 10:
             if (v == 1) tile_strided_launch<T10v1, GS>(ctx, a, ncols, ncosets);
+            else if (v == 2 && tune_strided_c4()) tile_strided_launch_m<T10c4, GS>(ctx, a, ncols, ncosets);
             else if (v == 2) tile_strided_launch_m<T10v2, GS>(ctx, a, ncols, ncosets);
             else if (v == 3) tile_strided_launch<T10v3, GS>(ctx, a, ncols, ncosets);
             else tile_strided_launch<T10, GS>(ctx, a, ncols, ncosets);

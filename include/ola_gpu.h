@@ -338,6 +338,82 @@ int ola_generate_memory_trace(ola_ctx* ctx, const uint64_t* cells, size_t ncells
  * steps, prog_rows and out are device pointers (roots and beta_out stay on the host). */
 int ola_generate_program_trace(ola_ctx* ctx, const uint64_t* steps, size_t nsteps, const uint64_t* prog_rows, size_t nprog_rows, const uint64_t* roots,
                                uint32_t log_n, uint64_t* out, uint64_t* beta_out, int on_device);
+/* generate_poseidon_chunk_trace (circuits/src/generation/poseidon_chunk.rs:7-88): the executor's PoseidonChunkRow list
+ * (core/src/trace/trace.rs:179-192), one record of 32 u64 per line -> the column-major PoseidonChunk table out [53][2^log_n]
+ * (builtins/poseidon/columns.rs:42-68); the result-line, first-padding and filter columns are derived as the Rust derives them,
+ * rows past nrows are padding lines.  Record layout (struct field order):
+ *    0 env_idx   1 clk   2 opcode   3 dst   4 op0   5 op1   6 acc_cnt   7..14 value[8]   15..18 cap[4]   19..30 hash[12]   31 is_ext_line
+ * Every ola_generate_* below: 2^log_n >= max(2, nrows) rows; on_device: rows and out are device pointers. */
+int ola_generate_poseidon_chunk_trace(ola_ctx* ctx, const uint64_t* rows, size_t nrows, uint32_t log_n, uint64_t* out, int on_device);
+/* generate_storage_access_trace (circuits/src/generation/storage.rs:7-123): StorageHashRow records (core/src/trace/trace.rs:279-295),
+ * 38 u64 each, the n_access storage accesses first and the n_prog_reads program-hash reads after them (the Rust chains the two
+ * slices, storage.rs:23) -> the column-major StorageAccess table out [48][2^log_n] (builtins/storage/columns.rs:3-33); padding rows
+ * carry the last root.  Record layout:
+ *    0 storage_access_idx   1..4 pre_root   5..8 root   9 is_write   10 layer   11 layer_bit   12 addr_acc   13..16 addr
+ *   17..20 pre_path   21..24 path   25 hash_type   26..29 pre_hash   30..33 hash   34..37 sibling */
+int ola_generate_storage_access_trace(ola_ctx* ctx, const uint64_t* rows, size_t n_access, size_t n_prog_reads, uint32_t log_n, uint64_t* out,
+                                      int on_device);
+/* generate_tape_trace (circuits/src/generation/tape.rs:10-73): TapeRow records (core/src/trace/trace.rs:297-304) of 5 u64
+ * (is_init, opcode, addr, value, filter_looked) -> the column-major Tape table out [6][2^log_n] (builtins/tape/columns.rs:3-9);
+ * padding rows repeat the last row as an unlooked TLOAD. */
+int ola_generate_tape_trace(ola_ctx* ctx, const uint64_t* rows, size_t nrows, uint32_t log_n, uint64_t* out, int on_device);
+/* generate_sccall_trace (circuits/src/generation/sccall.rs:11-64): SCCallRow records (core/src/trace/trace.rs:306-317) of 24 u64
+ *    0 caller_env_idx   1..4 addr_storage   5..8 addr_code   9 caller_op1_imm   10 clk_caller_call   11 clk_caller_ret
+ *   12..21 regs[10]   22 callee_env_idx   23 clk_callee_end
+ * -> the column-major SCCall table out [26][2^log_n] (builtins/sccall/columns.rs:4-20). */
+int ola_generate_sccall_trace(ola_ctx* ctx, const uint64_t* rows, size_t nrows, uint32_t log_n, uint64_t* out, int on_device);
+/* generate_prog_chunk_trace (circuits/src/generation/prog.rs:158-249): prog_rows [nprog_rows][6] = (code address 0..3, pc, word)
+ * for every word of every program in the order the Rust walks `progs` (the buffer ola_generate_program_trace takes; a program
+ * starts where pc == 0) -> the column-major ProgChunk table out [40][2^log_n] (program/columns.rs:47-62): lines of eight words
+ * absorbed by a Poseidon sponge.  The table is the one the reference produces: the unused word slots of a program's last line
+ * hold the previous line's hash (overwrite-mode sponge, prog.rs:212-216) and the sponge state is NOT reset between programs
+ * (prog.rs:199 declares pre_hash once), so with more than one program the later programs' first lines carry a non-zero capacity.
+ * The line placement is a prefix sum, the hash chain is sequential by construction (one GPU thread). */
+int ola_generate_prog_chunk_trace(ola_ctx* ctx, const uint64_t* prog_rows, size_t nprog_rows, uint32_t log_n, uint64_t* out, int on_device);
+/* ---- Trace JSON ingest and the `ola prove` flow ----
+ * `ola run` writes serde_json::to_writer(&program.trace) (client/src/main.rs:166-169) and `ola prove` reads it back with
+ * serde_json::from_reader::<Trace> (:172-181), calls generate_traces + prove_with_traces (circuits/src/stark/prover.rs:43-66)
+ * and writes Buffer::write_all_proof's bytes (:199-206).  The entry points below are that flow for a host without serde: the
+ * JSON text of a core::trace::trace::Trace (trace.rs:320-342) is parsed once into the flat executor records the
+ * ola_generate_* entry points take (host code, no context needed), and ola_prove_trace generates the twelve tables in device
+ * memory and proves them there.  A Rust host does not need the parser: it flattens its own Trace into the same records. */
+typedef struct ola_trace ola_trace;
+/* Returns OLA_ERR_INVALID_ARG with the reason (and the byte offset) in err when the text is not a serialised Trace.  Unknown
+ * keys are skipped; fields the generators recompute (PoseidonRow's round states, RangeCheckRow's limbs) are not read.
+ * addr_program_hash (a HashMap the Rust iterates in unspecified order) is taken in file order. */
+int ola_trace_from_json(const char* json, size_t len, ola_trace** out, char* err, size_t errcap);
+void ola_trace_free(ola_trace* t);
+#define OLA_REC_STEP 0             /* exec                      [k][66]  (ola_generate_cpu_trace's record)            */
+#define OLA_REC_MEMORY 1           /* memory                    [k][15]                                               */
+#define OLA_REC_RC_VAL 2           /* builtin_rangecheck        [k]      val                                          */
+#define OLA_REC_RC_KIND 3          /*                           [k]      0 cpu 1 mem sort 2 mem region 3 comparison 4 none */
+#define OLA_REC_BITWISE_TAG 4      /* builtin_bitwise_combined  [k]      opcode                                       */
+#define OLA_REC_BITWISE_OP0 5
+#define OLA_REC_BITWISE_OP1 6
+#define OLA_REC_BITWISE_RES 7
+#define OLA_REC_CMP 8              /* builtin_cmp               [k][6]                                                */
+#define OLA_REC_POSEIDON_INPUT 9   /* builtin_poseidon          [k][12]  input                                        */
+#define OLA_REC_POSEIDON_FILTER 10 /*                           [k][4]   normal, treekey, storage, storage_branch     */
+#define OLA_REC_POSEIDON_CHUNK 11  /* builtin_poseidon_chunk    [k][32]                                               */
+#define OLA_REC_STORAGE_HASH 12    /* builtin_storage_hash then builtin_program_hash  [k][38]                         */
+#define OLA_REC_TAPE 13            /* tape                      [k][5]                                                */
+#define OLA_REC_SCCALL 14          /* sc_call                   [k][24]                                               */
+#define OLA_REC_PROG_ROW 15        /* addr_program_hash         [m][6]   (code address 0..3, pc, word)                */
+#define OLA_REC_ROOTS 16           /* start_end_roots           [1][8]                                                */
+#define OLA_REC_STORAGE_ACCESS_COUNT 17 /* *nrows = how many OLA_REC_STORAGE_HASH records are storage accesses (rows = NULL) */
+/* *rows points into the trace object (valid until ola_trace_free), *nrows records of *rec_u64 u64 each */
+int ola_trace_records(const ola_trace* t, int kind, const uint64_t** rows, size_t* nrows, uint32_t* rec_u64);
+/* log2 of the row count generate_traces gives table `table_id` (0..11) for this trace, or a negative error */
+int ola_trace_table_log_rows(const ola_trace* t, int table_id);
+/* generate_traces (circuits/src/generation/mod.rs:79-213): the twelve tables, column-major, generated in device memory.
+ * tables_dev[12] receives device pointers the caller frees with ola_dev_free (table i: ola_table_columns(i) << log_ns[i] u64),
+ * log_ns[12] the row counts, compress_challenges[12] the Bitwise / Program betas (other entries 0) -- the three arrays
+ * ola_prove takes with on_device = 1. */
+int ola_generate_traces(ola_ctx* ctx, const ola_trace* t, uint64_t** tables_dev, uint32_t* log_ns, uint64_t* compress_challenges);
+/* `ola prove`: ola_generate_traces + ola_prove over the twelve tables (degree check on) + the proof bytes; the tables never
+ * leave the device.  proof_out / proof_cap / proof_len as in ola_prove. */
+int ola_prove_trace(ola_ctx* ctx, const ola_trace* t, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+
 /* The compress challenge of the Bitwise / Program tables: a fresh Poseidon Challenger observes `ncols` HOST columns of n
  * elements, column after column, and squeezes one element (generate_bitwise_trace, generation/builtin.rs:118-131: the 12
  * limb columns; generate_prog_trace, generation/prog.rs:23-29: the 8 interleaved root limbs as one column).  A duplex

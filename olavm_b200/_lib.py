@@ -76,6 +76,17 @@ SIGNATURES = {
     "ola_generate_cpu_trace": (_int, [_vp, _vp, _sz, _u32, _vp, _int]),
     "ola_generate_memory_trace": (_int, [_vp, _vp, _sz, _u32, _vp, _int]),
     "ola_generate_program_trace": (_int, [_vp, _vp, _sz, _vp, _sz, _vp, _u32, _vp, ctypes.POINTER(_u64), _int]),
+    "ola_generate_poseidon_chunk_trace": (_int, [_vp, _vp, _sz, _u32, _vp, _int]),
+    "ola_generate_storage_access_trace": (_int, [_vp, _vp, _sz, _sz, _u32, _vp, _int]),
+    "ola_generate_tape_trace": (_int, [_vp, _vp, _sz, _u32, _vp, _int]),
+    "ola_generate_sccall_trace": (_int, [_vp, _vp, _sz, _u32, _vp, _int]),
+    "ola_generate_prog_chunk_trace": (_int, [_vp, _vp, _sz, _u32, _vp, _int]),
+    "ola_trace_from_json": (_int, [ctypes.c_char_p, _sz, ctypes.POINTER(_vp), ctypes.c_char_p, _sz]),
+    "ola_trace_free": (None, [_vp]),
+    "ola_trace_records": (_int, [_vp, _int, ctypes.POINTER(_vp), ctypes.POINTER(_sz), ctypes.POINTER(_u32)]),
+    "ola_trace_table_log_rows": (_int, [_vp, _int]),
+    "ola_generate_traces": (_int, [_vp, _vp, ctypes.POINTER(_vp), ctypes.POINTER(_u32), ctypes.POINTER(_u64)]),
+    "ola_prove_trace": (_int, [_vp, _vp, _vp, _sz, ctypes.POINTER(_sz)]),
     "ola_compress_challenge": (_int, [ctypes.POINTER(_vp), _u32, _sz, ctypes.POINTER(_u64)]),
     "ola_verify": (_int, [ctypes.POINTER(_int), _u32, _vp, _sz, ctypes.c_char_p, _sz]),
     "ola_verify_cfg": (_int, [_int, ctypes.POINTER(_int), _u32, _vp, _sz, ctypes.c_char_p, _sz]),

@@ -744,6 +744,56 @@ int ola_generate_program_trace(ola_ctx* ctx, const uint64_t* steps, size_t nstep
         to_host(ctx, out, d_out.p, 18 * n);
     });
 }
+extern "C++" {
+// the five small tables: record rows in, one column-major table out (gen_tables.cu)
+template <class F>
+static int generate_small(ola_ctx* ctx, const uint64_t* rows, size_t nrows, size_t rec, uint32_t log_n, int ncols, uint64_t* out, int on_device, F&& run) {
+    if (!ctx || (!rows && nrows) || !out || log_n < 1 || log_n > 28 || nrows > ((size_t)1 << log_n)) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        const size_t n = (size_t)1 << log_n;
+        if (on_device) {
+            run(rows, out);
+            return;
+        }
+        DevBuf d_r(std::max<size_t>(nrows * rec, 1)), d_out((size_t)ncols * n);
+        if (nrows) to_device(ctx, d_r.p, rows, nrows * rec);
+        run(d_r.p, d_out.p);
+        to_host(ctx, out, d_out.p, (size_t)ncols * n);
+    });
+}
+}
+int ola_generate_poseidon_chunk_trace(ola_ctx* ctx, const uint64_t* rows, size_t nrows, uint32_t log_n, uint64_t* out, int on_device) {
+    return generate_small(ctx, rows, nrows, 32, log_n, 53, out, on_device,
+                          [&](const uint64_t* r, uint64_t* o) { ola::lookup::poseidon_chunk_trace(ctx, r, nrows, log_n, o); });
+}
+int ola_generate_storage_access_trace(ola_ctx* ctx, const uint64_t* rows, size_t n_access, size_t n_prog_reads, uint32_t log_n, uint64_t* out,
+                                      int on_device) {
+    if (n_access + n_prog_reads < n_access) return OLA_ERR_INVALID_ARG;
+    return generate_small(ctx, rows, n_access + n_prog_reads, 38, log_n, 48, out, on_device,
+                          [&](const uint64_t* r, uint64_t* o) { ola::lookup::storage_access_trace(ctx, r, n_access, n_prog_reads, log_n, o); });
+}
+int ola_generate_tape_trace(ola_ctx* ctx, const uint64_t* rows, size_t nrows, uint32_t log_n, uint64_t* out, int on_device) {
+    return generate_small(ctx, rows, nrows, 5, log_n, 6, out, on_device,
+                          [&](const uint64_t* r, uint64_t* o) { ola::lookup::tape_trace(ctx, r, nrows, log_n, o); });
+}
+int ola_generate_sccall_trace(ola_ctx* ctx, const uint64_t* rows, size_t nrows, uint32_t log_n, uint64_t* out, int on_device) {
+    return generate_small(ctx, rows, nrows, 24, log_n, 26, out, on_device,
+                          [&](const uint64_t* r, uint64_t* o) { ola::lookup::sccall_trace(ctx, r, nrows, log_n, o); });
+}
+int ola_generate_prog_chunk_trace(ola_ctx* ctx, const uint64_t* prog_rows, size_t nprog_rows, uint32_t log_n, uint64_t* out, int on_device) {
+    if (!ctx || (!prog_rows && nprog_rows) || !out || log_n < 1 || log_n > 28 || nprog_rows > ((size_t)1 << 31)) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        const size_t n = (size_t)1 << log_n;
+        if (on_device) {
+            ola::lookup::prog_chunk_trace(ctx, prog_rows, nprog_rows, log_n, out);
+            return;
+        }
+        DevBuf d_r(std::max<size_t>(nprog_rows * 6, 1)), d_out(40 * n);
+        if (nprog_rows) to_device(ctx, d_r.p, prog_rows, nprog_rows * 6);
+        ola::lookup::prog_chunk_trace(ctx, d_r.p, nprog_rows, log_n, d_out.p);
+        to_host(ctx, out, d_out.p, 40 * n);
+    });
+}
 int ola_compress_challenge(const uint64_t* const* cols, uint32_t ncols, size_t n, uint64_t* beta_out) {
     if ((!cols && ncols) || !beta_out) return OLA_ERR_INVALID_ARG;
     try {
@@ -826,6 +876,191 @@ int ola_batch_prove_leaf(ola_ctx* ctx, const ola_batch* b, size_t leaf_index, ui
     int n = 0;
     int rc = guarded(ctx, [&] { n = ola::batch_prove_leaf(ctx, b, leaf_index, siblings_out_host); });
     return rc == OLA_OK ? n : rc;
+}
+
+// ---- Trace JSON ingest and the `ola prove` flow ----
+}  // extern "C"
+#include "trace_json.h"
+struct ola_trace {
+    ola::tracejson::Records rec;
+};
+namespace {
+uint32_t log_rows(size_t filled, size_t at_least) {  // the generators' "next power of two, at least `at_least`"
+    uint32_t lg = 0;
+    while (((size_t)1 << lg) < std::max(filled, at_least)) ++lg;
+    return lg;
+}
+// the row count generate_traces gives each table (circuits/src/generation/*.rs, the first lines of every generator)
+uint32_t trace_table_log_rows(const ola::tracejson::Records& r, int table) {
+    switch (table) {
+        case 0: return log_rows(r.steps.size() / 66, 1);                  // cpu.rs:13-18
+        case 1: return log_rows(r.memory.size() / 15, 2);                 // memory.rs:11-20
+        case 2: return log_rows(r.bw_tags.size(), (size_t)3 << 16);       // builtin.rs:39-52 (BITWISE_U8_SIZE = 3 * 2^16)
+        case 3: return log_rows(r.cmp.size() / 6, 2);                     // builtin.rs:209-218
+        case 4: return log_rows(r.rc_vals.size(), (size_t)1 << 16);       // builtin.rs:252-262
+        case 5: return log_rows(r.psdn_inputs.size() / 12, 2);            // poseidon.rs:6-15
+        case 6: return log_rows(r.pchunk.size() / 32, 2);
+        case 7: return log_rows(r.storage.size() / 38, 2);
+        case 8: return log_rows(r.tape.size() / 5, 2);
+        case 9: return log_rows(r.sccall.size() / 24, 2);
+        case 10: {  // prog.rs:30-55: max(words fetched by the executed lines, words of all programs)
+            size_t exec_len = 0;
+            for (size_t i = 0; i < r.steps.size() / 66; ++i) {
+                const uint64_t* s = r.steps.data() + i * 66;
+                if (s[13] != 0) continue;
+                exec_len += (s[26] == 1 || s[27] == (1ull << 22) || s[27] == (1ull << 21)) ? 2 : 1;
+            }
+            return log_rows(std::max(exec_len, r.prog_rows.size() / 6), 2);
+        }
+        case 11: {
+            size_t lines = 0;
+            for (size_t i = 0; i < r.prog_rows.size() / 6; ++i) lines += r.prog_rows[i * 6 + 4] % 8 == 0;
+            return log_rows(lines, 2);
+        }
+    }
+    return 0;
+}
+struct Upload {  // a record array in device memory for the duration of one generator call
+    DevBuf d;
+    Upload(ola_ctx* ctx, const std::vector<uint64_t>& v) : d(std::max<size_t>(v.size(), 1)) {
+        if (!v.empty()) to_device(ctx, d.p, v.data(), v.size());
+    }
+};
+// generate_traces (circuits/src/generation/mod.rs:79-213): twelve column-major tables in device memory, tables[t] of
+// ola_table_columns(t) << log_ns[t] u64 (owned by the caller: ola_dev_free), and the two compress challenges
+void generate_all(ola_ctx* ctx, const ola::tracejson::Records& r, uint64_t** tables, uint32_t* log_ns, uint64_t* cc) {
+    namespace L = ola::lookup;
+    for (int t = 0; t < 12; ++t) {
+        tables[t] = nullptr;
+        cc[t] = 0;
+        log_ns[t] = trace_table_log_rows(r, t);
+    }
+    try {
+        for (int t = 0; t < 12; ++t) ola::dev_alloc(&tables[t], (size_t)ola::stark::table_info(t).columns << log_ns[t]);
+        { Upload u(ctx, r.steps); L::cpu_trace(ctx, u.d.p, r.steps.size() / 66, log_ns[0], tables[0]); }
+        { Upload u(ctx, r.memory); L::memory_trace(ctx, u.d.p, r.memory.size() / 15, log_ns[1], tables[1]); }
+        {
+            Upload a(ctx, r.bw_tags), b(ctx, r.bw_op0), c(ctx, r.bw_op1), d(ctx, r.bw_res);
+            cc[2] = L::bitwise_trace(ctx, a.d.p, b.d.p, c.d.p, d.d.p, r.bw_tags.size(), log_ns[2], tables[2]);
+        }
+        { Upload u(ctx, r.cmp); L::cmp_trace(ctx, u.d.p, r.cmp.size() / 6, log_ns[3], tables[3]); }
+        { Upload v(ctx, r.rc_vals), k(ctx, r.rc_kinds); L::rangecheck_trace(ctx, v.d.p, k.d.p, r.rc_vals.size(), log_ns[4], tables[4]); }
+        {
+            Upload i(ctx, r.psdn_inputs), f(ctx, r.psdn_filters);
+            ola::generation::poseidon_trace(ctx, i.d.p, f.d.p, r.psdn_inputs.size() / 12, log_ns[5], tables[5]);
+        }
+        { Upload u(ctx, r.pchunk); L::poseidon_chunk_trace(ctx, u.d.p, r.pchunk.size() / 32, log_ns[6], tables[6]); }
+        {
+            Upload u(ctx, r.storage);
+            L::storage_access_trace(ctx, u.d.p, r.n_storage_access, r.storage.size() / 38 - r.n_storage_access, log_ns[7], tables[7]);
+        }
+        { Upload u(ctx, r.tape); L::tape_trace(ctx, u.d.p, r.tape.size() / 5, log_ns[8], tables[8]); }
+        { Upload u(ctx, r.sccall); L::sccall_trace(ctx, u.d.p, r.sccall.size() / 24, log_ns[9], tables[9]); }
+        {
+            Upload s(ctx, r.steps), p(ctx, r.prog_rows);
+            cc[10] = L::program_trace(ctx, s.d.p, r.steps.size() / 66, p.d.p, r.prog_rows.size() / 6, r.roots, log_ns[10], tables[10]);
+            L::prog_chunk_trace(ctx, p.d.p, r.prog_rows.size() / 6, log_ns[11], tables[11]);
+            OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+    } catch (...) {
+        cudaStreamSynchronize(ctx->stream);
+        for (int t = 0; t < 12; ++t)
+            if (tables[t]) ola::dev_free(tables[t]), tables[t] = nullptr;
+        throw;
+    }
+}
+}  // namespace
+extern "C" {
+int ola_trace_from_json(const char* json, size_t len, ola_trace** out, char* err, size_t errcap) {
+    if (err && errcap) err[0] = 0;
+    if (!json || !out) return OLA_ERR_INVALID_ARG;
+    *out = nullptr;
+    try {
+        std::unique_ptr<ola_trace> t(new ola_trace());
+        ola::tracejson::parse(json, len, t->rec);
+        *out = t.release();
+        return OLA_OK;
+    } catch (const std::exception& e) {
+        if (err && errcap) {
+            strncpy(err, e.what(), errcap - 1);
+            err[errcap - 1] = 0;
+        }
+        return OLA_ERR_INVALID_ARG;
+    } catch (...) {
+        return OLA_ERR_INTERNAL;
+    }
+}
+void ola_trace_free(ola_trace* t) { delete t; }
+int ola_trace_records(const ola_trace* t, int kind, const uint64_t** rows, size_t* nrows, uint32_t* rec_u64) {
+    if (!t || !rows || !nrows || !rec_u64) return OLA_ERR_INVALID_ARG;
+    const ola::tracejson::Records& r = t->rec;
+    const std::vector<uint64_t>* v = nullptr;
+    uint32_t rec = 1;
+    switch (kind) {
+        case OLA_REC_STEP: v = &r.steps, rec = 66; break;
+        case OLA_REC_MEMORY: v = &r.memory, rec = 15; break;
+        case OLA_REC_RC_VAL: v = &r.rc_vals; break;
+        case OLA_REC_RC_KIND: v = &r.rc_kinds; break;
+        case OLA_REC_BITWISE_TAG: v = &r.bw_tags; break;
+        case OLA_REC_BITWISE_OP0: v = &r.bw_op0; break;
+        case OLA_REC_BITWISE_OP1: v = &r.bw_op1; break;
+        case OLA_REC_BITWISE_RES: v = &r.bw_res; break;
+        case OLA_REC_CMP: v = &r.cmp, rec = 6; break;
+        case OLA_REC_POSEIDON_INPUT: v = &r.psdn_inputs, rec = 12; break;
+        case OLA_REC_POSEIDON_FILTER: v = &r.psdn_filters, rec = 4; break;
+        case OLA_REC_POSEIDON_CHUNK: v = &r.pchunk, rec = 32; break;
+        case OLA_REC_STORAGE_HASH: v = &r.storage, rec = 38; break;
+        case OLA_REC_TAPE: v = &r.tape, rec = 5; break;
+        case OLA_REC_SCCALL: v = &r.sccall, rec = 24; break;
+        case OLA_REC_PROG_ROW: v = &r.prog_rows, rec = 6; break;
+        case OLA_REC_ROOTS:
+            *rows = r.roots, *nrows = 1, *rec_u64 = 8;
+            return OLA_OK;
+        case OLA_REC_STORAGE_ACCESS_COUNT:
+            *rows = nullptr, *nrows = r.n_storage_access, *rec_u64 = 0;
+            return OLA_OK;
+        default: return OLA_ERR_INVALID_ARG;
+    }
+    *rows = v->empty() ? nullptr : v->data();
+    *nrows = v->size() / rec;
+    *rec_u64 = rec;
+    return OLA_OK;
+}
+int ola_trace_table_log_rows(const ola_trace* t, int table_id) {
+    if (!t || table_id < 0 || table_id > 11) return OLA_ERR_INVALID_ARG;
+    return (int)trace_table_log_rows(t->rec, table_id);
+}
+int ola_generate_traces(ola_ctx* ctx, const ola_trace* t, uint64_t** tables_dev, uint32_t* log_ns, uint64_t* compress_challenges) {
+    if (!ctx || !t || !tables_dev || !log_ns || !compress_challenges) return OLA_ERR_INVALID_ARG;
+    return guarded(ctx, [&] { generate_all(ctx, t->rec, tables_dev, log_ns, compress_challenges); });
+}
+int ola_prove_trace(ola_ctx* ctx, const ola_trace* t, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+    if (!ctx || !t || !proof_len || (!proof_out && proof_cap)) return OLA_ERR_INVALID_ARG;
+    *proof_len = 0;
+    return guarded(ctx, [&] {
+        uint64_t* tables[12];
+        uint32_t log_ns[12];
+        uint64_t cc[12];
+        generate_all(ctx, t->rec, tables, log_ns, cc);
+        std::vector<uint8_t> bytes;
+        try {
+            ola::stark::Config cfg;  // StarkConfig::standard_fast_config(), the degree check on (client/src/main.rs:192)
+            std::vector<int> ids = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11};
+            std::vector<const uint64_t*> tr(tables, tables + 12);
+            std::vector<uint32_t> lg(log_ns, log_ns + 12);
+            std::vector<uint64_t> c(cc, cc + 12);
+            bytes = ola::stark::prove_all(ctx, ids, tr, true, lg, c, cfg);
+        } catch (...) {
+            cudaStreamSynchronize(ctx->stream);
+            for (int i = 0; i < 12; ++i) ola::dev_free(tables[i]);
+            throw;
+        }
+        for (int i = 0; i < 12; ++i) ola::dev_free(tables[i]);
+        *proof_len = bytes.size();
+        OLA_CHECK(bytes.size() <= proof_cap, OLA_ERR_INVALID_ARG, "proof buffer too small (needed size returned in proof_len)");
+        memcpy(proof_out, bytes.data(), bytes.size());
+    });
 }
 
 }  // extern "C"

@@ -10,5 +10,6 @@
 #include "stark.cu"
 #include "generation.cu"
 #include "lookup.cu"
+#include "gen_tables.cu"
 #include "nccl_comm.cu"
 #include "api.cu"

@@ -145,3 +145,54 @@ class Hasher:
 
     def poseidon_table_row(self, inp):
         return generate_poseidon_trace(self.ctx, np.asarray(inp, dtype=np.uint64).reshape(1, 12), log_n=1)[:, 0].copy()
+
+
+def _padded_log(k, log_n):
+    return max(1, (max(k, 1) - 1).bit_length()) if log_n is None else log_n
+
+
+def _small(ctx, fn, rows, rec, ncols, log_n, *extra):
+    r = np.ascontiguousarray(rows, dtype=np.uint64).reshape(-1, rec)
+    k = r.shape[0]
+    log_n = _padded_log(k, log_n)
+    out = np.empty((ncols, 1 << log_n), dtype=np.uint64)
+    args = extra if extra else (k,)
+    ctx.check(fn(ctx.handle, _lib.hptr(r) if k else None, *args, log_n, _lib.hptr(out), 0))
+    return out
+
+
+def generate_poseidon_chunk_trace(ctx, rows, log_n=None):
+    """generate_poseidon_chunk_trace (generation/poseidon_chunk.rs:7-88): PoseidonChunkRow records [k, 32] (layout:
+    include/ola_gpu.h) -> the PoseidonChunk table [53, 2^log_n]."""
+    return _small(ctx, ctx._lib.ola_generate_poseidon_chunk_trace, rows, 32, 53, log_n)
+
+
+def generate_storage_access_trace(ctx, accesses, prog_hash_reads=(), log_n=None):
+    """generate_storage_access_trace (generation/storage.rs:7-123): StorageHashRow records [k, 38] of the storage accesses and
+    of the program-hash reads -> the StorageAccess table [48, 2^log_n]."""
+    a = np.ascontiguousarray(accesses, dtype=np.uint64).reshape(-1, 38)
+    b = np.ascontiguousarray(prog_hash_reads, dtype=np.uint64).reshape(-1, 38)
+    return _small(ctx, ctx._lib.ola_generate_storage_access_trace, np.concatenate([a, b]), 38, 48, log_n, a.shape[0], b.shape[0])
+
+
+def generate_tape_trace(ctx, rows, log_n=None):
+    """generate_tape_trace (generation/tape.rs:10-73): TapeRow records [k, 5] -> the Tape table [6, 2^log_n]."""
+    return _small(ctx, ctx._lib.ola_generate_tape_trace, rows, 5, 6, log_n)
+
+
+def generate_sccall_trace(ctx, rows, log_n=None):
+    """generate_sccall_trace (generation/sccall.rs:11-64): SCCallRow records [k, 24] -> the SCCall table [26, 2^log_n]."""
+    return _small(ctx, ctx._lib.ola_generate_sccall_trace, rows, 24, 26, log_n)
+
+
+def generate_prog_chunk_trace(ctx, prog_rows, log_n=None):
+    """generate_prog_chunk_trace (generation/prog.rs:158-249): prog_rows [m, 6] = (code address 0..3, pc, word) -> the
+    ProgChunk table [40, 2^log_n]."""
+    r = np.ascontiguousarray(prog_rows, dtype=np.uint64).reshape(-1, 6)
+    m = r.shape[0]
+    if log_n is None:
+        lines = int(((r[:, 4] % np.uint64(8)) == 0).sum()) if m else 0
+        log_n = _padded_log(lines, None)
+    out = np.empty((40, 1 << log_n), dtype=np.uint64)
+    ctx.check(ctx._lib.ola_generate_prog_chunk_trace(ctx.handle, _lib.hptr(r) if m else None, m, log_n, _lib.hptr(out), 0))
+    return out

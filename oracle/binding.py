@@ -108,6 +108,10 @@ def _set_sigs(L):
     L.orc_generate_memory_trace.restype = None
     L.orc_generate_prog_trace.argtypes = [_u64p, _sz, _u64p, _sz, _u64p, _u64p, _sz, _u64p]
     L.orc_generate_prog_trace.restype = _sz
+    for name, nsz in (("poseidon_chunk", 1), ("storage_access", 2), ("tape", 1), ("sccall", 1), ("prog_chunk", 1)):
+        f = getattr(L, "orc_generate_%s_trace" % name)
+        f.argtypes = [_u64p] + [_sz] * nsz + [_u64p, _sz]
+        f.restype = _sz
     L.orc_compress_challenge.argtypes = [ctypes.POINTER(ctypes.c_void_p), _u32, _sz]
     L.orc_compress_challenge.restype = _u64
 
@@ -417,6 +421,48 @@ def generate_prog_trace(steps, prog_rows, roots, log_n=None):
     beta = np.zeros(1, dtype=np.uint64)
     lib().orc_generate_prog_trace(_p(r), r.shape[0], _p(pr), pr.shape[0], _p(ro), _p(out), n, _p(beta))
     return out, int(beta[0])
+
+
+def _small_table(fn, ncols, args, log_n):
+    n = int(fn(*args, None, 0))
+    if log_n is not None:
+        assert (1 << log_n) >= n
+        n = 1 << log_n
+    out = np.empty((ncols, n), dtype=np.uint64)
+    fn(*args, _p(out), n)
+    return out
+
+
+def generate_poseidon_chunk_trace(cells, log_n=None):
+    """generate_poseidon_chunk_trace (generation/poseidon_chunk.rs:7-88): PoseidonChunkRow records [k, 32] -> [53, n]."""
+    c = np.ascontiguousarray(cells, dtype=np.uint64).reshape(-1, 32)
+    return _small_table(lib().orc_generate_poseidon_chunk_trace, 53, (_p(c), c.shape[0]), log_n)
+
+
+def generate_storage_access_trace(accesses, prog_hash_reads=(), log_n=None):
+    """generate_storage_access_trace (generation/storage.rs:7-123): StorageHashRow records [k, 38] -> [48, n]."""
+    a = np.ascontiguousarray(accesses, dtype=np.uint64).reshape(-1, 38)
+    b = np.ascontiguousarray(prog_hash_reads, dtype=np.uint64).reshape(-1, 38)
+    r = np.ascontiguousarray(np.concatenate([a, b]))
+    return _small_table(lib().orc_generate_storage_access_trace, 48, (_p(r), a.shape[0], b.shape[0]), log_n)
+
+
+def generate_tape_trace(cells, log_n=None):
+    """generate_tape_trace (generation/tape.rs:10-73): TapeRow records [k, 5] -> [6, n]."""
+    c = np.ascontiguousarray(cells, dtype=np.uint64).reshape(-1, 5)
+    return _small_table(lib().orc_generate_tape_trace, 6, (_p(c), c.shape[0]), log_n)
+
+
+def generate_sccall_trace(cells, log_n=None):
+    """generate_sccall_trace (generation/sccall.rs:11-64): SCCallRow records [k, 24] -> [26, n]."""
+    c = np.ascontiguousarray(cells, dtype=np.uint64).reshape(-1, 24)
+    return _small_table(lib().orc_generate_sccall_trace, 26, (_p(c), c.shape[0]), log_n)
+
+
+def generate_prog_chunk_trace(prog_rows, log_n=None):
+    """generate_prog_chunk_trace (generation/prog.rs:158-249): program words [m, 6] = (addr0..3, pc, word) -> [40, n]."""
+    r = np.ascontiguousarray(prog_rows, dtype=np.uint64).reshape(-1, 6)
+    return _small_table(lib().orc_generate_prog_chunk_trace, 40, (_p(r), r.shape[0]), log_n)
 
 
 def compress_challenge(columns):

@@ -49,6 +49,14 @@ void orc_generate_memory_trace(const uint64_t *cells, size_t ncells, size_t n, u
 size_t orc_generate_prog_trace(const uint64_t *steps, size_t nsteps, const uint64_t *prog_rows, size_t m, const uint64_t roots[8], uint64_t *out,
                                size_t out_cap_rows, uint64_t *beta_out);
 
+/* generation_small.c: the five small tables (records in struct field order, see the file).  Each returns the reference's row count and
+ * fills out[ncols][out_rows] when out_rows >= that count. */
+size_t orc_generate_poseidon_chunk_trace(const uint64_t *cells, size_t k, uint64_t *out, size_t out_rows);
+size_t orc_generate_storage_access_trace(const uint64_t *rows, size_t n_access, size_t n_prog, uint64_t *out, size_t out_rows);
+size_t orc_generate_tape_trace(const uint64_t *cells, size_t k, uint64_t *out, size_t out_rows);
+size_t orc_generate_sccall_trace(const uint64_t *cells, size_t k, uint64_t *out, size_t out_rows);
+size_t orc_generate_prog_chunk_trace(const uint64_t *prog_rows, size_t m, uint64_t *out, size_t out_rows);
+
 /* blake3.c */
 void orc_blake3(const uint8_t *in, size_t len, uint8_t out[32]);
 void orc_blake3_hash_no_pad(const uint64_t *in, size_t n, uint64_t out[4]);

@@ -459,3 +459,175 @@ def test_generate_prog_trace_equals_oracle(ctx, orc):
     ref, rbeta = orc.generate_prog_trace(rec, prog_rows, _ROOTS)
     got, beta = generation.generate_prog_trace(ctx, rec, prog_rows, _ROOTS, int(ref.shape[1]).bit_length() - 1)
     assert beta == rbeta and (got == ref).all()
+
+
+# ---- the five small tables: PoseidonChunk, StorageAccess, Tape, SCCall, ProgChunk -----------------------------------------------------
+_SMALL_PROGRAMS = ("poseidon_hash", "storage", "tape", "fibo_loop", "context_fetch")
+
+
+def _vm_tables(orc, name):
+    """A reference program through the restated VM -> {table id: table} of the whole system and the program's words."""
+    import json
+    import os
+
+    from workload import tracegen
+
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ola_programs.json")))
+    prog, prophets = tracegen.parse_ola_prophets({"program": g["programs"][name], "prophets": g["prophets"].get(name, [])})
+    if name in tracegen.REFERENCE_CALLDATA:
+        tape = tracegen.reference_test_tape(tracegen.REFERENCE_CALLDATA[name])
+    else:
+        tape = tracegen.CONTEXT_TAPE if name == "context_fetch" else ()
+    ids, traces, cc, steps = tracegen.run_system(orc, np.random.default_rng(3), prog, prophets=prophets, init_tape=tape)
+    return dict(zip(ids, traces))
+
+
+def _tape_records_of_table(t):
+    """TapeRow records of a Tape table: the rows up to the last one that is not the padding form of its predecessor."""
+    n = t.shape[1]
+    k = n
+    while k > 1 and t[1, k - 1] == t[1, k - 2] and t[2, k - 1] == (1 << 9) and t[3, k - 1] == t[3, k - 2] and t[4, k - 1] == t[4, k - 2] \
+            and t[5, k - 1] == 0:
+        k -= 1
+    return np.ascontiguousarray(t[1:6, :k].T)
+
+
+@pytest.mark.parametrize("name", _SMALL_PROGRAMS)
+def test_oracle_small_tables_equal_the_vm_tables(orc, name):
+    """The VM's tables satisfy the AIRs and prove (tests/test_oracle_stark.py); the oracle's generators, fed the executor records
+    read back from those tables, must rebuild them: every derived flag column and every padding row."""
+    from workload import tracegen
+
+    tabs = _vm_tables(orc, name)
+    checked = 0
+    if 6 in tabs:
+        t = tabs[6]
+        got = orc.generate_poseidon_chunk_trace(tracegen.poseidon_chunk_records_of_table(t), int(t.shape[1]).bit_length() - 1)
+        assert not [c for c in range(53) if not (got[c] == t[c]).all()]
+        checked += 1
+    if 7 in tabs:
+        t = tabs[7]
+        rec, n_access = tracegen.storage_records_of_table(t)
+        got = orc.generate_storage_access_trace(rec[:n_access], rec[n_access:], int(t.shape[1]).bit_length() - 1)
+        assert not [c for c in range(48) if not (got[c] == t[c]).all()]
+        checked += 1
+    if 8 in tabs:
+        t = tabs[8]
+        got = orc.generate_tape_trace(_tape_records_of_table(t), int(t.shape[1]).bit_length() - 1)
+        assert (got == t).all()
+        checked += 1
+    assert checked >= 1
+
+
+@pytest.mark.parametrize("name", ("fibo_loop", "storage", "poseidon_hash"))
+def test_oracle_prog_chunk_trace_equals_the_vm_table(orc, name):
+    """One program: the VM's ProgChunk table (lines of eight words, sponge in overwrite mode, capacity reset on the first line)
+    is the reference's; it satisfies the AIR."""
+    from workload import tracegen
+
+    _, prog_rows, _ = _vm_program(orc, name)
+    words = [int(w) for w in prog_rows[:, 5]]
+    addr = [int(x) for x in prog_rows[0, :4]]
+    lines = (len(words) + 7) // 8
+    log_n = max(1, (lines - 1).bit_length())
+    t = tracegen.prog_chunk_valid_trace(orc, np.random.default_rng(0), log_n, programs=[(addr, words)])[0]
+    got = orc.generate_prog_chunk_trace(prog_rows)
+    assert got.shape == t.shape
+    assert not [c for c in range(40) if not (got[c] == t[c]).all()]
+    assert orc.air_first_failure(11, got) is None
+
+
+def _random_small_records(rng, kind, k):
+    if kind == "poseidon_chunk":
+        r = rng.integers(0, P, size=(k, 32), dtype=np.uint64)
+        r[:, 1] = rng.integers(0, 1 << 32, size=k)
+        r[:, 31] = rng.integers(0, 2, size=k)
+        r[:, 5] = rng.integers(1, 40, size=k)
+        r[:, 6] = np.where(rng.random(k) < 0.5, r[:, 5], rng.integers(0, 40, size=k).astype(np.uint64))
+        return r
+    if kind == "storage":
+        r = rng.integers(0, P, size=(k, 38), dtype=np.uint64)
+        r[:, 10] = rng.choice([1, 2, 63, 64, 65, 127, 128, 191, 192, 255, 256, 300], size=k)
+        r[:, 11] = rng.integers(0, 3, size=k)
+        r[:, 9] = rng.integers(0, 2, size=k)
+        return r
+    if kind == "tape":
+        r = rng.integers(0, P, size=(k, 5), dtype=np.uint64)
+        r[:, 0] = rng.integers(0, 2, size=k)
+        return r
+    return rng.integers(0, P, size=(k, 24), dtype=np.uint64)
+
+
+def test_oracle_small_tables_row_counts_and_padding(orc):
+    """The reference's row count (next power of two, at least 2) and the padding rows of each table."""
+    rng = np.random.default_rng(5)
+    for k, n in ((0, 2), (1, 2), (2, 2), (3, 4), (8, 8), (9, 16)):
+        assert orc.generate_poseidon_chunk_trace(_random_small_records(rng, "poseidon_chunk", k)).shape == (53, n)
+        assert orc.generate_sccall_trace(_random_small_records(rng, "sccall", k)).shape == (26, n)
+        rec = _random_small_records(rng, "tape", k)
+        t = orc.generate_tape_trace(rec)
+        assert t.shape == (6, n)
+        if k < n:
+            assert (t[2, k:] == 1 << 9).all() and (t[5, k:] == 0).all() and (t[0] == 0).all()
+            assert (t[3, k:] == (rec[k - 1, 2] % P if k else 0)).all() and (t[4, k:] == (rec[k - 1, 3] % P if k else 0)).all()
+        rec = _random_small_records(rng, "storage", k)
+        t = orc.generate_storage_access_trace(rec[: k // 2], rec[k // 2:])
+        assert t.shape == (48, n) and (t[47, k:] == 1).all() and (t[47, :k] == 0).all()
+        if 0 < k < n:
+            assert (t[5:9, k:] == (rec[k - 1, 5:9] % P)[:, None]).all()
+        assert (t[46, : k // 2] == 0).all() and (t[46, k // 2:k] == (rec[k // 2:, 10] == 256)).all()
+    # two programs: the sponge state runs on from the first program's last line into the second's first line (prog.rs:199)
+    words = rng.integers(0, P, size=13 + 5, dtype=np.uint64)
+    rows = [(1, 2, 3, 4, pc, int(words[pc])) for pc in range(13)] + [(5, 6, 7, 8, pc, int(words[13 + pc])) for pc in range(5)]
+    t = orc.generate_prog_chunk_trace(np.array(rows, dtype=np.uint64))
+    assert t.shape == (40, 4) and list(t[39]) == [0, 0, 0, 1] and list(t[29]) == [1, 0, 1, 0] and list(t[30]) == [0, 1, 1, 0]
+    assert list(t[4]) == [0, 8, 0, 0] and list(t[31:39, 1]) == [1] * 5 + [0] * 3
+    assert (t[10:13, 1] == t[22:25, 0]).all()      # unused slots 5..7 of line 1 = hash[5..8] of line 0
+    assert (t[13:17, 2] == t[25:29, 1]).all() and t[13:17, 2].any()   # the second program's first line carries the capacity
+    h = orc.poseidon(np.concatenate([t[5:13, 1], t[13:17, 1]]))
+    assert (t[17:29, 1] == h).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,log_n", [(0, 1), (1, 1), (5, 3), (1000, 10), (40000, 16)])
+def test_generate_small_tables_equal_oracle(ctx, orc, k, log_n):
+    from olavm_b200 import generation
+
+    rng = np.random.default_rng(k + 77)
+    rec = _random_small_records(rng, "poseidon_chunk", k)
+    if k:
+        rec[0, 0] = np.uint64(P + 3)   # a non-canonical representative lands in the table as its canonical value
+    assert (generation.generate_poseidon_chunk_trace(ctx, rec, log_n) == orc.generate_poseidon_chunk_trace(rec, log_n)).all()
+    rec = _random_small_records(rng, "storage", k)
+    for n_access in (0, k // 3, k):
+        got = generation.generate_storage_access_trace(ctx, rec[:n_access], rec[n_access:], log_n)
+        assert (got == orc.generate_storage_access_trace(rec[:n_access], rec[n_access:], log_n)).all()
+    rec = _random_small_records(rng, "tape", k)
+    assert (generation.generate_tape_trace(ctx, rec, log_n) == orc.generate_tape_trace(rec, log_n)).all()
+    rec = _random_small_records(rng, "sccall", k)
+    assert (generation.generate_sccall_trace(ctx, rec, log_n) == orc.generate_sccall_trace(rec, log_n)).all()
+
+
+@pytest.mark.gpu
+def test_generate_prog_chunk_trace_equals_oracle(ctx, orc):
+    from olavm_b200 import generation
+
+    rng = np.random.default_rng(21)
+    for lens in ((), (1,), (8,), (13,), (16, 1), (3, 700, 8, 9), (4001,)):
+        rows = []
+        for p, L in enumerate(lens):
+            addr = [int(x) for x in rng.integers(0, P, size=4, dtype=np.uint64)]
+            rows += [tuple(addr) + (pc, int(rng.integers(0, P, dtype=np.uint64))) for pc in range(L)]
+        rows = np.array(rows, dtype=np.uint64).reshape(-1, 6)
+        ref = orc.generate_prog_chunk_trace(rows)
+        got = generation.generate_prog_chunk_trace(ctx, rows)
+        assert got.shape == ref.shape, lens
+        bad = [c for c in range(40) if not (got[c] == ref[c]).all()]
+        assert not bad, (lens, bad)
+        got = generation.generate_prog_chunk_trace(ctx, rows, int(ref.shape[1]).bit_length() + 1)   # a larger table: more padding lines
+        assert (got == orc.generate_prog_chunk_trace(rows, int(ref.shape[1]).bit_length() + 1)).all()
+    for name in ("fibo_loop", "storage"):
+        _, prog_rows, _ = _vm_program(orc, name)
+        ref = orc.generate_prog_chunk_trace(prog_rows)
+        assert (generation.generate_prog_chunk_trace(ctx, prog_rows) == ref).all()
+        assert orc.air_first_failure(11, ref) is None

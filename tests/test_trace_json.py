@@ -1,0 +1,121 @@
+"""Trace JSON ingest and the `ola prove` flow: ola_trace_from_json (host code) against the records the text
+was written from, and -- on the GPU -- ola_generate_traces against the oracle's generators and ola_prove_trace against the
+verifiers.  The text is serde's layout of core::trace::trace::Trace (core/src/trace/trace.rs:320-342)."""
+import json
+import re
+
+import numpy as np
+import pytest
+
+P = 0xFFFFFFFF00000001
+_KEYS = dict(steps="step", memory="memory", rc_vals="rc_val", rc_kinds="rc_kind", bw_tags="bitwise_tag", bw_op0="bitwise_op0", bw_op1="bitwise_op1",
+             bw_res="bitwise_res", cmp="cmp", psdn_inputs="poseidon_input", psdn_filters="poseidon_filter", pchunk="poseidon_chunk", storage="storage_hash",
+             tape="tape", sccall="sccall", prog_rows="prog_row")
+
+
+@pytest.fixture(scope="module")
+def run(orc):
+    from workload import trace_json as wj
+
+    rec = wj.system_records(orc, np.random.default_rng(9))
+    return rec, wj.records_to_json(rec, orc)
+
+
+def test_parser_returns_the_records_the_text_was_written_from(run):
+    from olavm_b200 import trace_json
+
+    rec, text = run
+    assert len(text) > 100000 and json.loads(text)["exec"][0]["register_selector"]["op0_reg_sel"]   # the nested serde shape
+    t = trace_json.Trace(text)
+    for key, kind in _KEYS.items():
+        got = t.records(kind)
+        assert got.shape == rec[key].shape and (got == rec[key]).all(), key
+    assert t.records("storage_access_count") == rec["n_storage_access"]
+    assert (t.records("roots").reshape(8) == rec["roots"]).all()
+    # the reference's row counts: next power of two, at least 2 (2^16 RangeCheck, 3 * 2^16 -> 2^18 Bitwise, 1 for the CPU table)
+    assert t.table_log_rows(0) == (len(rec["steps"]) - 1).bit_length()
+    assert t.table_log_rows(2) == 18 and t.table_log_rows(4) == 16 and t.table_log_rows(9) == 1
+    assert t.table_log_rows(7) == 8 and t.table_log_rows(11) == max(1, ((len(rec["prog_rows"]) + 7) // 8 - 1).bit_length())
+    t.close()
+
+
+def test_parser_accepts_any_key_order_whitespace_and_unknown_fields(run):
+    from olavm_b200 import trace_json
+
+    rec, text = run
+    doc = json.loads(text)
+    doc = {k: doc[k] for k in reversed(list(doc))}                      # builtin_program_hash before builtin_storage_hash
+    doc["exec"] = [dict(reversed(list(s.items())), added_later={"x": [1, {"y": "}]"}]}) for s in doc["exec"]]
+    doc["a_new_table"] = [{"v": 1.5e3, "w": None, "s": 'esc " [ { \\ '}]
+    t = trace_json.Trace(json.dumps(doc, indent=1))
+    for key, kind in _KEYS.items():
+        assert (t.records(kind) == rec[key]).all(), key
+    assert t.records("storage_access_count") == rec["n_storage_access"]
+
+
+def test_parser_limits():
+    from olavm_b200 import trace_json
+
+    t = trace_json.Trace('{"exec":[],"ret":[18446744069414584320,18446744073709551615]}')
+    assert t.records("step").shape == (0, 66) and t.table_log_rows(0) == 0 and t.table_log_rows(1) == 1
+    t = trace_json.Trace('{"builtin_cmp":[{"op0":18446744073709551615,"op1":0,"gte":1,"abs_diff":2,"abs_diff_inv":3,"filter_looking_rc":1}]}')
+    assert [int(x) for x in t.records("cmp")[0]] == [(1 << 64) - 1, 0, 1, 2, 3, 1]
+    t = trace_json.Trace('{"tape":[{"is_init":true,"opcode":0,"addr":3,"value":4,"filter_looked":0},{"is_init":false,"opcode":512,"addr":3,"value":4,'
+                         '"filter_looked":1}]}')
+    assert t.records("tape").tolist() == [[1, 0, 3, 4, 0], [0, 512, 3, 4, 1]]
+    t = trace_json.Trace('{"addr_program_hash":{"%s":[7,8,9],"%s":[]}}' % ("00" * 7 + "01" + "00" * 15 + "02" + "ff" * 8, "ab" * 32))
+    assert t.records("prog_row").tolist() == [[1, 0, 2, (1 << 64) - 1, 0, 7], [1, 0, 2, (1 << 64) - 1, 1, 8], [1, 0, 2, (1 << 64) - 1, 2, 9]]
+
+
+@pytest.mark.parametrize("text,why", [
+    ("", "unexpected end"), ("[]", "expected '{'"), ('{"exec":[{"clk":1.5}]}', "float"), ('{"exec":[{"clk":-1}]}', "unsigned integer"),
+    ('{"exec":[{"clk":18446744073709551616}]}', "64 bits"), ('{"exec":[{"regs":[1,2,3]}]}', "unexpected length"),
+    ('{"exec":[{"regs":[1,2,3,4,5,6,7,8,9,10,11]}]}', "unexpected length"), ('{"exec":[{"clk":1}', "unexpected end"),
+    ('{"exec":[]} x', "trailing"), ('{"addr_program_hash":{"12":[1]}}', "64 hex"), ('{"start_end_roots":[[1,2,3,4]]}', "pair"),
+    ('{"tape":[{"is_init":maybe}]}', "unsigned integer or a bool"), ('{"exec":{"clk":1}}', "expected '['"),
+])
+def test_parser_rejects_what_serde_would_reject(text, why):
+    from olavm_b200 import trace_json
+
+    with pytest.raises(ValueError, match=re.escape(why)):
+        trace_json.Trace(text)
+
+
+@pytest.mark.gpu
+def test_generate_traces_equals_the_oracle_generators_and_the_proof_verifies(ctx, orc, run):
+    """The whole `ola prove` flow on the device: JSON -> records -> twelve tables generated in HBM -> proof.  Every table equals the
+    oracle generator's on the same records; both verifiers accept the proof; the bytes equal ola_prove's on host copies of the
+    tables (nothing in the flow depends on where the tables were generated)."""
+    import olavm_b200
+    from olavm_b200 import trace_json
+
+    rec, text = run
+    t = trace_json.Trace(text)
+    tabs, logs, cc = trace_json.generate_traces(ctx, t)
+    cols = [94, 29, 59, 6, 12, 134, 53, 48, 6, 26, 18, 40]
+    try:
+        host = [ctx.download(tabs[i], (cols[i], 1 << logs[i])) for i in range(12)]
+    finally:
+        for p in tabs:
+            ctx.free(p)
+    assert logs == [t.table_log_rows(i) for i in range(12)]
+    ref = {0: orc.generate_cpu_trace(rec["steps"], logs[0]), 1: orc.generate_memory_trace(rec["memory"], logs[1]),
+           3: orc.generate_cmp_trace(rec["cmp"]), 4: orc.generate_rc_trace(rec["rc_vals"], rec["rc_kinds"]),
+           6: orc.generate_poseidon_chunk_trace(rec["pchunk"], logs[6]),
+           7: orc.generate_storage_access_trace(rec["storage"][: rec["n_storage_access"]], rec["storage"][rec["n_storage_access"]:], logs[7]),
+           8: orc.generate_tape_trace(rec["tape"], logs[8]), 9: orc.generate_sccall_trace(rec["sccall"], logs[9]),
+           11: orc.generate_prog_chunk_trace(rec["prog_rows"], logs[11])}
+    bw, beta_bw = orc.generate_bitwise_trace(rec["bw_tags"], rec["bw_op0"], rec["bw_op1"], rec["bw_res"])
+    pt, beta_p = orc.generate_prog_trace(rec["steps"], rec["prog_rows"], rec["roots"], logs[10])
+    ref[2], ref[10] = bw, pt
+    assert cc[2] == beta_bw and cc[10] == beta_p and all(cc[i] == 0 for i in range(12) if i not in (2, 10))
+    for i, r in ref.items():
+        bad = [c for c in range(cols[i]) if not (host[i][c] == r[c]).all()]
+        assert not bad, (i, bad)
+    for i in range(12):
+        assert orc.air_first_failure(i, host[i], compress_challenge=cc[i]) is None, i
+    proof = trace_json.prove_trace(ctx, t)
+    ok, why = olavm_b200.verify_proof(list(range(12)), proof)
+    assert ok, why
+    assert orc.stark_verify(list(range(12)), proof)[0]
+    assert proof == olavm_b200.prove_with_traces(ctx, list(range(12)), host, compress_challenges=cc)

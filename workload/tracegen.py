@@ -361,6 +361,7 @@ def prog_chunk_valid_trace(orc, rng, log_n, line_counts=(1, 3, 2), programs=None
     for paddr, pwords, L in todo:
         addr = [int(x) for x in _rand(rng, 4)] if paddr is None else [int(x) for x in paddr]
         cap = [0, 0, 0, 0]
+        h = [0] * 12
         for j in range(L):
             last = j == L - 1
             if pwords is None:
@@ -370,7 +371,7 @@ def prog_chunk_valid_trace(orc, rng, log_n, line_counts=(1, 3, 2), programs=None
                 cnt = min(8, len(pwords) - 8 * j)
                 inst = [int(x) for x in pwords[8 * j:8 * j + cnt]] + [0] * (8 - cnt)
             for k in range(cnt, 8):
-                inst[k] = 0
+                inst[k] = h[k]  # overwrite-mode sponge: the unused slots keep the previous line's output (prog.rs:212-216)
             h = [int(x) for x in orc.poseidon(np.array(inst + cap, dtype=np.uint64))]
             t[0:4, row] = addr
             t[4, row] = 8 * j
@@ -1109,6 +1110,41 @@ def poseidon_chunk_trace_from_calls(calls, log_n):
     assert 2 <= row <= n
     t[52, row:] = 1
     return t, psdn
+
+
+def tape_records_from_log(tape_log):
+    """TapeRow records [k, 5] = (is_init, opcode, addr, value, filter_looked) in gen_tape_table's order."""
+    rows = [(is_init, op, addr, value, looked) for addr in sorted(tape_log) for is_init, op, value, looked in tape_log[addr]]
+    return np.array(rows, dtype=np.uint64).reshape(-1, 5)
+
+
+def poseidon_chunk_records_of_table(t):
+    """PoseidonChunkRow records [k, 32] read back from the filled rows of a PoseidonChunk table (the record fields are table
+    columns; the derived columns 33..52 are what the generator must reproduce)."""
+    k = int((t[52] == 0).sum())
+    r = np.zeros((k, 32), dtype=np.uint64)
+    r[:, 0], r[:, 1], r[:, 2], r[:, 3], r[:, 4], r[:, 5], r[:, 6] = t[1, :k], t[2, :k], t[3, :k], t[6, :k], t[4, :k], t[5, :k], t[7, :k]
+    r[:, 7:15], r[:, 15:19], r[:, 19:31], r[:, 31] = t[8:16, :k].T, t[16:20, :k].T, t[20:32, :k].T, t[32, :k]
+    return r
+
+
+def storage_records_of_table(t):
+    """StorageHashRow records [k, 38] read back from the filled rows of a StorageAccess table, and how many of them are storage
+    accesses (the program-hash reads, marked in column 46 on their layer-256 row, come last)."""
+    k = int((t[47] == 0).sum())
+    r = np.zeros((k, 38), dtype=np.uint64)
+    r[:, 0], r[:, 1:5], r[:, 5:9] = t[0, :k], t[1:5, :k].T, t[5:9, :k].T
+    r[:, 9], r[:, 10], r[:, 11], r[:, 12] = t[9, :k], t[10, :k], t[11, :k], t[12, :k]
+    r[:, 13:17], r[:, 17:21], r[:, 21:25], r[:, 25] = t[13:17, :k].T, t[17:21, :k].T, t[21:25, :k].T, t[29, :k]
+    r[:, 26:30], r[:, 30:34], r[:, 34:38] = t[30:34, :k].T, t[34:38, :k].T, t[25:29, :k].T
+    prog = np.nonzero(t[46, :k])[0]
+    n_access = k if len(prog) == 0 else int(prog[0]) - 255
+    return r, n_access
+
+
+def sccall_records_of_table(t):
+    k = int((t[25] == 0).sum())
+    return np.ascontiguousarray(t[1:25, :k].T)
 
 
 def memory_cells_to_records(cells):

@@ -401,6 +401,12 @@ void ola_trace_free(ola_trace* t);
 #define OLA_REC_PROG_ROW 15        /* addr_program_hash         [m][6]   (code address 0..3, pc, word)                */
 #define OLA_REC_ROOTS 16           /* start_end_roots           [1][8]                                                */
 #define OLA_REC_STORAGE_ACCESS_COUNT 17 /* *nrows = how many OLA_REC_STORAGE_HASH records are storage accesses (rows = NULL) */
+/* The same object built from records the caller already holds (a Rust host flattening its own Trace: no JSON, no copy).
+ * ola_trace_new makes an empty trace; ola_trace_set_records points kind `kind` at nrows records the CALLER keeps alive until the
+ * trace is freed or the kind is set again (OLA_REC_ROOTS copies its 8 values; OLA_REC_STORAGE_ACCESS_COUNT takes the count in
+ * nrows, rows ignored).  Kinds that are never set are empty lists, as in a Trace::default(). */
+int ola_trace_new(ola_trace** out);
+int ola_trace_set_records(ola_trace* t, int kind, const uint64_t* rows, size_t nrows);
 /* *rows points into the trace object (valid until ola_trace_free), *nrows records of *rec_u64 u64 each */
 int ola_trace_records(const ola_trace* t, int kind, const uint64_t** rows, size_t* nrows, uint32_t* rec_u64);
 /* log2 of the row count generate_traces gives table `table_id` (0..11) for this trace, or a negative error */

@@ -83,6 +83,8 @@ SIGNATURES = {
     "ola_generate_prog_chunk_trace": (_int, [_vp, _vp, _sz, _u32, _vp, _int]),
     "ola_trace_from_json": (_int, [ctypes.c_char_p, _sz, ctypes.POINTER(_vp), ctypes.c_char_p, _sz]),
     "ola_trace_free": (None, [_vp]),
+    "ola_trace_new": (_int, [ctypes.POINTER(_vp)]),
+    "ola_trace_set_records": (_int, [_vp, _int, _vp, _sz]),
     "ola_trace_records": (_int, [_vp, _int, ctypes.POINTER(_vp), ctypes.POINTER(_sz), ctypes.POINTER(_u32)]),
     "ola_trace_table_log_rows": (_int, [_vp, _int]),
     "ola_generate_traces": (_int, [_vp, _vp, ctypes.POINTER(_vp), ctypes.POINTER(_u32), ctypes.POINTER(_u64)]),

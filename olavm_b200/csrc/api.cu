@@ -892,29 +892,32 @@ uint32_t log_rows(size_t filled, size_t at_least) {  // the generators' "next po
 }
 // the row count generate_traces gives each table (circuits/src/generation/*.rs, the first lines of every generator)
 uint32_t trace_table_log_rows(const ola::tracejson::Records& r, int table) {
+    using namespace ola::tracejson;
     switch (table) {
-        case 0: return log_rows(r.steps.size() / 66, 1);                  // cpu.rs:13-18
-        case 1: return log_rows(r.memory.size() / 15, 2);                 // memory.rs:11-20
-        case 2: return log_rows(r.bw_tags.size(), (size_t)3 << 16);       // builtin.rs:39-52 (BITWISE_U8_SIZE = 3 * 2^16)
-        case 3: return log_rows(r.cmp.size() / 6, 2);                     // builtin.rs:209-218
-        case 4: return log_rows(r.rc_vals.size(), (size_t)1 << 16);       // builtin.rs:252-262
-        case 5: return log_rows(r.psdn_inputs.size() / 12, 2);            // poseidon.rs:6-15
-        case 6: return log_rows(r.pchunk.size() / 32, 2);
-        case 7: return log_rows(r.storage.size() / 38, 2);
-        case 8: return log_rows(r.tape.size() / 5, 2);
-        case 9: return log_rows(r.sccall.size() / 24, 2);
+        case 0: return log_rows(r.n(REC_STEP), 1);                        // cpu.rs:13-18
+        case 1: return log_rows(r.n(REC_MEMORY), 2);                      // memory.rs:11-20
+        case 2: return log_rows(r.n(REC_BW_TAG), (size_t)3 << 16);        // builtin.rs:39-52 (BITWISE_U8_SIZE = 3 * 2^16)
+        case 3: return log_rows(r.n(REC_CMP), 2);                         // builtin.rs:209-218
+        case 4: return log_rows(r.n(REC_RC_VAL), (size_t)1 << 16);        // builtin.rs:252-262
+        case 5: return log_rows(r.n(REC_PSDN_INPUT), 2);                  // poseidon.rs:6-15
+        case 6: return log_rows(r.n(REC_PCHUNK), 2);
+        case 7: return log_rows(r.n(REC_STORAGE), 2);
+        case 8: return log_rows(r.n(REC_TAPE), 2);
+        case 9: return log_rows(r.n(REC_SCCALL), 2);
         case 10: {  // prog.rs:30-55: max(words fetched by the executed lines, words of all programs)
             size_t exec_len = 0;
-            for (size_t i = 0; i < r.steps.size() / 66; ++i) {
-                const uint64_t* s = r.steps.data() + i * 66;
+            const uint64_t* steps = r.rows(REC_STEP);
+            for (size_t i = 0; i < r.n(REC_STEP); ++i) {
+                const uint64_t* s = steps + i * 66;
                 if (s[13] != 0) continue;
                 exec_len += (s[26] == 1 || s[27] == (1ull << 22) || s[27] == (1ull << 21)) ? 2 : 1;
             }
-            return log_rows(std::max(exec_len, r.prog_rows.size() / 6), 2);
+            return log_rows(std::max(exec_len, r.n(REC_PROG_ROW)), 2);
         }
         case 11: {
             size_t lines = 0;
-            for (size_t i = 0; i < r.prog_rows.size() / 6; ++i) lines += r.prog_rows[i * 6 + 4] % 8 == 0;
+            const uint64_t* pr = r.rows(REC_PROG_ROW);
+            for (size_t i = 0; i < r.n(REC_PROG_ROW); ++i) lines += pr[i * 6 + 4] % 8 == 0;
             return log_rows(lines, 2);
         }
     }
@@ -922,14 +925,18 @@ uint32_t trace_table_log_rows(const ola::tracejson::Records& r, int table) {
 }
 struct Upload {  // a record array in device memory for the duration of one generator call
     DevBuf d;
-    Upload(ola_ctx* ctx, const std::vector<uint64_t>& v) : d(std::max<size_t>(v.size(), 1)) {
-        if (!v.empty()) to_device(ctx, d.p, v.data(), v.size());
+    Upload(ola_ctx* ctx, const ola::tracejson::Records& r, int kind) : d(std::max<size_t>(r.u64s(kind), 1)) {
+        if (r.u64s(kind)) to_device(ctx, d.p, r.rows(kind), r.u64s(kind));
     }
 };
 // generate_traces (circuits/src/generation/mod.rs:79-213): twelve column-major tables in device memory, tables[t] of
 // ola_table_columns(t) << log_ns[t] u64 (owned by the caller: ola_dev_free), and the two compress challenges
 void generate_all(ola_ctx* ctx, const ola::tracejson::Records& r, uint64_t** tables, uint32_t* log_ns, uint64_t* cc) {
     namespace L = ola::lookup;
+    using namespace ola::tracejson;
+    OLA_CHECK(r.n(REC_RC_KIND) == r.n(REC_RC_VAL) && r.n(REC_BW_OP0) == r.n(REC_BW_TAG) && r.n(REC_BW_OP1) == r.n(REC_BW_TAG) &&
+                  r.n(REC_BW_RES) == r.n(REC_BW_TAG) && r.n(REC_PSDN_FILTER) == r.n(REC_PSDN_INPUT) && r.n_storage_access <= r.n(REC_STORAGE),
+              OLA_ERR_INVALID_ARG, "trace records: the parallel arrays of one table differ in length");
     for (int t = 0; t < 12; ++t) {
         tables[t] = nullptr;
         cc[t] = 0;
@@ -937,31 +944,31 @@ void generate_all(ola_ctx* ctx, const ola::tracejson::Records& r, uint64_t** tab
     }
     try {
         for (int t = 0; t < 12; ++t) ola::dev_alloc(&tables[t], (size_t)ola::stark::table_info(t).columns << log_ns[t]);
-        { Upload u(ctx, r.steps); L::cpu_trace(ctx, u.d.p, r.steps.size() / 66, log_ns[0], tables[0]); }
-        { Upload u(ctx, r.memory); L::memory_trace(ctx, u.d.p, r.memory.size() / 15, log_ns[1], tables[1]); }
         {
-            Upload a(ctx, r.bw_tags), b(ctx, r.bw_op0), c(ctx, r.bw_op1), d(ctx, r.bw_res);
-            cc[2] = L::bitwise_trace(ctx, a.d.p, b.d.p, c.d.p, d.d.p, r.bw_tags.size(), log_ns[2], tables[2]);
-        }
-        { Upload u(ctx, r.cmp); L::cmp_trace(ctx, u.d.p, r.cmp.size() / 6, log_ns[3], tables[3]); }
-        { Upload v(ctx, r.rc_vals), k(ctx, r.rc_kinds); L::rangecheck_trace(ctx, v.d.p, k.d.p, r.rc_vals.size(), log_ns[4], tables[4]); }
-        {
-            Upload i(ctx, r.psdn_inputs), f(ctx, r.psdn_filters);
-            ola::generation::poseidon_trace(ctx, i.d.p, f.d.p, r.psdn_inputs.size() / 12, log_ns[5], tables[5]);
-        }
-        { Upload u(ctx, r.pchunk); L::poseidon_chunk_trace(ctx, u.d.p, r.pchunk.size() / 32, log_ns[6], tables[6]); }
-        {
-            Upload u(ctx, r.storage);
-            L::storage_access_trace(ctx, u.d.p, r.n_storage_access, r.storage.size() / 38 - r.n_storage_access, log_ns[7], tables[7]);
-        }
-        { Upload u(ctx, r.tape); L::tape_trace(ctx, u.d.p, r.tape.size() / 5, log_ns[8], tables[8]); }
-        { Upload u(ctx, r.sccall); L::sccall_trace(ctx, u.d.p, r.sccall.size() / 24, log_ns[9], tables[9]); }
-        {
-            Upload s(ctx, r.steps), p(ctx, r.prog_rows);
-            cc[10] = L::program_trace(ctx, s.d.p, r.steps.size() / 66, p.d.p, r.prog_rows.size() / 6, r.roots, log_ns[10], tables[10]);
-            L::prog_chunk_trace(ctx, p.d.p, r.prog_rows.size() / 6, log_ns[11], tables[11]);
+            Upload s(ctx, r, REC_STEP), p(ctx, r, REC_PROG_ROW);  // the Step records serve the CPU and the Program table
+            L::cpu_trace(ctx, s.d.p, r.n(REC_STEP), log_ns[0], tables[0]);
+            cc[10] = L::program_trace(ctx, s.d.p, r.n(REC_STEP), p.d.p, r.n(REC_PROG_ROW), r.roots, log_ns[10], tables[10]);
+            L::prog_chunk_trace(ctx, p.d.p, r.n(REC_PROG_ROW), log_ns[11], tables[11]);
             OLA_CUDA(cudaStreamSynchronize(ctx->stream));
         }
+        { Upload u(ctx, r, REC_MEMORY); L::memory_trace(ctx, u.d.p, r.n(REC_MEMORY), log_ns[1], tables[1]); }
+        {
+            Upload a(ctx, r, REC_BW_TAG), b(ctx, r, REC_BW_OP0), c(ctx, r, REC_BW_OP1), d(ctx, r, REC_BW_RES);
+            cc[2] = L::bitwise_trace(ctx, a.d.p, b.d.p, c.d.p, d.d.p, r.n(REC_BW_TAG), log_ns[2], tables[2]);
+        }
+        { Upload u(ctx, r, REC_CMP); L::cmp_trace(ctx, u.d.p, r.n(REC_CMP), log_ns[3], tables[3]); }
+        { Upload v(ctx, r, REC_RC_VAL), k(ctx, r, REC_RC_KIND); L::rangecheck_trace(ctx, v.d.p, k.d.p, r.n(REC_RC_VAL), log_ns[4], tables[4]); }
+        {
+            Upload i(ctx, r, REC_PSDN_INPUT), f(ctx, r, REC_PSDN_FILTER);
+            ola::generation::poseidon_trace(ctx, i.d.p, f.d.p, r.n(REC_PSDN_INPUT), log_ns[5], tables[5]);
+        }
+        { Upload u(ctx, r, REC_PCHUNK); L::poseidon_chunk_trace(ctx, u.d.p, r.n(REC_PCHUNK), log_ns[6], tables[6]); }
+        {
+            Upload u(ctx, r, REC_STORAGE);
+            L::storage_access_trace(ctx, u.d.p, r.n_storage_access, r.n(REC_STORAGE) - r.n_storage_access, log_ns[7], tables[7]);
+        }
+        { Upload u(ctx, r, REC_TAPE); L::tape_trace(ctx, u.d.p, r.n(REC_TAPE), log_ns[8], tables[8]); }
+        { Upload u(ctx, r, REC_SCCALL); L::sccall_trace(ctx, u.d.p, r.n(REC_SCCALL), log_ns[9], tables[9]); }
         OLA_CUDA(cudaStreamSynchronize(ctx->stream));
     } catch (...) {
         cudaStreamSynchronize(ctx->stream);
@@ -992,39 +999,46 @@ int ola_trace_from_json(const char* json, size_t len, ola_trace** out, char* err
     }
 }
 void ola_trace_free(ola_trace* t) { delete t; }
+int ola_trace_new(ola_trace** out) {
+    if (!out) return OLA_ERR_INVALID_ARG;
+    try {
+        *out = new ola_trace();
+        return OLA_OK;
+    } catch (...) {
+        return OLA_ERR_OOM;
+    }
+}
+int ola_trace_set_records(ola_trace* t, int kind, const uint64_t* rows, size_t nrows) {
+    if (!t || (!rows && nrows && kind != OLA_REC_STORAGE_ACCESS_COUNT)) return OLA_ERR_INVALID_ARG;
+    ola::tracejson::Records& r = t->rec;
+    if (kind == OLA_REC_ROOTS) {
+        if (nrows != 1) return OLA_ERR_INVALID_ARG;
+        memcpy(r.roots, rows, sizeof r.roots);
+        return OLA_OK;
+    }
+    if (kind == OLA_REC_STORAGE_ACCESS_COUNT) {
+        r.n_storage_access = nrows;
+        return OLA_OK;
+    }
+    if (kind < 0 || kind >= ola::tracejson::REC_KINDS) return OLA_ERR_INVALID_ARG;
+    r.own[kind].clear();
+    r.ptr[kind] = nrows ? rows : nullptr;  // borrowed: the caller keeps the array alive while the trace is in use
+    r.count[kind] = nrows;
+    return OLA_OK;
+}
 int ola_trace_records(const ola_trace* t, int kind, const uint64_t** rows, size_t* nrows, uint32_t* rec_u64) {
     if (!t || !rows || !nrows || !rec_u64) return OLA_ERR_INVALID_ARG;
     const ola::tracejson::Records& r = t->rec;
-    const std::vector<uint64_t>* v = nullptr;
-    uint32_t rec = 1;
-    switch (kind) {
-        case OLA_REC_STEP: v = &r.steps, rec = 66; break;
-        case OLA_REC_MEMORY: v = &r.memory, rec = 15; break;
-        case OLA_REC_RC_VAL: v = &r.rc_vals; break;
-        case OLA_REC_RC_KIND: v = &r.rc_kinds; break;
-        case OLA_REC_BITWISE_TAG: v = &r.bw_tags; break;
-        case OLA_REC_BITWISE_OP0: v = &r.bw_op0; break;
-        case OLA_REC_BITWISE_OP1: v = &r.bw_op1; break;
-        case OLA_REC_BITWISE_RES: v = &r.bw_res; break;
-        case OLA_REC_CMP: v = &r.cmp, rec = 6; break;
-        case OLA_REC_POSEIDON_INPUT: v = &r.psdn_inputs, rec = 12; break;
-        case OLA_REC_POSEIDON_FILTER: v = &r.psdn_filters, rec = 4; break;
-        case OLA_REC_POSEIDON_CHUNK: v = &r.pchunk, rec = 32; break;
-        case OLA_REC_STORAGE_HASH: v = &r.storage, rec = 38; break;
-        case OLA_REC_TAPE: v = &r.tape, rec = 5; break;
-        case OLA_REC_SCCALL: v = &r.sccall, rec = 24; break;
-        case OLA_REC_PROG_ROW: v = &r.prog_rows, rec = 6; break;
-        case OLA_REC_ROOTS:
-            *rows = r.roots, *nrows = 1, *rec_u64 = 8;
-            return OLA_OK;
-        case OLA_REC_STORAGE_ACCESS_COUNT:
-            *rows = nullptr, *nrows = r.n_storage_access, *rec_u64 = 0;
-            return OLA_OK;
-        default: return OLA_ERR_INVALID_ARG;
+    if (kind == OLA_REC_ROOTS) {
+        *rows = r.roots, *nrows = 1, *rec_u64 = 8;
+        return OLA_OK;
     }
-    *rows = v->empty() ? nullptr : v->data();
-    *nrows = v->size() / rec;
-    *rec_u64 = rec;
+    if (kind == OLA_REC_STORAGE_ACCESS_COUNT) {
+        *rows = nullptr, *nrows = r.n_storage_access, *rec_u64 = 0;
+        return OLA_OK;
+    }
+    if (kind < 0 || kind >= ola::tracejson::REC_KINDS) return OLA_ERR_INVALID_ARG;
+    *rows = r.rows(kind), *nrows = r.n(kind), *rec_u64 = ola::tracejson::kRecWidth[kind];
     return OLA_OK;
 }
 int ola_trace_table_log_rows(const ola_trace* t, int table_id) {

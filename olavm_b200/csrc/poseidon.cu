@@ -169,37 +169,91 @@ void merkle_levels(ola_ctx* ctx, uint64_t* d_nodes, size_t nleaves, size_t stop)
 }
 
 // ---- host permutation for the Fiat-Shamir transcript (iop/challenger.rs:137-152 duplexing) ----
-static uint64_t h_sbox(uint64_t x) {
-    uint64_t x2 = gl::sqr(x), x4 = gl::sqr(x2), x3 = gl::mul(x, x2);
-    return gl::mul(x3, x4);
+// The transcript is sequential and some callers push millions of elements through it (the Bitwise table's compress challenge
+// observes twelve whole columns, generation/builtin.rs:118-131), so the host path uses the same formulation as the kernels:
+// MDS rows as 32-bit-half dot products with the small circulant constants, and the fast partial rounds (poseidon.rs:392-421).
+static inline uint64_t h_red(unsigned __int128 x) {
+    const uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64), EPSV = 0xFFFFFFFFULL, PV = 0xFFFFFFFF00000001ULL;
+    const uint64_t hi_hi = hi >> 32, hi_lo = hi & EPSV;
+    uint64_t t0;
+    const uint64_t borrow = __builtin_sub_overflow(lo, hi_hi, &t0);
+    t0 -= EPSV & (0 - borrow);
+    const uint64_t t1 = (hi_lo << 32) - hi_lo;
+    uint64_t t2;
+    const uint64_t carry = __builtin_add_overflow(t0, t1, &t2);
+    t2 += EPSV & (0 - carry);
+    t2 -= PV & (0 - (uint64_t)(t2 >= PV));
+    return t2;
 }
-static void h_mds(uint64_t* s) {
-    uint64_t o[12];
-    for (int r = 0; r < 12; ++r) {
-        unsigned __int128 acc = 0;
-        for (int i = 0; i < 12; ++i) acc += (unsigned __int128)s[(i + r) % 12] * OLA_MDS_MATRIX_CIRC[i];
-        acc += (unsigned __int128)s[r] * OLA_MDS_MATRIX_DIAG[r];
-        o[r] = gl::reduce128((uint64_t)acc, (uint64_t)(acc >> 64));
+static inline uint64_t h_mulmod(uint64_t a, uint64_t b) { return h_red((unsigned __int128)a * b); }
+static inline uint64_t h_sbox(uint64_t x) {
+    const uint64_t x2 = h_mulmod(x, x), x4 = h_mulmod(x2, x2), x3 = h_mulmod(x, x2);
+    return h_mulmod(x3, x4);
+}
+__attribute__((target_clones("avx2", "default"))) static void h_mds(uint64_t* s) {
+    uint32_t C[12], D[12];  // the circulant's first row and the diagonal (all below 2^6)
+    for (int i = 0; i < 12; ++i) C[i] = (uint32_t)OLA_MDS_MATRIX_CIRC[i], D[i] = (uint32_t)OLA_MDS_MATRIX_DIAG[i];
+    uint32_t lo[24], hi[24];
+    for (int i = 0; i < 12; ++i) lo[i] = lo[i + 12] = (uint32_t)s[i], hi[i] = hi[i + 12] = (uint32_t)(s[i] >> 32);
+    uint64_t al[12], ah[12];
+    for (int r = 0; r < 12; ++r) al[r] = ah[r] = 0;
+    for (int i = 0; i < 12; ++i)          // output rows are the vector lanes: al[r] += lo[r + i] * C[i]
+        for (int r = 0; r < 12; ++r) al[r] += (uint64_t)lo[r + i] * C[i], ah[r] += (uint64_t)hi[r + i] * C[i];
+    for (int r = 0; r < 12; ++r) al[r] += (uint64_t)lo[r] * D[r], ah[r] += (uint64_t)hi[r] * D[r];
+    for (int r = 0; r < 12; ++r) s[r] = h_red(((unsigned __int128)ah[r] << 32) + al[r]);
+}
+// sum of up to 2^32 64 x 64-bit products without carry tests: the low and the high words are summed separately (each sum fits 128
+// bits), and 2^64 = 2^32 - 1 (mod p) folds the high sum back: total = lo_sum + hi_sum * (2^32 - 1) < 2^101
+struct HostAcc {
+    unsigned __int128 lo = 0, hi = 0;
+    inline void mac(uint64_t a, uint64_t b) {
+        const unsigned __int128 p = (unsigned __int128)a * b;
+        lo += (uint64_t)p;
+        hi += (uint64_t)(p >> 64);
     }
-    for (int r = 0; r < 12; ++r) s[r] = o[r];
+    inline uint64_t reduce() const { return h_red(lo + hi * 0xFFFFFFFFULL); }
+};
+static inline uint64_t h_add(uint64_t a, uint64_t b) {  // canonical a, b -> canonical a + b, branch-free
+    uint64_t s;
+    const uint64_t carry = __builtin_add_overflow(a, b, &s);
+    s += 0xFFFFFFFFULL & (0 - carry);                                  // + 2^64 mod p
+    s -= 0xFFFFFFFF00000001ULL & (0 - (uint64_t)(s >= 0xFFFFFFFF00000001ULL));
+    return s;
 }
 void permute_host(uint64_t s[12]) {
     for (int i = 0; i < 12; ++i) s[i] = gl::canon(s[i]);
     int rc = 0;
     auto full = [&]() {
         for (int r = 0; r < 4; ++r, ++rc) {
-            for (int i = 0; i < 12; ++i) s[i] = h_sbox(gl::add(s[i], gl::canon(OLA_ALL_ROUND_CONSTANTS[rc * 12 + i])));
+            for (int i = 0; i < 12; ++i) s[i] = h_sbox(h_add(s[i], gl::canon(OLA_ALL_ROUND_CONSTANTS[rc * 12 + i])));
             h_mds(s);
         }
     };
     full();
-    for (int r = 0; r < 22; ++r, ++rc) {  // host path: naive partial rounds (poseidon.rs:607-617), same function
-        for (int i = 0; i < 12; ++i) s[i] = gl::add(s[i], gl::canon(OLA_ALL_ROUND_CONSTANTS[rc * 12 + i]));
-        s[0] = h_sbox(s[0]);
-        h_mds(s);
+    {  // partial_first_constant_layer + mds_partial_layer_init (poseidon.rs:303-313, :332-358)
+        for (int i = 0; i < 12; ++i) s[i] = h_add(s[i], gl::canon(OLA_FAST_PARTIAL_FIRST_ROUND_CONSTANT[i]));
+        uint64_t q[11];
+        for (int c = 0; c < 11; ++c) {
+            HostAcc acc;
+            for (int r = 1; r < 12; ++r) acc.mac(s[r], OLA_FAST_PARTIAL_ROUND_INITIAL_MATRIX[r - 1][c]);
+            q[c] = acc.reduce();
+        }
+        for (int c = 0; c < 11; ++c) s[c + 1] = q[c];
     }
+    for (int r = 0; r < 22; ++r) {  // poseidon.rs:582-588 with mds_partial_layer_fast (:392-421)
+        s[0] = h_add(h_sbox(s[0]), gl::canon(OLA_FAST_PARTIAL_ROUND_CONSTANTS[r]));
+        HostAcc d;
+        d.mac(s[0], OLA_MDS_MATRIX_CIRC[0] + OLA_MDS_MATRIX_DIAG[0]);
+        for (int i = 1; i < 12; ++i) d.mac(s[i], OLA_FAST_PARTIAL_ROUND_W_HATS[r][i - 1]);
+        const uint64_t s0 = s[0];
+        for (int i = 1; i < 12; ++i) s[i] = h_add(s[i], h_mulmod(s0, OLA_FAST_PARTIAL_ROUND_VS[r][i - 1]));
+        s[0] = d.reduce();
+    }
+    rc += 22;
     full();
 }
+
+
 
 }  // namespace poseidon
 }  // namespace ola

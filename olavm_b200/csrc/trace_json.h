@@ -26,21 +26,26 @@ struct Field {
     int nsub;
 };
 
+// record kinds (= OLA_REC_* of include/ola_gpu.h) and their widths in u64
+enum { REC_STEP = 0, REC_MEMORY, REC_RC_VAL, REC_RC_KIND, REC_BW_TAG, REC_BW_OP0, REC_BW_OP1, REC_BW_RES, REC_CMP, REC_PSDN_INPUT, REC_PSDN_FILTER,
+       REC_PCHUNK, REC_STORAGE, REC_TAPE, REC_SCCALL, REC_PROG_ROW, REC_KINDS };
+static constexpr uint32_t kRecWidth[REC_KINDS] = {66, 15, 1, 1, 1, 1, 1, 1, 6, 12, 4, 32, 38, 5, 24, 6};
+
 struct Records {
-    std::vector<uint64_t> steps;        // [k][66]  Step                       (ola_generate_cpu_trace / _program_trace)
-    std::vector<uint64_t> memory;       // [k][15]  MemoryTraceCell
-    std::vector<uint64_t> rc_vals, rc_kinds;                    // RangeCheckRow: val, looking table (0 cpu 1 sort 2 region 3 cmp 4 none)
-    std::vector<uint64_t> bw_tags, bw_op0, bw_op1, bw_res;      // BitwiseCombinedRow
-    std::vector<uint64_t> cmp;          // [k][6]   CmpRow
-    std::vector<uint64_t> psdn_inputs;  // [k][12]  PoseidonRow.input
-    std::vector<uint64_t> psdn_filters; // [k][4]   normal, treekey, storage (leaf), storage_branch
-    std::vector<uint64_t> pchunk;       // [k][32]  PoseidonChunkRow
-    std::vector<uint64_t> storage;      // [k][38]  StorageHashRow: builtin_storage_hash then builtin_program_hash
-    size_t n_storage_access = 0;
-    std::vector<uint64_t> tape;         // [k][5]   TapeRow
-    std::vector<uint64_t> sccall;       // [k][24]  SCCallRow
-    std::vector<uint64_t> prog_rows;    // [m][6]   (code address 0..3, pc, word) for addr_program_hash in file order
+    // own[k]: the records the parser produced; view k is what the generators read -- own[k], or memory borrowed from the caller
+    // (ola_trace_set_records: a Rust host hands over its flattened Vec<Row> without a copy)
+    std::vector<uint64_t> own[REC_KINDS];
+    const uint64_t* ptr[REC_KINDS] = {};
+    size_t count[REC_KINDS] = {};       // records (not u64) per kind
+    size_t n_storage_access = 0;        // REC_STORAGE: builtin_storage_hash records first, builtin_program_hash after them
     uint64_t roots[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // start_end_roots
+
+    void bind_owned() {
+        for (int k = 0; k < REC_KINDS; ++k) ptr[k] = own[k].empty() ? nullptr : own[k].data(), count[k] = own[k].size() / kRecWidth[k];
+    }
+    const uint64_t* rows(int k) const { return ptr[k]; }
+    size_t n(int k) const { return count[k]; }
+    size_t u64s(int k) const { return count[k] * kRecWidth[k]; }
 };
 
 class Parser {
@@ -270,49 +275,49 @@ inline int hex_nibble(char c) { return c >= '0' && c <= '9' ? c - '0' : c >= 'a'
 
 inline void Parser::top_level(const std::string& key, Records& r) {
     if (key == "exec") {
-        parse_records(kStep, OLA_NF(kStep), 66, r.steps);
+        parse_records(kStep, OLA_NF(kStep), 66, r.own[REC_STEP]);
     } else if (key == "memory") {
-        parse_records(kMemory, OLA_NF(kMemory), 15, r.memory);
+        parse_records(kMemory, OLA_NF(kMemory), 15, r.own[REC_MEMORY]);
     } else if (key == "builtin_rangecheck") {
         std::vector<uint64_t> rows;
         const size_t k = parse_records(kRangeCheck, OLA_NF(kRangeCheck), 5, rows);
-        r.rc_vals.resize(k), r.rc_kinds.resize(k);
+        r.own[REC_RC_VAL].resize(k), r.own[REC_RC_KIND].resize(k);
         for (size_t i = 0; i < k; ++i) {
             const uint64_t* c = rows.data() + i * 5;
-            r.rc_vals[i] = c[0];
-            r.rc_kinds[i] = c[1] ? 0 : c[2] ? 1 : c[3] ? 2 : c[4] ? 3 : 4;
+            r.own[REC_RC_VAL][i] = c[0];
+            r.own[REC_RC_KIND][i] = c[1] ? 0 : c[2] ? 1 : c[3] ? 2 : c[4] ? 3 : 4;
         }
     } else if (key == "builtin_bitwise_combined") {
         std::vector<uint64_t> rows;
         const size_t k = parse_records(kBitwise, OLA_NF(kBitwise), 4, rows);
-        r.bw_tags.resize(k), r.bw_op0.resize(k), r.bw_op1.resize(k), r.bw_res.resize(k);
-        for (size_t i = 0; i < k; ++i) r.bw_tags[i] = rows[i * 4], r.bw_op0[i] = rows[i * 4 + 1], r.bw_op1[i] = rows[i * 4 + 2], r.bw_res[i] = rows[i * 4 + 3];
+        r.own[REC_BW_TAG].resize(k), r.own[REC_BW_OP0].resize(k), r.own[REC_BW_OP1].resize(k), r.own[REC_BW_RES].resize(k);
+        for (size_t i = 0; i < k; ++i) r.own[REC_BW_TAG][i] = rows[i * 4], r.own[REC_BW_OP0][i] = rows[i * 4 + 1], r.own[REC_BW_OP1][i] = rows[i * 4 + 2], r.own[REC_BW_RES][i] = rows[i * 4 + 3];
     } else if (key == "builtin_cmp") {
-        parse_records(kCmp, OLA_NF(kCmp), 6, r.cmp);
+        parse_records(kCmp, OLA_NF(kCmp), 6, r.own[REC_CMP]);
     } else if (key == "builtin_poseidon") {
         std::vector<uint64_t> rows;
         const size_t k = parse_records(kPoseidon, OLA_NF(kPoseidon), 16, rows);
-        r.psdn_inputs.resize(k * 12), r.psdn_filters.resize(k * 4);
+        r.own[REC_PSDN_INPUT].resize(k * 12), r.own[REC_PSDN_FILTER].resize(k * 4);
         for (size_t i = 0; i < k; ++i) {
-            memcpy(r.psdn_inputs.data() + i * 12, rows.data() + i * 16, 12 * sizeof(uint64_t));
-            memcpy(r.psdn_filters.data() + i * 4, rows.data() + i * 16 + 12, 4 * sizeof(uint64_t));
+            memcpy(r.own[REC_PSDN_INPUT].data() + i * 12, rows.data() + i * 16, 12 * sizeof(uint64_t));
+            memcpy(r.own[REC_PSDN_FILTER].data() + i * 4, rows.data() + i * 16 + 12, 4 * sizeof(uint64_t));
         }
     } else if (key == "builtin_poseidon_chunk") {
-        parse_records(kPoseidonChunk, OLA_NF(kPoseidonChunk), 32, r.pchunk);
+        parse_records(kPoseidonChunk, OLA_NF(kPoseidonChunk), 32, r.own[REC_PCHUNK]);
     } else if (key == "builtin_storage_hash" || key == "builtin_program_hash") {
         // generate_storage_access_trace chains accesses then program-hash reads (storage.rs:23): keep that order whatever the file's
         std::vector<uint64_t> rows;
         const size_t k = parse_records(kStorageHash, OLA_NF(kStorageHash), 38, rows);
         if (key == "builtin_storage_hash") {
-            r.storage.insert(r.storage.begin(), rows.begin(), rows.end());
+            r.own[REC_STORAGE].insert(r.own[REC_STORAGE].begin(), rows.begin(), rows.end());
             r.n_storage_access = k;
         } else {
-            r.storage.insert(r.storage.end(), rows.begin(), rows.end());
+            r.own[REC_STORAGE].insert(r.own[REC_STORAGE].end(), rows.begin(), rows.end());
         }
     } else if (key == "tape") {
-        parse_records(kTape, OLA_NF(kTape), 5, r.tape);
+        parse_records(kTape, OLA_NF(kTape), 5, r.own[REC_TAPE]);
     } else if (key == "sc_call") {
-        parse_records(kSCCall, OLA_NF(kSCCall), 24, r.sccall);
+        parse_records(kSCCall, OLA_NF(kSCCall), 24, r.own[REC_SCCALL]);
     } else if (key == "start_end_roots") {
         expect('[');
         parse_scalars(r.roots, 4);
@@ -341,7 +346,7 @@ inline void Parser::top_level(const std::string& key, Records& r) {
             } else {
                 for (;;) {
                     const uint64_t w = parse_scalar();
-                    r.prog_rows.insert(r.prog_rows.end(), {addr[0], addr[1], addr[2], addr[3], pc, w});
+                    r.own[REC_PROG_ROW].insert(r.own[REC_PROG_ROW].end(), {addr[0], addr[1], addr[2], addr[3], pc, w});
                     ++pc;
                     if (!more(']')) break;
                 }
@@ -353,7 +358,10 @@ inline void Parser::top_level(const std::string& key, Records& r) {
     }
 }
 
-inline void parse(const char* json, size_t len, Records& out) { Parser(json, len).parse_trace(out); }
+inline void parse(const char* json, size_t len, Records& out) {
+    Parser(json, len).parse_trace(out);
+    out.bind_owned();
+}
 
 }  // namespace tracejson
 }  // namespace ola

@@ -24,6 +24,34 @@ class Trace:
             raise ValueError(err.value.decode() or "ola_trace_from_json: error %d" % rc)
         self.handle = h
 
+    @classmethod
+    def from_records(cls, **arrays):
+        """The trace object over records the caller already holds (what a Rust host does with its own Trace): keyword = a kind of
+        REC (`step`, `memory`, `rc_val`, ... `prog_row`, `roots`), value = the record array; `storage_access_count` = int.  The
+        arrays are borrowed, not copied: they are kept alive by this object."""
+        self = cls.__new__(cls)
+        self._lib = _lib.load()
+        h = ctypes.c_void_p()
+        rc = self._lib.ola_trace_new(ctypes.byref(h))
+        if rc != 0:
+            raise _lib.OlaError(rc, "ola_trace_new")
+        self.handle = h
+        self._keep = []
+        for kind, a in arrays.items():
+            if kind == "storage_access_count":
+                rc = self._lib.ola_trace_set_records(h, REC[kind], None, int(a))
+            else:
+                a = np.ascontiguousarray(a, dtype=np.uint64)
+                self._keep.append(a)
+                width = 8 if kind == "roots" else None
+                n = 1 if kind == "roots" else (a.shape[0] if a.ndim else 0)
+                if width and a.size != 8:
+                    raise ValueError("roots = start_root[4], end_root[4]")
+                rc = self._lib.ola_trace_set_records(h, REC[kind], a.ctypes.data_as(ctypes.c_void_p) if a.size else None, n)
+            if rc != 0:
+                raise _lib.OlaError(rc, "ola_trace_set_records(%s)" % kind)
+        return self
+
     def records(self, kind):
         rows, n, rec = ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_uint32()
         rc = self._lib.ola_trace_records(self.handle, REC[kind], ctypes.byref(rows), ctypes.byref(n), ctypes.byref(rec))

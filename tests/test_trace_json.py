@@ -119,3 +119,54 @@ def test_generate_traces_equals_the_oracle_generators_and_the_proof_verifies(ctx
     assert ok, why
     assert orc.stark_verify(list(range(12)), proof)[0]
     assert proof == olavm_b200.prove_with_traces(ctx, list(range(12)), host, compress_challenges=cc)
+
+
+def _oracle_tables(orc, rec):
+    """generate_traces with the oracle's generators -> ({table id: table}, {table id: compress challenge})."""
+    na = rec["n_storage_access"]
+    tabs = {0: orc.generate_cpu_trace(rec["steps"]), 1: orc.generate_memory_trace(rec["memory"]), 3: orc.generate_cmp_trace(rec["cmp"]),
+            4: orc.generate_rc_trace(rec["rc_vals"], rec["rc_kinds"]), 6: orc.generate_poseidon_chunk_trace(rec["pchunk"]),
+            7: orc.generate_storage_access_trace(rec["storage"][:na], rec["storage"][na:]), 8: orc.generate_tape_trace(rec["tape"]),
+            9: orc.generate_sccall_trace(rec["sccall"]), 11: orc.generate_prog_chunk_trace(rec["prog_rows"])}
+    tabs[2], beta_bw = orc.generate_bitwise_trace(rec["bw_tags"], rec["bw_op0"], rec["bw_op1"], rec["bw_res"])
+    tabs[10], beta_p = orc.generate_prog_trace(rec["steps"], rec["prog_rows"], rec["roots"])
+    return tabs, {2: beta_bw, 10: beta_p}
+
+
+def test_fib_system_records_regenerate_its_tables(orc):
+    """workload.trace_json.records_of_fib_system reads the executor records back out of the benchmark workload's tables; the
+    oracle's generators rebuild from them the tables the records came from (every column that is not a free choice: the permuted
+    lookup columns may fill unused table values in another order, the two beta-compressed tables use the transcript's beta), and
+    what they build satisfies every AIR."""
+    from workload import fibloop
+    from workload import trace_json as wj
+
+    ids, traces, cc, info = fibloop.fib_loop_system(9, orc)
+    rec = wj.records_of_fib_system(traces, info)
+    tabs, betas = _oracle_tables(orc, rec)
+    free = {2: set(range(17, 59)), 4: {7, 8, 10, 11}, 10: {6, 7, 14, 15}, 3: set()}
+    for i in (0, 1, 2, 4, 5, 7, 11, 10):
+        if i == 5:
+            continue
+        got, want = tabs[i], traces[i]
+        n = min(got.shape[1], want.shape[1])   # the workload pads some tables one power of two further than the reference
+        rows = {0: info["cpu_steps"], 1: info["memory_accesses"], 2: info["bitwise_rows"]}.get(i, n)
+        bad = [c for c in range(got.shape[0]) if c not in free.get(i, set()) and not (got[c, :min(rows, n)] == want[c, :min(rows, n)]).all()]
+        assert not bad, (i, bad)
+    for i, t in tabs.items():
+        assert orc.air_first_failure(i, t, compress_challenge=betas.get(i, 0)) is None, i
+
+
+def test_trace_from_records_is_the_trace_from_json(run):
+    from olavm_b200 import trace_json
+    from workload import trace_json as wj
+
+    rec, text = run
+    a = trace_json.Trace(text)
+    b = trace_json.Trace.from_records(**{wj.REC_KIND_OF[k]: v for k, v in rec.items()})
+    for kind in list(_KEYS.values()) + ["roots"]:
+        assert (np.asarray(a.records(kind)) == np.asarray(b.records(kind))).all(), kind
+    assert a.records("storage_access_count") == b.records("storage_access_count")
+    assert [a.table_log_rows(i) for i in range(12)] == [b.table_log_rows(i) for i in range(12)]
+    empty = trace_json.Trace.from_records()
+    assert [empty.table_log_rows(i) for i in range(12)] == [0, 1, 18, 1, 16, 1, 1, 1, 1, 1, 1, 1]

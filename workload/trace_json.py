@@ -123,3 +123,41 @@ def records_to_json(rec, orc=None):
                builtin_storage_hash=[storage_row(c) for c in rec["storage"][:na]], builtin_program_hash=[storage_row(c) for c in rec["storage"][na:]],
                tape=tape, sc_call=sccall, ret=[1, 2, 3])
     return json.dumps(doc, separators=(",", ":"))
+
+
+def records_of_fib_system(traces, info):
+    """The executor records behind workload.fibloop.fib_loop_system's twelve tables, read back out of the tables (every record
+    field is a table column: generate_cpu_trace copies Step field i to column i + 1, generate_memory_trace copies the cell into
+    columns 1..5 and 17..26, and so on), so that the `ola prove` flow can be driven at BASELINE configs[2]'s scale: records in,
+    tables generated on the GPU.  `info` = the dict fib_loop_system returns (filled row counts)."""
+    cpu_t, mem_t, bw_t, cmp_t, rc_t, ps_t, pch_t, st_t, tape_t, sc_t, pt, pc_t = traces
+    k = info["cpu_steps"]
+    steps = np.empty((k, 66), dtype=np.uint64)
+    steps[:, 0:65] = cpu_t[1:66, :k].T
+    steps[:, 65] = cpu_t[88, :k]
+    k = info["memory_accesses"]
+    memory = np.empty((k, 15), dtype=np.uint64)
+    memory[:, 0:5], memory[:, 5:15] = mem_t[1:6, :k].T, mem_t[17:27, :k].T
+    k = info["bitwise_rows"]
+    kc = info["cmp_rows"]
+    live = rc_t[0:4].any(axis=0)
+    kr = int(live.sum())
+    assert live[:kr].all()
+    kinds = np.argmax(rc_t[0:4, :kr] != 0, axis=0).astype(np.uint64)
+    live = ps_t[0:4].any(axis=0)
+    kp = int(live.sum())
+    assert live[:kp].all()
+    storage, n_access = tg.storage_records_of_table(st_t)
+    lines = int((pc_t[39] == 0).sum())
+    prog_rows = [tuple(int(pc_t[c, i]) for c in range(4)) + (int(pc_t[4, i]) + j, int(pc_t[5 + j, i])) for i in range(lines) for j in range(8) if pc_t[31 + j, i]]
+    c = np.ascontiguousarray
+    return dict(steps=steps, memory=memory, rc_vals=c(rc_t[4, :kr]), rc_kinds=kinds, bw_tags=c(bw_t[1, :k]), bw_op0=c(bw_t[2, :k]), bw_op1=c(bw_t[3, :k]),
+                bw_res=c(bw_t[4, :k]), cmp=c(cmp_t[:, :kc].T), psdn_inputs=c(ps_t[4:16, :kp].T), psdn_filters=c(ps_t[0:4, :kp].T),
+                pchunk=np.zeros((0, 32), dtype=np.uint64), storage=storage, n_storage_access=n_access, tape=np.zeros((0, 5), dtype=np.uint64),
+                sccall=np.zeros((0, 24), dtype=np.uint64), prog_rows=np.array(prog_rows, dtype=np.uint64).reshape(-1, 6),
+                roots=np.array(list(st_t[5:9, 0]) * 2, dtype=np.uint64))
+
+
+REC_KIND_OF = dict(steps="step", memory="memory", rc_vals="rc_val", rc_kinds="rc_kind", bw_tags="bitwise_tag", bw_op0="bitwise_op0", bw_op1="bitwise_op1",
+                   bw_res="bitwise_res", cmp="cmp", psdn_inputs="poseidon_input", psdn_filters="poseidon_filter", pchunk="poseidon_chunk",
+                   storage="storage_hash", tape="tape", sccall="sccall", prog_rows="prog_row", roots="roots", n_storage_access="storage_access_count")

@@ -931,7 +931,17 @@ struct Upload {  // a record array in device memory for the duration of one gene
 };
 // generate_traces (circuits/src/generation/mod.rs:79-213): twelve column-major tables in device memory, tables[t] of
 // ola_table_columns(t) << log_ns[t] u64 (owned by the caller: ola_dev_free), and the two compress challenges
-void generate_all(ola_ctx* ctx, const ola::tracejson::Records& r, uint64_t** tables, uint32_t* log_ns, uint64_t* cc) {
+// The Bitwise table's compress challenge computed on a second host thread (host-only work: lookup.cu bitwise_beta)
+struct BitwiseLate {
+    std::vector<uint64_t> limbs;
+    std::thread worker;
+    uint64_t beta = 0;
+    bool failed = false;
+    ~BitwiseLate() {
+        if (worker.joinable()) worker.join();
+    }
+};
+void generate_all(ola_ctx* ctx, const ola::tracejson::Records& r, uint64_t** tables, uint32_t* log_ns, uint64_t* cc, BitwiseLate* defer = nullptr) {
     namespace L = ola::lookup;
     using namespace ola::tracejson;
     OLA_CHECK(r.n(REC_RC_KIND) == r.n(REC_RC_VAL) && r.n(REC_BW_OP0) == r.n(REC_BW_TAG) && r.n(REC_BW_OP1) == r.n(REC_BW_TAG) &&
@@ -944,6 +954,21 @@ void generate_all(ola_ctx* ctx, const ola::tracejson::Records& r, uint64_t** tab
     }
     try {
         for (int t = 0; t < 12; ++t) ola::dev_alloc(&tables[t], (size_t)ola::stark::table_info(t).columns << log_ns[t]);
+        {  // first: with `defer` its sequential host transcript then runs beside everything below (and beside the commitments)
+            Upload a(ctx, r, REC_BW_TAG), b(ctx, r, REC_BW_OP0), c(ctx, r, REC_BW_OP1), d(ctx, r, REC_BW_RES);
+            if (defer) {
+                defer->limbs = L::bitwise_trace_begin(ctx, a.d.p, b.d.p, c.d.p, d.d.p, r.n(REC_BW_TAG), log_ns[2], tables[2]);
+                defer->worker = std::thread([defer] {
+                    try {
+                        defer->beta = L::bitwise_beta(defer->limbs);
+                    } catch (...) {
+                        defer->failed = true;
+                    }
+                });
+            } else {
+                cc[2] = L::bitwise_trace(ctx, a.d.p, b.d.p, c.d.p, d.d.p, r.n(REC_BW_TAG), log_ns[2], tables[2]);
+            }
+        }
         {
             Upload s(ctx, r, REC_STEP), p(ctx, r, REC_PROG_ROW);  // the Step records serve the CPU and the Program table
             L::cpu_trace(ctx, s.d.p, r.n(REC_STEP), log_ns[0], tables[0]);
@@ -952,10 +977,6 @@ void generate_all(ola_ctx* ctx, const ola::tracejson::Records& r, uint64_t** tab
             OLA_CUDA(cudaStreamSynchronize(ctx->stream));
         }
         { Upload u(ctx, r, REC_MEMORY); L::memory_trace(ctx, u.d.p, r.n(REC_MEMORY), log_ns[1], tables[1]); }
-        {
-            Upload a(ctx, r, REC_BW_TAG), b(ctx, r, REC_BW_OP0), c(ctx, r, REC_BW_OP1), d(ctx, r, REC_BW_RES);
-            cc[2] = L::bitwise_trace(ctx, a.d.p, b.d.p, c.d.p, d.d.p, r.n(REC_BW_TAG), log_ns[2], tables[2]);
-        }
         { Upload u(ctx, r, REC_CMP); L::cmp_trace(ctx, u.d.p, r.n(REC_CMP), log_ns[3], tables[3]); }
         { Upload v(ctx, r, REC_RC_VAL), k(ctx, r, REC_RC_KIND); L::rangecheck_trace(ctx, v.d.p, k.d.p, r.n(REC_RC_VAL), log_ns[4], tables[4]); }
         {
@@ -1056,7 +1077,14 @@ int ola_prove_trace(ola_ctx* ctx, const ola_trace* t, uint8_t* proof_out, size_t
         uint64_t* tables[12];
         uint32_t log_ns[12];
         uint64_t cc[12];
-        generate_all(ctx, t->rec, tables, log_ns, cc);
+        BitwiseLate bw;  // joined by its destructor on every path
+        generate_all(ctx, t->rec, tables, log_ns, cc, &bw);
+        const ola::stark::LateTable late{2, [&]() -> uint64_t {
+                                             bw.worker.join();
+                                             OLA_CHECK(!bw.failed, OLA_ERR_INTERNAL, "the Bitwise compress challenge could not be computed");
+                                             ola::lookup::bitwise_trace_finish(ctx, log_ns[2], bw.beta, tables[2]);
+                                             return bw.beta;
+                                         }};
         std::vector<uint8_t> bytes;
         try {
             ola::stark::Config cfg;  // StarkConfig::standard_fast_config(), the degree check on (client/src/main.rs:192)
@@ -1064,7 +1092,7 @@ int ola_prove_trace(ola_ctx* ctx, const ola_trace* t, uint8_t* proof_out, size_t
             std::vector<const uint64_t*> tr(tables, tables + 12);
             std::vector<uint32_t> lg(log_ns, log_ns + 12);
             std::vector<uint64_t> c(cc, cc + 12);
-            bytes = ola::stark::prove_all(ctx, ids, tr, true, lg, c, cfg);
+            bytes = ola::stark::prove_all(ctx, ids, tr, true, lg, c, cfg, nullptr, &late);
         } catch (...) {
             cudaStreamSynchronize(ctx->stream);
             for (int i = 0; i < 12; ++i) ola::dev_free(tables[i]);

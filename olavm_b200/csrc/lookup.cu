@@ -420,9 +420,14 @@ __global__ void bitwise_compress_kernel(size_t n, uint64_t beta, uint64_t* __res
         out[(size_t)(29 + k) * n + i] = gl::add(gl::add(gl::add(tag, gl::mul(at(5 + k), beta)), gl::mul(at(9 + k), b2)), gl::mul(at(13 + k), b3));
     out[(size_t)54 * n + i] = gl::add(gl::add(gl::add(at(50), gl::mul(at(51), beta)), gl::mul(at(52), b2)), gl::mul(at(53), b3));
 }
-// returns beta.  d_out = [59][n]
-uint64_t bitwise_trace(ola_ctx* ctx, const uint64_t* d_tags, const uint64_t* d_op0, const uint64_t* d_op1, const uint64_t* d_res, size_t nrows, uint32_t log_n,
-                       uint64_t* d_out) {
+// The generator in three steps, so that a caller can run the middle one -- host-only, sequential, 3 * n / 2 permutations -- on
+// another thread while the GPU does other work (ola_prove_trace commits the other eleven tables meanwhile):
+//   bitwise_trace_begin   row fill and the twelve lookups that do not involve beta; returns the twelve limb columns (host)
+//   bitwise_beta          the compress challenge: a fresh Challenger observes the limb columns (builtin.rs:118-131); no CUDA
+//   bitwise_trace_finish  the beta-compressed columns and their four lookups
+// d_out = [59][n]
+std::vector<uint64_t> bitwise_trace_begin(ola_ctx* ctx, const uint64_t* d_tags, const uint64_t* d_op0, const uint64_t* d_op1, const uint64_t* d_res,
+                                          size_t nrows, uint32_t log_n, uint64_t* d_out) {
     const size_t n = (size_t)1 << log_n;
     OLA_CHECK(log_n >= 18 && log_n <= 24 && nrows <= n, OLA_ERR_INVALID_ARG, "Bitwise table: at least 2^18 rows (3 * 2^16 fixed rows) and room for every operation");
     const unsigned gb = (unsigned)((n + 255) / 256);
@@ -431,26 +436,37 @@ uint64_t bitwise_trace(ola_ctx* ctx, const uint64_t* d_tags, const uint64_t* d_o
         bitwise_fill_kernel<<<gb, 256, 0, ctx->stream>>>(d_tags, d_op0, d_op1, d_res, nrows, n, d_out);
         check_launch("bitwise_fill_kernel");
     }
-    // the compress challenge: a fresh Challenger observes the twelve limb columns (builtin.rs:118-131) -- a duplex sponge is
-    // sequential, so the columns come to the host and the library's own transcript absorbs them
     std::vector<uint64_t> limbs(12 * n);
     OLA_CUDA(cudaMemcpyAsync(limbs.data(), d_out + 5 * n, 12 * n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    OLA_CUDA(cudaStreamSynchronize(ctx->stream));
-    stark::Challenger ch(OLA_HASH_POSEIDON);
-    for (size_t k = 0; k < 12 * n; ++k) ch.observe(limbs[k]);
-    const uint64_t beta = ch.get_challenge();
-    {
-        Launch lz(ctx, "gen_bitwise_compress");
-        bitwise_compress_kernel<<<gb, 256, 0, ctx->stream>>>(n, beta, d_out);
-        check_launch("bitwise_compress_kernel");
-    }
     auto col = [&](int c) { return d_out + (size_t)c * n; };
-    for (int k = 0; k < 4; ++k) {  // builtin.rs:162-195
+    for (int k = 0; k < 4; ++k) {  // builtin.rs:162-195, the byte range checks
         permuted_cols(ctx, col(5 + k), col(37), n, col(17 + k), col(38 + k));
         permuted_cols(ctx, col(9 + k), col(37), n, col(21 + k), col(38 + 4 + k));
         permuted_cols(ctx, col(13 + k), col(37), n, col(25 + k), col(38 + 8 + k));
-        permuted_cols(ctx, col(29 + k), col(54), n, col(33 + k), col(55 + k));
     }
+    OLA_CUDA(cudaStreamSynchronize(ctx->stream));
+    return limbs;
+}
+uint64_t bitwise_beta(const std::vector<uint64_t>& limbs) {
+    stark::Challenger ch(OLA_HASH_POSEIDON);
+    for (size_t k = 0; k < limbs.size(); ++k) ch.observe(limbs[k]);
+    return ch.get_challenge();
+}
+void bitwise_trace_finish(ola_ctx* ctx, uint32_t log_n, uint64_t beta, uint64_t* d_out) {
+    const size_t n = (size_t)1 << log_n;
+    {
+        Launch lz(ctx, "gen_bitwise_compress");
+        bitwise_compress_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, beta, d_out);
+        check_launch("bitwise_compress_kernel");
+    }
+    auto col = [&](int c) { return d_out + (size_t)c * n; };
+    for (int k = 0; k < 4; ++k) permuted_cols(ctx, col(29 + k), col(54), n, col(33 + k), col(55 + k));  // the compressed triples against FIX_COMPRESS
+}
+// returns beta
+uint64_t bitwise_trace(ola_ctx* ctx, const uint64_t* d_tags, const uint64_t* d_op0, const uint64_t* d_op1, const uint64_t* d_res, size_t nrows, uint32_t log_n,
+                       uint64_t* d_out) {
+    const uint64_t beta = bitwise_beta(bitwise_trace_begin(ctx, d_tags, d_op0, d_op1, d_res, nrows, log_n, d_out));
+    bitwise_trace_finish(ctx, log_n, beta, d_out);
     return beta;
 }
 

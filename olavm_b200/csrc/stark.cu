@@ -1010,8 +1010,9 @@ static StarkProof prove_single_table(ola_ctx* ctx, const TableInfo& t, const Con
 // prove_with_traces (prover.rs:79-327) + Buffer::write_all_proof (serialization.rs:377-393)
 std::vector<uint8_t> prove_all(ola_ctx* ctx, const std::vector<int>& table_ids, const std::vector<const uint64_t*>& traces, bool on_device,
                                const std::vector<uint32_t>& log_ns, const std::vector<uint64_t>& compress_challenges, const Config& cfg,
-                               TranscriptHost* transcript_host) {
+                               TranscriptHost* transcript_host, const LateTable* late) {
     System sys = make_system(table_ids);
+    OLA_CHECK(!late || (on_device && late->index < table_ids.size()), OLA_ERR_INVALID_ARG, "a late table is a device-resident table of the system");
     OLA_CHECK(compress_challenges.empty() || compress_challenges.size() == sys.tables.size(), OLA_ERR_INVALID_ARG, "one compress challenge per table");
     for (size_t i = 0; i < compress_challenges.size(); ++i)
         if (sys.tables[i].id == T_BITWISE || sys.tables[i].id == T_PROGRAM)
@@ -1037,6 +1038,10 @@ std::vector<uint8_t> prove_all(ola_ctx* ctx, const std::vector<int>& table_ids, 
         std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) {
             return ((size_t)sys.tables[x].columns << log_ns[x]) < ((size_t)sys.tables[y].columns << log_ns[y]);
         });
+    if (late) {  // committed last: whatever completes it runs beside the other commitments
+        order.erase(std::find(order.begin(), order.end(), late->index));
+        order.push_back(late->index);
+    }
     std::vector<cudaEvent_t> uploaded(T, nullptr);
     struct EventGuard {
         std::vector<cudaEvent_t>& v;
@@ -1106,6 +1111,7 @@ std::vector<uint8_t> prove_all(ola_ctx* ctx, const std::vector<int>& table_ids, 
                 OLA_CUDA(cudaStreamWaitEvent(ctx->stream, uploaded[i], 0));
                 canon_copy(ctx, d_vals[i]->p, d_vals[i]->p, cnt);  // the Z kernels read these values with canonical-input arithmetic
             } else {
+                if (late && late->index == i) sys.tables[i].compress_challenge = sys.compress_challenges[i] = gl::canon(late->finish());
                 d_vals[i].reset(new DevBuf(cnt));
                 OLA_CUDA(cudaMemcpyAsync(d_vals[i]->p, traces[i], cnt * 8, cudaMemcpyDeviceToDevice, ctx->stream));
                 canon_copy(ctx, d_vals[i]->p, d_vals[i]->p, cnt);

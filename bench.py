@@ -15,7 +15,8 @@ uniform Goldilocks columns.  A "step" is one pass of that path over the whole 20
   coset_shard_commit (every N) : one 94-column 2^20-row commitment strong-scaled over the ranks by LDE cosets, cap
                assembled by one NCCL all-gather
   prove_all_tables             : wall time of one 12-table proof with a 2^22-row CPU table from pinned host traces (coset-sharded
-               over the ranks at N > 1); at N = 1 also under Blake3GoldilocksConfig (key "blake3")
+               over the ranks at N > 1); at N = 1 also under Blake3GoldilocksConfig (key "blake3") and as the `ola prove` flow
+               (key "from_records": executor records in, the twelve tables generated on the GPU, proof out)
 
 Multi-GPU (torchrun, one rank per GPU): columns are independent, so ranks shard by column with no data-path
 collective (weak scaling: 200 columns per GPU); time = max over ranks.
@@ -267,6 +268,62 @@ def prove_all_tables(ctx, log_n, world=1, rank=0, odist=None, device=None, cpu_s
                 ctx.hasher = olavm_b200.POSEIDON
             except Exception:  # noqa: BLE001
                 pass
+        # the `ola prove` flow (client/src/main.rs:172-207) on the same run: executor RECORDS in (pinned), the twelve tables
+        # generated on the GPU (ola_generate_*: SURVEY.md 8 f1), proved where they lie.  Last and fenced, like the leg above.
+        try:
+            out["from_records"] = prove_from_records(ctx, ids, traces, info)
+        except Exception as e:  # noqa: BLE001
+            out["from_records"] = {"error": repr(e)[:300]}
+    return out
+
+
+def prove_from_records(ctx, ids, traces, info, reps=3):
+    """generate_traces + prove_with_traces through ola_prove_trace: the executor records behind the workload's tables (read back out of
+    them: every record field is a table column) cross PCIe instead of the tables, all twelve tables are generated in HBM, and the
+    proof is made from them there.  Wall time, best of `reps`; the proof is checked by ola_verify."""
+    import hashlib
+
+    import torch
+
+    import olavm_b200
+    from olavm_b200 import trace_json
+    from workload import trace_json as wj
+
+    rec = wj.records_of_fib_system(traces, info)
+    keep, pinned = [], {}
+    for k, v in rec.items():
+        if isinstance(v, np.ndarray) and v.size:
+            buf = torch.empty(v.shape, dtype=torch.int64).pin_memory()
+            w = buf.numpy().view(np.uint64)
+            w[...] = v
+            keep.append(buf)
+            pinned[wj.REC_KIND_OF[k]] = w
+        else:
+            pinned[wj.REC_KIND_OF[k]] = v
+    trace = trace_json.Trace.from_records(**pinned)
+    proof = trace_json.prove_trace(ctx, trace)  # grows the pool
+    runs = []
+    for _ in range(reps):
+        ctx.sync()
+        t0 = time.perf_counter()
+        p2 = trace_json.prove_trace(ctx, trace)
+        runs.append(time.perf_counter() - t0)
+        assert p2 == proof, "two proofs of the same records differ"
+    ctx.profile_begin()
+    tabs, logs, _ = trace_json.generate_traces(ctx, trace)
+    prof = ctx.profile_end()
+    for p in tabs:
+        ctx.free(p)
+    ok, why = olavm_b200.verify_proof(ids, proof)
+    trace.close()
+    out = {"mode": "executor records in (pinned host), twelve tables generated on the GPU, proof bytes out; degree check ON",
+           "seconds": min(runs), "seconds_runs": runs, "h2d_bytes": int(sum(v.nbytes for v in pinned.values() if isinstance(v, np.ndarray))),
+           "table_log_n": logs, "generation_kernel_ms": round(sum(v["ms"] for k, v in prof.items() if k.startswith(("gen", "lookup"))), 2),
+           "proof_bytes": len(proof), "proof_sha256_16": hashlib.sha256(proof).hexdigest()[:16], "verified_by_ola_verify": bool(ok),
+           "note": "not the bytes of prove_all_tables: this flow uses the reference's row counts and draws the Bitwise / Program compress challenges "
+                   "from its own tables' transcript, as generate_traces does"}
+    if not ok:
+        out["verify_error"] = why
     return out
 
 

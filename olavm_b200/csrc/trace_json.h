@@ -181,14 +181,21 @@ private:
     void parse_record(const Field* f, int nf, uint64_t* row) {
         expect('{');
         if (peek() == '}') { ++p_; return; }
+        int next = 0;
         for (;;) {
             const char* k0;
             size_t klen;
             raw_key(k0, klen);
             expect(':');
+            // serde writes the fields in declaration order, so the search resumes behind the previous hit: one comparison per
+            // field for a file in that order, a full scan only for unknown keys
             const Field* hit = nullptr;
-            for (int i = 0; i < nf; ++i)
-                if (strlen(f[i].key) == klen && memcmp(f[i].key, k0, klen) == 0) { hit = &f[i]; break; }
+            for (int tries = 0, i = next; tries < nf; ++tries, i = i + 1 == nf ? 0 : i + 1)
+                if (f[i].key[0] == k0[0] && strncmp(f[i].key, k0, klen) == 0 && f[i].key[klen] == 0) {
+                    hit = &f[i];
+                    next = i + 1 == nf ? 0 : i + 1;
+                    break;
+                }
             if (!hit)
                 skip_value();
             else if (hit->sub)
@@ -232,22 +239,43 @@ private:
 static const Field kRegisterSelector[] = {{"op0", 29, 0, nullptr, 0},  {"op1", 30, 0, nullptr, 0},          {"dst", 31, 0, nullptr, 0},
                                           {"aux0", 32, 0, nullptr, 0}, {"aux1", 33, 0, nullptr, 0},         {"op0_reg_sel", 35, 10, nullptr, 0},
                                           {"op1_reg_sel", 45, 10, nullptr, 0}, {"dst_reg_sel", 55, 10, nullptr, 0}};
-static const Field kStep[] = {{"env_idx", 0, 0, nullptr, 0},      {"call_sc_cnt", 1, 0, nullptr, 0},     {"addr_storage", 2, 4, nullptr, 0},
-                              {"addr_code", 6, 4, nullptr, 0},    {"tp", 10, 0, nullptr, 0},             {"clk", 11, 0, nullptr, 0},
-                              {"pc", 12, 0, nullptr, 0},          {"is_ext_line", 13, 0, nullptr, 0},    {"ext_cnt", 14, 0, nullptr, 0},
-                              {"regs", 15, 10, nullptr, 0},       {"instruction", 25, 0, nullptr, 0},    {"op1_imm", 26, 0, nullptr, 0},
-                              {"opcode", 27, 0, nullptr, 0},      {"immediate_data", 28, 0, nullptr, 0}, {"register_selector", 0, 0, kRegisterSelector, 8},
-                              {"storage_access_idx", 34, 0, nullptr, 0}, {"filter_tape_looking", 65, 0, nullptr, 0}};
-static const Field kMemory[] = {{"env_idx", 0, 0, nullptr, 0},        {"is_rw", 1, 0, nullptr, 0},          {"addr", 2, 0, nullptr, 0},
-                                {"clk", 3, 0, nullptr, 0},            {"op", 4, 0, nullptr, 0},             {"is_write", 5, 0, nullptr, 0},
-                                {"value", 6, 0, nullptr, 0},          {"diff_addr", 7, 0, nullptr, 0},      {"diff_addr_inv", 8, 0, nullptr, 0},
-                                {"diff_clk", 9, 0, nullptr, 0},       {"diff_addr_cond", 10, 0, nullptr, 0}, {"rw_addr_unchanged", 11, 0, nullptr, 0},
-                                {"region_prophet", 12, 0, nullptr, 0}, {"region_heap", 13, 0, nullptr, 0},  {"rc_value", 14, 0, nullptr, 0}};
+static const Field kStep[] = {{"env_idx", 0, 0, nullptr, 0},
+    {"call_sc_cnt", 1, 0, nullptr, 0},
+    {"clk", 11, 0, nullptr, 0},
+    {"pc", 12, 0, nullptr, 0},
+    {"tp", 10, 0, nullptr, 0},
+    {"addr_storage", 2, 4, nullptr, 0},
+    {"addr_code", 6, 4, nullptr, 0},
+    {"instruction", 25, 0, nullptr, 0},
+    {"immediate_data", 28, 0, nullptr, 0},
+    {"opcode", 27, 0, nullptr, 0},
+    {"op1_imm", 26, 0, nullptr, 0},
+    {"regs", 15, 10, nullptr, 0},
+    {"register_selector", 0, 0, kRegisterSelector, 8},
+    {"is_ext_line", 13, 0, nullptr, 0},
+    {"ext_cnt", 14, 0, nullptr, 0},
+    {"filter_tape_looking", 65, 0, nullptr, 0},
+    {"storage_access_idx", 34, 0, nullptr, 0}};
+static const Field kMemory[] = {{"env_idx", 0, 0, nullptr, 0},
+    {"addr", 2, 0, nullptr, 0},
+    {"clk", 3, 0, nullptr, 0},
+    {"is_rw", 1, 0, nullptr, 0},
+    {"op", 4, 0, nullptr, 0},
+    {"is_write", 5, 0, nullptr, 0},
+    {"diff_addr", 7, 0, nullptr, 0},
+    {"diff_addr_inv", 8, 0, nullptr, 0},
+    {"diff_clk", 9, 0, nullptr, 0},
+    {"diff_addr_cond", 10, 0, nullptr, 0},
+    {"rw_addr_unchanged", 11, 0, nullptr, 0},
+    {"region_prophet", 12, 0, nullptr, 0},
+    {"region_heap", 13, 0, nullptr, 0},
+    {"value", 6, 0, nullptr, 0},
+    {"rc_value", 14, 0, nullptr, 0}};
 static const Field kRangeCheck[] = {{"val", 0, 0, nullptr, 0},
-                                    {"filter_looked_for_cpu", 1, 0, nullptr, 0},
-                                    {"filter_looked_for_mem_sort", 2, 0, nullptr, 0},
-                                    {"filter_looked_for_mem_region", 3, 0, nullptr, 0},
-                                    {"filter_looked_for_comparison", 4, 0, nullptr, 0}};
+    {"filter_looked_for_mem_sort", 2, 0, nullptr, 0},
+    {"filter_looked_for_mem_region", 3, 0, nullptr, 0},
+    {"filter_looked_for_cpu", 1, 0, nullptr, 0},
+    {"filter_looked_for_comparison", 4, 0, nullptr, 0}};
 static const Field kBitwise[] = {{"opcode", 0, 0, nullptr, 0}, {"op0", 1, 0, nullptr, 0}, {"op1", 2, 0, nullptr, 0}, {"res", 3, 0, nullptr, 0}};
 static const Field kCmp[] = {{"op0", 0, 0, nullptr, 0},      {"op1", 1, 0, nullptr, 0},          {"gte", 2, 0, nullptr, 0},
                              {"abs_diff", 3, 0, nullptr, 0}, {"abs_diff_inv", 4, 0, nullptr, 0}, {"filter_looking_rc", 5, 0, nullptr, 0}};

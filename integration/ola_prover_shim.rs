@@ -18,17 +18,17 @@ use plonky2::util::serialization::Buffer;
 use crate::stark::ola_stark::{OlaStark, NUM_TABLES};
 use crate::stark::proof::AllProof;
 
-type F = GoldilocksField;
-type C = PoseidonGoldilocksConfig;
-const D: usize = 2;
+pub(crate) type F = GoldilocksField;
+pub(crate) type C = PoseidonGoldilocksConfig;
+pub(crate) const D: usize = 2;
 
 /// One context per process and GPU: replaces `init_gpu()` / `free_gpu()` (plonky2/field/src/cfft/ntt/mod.rs:55-101).
-struct Ctx(*mut ola_ctx);
+pub(crate) struct Ctx(pub(crate) *mut ola_ctx);
 unsafe impl Send for Ctx {}
 unsafe impl Sync for Ctx {}
 static CTX: OnceCell<std::sync::Mutex<Ctx>> = OnceCell::new();
 
-fn ctx() -> Result<&'static std::sync::Mutex<Ctx>> {
+pub(crate) fn ctx() -> Result<&'static std::sync::Mutex<Ctx>> {
     CTX.get_or_try_init(|| {
         let mut p: *mut ola_ctx = ptr::null_mut();
         let device = std::env::var("OLA_GPU_DEVICE").ok().and_then(|s| s.parse().ok()).unwrap_or(0);
@@ -38,7 +38,7 @@ fn ctx() -> Result<&'static std::sync::Mutex<Ctx>> {
     })
 }
 
-fn last_error(c: *mut ola_ctx) -> String {
+pub(crate) fn last_error(c: *mut ola_ctx) -> String {
     unsafe { std::ffi::CStr::from_ptr(ola_gpu_last_error(c)).to_string_lossy().into_owned() }
 }
 

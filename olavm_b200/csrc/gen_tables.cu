@@ -165,6 +165,7 @@ __global__ void pc_place_kernel(const uint64_t* __restrict__ rows, size_t m, con
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     const uint64_t* r = rows + i * 6;
+    if (at[i] + starts[i] == 0) return;  // words in front of the first line start (a program that does not begin at pc = 0): no line to put them in
     const size_t line = (size_t)at[i] + starts[i] - 1;
     const uint64_t pc = r[4];
     const int j = (int)(pc % 8);

@@ -170,3 +170,43 @@ def test_trace_from_records_is_the_trace_from_json(run):
     assert [a.table_log_rows(i) for i in range(12)] == [b.table_log_rows(i) for i in range(12)]
     empty = trace_json.Trace.from_records()
     assert [empty.table_log_rows(i) for i in range(12)] == [0, 1, 18, 1, 16, 1, 1, 1, 1, 1, 1, 1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4])
+def test_prove_trace_coset_sharded_equals_the_single_gpu_proof(ctx, run, world):
+    """ola_prove_trace under ola_set_comm (ranks as host threads on one GPU, olavm_b200.dist.LocalComm): every rank generates the
+    twelve tables itself, runs its own Bitwise transcript thread, the proof is coset-sharded -- and every rank returns the
+    single-GPU bytes."""
+    import threading
+
+    import olavm_b200
+    from olavm_b200 import dist as odist
+    from olavm_b200 import trace_json
+
+    rec, text = run
+    trace = trace_json.Trace(text)
+    single = trace_json.prove_trace(ctx, trace)
+    comm = odist.LocalComm(world)
+    out, err = [None] * world, [None] * world
+
+    def rank_main(rank):
+        try:
+            c = olavm_b200.Context(0)
+            comm.attach(c, rank)
+            out[rank] = trace_json.prove_trace(c, trace)
+            c.close()
+        except BaseException as e:  # noqa: B902
+            err[rank] = e
+            comm.barrier.abort()
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for e in err:
+        if e is not None:
+            raise e
+    assert all(p == single for p in out)
+    assert olavm_b200.verify_proof(list(range(12)), single)[0]

@@ -127,11 +127,12 @@ private:
         if (p_ >= end_) fail("unterminated string");
         ++p_;
     }
-    void skip_value() {
+    void skip_value(int depth = 0) {
         const char c = peek();
         if (c == '"') {
             skip_string();
         } else if (c == '{' || c == '[') {
+            if (depth >= 64) fail("nesting deeper than 64 levels");  // no field of a Trace nests deeper than 4; bounds the recursion
             const char close = c == '{' ? '}' : ']';
             ++p_;
             if (peek() == close) { ++p_; return; }
@@ -140,7 +141,7 @@ private:
                     skip_string();
                     expect(':');
                 }
-                skip_value();
+                skip_value(depth + 1);
                 if (!more(close)) break;
             }
         } else {

@@ -73,6 +73,7 @@ def test_parser_limits():
     ('{"exec":[{"regs":[1,2,3,4,5,6,7,8,9,10,11]}]}', "unexpected length"), ('{"exec":[{"clk":1}', "unexpected end"),
     ('{"exec":[]} x', "trailing"), ('{"addr_program_hash":{"12":[1]}}', "64 hex"), ('{"start_end_roots":[[1,2,3,4]]}', "pair"),
     ('{"tape":[{"is_init":maybe}]}', "unsigned integer or a bool"), ('{"exec":{"clk":1}}', "expected '['"),
+    ('{"unknown":' + "[" * 100000 + "]" * 100000 + "}", "nesting deeper"),
 ])
 def test_parser_rejects_what_serde_would_reject(text, why):
     from olavm_b200 import trace_json

@@ -929,8 +929,6 @@ struct Upload {  // a record array in device memory for the duration of one gene
         if (r.u64s(kind)) to_device(ctx, d.p, r.rows(kind), r.u64s(kind));
     }
 };
-// generate_traces (circuits/src/generation/mod.rs:79-213): twelve column-major tables in device memory, tables[t] of
-// ola_table_columns(t) << log_ns[t] u64 (owned by the caller: ola_dev_free), and the two compress challenges
 // The Bitwise table's compress challenge computed on a second host thread (host-only work: lookup.cu bitwise_beta)
 struct BitwiseLate {
     std::vector<uint64_t> limbs;
@@ -941,6 +939,10 @@ struct BitwiseLate {
         if (worker.joinable()) worker.join();
     }
 };
+// generate_traces (circuits/src/generation/mod.rs:79-213): twelve column-major tables in device memory, tables[t] of
+// ola_table_columns(t) << log_ns[t] u64 (owned by the caller: ola_dev_free), and the two compress challenges.  With `defer` the
+// Bitwise table is left at bitwise_trace_begin (its challenge is being computed by defer->worker; cc[2] stays 0) and the caller
+// completes it with bitwise_trace_finish after joining the worker.
 void generate_all(ola_ctx* ctx, const ola::tracejson::Records& r, uint64_t** tables, uint32_t* log_ns, uint64_t* cc, BitwiseLate* defer = nullptr) {
     namespace L = ola::lookup;
     using namespace ola::tracejson;

@@ -211,3 +211,54 @@ def test_prove_trace_coset_sharded_equals_the_single_gpu_proof(ctx, run, world):
             raise e
     assert all(p == single for p in out)
     assert olavm_b200.verify_proof(list(range(12)), single)[0]
+
+
+def test_parser_on_random_documents():
+    """Property test (seeded): random records of every kind -> serde-shaped text with shuffled keys, random whitespace and extra
+    unknown fields -> the parser returns the records."""
+    import random
+
+    from olavm_b200 import trace_json
+    from workload import trace_json as wj
+
+    rnd = random.Random(1234)
+    rng = np.random.default_rng(1234)
+    for trial in range(25):
+        k = lambda: rnd.randrange(0, 5)
+        big = lambda shape: rng.integers(0, 1 << 63, size=shape, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=shape, dtype=np.uint64)
+        n_bw, n_rc, n_ps, n_st = k(), k(), k(), k()
+        rec = dict(steps=big((k(), 66)), memory=big((k(), 15)), rc_vals=big(n_rc), rc_kinds=rng.integers(0, 4, size=n_rc).astype(np.uint64),
+                   bw_tags=big(n_bw), bw_op0=big(n_bw), bw_op1=big(n_bw), bw_res=big(n_bw), cmp=big((k(), 6)), psdn_inputs=big((n_ps, 12)),
+                   psdn_filters=rng.integers(0, 2, size=(n_ps, 4)).astype(np.uint64), pchunk=big((k(), 32)), storage=big((n_st, 38)),
+                   n_storage_access=rnd.randrange(0, n_st + 1), tape=big((k(), 5)), sccall=big((k(), 24)), prog_rows=np.zeros((0, 6), dtype=np.uint64),
+                   roots=big(8))
+        rec["steps"][:, 11] &= np.uint64(0xFFFFFFFF)          # clk is a u32 in the Rust struct
+        rec["pchunk"][:, 1] &= np.uint64(0xFFFFFFFF)
+        rec["tape"][:, 0] &= np.uint64(1)                     # is_init is a bool
+        progs = [(big(4), big(rnd.randrange(0, 20))) for _ in range(rnd.randrange(0, 3))]
+        rows = [list(a) + [pc, w] for a, ws in progs for pc, w in enumerate(ws)]
+        rec["prog_rows"] = np.array(rows, dtype=np.uint64).reshape(-1, 6)
+        doc = json.loads(wj.records_to_json(rec))
+
+        def shuffle(x):
+            if isinstance(x, dict):
+                items = [(key, shuffle(v)) for key, v in x.items()]
+                if "addr_program_hash" not in x and not any(len(key) == 64 for key in x):   # the programs keep their file order
+                    rnd.shuffle(items)
+                out = dict(items)
+                if rnd.random() < 0.3:
+                    out["unknown_%d" % rnd.randrange(100)] = rnd.choice([None, 1.5, 'x"y \\ ]}', [1, [2, {"z": []}]], {}])
+                return out
+            if isinstance(x, list):
+                return [shuffle(v) for v in x]
+            return x
+
+        top = shuffle({key: v for key, v in doc.items() if key != "addr_program_hash"})
+        top["addr_program_hash"] = doc["addr_program_hash"]
+        text = json.dumps(top, indent=rnd.choice([None, 0, 3]), separators=rnd.choice([(",", ":"), (", ", ": "), (" ,\n", " :\t")]))
+        t = trace_json.Trace(text)
+        for key, kind in _KEYS.items():
+            got = t.records(kind)
+            assert got.shape == rec[key].shape and (got == rec[key]).all(), (trial, key)
+        assert t.records("storage_access_count") == rec["n_storage_access"] and (t.records("roots").reshape(8) == rec["roots"]).all()
+        t.close()
